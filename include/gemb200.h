@@ -1,0 +1,230 @@
+/*
+ * gemb200.h — C-ABI of the B200-native vectorised GEM physical-system step.
+ *
+ * One handle = N independent motor environments of ONE (motor, converter, load, solver) combination living on
+ * one CUDA device.  The library owns only the persistent per-env state (ODE state, converter switching state,
+ * reference-generator state); the caller owns every I/O buffer.  All device-pointer entry points are
+ * stream-ordered and asynchronous (no host synchronisation inside); the *_host entry points take plain host
+ * pointers, do the H2D/D2H copies themselves and return after the results are in the host buffers.
+ * Every function returns 0 on success or a negative GEMB200_E_* code and never throws; the message for the last
+ * failure on the calling thread is available from gemb200_last_error().  A handle is not thread-safe; different
+ * handles may be used from different threads.
+ *
+ * The reference (upb-lea/gym-electric-motor, pure Python) has no FFI: each entry point below replaces a Python
+ * method of its plugin API and cites it (paths relative to the reference's src/gym_electric_motor/).
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ */
+#ifndef GEMB200_H_
+#define GEMB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEMB200_ABI_VERSION 1
+
+/* limits of the POD config */
+#define GEMB200_MAX_STATE 24   /* longest state vector in scope: EESM 16 */
+#define GEMB200_MAX_ODE 8      /* SCIM: omega + 4 + eps = 6 */
+#define GEMB200_MAX_ACT 4      /* EESM: 3 (B6) + 1 (4QC) */
+#define GEMB200_MAX_REF 4
+#define GEMB200_MAX_CONSTRAINTS 4
+#define GEMB200_MAX_MOTOR_PARAM 16
+
+/* error codes */
+#define GEMB200_OK 0
+#define GEMB200_E_INVALID -1    /* bad argument / unsupported combination (reference: assert / Exception) */
+#define GEMB200_E_CUDA -2       /* CUDA runtime error, see gemb200_last_error() */
+#define GEMB200_E_NOMEM -3
+#define GEMB200_E_ABI -4        /* struct_size / abi_version mismatch */
+
+/* motor kinds — reference physical_systems/electric_motors/<file>.py */
+enum gemb200_motor_kind {
+  GEMB200_MOTOR_PERMEX_DC = 0, /* dc_permanently_excited_motor.py:67-92   params: r_a l_a psi_e j_rotor */
+  GEMB200_MOTOR_SERIES_DC = 1, /* dc_series_motor.py                      params: r_a r_e l_a l_e l_e_prime j_rotor */
+  GEMB200_MOTOR_SHUNT_DC = 2,  /* dc_shunt_motor.py                       params: r_a r_e l_a l_e l_e_prime j_rotor */
+  GEMB200_MOTOR_EXTEX_DC = 3,  /* dc_externally_excited_motor.py, dc_motor.py */
+  GEMB200_MOTOR_PMSM = 4,      /* permanent_magnet_synchronous_motor.py:107-139 params: p l_d l_q r_s psi_p j_rotor */
+  GEMB200_MOTOR_SYNRM = 5,     /* synchronous_reluctance_motor.py:117-139      params: p l_d l_q r_s j_rotor */
+  GEMB200_MOTOR_EESM = 6,      /* externally_excited_synchronous_motor.py:125-203 params: p l_d l_q l_m l_e r_s r_e k j_rotor */
+  GEMB200_MOTOR_SCIM = 7       /* induction_motor.py:187-310, squirrel_cage_induction_motor.py:121-129
+                                  params: p l_m l_sigs l_sigr r_s r_r j_rotor */
+};
+
+/* motor_param[] slots (physical parameters exactly as in the reference's motor_parameter dicts) */
+enum gemb200_motor_param {
+  GEMB200_MP_P = 0, GEMB200_MP_R_S = 1, GEMB200_MP_L_D = 2, GEMB200_MP_L_Q = 3, GEMB200_MP_PSI_P = 4,
+  GEMB200_MP_J_ROTOR = 5,
+  GEMB200_MP_R_A = 6, GEMB200_MP_L_A = 7, GEMB200_MP_PSI_E = 8, GEMB200_MP_R_E = 9, GEMB200_MP_L_E = 10,
+  GEMB200_MP_L_E_PRIME = 11,
+  GEMB200_MP_L_M = 12, GEMB200_MP_K = 13, GEMB200_MP_L_SIGS = 14, GEMB200_MP_L_SIGR = 15
+  /* SCIM's r_r is passed in GEMB200_MP_R_E */
+};
+
+/* converter slots — reference physical_systems/converters.py.  A converter is 1 or 2 slots:
+ * DC motors: slot0 in {1QC,2QC,4QC}; ExtEx: slot0 (armature) + slot1 (excitation);
+ * PMSM/SynRM/SCIM: slot0 = B6; EESM: slot0 = B6, slot1 in {1QC,2QC,4QC}  (Cont/FiniteMultiConverter :498-740). */
+enum gemb200_converter_kind {
+  GEMB200_CONV_NONE = 0,
+  GEMB200_CONV_1QC = 1, /* :218-245 finite, :371-401 continuous */
+  GEMB200_CONV_2QC = 2, /* :248-310 finite, :404-435 continuous */
+  GEMB200_CONV_4QC = 3, /* :313-368 finite, :438-495 continuous */
+  GEMB200_CONV_B6 = 4   /* :743-839 finite, :842-911 continuous */
+};
+
+enum gemb200_load_kind {
+  GEMB200_LOAD_CONST_SPEED = 0, /* mechanical_loads/constant_speed_load.py:40-42 */
+  GEMB200_LOAD_POLY_STATIC = 1  /* mechanical_loads/polynomial_static_load.py:87-99 */
+};
+enum gemb200_load_param { GEMB200_LP_A = 0, GEMB200_LP_B = 1, GEMB200_LP_C = 2, GEMB200_LP_J_LOAD = 3, GEMB200_LP_TAU_DECAY = 4 };
+
+enum gemb200_solver_kind {
+  GEMB200_SOLVER_EULER = 0, /* physical_systems/solvers.py:79-136 (incl. the n-step time quirk :113-119) */
+  GEMB200_SOLVER_RK4 = 1    /* classic RK4, solver_nsteps equal sub-steps per switching segment (reference has none;
+                               within 1e-6 of its default dopri5) */
+};
+
+enum gemb200_constraint_kind {
+  GEMB200_CONSTRAINT_LIMIT = 0,  /* constraints.py:55-58  any(|s_i| > 1) over the masked states */
+  GEMB200_CONSTRAINT_SQUARED = 1 /* constraints.py:96-98  sum(s_i^2) > 1 over the masked states */
+};
+
+enum gemb200_ref_kind {
+  GEMB200_REF_CONST = 0,   /* reference_generators/const_reference_generator.py */
+  GEMB200_REF_WIENER = 1,  /* reference_generators/wiener_process_reference_generator.py:7-49 on
+                              subepisoded_reference_generator.py:9-119 */
+  GEMB200_REF_EXTERNAL = 2 /* value injected with gemb200_set_reference() before each step (oracle injection hook,
+                              user-side generators) */
+};
+
+enum gemb200_dtype { GEMB200_F32 = 0 /* fp32 state, fp64 rotor angle */, GEMB200_F64 = 1 };
+enum gemb200_layout {
+  GEMB200_LAYOUT_AOS = 0, /* obs[N][n_state], action[N][n_act], ref[N][n_ref]  (row per env, the gym layout) */
+  GEMB200_LAYOUT_SOA = 1  /* obs[n_state][N], action[n_act][N], ref[n_ref][N]  (field-major, fully coalesced) */
+};
+enum gemb200_autoreset {
+  GEMB200_AUTORESET_NONE = 0,     /* caller resets terminated envs with gemb200_reset(mask) (reference core.py:341) */
+  GEMB200_AUTORESET_SAME_STEP = 1 /* a terminated env is reset inside the same launch; obs/ref returned are the
+                                     first observation of the new episode, reward/terminated those of the old one */
+};
+
+typedef struct gemb200_config {
+  int32_t struct_size; /* = sizeof(gemb200_config), set by gemb200_config_init */
+  int32_t abi_version; /* = GEMB200_ABI_VERSION */
+  int32_t n_envs;
+  int32_t device;      /* CUDA device ordinal */
+  int32_t dtype;       /* gemb200_dtype */
+  int32_t layout;      /* gemb200_layout */
+  int32_t autoreset;   /* gemb200_autoreset */
+  int32_t finite;      /* 0: continuous converters, float actions; 1: finite converters, int32 actions [N][n_slots] */
+
+  /* SCML components (reference physical_systems.py:54 SCMLSystem.__init__) */
+  int32_t motor_kind;
+  int32_t converter_kind[2];
+  int32_t load_kind;
+  int32_t solver_kind;
+  int32_t solver_nsteps;
+  double tau;                /* physical_systems.py:54; converter.tau :103 */
+  double interlocking_time;  /* converters.py:37-44 */
+  double u_sup;              /* IdealVoltageSupply.u_nominal voltage_supplies.py:60-72 */
+  double motor_param[GEMB200_MAX_MOTOR_PARAM];
+  double load_param[8];      /* a b c j_load tau_decay ; for CONST_SPEED nothing is read (omega lives in init_ode) */
+  double limits[GEMB200_MAX_STATE];   /* SCMLSystem.limits physical_systems.py:105-112 (host-derived) */
+  double init_ode[GEMB200_MAX_ODE];   /* constant initial ODE state [omega, motor states...] used by reset */
+
+  /* constraint monitor (core.py:756-844) */
+  int32_t n_constraints;
+  int32_t constraint_kind[GEMB200_MAX_CONSTRAINTS];
+  uint32_t constraint_mask[GEMB200_MAX_CONSTRAINTS]; /* bit i = state i observed */
+
+  /* WeightedSumOfErrors (reward_functions/weighted_sum_of_errors.py:88-129), already resolved per state */
+  double reward_weight[GEMB200_MAX_STATE];
+  double reward_power[GEMB200_MAX_STATE];
+  double state_length[GEMB200_MAX_STATE]; /* state_space.high - low */
+  double reward_bias;
+  double violation_reward;
+
+  /* reference generators: one slot per referenced state (MultipleReferenceGenerator = several slots) */
+  int32_t n_ref;
+  int32_t ref_kind[GEMB200_MAX_REF];
+  int32_t ref_state[GEMB200_MAX_REF];       /* index into the state vector */
+  double ref_value[GEMB200_MAX_REF];        /* CONST: the value; others: value after reset when no random init */
+  double ref_margin_lo[GEMB200_MAX_REF], ref_margin_hi[GEMB200_MAX_REF];   /* clip range of the walk */
+  double ref_init_lo[GEMB200_MAX_REF], ref_init_hi[GEMB200_MAX_REF];       /* U() range of the value at reset */
+  double ref_sigma_lo[GEMB200_MAX_REF], ref_sigma_hi[GEMB200_MAX_REF];     /* log-uniform sigma range */
+  int32_t ref_len_lo[GEMB200_MAX_REF], ref_len_hi[GEMB200_MAX_REF];        /* sub-episode length U(lo,hi) */
+
+  uint64_t seed;            /* Philox key; streams are keyed by (seed, global env index) */
+  int64_t env_index_offset; /* global index of env 0 of this handle (rank*N_local when sharded) */
+} gemb200_config;
+
+typedef struct gemb200_handle gemb200_handle;
+
+/* library / error reporting */
+int gemb200_version(void);
+const char* gemb200_last_error(void);
+
+/* Fill *cfg with zeros + struct_size/abi_version + neutral defaults (nsteps=1, tau_decay=1e-3, …). */
+int gemb200_config_init(gemb200_config* cfg);
+
+/* Derived sizes of a configuration (no GPU needed): n_state, n_ode, n_act (floats or ints per env), n_ref.
+ * Replaces the index bookkeeping of SCMLSystem._set_indices (physical_systems.py:141-162, :462-485). */
+int gemb200_query_dims(const gemb200_config* cfg, int32_t* n_state, int32_t* n_ode, int32_t* n_act, int32_t* n_ref);
+
+/* SCMLSystem.__init__ (physical_systems.py:54-103) + ElectricMotorEnvironment.__init__ wiring (core.py:197-289):
+ * validates the combination, derives the model constants from the physical parameters (the *_update_model
+ * methods), allocates the per-env state on cfg->device and resets every env. */
+int gemb200_create(const gemb200_config* cfg, gemb200_handle** out);
+int gemb200_destroy(gemb200_handle* h);
+
+/* ElectricMotorEnvironment.reset (core.py:300-319) -> SCMLSystem.reset (physical_systems.py:256-287, :527-561,
+ * :659-693, :816-847) + ReferenceGenerator.reset.  reset_mask: device uint8[N] (non-zero = reset) or NULL for all.
+ * obs_out/ref_out (device, layout per cfg, element type per cfg->dtype) may be NULL. */
+int gemb200_reset(gemb200_handle* h, const uint8_t* reset_mask, void* obs_out, void* ref_out, void* stream);
+
+/* ElectricMotorEnvironment.step (core.py:328-371): SCMLSystem.simulate (physical_systems.py:171-203, :487-525,
+ * :619-657, :771-814) + get_reference + check_constraints + reward + get_reference_observation, one launch for all
+ * N envs.  action: float/double [N][n_act] (continuous) or int32 [N][n_slots] (finite).  Outputs: obs [N][n_state],
+ * ref_next [N][n_ref], reward [N], terminated uint8 [N]; any output pointer may be NULL. */
+int gemb200_step(gemb200_handle* h, const void* action, void* obs_out, void* ref_out, void* reward_out,
+                 uint8_t* terminated_out, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): H2D of the actions, the launch, D2H of the results and a stream
+ * synchronise all happen inside.  This is the drop-in for a host-side caller of env.step. */
+int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void* ref_out, void* reward_out,
+                      uint8_t* terminated_out);
+int gemb200_reset_host(gemb200_handle* h, const uint8_t* reset_mask, void* obs_out, void* ref_out);
+
+/* K consecutive steps in one call with actions[K][N][n_act] resident on the device (open-loop rollout; the outputs
+ * are those of the last step).  Used for benchmarking the kernel without per-step host work. */
+int gemb200_rollout(gemb200_handle* h, const void* actions, int32_t n_steps, void* obs_out, void* ref_out,
+                    void* reward_out, uint8_t* terminated_out, void* stream);
+
+/* OdeSolver.y / set_initial_value (physical_systems/solvers.py:4-76): ODE state as double [N][n_ode]
+ * (AoS, device), angle unwrapped to (-pi, pi].  Used for checkpointing and oracle injection. */
+int gemb200_get_ode_state(gemb200_handle* h, double* ode_out, void* stream);
+int gemb200_set_ode_state(gemb200_handle* h, const double* ode_in, void* stream);
+
+/* Reference-generator value that the NEXT step's reward is computed against (ReferenceGenerator.get_reference,
+ * core.py:439-452): double [N][n_ref] (device). */
+int gemb200_get_reference(gemb200_handle* h, double* ref_out, void* stream);
+int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream);
+
+/* Opaque checkpoint of everything a handle owns (ODE state, switching state, reference state, step counter):
+ * size query, export to / import from a HOST blob. */
+int64_t gemb200_checkpoint_size(gemb200_handle* h);
+int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob);
+int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob);
+
+/* Introspection used by bench.py: number of kernel launches issued through this handle so far, and the
+ * CUDA-event time in ms of the step launches since the last call (see DESIGN.md "Measurement"). */
+int64_t gemb200_launch_count(gemb200_handle* h);
+int gemb200_kernel_time_begin(gemb200_handle* h, void* stream);
+int gemb200_kernel_time_end(gemb200_handle* h, void* stream, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMB200_H_ */

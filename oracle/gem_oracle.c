@@ -1,0 +1,937 @@
+/*
+ * gem_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, float64, one-env-at-a-time restatement of the reference's physical-system step
+ * (upb-lea/gym-electric-motor @ 5555196, src/gym_electric_motor/...).  It exists to CHECK the CUDA path and to be
+ * timed as the CPU baseline; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it.  The product (gym_electric_motor_b200/) never links, imports or calls anything in oracle/.
+ *
+ * Pinning: tests/test_oracle_golden.py replays every trajectory in tests/golden/*.npz (recorded from the
+ * UNMODIFIED reference by tests/golden/make_golden.py, including a regeneration of the reference's own
+ * tests/integration_tests/ref_data.npz) through this file and requires agreement to <=1e-9 (Euler / RK4,
+ * algorithm-identical) and <=2e-7 (dopri5, adaptive).  Reference converter truth tables
+ * (tests/test_physical_systems/test_converters.py) are re-checked in the same test module.
+ *
+ * Every function cites the reference lines it restates.  The structure deliberately follows the reference
+ * (dense model-constant matrices, per-segment convert/integrate loop) rather than the optimised CUDA kernels.
+ *
+ * The POD configuration struct is the public one from include/gemb200.h (header only, no product code).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/gemb200.h"
+
+#define ORACLE_SOLVER_DOPRI5 100 /* oracle-only: restatement of scipy.integrate.ode('dopri5') defaults (solvers.py:139-184) */
+
+#define MAXM 6  /* motor ODE states incl. eps */
+#define MAXF 12 /* feature-vector length of the model-constant product */
+
+typedef struct {
+  /* finite 2QC (converters.py:248-310) */
+  int pattern[2];
+  int pattern_len;
+  int switching_state; /* persists across steps AND resets (converters.py:193-197,45-54) */
+  double action_start_time;
+  int cur_action_i;
+  /* continuous 2QC / 1QC (converters.py:130-184, 371-435) */
+  double cur_action;
+} sub2qc_t;
+
+typedef struct {
+  double ode[GEMB200_MAX_ODE]; /* [mechanical | motor] physical_systems.py:270 */
+  double t;
+  long k;
+  sub2qc_t sub[5]; /* slot0: up to 3 legs (B6) or 2 (4QC) ; slot1: up to 2 */
+  int cur_action1qc[2];
+  /* reference generator slots (subepisoded_reference_generator.py) */
+  double ref_value[GEMB200_MAX_REF];
+  double ref_sigma[GEMB200_MAX_REF];
+  int ref_left[GEMB200_MAX_REF];
+  uint32_t episode; /* reset counter: part of the RNG counter */
+  uint32_t step;    /* steps since reset */
+} env_t;
+
+typedef struct gem_oracle {
+  gemb200_config cfg;
+  int n_state, n_ode, n_act, n_ref, n_motor, n_cur, n_volt;
+  int n_sub[2];     /* 2QC sub-converters per slot */
+  int slot_off[2];  /* first sub index per slot */
+  double mc[MAXM][MAXF]; /* _model_constants */
+  int mc_rows, mc_cols;
+  double j_total, omega_lim, omega_lin; /* polynomial_static_load.py:72-85 */
+  /* derived EESM constants (externally_excited_synchronous_motor.py:129-136) */
+  double l_M, i_k_rs;
+  double tq0; /* SCIM torque factor */
+  env_t* env;
+} gem_oracle;
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., SC'11) — the published counter-based generator; the CUDA path uses the same    */
+/* construction with the same (key, counter) convention so that the device reference generator can be checked   */
+/* value-for-value.  The reference's numpy PCG64 streams cannot be reproduced on a device.        */
+/* ------------------------------------------------------------------------------------------------------------ */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); } /* (0,1) */
+
+/* stream ids for the counter word 3 */
+enum { STREAM_REF_WALK = 1, STREAM_REF_SUBEP = 2, STREAM_REF_INIT = 3 };
+
+static void rng4(const gem_oracle* o, int64_t env, uint32_t episode, uint32_t step, uint32_t stream, uint32_t out[4]) {
+  uint64_t g = (uint64_t)(env + o->cfg.env_index_offset);
+  out[0] = step; out[1] = episode; out[2] = (uint32_t)g; out[3] = ((uint32_t)(g >> 32) << 8) | stream;
+  philox4x32_10(out, (uint32_t)o->cfg.seed, (uint32_t)(o->cfg.seed >> 32));
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* dimensions — SCMLSystem._set_indices physical_systems.py:141-162, :462-485, :594-617, :737-763               */
+/* ------------------------------------------------------------------------------------------------------------ */
+static int slot_nsub(int kind) {
+  switch (kind) {
+    case GEMB200_CONV_1QC: return 1;
+    case GEMB200_CONV_2QC: return 1;
+    case GEMB200_CONV_4QC: return 2;
+    case GEMB200_CONV_B6: return 3;
+    default: return 0;
+  }
+}
+static int slot_nvolt(int kind) { return kind == GEMB200_CONV_B6 ? 3 : (kind == GEMB200_CONV_NONE ? 0 : 1); }
+
+static int dims(gem_oracle* o) {
+  const gemb200_config* c = &o->cfg;
+  switch (c->motor_kind) {
+    case GEMB200_MOTOR_PERMEX_DC:
+    case GEMB200_MOTOR_SERIES_DC: o->n_motor = 1; o->n_cur = 1; o->n_volt = 1; o->n_state = 5; break;
+    case GEMB200_MOTOR_SHUNT_DC: o->n_motor = 2; o->n_cur = 2; o->n_volt = 1; o->n_state = 7; break; /* 6 + i_sum: every ShuntDc env
+      appends CurrentSumProcessor(('i_a','i_e')) (envs/gym_dcm/shunt_dc_motor_env/*.py), restated natively */
+    case GEMB200_MOTOR_EXTEX_DC: o->n_motor = 2; o->n_cur = 2; o->n_volt = 2; o->n_state = 7; break;
+    case GEMB200_MOTOR_PMSM:
+    case GEMB200_MOTOR_SYNRM: o->n_motor = 3; o->n_cur = 2; o->n_volt = 2; o->n_state = 14; break;
+    case GEMB200_MOTOR_EESM: o->n_motor = 4; o->n_cur = 3; o->n_volt = 3; o->n_state = 16; break;
+    case GEMB200_MOTOR_SCIM: o->n_motor = 5; o->n_cur = 2; o->n_volt = 2; o->n_state = 14; break;
+    default: return -1;
+  }
+  o->n_ode = 1 + o->n_motor;
+  o->n_sub[0] = slot_nsub(c->converter_kind[0]);
+  o->n_sub[1] = slot_nsub(c->converter_kind[1]);
+  o->slot_off[0] = 0;
+  o->slot_off[1] = o->n_sub[0];
+  if (c->finite) o->n_act = (c->converter_kind[0] != 0) + (c->converter_kind[1] != 0);
+  else o->n_act = slot_nvolt(c->converter_kind[0]) + slot_nvolt(c->converter_kind[1]);
+  o->n_ref = c->n_ref;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* model constants — the motors' _update_model methods                                                           */
+/* ------------------------------------------------------------------------------------------------------------ */
+static void update_model(gem_oracle* o) {
+  const double* mp = o->cfg.motor_param;
+  memset(o->mc, 0, sizeof(o->mc));
+  double p = mp[GEMB200_MP_P], r_s = mp[GEMB200_MP_R_S], l_d = mp[GEMB200_MP_L_D], l_q = mp[GEMB200_MP_L_Q];
+  switch (o->cfg.motor_kind) {
+    case GEMB200_MOTOR_PERMEX_DC: { /* dc_permanently_excited_motor.py:71-75  features [omega, i, u] */
+      double l_a = mp[GEMB200_MP_L_A];
+      o->mc_rows = 1; o->mc_cols = 3;
+      o->mc[0][0] = -mp[GEMB200_MP_PSI_E] / l_a; o->mc[0][1] = -mp[GEMB200_MP_R_A] / l_a; o->mc[0][2] = 1.0 / l_a;
+    } break;
+    case GEMB200_MOTOR_SERIES_DC: { /* dc_series_motor.py:66-70  features [i, omega*i, u] */
+      double l = mp[GEMB200_MP_L_A] + mp[GEMB200_MP_L_E];
+      o->mc_rows = 1; o->mc_cols = 3;
+      o->mc[0][0] = (-mp[GEMB200_MP_R_A] - mp[GEMB200_MP_R_E]) / l; o->mc[0][1] = -mp[GEMB200_MP_L_E_PRIME] / l; o->mc[0][2] = 1.0 / l;
+    } break;
+    case GEMB200_MOTOR_SHUNT_DC:
+    case GEMB200_MOTOR_EXTEX_DC: { /* dc_motor.py:95-104  features [i_a, i_e, omega*i_e, u_a, u_e] */
+      double l_a = mp[GEMB200_MP_L_A], l_e = mp[GEMB200_MP_L_E];
+      o->mc_rows = 2; o->mc_cols = 5;
+      o->mc[0][0] = -mp[GEMB200_MP_R_A] / l_a; o->mc[0][2] = -mp[GEMB200_MP_L_E_PRIME] / l_a; o->mc[0][3] = 1.0 / l_a;
+      o->mc[1][1] = -mp[GEMB200_MP_R_E] / l_e; o->mc[1][4] = 1.0 / l_e;
+    } break;
+    case GEMB200_MOTOR_PMSM: { /* permanent_magnet_synchronous_motor.py:107-119
+                                  features [omega, i_d, i_q, u_d, u_q, omega*i_d, omega*i_q] */
+      double psi_p = mp[GEMB200_MP_PSI_P];
+      o->mc_rows = 3; o->mc_cols = 7;
+      o->mc[0][1] = -r_s / l_d; o->mc[0][3] = 1.0 / l_d; o->mc[0][6] = l_q * p / l_d;
+      o->mc[1][0] = -psi_p * p / l_q; o->mc[1][2] = -r_s / l_q; o->mc[1][4] = 1.0 / l_q; o->mc[1][5] = -l_d * p / l_q;
+      o->mc[2][0] = p;
+    } break;
+    case GEMB200_MOTOR_SYNRM: { /* synchronous_reluctance_motor.py:117-131 */
+      o->mc_rows = 3; o->mc_cols = 7;
+      o->mc[0][1] = -r_s / l_d; o->mc[0][3] = 1.0 / l_d; o->mc[0][6] = l_q * p / l_d;
+      o->mc[1][2] = -r_s / l_q; o->mc[1][4] = 1.0 / l_q; o->mc[1][5] = -l_d * p / l_q;
+      o->mc[2][0] = p;
+    } break;
+    case GEMB200_MOTOR_EESM: { /* externally_excited_synchronous_motor.py:125-153
+        features [omega, i_d, i_q, i_e, u_d, u_q, u_e, omega*i_d, omega*i_q, omega*i_e] */
+      double k = mp[GEMB200_MP_K], r_e = mp[GEMB200_MP_R_E], l_m = mp[GEMB200_MP_L_M], l_e = mp[GEMB200_MP_L_E];
+      double r_E = k * k * 3.0 / 2.0 * r_e;
+      double l_M = k * 3.0 / 2.0 * l_m;
+      double l_E = k * k * 3.0 / 2.0 * l_e;
+      double i_k_rs = 2.0 / 3.0 / k;
+      double sigma = 1.0 - l_M * l_M / (l_d * l_E);
+      o->l_M = l_M; o->i_k_rs = i_k_rs;
+      o->mc_rows = 4; o->mc_cols = 10;
+      double (*m)[MAXF] = o->mc;
+      m[0][1] = -r_s / sigma; m[0][3] = l_M * r_E / (sigma * l_E) * i_k_rs; m[0][4] = 1.0 / sigma;
+      m[0][6] = -l_M * k / (sigma * l_E); m[0][8] = l_q * p / sigma;
+      m[1][2] = -r_s; m[1][5] = 1.0; m[1][7] = -l_d * p; m[1][9] = -p * l_M * i_k_rs;
+      m[2][1] = l_M * r_s / (sigma * l_d); m[2][3] = -r_E / sigma * i_k_rs; m[2][4] = -l_M / (sigma * l_d);
+      m[2][6] = k / sigma; m[2][8] = -p * l_M * l_q / (sigma * l_d);
+      m[3][0] = p;
+      for (int j = 0; j < 10; ++j) { m[0][j] = m[0][j] / l_d; m[1][j] = m[1][j] / l_q; m[2][j] = m[2][j] / l_E / i_k_rs; }
+    } break;
+    case GEMB200_MOTOR_SCIM: { /* induction_motor.py:287-310
+        features [omega, i_a, i_b, psi_a, psi_b, omega*psi_a, omega*psi_b, u_sa, u_sb, u_ra, u_rb] */
+      double l_m = mp[GEMB200_MP_L_M], r_r = mp[GEMB200_MP_R_E];
+      double l_s = l_m + mp[GEMB200_MP_L_SIGS], l_r = l_m + mp[GEMB200_MP_L_SIGR];
+      double sigma = (l_s * l_r - l_m * l_m) / (l_s * l_r);
+      double tau_r = l_r / r_r;
+      double tau_sig = sigma * l_s / (r_s + r_r * (l_m * l_m) / (l_r * l_r));
+      o->mc_rows = 5; o->mc_cols = 11;
+      double (*m)[MAXF] = o->mc;
+      m[0][1] = -1 / tau_sig; m[0][3] = l_m * r_r / (sigma * l_s * l_r * l_r); m[0][6] = l_m * p / (sigma * l_r * l_s);
+      m[0][7] = 1 / (sigma * l_s); m[0][9] = -l_m / (sigma * l_r * l_s);
+      m[1][2] = -1 / tau_sig; m[1][4] = l_m * r_r / (sigma * l_s * l_r * l_r); m[1][5] = -l_m * p / (sigma * l_r * l_s);
+      m[1][8] = 1 / (sigma * l_s); m[1][10] = -l_m / (sigma * l_r * l_s);
+      m[2][1] = l_m / tau_r; m[2][3] = -1 / tau_r; m[2][6] = -p; m[2][9] = 1;
+      m[3][2] = l_m / tau_r; m[3][4] = -1 / tau_r; m[3][5] = p; m[3][10] = 1;
+      m[4][0] = p;
+      o->tq0 = 1.5 * p * l_m / (l_m + mp[GEMB200_MP_L_SIGR]);
+    } break;
+  }
+  /* MechanicalLoad.set_j_rotor mechanical_load.py:188-193 ; PolynomialStaticLoad.set_j_rotor polynomial_static_load.py:60-64 */
+  const double* lp = o->cfg.load_param;
+  o->j_total = lp[GEMB200_LP_J_LOAD] + mp[GEMB200_MP_J_ROTOR];
+  o->omega_lin = o->j_total / lp[GEMB200_LP_TAU_DECAY];
+  o->omega_lim = lp[GEMB200_LP_A] / o->j_total * lp[GEMB200_LP_TAU_DECAY];
+}
+
+/* ElectricMotor.electrical_ode: np.matmul(_model_constants, features) */
+static void electrical_ode(const gem_oracle* o, const double* ms, const double* u, double omega, double* d) {
+  double f[MAXF];
+  int n = 0;
+  switch (o->cfg.motor_kind) {
+    case GEMB200_MOTOR_PERMEX_DC: f[0] = omega; f[1] = ms[0]; f[2] = u[0]; n = 3; break; /* dc_permanently_excited_motor.py:81-84 */
+    case GEMB200_MOTOR_SERIES_DC: f[0] = ms[0]; f[1] = omega * ms[0]; f[2] = u[0]; n = 3; break; /* dc_series_motor.py:76-81 */
+    case GEMB200_MOTOR_SHUNT_DC: /* dc_shunt_motor.py:70-72: u_in -> (u, u) */
+      f[0] = ms[0]; f[1] = ms[1]; f[2] = omega * ms[1]; f[3] = u[0]; f[4] = u[0]; n = 5; break;
+    case GEMB200_MOTOR_EXTEX_DC: /* dc_motor.py:114-128 */
+      f[0] = ms[0]; f[1] = ms[1]; f[2] = omega * ms[1]; f[3] = u[0]; f[4] = u[1]; n = 5; break;
+    case GEMB200_MOTOR_PMSM:
+    case GEMB200_MOTOR_SYNRM: /* synchronous_motor.py:143-168 */
+      f[0] = omega; f[1] = ms[0]; f[2] = ms[1]; f[3] = u[0]; f[4] = u[1]; f[5] = omega * ms[0]; f[6] = omega * ms[1]; n = 7; break;
+    case GEMB200_MOTOR_EESM: /* externally_excited_synchronous_motor.py:155-185 */
+      f[0] = omega; f[1] = ms[0]; f[2] = ms[1]; f[3] = ms[2]; f[4] = u[0]; f[5] = u[1]; f[6] = u[2];
+      f[7] = omega * ms[0]; f[8] = omega * ms[1]; f[9] = omega * ms[2]; n = 10; break;
+    case GEMB200_MOTOR_SCIM: /* induction_motor.py:187-217 with rotor voltages 0 (squirrel_cage_induction_motor.py:121-129) */
+      f[0] = omega; f[1] = ms[0]; f[2] = ms[1]; f[3] = ms[2]; f[4] = ms[3]; f[5] = omega * ms[2]; f[6] = omega * ms[3];
+      f[7] = u[0]; f[8] = u[1]; f[9] = 0.0; f[10] = 0.0; n = 11; break;
+  }
+  for (int i = 0; i < o->mc_rows; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += o->mc[i][j] * f[j];
+    d[i] = s;
+  }
+}
+
+static double torque(const gem_oracle* o, const double* ms) {
+  const double* mp = o->cfg.motor_param;
+  switch (o->cfg.motor_kind) {
+    case GEMB200_MOTOR_PERMEX_DC: return mp[GEMB200_MP_PSI_E] * ms[0];            /* dc_permanently_excited_motor.py:67-69 */
+    case GEMB200_MOTOR_SERIES_DC: return mp[GEMB200_MP_L_E_PRIME] * ms[0] * ms[0]; /* dc_series_motor.py:72-74 */
+    case GEMB200_MOTOR_SHUNT_DC:
+    case GEMB200_MOTOR_EXTEX_DC: return mp[GEMB200_MP_L_E_PRIME] * ms[0] * ms[1];  /* dc_motor.py:106-108 */
+    case GEMB200_MOTOR_PMSM: /* permanent_magnet_synchronous_motor.py:134-139 */
+      return 1.5 * mp[GEMB200_MP_P] * (mp[GEMB200_MP_PSI_P] + (mp[GEMB200_MP_L_D] - mp[GEMB200_MP_L_Q]) * ms[0]) * ms[1];
+    case GEMB200_MOTOR_SYNRM: /* synchronous_reluctance_motor.py:137-139 */
+      return 1.5 * mp[GEMB200_MP_P] * ((mp[GEMB200_MP_L_D] - mp[GEMB200_MP_L_Q]) * ms[0]) * ms[1];
+    case GEMB200_MOTOR_EESM: /* externally_excited_synchronous_motor.py:200-203 */
+      return 1.5 * mp[GEMB200_MP_P] * (o->l_M * ms[2] * o->i_k_rs + (mp[GEMB200_MP_L_D] - mp[GEMB200_MP_L_Q]) * ms[0]) * ms[1];
+    case GEMB200_MOTOR_SCIM: /* induction_motor.py:236-249 */
+      return o->tq0 * (ms[2] * ms[1] - ms[3] * ms[0]);
+  }
+  return 0.0;
+}
+
+/* MechanicalLoad.mechanical_ode */
+static double mechanical_ode(const gem_oracle* o, double omega, double tq) {
+  if (o->cfg.load_kind == GEMB200_LOAD_CONST_SPEED) return 0.0; /* constant_speed_load.py:40-42 */
+  /* polynomial_static_load.py:87-99 */
+  const double* lp = o->cfg.load_param;
+  double sign = omega > 0 ? 1.0 : (omega < 0 ? -1.0 : 0.0);
+  double a = fabs(omega) > o->omega_lim ? sign * lp[GEMB200_LP_A] : o->omega_lin * omega;
+  double static_torque = sign * lp[GEMB200_LP_C] * omega * omega + lp[GEMB200_LP_B] * omega + a;
+  return (tq - static_torque) / o->j_total;
+}
+
+/* SCMLSystem._system_equation physical_systems.py:205-236 */
+static void system_equation(const gem_oracle* o, const double* y, const double* u, double* dy) {
+  double tq = torque(o, y + 1);
+  dy[0] = mechanical_ode(o, y[0], tq);
+  electrical_ode(o, y + 1, u, y[0], dy + 1);
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* solvers                                                                                                       */
+/* ------------------------------------------------------------------------------------------------------------ */
+static void integrate_euler(const gem_oracle* o, double* y, double dt, int nsteps, const double* u) {
+  int n = o->n_ode;
+  double dy[GEMB200_MAX_ODE];
+  if (nsteps <= 1) { /* solvers.py:124-136 */
+    system_equation(o, y, u, dy);
+    for (int i = 0; i < n; ++i) y[i] = y[i] + dy[i] * dt;
+    return;
+  }
+  /* solvers.py:103-122 (the time argument quirk is irrelevant: the RHS is autonomous) */
+  double tau = dt / nsteps;
+  for (int s = 0; s < nsteps; ++s) {
+    system_equation(o, y, u, dy);
+    for (int i = 0; i < n; ++i) y[i] = y[i] + dy[i] * tau;
+  }
+}
+
+static void integrate_rk4(const gem_oracle* o, double* y, double dt, int nsteps, const double* u) {
+  /* classic RK4; mirrors the test-side RK4Solver plugin in tests/golden/make_golden.py that produced the goldens */
+  int n = o->n_ode;
+  if (nsteps < 1) nsteps = 1;
+  double h = dt / nsteps;
+  double k1[GEMB200_MAX_ODE], k2[GEMB200_MAX_ODE], k3[GEMB200_MAX_ODE], k4[GEMB200_MAX_ODE], yt[GEMB200_MAX_ODE];
+  for (int s = 0; s < nsteps; ++s) {
+    system_equation(o, y, u, k1);
+    for (int i = 0; i < n; ++i) yt[i] = y[i] + 0.5 * h * k1[i];
+    system_equation(o, yt, u, k2);
+    for (int i = 0; i < n; ++i) yt[i] = y[i] + 0.5 * h * k2[i];
+    system_equation(o, yt, u, k3);
+    for (int i = 0; i < n; ++i) yt[i] = y[i] + h * k3[i];
+    system_equation(o, yt, u, k4);
+    for (int i = 0; i < n; ++i) y[i] = y[i] + h / 6.0 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+  }
+}
+
+/* scipy.integrate.ode('dopri5') with the defaults the reference uses (solvers.py:155-184): rtol=1e-6, atol=1e-12,
+ * nsteps=500, first_step=0 (-> Hairer's HINIT), safety=0.9, ifactor=10, dfactor=0.2, beta=0 (-> 0.04 inside the
+ * integrator).  Restates the published Dormand-Prince 5(4) core (Hairer, Norsett, Wanner, "Solving ODEs I", DOPRI5);
+ * scipy is a dependency of the reference, not part of /root/reference (requirements.txt:3, unpinned; 1.18.1 here). */
+static double integrate_dopri5(const gem_oracle* o, double* y, double t_start, double t_end, const double* u) {
+  const double dt = t_end - t_start;
+  const double uround = 2.3e-16; /* dopri5.f default UROUND */
+  const int n = o->n_ode;
+  const double rtol = 1e-6, atol = 1e-12, safe = 0.9, fac1 = 0.2, fac2 = 10.0, beta = 0.04;
+  const double expo1 = 0.2 - beta * 0.75, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
+  static const double a21 = 0.2, a31 = 3.0 / 40.0, a32 = 9.0 / 40.0, a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0,
+                      a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0, a54 = -212.0 / 729.0,
+                      a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0, a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0,
+                      a71 = 35.0 / 384.0, a73 = 500.0 / 1113.0, a74 = 125.0 / 192.0, a75 = -2187.0 / 6784.0, a76 = 11.0 / 84.0,
+                      e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0, e5 = -17253.0 / 339200.0, e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+  double k1[GEMB200_MAX_ODE], k2[GEMB200_MAX_ODE], k3[GEMB200_MAX_ODE], k4[GEMB200_MAX_ODE], k5[GEMB200_MAX_ODE], k6[GEMB200_MAX_ODE];
+  double y1[GEMB200_MAX_ODE], ysti[GEMB200_MAX_ODE];
+  double x = t_start, xend = t_end, posneg = dt >= 0 ? 1.0 : -1.0, hmax = fabs(dt);
+  double facold = 1e-4;
+  system_equation(o, y, u, k1);
+  /* HINIT */
+  double h;
+  {
+    double dnf = 0, dny = 0;
+    for (int i = 0; i < n; ++i) { double sk = atol + rtol * fabs(y[i]); dnf += (k1[i] / sk) * (k1[i] / sk); dny += (y[i] / sk) * (y[i] / sk); }
+    h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+    h = fmin(h, hmax) * posneg;
+    for (int i = 0; i < n; ++i) y1[i] = y[i] + h * k1[i];
+    system_equation(o, y1, u, k2);
+    double der2 = 0;
+    for (int i = 0; i < n; ++i) { double sk = atol + rtol * fabs(y[i]); double d = (k2[i] - k1[i]) / sk; der2 += d * d; }
+    der2 = sqrt(der2) / h;
+    double der12 = fmax(fabs(der2), sqrt(dnf));
+    double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3) : pow(0.01 / der12, 1.0 / 5.0);
+    h = fmin(fmin(100 * fabs(h), h1), hmax) * posneg;
+  }
+  int last = 0, reject = 0;
+  for (int nstep = 0; nstep <= 500; ++nstep) {
+    /* IDID=-3 "step size too small": scipy only warns, ode.integrate returns the state reached so far and the
+     * reference carries on with solver.t NOT advanced (physical_systems.py:514).  This really happens with the
+     * default solver on Finite envs when the state is round-off-sized (|y|~1e-16, atol=1e-12), see DESIGN.md. */
+    if (0.1 * fabs(h) <= fabs(x) * uround) return x;
+    if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = 1; }
+    for (int i = 0; i < n; ++i) y1[i] = y[i] + h * a21 * k1[i];
+    system_equation(o, y1, u, k2);
+    for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a31 * k1[i] + a32 * k2[i]);
+    system_equation(o, y1, u, k3);
+    for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
+    system_equation(o, y1, u, k4);
+    for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+    system_equation(o, y1, u, k5);
+    for (int i = 0; i < n; ++i) ysti[i] = y[i] + h * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+    system_equation(o, ysti, u, k6);
+    for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a71 * k1[i] + a73 * k3[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
+    system_equation(o, y1, u, k2);
+    double err = 0;
+    for (int i = 0; i < n; ++i) {
+      k4[i] = (e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k2[i]) * h;
+      double sk = atol + rtol * fmax(fabs(y[i]), fabs(y1[i]));
+      err += (k4[i] / sk) * (k4[i] / sk);
+    }
+    err = sqrt(err / n);
+    double fac11 = pow(err, expo1);
+    double fac = fac11 / pow(facold, beta);
+    fac = fmax(facc2, fmin(facc1, fac / safe));
+    double hnew = h / fac;
+    if (err <= 1.0) {
+      facold = fmax(err, 1e-4);
+      for (int i = 0; i < n; ++i) { k1[i] = k2[i]; y[i] = y1[i]; }
+      x += h;
+      if (last) return xend;
+      if (fabs(hnew) > hmax) hnew = posneg * hmax;
+      if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
+      reject = 0;
+    } else {
+      hnew = h / fmin(facc1, fac11 / safe);
+      reject = 1;
+      last = 0;
+    }
+    h = hnew;
+  }
+  return x; /* IDID=-2: more than nsteps=500 steps needed */
+}
+
+/* OdeSolver.integrate(t): returns the time actually reached (== t_end except for a failing dopri5) */
+static double integrate(const gem_oracle* o, double* y, double t_start, double t_end, const double* u) {
+  switch (o->cfg.solver_kind) {
+    case GEMB200_SOLVER_EULER: integrate_euler(o, y, t_end - t_start, o->cfg.solver_nsteps, u); return t_end;
+    case GEMB200_SOLVER_RK4: integrate_rk4(o, y, t_end - t_start, o->cfg.solver_nsteps, u); return t_end;
+    default: return integrate_dopri5(o, y, t_start, t_end, u);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* converters (converters.py)                                                                                    */
+/* ------------------------------------------------------------------------------------------------------------ */
+static double clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); } /* min(max(.)) :146 */
+static double sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }         /* np.sign :184 */
+
+/* FiniteTwoQuadrantConverter._set_switching_pattern :300-310; returns number of switching times (1 or 2) */
+static int f2qc_set_action(const gem_oracle* o, sub2qc_t* s, int action, double t) {
+  s->action_start_time = t;
+  s->cur_action_i = action;
+  if (action == 0 || s->switching_state == 0 || action == s->switching_state || o->cfg.interlocking_time == 0) {
+    s->pattern[0] = action; s->pattern_len = 1;
+    return 1;
+  }
+  s->pattern[0] = 0; s->pattern[1] = action; s->pattern_len = 2;
+  return 2;
+}
+/* FiniteTwoQuadrantConverter.convert :270-287 */
+static double f2qc_convert(const gem_oracle* o, sub2qc_t* s, double i_out, double t) {
+  if (t - o->cfg.tau / 1000 > s->action_start_time + o->cfg.interlocking_time) s->switching_state = s->pattern[s->pattern_len - 1];
+  else s->switching_state = s->pattern[0];
+  if (s->switching_state == 0) return i_out < 0 ? 1.0 : 0.0;
+  if (s->switching_state == 1) return 1.0;
+  return 0.0;
+}
+/* FiniteTwoQuadrantConverter.i_sup :289-298 */
+static double f2qc_i_sup(const sub2qc_t* s, double i_out) {
+  if (s->switching_state == 0) return i_out < 0 ? i_out : 0.0;
+  if (s->switching_state == 1) return i_out;
+  return 0.0;
+}
+/* ContTwoQuadrantConverter via ContDynamicallyAveragedConverter.convert :148-158, _interlock :176-184 */
+static double c2qc_convert(const gem_oracle* o, const sub2qc_t* s, double i_out) {
+  return clip(s->cur_action - sgn(i_out) / o->cfg.tau * o->cfg.interlocking_time, 0.0, 1.0);
+}
+/* ContTwoQuadrantConverter.i_sup :429-435 */
+static double c2qc_i_sup(const gem_oracle* o, const sub2qc_t* s, double i_out) {
+  double ic = i_out < 0 ? 1.0 : 0.0;
+  return (s->cur_action + o->cfg.interlocking_time / o->cfg.tau * (ic - s->cur_action)) * i_out;
+}
+
+static const int B6_SUBACTIONS[8][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 2}, {2, 1, 1}, {1, 2, 2}, {1, 2, 1}, {1, 1, 2}, {1, 1, 1}}; /* :788-797 */
+
+/* converter.set_action: returns the number of switching segments (1 or 2) and the first switching time offset.
+ * With equal interlocking times on all legs the sorted unique set of times is {t+t_il, t+tau} or {t+tau}. */
+static int conv_set_action(const gem_oracle* o, env_t* e, const double* act_f, const int32_t* act_i, double t) {
+  int nseg = 1;
+  int ai = 0, af = 0;
+  for (int slot = 0; slot < 2; ++slot) {
+    int kind = o->cfg.converter_kind[slot];
+    if (kind == GEMB200_CONV_NONE) continue;
+    sub2qc_t* s = e->sub + o->slot_off[slot];
+    if (o->cfg.finite) {
+      int a = act_i[ai++];
+      switch (kind) {
+        case GEMB200_CONV_1QC: e->cur_action1qc[slot] = a; break; /* :59-61 */
+        case GEMB200_CONV_2QC: if (f2qc_set_action(o, s, a, t) > 1) nseg = 2; break;
+        case GEMB200_CONV_4QC: { /* :350-360 */
+          static const int a0[4] = {1, 1, 2, 2}, a1[4] = {1, 2, 1, 2};
+          if (f2qc_set_action(o, s, a0[a], t) > 1) nseg = 2;
+          if (f2qc_set_action(o, s + 1, a1[a], t) > 1) nseg = 2;
+        } break;
+        case GEMB200_CONV_B6: /* :824-835 */
+          for (int l = 0; l < 3; ++l) if (f2qc_set_action(o, s + l, B6_SUBACTIONS[a][l], t) > 1) nseg = 2;
+          break;
+      }
+    } else {
+      switch (kind) {
+        case GEMB200_CONV_1QC: /* :371-401, clip to its action space [0,1] :144-146 */
+        case GEMB200_CONV_2QC: s->cur_action = clip(act_f[af++], 0.0, 1.0); break;
+        case GEMB200_CONV_4QC: { /* :484-491 */
+          double a = act_f[af++];
+          s[0].cur_action = clip(0.5 * (a + 1), 0.0, 1.0);
+          s[1].cur_action = clip(-0.5 * (a - 1), 0.0, 1.0);
+        } break;
+        case GEMB200_CONV_B6: /* :897-903 */
+          for (int l = 0; l < 3; ++l) s[l].cur_action = clip(0.5 * (act_f[af++] + 1), 0.0, 1.0);
+          break;
+      }
+    }
+  }
+  return nseg;
+}
+
+/* converter.convert(i_out, t) -> u_in (not yet multiplied by u_sup); i_out laid out per slot */
+static void conv_convert(const gem_oracle* o, env_t* e, const double* i_out, double t, double* u_out) {
+  int io = 0, uo = 0;
+  for (int slot = 0; slot < 2; ++slot) {
+    int kind = o->cfg.converter_kind[slot];
+    if (kind == GEMB200_CONV_NONE) continue;
+    sub2qc_t* s = e->sub + o->slot_off[slot];
+    if (o->cfg.finite) {
+      switch (kind) {
+        case GEMB200_CONV_1QC: u_out[uo++] = i_out[io] >= 0 ? (double)e->cur_action1qc[slot] : 1.0; io++; break; /* :236-238 */
+        case GEMB200_CONV_2QC: u_out[uo++] = f2qc_convert(o, s, i_out[io], t); io++; break;
+        case GEMB200_CONV_4QC: u_out[uo++] = f2qc_convert(o, s, i_out[io], t) - f2qc_convert(o, s + 1, -i_out[io], t); io++; break; /* :346-348 */
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) u_out[uo++] = f2qc_convert(o, s + l, i_out[io++], t) - 0.5; break; /* :814-822 */
+      }
+    } else {
+      switch (kind) {
+        case GEMB200_CONV_1QC: u_out[uo++] = clip(i_out[io] >= 0 ? s->cur_action : 1.0, 0.0, 1.0); io++; break; /* :388-394 */
+        case GEMB200_CONV_2QC: u_out[uo++] = c2qc_convert(o, s, i_out[io]); io++; break;
+        case GEMB200_CONV_4QC: u_out[uo++] = c2qc_convert(o, s, i_out[io]) - c2qc_convert(o, s + 1, i_out[io]); io++; break; /* :480-482 (same i_out for both) */
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) u_out[uo++] = c2qc_convert(o, s + l, i_out[io++]) - 0.5; break; /* :888-895 */
+      }
+    }
+  }
+}
+
+/* converter.i_sup — computed and ignored by the ideal supply (voltage_supplies.py:70-72); kept for fidelity */
+static double conv_i_sup(const gem_oracle* o, const env_t* e, const double* i_out) {
+  double r = 0;
+  int io = 0;
+  for (int slot = 0; slot < 2; ++slot) {
+    int kind = o->cfg.converter_kind[slot];
+    if (kind == GEMB200_CONV_NONE) continue;
+    const sub2qc_t* s = e->sub + o->slot_off[slot];
+    if (o->cfg.finite) {
+      switch (kind) {
+        case GEMB200_CONV_1QC: r += e->cur_action1qc[slot] == 1 ? i_out[io] : 0; io++; break;
+        case GEMB200_CONV_2QC: r += f2qc_i_sup(s, i_out[io]); io++; break;
+        case GEMB200_CONV_4QC: r += f2qc_i_sup(s, i_out[io]) + f2qc_i_sup(s + 1, -i_out[io]); io++; break;
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) r += f2qc_i_sup(s + l, i_out[io++]); break;
+      }
+    } else {
+      switch (kind) {
+        case GEMB200_CONV_1QC: r += s->cur_action * i_out[io]; io++; break;
+        case GEMB200_CONV_2QC: r += c2qc_i_sup(o, s, i_out[io]); io++; break;
+        case GEMB200_CONV_4QC: r += c2qc_i_sup(o, s, i_out[io]) + c2qc_i_sup(o, s + 1, -i_out[io]); io++; break;
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) r += c2qc_i_sup(o, s + l, i_out[io++]); break;
+      }
+    }
+  }
+  return r;
+}
+
+/* converter.reset(): [0.0] per QC, [-0.5]*3 for B6 (:45-54, :805-812, :880-886); _switching_state is NOT cleared */
+static void conv_reset(const gem_oracle* o, env_t* e, double* u_out) {
+  int uo = 0;
+  for (int slot = 0; slot < 2; ++slot) {
+    int kind = o->cfg.converter_kind[slot];
+    if (kind == GEMB200_CONV_NONE) continue;
+    sub2qc_t* s = e->sub + o->slot_off[slot];
+    for (int l = 0; l < o->n_sub[slot]; ++l) { s[l].cur_action = 0.0; s[l].cur_action_i = 0; s[l].action_start_time = 0.0; }
+    e->cur_action1qc[slot] = 0;
+    if (kind == GEMB200_CONV_B6) { u_out[uo++] = -0.5; u_out[uo++] = -0.5; u_out[uo++] = -0.5; }
+    else u_out[uo++] = 0.0;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* three-phase transforms three_phase_motor.py:18-88                                                             */
+/* ------------------------------------------------------------------------------------------------------------ */
+/* The matrices are pre-multiplied exactly like the reference's class attributes (_t23 = 2/3 * [[...]]) and the
+ * products accumulated like np.matmul does for these tiny shapes, so that even the round-off residue
+ * (e.g. u_dq ~ 1e-14 V for a zero vector) is reproduced; the default dopri5's behaviour depends on it. */
+static void t_23(const double* abc, double* ab) {
+  const double s3 = sqrt(3.0);
+  const double m00 = 2.0 / 3.0 * 1.0, m01 = 2.0 / 3.0 * -0.5, m02 = 2.0 / 3.0 * -0.5;
+  const double m11 = 2.0 / 3.0 * (0.5 * s3), m12 = 2.0 / 3.0 * (-0.5 * s3);
+  /* accumulation order + fused multiply-adds of the BLAS gemv numpy dispatches to here (probed: reproduces
+   * np.matmul(_t23, [210,210,210]) = [-1.0325e-14, 8.88e-16] bit for bit) */
+  ab[0] = fma(m02, abc[2], fma(m00, abc[0], m01 * abc[1]));
+  ab[1] = fma(m12, abc[2], fma(0.0, abc[0], m11 * abc[1]));
+}
+static void t_32(const double* ab, double* abc) {
+  const double s3 = sqrt(3.0);
+  abc[0] = 1.0 * ab[0] + 0.0 * ab[1];
+  abc[1] = -0.5 * ab[0] + (0.5 * s3) * ab[1];
+  abc[2] = -0.5 * ab[0] + (-0.5 * s3) * ab[1];
+}
+static void q_rot(const double* x, double eps, double* out) {
+  double c = cos(eps), s = sin(eps);
+  out[0] = c * x[0] - s * x[1];
+  out[1] = s * x[0] + c * x[1];
+}
+static void abc_to_dq(const double* abc, double eps, double* dq) { double ab[2]; t_23(abc, ab); q_rot(ab, -eps, dq); }
+static void dq_to_abc(const double* dq, double eps, double* abc) { double ab[2]; q_rot(dq, eps, ab); t_32(ab, abc); }
+
+static double wrap_eps(double eps) { /* physical_systems.py:520-522: python float % */
+  double r = fmod(eps, 2 * M_PI);
+  if (r < 0) r += 2 * M_PI;
+  if (r > M_PI) r -= 2 * M_PI;
+  return r;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* simulate                                                                                                      */
+/* ------------------------------------------------------------------------------------------------------------ */
+static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const int32_t* act_i, double* state) {
+  const gemb200_config* c = &o->cfg;
+  const int mk = c->motor_kind;
+  const double u_sup = c->u_sup; /* IdealVoltageSupply.get_voltage voltage_supplies.py:70-72 */
+  double* y = e->ode;
+  double i_in[4], u_in[4], u_solver[4];
+  double t0 = e->t;
+  int nseg = conv_set_action(o, e, act_f, act_i, t0);
+  double seg_end[2];
+  if (nseg == 2) { seg_end[0] = t0 + c->interlocking_time; seg_end[1] = t0 + c->tau; }
+  else seg_end[0] = t0 + c->tau;
+  double t_solver = t0;
+  double eps = 0.0, eps_fs = 0.0;
+  for (int seg = 0; seg < nseg; ++seg) {
+    /* currents flowing into the motor at the start of the segment, in converter coordinates */
+    switch (mk) {
+      case GEMB200_MOTOR_PERMEX_DC:
+      case GEMB200_MOTOR_SERIES_DC: i_in[0] = y[1]; break;              /* physical_systems.py:174 */
+      case GEMB200_MOTOR_SHUNT_DC: i_in[0] = y[1] + y[2]; break;         /* dc_shunt_motor.py:66-68 */
+      case GEMB200_MOTOR_EXTEX_DC: i_in[0] = y[1]; i_in[1] = y[2]; break; /* dc_motor.py:110-112 */
+      case GEMB200_MOTOR_PMSM:
+      case GEMB200_MOTOR_SYNRM: eps = y[3]; dq_to_abc(y + 1, eps, i_in); break; /* :489-493, :505 */
+      case GEMB200_MOTOR_EESM: eps = y[4]; dq_to_abc(y + 1, eps, i_in); i_in[3] = y[3]; break; /* :621-624 */
+      case GEMB200_MOTOR_SCIM: eps_fs = atan2(y[4], y[3]); t_32(y + 1, i_in); break; /* :775-782, :765-769 */
+    }
+    (void)conv_i_sup(o, e, i_in);             /* :507 */
+    conv_convert(o, e, i_in, t_solver, u_in); /* :509 */
+    for (int j = 0; j < 4; ++j) u_in[j] *= u_sup; /* :510 */
+    switch (mk) {
+      case GEMB200_MOTOR_PMSM:
+      case GEMB200_MOTOR_SYNRM: abc_to_dq(u_in, eps, u_solver); break;                  /* :511 */
+      case GEMB200_MOTOR_EESM: abc_to_dq(u_in, eps, u_solver); u_solver[2] = u_in[3]; break; /* :642 */
+      case GEMB200_MOTOR_SCIM: t_23(u_in, u_solver); break;                             /* :797-799 */
+      default: u_solver[0] = u_in[0]; u_solver[1] = u_in[1]; break;
+    }
+    t_solver = integrate(o, y, t_solver, seg_end[seg], u_solver); /* :513 */
+  }
+  e->t = t_solver;
+  e->k += 1;
+  const double* lim = c->limits;
+  double tq = torque(o, y + 1);
+  int n = 0;
+  state[n++] = y[0];
+  state[n++] = tq;
+  switch (mk) {
+    case GEMB200_MOTOR_PERMEX_DC:
+    case GEMB200_MOTOR_SERIES_DC: state[n++] = y[1]; state[n++] = u_in[0]; break; /* :194-201 */
+    case GEMB200_MOTOR_SHUNT_DC: state[n++] = y[1]; state[n++] = y[2]; state[n++] = u_in[0]; break;
+    case GEMB200_MOTOR_EXTEX_DC: state[n++] = y[1]; state[n++] = y[2]; state[n++] = u_in[0]; state[n++] = u_in[1]; break;
+    case GEMB200_MOTOR_PMSM:
+    case GEMB200_MOTOR_SYNRM: { /* :516-525 (eps here is the angle at the start of the LAST segment) */
+      double i_abc[3];
+      dq_to_abc(y + 1, eps, i_abc);
+      for (int j = 0; j < 3; ++j) state[n++] = i_abc[j];
+      state[n++] = y[1]; state[n++] = y[2];
+      for (int j = 0; j < 3; ++j) state[n++] = u_in[j];
+      state[n++] = u_solver[0]; state[n++] = u_solver[1];
+      state[n++] = wrap_eps(y[3]);
+    } break;
+    case GEMB200_MOTOR_EESM: { /* :646-657 */
+      double i_abc[3];
+      dq_to_abc(y + 1, eps, i_abc);
+      for (int j = 0; j < 3; ++j) state[n++] = i_abc[j];
+      state[n++] = y[1]; state[n++] = y[2]; state[n++] = y[3];
+      for (int j = 0; j < 3; ++j) state[n++] = u_in[j];
+      state[n++] = u_solver[0]; state[n++] = u_solver[1]; state[n++] = u_solver[2];
+      state[n++] = wrap_eps(y[4]);
+    } break;
+    case GEMB200_MOTOR_SCIM: { /* :794-814: u_dq and i_dq use the field angle at the start of the last segment */
+      double u_dq[2], i_dq[2], i_abc[3];
+      abc_to_dq(u_in, eps_fs, u_dq);
+      q_rot(y + 1, -eps_fs, i_dq);
+      dq_to_abc(i_dq, eps_fs, i_abc);
+      for (int j = 0; j < 3; ++j) state[n++] = i_abc[j];
+      state[n++] = i_dq[0]; state[n++] = i_dq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = u_in[j];
+      state[n++] = u_dq[0]; state[n++] = u_dq[1];
+      state[n++] = wrap_eps(y[5]);
+    } break;
+  }
+  state[n++] = u_sup;
+  for (int j = 0; j < n; ++j) state[j] = state[j] / lim[j];
+  /* CurrentSumProcessor.simulate physical_system_wrappers/current_sum_processor.py:52-66: sum of the NORMALISED currents */
+  if (mk == GEMB200_MOTOR_SHUNT_DC) state[n] = state[2] + state[3];
+}
+
+/* SCMLSystem.reset and overrides: physical_systems.py:256-287, :527-561, :659-693, :816-847 */
+static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
+  const gemb200_config* c = &o->cfg;
+  const int mk = c->motor_kind;
+  double* y = e->ode;
+  for (int j = 0; j < o->n_ode; ++j) y[j] = c->init_ode[j];
+  double u_abc[5] = {0, 0, 0, 0, 0};
+  conv_reset(o, e, u_abc);
+  for (int j = 0; j < 4; ++j) u_abc[j] *= c->u_sup;
+  e->t = 0; e->k = 0;
+  double tq = torque(o, y + 1);
+  int n = 0;
+  state[n++] = y[0];
+  state[n++] = tq;
+  switch (mk) {
+    case GEMB200_MOTOR_PERMEX_DC:
+    case GEMB200_MOTOR_SERIES_DC: state[n++] = y[1]; state[n++] = u_abc[0]; break;
+    case GEMB200_MOTOR_SHUNT_DC: state[n++] = y[1]; state[n++] = y[2]; state[n++] = u_abc[0]; break;
+    case GEMB200_MOTOR_EXTEX_DC: state[n++] = y[1]; state[n++] = y[2]; state[n++] = u_abc[0]; state[n++] = u_abc[1]; break;
+    case GEMB200_MOTOR_PMSM:
+    case GEMB200_MOTOR_SYNRM: {
+      double eps = y[3], u_dq[2], i_abc[3];
+      if (eps > M_PI) eps -= 2 * M_PI;
+      abc_to_dq(u_abc, eps, u_dq);
+      dq_to_abc(y + 1, eps, i_abc);
+      for (int j = 0; j < 3; ++j) state[n++] = i_abc[j];
+      state[n++] = y[1]; state[n++] = y[2];
+      for (int j = 0; j < 3; ++j) state[n++] = u_abc[j];
+      state[n++] = u_dq[0]; state[n++] = u_dq[1];
+      state[n++] = eps;
+    } break;
+    case GEMB200_MOTOR_EESM: { /* :659-693 — note the reference's slot shift: u_abc has 4 entries, u_dq 2 */
+      double eps = y[4], u_dq[2], i_abc[3];
+      if (eps > M_PI) eps -= 2 * M_PI;
+      abc_to_dq(u_abc, eps, u_dq);
+      dq_to_abc(y + 1, eps, i_abc);
+      for (int j = 0; j < 3; ++j) state[n++] = i_abc[j];
+      state[n++] = y[1]; state[n++] = y[2]; state[n++] = y[3];
+      for (int j = 0; j < 4; ++j) state[n++] = u_abc[j];
+      state[n++] = u_dq[0]; state[n++] = u_dq[1];
+      state[n++] = eps;
+    } break;
+    case GEMB200_MOTOR_SCIM: {
+      double eps = y[5], eps_fs = atan2(y[4], y[3]), u_dq[2], i_dq[2], i_abc[3];
+      if (eps > M_PI) eps -= 2 * M_PI;
+      abc_to_dq(u_abc, eps_fs, u_dq);
+      q_rot(y + 1, -eps_fs, i_dq);
+      dq_to_abc(i_dq, eps_fs, i_abc);
+      for (int j = 0; j < 3; ++j) state[n++] = i_abc[j];
+      state[n++] = i_dq[0]; state[n++] = i_dq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = u_abc[j];
+      state[n++] = u_dq[0]; state[n++] = u_dq[1];
+      state[n++] = eps;
+    } break;
+  }
+  state[n++] = c->u_sup;
+  for (int j = 0; j < n; ++j) state[j] = state[j] / c->limits[j];
+  if (mk == GEMB200_MOTOR_SHUNT_DC) state[n] = state[2] + state[3]; /* current_sum_processor.py:47-50 */
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* epilogue: constraints, reward, reference generators                                                           */
+/* ------------------------------------------------------------------------------------------------------------ */
+/* ConstraintMonitor.check_constraints core.py:834-844 with merge 'max'; constraints.py:55-58, :96-98 */
+static double check_constraints(const gem_oracle* o, const double* s) {
+  double v = 0.0;
+  for (int ci = 0; ci < o->cfg.n_constraints; ++ci) {
+    uint32_t mask = o->cfg.constraint_mask[ci];
+    double vi = 0.0;
+    if (o->cfg.constraint_kind[ci] == GEMB200_CONSTRAINT_LIMIT) {
+      for (int j = 0; j < o->n_state; ++j) if ((mask >> j) & 1u) if (fabs(s[j]) > 1.0) vi = 1.0;
+    } else {
+      double sum = 0.0;
+      for (int j = 0; j < o->n_state; ++j) if ((mask >> j) & 1u) sum += s[j] * s[j];
+      vi = sum > 1.0 ? 1.0 : 0.0;
+    }
+    if (vi > v) v = vi;
+  }
+  return v;
+}
+
+/* WeightedSumOfErrors.reward weighted_sum_of_errors.py:125-129 */
+static double reward(const gem_oracle* o, const double* s, const double* ref_full, double violation) {
+  double sum = 0.0;
+  for (int j = 0; j < o->n_state; ++j) {
+    double w = o->cfg.reward_weight[j];
+    if (w == 0.0) continue; /* 0 * x = 0 for the finite x met here */
+    sum += w * pow(fabs(s[j] - ref_full[j]) / o->cfg.state_length[j], o->cfg.reward_power[j]);
+  }
+  double wse = -sum + o->cfg.reward_bias;
+  return (1.0 - violation) * wse + violation * o->cfg.violation_reward;
+}
+
+/* SubepisodedReferenceGenerator.get_reference_observation :93-100 + WienerProcess._reset_reference :30-41, one value
+ * per call instead of a pre-computed sub-episode (same distribution; RNG stream differs from numpy, see header) */
+static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx) {
+  const gemb200_config* c = &o->cfg;
+  uint32_t rw[4], rs[4];
+  int have_w = 0, have_s = 0;
+  for (int r = 0; r < c->n_ref; ++r) {
+    if (c->ref_kind[r] != GEMB200_REF_WIENER) continue;
+    if (e->ref_left[r] <= 0) {
+      if (!have_s) { rng4(o, idx, e->episode, e->step, STREAM_REF_SUBEP, rs); have_s = 1; }
+      /* two uniforms per slot: slots 0,1 share one Philox block, slots 2,3 a second one */
+      uint32_t blk[4];
+      if (r < 2) memcpy(blk, rs, sizeof(blk));
+      else { rng4(o, idx, e->episode, e->step, STREAM_REF_SUBEP + 16, blk); }
+      double ul = u01(blk[2 * (r & 1)]), us = u01(blk[2 * (r & 1) + 1]);
+      e->ref_left[r] = (int)((c->ref_len_hi[r] - c->ref_len_lo[r]) * ul + c->ref_len_lo[r]); /* int(U(lo,hi)) :37,:115-119 */
+      double l0 = log10(c->ref_sigma_lo[r]), l1 = log10(c->ref_sigma_hi[r]);
+      e->ref_sigma[r] = pow(10.0, (l1 - l0) * us + l0); /* wiener_process_reference_generator.py:31 */
+    }
+    if (!have_w) { rng4(o, idx, e->episode, e->step, STREAM_REF_WALK, rw); have_w = 1; }
+    /* Box-Muller: slots (0,1) from words (0,1), slots (2,3) from words (2,3) */
+    double u1 = u01(rw[2 * (r >> 1)]), u2 = u01(rw[2 * (r >> 1) + 1]);
+    double rad = sqrt(-2.0 * log(u1));
+    double z = (r & 1) ? rad * sin(2 * M_PI * u2) : rad * cos(2 * M_PI * u2);
+    double v = e->ref_value[r] + e->ref_sigma[r] * z; /* :35-40 */
+    if (v > c->ref_margin_hi[r]) v = c->ref_margin_hi[r];
+    if (v < c->ref_margin_lo[r]) v = c->ref_margin_lo[r];
+    e->ref_value[r] = v;
+    e->ref_left[r] -= 1;
+  }
+}
+
+/* ReferenceGenerator.reset: WienerProcessReferenceGenerator.reset :43-49 + Subepisoded.reset :71-91 */
+static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
+  const gemb200_config* c = &o->cfg;
+  uint32_t ri[4];
+  rng4(o, idx, e->episode, 0, STREAM_REF_INIT, ri);
+  for (int r = 0; r < c->n_ref; ++r) {
+    if (c->ref_kind[r] == GEMB200_REF_WIENER) {
+      e->ref_value[r] = c->ref_init_lo[r] + (c->ref_init_hi[r] - c->ref_init_lo[r]) * u01(ri[r]);
+      e->ref_left[r] = 0; /* _current_episode_length = -1 forces a new sub-episode */
+      e->ref_sigma[r] = 0;
+    } else {
+      e->ref_value[r] = c->ref_value[r];
+    }
+  }
+  ref_advance(o, e, idx); /* reset() returns get_reference_observation() :82-91 via core.py:499-503 */
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* public API (loaded by tests/bench via ctypes)                                                                 */
+/* ------------------------------------------------------------------------------------------------------------ */
+int gem_oracle_create(const gemb200_config* cfg, gem_oracle** out) {
+  if (!cfg || cfg->struct_size != (int32_t)sizeof(gemb200_config)) return -4;
+  gem_oracle* o = (gem_oracle*)calloc(1, sizeof(gem_oracle));
+  o->cfg = *cfg;
+  if (dims(o)) { free(o); return -1; }
+  update_model(o);
+  o->env = (env_t*)calloc((size_t)cfg->n_envs, sizeof(env_t));
+  *out = o;
+  return 0;
+}
+void gem_oracle_destroy(gem_oracle* o) { if (o) { free(o->env); free(o); } }
+void gem_oracle_dims(const gem_oracle* o, int32_t* n_state, int32_t* n_ode, int32_t* n_act, int32_t* n_ref) {
+  *n_state = o->n_state; *n_ode = o->n_ode; *n_act = o->n_act; *n_ref = o->n_ref;
+}
+
+/* env.reset (core.py:300-319). mask NULL = all. obs [N][n_state], ref_next [N][n_ref] (may be NULL). */
+void gem_oracle_reset(gem_oracle* o, const uint8_t* mask, double* obs, double* ref_next) {
+  double st[GEMB200_MAX_STATE];
+  for (int64_t i = 0; i < o->cfg.n_envs; ++i) {
+    if (mask && !mask[i]) continue;
+    env_t* e = o->env + i;
+    e->episode += 1;
+    e->step = 0;
+    ps_reset(o, e, st);
+    ref_reset(o, e, i);
+    if (obs) memcpy(obs + i * o->n_state, st, sizeof(double) * o->n_state);
+    if (ref_next) for (int r = 0; r < o->n_ref; ++r) ref_next[i * o->n_ref + r] = e->ref_value[r];
+  }
+}
+
+static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, double* ref_next, double* rew, uint8_t* term) {
+  env_t* e = o->env + i;
+  double st[GEMB200_MAX_STATE], ref_full[GEMB200_MAX_STATE];
+  const double* af = o->cfg.finite ? NULL : (const double*)action + i * o->n_act;
+  const int32_t* ai = o->cfg.finite ? (const int32_t*)action + i * o->n_act : NULL;
+  simulate(o, e, af, ai, st);                                   /* core.py:344 */
+  memset(ref_full, 0, sizeof(ref_full));
+  for (int r = 0; r < o->n_ref; ++r) ref_full[o->cfg.ref_state[r]] = e->ref_value[r]; /* core.py:346 */
+  double v = check_constraints(o, st);                          /* core.py:348 */
+  double rw = reward(o, st, ref_full, v);                        /* core.py:349 */
+  int terminated = v >= 1.0;                                    /* core.py:350 */
+  e->step += 1;
+  ref_advance(o, e, i);                                         /* core.py:351 */
+  if (terminated && o->cfg.autoreset == GEMB200_AUTORESET_SAME_STEP) {
+    e->episode += 1;
+    e->step = 0;
+    ps_reset(o, e, st);
+    ref_reset(o, e, i);
+  }
+  if (obs) memcpy(obs + i * o->n_state, st, sizeof(double) * o->n_state);
+  if (ref_next) for (int r = 0; r < o->n_ref; ++r) ref_next[i * o->n_ref + r] = e->ref_value[r];
+  if (rew) rew[i] = rw;
+  if (term) term[i] = (uint8_t)terminated;
+}
+
+/* env.step for all envs (core.py:328-371); action: double [N][n_act] or int32 [N][n_slots].
+ * nthreads > 1 splits the env range over POSIX threads (envs are independent; the reference itself is
+ * single-threaded — process/thread replication is its best case). */
+typedef struct { gem_oracle* o; const void* action; double* obs; double* ref; double* rew; uint8_t* term; int64_t lo, hi; } job_t;
+static void* step_range(void* arg) {
+  job_t* j = (job_t*)arg;
+  for (int64_t i = j->lo; i < j->hi; ++i) step_one(j->o, i, j->action, j->obs, j->ref, j->rew, j->term);
+  return NULL;
+}
+void gem_oracle_step(gem_oracle* o, const void* action, double* obs, double* ref_next, double* rew, uint8_t* term, int nthreads) {
+  int64_t n = o->cfg.n_envs;
+  if (nthreads > n) nthreads = (int)n;
+  if (nthreads <= 1) {
+    job_t j = {o, action, obs, ref_next, rew, term, 0, n};
+    step_range(&j);
+    return;
+  }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  job_t* jobs = (job_t*)malloc(sizeof(job_t) * nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t] = (job_t){o, action, obs, ref_next, rew, term, n * t / nthreads, n * (t + 1) / nthreads};
+    pthread_create(&th[t], NULL, step_range, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+void gem_oracle_get_ode_state(const gem_oracle* o, double* out) {
+  for (int64_t i = 0; i < o->cfg.n_envs; ++i) memcpy(out + i * o->n_ode, o->env[i].ode, sizeof(double) * o->n_ode);
+}
+void gem_oracle_set_ode_state(gem_oracle* o, const double* in) {
+  for (int64_t i = 0; i < o->cfg.n_envs; ++i) memcpy(o->env[i].ode, in + i * o->n_ode, sizeof(double) * o->n_ode);
+}
+void gem_oracle_get_reference(const gem_oracle* o, double* out) {
+  for (int64_t i = 0; i < o->cfg.n_envs; ++i) for (int r = 0; r < o->n_ref; ++r) out[i * o->n_ref + r] = o->env[i].ref_value[r];
+}
+void gem_oracle_set_reference(gem_oracle* o, const double* in) {
+  for (int64_t i = 0; i < o->cfg.n_envs; ++i) for (int r = 0; r < o->n_ref; ++r) o->env[i].ref_value[r] = in[i * o->n_ref + r];
+}
+/* sub-episode bookkeeping, exposed so that the device generator can be compared slot by slot */
+void gem_oracle_get_ref_aux(const gem_oracle* o, double* sigma, int32_t* left) {
+  for (int64_t i = 0; i < o->cfg.n_envs; ++i) for (int r = 0; r < o->n_ref; ++r) { sigma[i * o->n_ref + r] = o->env[i].ref_sigma[r]; left[i * o->n_ref + r] = o->env[i].ref_left[r]; }
+}
+/* exposed for the known-answer tests of the reference's converter tables / solver vectors */
+void gem_oracle_philox(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_10(ctr, k0, k1); }

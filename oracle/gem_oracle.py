@@ -1,0 +1,119 @@
+"""ctypes wrapper of oracle/gem_oracle.c — TEST INFRASTRUCTURE, never imported by the product package.
+
+The oracle takes the same POD `gemb200_config` as the C-ABI (struct definition only; see include/gemb200.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libgem_oracle.so")
+SOLVER_DOPRI5 = 100  # oracle-only solver kind
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "gem_oracle.c")
+    hdr = os.path.join(HERE, "..", "include", "gemb200.h")
+    stale = (not os.path.exists(LIB)) or any(
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(LIB) for p in (src, hdr)
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.gem_oracle_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib.gem_oracle_destroy.argtypes = [C.c_void_p]
+        _lib.gem_oracle_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+        _lib.gem_oracle_reset.argtypes = [C.c_void_p] * 4
+        _lib.gem_oracle_step.argtypes = [C.c_void_p] * 6 + [C.c_int]
+        for n in ("get_ode_state", "set_ode_state", "get_reference", "set_reference"):
+            getattr(_lib, "gem_oracle_" + n).argtypes = [C.c_void_p, C.c_void_p]
+        _lib.gem_oracle_get_ref_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.gem_oracle_philox.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """N-env float64 CPU oracle with the env.reset / env.step contract of the reference (core.py:300-371)."""
+
+    def __init__(self, cfg, nthreads=1):
+        self._lib = lib()
+        self.cfg = cfg
+        self.n = int(cfg.n_envs)
+        self.nthreads = int(nthreads)
+        h = C.c_void_p()
+        rc = self._lib.gem_oracle_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise ValueError(f"gem_oracle_create rc={rc}")
+        self._h = h
+        d = [C.c_int32() for _ in range(4)]
+        self._lib.gem_oracle_dims(h, *[C.byref(x) for x in d])
+        self.n_state, self.n_ode, self.n_act, self.n_ref = [x.value for x in d]
+        self.finite = bool(cfg.finite)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.gem_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        obs = np.zeros((self.n, self.n_state))
+        ref = np.zeros((self.n, self.n_ref))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._lib.gem_oracle_reset(self._h, _p(m), _p(obs), _p(ref))
+        return obs, ref
+
+    def step(self, action):
+        if self.finite:
+            a = np.ascontiguousarray(np.asarray(action).reshape(self.n, self.n_act), dtype=np.int32)
+        else:
+            a = np.ascontiguousarray(np.asarray(action, dtype=np.float64).reshape(self.n, self.n_act))
+        obs = np.zeros((self.n, self.n_state))
+        ref = np.zeros((self.n, self.n_ref))
+        rew = np.zeros(self.n)
+        term = np.zeros(self.n, dtype=np.uint8)
+        self._lib.gem_oracle_step(self._h, _p(a), _p(obs), _p(ref), _p(rew), _p(term), self.nthreads)
+        return obs, ref, rew, term
+
+    def get_ode_state(self):
+        out = np.zeros((self.n, self.n_ode))
+        self._lib.gem_oracle_get_ode_state(self._h, _p(out))
+        return out
+
+    def set_ode_state(self, y):
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(self.n, self.n_ode))
+        self._lib.gem_oracle_set_ode_state(self._h, _p(y))
+
+    def get_reference(self):
+        out = np.zeros((self.n, self.n_ref))
+        self._lib.gem_oracle_get_reference(self._h, _p(out))
+        return out
+
+    def set_reference(self, r):
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.float64).reshape(self.n, self.n_ref))
+        self._lib.gem_oracle_set_reference(self._h, _p(r))
+
+    def get_ref_aux(self):
+        sigma = np.zeros((self.n, self.n_ref))
+        left = np.zeros((self.n, self.n_ref), dtype=np.int32)
+        self._lib.gem_oracle_get_ref_aux(self._h, _p(sigma), _p(left))
+        return sigma, left
+
+
+def philox(counter, key):
+    c = np.array(counter, dtype=np.uint32)
+    lib().gem_oracle_philox(_p(c), int(key[0]), int(key[1]))
+    return c

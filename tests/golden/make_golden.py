@@ -173,6 +173,10 @@ def record(case):
         kwargs["motor"] = dict(case["motor"])
     if case.get("tau") is not None:
         kwargs["tau"] = case["tau"]
+    if case.get("converter_cls") is not None:
+        kwargs["converter"] = getattr(ps, case["converter_cls"])(**case.get("converter_args", {}))
+    if case.get("no_wrappers"):
+        kwargs["physical_system_wrappers"] = ()
     env = gem.make(case["env_id"], visualization=NoViz(), ode_solver=make_solver(case["solver"]), **kwargs)
     K = case["steps"]
     actions = action_sequence(env, K, case["seed"], case.get("style", "mixed"))
@@ -266,6 +270,24 @@ CASES = [
     C("extex_cc_rk4", "Cont-CC-ExtExDc-v0", "rk4", steps=1500),
     C("extex_sc_dopri5", "Cont-SC-ExtExDc-v0", "dopri5", steps=1500),
     C("extex_fin_cc_rk4", "Finite-CC-ExtExDc-v0", "rk4", steps=1500),
+    C("shunt_cc_rk4", "Cont-CC-ShuntDc-v0", "rk4", steps=1500),
+    C("shunt_fin_sc_rk4", "Finite-SC-ShuntDc-v0", "rk4", steps=1500),
+    # elementary converters (converters.py:218-310, :371-435) incl. interlocking
+    C("permex_cont1qc_rk4", "Cont-CC-PermExDc-v0", "rk4", steps=1000, converter_cls="ContOneQuadrantConverter"),
+    C("permex_cont2qc_rk4", "Cont-CC-PermExDc-v0", "rk4", steps=1000, converter_cls="ContTwoQuadrantConverter",
+      converter_args=dict(interlocking_time=3e-6)),
+    C("permex_cont4qc_interlock_rk4", "Cont-SC-PermExDc-v0", "rk4", steps=1000, converter=dict(interlocking_time=5e-6)),
+    C("permex_fin1qc_rk4", "Finite-CC-PermExDc-v0", "rk4", steps=1000, converter_cls="FiniteOneQuadrantConverter"),
+    C("permex_fin2qc_interlock_rk4", "Finite-CC-PermExDc-v0", "rk4", steps=1000, converter_cls="FiniteTwoQuadrantConverter",
+      converter_args=dict(interlocking_time=1e-6)),
+    C("permex_fin4qc_interlock_rk4", "Finite-SC-PermExDc-v0", "rk4", steps=1000, converter=dict(interlocking_time=1e-6)),
+    C("scim_fin_cc_interlock_rk4", "Finite-CC-SCIM-v0", "rk4", steps=1500, converter=dict(interlocking_time=1e-6)),
+    # non-default parameters: load polynomial with all terms, custom motor, non-zero constant initial state
+    C("pmsm_sc_polyload_rk4", "Cont-SC-PMSM-v0", "rk4", steps=1500,
+      load=dict(load_parameter=dict(a=0.5, b=0.02, c=1e-4, j_load=2e-3))),
+    C("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500,
+      motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
+                 motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0)))),
 ]
 
 

@@ -1,0 +1,162 @@
+"""Shared test helpers: golden-fixture loading and golden-meta -> gemb200_config translation.
+
+The translation here is deliberately independent of the product's own spec compiler
+(gym_electric_motor_b200/spec.py): it takes limits / weights verbatim from the values the REFERENCE reported
+when the golden was recorded, so oracle-vs-golden tests do not depend on the product's host logic.
+"""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from gym_electric_motor_b200 import _cabi as K  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+MOTOR_KIND = {
+    "DcPermanentlyExcitedMotor": K.MOTOR_PERMEX_DC,
+    "DcSeriesMotor": K.MOTOR_SERIES_DC,
+    "DcShuntMotor": K.MOTOR_SHUNT_DC,
+    "DcExternallyExcitedMotor": K.MOTOR_EXTEX_DC,
+    "PermanentMagnetSynchronousMotor": K.MOTOR_PMSM,
+    "SynchronousReluctanceMotor": K.MOTOR_SYNRM,
+    "ExternallyExcitedSynchronousMotor": K.MOTOR_EESM,
+    "SquirrelCageInductionMotor": K.MOTOR_SCIM,
+}
+MP_SLOT = dict(
+    p=K.MP_P, r_s=K.MP_R_S, l_d=K.MP_L_D, l_q=K.MP_L_Q, psi_p=K.MP_PSI_P, j_rotor=K.MP_J_ROTOR, r_a=K.MP_R_A,
+    l_a=K.MP_L_A, psi_e=K.MP_PSI_E, r_e=K.MP_R_E, l_e=K.MP_L_E, l_e_prime=K.MP_L_E_PRIME, l_m=K.MP_L_M, k=K.MP_K,
+    l_sigs=K.MP_L_SIGS, l_sigr=K.MP_L_SIGR, r_r=K.MP_R_E,
+)
+CONV = {
+    "ContOneQuadrantConverter": (0, [K.CONV_1QC]),
+    "ContTwoQuadrantConverter": (0, [K.CONV_2QC]),
+    "ContFourQuadrantConverter": (0, [K.CONV_4QC]),
+    "ContB6BridgeConverter": (0, [K.CONV_B6]),
+    "FiniteOneQuadrantConverter": (1, [K.CONV_1QC]),
+    "FiniteTwoQuadrantConverter": (1, [K.CONV_2QC]),
+    "FiniteFourQuadrantConverter": (1, [K.CONV_4QC]),
+    "FiniteB6BridgeConverter": (1, [K.CONV_B6]),
+}
+N_MOTOR_ODE = {K.MOTOR_PERMEX_DC: 1, K.MOTOR_SERIES_DC: 1, K.MOTOR_SHUNT_DC: 2, K.MOTOR_EXTEX_DC: 2, K.MOTOR_PMSM: 3,
+               K.MOTOR_SYNRM: 3, K.MOTOR_EESM: 4, K.MOTOR_SCIM: 5}
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if "ref_data" not in p)
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files if k != "meta"}
+    d["meta"] = json.loads(str(z["meta"]))
+    return d
+
+
+def solver_from_name(name):
+    """'euler', 'euler3', 'rk4', 'rk4x2', 'dopri5' -> (kind, nsteps); dopri5 is oracle-only (kind 100)."""
+    if name == "dopri5":
+        return 100, 1
+    if name.startswith("euler"):
+        return K.SOLVER_EULER, int(name[5:] or 1)
+    if name.startswith("rk4x"):
+        return K.SOLVER_RK4, int(name[4:])
+    if name == "rk4":
+        return K.SOLVER_RK4, 1
+    raise ValueError(name)
+
+
+def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype=K.F64, layout=K.LAYOUT_AOS,
+                     autoreset=K.AUTORESET_NONE, seed=0, reset_ode=None):
+    cfg = K.new_config()
+    cfg.n_envs = n_envs
+    cfg.dtype, cfg.layout, cfg.autoreset = dtype, layout, autoreset
+    mk = MOTOR_KIND[meta["motor_class"]]
+    cfg.motor_kind = mk
+    cc = meta["converter_class"]
+    if cc in CONV:
+        cfg.finite, kinds = CONV[cc]
+    elif cc in ("ContMultiConverter", "FiniteMultiConverter"):
+        cfg.finite = int(cc.startswith("Finite"))
+        kinds = [K.CONV_B6, K.CONV_4QC] if mk == K.MOTOR_EESM else [K.CONV_4QC, K.CONV_4QC]
+    else:
+        raise ValueError(cc)
+    for i, kd in enumerate(kinds):
+        cfg.converter_kind[i] = kd
+    cfg.load_kind = K.LOAD_CONST_SPEED if meta["load_class"] == "ConstantSpeedLoad" else K.LOAD_POLY_STATIC
+    kind, nsteps = solver_from_name(solver or meta["case"]["solver"])
+    cfg.solver_kind, cfg.solver_nsteps = kind, nsteps
+    cfg.tau = meta["tau"]
+    cfg.interlocking_time = meta["interlocking_time"]
+    cfg.u_sup = meta["u_sup"]
+    for k, v in meta["motor_parameter"].items():
+        if k in MP_SLOT:
+            cfg.motor_param[MP_SLOT[k]] = v
+    lp = meta.get("load_parameter") or {}
+    cfg.load_param[K.LP_A] = lp.get("a", 0.0)
+    cfg.load_param[K.LP_B] = lp.get("b", 0.0)
+    cfg.load_param[K.LP_C] = lp.get("c", 0.0)
+    # j_total = j_load + j_rotor (mechanical_load.py:188-193); golden meta stores j_total
+    cfg.load_param[K.LP_J_LOAD] = meta["j_total"] - meta["motor_parameter"]["j_rotor"]
+    cfg.load_param[K.LP_TAU_DECAY] = 1e-3
+    n_state = len(meta["state_names"])
+    for i in range(n_state):
+        cfg.limits[i] = meta["limits"][i]
+        cfg.reward_weight[i] = meta["reward_weights"][i]
+        cfg.reward_power[i] = meta["reward_power"][i]
+        cfg.state_length[i] = meta["state_length"][i]
+    cfg.reward_bias = meta["reward_bias"]
+    cfg.violation_reward = meta["violation_reward"]
+    n_ode = 1 + N_MOTOR_ODE[mk]
+    if reset_ode is not None:
+        for i in range(n_ode):
+            cfg.init_ode[i] = float(reset_ode[i])
+    names = meta["state_names"]
+    cfg.n_constraints = len(meta["constraints"])
+    for ci, con in enumerate(meta["constraints"]):
+        cfg.constraint_kind[ci] = K.CONSTRAINT_SQUARED if con["kind"] == "SquaredConstraint" else K.CONSTRAINT_LIMIT
+        m = 0
+        for s in con["states"]:
+            m |= 1 << names.index(s)
+        cfg.constraint_mask[ci] = m
+    ref_names = meta["reference_names"]
+    cfg.n_ref = len(ref_names)
+    for r, rn in enumerate(ref_names):
+        cfg.ref_kind[r] = ref_kind
+        cfg.ref_state[r] = names.index(rn)
+    cfg.seed = seed
+    return cfg
+
+
+def replay_golden(sim, g, inject_refs=True):
+    """Drive `sim` (Oracle or device env with the same reset/step/set_reference API, N=1) through a golden
+    trajectory: same actions, reference injected before every step, reset on termination exactly where the
+    reference harness did (tests/golden/make_golden.py:record).  Returns dict of arrays shaped like the golden."""
+    K_ = len(g["actions"])
+    ref_idx = [g["meta"]["state_names"].index(n) for n in g["meta"]["reference_names"]]
+    obs0, _ = sim.reset()
+    out = dict(states=np.zeros_like(g["states"]), rewards=np.zeros(K_), terminated=np.zeros(K_, dtype=np.uint8),
+               reset_state=np.asarray(obs0, dtype=np.float64)[0])
+    for k in range(K_):
+        if inject_refs and ref_idx:
+            sim.set_reference(g["refs_used"][k][ref_idx][None, :])
+        obs, ref, rew, term = sim.step(g["actions"][k][None, ...] if g["actions"].ndim > 1 else g["actions"][k : k + 1])
+        out["states"][k] = np.asarray(obs, dtype=np.float64)[0]
+        out["rewards"][k] = float(np.asarray(rew)[0])
+        out["terminated"][k] = int(np.asarray(term)[0])
+        if g["terminated"][k]:
+            sim.reset()
+    return out
+
+
+def col_rel_err(a, b):
+    """max over columns of max|a-b| / max(|b|) — the 'column-relative' error of SURVEY.md §7."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b).max(axis=0), 1e-12)
+    return float((np.abs(a - b).max(axis=0) / scale).max())
