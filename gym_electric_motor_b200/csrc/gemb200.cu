@@ -1,0 +1,692 @@
+// gemb200.cu — C-ABI implementation (include/gemb200.h): handle management, host-side derivation of the model
+// constants from the physical parameters (the reference's *_update_model methods), kernel dispatch.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "gemb200_kernels.cuh"
+
+using namespace gemb200;
+
+// ----------------------------------------------------------------------------------------------------------------
+// error reporting
+// ----------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) return fail(GEMB200_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------------------------
+struct gemb200_handle {
+  gemb200_config cfg;
+  int fam = 0, n_state = 0, n_ode = 0, n_act = 0, n_ref = 0, nx = 0;
+  bool has_eps = false, any_wiener = false, two_segment = false;
+  size_t rsz = 4;  // sizeof(real)
+  // persistent device state
+  void* d_x = nullptr;
+  double* d_eps = nullptr;
+  void* d_ref_val = nullptr;
+  void* d_ref_sigma = nullptr;
+  int32_t* d_ref_left = nullptr;
+  uint16_t* d_sw = nullptr;
+  StepParams<float> pf;
+  StepParams<double> pd;
+  uint64_t gstep = 0;
+  int64_t launches = 0;
+  // host-buffer path
+  cudaStream_t hstream = nullptr;
+  void *d_act = nullptr, *d_obs = nullptr, *d_ref = nullptr, *d_rew = nullptr;
+  uint8_t *d_term = nullptr, *d_mask = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// dimensions / validation (SCMLSystem._set_indices physical_systems.py:141-162, :462-485, :594-617, :737-763)
+// ----------------------------------------------------------------------------------------------------------------
+static bool is_qc(int k) { return k == GEMB200_CONV_1QC || k == GEMB200_CONV_2QC || k == GEMB200_CONV_4QC; }
+
+struct Dims { int fam, n_state, n_ode, n_act, nx; bool has_eps; };
+
+static int derive_dims(const gemb200_config* c, Dims* d) {
+  const int k0 = c->converter_kind[0], k1 = c->converter_kind[1];
+  switch (c->motor_kind) {
+    case GEMB200_MOTOR_PERMEX_DC:
+    case GEMB200_MOTOR_SERIES_DC: *d = {kDC1, 5, 2, 1, 2, false}; break;
+    case GEMB200_MOTOR_SHUNT_DC: *d = {kDC2, 7, 3, 1, 3, false}; break;
+    case GEMB200_MOTOR_EXTEX_DC: *d = {kDC2, 7, 3, 2, 3, false}; break;
+    case GEMB200_MOTOR_PMSM:
+    case GEMB200_MOTOR_SYNRM: *d = {kSYNC, 14, 4, c->finite ? 1 : 3, 3, true}; break;
+    case GEMB200_MOTOR_EESM: *d = {kEESM, 16, 5, c->finite ? 2 : 4, 4, true}; break;
+    case GEMB200_MOTOR_SCIM: *d = {kSCIM, 14, 6, c->finite ? 1 : 3, 5, true}; break;
+    default: return fail(GEMB200_E_INVALID, "unknown motor_kind");
+  }
+  const bool three_phase = d->fam >= kSYNC;
+  if (three_phase) {
+    if (k0 != GEMB200_CONV_B6) return fail(GEMB200_E_INVALID, "three-phase motors need a B6 bridge in converter slot 0");
+    if (c->motor_kind == GEMB200_MOTOR_EESM) {
+      if (!is_qc(k1)) return fail(GEMB200_E_INVALID, "EESM needs a 1QC/2QC/4QC excitation converter in slot 1");
+    } else if (k1 != GEMB200_CONV_NONE) return fail(GEMB200_E_INVALID, "converter slot 1 must be NONE for this motor");
+  } else {
+    if (!is_qc(k0)) return fail(GEMB200_E_INVALID, "DC motors need a 1QC/2QC/4QC converter in slot 0");
+    if (c->motor_kind == GEMB200_MOTOR_EXTEX_DC) {
+      if (!is_qc(k1)) return fail(GEMB200_E_INVALID, "ExtEx DC motor needs an excitation converter in slot 1");
+    } else if (k1 != GEMB200_CONV_NONE) return fail(GEMB200_E_INVALID, "converter slot 1 must be NONE for this motor");
+  }
+  return GEMB200_OK;
+}
+
+static int validate(const gemb200_config* c) {
+  if (!c) return fail(GEMB200_E_INVALID, "config is NULL");
+  if (c->struct_size != (int32_t)sizeof(gemb200_config) || c->abi_version != GEMB200_ABI_VERSION)
+    return fail(GEMB200_E_ABI, "gemb200_config struct_size/abi_version mismatch (use gemb200_config_init)");
+  if (c->n_envs < 1) return fail(GEMB200_E_INVALID, "n_envs must be >= 1");
+  if (c->dtype != GEMB200_F32 && c->dtype != GEMB200_F64) return fail(GEMB200_E_INVALID, "bad dtype");
+  if (c->layout != GEMB200_LAYOUT_AOS && c->layout != GEMB200_LAYOUT_SOA) return fail(GEMB200_E_INVALID, "bad layout");
+  if (c->solver_kind != GEMB200_SOLVER_EULER && c->solver_kind != GEMB200_SOLVER_RK4)
+    return fail(GEMB200_E_INVALID, "solver_kind must be EULER or RK4 (the scipy solvers of the reference map to RK4 sub-stepping, see DESIGN.md)");
+  if (c->solver_nsteps < 1 || c->solver_nsteps > 1024) return fail(GEMB200_E_INVALID, "solver_nsteps out of range");
+  if (!(c->tau > 0)) return fail(GEMB200_E_INVALID, "tau must be positive");
+  if (c->interlocking_time < 0 || c->interlocking_time >= c->tau) return fail(GEMB200_E_INVALID, "interlocking_time must be in [0, tau)");
+  if (c->load_kind != GEMB200_LOAD_CONST_SPEED && c->load_kind != GEMB200_LOAD_POLY_STATIC) return fail(GEMB200_E_INVALID, "bad load_kind");
+  if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
+  if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
+  Dims d;
+  int rc = derive_dims(c, &d);
+  if (rc) return rc;
+  if (c->finite && c->interlocking_time > 0 && c->motor_kind == GEMB200_MOTOR_EESM)
+    return fail(GEMB200_E_INVALID, "finite EESM with interlocking time: the reference raises in this configuration "
+                                   "(physical_systems.py:632 slices u_in[:2]); not supported");
+  for (int r = 0; r < c->n_ref; ++r) {
+    if (c->ref_state[r] < 0 || c->ref_state[r] >= d.n_state) return fail(GEMB200_E_INVALID, "ref_state out of range");
+    if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_EXTERNAL) return fail(GEMB200_E_INVALID, "bad ref_kind");
+    if (c->ref_kind[r] == GEMB200_REF_WIENER && (c->ref_len_lo[r] < 1 || c->ref_len_hi[r] < c->ref_len_lo[r] || !(c->ref_sigma_lo[r] > 0)))
+      return fail(GEMB200_E_INVALID, "bad Wiener reference ranges");
+  }
+  for (int j = 0; j < d.n_state; ++j)
+    if (!(c->limits[j] != 0.0) && !(c->motor_kind == GEMB200_MOTOR_SHUNT_DC && j == 6)) return fail(GEMB200_E_INVALID, "limits must be non-zero");
+  const double j_total = c->load_param[GEMB200_LP_J_LOAD] + c->motor_param[GEMB200_MP_J_ROTOR];
+  if (c->load_kind == GEMB200_LOAD_POLY_STATIC && !(j_total > 0)) return fail(GEMB200_E_INVALID, "total inertia must be positive");
+  return GEMB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// model constants (double) -> StepParams<real>
+// ----------------------------------------------------------------------------------------------------------------
+struct Derived {
+  double c[20] = {0};
+  double tq[4] = {0};
+  double reset_obs[GEMB200_MAX_STATE] = {0};
+  double inv_j = 0, omega_lim = 0, omega_lin = 0;
+};
+
+static void derive_model(const gemb200_config* cfg, const Dims& dm, Derived* o) {
+  const double* mp = cfg->motor_param;
+  const double p = mp[GEMB200_MP_P], r_s = mp[GEMB200_MP_R_S], l_d = mp[GEMB200_MP_L_D], l_q = mp[GEMB200_MP_L_Q];
+  double* c = o->c;
+  switch (cfg->motor_kind) {
+    case GEMB200_MOTOR_PERMEX_DC: {  // dc_permanently_excited_motor.py:71-75
+      const double l_a = mp[GEMB200_MP_L_A];
+      c[0] = -mp[GEMB200_MP_PSI_E] / l_a; c[1] = -mp[GEMB200_MP_R_A] / l_a; c[2] = 0; c[3] = 1.0 / l_a;
+      o->tq[0] = mp[GEMB200_MP_PSI_E]; o->tq[1] = 0;
+    } break;
+    case GEMB200_MOTOR_SERIES_DC: {  // dc_series_motor.py:66-74
+      const double l = mp[GEMB200_MP_L_A] + mp[GEMB200_MP_L_E];
+      c[0] = 0; c[1] = (-mp[GEMB200_MP_R_A] - mp[GEMB200_MP_R_E]) / l; c[2] = -mp[GEMB200_MP_L_E_PRIME] / l; c[3] = 1.0 / l;
+      o->tq[0] = 0; o->tq[1] = mp[GEMB200_MP_L_E_PRIME];
+    } break;
+    case GEMB200_MOTOR_SHUNT_DC:
+    case GEMB200_MOTOR_EXTEX_DC: {  // dc_motor.py:95-108
+      const double l_a = mp[GEMB200_MP_L_A], l_e = mp[GEMB200_MP_L_E];
+      c[0] = -mp[GEMB200_MP_R_A] / l_a; c[1] = -mp[GEMB200_MP_L_E_PRIME] / l_a; c[2] = 1.0 / l_a;
+      c[3] = -mp[GEMB200_MP_R_E] / l_e; c[4] = 1.0 / l_e;
+      o->tq[0] = mp[GEMB200_MP_L_E_PRIME];
+    } break;
+    case GEMB200_MOTOR_PMSM:
+    case GEMB200_MOTOR_SYNRM: {  // permanent_magnet_synchronous_motor.py:107-139, synchronous_reluctance_motor.py:117-139
+      const double psi_p = cfg->motor_kind == GEMB200_MOTOR_PMSM ? mp[GEMB200_MP_PSI_P] : 0.0;
+      c[0] = -r_s / l_d; c[1] = 1.0 / l_d; c[2] = l_q * p / l_d;
+      c[3] = -psi_p * p / l_q; c[4] = -r_s / l_q; c[5] = 1.0 / l_q; c[6] = -l_d * p / l_q;
+      o->tq[0] = 1.5 * p * psi_p; o->tq[1] = 1.5 * p * (l_d - l_q);
+    } break;
+    case GEMB200_MOTOR_EESM: {  // externally_excited_synchronous_motor.py:125-153, :200-203
+      const double k = mp[GEMB200_MP_K], r_e = mp[GEMB200_MP_R_E], l_m = mp[GEMB200_MP_L_M], l_e = mp[GEMB200_MP_L_E];
+      const double r_E = k * k * 1.5 * r_e, l_M = k * 1.5 * l_m, l_E = k * k * 1.5 * l_e, ik = 2.0 / 3.0 / k;
+      const double sigma = 1.0 - l_M * l_M / (l_d * l_E);
+      c[0] = (-r_s / sigma) / l_d; c[1] = (l_M * r_E / (sigma * l_E) * ik) / l_d; c[2] = (1.0 / sigma) / l_d;
+      c[3] = (-l_M * k / (sigma * l_E)) / l_d; c[4] = (l_q * p / sigma) / l_d;
+      c[5] = -r_s / l_q; c[6] = 1.0 / l_q; c[7] = -l_d * p / l_q; c[8] = -p * l_M * ik / l_q;
+      const double s2 = l_E * ik;
+      c[9] = (l_M * r_s / (sigma * l_d)) / s2; c[10] = (-r_E / sigma * ik) / s2; c[11] = (-l_M / (sigma * l_d)) / s2;
+      c[12] = (k / sigma) / s2; c[13] = (-p * l_M * l_q / (sigma * l_d)) / s2;
+      o->tq[0] = 1.5 * p * l_M * ik; o->tq[1] = 1.5 * p * (l_d - l_q);
+    } break;
+    case GEMB200_MOTOR_SCIM: {  // induction_motor.py:287-310, :236-249
+      const double l_m = mp[GEMB200_MP_L_M], r_r = mp[GEMB200_MP_R_E];
+      const double l_s = l_m + mp[GEMB200_MP_L_SIGS], l_r = l_m + mp[GEMB200_MP_L_SIGR];
+      const double sigma = (l_s * l_r - l_m * l_m) / (l_s * l_r);
+      const double tau_r = l_r / r_r, tau_sig = sigma * l_s / (r_s + r_r * (l_m * l_m) / (l_r * l_r));
+      c[0] = -1.0 / tau_sig; c[1] = l_m * r_r / (sigma * l_s * l_r * l_r); c[2] = l_m * p / (sigma * l_r * l_s);
+      c[3] = 1.0 / (sigma * l_s); c[4] = l_m / tau_r; c[5] = -1.0 / tau_r; c[6] = p;
+      o->tq[0] = 1.5 * p * l_m / l_r;
+    } break;
+  }
+  // MechanicalLoad.set_j_rotor mechanical_load.py:188-193, polynomial_static_load.py:60-64
+  const double* lp = cfg->load_param;
+  const double j_total = lp[GEMB200_LP_J_LOAD] + mp[GEMB200_MP_J_ROTOR];
+  o->inv_j = j_total > 0 ? 1.0 / j_total : 0.0;
+  o->omega_lin = j_total / lp[GEMB200_LP_TAU_DECAY];
+  o->omega_lim = j_total > 0 ? lp[GEMB200_LP_A] / j_total * lp[GEMB200_LP_TAU_DECAY] : 0.0;
+
+  // observation right after reset (SCMLSystem.reset physical_systems.py:256-287, :527-561, :659-693, :816-847) for the
+  // constant initial state; converter.reset() gives 0 per QC and -0.5 per B6 leg (converters.py:45-54, :880-886)
+  const double* y = cfg->init_ode;
+  const double U = cfg->u_sup;
+  double* s = o->reset_obs;
+  int n = 0;
+  s[n++] = y[0];
+  switch (dm.fam) {
+    case kDC1: s[n++] = (o->tq[0] + o->tq[1] * y[1]) * y[1]; s[n++] = y[1]; s[n++] = 0.0; break;
+    case kDC2:
+      s[n++] = o->tq[0] * y[1] * y[2]; s[n++] = y[1]; s[n++] = y[2]; s[n++] = 0.0;
+      if (cfg->motor_kind == GEMB200_MOTOR_EXTEX_DC) s[n++] = 0.0;
+      break;
+    default: {
+      double eps = y[dm.nx];
+      if (eps > M_PI) eps -= 2 * M_PI;
+      const double ua = -0.5 * U;
+      // abc -> alpha/beta of (ua,ua,ua) is mathematically 0 (the reference shows ~1e-17 round-off here)
+      const double ualpha = 2.0 / 3.0 * (ua - 0.5 * ua - 0.5 * ua), ubeta = 2.0 / 3.0 * (0.5 * std::sqrt(3.0) * ua - 0.5 * std::sqrt(3.0) * ua);
+      double cs, sn, tqv, ia, ib;
+      if (dm.fam == kSCIM) {
+        const double ef = std::atan2(y[4], y[3]);
+        cs = std::cos(ef); sn = std::sin(ef);
+        tqv = o->tq[0] * (y[3] * y[2] - y[4] * y[1]);
+        ia = y[1]; ib = y[2];
+      } else {
+        cs = std::cos(eps); sn = std::sin(eps);
+        tqv = dm.fam == kSYNC ? (o->tq[0] + o->tq[1] * y[1]) * y[2] : (o->tq[0] * y[3] + o->tq[1] * y[1]) * y[2];
+        ia = cs * y[1] - sn * y[2]; ib = sn * y[1] + cs * y[2];
+      }
+      const double ud = cs * ualpha + sn * ubeta, uq = -sn * ualpha + cs * ubeta;
+      s[n++] = tqv;
+      s[n++] = ia; s[n++] = -0.5 * ia + 0.5 * std::sqrt(3.0) * ib; s[n++] = -0.5 * ia - 0.5 * std::sqrt(3.0) * ib;
+      if (dm.fam == kSCIM) { s[n++] = cs * y[1] + sn * y[2]; s[n++] = -sn * y[1] + cs * y[2]; }
+      else { s[n++] = y[1]; s[n++] = y[2]; }
+      if (dm.fam == kEESM) {
+        // reference quirk (:659-693): u_abc has 4 entries [ua,ub,uc,u_e=0], then u_dq -> the slots named
+        // u_sd,u_sq,u_e receive (0, u_d, u_q)
+        s[n++] = y[3];
+        s[n++] = ua; s[n++] = ua; s[n++] = ua; s[n++] = 0.0; s[n++] = ud; s[n++] = uq;
+      } else {
+        s[n++] = ua; s[n++] = ua; s[n++] = ua; s[n++] = ud; s[n++] = uq;
+      }
+      s[n++] = eps;
+    } break;
+  }
+  s[n++] = U;
+  for (int j = 0; j < n; ++j) s[j] /= cfg->limits[j];
+  if (cfg->motor_kind == GEMB200_MOTOR_SHUNT_DC) s[n] = s[2] + s[3];
+}
+
+template <typename real>
+static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& dv, StepParams<real>* p) {
+  const gemb200_config& c = h->cfg;
+  std::memset(p, 0, sizeof(*p));
+  p->n = c.n_envs;
+  p->env_offset = c.env_index_offset;
+  p->seed_lo = (uint32_t)c.seed; p->seed_hi = (uint32_t)(c.seed >> 32);
+  p->x = static_cast<real*>(h->d_x);
+  p->eps = h->d_eps;
+  p->ref_val = static_cast<real*>(h->d_ref_val);
+  p->ref_sigma = static_cast<real*>(h->d_ref_sigma);
+  p->ref_left = h->d_ref_left;
+  p->sw = h->d_sw;
+  p->motor_kind = c.motor_kind;
+  p->conv_kind[0] = c.converter_kind[0]; p->conv_kind[1] = c.converter_kind[1];
+  p->load_kind = c.load_kind; p->solver_kind = c.solver_kind; p->nsteps = c.solver_nsteps;
+  p->autoreset = c.autoreset;
+  p->two_segment = h->two_segment;
+  p->tau = (real)c.tau; p->til = (real)c.interlocking_time; p->til_over_tau = (real)(c.interlocking_time / c.tau);
+  p->u_sup = (real)c.u_sup;
+  p->pole_pairs = c.motor_param[GEMB200_MP_P];
+  for (int j = 0; j < 20; ++j) p->c[j] = (real)dv.c[j];
+  for (int j = 0; j < 4; ++j) p->tq[j] = (real)dv.tq[j];
+  p->load_a = (real)c.load_param[GEMB200_LP_A]; p->load_b = (real)c.load_param[GEMB200_LP_B]; p->load_c = (real)c.load_param[GEMB200_LP_C];
+  p->inv_j = (real)dv.inv_j; p->omega_lim = (real)dv.omega_lim; p->omega_lin = (real)dv.omega_lin;
+  for (int j = 0; j < dm.n_state; ++j) {
+    p->inv_lim[j] = c.limits[j] != 0.0 ? (real)(1.0 / c.limits[j]) : real(0);
+    p->reset_obs[j] = (real)dv.reset_obs[j];
+  }
+  for (int j = 0; j < dm.nx; ++j) p->init_x[j] = (real)c.init_ode[j];
+  if (dm.has_eps) {
+    double e = c.init_ode[dm.nx];
+    e = e - 2 * M_PI * std::rint(e / (2 * M_PI));
+    if (e <= -M_PI) e += 2 * M_PI;
+    p->init_eps = e;
+  }
+  p->n_constraints = c.n_constraints;
+  for (int i = 0; i < c.n_constraints; ++i) { p->con_kind[i] = c.constraint_kind[i]; p->con_mask[i] = c.constraint_mask[i] & ((1u << dm.n_state) - 1u); }
+  // WeightedSumOfErrors: only non-zero weights become terms (weighted_sum_of_errors.py:128-129)
+  int t = 0;
+  for (int j = 0; j < dm.n_state; ++j) {
+    if (c.reward_weight[j] == 0.0) continue;
+    p->rw_state[t] = j;
+    p->rw_ref[t] = -1;
+    for (int r = 0; r < c.n_ref; ++r) if (c.ref_state[r] == j) p->rw_ref[t] = r;
+    p->rw_w[t] = (real)c.reward_weight[j];
+    p->rw_inv_len[t] = (real)(1.0 / c.state_length[j]);
+    p->rw_pow[t] = (real)c.reward_power[j];
+    p->rw_pow1[t] = c.reward_power[j] == 1.0;
+    ++t;
+  }
+  p->n_rw = t;
+  p->bias = (real)c.reward_bias; p->viol_reward = (real)c.violation_reward;
+  p->n_ref = c.n_ref;
+  p->any_wiener = h->any_wiener;
+  for (int r = 0; r < c.n_ref; ++r) {
+    p->ref_kind[r] = c.ref_kind[r]; p->ref_state[r] = c.ref_state[r];
+    p->ref_const[r] = (real)c.ref_value[r];
+    p->ref_lo[r] = (real)c.ref_margin_lo[r]; p->ref_hi[r] = (real)c.ref_margin_hi[r];
+    p->ref_init_lo[r] = (real)c.ref_init_lo[r]; p->ref_init_span[r] = (real)(c.ref_init_hi[r] - c.ref_init_lo[r]);
+    if (c.ref_kind[r] == GEMB200_REF_WIENER) {
+      p->ref_lsig_lo[r] = (real)std::log10(c.ref_sigma_lo[r]);
+      p->ref_lsig_span[r] = (real)(std::log10(c.ref_sigma_hi[r]) - std::log10(c.ref_sigma_lo[r]));
+    }
+    p->ref_len_lo[r] = c.ref_len_lo[r]; p->ref_len_span[r] = c.ref_len_hi[r] - c.ref_len_lo[r];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kBlock = 256;
+
+template <int FAM, bool FINITE, typename real, int LAYOUT>
+static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
+  const int grid = (p.n + kBlock - 1) / kBlock;
+  const size_t smem = (size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD * sizeof(real);
+  step_kernel<FAM, FINITE, real, LAYOUT><<<grid, kBlock, smem, st>>>(p);
+  return cudaGetLastError();
+}
+template <int FAM, typename real, int LAYOUT>
+static cudaError_t launch_reset_t(const StepParams<real>& p, cudaStream_t st) {
+  const int grid = (p.n + kBlock - 1) / kBlock;
+  reset_kernel<FAM, real, LAYOUT><<<grid, kBlock, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename real>
+static cudaError_t launch_step(int fam, bool finite, int layout, const StepParams<real>& p, cudaStream_t st) {
+#define GEMB200_CASE(F)                                                                                        \
+  case F:                                                                                                      \
+    if (finite) return layout == GEMB200_LAYOUT_AOS ? launch_step_t<F, true, real, GEMB200_LAYOUT_AOS>(p, st)  \
+                                                    : launch_step_t<F, true, real, GEMB200_LAYOUT_SOA>(p, st); \
+    return layout == GEMB200_LAYOUT_AOS ? launch_step_t<F, false, real, GEMB200_LAYOUT_AOS>(p, st)             \
+                                        : launch_step_t<F, false, real, GEMB200_LAYOUT_SOA>(p, st);
+  switch (fam) {
+    GEMB200_CASE(kDC1)
+    GEMB200_CASE(kDC2)
+    GEMB200_CASE(kSYNC)
+    GEMB200_CASE(kEESM)
+    GEMB200_CASE(kSCIM)
+  }
+#undef GEMB200_CASE
+  return cudaErrorInvalidValue;
+}
+template <typename real>
+static cudaError_t launch_reset(int fam, int layout, const StepParams<real>& p, cudaStream_t st) {
+#define GEMB200_CASE(F)                                                                                    \
+  case F:                                                                                                  \
+    return layout == GEMB200_LAYOUT_AOS ? launch_reset_t<F, real, GEMB200_LAYOUT_AOS>(p, st)               \
+                                        : launch_reset_t<F, real, GEMB200_LAYOUT_SOA>(p, st);
+  switch (fam) {
+    GEMB200_CASE(kDC1)
+    GEMB200_CASE(kDC2)
+    GEMB200_CASE(kSYNC)
+    GEMB200_CASE(kEESM)
+    GEMB200_CASE(kSCIM)
+  }
+#undef GEMB200_CASE
+  return cudaErrorInvalidValue;
+}
+
+static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, void* rew, uint8_t* term, cudaStream_t st) {
+  if (!action) return fail(GEMB200_E_INVALID, "action is NULL");
+  h->gstep += 1;
+  cudaError_t e;
+  if (h->cfg.dtype == GEMB200_F32) {
+    StepParams<float>& p = h->pf;
+    p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
+    p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
+    e = launch_step<float>(h->fam, h->cfg.finite != 0, h->cfg.layout, p, st);
+  } else {
+    StepParams<double>& p = h->pd;
+    p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
+    p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
+    e = launch_step<double>(h->fam, h->cfg.finite != 0, h->cfg.layout, p, st);
+  }
+  if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  return GEMB200_OK;
+}
+
+static int do_reset(gemb200_handle* h, const uint8_t* mask, void* obs, void* ref, cudaStream_t st) {
+  h->gstep += 1;
+  cudaError_t e;
+  if (h->cfg.dtype == GEMB200_F32) {
+    StepParams<float>& p = h->pf;
+    p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
+    p.reset_mask = mask; p.obs = (float*)obs; p.ref_out = (float*)ref;
+    e = launch_reset<float>(h->fam, h->cfg.layout, p, st);
+    p.reset_mask = nullptr;
+  } else {
+    StepParams<double>& p = h->pd;
+    p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
+    p.reset_mask = mask; p.obs = (double*)obs; p.ref_out = (double*)ref;
+    e = launch_reset<double>(h->fam, h->cfg.layout, p, st);
+    p.reset_mask = nullptr;
+  }
+  if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string("reset launch: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  return GEMB200_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// C-ABI
+// ----------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gemb200_version(void) { return GEMB200_ABI_VERSION; }
+const char* gemb200_last_error(void) { return g_last_error.c_str(); }
+
+int gemb200_config_init(gemb200_config* cfg) {
+  if (!cfg) return fail(GEMB200_E_INVALID, "config is NULL");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = (int32_t)sizeof(gemb200_config);
+  cfg->abi_version = GEMB200_ABI_VERSION;
+  cfg->n_envs = 1;
+  cfg->solver_kind = GEMB200_SOLVER_RK4;
+  cfg->solver_nsteps = 1;
+  cfg->tau = 1e-4;
+  cfg->load_param[GEMB200_LP_TAU_DECAY] = 1e-3;
+  for (int i = 0; i < GEMB200_MAX_STATE; ++i) { cfg->limits[i] = 1.0; cfg->state_length[i] = 2.0; cfg->reward_power[i] = 1.0; }
+  for (int r = 0; r < GEMB200_MAX_REF; ++r) {
+    cfg->ref_len_lo[r] = 500; cfg->ref_len_hi[r] = 2000;
+    cfg->ref_sigma_lo[r] = 1e-3; cfg->ref_sigma_hi[r] = 1e-1;
+    cfg->ref_margin_lo[r] = -1; cfg->ref_margin_hi[r] = 1; cfg->ref_init_lo[r] = -1; cfg->ref_init_hi[r] = 1;
+  }
+  return GEMB200_OK;
+}
+
+int gemb200_query_dims(const gemb200_config* cfg, int32_t* n_state, int32_t* n_ode, int32_t* n_act, int32_t* n_ref) {
+  if (!cfg) return fail(GEMB200_E_INVALID, "config is NULL");
+  Dims d;
+  int rc = derive_dims(cfg, &d);
+  if (rc) return rc;
+  if (n_state) *n_state = d.n_state;
+  if (n_ode) *n_ode = d.n_ode;
+  if (n_act) *n_act = d.n_act;
+  if (n_ref) *n_ref = cfg->n_ref;
+  return GEMB200_OK;
+}
+
+int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
+  if (!out) return fail(GEMB200_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(GEMB200_E_INVALID, "device ordinal out of range");
+  DeviceGuard guard(cfg->device);
+  gemb200_handle* h = new (std::nothrow) gemb200_handle();
+  if (!h) return fail(GEMB200_E_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  Dims d;
+  derive_dims(cfg, &d);
+  h->fam = d.fam; h->n_state = d.n_state; h->n_ode = d.n_ode; h->n_act = d.n_act; h->nx = d.nx; h->has_eps = d.has_eps;
+  h->n_ref = cfg->n_ref;
+  h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
+  h->two_segment = cfg->finite && cfg->interlocking_time > 0;
+  for (int r = 0; r < cfg->n_ref; ++r) h->any_wiener = h->any_wiener || cfg->ref_kind[r] == GEMB200_REF_WIENER;
+  const size_t n = (size_t)cfg->n_envs;
+#define ALLOC(ptr, bytes)                                                                                     \
+  do {                                                                                                        \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                                     \
+    if (e_ != cudaSuccess) { gemb200_destroy(h); return fail(e_ == cudaErrorMemoryAllocation ? GEMB200_E_NOMEM : GEMB200_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); } \
+    cudaMemset((ptr), 0, (bytes));                                                                            \
+  } while (0)
+  ALLOC(h->d_x, n * d.nx * h->rsz);
+  if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
+  if (cfg->n_ref > 0) {
+    ALLOC(h->d_ref_val, n * cfg->n_ref * h->rsz);
+    if (h->any_wiener) { ALLOC(h->d_ref_sigma, n * cfg->n_ref * h->rsz); ALLOC(h->d_ref_left, n * cfg->n_ref * sizeof(int32_t)); }
+  }
+  if (h->two_segment) ALLOC(h->d_sw, n * sizeof(uint16_t));
+#undef ALLOC
+  Derived dv;
+  derive_model(cfg, d, &dv);
+  fill_params<float>(h, d, dv, &h->pf);
+  fill_params<double>(h, d, dv, &h->pd);
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  rc = do_reset(h, nullptr, nullptr, nullptr, nullptr);
+  if (rc) { gemb200_destroy(h); return rc; }
+  cudaError_t e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) { gemb200_destroy(h); return fail(GEMB200_E_CUDA, std::string("initial reset: ") + cudaGetErrorString(e)); }
+  *out = h;
+  return GEMB200_OK;
+}
+
+int gemb200_destroy(gemb200_handle* h) {
+  if (!h) return GEMB200_OK;
+  DeviceGuard guard(h->cfg.device);
+  cudaFree(h->d_x); cudaFree(h->d_eps); cudaFree(h->d_ref_val); cudaFree(h->d_ref_sigma); cudaFree(h->d_ref_left); cudaFree(h->d_sw);
+  cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
+  if (h->hstream) cudaStreamDestroy(h->hstream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return GEMB200_OK;
+}
+
+int gemb200_reset(gemb200_handle* h, const uint8_t* reset_mask, void* obs_out, void* ref_out, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  return do_reset(h, reset_mask, obs_out, ref_out, (cudaStream_t)stream);
+}
+
+int gemb200_step(gemb200_handle* h, const void* action, void* obs_out, void* ref_out, void* reward_out, uint8_t* terminated_out, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  return do_step(h, action, obs_out, ref_out, reward_out, terminated_out, (cudaStream_t)stream);
+}
+
+int gemb200_rollout(gemb200_handle* h, const void* actions, int32_t n_steps, void* obs_out, void* ref_out, void* reward_out,
+                    uint8_t* terminated_out, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  if (n_steps < 1) return fail(GEMB200_E_INVALID, "n_steps must be >= 1");
+  DeviceGuard guard(h->cfg.device);
+  const size_t asz = (size_t)h->cfg.n_envs * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz);
+  for (int k = 0; k < n_steps; ++k) {
+    const bool last = k == n_steps - 1;
+    int rc = do_step(h, (const char*)actions + asz * k, last ? obs_out : nullptr, last ? ref_out : nullptr, last ? reward_out : nullptr,
+                     last ? terminated_out : nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return GEMB200_OK;
+}
+
+static int ensure_host_buffers(gemb200_handle* h) {
+  if (h->hstream) return GEMB200_OK;
+  const size_t n = (size_t)h->cfg.n_envs;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&h->d_act, n * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz)));
+  CUDA_TRY(cudaMalloc(&h->d_obs, n * h->n_state * h->rsz));
+  CUDA_TRY(cudaMalloc(&h->d_ref, n * (h->n_ref > 0 ? h->n_ref : 1) * h->rsz));
+  CUDA_TRY(cudaMalloc(&h->d_rew, n * h->rsz));
+  CUDA_TRY(cudaMalloc((void**)&h->d_term, n));
+  CUDA_TRY(cudaMalloc((void**)&h->d_mask, n));
+  return GEMB200_OK;
+}
+
+int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void* ref_out, void* reward_out, uint8_t* terminated_out) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  if (!action) return fail(GEMB200_E_INVALID, "action is NULL");
+  DeviceGuard guard(h->cfg.device);
+  int rc = ensure_host_buffers(h);
+  if (rc) return rc;
+  const size_t n = (size_t)h->cfg.n_envs;
+  cudaStream_t st = h->hstream;
+  CUDA_TRY(cudaMemcpyAsync(h->d_act, action, n * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz), cudaMemcpyHostToDevice, st));
+  rc = do_step(h, h->d_act, obs_out ? h->d_obs : nullptr, (ref_out && h->n_ref) ? h->d_ref : nullptr, reward_out ? h->d_rew : nullptr,
+               terminated_out ? h->d_term : nullptr, st);
+  if (rc) return rc;
+  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_state * h->rsz, cudaMemcpyDeviceToHost, st));
+  if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(ref_out, h->d_ref, n * h->n_ref * h->rsz, cudaMemcpyDeviceToHost, st));
+  if (reward_out) CUDA_TRY(cudaMemcpyAsync(reward_out, h->d_rew, n * h->rsz, cudaMemcpyDeviceToHost, st));
+  if (terminated_out) CUDA_TRY(cudaMemcpyAsync(terminated_out, h->d_term, n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return GEMB200_OK;
+}
+
+int gemb200_reset_host(gemb200_handle* h, const uint8_t* reset_mask, void* obs_out, void* ref_out) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  int rc = ensure_host_buffers(h);
+  if (rc) return rc;
+  const size_t n = (size_t)h->cfg.n_envs;
+  cudaStream_t st = h->hstream;
+  if (reset_mask) CUDA_TRY(cudaMemcpyAsync(h->d_mask, reset_mask, n, cudaMemcpyHostToDevice, st));
+  if (reset_mask && (obs_out || ref_out)) {
+    // unmasked envs keep the caller's previous values: pre-load the device staging buffers with them
+    if (obs_out) CUDA_TRY(cudaMemcpyAsync(h->d_obs, obs_out, n * h->n_state * h->rsz, cudaMemcpyHostToDevice, st));
+    if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(h->d_ref, ref_out, n * h->n_ref * h->rsz, cudaMemcpyHostToDevice, st));
+  }
+  rc = do_reset(h, reset_mask ? h->d_mask : nullptr, obs_out ? h->d_obs : nullptr, (ref_out && h->n_ref) ? h->d_ref : nullptr, st);
+  if (rc) return rc;
+  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_state * h->rsz, cudaMemcpyDeviceToHost, st));
+  if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(ref_out, h->d_ref, n * h->n_ref * h->rsz, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return GEMB200_OK;
+}
+
+int gemb200_get_ode_state(gemb200_handle* h, double* ode_out, void* stream) {
+  if (!h || !ode_out) return fail(GEMB200_E_INVALID, "NULL argument");
+  DeviceGuard guard(h->cfg.device);
+  const int n = h->cfg.n_envs, grid = (n + 255) / 256;
+  if (h->cfg.dtype == GEMB200_F32) get_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_x, h->d_eps, ode_out, n, h->nx, h->has_eps);
+  else get_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_x, h->d_eps, ode_out, n, h->nx, h->has_eps);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GEMB200_OK;
+}
+int gemb200_set_ode_state(gemb200_handle* h, const double* ode_in, void* stream) {
+  if (!h || !ode_in) return fail(GEMB200_E_INVALID, "NULL argument");
+  DeviceGuard guard(h->cfg.device);
+  const int n = h->cfg.n_envs, grid = (n + 255) / 256;
+  if (h->cfg.dtype == GEMB200_F32) set_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_x, h->d_eps, ode_in, n, h->nx, h->has_eps);
+  else set_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_x, h->d_eps, ode_in, n, h->nx, h->has_eps);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GEMB200_OK;
+}
+int gemb200_get_reference(gemb200_handle* h, double* ref_out, void* stream) {
+  if (!h || !ref_out) return fail(GEMB200_E_INVALID, "NULL argument");
+  if (h->n_ref == 0) return GEMB200_OK;
+  DeviceGuard guard(h->cfg.device);
+  const int n = h->cfg.n_envs, grid = (n + 255) / 256;
+  if (h->cfg.dtype == GEMB200_F32) get_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_ref_val, ref_out, n, h->n_ref);
+  else get_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_ref_val, ref_out, n, h->n_ref);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GEMB200_OK;
+}
+int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream) {
+  if (!h || !ref_in) return fail(GEMB200_E_INVALID, "NULL argument");
+  if (h->n_ref == 0) return GEMB200_OK;
+  DeviceGuard guard(h->cfg.device);
+  const int n = h->cfg.n_envs, grid = (n + 255) / 256;
+  if (h->cfg.dtype == GEMB200_F32) set_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_ref_val, ref_in, n, h->n_ref);
+  else set_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_ref_val, ref_in, n, h->n_ref);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GEMB200_OK;
+}
+
+// checkpoint blob: [gstep u64][x][eps][ref_val][ref_sigma][ref_left][sw]
+struct Section { void* ptr; size_t bytes; };
+static int sections(gemb200_handle* h, Section* s) {
+  const size_t n = (size_t)h->cfg.n_envs;
+  int k = 0;
+  s[k++] = {h->d_x, n * h->nx * h->rsz};
+  if (h->d_eps) s[k++] = {h->d_eps, n * sizeof(double)};
+  if (h->d_ref_val) s[k++] = {h->d_ref_val, n * h->n_ref * h->rsz};
+  if (h->d_ref_sigma) s[k++] = {h->d_ref_sigma, n * h->n_ref * h->rsz};
+  if (h->d_ref_left) s[k++] = {h->d_ref_left, n * h->n_ref * sizeof(int32_t)};
+  if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
+  return k;
+}
+int64_t gemb200_checkpoint_size(gemb200_handle* h) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  Section s[8];
+  const int k = sections(h, s);
+  int64_t total = 8;
+  for (int i = 0; i < k; ++i) total += (int64_t)s[i].bytes;
+  return total;
+}
+int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
+  if (!h || !host_blob) return fail(GEMB200_E_INVALID, "NULL argument");
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  char* b = (char*)host_blob;
+  std::memcpy(b, &h->gstep, 8); b += 8;
+  Section s[8];
+  const int k = sections(h, s);
+  for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(b, s[i].ptr, s[i].bytes, cudaMemcpyDeviceToHost)); b += s[i].bytes; }
+  return GEMB200_OK;
+}
+int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob) {
+  if (!h || !host_blob) return fail(GEMB200_E_INVALID, "NULL argument");
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  const char* b = (const char*)host_blob;
+  std::memcpy(&h->gstep, b, 8); b += 8;
+  Section s[8];
+  const int k = sections(h, s);
+  for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(s[i].ptr, b, s[i].bytes, cudaMemcpyHostToDevice)); b += s[i].bytes; }
+  return GEMB200_OK;
+}
+
+int64_t gemb200_launch_count(gemb200_handle* h) { return h ? h->launches : 0; }
+int gemb200_kernel_time_begin(gemb200_handle* h, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(cudaEventRecord(h->ev0, (cudaStream_t)stream));
+  return GEMB200_OK;
+}
+int gemb200_kernel_time_end(gemb200_handle* h, void* stream, float* ms_out) {
+  if (!h || !ms_out) return fail(GEMB200_E_INVALID, "NULL argument");
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(cudaEventRecord(h->ev1, (cudaStream_t)stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+  return GEMB200_OK;
+}
+
+}  // extern "C"

@@ -51,8 +51,6 @@ typedef struct {
   double ref_value[GEMB200_MAX_REF];
   double ref_sigma[GEMB200_MAX_REF];
   int ref_left[GEMB200_MAX_REF];
-  uint32_t episode; /* reset counter: part of the RNG counter */
-  uint32_t step;    /* steps since reset */
 } env_t;
 
 typedef struct gem_oracle {
@@ -66,8 +64,16 @@ typedef struct gem_oracle {
   /* derived EESM constants (externally_excited_synchronous_motor.py:129-136) */
   double l_M, i_k_rs;
   double tq0; /* SCIM torque factor */
+  uint64_t gstep; /* id of the current API call (RNG counter) */
   env_t* env;
 } gem_oracle;
+
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1);
+static void rng4(const gem_oracle* o, int64_t env, uint32_t stream, uint32_t out[4]) {
+  uint64_t g = (uint64_t)(env + o->cfg.env_index_offset);
+  out[0] = (uint32_t)o->gstep; out[1] = (uint32_t)(o->gstep >> 32); out[2] = (uint32_t)g; out[3] = ((uint32_t)(g >> 32) << 8) | stream;
+  philox4x32_10(out, (uint32_t)o->cfg.seed, (uint32_t)(o->cfg.seed >> 32));
+}
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al., SC'11) — the published counter-based generator; the CUDA path uses the same    */
@@ -88,14 +94,13 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 }
 static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); } /* (0,1) */
 
-/* stream ids for the counter word 3 */
-enum { STREAM_REF_WALK = 1, STREAM_REF_SUBEP = 2, STREAM_REF_INIT = 3 };
+/* Counter = (id of the API call lo, hi, global env index lo, (hi << 8) | stream id); key = seed.  Every reset/step
+ * call of a handle gets a fresh call id, so no per-env RNG state exists.  Stream ids: */
+enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
+       STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */ };
 
-static void rng4(const gem_oracle* o, int64_t env, uint32_t episode, uint32_t step, uint32_t stream, uint32_t out[4]) {
-  uint64_t g = (uint64_t)(env + o->cfg.env_index_offset);
-  out[0] = step; out[1] = episode; out[2] = (uint32_t)g; out[3] = ((uint32_t)(g >> 32) << 8) | stream;
-  philox4x32_10(out, (uint32_t)o->cfg.seed, (uint32_t)(o->cfg.seed >> 32));
-}
+struct gem_oracle;
+static void rng4(const struct gem_oracle* o, int64_t env, uint32_t stream, uint32_t out[4]);
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* dimensions — SCMLSystem._set_indices physical_systems.py:141-162, :462-485, :594-617, :737-763               */
@@ -785,24 +790,28 @@ static double reward(const gem_oracle* o, const double* s, const double* ref_ful
 
 /* SubepisodedReferenceGenerator.get_reference_observation :93-100 + WienerProcess._reset_reference :30-41, one value
  * per call instead of a pre-computed sub-episode (same distribution; RNG stream differs from numpy, see header) */
-static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx) {
+static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_reset) {
   const gemb200_config* c = &o->cfg;
-  uint32_t rw[4], rs[4];
-  int have_w = 0, have_s = 0;
+  uint32_t rw[4], rs[4], rs2[4];
+  int have_w = 0, have_s = 0, have_s2 = 0;
   for (int r = 0; r < c->n_ref; ++r) {
     if (c->ref_kind[r] != GEMB200_REF_WIENER) continue;
     if (e->ref_left[r] <= 0) {
-      if (!have_s) { rng4(o, idx, e->episode, e->step, STREAM_REF_SUBEP, rs); have_s = 1; }
       /* two uniforms per slot: slots 0,1 share one Philox block, slots 2,3 a second one */
-      uint32_t blk[4];
-      if (r < 2) memcpy(blk, rs, sizeof(blk));
-      else { rng4(o, idx, e->episode, e->step, STREAM_REF_SUBEP + 16, blk); }
-      double ul = u01(blk[2 * (r & 1)]), us = u01(blk[2 * (r & 1) + 1]);
-      e->ref_left[r] = (int)((c->ref_len_hi[r] - c->ref_len_lo[r]) * ul + c->ref_len_lo[r]); /* int(U(lo,hi)) :37,:115-119 */
+      uint32_t a, b;
+      if (r < 2) {
+        if (!have_s) { rng4(o, idx, after_reset ? STREAM_SUBEP_R : STREAM_SUBEP, rs); have_s = 1; }
+        a = rs[2 * (r & 1)]; b = rs[2 * (r & 1) + 1];
+      } else {
+        if (!have_s2) { rng4(o, idx, after_reset ? STREAM_SUBEP_HI_R : STREAM_SUBEP_HI, rs2); have_s2 = 1; }
+        a = rs2[2 * (r & 1)]; b = rs2[2 * (r & 1) + 1];
+      }
+      /* int(U[0,1)*(hi-lo) + lo) subepisoded_reference_generator.py:37,:115-119 with U = a / 2^32 */
+      e->ref_left[r] = (int)((double)(c->ref_len_hi[r] - c->ref_len_lo[r]) * ((double)a / 4294967296.0) + c->ref_len_lo[r]);
       double l0 = log10(c->ref_sigma_lo[r]), l1 = log10(c->ref_sigma_hi[r]);
-      e->ref_sigma[r] = pow(10.0, (l1 - l0) * us + l0); /* wiener_process_reference_generator.py:31 */
+      e->ref_sigma[r] = pow(10.0, (l1 - l0) * u01(b) + l0); /* wiener_process_reference_generator.py:31 */
     }
-    if (!have_w) { rng4(o, idx, e->episode, e->step, STREAM_REF_WALK, rw); have_w = 1; }
+    if (!have_w) { rng4(o, idx, after_reset ? STREAM_WALK_R : STREAM_WALK, rw); have_w = 1; }
     /* Box-Muller: slots (0,1) from words (0,1), slots (2,3) from words (2,3) */
     double u1 = u01(rw[2 * (r >> 1)]), u2 = u01(rw[2 * (r >> 1) + 1]);
     double rad = sqrt(-2.0 * log(u1));
@@ -819,7 +828,7 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx) {
 static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
   const gemb200_config* c = &o->cfg;
   uint32_t ri[4];
-  rng4(o, idx, e->episode, 0, STREAM_REF_INIT, ri);
+  rng4(o, idx, STREAM_INIT, ri);
   for (int r = 0; r < c->n_ref; ++r) {
     if (c->ref_kind[r] == GEMB200_REF_WIENER) {
       e->ref_value[r] = c->ref_init_lo[r] + (c->ref_init_hi[r] - c->ref_init_lo[r]) * u01(ri[r]);
@@ -829,7 +838,7 @@ static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
       e->ref_value[r] = c->ref_value[r];
     }
   }
-  ref_advance(o, e, idx); /* reset() returns get_reference_observation() :82-91 via core.py:499-503 */
+  ref_advance(o, e, idx, 1); /* reset() returns get_reference_observation() :82-91 via core.py:499-503 */
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -853,11 +862,10 @@ void gem_oracle_dims(const gem_oracle* o, int32_t* n_state, int32_t* n_ode, int3
 /* env.reset (core.py:300-319). mask NULL = all. obs [N][n_state], ref_next [N][n_ref] (may be NULL). */
 void gem_oracle_reset(gem_oracle* o, const uint8_t* mask, double* obs, double* ref_next) {
   double st[GEMB200_MAX_STATE];
+  o->gstep += 1;
   for (int64_t i = 0; i < o->cfg.n_envs; ++i) {
     if (mask && !mask[i]) continue;
     env_t* e = o->env + i;
-    e->episode += 1;
-    e->step = 0;
     ps_reset(o, e, st);
     ref_reset(o, e, i);
     if (obs) memcpy(obs + i * o->n_state, st, sizeof(double) * o->n_state);
@@ -876,11 +884,8 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
   double v = check_constraints(o, st);                          /* core.py:348 */
   double rw = reward(o, st, ref_full, v);                        /* core.py:349 */
   int terminated = v >= 1.0;                                    /* core.py:350 */
-  e->step += 1;
-  ref_advance(o, e, i);                                         /* core.py:351 */
+  ref_advance(o, e, i, 0);                                      /* core.py:351 */
   if (terminated && o->cfg.autoreset == GEMB200_AUTORESET_SAME_STEP) {
-    e->episode += 1;
-    e->step = 0;
     ps_reset(o, e, st);
     ref_reset(o, e, i);
   }
@@ -901,6 +906,7 @@ static void* step_range(void* arg) {
 }
 void gem_oracle_step(gem_oracle* o, const void* action, double* obs, double* ref_next, double* rew, uint8_t* term, int nthreads) {
   int64_t n = o->cfg.n_envs;
+  o->gstep += 1;
   if (nthreads > n) nthreads = (int)n;
   if (nthreads <= 1) {
     job_t j = {o, action, obs, ref_next, rew, term, 0, n};

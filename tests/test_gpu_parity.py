@@ -1,0 +1,259 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path, called through the C-ABI, against
+ (1) the golden trajectories recorded from the unmodified reference, and
+ (2) the float64 CPU oracle on many envs with random actions, auto-reset and the Wiener reference generator.
+
+Tolerances: float64 build 1e-9 column-relative (algorithm-identical to the oracle); float32 build 1e-5
+column-relative — the bar BASELINE.json's north_star sets for state trajectories.
+"""
+import numpy as np
+import pytest
+
+from helpers import col_rel_err, config_from_meta, golden_names, load_golden, replay_golden
+from gym_electric_motor_b200 import _cabi as K
+
+pytestmark = pytest.mark.gpu
+
+TOL = {K.F64: 1e-9, K.F32: 1e-5}
+# dopri5 goldens are compared against RK4 with 2 sub-steps: accuracy of the substitute solver, not identity
+TOL_DOPRI = {K.F64: 2e-6, K.F32: 1e-5}
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    return torch
+
+
+class DeviceAdapter:
+    """Gives VectorSim the numpy reset/step/set_reference API that helpers.replay_golden drives."""
+
+    def __init__(self, cfg):
+        from gym_electric_motor_b200.vector_sim import VectorSim
+
+        self.sim = VectorSim(cfg)
+
+    def reset(self, mask=None):
+        obs, ref = self.sim.reset(mask)
+        return obs.double().cpu().numpy(), ref.double().cpu().numpy()
+
+    def step(self, action):
+        obs, ref, rew, term = self.sim.step(np.asarray(action))
+        return obs.double().cpu().numpy(), ref.double().cpu().numpy(), rew.double().cpu().numpy(), term.cpu().numpy()
+
+    def set_reference(self, r):
+        self.sim.set_reference(r)
+
+
+def _golden_cases():
+    out = []
+    for name in golden_names():
+        for dt in (K.F64, K.F32):
+            out.append(pytest.param(name, dt, id=f"{name}-{'f64' if dt == K.F64 else 'f32'}"))
+    return out
+
+
+@pytest.mark.parametrize("name,dtype", _golden_cases())
+def test_device_reproduces_reference_trajectory(torch_cuda, name, dtype):
+    g = load_golden(name)
+    solver = g["meta"]["case"]["solver"]
+    is_dopri = solver == "dopri5"
+    if is_dopri and name == "pmsm_fin_sc_dopri5":
+        pytest.skip("the reference's default dopri5 silently drops steps here (scipy 'step size too small'); "
+                    "only the oracle restates that pathology, see DESIGN.md")
+    cfg = config_from_meta(g["meta"], reset_ode=g["reset_ode"], dtype=dtype, solver="rk4x2" if is_dopri else solver)
+    sim = DeviceAdapter(cfg)
+    out = replay_golden(sim, g)
+    tol = (TOL_DOPRI if is_dopri else TOL)[dtype]
+    assert np.abs(out["reset_state"] - g["reset_state"]).max() < 1e-6
+    err = col_rel_err(out["states"], g["states"])
+    assert err < tol, f"{name}: column-relative state error {err:.3e}"
+    # terminations / rewards: identical unless a constraint sits within rounding of its threshold
+    mism = np.nonzero(out["terminated"] != g["terminated"])[0]
+    assert len(mism) == 0, f"termination mismatch at steps {mism[:5]}"
+    assert np.abs(out["rewards"] - g["rewards"]).max() < 10 * tol
+
+
+BATCH_CASES = [
+    ("pmsm_cc_rk4", "rk4"), ("pmsm_cc_euler3", "euler3"), ("pmsm_sc_polyload_rk4", "rk4"), ("pmsm_fin_sc_rk4_interlock", "rk4"),
+    ("synrm_cc_rk4", "rk4x2"), ("eesm_cc_rk4", "rk4"), ("eesm_fin_cc_rk4", "rk4"), ("scim_cc_rk4", "rk4"),
+    ("scim_fin_cc_interlock_rk4", "rk4"), ("permex_cc_euler_10k", "euler"), ("permex_fin4qc_interlock_rk4", "rk4"),
+    ("series_cc_rk4", "rk4"), ("shunt_cc_rk4", "rk4"), ("extex_cc_rk4", "rk4"),
+]
+
+
+def _random_actions(rng, g, n, steps):
+    a = g["actions"]
+    if a.ndim == 1:
+        hi = int(a.max()) + 1
+        return rng.integers(0, max(hi, 2), size=(steps, n, 1)).astype(np.int32)
+    if a.dtype.kind == "i":
+        hi = a.max(axis=0) + 1
+        return (rng.random((steps, n, a.shape[1])) * hi).astype(np.int32)
+    # smooth-ish random actions so that currents build up and constraints trigger
+    base = rng.uniform(-1, 1, size=(steps, n, a.shape[1]))
+    hold = rng.uniform(-1, 1, size=(1, n, a.shape[1]))
+    lo, hi = a.min(), a.max()
+    out = 0.5 * base + 0.5 * hold
+    if lo >= 0:
+        out = np.abs(out)
+    return out
+
+
+@pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("name,solver", BATCH_CASES)
+def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dtype):
+    """N envs, random actions, Wiener references (same Philox streams on both sides), in-kernel auto-reset."""
+    g = load_golden(name)
+    n, steps = 1000, 150  # n deliberately not a multiple of the warp / block size
+    rng = np.random.default_rng(42)
+    actions = _random_actions(rng, g, n, steps)
+
+    def mk(dt):
+        cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=dt, solver=solver, ref_kind=K.REF_WIENER,
+                               autoreset=K.AUTORESET_SAME_STEP, seed=1234)
+        for r in range(cfg.n_ref):
+            cfg.ref_margin_lo[r], cfg.ref_margin_hi[r] = -0.7, 0.7
+            cfg.ref_init_lo[r], cfg.ref_init_hi[r] = -0.7, 0.7
+            cfg.ref_len_lo[r], cfg.ref_len_hi[r] = 5, 40  # many sub-episode changes inside the test
+        cfg.env_index_offset = 7 * n
+        return cfg
+
+    dev = DeviceAdapter(mk(dtype))
+    ora = oracle_lib.Oracle(mk(K.F64), nthreads=8)
+    o_obs, o_ref = ora.reset()
+    d_obs, d_ref = dev.reset()
+    tol = TOL[dtype]
+    assert np.abs(d_obs - o_obs).max() < 1e-6
+    assert np.abs(d_ref - o_ref).max() < max(tol, 1e-12) * 10
+    alive = np.ones(n, dtype=bool)  # envs whose device/oracle episodes are still aligned
+    scale = np.maximum(np.abs(o_obs).max(axis=0), 1e-3)
+    n_term = 0
+    for k in range(steps):
+        o_obs, o_ref, o_rew, o_term = ora.step(actions[k])
+        d_obs, d_ref, d_rew, d_term = dev.step(actions[k])
+        split = alive & (o_term != d_term)
+        alive &= ~split  # a constraint within rounding of its threshold: episodes diverge from here on
+        scale = np.maximum(scale, np.abs(o_obs[alive]).max(axis=0))
+        err = (np.abs(d_obs - o_obs)[alive] / scale).max()
+        assert err < tol, f"step {k}: state error {err:.3e}"
+        assert np.abs(d_ref - o_ref)[alive].max() < 20 * tol if d_ref.size else True
+        assert np.abs(d_rew - o_rew)[alive].max() < 20 * tol
+        n_term += int(o_term[alive].sum())
+    assert alive.mean() > 0.995, f"too many diverged envs: {n - alive.sum()}"
+    if name not in ("series_cc_rk4",):
+        assert n_term > 0, "test is meant to exercise termination + auto-reset"
+
+
+def _cfg(name, n, dtype=K.F32, **kw):
+    g = load_golden(name)
+    return g, config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=dtype, solver="rk4", ref_kind=K.REF_WIENER,
+                               autoreset=K.AUTORESET_SAME_STEP, seed=3, **kw)
+
+
+@pytest.mark.parametrize("name", ["pmsm_cc_rk4", "eesm_cc_rk4", "permex_cc_rk4", "extex_cc_rk4", "scim_fin_sc_rk4"])
+@pytest.mark.parametrize("n", [1, 31, 33, 257, 4096 + 5])
+def test_layouts_and_host_path_agree_bitwise(torch_cuda, name, n):
+    """row-per-env (AoS, smem transpose + vector stores) vs field-major (SoA) vs the host-buffer entry point."""
+    import torch
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    g, cfg_a = _cfg(name, n, layout=K.LAYOUT_AOS)
+    _, cfg_s = _cfg(name, n, layout=K.LAYOUT_SOA)
+    _, cfg_h = _cfg(name, n, layout=K.LAYOUT_AOS)
+    sa, ss, sh = VectorSim(cfg_a), VectorSim(cfg_s), VectorSim(cfg_h)
+    rng = np.random.default_rng(0)
+    steps = 20
+    acts = _random_actions(rng, g, n, steps)
+    ra, rs, rh = sa.reset(), ss.reset(), sh.reset_host()
+    assert torch.equal(ra[0], rs[0].T) and torch.equal(ra[1], rs[1].T)
+    assert np.array_equal(ra[0].cpu().numpy(), rh[0])
+    for k in range(steps):
+        a = acts[k]
+        oa = sa.step(a)
+        os_ = ss.step(np.ascontiguousarray(a.T) if not sa.finite else np.ascontiguousarray(a.reshape(n, -1).T))
+        oh = sh.step_host(a)
+        assert torch.equal(oa[0], os_[0].T) and torch.equal(oa[1], os_[1].T)
+        assert torch.equal(oa[2], os_[2]) and torch.equal(oa[3], os_[3])
+        for x, y in zip(oa, oh):
+            assert np.array_equal(x.cpu().numpy(), y)
+
+
+def test_checkpoint_roundtrip(torch_cuda):
+    import torch
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    g, cfg = _cfg("pmsm_fin_sc_rk4_interlock", 513)
+    sim = VectorSim(cfg, reuse_outputs=False)
+    rng = np.random.default_rng(1)
+    acts = _random_actions(rng, g, 513, 30)
+    sim.reset()
+    for k in range(10):
+        sim.step(acts[k])
+    sd = sim.state_dict()
+    a = [sim.step(acts[k]) for k in range(10, 30)]
+    sim.load_state_dict(sd)
+    b = [sim.step(acts[k]) for k in range(10, 30)]
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v)
+
+
+def test_masked_reset_and_get_set_state(torch_cuda):
+    import torch
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    g = load_golden("pmsm_cc_rk4")
+    n = 300
+    cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=K.F32, solver="rk4", ref_kind=K.REF_CONST)
+    sim = VectorSim(cfg, reuse_outputs=False)
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        sim.step(rng.uniform(-1, 1, size=(n, 3)))
+    y = sim.get_ode_state()
+    assert (y[:, 1:3].abs().sum(dim=1) > 0).all()
+    mask = torch.zeros(n, dtype=torch.uint8)
+    mask[::3] = 1
+    sim.reset(mask)
+    y2 = sim.get_ode_state()
+    m = mask.bool().cuda()
+    assert torch.equal(y2[~m], y[~m])
+    assert (y2[m][:, 1:] == 0).all() and torch.allclose(y2[m][:, 0], torch.full_like(y2[m][:, 0], float(g["reset_ode"][0])))
+    y3 = y.clone()
+    y3[:, 3] = y3[:, 3] + 4 * np.pi  # angle is stored wrapped
+    sim.set_ode_state(y3)
+    assert torch.allclose(sim.get_ode_state(), y, atol=1e-6)
+
+
+def test_full_size_replication_property(torch_cuda, oracle_lib):
+    """BASELINE size (N = 2^20, Cont-CC-PMSM-v0, RK4): 1024 distinct action streams, each replicated 1024 times across the
+    grid.  Size-independent properties: every replica is bit-identical to its prototype (no indexing/tail/layout
+    error anywhere in the 4096-block grid) and the prototypes match the CPU oracle."""
+    import torch
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    g = load_golden("pmsm_cc_rk4")
+    n, proto, steps = 1 << 20, 1024, 25
+    cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=K.F32, solver="rk4", ref_kind=K.REF_CONST)
+    cfg_o = config_from_meta(g["meta"], n_envs=proto, reset_ode=g["reset_ode"], dtype=K.F64, solver="rk4", ref_kind=K.REF_CONST)
+    for c in (cfg, cfg_o):
+        for r in range(c.n_ref):
+            c.ref_value[r] = 0.1 * (r + 1)
+    sim = VectorSim(cfg)
+    ora = oracle_lib.Oracle(cfg_o, nthreads=8)
+    sim.reset()
+    ora.reset()
+    rng = np.random.default_rng(9)
+    for k in range(steps):
+        a = rng.uniform(-1, 1, size=(proto, 3))
+        a_dev = torch.as_tensor(a, dtype=torch.float32, device="cuda").repeat(n // proto, 1)
+        obs, ref, rew, term = sim.step(a_dev)
+        o_obs, _, o_rew, o_term = ora.step(a)
+        v = obs.view(n // proto, proto, -1)
+        assert torch.equal(v, v[0:1].expand_as(v))
+        assert torch.equal(rew.view(-1, proto), rew[:proto].expand(n // proto, proto))
+        d = obs[:proto].double().cpu().numpy()
+        assert col_rel_err(d, o_obs) < 1e-5 or np.abs(d - o_obs).max() < 1e-6
+        assert np.abs(rew[:proto].double().cpu().numpy() - o_rew).max() < 1e-4
