@@ -1,0 +1,241 @@
+"""Batched `ElectricMotorEnvironment` — the drop-in for reference core.py:53-392.
+
+`reset()` / `step()` keep the reference's return structure
+    reset -> ((state, reference_observation), info)
+    step  -> ((state, reference_observation), reward, terminated, truncated, info)
+with a leading env dimension N on every array (torch tensors on the CUDA device).  With `num_envs=None` the
+environment runs ONE env and converts to the reference's scalar contract (numpy vectors, float reward, bool
+terminated, assertion on stepping a terminated env, core.py:341).
+
+The whole step — physical system, reference lookup, constraint check, reward, next reference — is one CUDA launch
+through the C-ABI (include/gemb200.h: gemb200_step); see DESIGN.md.
+"""
+import numpy as np
+
+from . import _cabi as K
+from .constraints import Constraint, ConstraintMonitor
+from .reference_generators import ReferenceGenerator
+from .reward_functions import RewardFunction
+from .spaces import Box, Tuple
+
+
+class Callback:
+    """reference core.py:708-740 (hooks receive batched tensors)"""
+
+    _env = None
+
+    def set_env(self, env):
+        self._env = env
+
+    def on_reset_begin(self):
+        pass
+
+    def on_reset_end(self, state, reference):
+        pass
+
+    def on_step_begin(self, k, action):
+        pass
+
+    def on_step_end(self, k, state, reference, reward, terminated):
+        pass
+
+    def on_close(self):
+        pass
+
+
+class ElectricMotorVisualization(Callback):
+    """reference core.py:743-753.  Plotting is host-side and out of scope; subclasses may still hook in."""
+
+    def render(self):
+        pass
+
+
+class ElectricMotorEnvironment:
+    """See module docstring.  Constructor signature follows reference core.py:197-209 plus the batch options
+    `num_envs`, `autoreset` ('same_step' | None), `seed`."""
+
+    metadata = {}
+    render_mode = None
+    env_id = None
+
+    def __init__(self, physical_system, reference_generator, reward_function, visualization=(), state_filter=None, callbacks=(),
+                 constraints=(), physical_system_wrappers=(), scale_plots=False, num_envs=None, autoreset=None, seed=None, **kwargs):
+        if len(tuple(physical_system_wrappers)) > 0:
+            raise NotImplementedError("physical_system_wrappers are not on the device path yet (SURVEY.md §8f row 1); "
+                                      "CurrentSumProcessor of the ShuntDc envs is built in")
+        if not isinstance(reference_generator, ReferenceGenerator):
+            raise TypeError("reference_generator must be a built-in gym_electric_motor_b200 ReferenceGenerator")
+        if not isinstance(reward_function, RewardFunction):
+            raise TypeError("reward_function must be a built-in gym_electric_motor_b200 RewardFunction")
+        self._scalar = num_envs is None
+        self._physical_system = physical_system
+        self._reference_generator = reference_generator
+        self._reward_function = reward_function
+        self.num_envs = physical_system.num_envs
+        if isinstance(constraints, ConstraintMonitor):
+            cm = constraints
+        else:
+            limit_constraints = [c for c in constraints if isinstance(c, str)]
+            additional = [c for c in constraints if isinstance(c, Constraint)]
+            bad = [c for c in constraints if not isinstance(c, (str, Constraint))]
+            if bad:
+                raise TypeError("callable constraints are host code and cannot be fused into the kernel epilogue")
+            cm = ConstraintMonitor(limit_constraints, additional)
+        self._constraint_monitor = cm
+        self._reference_generator.set_modules(self._physical_system)
+        self._constraint_monitor.set_modules(self._physical_system)
+        self._reward_function.set_modules(self._physical_system, self._reference_generator, self._constraint_monitor)
+        ps = self._physical_system
+        state_filter = state_filter or ps.state_names
+        self.state_filter = [ps.state_names.index(s) for s in state_filter]
+        self._filter_identity = self.state_filter == list(range(len(ps.state_names)))
+        state_space = Box(ps.state_space.low[self.state_filter], ps.state_space.high[self.state_filter], dtype=np.float64)
+        self.observation_space = Tuple((state_space, self._reference_generator.reference_space))
+        self.action_space = ps.action_space
+        self.reward_range = self._reward_function.reward_range
+        self._terminated = True
+        self._truncated = False
+        self.scale_plots = scale_plots
+        if isinstance(visualization, ElectricMotorVisualization):
+            visualization = [visualization]
+        self._visualizations = [v for v in (visualization or []) if isinstance(v, ElectricMotorVisualization)]
+        self._callbacks = list(callbacks) + list(self._visualizations)
+        self._autoreset = K.AUTORESET_SAME_STEP if (autoreset in ("same_step", True, K.AUTORESET_SAME_STEP)) else K.AUTORESET_NONE
+        self._seed_value = 0 if seed is None else int(seed)
+        self._sim = None
+        self._filter_index = None
+        self._call_callbacks("set_env", self)
+
+    # ------------------------------------------------------------------ reference-compatible properties
+    @property
+    def physical_system(self):
+        return self._physical_system
+
+    @property
+    def reference_generator(self):
+        return self._reference_generator
+
+    @property
+    def reward_function(self):
+        return self._reward_function
+
+    @property
+    def constraint_monitor(self):
+        return self._constraint_monitor
+
+    @property
+    def limits(self):
+        return self._physical_system.limits
+
+    @property
+    def state_names(self):
+        return self._physical_system.state_names
+
+    @property
+    def reference_names(self):
+        return self._reference_generator.reference_names
+
+    @property
+    def nominal_state(self):
+        return self._physical_system.nominal_state
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def sim(self):
+        """The underlying device handle wrapper (VectorSim)."""
+        return self._ensure_sim()
+
+    # ------------------------------------------------------------------ device handle
+    def build_config(self):
+        cfg = self._physical_system.fill_config(K.new_config())
+        self._constraint_monitor.fill_config(cfg)
+        self._reward_function.fill_config(cfg)
+        self._reference_generator.fill_config(cfg)
+        cfg.autoreset = self._autoreset
+        cfg.seed = self._seed_value & 0xFFFFFFFFFFFFFFFF
+        return cfg
+
+    def _ensure_sim(self):
+        if self._sim is None:
+            from .vector_sim import VectorSim
+
+            self._sim = VectorSim(self.build_config())
+            self._physical_system.attach(self._sim)
+        return self._sim
+
+    def _call_callbacks(self, func_name, *args):
+        for callback in self._callbacks:
+            getattr(callback, func_name)(*args)
+
+    def _filter(self, obs):
+        if self._filter_identity:
+            return obs
+        import torch
+
+        if self._filter_index is None:
+            self._filter_index = torch.as_tensor(self.state_filter, device=obs.device)
+        dim = 0 if self._sim.soa else 1
+        return obs.index_select(dim, self._filter_index)
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, seed=None, options=None, mask=None, *_, **__):
+        """core.py:300-319.  `seed` re-keys the device RNG streams (new handle state); `mask` (batched mode only)
+        resets a subset of envs and returns the full observation tensors."""
+        if seed is not None and int(seed) != self._seed_value:
+            self._seed_value = int(seed)
+            if self._sim is not None:
+                self._sim.close()
+                self._sim = None
+        sim = self._ensure_sim()
+        self._call_callbacks("on_reset_begin")
+        obs, ref = sim.reset(mask)
+        self._terminated = False
+        self._physical_system._k = 0
+        state = self._filter(obs)
+        self._call_callbacks("on_reset_end", state, ref)
+        if self._scalar:
+            return (state.double().cpu().numpy()[0], ref.double().cpu().numpy()[0]), {}
+        return (state, ref), {}
+
+    def step(self, action):
+        """core.py:328-371"""
+        sim = self._ensure_sim()
+        if self._scalar:
+            assert not self._terminated, "A reset is required before the environment can perform further steps"
+            action = np.asarray(action).reshape(1, -1)
+        self._call_callbacks("on_step_begin", self._physical_system.k, action)
+        obs, ref, reward, terminated = sim.step(action)
+        self._physical_system._k += 1
+        state = self._filter(obs)
+        self._call_callbacks("on_step_end", self._physical_system.k, state, ref, reward, terminated)
+        if self._scalar:
+            term = bool(terminated[0].item())
+            self._terminated = term and self._autoreset == K.AUTORESET_NONE
+            return (state.double().cpu().numpy()[0], ref.double().cpu().numpy()[0]), float(reward[0].item()), term, self._truncated, {}
+        return (state, ref), reward, terminated.bool(), self._truncated, {}
+
+    def set_reference(self, values):
+        """Push reference values [N, n_ref] for ExternalReferenceGenerator slots (used by the next step's reward)."""
+        self._ensure_sim().set_reference(values)
+
+    def state_dict(self):
+        return self._ensure_sim().state_dict()
+
+    def load_state_dict(self, sd):
+        self._ensure_sim().load_state_dict(sd)
+
+    def render(self, *_, **__):
+        for v in self._visualizations:
+            v.render()
+
+    def close(self):
+        self._call_callbacks("on_close")
+        self._reward_function.close()
+        self._reference_generator.close()
+        if self._sim is not None:
+            self._sim.close()
+            self._sim = None
+        self._physical_system.attach(None)

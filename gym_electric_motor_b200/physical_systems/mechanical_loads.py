@@ -1,0 +1,123 @@
+"""Mechanical-load descriptors (reference physical_systems/mechanical_loads/*.py); the ODE runs in the kernel (load_ode)."""
+from .. import _cabi as K
+from ..utils import update_parameter_dict
+
+
+class MechanicalLoad:
+    """reference mechanical_load.py:9-236"""
+
+    OMEGA_IDX = 0
+    HAS_JACOBIAN = True
+    KIND = None
+    _default_initializer = {"states": {"omega": 0.0}, "interval": None, "random_init": None, "random_params": (None, None)}
+
+    def __init__(self, state_names=None, j_load=0.0, load_initializer=None):
+        self._j_total = self._j_load = j_load
+        self._state_names = list(state_names or ["omega"])
+        self._limits = {}
+        self._nominal_values = {}
+        self._initializer = dict(self._default_initializer)
+        self._initializer["states"] = dict(self._default_initializer["states"])
+        li = dict(load_initializer or {})
+        if "states" in li:
+            li["states"] = dict(li["states"])
+        self._initializer.update(li)
+        if self._initializer.get("random_init") is not None:
+            raise NotImplementedError("random load initialisers (mechanical_load.py:100-167) are not on the device path yet")
+        self._initial_states = self._initializer.get("states", {s: 0.0 for s in self._state_names})
+
+    @property
+    def j_total(self):
+        return self._j_total
+
+    @property
+    def state_names(self):
+        return self._state_names
+
+    @property
+    def limits(self):
+        return self._limits
+
+    @property
+    def nominal_values(self):
+        return self._nominal_values
+
+    @property
+    def initializer(self):
+        return self._initializer
+
+    def set_j_rotor(self, j_rotor):
+        self._j_total += j_rotor
+
+    def get_state_space(self, omega_range):
+        return {"omega": omega_range[0]}, {"omega": omega_range[1]}
+
+    def initial_omega(self):
+        return float(self._initial_states.get("omega", 0.0))
+
+    def check_initial_state(self, nominal_state, state_low, state_positions):
+        """MechanicalLoad.initialize constant branch (mechanical_load.py:151-160)."""
+        idx = state_positions["omega"]
+        upper = nominal_state[idx]
+        lower = upper * state_low[idx]
+        if not (lower <= self.initial_omega() <= upper):
+            raise Exception("Initialization Value have to be in nominal boundaries")
+
+
+class ConstantSpeedLoad(MechanicalLoad):
+    """reference constant_speed_load.py"""
+
+    KIND = K.LOAD_CONST_SPEED
+
+    def __init__(self, omega_fixed=0, load_initializer=None, **kwargs):
+        super().__init__(load_initializer=load_initializer, **kwargs)
+        self._omega = omega_fixed or self._initializer["states"]["omega"]
+        if omega_fixed != 0:
+            self._initializer["states"]["omega"] = omega_fixed
+        self._initial_states = self._initializer["states"]
+
+    @property
+    def omega_fixed(self):
+        return self._omega
+
+    def fill_config(self, cfg):
+        cfg.load_kind = self.KIND
+        cfg.load_param[K.LP_J_LOAD] = float(self._j_load)
+
+
+class PolynomialStaticLoad(MechanicalLoad):
+    """reference polynomial_static_load.py"""
+
+    KIND = K.LOAD_POLY_STATIC
+    _load_parameter = dict(a=0.0, b=0.0, c=0.0, j_load=1e-5)
+    tau_decay = 1e-3
+
+    def __init__(self, load_parameter=None, limits=None, load_initializer=None):
+        self._load_parameter = update_parameter_dict(self._load_parameter, load_parameter if load_parameter is not None else {})
+        super().__init__(j_load=self._load_parameter["j_load"], load_initializer=load_initializer)
+        self._limits.update(limits or {})
+
+    @property
+    def load_parameter(self):
+        return self._load_parameter
+
+    def fill_config(self, cfg):
+        cfg.load_kind = self.KIND
+        cfg.load_param[K.LP_A] = float(self._load_parameter["a"])
+        cfg.load_param[K.LP_B] = float(self._load_parameter["b"])
+        cfg.load_param[K.LP_C] = float(self._load_parameter["c"])
+        cfg.load_param[K.LP_J_LOAD] = float(self._load_parameter["j_load"])
+        cfg.load_param[K.LP_TAU_DECAY] = float(self.tau_decay)
+
+
+def _unsupported(name, why):
+    class _Unsupported(MechanicalLoad):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} is not available on the device path: {why}")
+
+    _Unsupported.__name__ = name
+    return _Unsupported
+
+
+ExternalSpeedLoad = _unsupported("ExternalSpeedLoad", "it calls a user Python function per step (host callback), out of scope (SURVEY.md §2 row 5)")
+OrnsteinUhlenbeckLoad = _unsupported("OrnsteinUhlenbeckLoad", "the reference's own constructor raises AttributeError (ornstein_uhlenbeck_load.py:22-27)")

@@ -1,0 +1,322 @@
+"""Batched SCML (Supply-Converter-Motor-Load) physical systems — the host-side mirror of reference
+physical_systems/physical_systems.py.  A system object derives everything the reference derives on the host
+(state names, positions, limits, nominal state, state/action spaces) and owns the device handle that steps all N
+environments; `simulate` / `reset` keep the reference's names and return the NORMALISED state for all envs.
+
+Layout on the device and the kernels are described in DESIGN.md; the constructor keeps the reference's signature
+(`converter, motor, load, supply, ode_solver, tau, calc_jacobian`) plus the batch arguments `num_envs, device, dtype`.
+"""
+import numpy as np
+
+from .. import _cabi as K
+from ..spaces import Box
+from ..utils import set_state_array
+from .converters import ContDynamicallyAveragedConverter, FiniteConverter, PowerElectronicConverter
+from .electric_motors import (DcExternallyExcitedMotor, DcMotor, DcPermanentlyExcitedMotor, DcSeriesMotor, DcShuntMotor, ElectricMotor,
+                              ExternallyExcitedSynchronousMotor, InductionMotor, SynchronousMotor)
+from .mechanical_loads import MechanicalLoad
+from .solvers import OdeSolver
+from .voltage_supplies import IdealVoltageSupply, VoltageSupply
+
+
+class PhysicalSystem:
+    """reference core.py:589-705 (batched: state arrays have a leading env dimension)."""
+
+    def __init__(self, action_space, state_space, state_names, tau):
+        self._action_space = action_space
+        self._state_space = state_space
+        self._state_names = list(state_names)
+        self._state_positions = {key: index for index, key in enumerate(self._state_names)}
+        self._tau = tau
+        self._k = 0
+
+    @property
+    def tau(self):
+        return self._tau
+
+    @property
+    def k(self):
+        return self._k
+
+    @property
+    def state_names(self):
+        return self._state_names
+
+    @property
+    def state_positions(self):
+        return self._state_positions
+
+    @property
+    def action_space(self):
+        return self._action_space
+
+    @property
+    def state_space(self):
+        return self._state_space
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        pass
+
+
+class SCMLSystem(PhysicalSystem):
+    """reference physical_systems.py:13-287, batched.
+
+    Extra args: num_envs (N), device (CUDA ordinal or 'cuda:k'), dtype ('float32' = fp32 state + fp64 rotor angle,
+    'float64'), layout ('aos' row-per-env [N, n_state] | 'soa' field-major [n_state, N])."""
+
+    _MOTOR_BASE = ElectricMotor
+
+    def __init__(self, converter, motor, load, supply, ode_solver, tau=1e-4, calc_jacobian=None, num_envs=1, device=0,
+                 dtype="float32", layout="aos", env_index_offset=0, **_):
+        for obj, base, what in ((converter, PowerElectronicConverter, "converter"), (motor, self._MOTOR_BASE, "motor"),
+                                (load, MechanicalLoad, "load"), (supply, VoltageSupply, "supply"), (ode_solver, OdeSolver, "ode_solver")):
+            if not isinstance(obj, base):
+                raise TypeError(f"{what}={type(obj).__name__} is not a built-in {base.__name__} of gym_electric_motor_b200; "
+                                "user-defined Python components cannot run inside the CUDA kernel (INTEGRATION.md)")
+        if not isinstance(supply, IdealVoltageSupply):
+            raise NotImplementedError("only IdealVoltageSupply is on the device path in this round")
+        self._converter, self._electrical_motor, self._mechanical_load, self._supply, self._ode_solver = converter, motor, load, supply, ode_solver
+        self.num_envs = int(num_envs)
+        self._device = _device_index(device)
+        self._dtype = K.F32 if str(dtype).replace("torch.", "") in ("float32", "f32") else K.F64
+        self._layout = K.LAYOUT_SOA if str(layout).lower() == "soa" else K.LAYOUT_AOS
+        self._env_index_offset = int(env_index_offset)
+        self._mechanical_load.set_j_rotor(self._electrical_motor.motor_parameter["j_rotor"])  # :83
+        state_names = self._build_state_names()
+        self._set_indices()
+        state_space = self._build_state_space(state_names)
+        super().__init__(self._converter.action_space, state_space, state_names, tau)
+        self._limits = np.zeros(len(state_names))
+        self._nominal_state = np.zeros(len(state_names))
+        self._set_limits()
+        self._set_nominal_state()
+        self._converter.tau = self.tau  # :103
+        if self._converter.interlocking_time < 0 or self._converter.interlocking_time >= self.tau:
+            raise ValueError("interlocking_time must be within [0, tau)")
+        self._electrical_motor.check_initial_state(self._nominal_state, self._state_space.low, self._state_positions)
+        self._mechanical_load.check_initial_state(self._nominal_state, self._state_space.low, self._state_positions)
+        self._sim = None
+        self._owns_sim = False
+
+    # ------------------------------------------------------------------ reference-compatible properties
+    @property
+    def limits(self):
+        return self._limits
+
+    @property
+    def nominal_state(self):
+        return self._nominal_state
+
+    @property
+    def supply(self):
+        return self._supply
+
+    @property
+    def converter(self):
+        return self._converter
+
+    @property
+    def electrical_motor(self):
+        return self._electrical_motor
+
+    @property
+    def mechanical_load(self):
+        return self._mechanical_load
+
+    @property
+    def ode_solver(self):
+        return self._ode_solver
+
+    # ------------------------------------------------------------------ host derivations
+    def _set_limits(self):  # :105-112
+        for ind, state in enumerate(self._state_names):
+            self._limits[ind] = min(self._electrical_motor.limits.get(state, np.inf), self._mechanical_load.limits.get(state, np.inf))
+        self._limits[self._state_positions["u_sup"]] = self.supply.u_nominal
+
+    def _set_nominal_state(self):  # :114-123
+        for ind, state in enumerate(self._state_names):
+            self._nominal_state[ind] = min(self._electrical_motor.nominal_values.get(state, np.inf),
+                                           self._mechanical_load.nominal_values.get(state, np.inf))
+        self._nominal_state[self._state_positions["u_sup"]] = self.supply.u_nominal
+
+    def _build_state_names(self):
+        raise NotImplementedError
+
+    def _build_state_space(self, state_names):
+        raise NotImplementedError
+
+    def _set_indices(self):
+        self.OMEGA_IDX = 0
+        self.TORQUE_IDX = 1
+
+    def initial_ode_state(self):
+        """[omega, motor states...] constant initial ODE state (SCMLSystem.reset :263-270)."""
+        return np.concatenate(([self._mechanical_load.initial_omega()], self._electrical_motor.initial_ode_state()))
+
+    # ------------------------------------------------------------------ config / handle
+    def fill_config(self, cfg):
+        """Write the physics part of a gemb200_config (everything except constraints / reward / references)."""
+        cfg.n_envs = self.num_envs
+        cfg.device = self._device
+        cfg.dtype = self._dtype
+        cfg.layout = self._layout
+        cfg.env_index_offset = self._env_index_offset
+        cfg.finite = int(isinstance(self._converter, FiniteConverter))
+        slots = self._converter.slots()
+        for i in range(2):
+            cfg.converter_kind[i] = slots[i] if i < len(slots) else K.CONV_NONE
+        cfg.tau = float(self.tau)
+        cfg.interlocking_time = float(self._converter.interlocking_time)
+        cfg.u_sup = float(self._supply.u_nominal)
+        self._electrical_motor.fill_config(cfg)
+        self._mechanical_load.fill_config(cfg)
+        self._ode_solver.fill_config(cfg)
+        for i, v in enumerate(self._limits):
+            cfg.limits[i] = float(v)
+        for i, v in enumerate(self.initial_ode_state()):
+            cfg.init_ode[i] = float(v)
+        return cfg
+
+    def attach(self, sim, owns=False):
+        """Called by the environment: the handle that also carries the fused epilogue."""
+        self._sim, self._owns_sim = sim, owns
+
+    def _ensure_sim(self):
+        if self._sim is None:
+            from ..vector_sim import VectorSim
+
+            cfg = self.fill_config(K.new_config())
+            self._sim, self._owns_sim = VectorSim(cfg), True
+        return self._sim
+
+    # ------------------------------------------------------------------ PhysicalSystem API (batched)
+    def reset(self, initial_state=None, mask=None):
+        """Reset all (or the masked) envs; returns the normalised state [N, n_state] (reference :256-287)."""
+        sim = self._ensure_sim()
+        obs, _ = sim.reset(mask)
+        self._k = 0
+        return obs
+
+    def simulate(self, action, *_, **__):
+        """One step for all envs; returns the normalised state [N, n_state] (reference :171-203 and overrides)."""
+        sim = self._ensure_sim()
+        obs, _, _, _ = sim.step(action)
+        self._k += 1
+        return obs
+
+    def close(self):
+        if self._sim is not None and self._owns_sim:
+            self._sim.close()
+        self._sim = None
+
+
+def _device_index(device):
+    if isinstance(device, int):
+        return device
+    s = str(device)
+    if s in ("cuda", "gpu"):
+        try:
+            import torch
+
+            return torch.cuda.current_device()
+        except Exception:
+            return 0
+    if ":" in s:
+        return int(s.split(":")[1])
+    return int(s)
+
+
+class DcMotorSystem(SCMLSystem):
+    """reference physical_systems.py:290-318"""
+
+    _MOTOR_BASE = DcMotor
+
+    def _build_state_names(self):
+        names = self._mechanical_load.state_names + ["torque"] + self._electrical_motor.CURRENTS + self._electrical_motor.VOLTAGES + ["u_sup"]
+        if isinstance(self._electrical_motor, DcShuntMotor):
+            # every ShuntDc env of the reference wraps the system in CurrentSumProcessor(('i_a','i_e'))
+            # (envs/gym_dcm/shunt_dc_motor_env/*.py); the i_sum state is produced natively by the kernel
+            names = names + ["i_sum"]
+        return names
+
+    def _build_state_space(self, state_names):
+        low, high = self._electrical_motor.get_state_space(self._converter.currents, self._converter.voltages)
+        low_m, high_m = self._mechanical_load.get_state_space((low["omega"], high["omega"]))
+        low.update(low_m)
+        high.update(high_m)
+        high["u_sup"] = self._supply.supply_range[1] / self._supply.u_nominal
+        low["u_sup"] = self._supply.supply_range[0] / self._supply.u_nominal if self._supply.supply_range[0] != self._supply.supply_range[1] else 0
+        if "i_sum" in state_names:
+            low["i_sum"], high["i_sum"] = -1.0, 1.0  # current_sum_processor.py:30-32
+        return Box(set_state_array(low, state_names), set_state_array(high, state_names), dtype=np.float64)
+
+    def _set_limits(self):
+        names = [n for n in self._state_names if n != "i_sum"]
+        for ind, state in enumerate(names):
+            self._limits[ind] = min(self._electrical_motor.limits.get(state, np.inf), self._mechanical_load.limits.get(state, np.inf))
+        self._limits[self._state_positions["u_sup"]] = self.supply.u_nominal
+        if "i_sum" in self._state_positions:  # current_sum_processor.py:34-37 (limit='max')
+            idx = [self._state_positions["i_a"], self._state_positions["i_e"]]
+            self._limits[self._state_positions["i_sum"]] = max(self._limits[idx])
+
+    def _set_nominal_state(self):
+        names = [n for n in self._state_names if n != "i_sum"]
+        for ind, state in enumerate(names):
+            self._nominal_state[ind] = min(self._electrical_motor.nominal_values.get(state, np.inf),
+                                           self._mechanical_load.nominal_values.get(state, np.inf))
+        self._nominal_state[self._state_positions["u_sup"]] = self.supply.u_nominal
+        if "i_sum" in self._state_positions:
+            idx = [self._state_positions["i_a"], self._state_positions["i_e"]]
+            self._nominal_state[self._state_positions["i_sum"]] = max(self._nominal_state[idx])
+
+
+class ThreePhaseMotorSystem(SCMLSystem):
+    """reference physical_systems.py:321-415 (the abc / alpha-beta / dq helpers run inside the kernel)."""
+
+    _NAMES = []
+
+    def __init__(self, control_space="abc", **kwargs):
+        if control_space != "abc":
+            raise NotImplementedError("control_space='dq' (physical_systems.py:423-435) is not on the device path yet (SURVEY.md §8f row 2)")
+        self.control_space = control_space
+        super().__init__(**kwargs)
+
+    def _build_state_names(self):
+        return self._mechanical_load.state_names + list(self._NAMES)
+
+    def _build_state_space(self, state_names):  # :437-442
+        low = -1 * np.ones(len(state_names))
+        low[state_names.index("u_sup")] = 0.0
+        return Box(low, np.ones(len(state_names)), dtype=np.float64)
+
+
+class SynchronousMotorSystem(ThreePhaseMotorSystem):
+    """reference physical_systems.py:418-561"""
+
+    _MOTOR_BASE = SynchronousMotor
+    _NAMES = ["torque", "i_a", "i_b", "i_c", "i_sd", "i_sq", "u_a", "u_b", "u_c", "u_sd", "u_sq", "epsilon", "u_sup"]
+
+
+class ExternallyExcitedSynchronousMotorSystem(SynchronousMotorSystem):
+    """reference physical_systems.py:564-693"""
+
+    _MOTOR_BASE = ExternallyExcitedSynchronousMotor
+    _NAMES = ["torque", "i_a", "i_b", "i_c", "i_sd", "i_sq", "i_e", "u_a", "u_b", "u_c", "u_sd", "u_sq", "u_e", "epsilon", "u_sup"]
+
+
+class SquirrelCageInductionMotorSystem(ThreePhaseMotorSystem):
+    """reference physical_systems.py:696-847"""
+
+    _MOTOR_BASE = InductionMotor
+    _NAMES = ["torque", "i_sa", "i_sb", "i_sc", "i_sd", "i_sq", "u_sa", "u_sb", "u_sc", "u_sd", "u_sq", "epsilon", "u_sup"]
+
+
+def _dfim(*a, **k):
+    raise NotImplementedError("DoublyFedInductionMotorSystem (physical_systems.py:850-1113) is out of scope this round (SURVEY.md §8f row 2)")
+
+
+DoublyFedInductionMotorSystem = _dfim

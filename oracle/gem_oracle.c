@@ -844,6 +844,7 @@ static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
 /* ------------------------------------------------------------------------------------------------------------ */
 /* public API (loaded by tests/bench via ctypes)                                                                 */
 /* ------------------------------------------------------------------------------------------------------------ */
+void gem_oracle_reset(gem_oracle* o, const uint8_t* mask, double* obs, double* ref_next);
 int gem_oracle_create(const gemb200_config* cfg, gem_oracle** out) {
   if (!cfg || cfg->struct_size != (int32_t)sizeof(gemb200_config)) return -4;
   gem_oracle* o = (gem_oracle*)calloc(1, sizeof(gem_oracle));
@@ -851,6 +852,7 @@ int gem_oracle_create(const gemb200_config* cfg, gem_oracle** out) {
   if (dims(o)) { free(o); return -1; }
   update_model(o);
   o->env = (env_t*)calloc((size_t)cfg->n_envs, sizeof(env_t));
+  gem_oracle_reset(o, NULL, NULL, NULL); /* like gemb200_create: every env starts reset; API call id 1 */
   *out = o;
   return 0;
 }

@@ -1,0 +1,122 @@
+"""Host logic (no GPU): the env registry and the limit / nominal / space / reference-margin / reward derivations must
+reproduce what the running reference reported for each of its registered ids (tests/golden/env_table.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gym_electric_motor_b200 as gem
+from gym_electric_motor_b200 import _cabi as K
+from helpers import GOLDEN_DIR, config_from_meta, load_golden
+
+TABLE = json.load(open(os.path.join(GOLDEN_DIR, "env_table.json")))
+IDS = [k for k in sorted(TABLE) if "DFIM" not in k]
+
+
+def test_registry_covers_reference_ids():
+    assert sorted(gem.env_ids()) == IDS
+    with pytest.raises(NotImplementedError):
+        gem.make("Cont-CC-DFIM-v0")
+    with pytest.raises(KeyError):
+        gem.make("Cont-CC-Nope-v0")
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_defaults_match_reference(env_id):
+    e = TABLE[env_id]
+    env = gem.make(env_id)
+    p = env.physical_system
+    assert p.state_names == e["state_names"]
+    np.testing.assert_allclose(p.limits, e["limits"], rtol=1e-12)
+    np.testing.assert_allclose(p.nominal_state, e["nominal_state"], rtol=1e-12)
+    np.testing.assert_allclose(p.state_space.low, e["state_low"])
+    np.testing.assert_allclose(p.state_space.high, e["state_high"])
+    assert p.tau == e["tau"]
+    assert p.supply.u_nominal == e["u_sup"]
+    assert type(p.electrical_motor).__name__ == e["motor_class"]
+    assert type(p.mechanical_load).__name__ == e["load_class"]
+    assert type(p.converter).__name__ == e["converter_class"]
+    assert p.mechanical_load.j_total == pytest.approx(e["j_total"], rel=1e-12)
+    for k_, v in e["motor_parameter"].items():
+        if k_ in p.electrical_motor.motor_parameter:
+            assert p.electrical_motor.motor_parameter[k_] == v
+    sp = e["action_space"]
+    if sp["kind"] == "Box":
+        np.testing.assert_allclose(env.action_space.low, sp["low"])
+        np.testing.assert_allclose(env.action_space.high, sp["high"])
+    elif sp["kind"] == "Discrete":
+        assert env.action_space.n == sp["n"]
+    else:
+        assert list(env.action_space.nvec) == sp["nvec"]
+    assert list(env.reference_names) == e["reference_names"]
+    np.testing.assert_allclose(env.reference_generator.reference_space.low, e["reference_space"]["low"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(env.reference_generator.reference_space.high, e["reference_space"]["high"], rtol=1e-12)
+    np.testing.assert_allclose(env.reward_function._reward_weights, e["reward_weights"], rtol=1e-12)
+    assert env.reward_function._violation_reward == pytest.approx(e["violation_reward"], rel=1e-12)
+    assert list(env.reward_range) == pytest.approx(e["reward_range"])
+    # compiled config: constraints, reference slots, initial observation
+    cfg = env.build_config()
+    names = e["state_names"]
+    assert cfg.n_constraints == len(e["constraints"])
+    for ci, con in enumerate(e["constraints"]):
+        assert cfg.constraint_kind[ci] == (K.CONSTRAINT_SQUARED if con["kind"] == "SquaredConstraint" else K.CONSTRAINT_LIMIT)
+        assert cfg.constraint_mask[ci] == sum(1 << names.index(s) for s in con["states"])
+    rg = e["reference_generator"]
+    subs = rg.get("sub_generators", [rg])
+    assert cfg.n_ref == len(subs)
+    for r, s in enumerate(subs):
+        assert cfg.ref_kind[r] == K.REF_WIENER and cfg.ref_state[r] == names.index(s["reference_state"])
+        assert (cfg.ref_margin_lo[r], cfg.ref_margin_hi[r]) == pytest.approx(tuple(s["limit_margin"]), rel=1e-12, abs=1e-15)
+        assert (cfg.ref_init_lo[r], cfg.ref_init_hi[r]) == pytest.approx(tuple(s["initial_range"]), rel=1e-12, abs=1e-15)
+        assert (cfg.ref_sigma_lo[r], cfg.ref_sigma_hi[r]) == pytest.approx(tuple(s["sigma_range"]))
+        assert (cfg.ref_len_lo[r], cfg.ref_len_hi[r]) == tuple(s["episode_len_range"])
+    assert cfg.interlocking_time == e["interlocking_time"]
+    assert np.allclose([cfg.init_ode[0]], [e["reset_state"][0] * e["limits"][0]])
+
+
+def test_config_equals_golden_meta_translation():
+    """The product's spec compiler and the independent golden-meta translation in tests/helpers.py must agree."""
+    for name, env_id, kw in [
+        ("pmsm_cc_rk4", "Cont-CC-PMSM-v0", {}),
+        ("pmsm_fin_sc_rk4_interlock", "Finite-SC-PMSM-v0", dict(converter=dict(interlocking_time=1e-6))),
+        ("eesm_cc_rk4", "Cont-CC-EESM-v0", {}),
+        ("scim_sc_rk4", "Cont-SC-SCIM-v0", {}),
+        ("permex_cc_rk4", "Cont-CC-PermExDc-v0", {}),
+        ("shunt_cc_rk4", "Cont-CC-ShuntDc-v0", {}),
+        ("pmsm_sc_polyload_rk4", "Cont-SC-PMSM-v0", dict(load=dict(load_parameter=dict(a=0.5, b=0.02, c=1e-4, j_load=2e-3)))),
+        ("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", dict(motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
+                                                              motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0))))),
+    ]:
+        g = load_golden(name)
+        ref = config_from_meta(g["meta"], reset_ode=g["reset_ode"], solver="rk4", ref_kind=K.REF_WIENER)
+        env = gem.make(env_id, ode_solver=gem.physical_systems.RK4Solver(), **kw)
+        cfg = env.build_config()
+        for f in ("motor_kind", "finite", "load_kind", "solver_kind", "solver_nsteps", "tau", "interlocking_time", "u_sup", "n_ref",
+                  "n_constraints", "reward_bias", "violation_reward"):
+            assert getattr(cfg, f) == pytest.approx(getattr(ref, f)), (name, f)
+        for f, n in (("converter_kind", 2), ("motor_param", 16), ("load_param", 5), ("limits", 24), ("init_ode", 8), ("reward_weight", 24),
+                     ("state_length", 24), ("constraint_mask", 4), ("ref_state", 4)):
+            a, b = list(getattr(cfg, f))[:n], list(getattr(ref, f))[:n]
+            assert a == pytest.approx(b, rel=1e-12), (name, f, a, b)
+
+
+def test_kwargs_semantics():
+    env = gem.make("Cont-CC-PMSM-v0", motor=dict(motor_parameter=dict(r_s=0.05)), tau=5e-5,
+                   ode_solver=gem.physical_systems.EulerSolver(nsteps=3), supply=dict(u_nominal=400.0), state_filter=["i_sd", "i_sq"])
+    assert env.physical_system.electrical_motor.motor_parameter["r_s"] == 0.05
+    assert env.physical_system.tau == 5e-5 and env.physical_system.converter.tau == 5e-5
+    assert env.physical_system.limits[-1] == 400.0
+    assert env.state_filter == [5, 6]
+    cfg = env.build_config()
+    assert cfg.solver_kind == K.SOLVER_EULER and cfg.solver_nsteps == 3
+    with pytest.raises(KeyError):
+        gem.make("Cont-CC-PMSM-v0", motor=dict(motor_parameter=dict(nope=1)))  # utils.update_parameter_dict
+    with pytest.raises(Exception):
+        gem.make("Cont-CC-PMSM-v0", converter="Finite-B6C")  # strings are deprecated in the reference (utils.py:12-13)
+    with pytest.raises(Exception):
+        gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(states=dict(i_sq=1e4, i_sd=0.0, epsilon=0.0))))
+    with pytest.raises(TypeError):
+        gem.make("Cont-CC-PMSM-v0", motor=object())
+    # default (scipy) solver of the reference maps to RK4 with two sub-steps
+    assert gem.make("Cont-CC-PMSM-v0").build_config().solver_nsteps == 2
