@@ -11,6 +11,7 @@ The whole step — physical system, reference lookup, constraint check, reward, 
 through the C-ABI (include/gemb200.h: gemb200_step); see DESIGN.md.
 """
 import numpy as np
+import torch
 
 from . import _cabi as K
 from .constraints import Constraint, ConstraintMonitor
@@ -206,16 +207,18 @@ class ElectricMotorEnvironment:
         if self._scalar:
             assert not self._terminated, "A reset is required before the environment can perform further steps"
             action = np.asarray(action).reshape(1, -1)
-        self._call_callbacks("on_step_begin", self._physical_system.k, action)
+        if self._callbacks:
+            self._call_callbacks("on_step_begin", self._physical_system.k, action)
         obs, ref, reward, terminated = sim.step(action)
         self._physical_system._k += 1
-        state = self._filter(obs)
-        self._call_callbacks("on_step_end", self._physical_system.k, state, ref, reward, terminated)
+        state = obs if self._filter_identity else self._filter(obs)
+        if self._callbacks:
+            self._call_callbacks("on_step_end", self._physical_system.k, state, ref, reward, terminated)
         if self._scalar:
             term = bool(terminated[0].item())
             self._terminated = term and self._autoreset == K.AUTORESET_NONE
             return (state.double().cpu().numpy()[0], ref.double().cpu().numpy()[0]), float(reward[0].item()), term, self._truncated, {}
-        return (state, ref), reward, terminated.bool(), self._truncated, {}
+        return (state, ref), reward, terminated.view(torch.bool), self._truncated, {}  # uint8 0/1 reinterpreted, no kernel
 
     def set_reference(self, values):
         """Push reference values [N, n_ref] for ExternalReferenceGenerator slots (used by the next step's reward)."""

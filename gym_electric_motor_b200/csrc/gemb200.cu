@@ -32,11 +32,9 @@ struct gemb200_handle {
   bool has_eps = false, any_wiener = false, two_segment = false;
   size_t rsz = 4;  // sizeof(real)
   // persistent device state
-  void* d_x = nullptr;
+  int W = 0;  // words per env in the packed record (state_words(nx, n_ref))
+  void* d_st = nullptr;
   double* d_eps = nullptr;
-  void* d_ref_val = nullptr;
-  void* d_ref_sigma = nullptr;
-  int32_t* d_ref_left = nullptr;
   uint16_t* d_sw = nullptr;
   StepParams<float> pf;
   StepParams<double> pd;
@@ -110,11 +108,15 @@ static int validate(const gemb200_config* c) {
     if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_EXTERNAL) return fail(GEMB200_E_INVALID, "bad ref_kind");
     if (c->ref_kind[r] == GEMB200_REF_WIENER && (c->ref_len_lo[r] < 1 || c->ref_len_hi[r] < c->ref_len_lo[r] || !(c->ref_sigma_lo[r] > 0)))
       return fail(GEMB200_E_INVALID, "bad Wiener reference ranges");
+    if (c->ref_kind[r] == GEMB200_REF_WIENER && c->ref_len_hi[r] > 65535)
+      return fail(GEMB200_E_INVALID, "sub-episode lengths above 65535 steps are not supported (16-bit counters)");
   }
   for (int j = 0; j < d.n_state; ++j)
     if (!(c->limits[j] != 0.0) && !(c->motor_kind == GEMB200_MOTOR_SHUNT_DC && j == 6)) return fail(GEMB200_E_INVALID, "limits must be non-zero");
   const double j_total = c->load_param[GEMB200_LP_J_LOAD] + c->motor_param[GEMB200_MP_J_ROTOR];
   if (c->load_kind == GEMB200_LOAD_POLY_STATIC && !(j_total > 0)) return fail(GEMB200_E_INVALID, "total inertia must be positive");
+  if ((int64_t)c->n_envs * (int64_t)(state_words(d.nx, c->n_ref) > d.n_state ? state_words(d.nx, c->n_ref) : d.n_state) >= (int64_t)1 << 31)
+    return fail(GEMB200_E_INVALID, "n_envs too large for 32-bit element indexing in one handle; shard the batch");
   return GEMB200_OK;
 }
 
@@ -244,12 +246,12 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->n = c.n_envs;
   p->env_offset = c.env_index_offset;
   p->seed_lo = (uint32_t)c.seed; p->seed_hi = (uint32_t)(c.seed >> 32);
-  p->x = static_cast<real*>(h->d_x);
+  p->st = static_cast<real*>(h->d_st);
   p->eps = h->d_eps;
-  p->ref_val = static_cast<real*>(h->d_ref_val);
-  p->ref_sigma = static_cast<real*>(h->d_ref_sigma);
-  p->ref_left = h->d_ref_left;
   p->sw = h->d_sw;
+  p->layout = c.layout;
+  p->n_act = dm.n_act;
+  p->inv_nsteps = (real)(1.0 / c.solver_nsteps);
   p->motor_kind = c.motor_kind;
   p->conv_kind[0] = c.converter_kind[0]; p->conv_kind[1] = c.converter_kind[1];
   p->load_kind = c.load_kind; p->solver_kind = c.solver_kind; p->nsteps = c.solver_nsteps;
@@ -280,7 +282,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   for (int j = 0; j < dm.n_state; ++j) {
     if (c.reward_weight[j] == 0.0) continue;
     p->rw_state[t] = j;
-    p->rw_ref[t] = -1;
+    p->rw_ref[t] = kMaxRef;
     for (int r = 0; r < c.n_ref; ++r) if (c.ref_state[r] == j) p->rw_ref[t] = r;
     p->rw_w[t] = (real)c.reward_weight[j];
     p->rw_inv_len[t] = (real)(1.0 / c.state_length[j]);
@@ -310,52 +312,67 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int kBlock = 256;
 
-template <int FAM, bool FINITE, typename real, int LAYOUT>
+template <int FAM, bool FINITE, typename real, int NREF>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const int grid = (p.n + kBlock - 1) / kBlock;
-  const size_t smem = (size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD * sizeof(real);
-  step_kernel<FAM, FINITE, real, LAYOUT><<<grid, kBlock, smem, st>>>(p);
+  const size_t smem = ((size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD + (size_t)kBlock * kRefPad) * sizeof(real);
+  step_kernel<FAM, FINITE, real, NREF><<<grid, kBlock, smem, st>>>(p);
   return cudaGetLastError();
 }
-template <int FAM, typename real, int LAYOUT>
+template <int FAM, typename real, int NREF>
 static cudaError_t launch_reset_t(const StepParams<real>& p, cudaStream_t st) {
   const int grid = (p.n + kBlock - 1) / kBlock;
-  reset_kernel<FAM, real, LAYOUT><<<grid, kBlock, 0, st>>>(p);
+  reset_kernel<FAM, real, NREF><<<grid, kBlock, 0, st>>>(p);
   return cudaGetLastError();
 }
 
-template <typename real>
-static cudaError_t launch_step(int fam, bool finite, int layout, const StepParams<real>& p, cudaStream_t st) {
-#define GEMB200_CASE(F)                                                                                        \
-  case F:                                                                                                      \
-    if (finite) return layout == GEMB200_LAYOUT_AOS ? launch_step_t<F, true, real, GEMB200_LAYOUT_AOS>(p, st)  \
-                                                    : launch_step_t<F, true, real, GEMB200_LAYOUT_SOA>(p, st); \
-    return layout == GEMB200_LAYOUT_AOS ? launch_step_t<F, false, real, GEMB200_LAYOUT_AOS>(p, st)             \
-                                        : launch_step_t<F, false, real, GEMB200_LAYOUT_SOA>(p, st);
-  switch (fam) {
-    GEMB200_CASE(kDC1)
-    GEMB200_CASE(kDC2)
-    GEMB200_CASE(kSYNC)
-    GEMB200_CASE(kEESM)
-    GEMB200_CASE(kSCIM)
+template <int FAM, typename real>
+static cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
+#define GEMB200_NREF(R)                                                                         \
+  case R:                                                                                       \
+    return finite ? launch_step_t<FAM, true, real, R>(p, st) : launch_step_t<FAM, false, real, R>(p, st);
+  switch (nref) {
+    GEMB200_NREF(0)
+    GEMB200_NREF(1)
+    GEMB200_NREF(2)
+    GEMB200_NREF(3)
+    GEMB200_NREF(4)
   }
-#undef GEMB200_CASE
+#undef GEMB200_NREF
+  return cudaErrorInvalidValue;
+}
+template <int FAM, typename real>
+static cudaError_t launch_reset_f(int nref, const StepParams<real>& p, cudaStream_t st) {
+  switch (nref) {
+    case 0: return launch_reset_t<FAM, real, 0>(p, st);
+    case 1: return launch_reset_t<FAM, real, 1>(p, st);
+    case 2: return launch_reset_t<FAM, real, 2>(p, st);
+    case 3: return launch_reset_t<FAM, real, 3>(p, st);
+    case 4: return launch_reset_t<FAM, real, 4>(p, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename real>
+static cudaError_t launch_step(int fam, bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
+  switch (fam) {
+    case kDC1: return launch_step_f<kDC1, real>(finite, nref, p, st);
+    case kDC2: return launch_step_f<kDC2, real>(finite, nref, p, st);
+    case kSYNC: return launch_step_f<kSYNC, real>(finite, nref, p, st);
+    case kEESM: return launch_step_f<kEESM, real>(finite, nref, p, st);
+    case kSCIM: return launch_step_f<kSCIM, real>(finite, nref, p, st);
+  }
   return cudaErrorInvalidValue;
 }
 template <typename real>
-static cudaError_t launch_reset(int fam, int layout, const StepParams<real>& p, cudaStream_t st) {
-#define GEMB200_CASE(F)                                                                                    \
-  case F:                                                                                                  \
-    return layout == GEMB200_LAYOUT_AOS ? launch_reset_t<F, real, GEMB200_LAYOUT_AOS>(p, st)               \
-                                        : launch_reset_t<F, real, GEMB200_LAYOUT_SOA>(p, st);
+static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cudaStream_t st) {
   switch (fam) {
-    GEMB200_CASE(kDC1)
-    GEMB200_CASE(kDC2)
-    GEMB200_CASE(kSYNC)
-    GEMB200_CASE(kEESM)
-    GEMB200_CASE(kSCIM)
+    case kDC1: return launch_reset_f<kDC1, real>(nref, p, st);
+    case kDC2: return launch_reset_f<kDC2, real>(nref, p, st);
+    case kSYNC: return launch_reset_f<kSYNC, real>(nref, p, st);
+    case kEESM: return launch_reset_f<kEESM, real>(nref, p, st);
+    case kSCIM: return launch_reset_f<kSCIM, real>(nref, p, st);
   }
-#undef GEMB200_CASE
   return cudaErrorInvalidValue;
 }
 
@@ -367,12 +384,12 @@ static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, 
     StepParams<float>& p = h->pf;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
-    e = launch_step<float>(h->fam, h->cfg.finite != 0, h->cfg.layout, p, st);
+    e = launch_step<float>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   } else {
     StepParams<double>& p = h->pd;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
-    e = launch_step<double>(h->fam, h->cfg.finite != 0, h->cfg.layout, p, st);
+    e = launch_step<double>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   }
   if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
   h->launches += 1;
@@ -386,13 +403,13 @@ static int do_reset(gemb200_handle* h, const uint8_t* mask, void* obs, void* ref
     StepParams<float>& p = h->pf;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.reset_mask = mask; p.obs = (float*)obs; p.ref_out = (float*)ref;
-    e = launch_reset<float>(h->fam, h->cfg.layout, p, st);
+    e = launch_reset<float>(h->fam, h->n_ref, p, st);
     p.reset_mask = nullptr;
   } else {
     StepParams<double>& p = h->pd;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.reset_mask = mask; p.obs = (double*)obs; p.ref_out = (double*)ref;
-    e = launch_reset<double>(h->fam, h->cfg.layout, p, st);
+    e = launch_reset<double>(h->fam, h->n_ref, p, st);
     p.reset_mask = nullptr;
   }
   if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string("reset launch: ") + cudaGetErrorString(e));
@@ -471,12 +488,9 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
     if (e_ != cudaSuccess) { gemb200_destroy(h); return fail(e_ == cudaErrorMemoryAllocation ? GEMB200_E_NOMEM : GEMB200_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); } \
     cudaMemset((ptr), 0, (bytes));                                                                            \
   } while (0)
-  ALLOC(h->d_x, n * d.nx * h->rsz);
+  h->W = state_words(d.nx, cfg->n_ref);
+  ALLOC(h->d_st, n * h->W * h->rsz);
   if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
-  if (cfg->n_ref > 0) {
-    ALLOC(h->d_ref_val, n * cfg->n_ref * h->rsz);
-    if (h->any_wiener) { ALLOC(h->d_ref_sigma, n * cfg->n_ref * h->rsz); ALLOC(h->d_ref_left, n * cfg->n_ref * sizeof(int32_t)); }
-  }
   if (h->two_segment) ALLOC(h->d_sw, n * sizeof(uint16_t));
 #undef ALLOC
   Derived dv;
@@ -496,7 +510,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_x); cudaFree(h->d_eps); cudaFree(h->d_ref_val); cudaFree(h->d_ref_sigma); cudaFree(h->d_ref_left); cudaFree(h->d_sw);
+  cudaFree(h->d_st); cudaFree(h->d_eps); cudaFree(h->d_sw);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -590,8 +604,8 @@ int gemb200_get_ode_state(gemb200_handle* h, double* ode_out, void* stream) {
   if (!h || !ode_out) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) get_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_x, h->d_eps, ode_out, n, h->nx, h->has_eps);
-  else get_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_x, h->d_eps, ode_out, n, h->nx, h->has_eps);
+  if (h->cfg.dtype == GEMB200_F32) get_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_st, h->d_eps, ode_out, n, h->nx, h->W, h->has_eps);
+  else get_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_st, h->d_eps, ode_out, n, h->nx, h->W, h->has_eps);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
@@ -600,8 +614,8 @@ int gemb200_set_ode_state(gemb200_handle* h, const double* ode_in, void* stream)
   if (!h || !ode_in) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) set_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_x, h->d_eps, ode_in, n, h->nx, h->has_eps);
-  else set_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_x, h->d_eps, ode_in, n, h->nx, h->has_eps);
+  if (h->cfg.dtype == GEMB200_F32) set_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_st, h->d_eps, ode_in, n, h->nx, h->W, h->has_eps);
+  else set_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_st, h->d_eps, ode_in, n, h->nx, h->W, h->has_eps);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
@@ -611,8 +625,8 @@ int gemb200_get_reference(gemb200_handle* h, double* ref_out, void* stream) {
   if (h->n_ref == 0) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) get_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_ref_val, ref_out, n, h->n_ref);
-  else get_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_ref_val, ref_out, n, h->n_ref);
+  if (h->cfg.dtype == GEMB200_F32) get_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_st, ref_out, n, h->nx, h->W, h->n_ref);
+  else get_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_st, ref_out, n, h->nx, h->W, h->n_ref);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
@@ -622,23 +636,20 @@ int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream)
   if (h->n_ref == 0) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) set_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_ref_val, ref_in, n, h->n_ref);
-  else set_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_ref_val, ref_in, n, h->n_ref);
+  if (h->cfg.dtype == GEMB200_F32) set_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_st, ref_in, n, h->nx, h->W, h->n_ref);
+  else set_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_st, ref_in, n, h->nx, h->W, h->n_ref);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
 }
 
-// checkpoint blob: [gstep u64][x][eps][ref_val][ref_sigma][ref_left][sw]
+// checkpoint blob: [gstep u64][packed records][eps][sw]
 struct Section { void* ptr; size_t bytes; };
 static int sections(gemb200_handle* h, Section* s) {
   const size_t n = (size_t)h->cfg.n_envs;
   int k = 0;
-  s[k++] = {h->d_x, n * h->nx * h->rsz};
+  s[k++] = {h->d_st, n * h->W * h->rsz};
   if (h->d_eps) s[k++] = {h->d_eps, n * sizeof(double)};
-  if (h->d_ref_val) s[k++] = {h->d_ref_val, n * h->n_ref * h->rsz};
-  if (h->d_ref_sigma) s[k++] = {h->d_ref_sigma, n * h->n_ref * h->rsz};
-  if (h->d_ref_left) s[k++] = {h->d_ref_left, n * h->n_ref * sizeof(int32_t)};
   if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
   return k;
 }

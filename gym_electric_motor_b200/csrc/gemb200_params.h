@@ -3,6 +3,8 @@
 // Everything a thread needs besides its own env's state is here, so a launch reads no global-memory parameter
 // table: uniform operands come straight from the constant bank (c[0x0][...]) at no issue cost.
 #pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace gemb200 {
@@ -11,6 +13,20 @@ constexpr int kMaxState = 24;
 constexpr int kMaxRef = 4;
 constexpr int kMaxConstraints = 4;
 constexpr int kMaxX = 6;  // real-typed ODE states per env (omega + motor states without the angle): SCIM 5
+
+// words of persistent state per env and their placement (shared by host and device code)
+__host__ __device__ constexpr int state_words(int nx, int nref) { return nx + 2 * nref + (nref + 1) / 2; }
+// element offset (in units of `real`) of word w of env i; vw = 16 / sizeof(real) words per 16-byte chunk
+__host__ __device__ inline size_t word_offset(int w, size_t i, size_t n, int W, int vw) {
+  const int nfull = (W / vw) * vw;
+  if (w < nfull) return (size_t)(w / vw) * vw * n + i * vw + (w % vw);
+  int rem = W - nfull, base = nfull;  // remaining words: for vw == 4 an optional 2-word chunk, then an optional 1-word chunk
+  if (vw == 4 && rem >= 2) {
+    if (w < base + 2) return (size_t)base * n + i * 2 + (w - base);
+    base += 2;
+  }
+  return (size_t)base * n + i + (w - base);
+}
 
 // Motor families = template specialisations of the step kernel.
 enum MotorFamily : int {
@@ -34,12 +50,12 @@ struct StepParams {
   int64_t env_offset;     // global index of env 0 (sharding)
   uint32_t seed_lo, seed_hi;
   uint32_t gstep_lo, gstep_hi;  // unique id of this API call (reset or step): RNG counter words 0,1
-  // ---- persistent per-env state (SoA, owned by the handle) ----
-  real* x;                // [n_x][n]  omega, currents (, fluxes)
+  // ---- persistent per-env state (owned by the handle) ----
+  // `st`: W = NX + 2*NREF + ceil(NREF/2) words per env: [x_0..x_{NX-1} | (ref value, sigma) per slot | sub-episode counters,
+  // two 16-bit counters per word].  Stored as SoA of VECTOR CHUNKS (16-byte chunks first, then an 8-byte, then a 4-byte chunk)
+  // so that a thread moves its record with W/4 fully coalesced 128-bit accesses (see word_offset()).
+  real* st;
   double* eps;            // [n]       electrical angle, wrapped to (-pi, pi]; nullptr for DC
-  real* ref_val;          // [n_ref][n]
-  real* ref_sigma;        // [n_ref][n]   (Wiener slots only)
-  int32_t* ref_left;      // [n_ref][n]
   uint16_t* sw;           // [n] finite 2QC switching states, 2 bits per leg; nullptr unless finite && interlock
   // ---- I/O of this call (caller-owned) ----
   const void* action;
@@ -55,7 +71,10 @@ struct StepParams {
   int32_t solver_kind;
   int32_t nsteps;
   int32_t autoreset;
+  int32_t layout;         // gemb200_layout of the I/O tensors
+  int32_t n_act;
   int32_t two_segment;    // finite && interlocking_time > 0
+  real inv_nsteps;
   real tau;               // step
   real til;               // interlocking time
   real til_over_tau;
@@ -75,7 +94,7 @@ struct StepParams {
   // ---- reward: sum over n_rw terms  w * (|s[idx] - ref| * inv_len)^pow ----
   int32_t n_rw;
   int32_t rw_state[kMaxState];
-  int32_t rw_ref[kMaxState];   // reference slot or -1 (reference 0)
+  int32_t rw_ref[kMaxState];   // reference slot, or kMaxRef for "no reference" (value 0)
   int32_t rw_pow1[kMaxState];  // 1 if power == 1
   real rw_w[kMaxState];
   real rw_inv_len[kMaxState];

