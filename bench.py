@@ -8,9 +8,13 @@ U(-1,1)^3 actions, Wiener references, in-kernel auto-reset; weak scaling: every 
 (keyed by global env index), no data-path collective.
 
 One "step" = one batched env.step = ONE launch of step_kernel over the rank's shard.
- * value    : whole-job env-steps/s with actions resident in HBM; every timed step is bracketed by CUDA events on the
-              launching stream and preceded by an (untimed) L2 flush, so the kernel sees cold L2 like it does behind a
-              policy network.  ms_per_step = mean event time, max over ranks.
+ * value    : whole-job env-steps/s with actions resident in HBM.  The K timed steps run back to back (one CUDA-event pair
+              on the launching stream around all K launches) and rotate over R=4 independent replicas of the 2^20-env batch
+              and 8 action tensors, so that every byte a launch touches was last touched >= 3 launches (~500 MB of traffic,
+              4x the 126 MB L2) earlier: inputs larger than L2, no flush kernels inside the timed region.
+              ms_per_step = event time / K, max over ranks.
+ * cold_events : the same step timed one launch at a time (CUDA events around every launch, 256 MiB L2 flush before it);
+              includes ~8 us of event/launch overhead per step and is reported for reference.
  * e2e      : same metric through the public host-buffer entry point (gemb200_step_host): pinned host actions -> H2D ->
               launch -> D2H of obs/ref/reward/terminated -> sync, every step.
  * roofline : algorithmic bytes per env-step (SURVEY.md §8d, 129 B for PMSM) * envs / mean kernel time vs the measured
@@ -47,7 +51,7 @@ def workload_config(n_envs, n_gpus):
     return {"workload": f"{ENV_ID} x {n_envs} envs/GPU, RK4 x1 per tau=1e-4, ContB6 + IdealSupply + ConstantSpeedLoad(100 rad/s), "
                         "Wiener refs (i_sd,i_sq) + WSE reward + SquaredConstraint fused, same-step auto-reset",
             "env_id": ENV_ID, "envs_per_gpu": n_envs, "global_envs": n_envs * n_gpus, "solver": "rk4x1", "tau": 1e-4,
-            "parallelism": f"env-shard x{n_gpus} (no collective)", "l2": "flushed (256 MiB memset) before every timed step",
+            "parallelism": f"env-shard x{n_gpus} (no collective)", "l2": "inputs larger than L2: timed steps rotate over 4 replicas of the env batch (4 x 166 MB touched per cycle), back-to-back launches",
             "layout": "obs [N,14] row-per-env (AoS), state SoA"}
 
 
@@ -195,9 +199,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs_per_gpu
-    env = make_env(n, device=local_rank, rank=rank)
+    R = 4  # replicas of the env batch that the timed steps rotate over (working set >> L2)
+    envs = [make_env(n, device=local_rank, rank=rank * R + r) for r in range(R)]
+    env = envs[0]
     sim = env.sim
-    env.reset()
+    for e in envs:
+        e.reset()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = [torch.rand((n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1 for _ in range(8)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -208,33 +215,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm: one launch per step, per-step CUDA events, L2 flushed before each ----------------
-    for k in range(W):
-        flush.zero_()
-        env.step(pool[k % 8])
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    # ---------------- device-resident arm: K back-to-back launches rotating over R replicas, one event pair ----------------
+    for k in range(max(W, R)):
+        envs[k % R].step(pool[k % 8])
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
-    l0 = sim.launch_count
+    l0 = sum(e.sim.launch_count for e in envs)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
+    ev0.record()
+    for k in range(K):
+        envs[k % R].step(pool[k % 8])
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = sum(e.sim.launch_count for e in envs) - l0
+    ms = ev0.elapsed_time(ev1)
+    # ---------------- one launch at a time: events around every launch, L2 flushed before it (reference figure) ----------------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for k in range(K):
         flush.zero_()
         evs[k][0].record()
         env.step(pool[k % 8])
         evs[k][1].record()
     barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = sim.launch_count - l0
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    # ---------------- same, hot L2 / back-to-back (reported for information) ----------------
-    barrier()
-    sim.time_begin()
-    for k in range(K):
-        env.step(pool[k % 8])
-    ms_hot = sim.time_end()
-    barrier()
+    ms_hot = sum(a.elapsed_time(b) for a, b in evs)
     # ---------------- e2e arm: host buffers through the C-ABI ----------------
     h_act = [torch.rand((n, 3), dtype=torch.float32).mul_(2).sub_(1).pin_memory() for _ in range(2)]
     h_obs = torch.empty((n, 14), dtype=torch.float32).pin_memory()
@@ -275,7 +282,8 @@ def main():
                     "api": "gemb200_step_host via VectorSim.step_host_ptr (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "hot_l2": {"value": total_envs * K / (ms_hot * 1e-3), "ms_per_step": ms_hot / K, "note": "back-to-back launches, no flush"},
+            "cold_events": {"value": total_envs * K / (ms_hot * 1e-3), "ms_per_step": ms_hot / K,
+                            "note": "one launch at a time, CUDA events around each launch, 256 MiB L2 flush before it"},
             "wall_ms_timed_region": t_wall * 1e3,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -74,6 +74,11 @@ class GemB200Config(C.Structure):
         ("ref_len_hi", C.c_int32 * MAX_REF),
         ("seed", C.c_uint64),
         ("env_index_offset", C.c_int64),
+        ("action_dq", C.c_int32),
+        ("dead_time_steps", C.c_int32),
+        ("dead_time_outer", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("angle_advance", C.c_double),
     ]
 
 
@@ -112,7 +117,8 @@ SYMBOLS = [
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    # GEMB200_LIB: developer override used by tools/variant_bench.py to load an experimental build of the SAME library
+    return os.environ.get("GEMB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class GemB200Error(RuntimeError):

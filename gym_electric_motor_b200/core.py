@@ -61,9 +61,7 @@ class ElectricMotorEnvironment:
 
     def __init__(self, physical_system, reference_generator, reward_function, visualization=(), state_filter=None, callbacks=(),
                  constraints=(), physical_system_wrappers=(), scale_plots=False, num_envs=None, autoreset=None, seed=None, **kwargs):
-        if len(tuple(physical_system_wrappers)) > 0:
-            raise NotImplementedError("physical_system_wrappers are not on the device path yet (SURVEY.md §8f row 1); "
-                                      "CurrentSumProcessor of the ShuntDc envs is built in")
+        physical_system.apply_wrappers(tuple(physical_system_wrappers))  # fused into the kernel (physical_system_wrappers.py)
         if not isinstance(reference_generator, ReferenceGenerator):
             raise TypeError("reference_generator must be a built-in gym_electric_motor_b200 ReferenceGenerator")
         if not isinstance(reward_function, RewardFunction):

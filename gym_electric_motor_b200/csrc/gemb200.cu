@@ -36,12 +36,16 @@ struct gemb200_handle {
   void* d_st = nullptr;
   double* d_eps = nullptr;
   uint16_t* d_sw = nullptr;
+  void* d_fifo = nullptr;
+  int fifo_dim = 0;
   StepParams<float> pf;
   StepParams<double> pd;
   uint64_t gstep = 0;
+  uint64_t n_steps = 0;  // step calls so far (dead-time ring position)
   int64_t launches = 0;
   // host-buffer path
   cudaStream_t hstream = nullptr;
+  cudaStream_t hpipe[3] = {nullptr, nullptr, nullptr};
   void *d_act = nullptr, *d_obs = nullptr, *d_ref = nullptr, *d_rew = nullptr;
   uint8_t *d_term = nullptr, *d_mask = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -68,6 +72,10 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
     default: return fail(GEMB200_E_INVALID, "unknown motor_kind");
   }
   const bool three_phase = d->fam >= kSYNC;
+  if (c->action_dq) {
+    if (!three_phase || c->finite) return fail(GEMB200_E_INVALID, "dq actions need a three-phase motor with a continuous converter");
+    d->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2;
+  }
   if (three_phase) {
     if (k0 != GEMB200_CONV_B6) return fail(GEMB200_E_INVALID, "three-phase motors need a B6 bridge in converter slot 0");
     if (c->motor_kind == GEMB200_MOTOR_EESM) {
@@ -96,6 +104,7 @@ static int validate(const gemb200_config* c) {
   if (c->interlocking_time < 0 || c->interlocking_time >= c->tau) return fail(GEMB200_E_INVALID, "interlocking_time must be in [0, tau)");
   if (c->load_kind != GEMB200_LOAD_CONST_SPEED && c->load_kind != GEMB200_LOAD_POLY_STATIC) return fail(GEMB200_E_INVALID, "bad load_kind");
   if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
+  if (c->dead_time_steps < 0 || c->dead_time_steps > GEMB200_MAX_DEAD_TIME) return fail(GEMB200_E_INVALID, "dead_time_steps out of range");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
   Dims d;
   int rc = derive_dims(c, &d);
@@ -244,6 +253,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   const gemb200_config& c = h->cfg;
   std::memset(p, 0, sizeof(*p));
   p->n = c.n_envs;
+  p->env_begin = 0; p->env_end = c.n_envs;
   p->env_offset = c.env_index_offset;
   p->seed_lo = (uint32_t)c.seed; p->seed_hi = (uint32_t)(c.seed >> 32);
   p->st = static_cast<real*>(h->d_st);
@@ -251,6 +261,10 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->sw = h->d_sw;
   p->layout = c.layout;
   p->n_act = dm.n_act;
+  p->fifo = static_cast<real*>(h->d_fifo);
+  p->action_dq = c.action_dq;
+  p->dead_steps = c.dead_time_steps; p->dead_outer = c.dead_time_outer; p->fifo_dim = h->fifo_dim; p->fifo_slot = 0;
+  p->adv_k = (real)(c.angle_advance * c.tau * c.motor_param[GEMB200_MP_P] * (sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0));
   p->inv_nsteps = (real)(1.0 / c.solver_nsteps);
   p->motor_kind = c.motor_kind;
   p->conv_kind[0] = c.converter_kind[0]; p->conv_kind[1] = c.converter_kind[1];
@@ -259,7 +273,20 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->two_segment = h->two_segment;
   p->tau = (real)c.tau; p->til = (real)c.interlocking_time; p->til_over_tau = (real)(c.interlocking_time / c.tau);
   p->u_sup = (real)c.u_sup;
-  p->pole_pairs = c.motor_param[GEMB200_MP_P];
+  {  // angle increment factors (see StepParams::kang): segments 0 = tau, 1 = interlocking time, 2 = tau - interlocking time
+    const double pp = c.motor_param[GEMB200_MP_P];
+    const double hs[3] = {c.tau, c.interlocking_time, c.tau - c.interlocking_time};
+    const double unit = sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0;  // fp32 build keeps the angle in turns
+    for (int sidx = 0; sidx < 3; ++sidx) {
+      const double k_tot = pp * hs[sidx] * unit;
+      const double k_sub = pp * (hs[sidx] / c.solver_nsteps) * (c.solver_kind == GEMB200_SOLVER_RK4 ? 1.0 / 6.0 : 1.0) * unit;
+      const double ks[2] = {k_tot, k_sub};
+      for (int m = 0; m < 2; ++m) {
+        p->kang[m][sidx][0] = (real)ks[m];
+        p->kang[m][sidx][1] = (real)(ks[m] - (double)p->kang[m][sidx][0]);
+      }
+    }
+  }
   for (int j = 0; j < 20; ++j) p->c[j] = (real)dv.c[j];
   for (int j = 0; j < 4; ++j) p->tq[j] = (real)dv.tq[j];
   p->load_a = (real)c.load_param[GEMB200_LP_A]; p->load_b = (real)c.load_param[GEMB200_LP_B]; p->load_c = (real)c.load_param[GEMB200_LP_C];
@@ -273,10 +300,24 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     double e = c.init_ode[dm.nx];
     e = e - 2 * M_PI * std::rint(e / (2 * M_PI));
     if (e <= -M_PI) e += 2 * M_PI;
-    p->init_eps = e;
+    const int eps_idx = dm.n_state - 2;  // [..., epsilon, u_sup]
+    if (sizeof(real) == 4) {
+      const double t = e / (2 * M_PI);
+      p->init_ang[0] = (real)t; p->init_ang[1] = (real)(t - (double)p->init_ang[0]);
+      p->eps_out_scale = (real)(2 * M_PI / c.limits[eps_idx]);
+    } else {
+      p->init_ang[0] = (real)e; p->init_ang[1] = real(0);
+      p->eps_out_scale = (real)(1.0 / c.limits[eps_idx]);
+    }
+    p->inv_lim[eps_idx] = real(1);  // the angle entry is already normalised by eps_out_scale
   }
   p->n_constraints = c.n_constraints;
-  for (int i = 0; i < c.n_constraints; ++i) { p->con_kind[i] = c.constraint_kind[i]; p->con_mask[i] = c.constraint_mask[i] & ((1u << dm.n_state) - 1u); }
+  for (int i = 0; i < c.n_constraints; ++i) {
+    p->con_kind[i] = c.constraint_kind[i];
+    int cnt = 0;
+    for (int j = 0; j < dm.n_state; ++j) if ((c.constraint_mask[i] >> j) & 1u) p->con_idx[i][cnt++] = (uint8_t)j;
+    p->con_cnt[i] = cnt;
+  }
   // WeightedSumOfErrors: only non-zero weights become terms (weighted_sum_of_errors.py:128-129)
   int t = 0;
   for (int j = 0; j < dm.n_state; ++j) {
@@ -310,19 +351,40 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
 // ----------------------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int kBlock = 256;
+constexpr int kBlock = GEMB200_BLOCK;
 
+#ifndef GEMB200_PERSISTENT
+#define GEMB200_PERSISTENT 0  /* measured slower, see the note in step_kernel */
+#endif
+
+// Persistent launch shape: at most as many CTAs as can be resident (SMs x occupancy), each thread looping over
+// ceil(range / resident threads) envs; the grid is then shrunk so that every thread gets the same trip count (no tail wave).
 template <int FAM, bool FINITE, typename real, int NREF>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
-  const int grid = (p.n + kBlock - 1) / kBlock;
   const size_t smem = ((size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD + (size_t)kBlock * kRefPad) * sizeof(real);
+  const int range = p.env_end - p.env_begin;
+  int grid = (range + kBlock - 1) / kBlock;
+#if GEMB200_PERSISTENT
+  static int resident = 0;  // per template instantiation
+  if (resident == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<FAM, FINITE, real, NREF>, kBlock, smem);
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  if (grid > resident) {
+    const int iters = (grid + resident - 1) / resident;
+    grid = (grid + iters - 1) / iters;
+  }
+#endif
   step_kernel<FAM, FINITE, real, NREF><<<grid, kBlock, smem, st>>>(p);
   return cudaGetLastError();
 }
 template <int FAM, typename real, int NREF>
 static cudaError_t launch_reset_t(const StepParams<real>& p, cudaStream_t st) {
-  const int grid = (p.n + kBlock - 1) / kBlock;
-  reset_kernel<FAM, real, NREF><<<grid, kBlock, 0, st>>>(p);
+  const int grid = (p.n + 255) / 256;
+  reset_kernel<FAM, real, NREF><<<grid, 256, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -376,17 +438,24 @@ static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cu
   return cudaErrorInvalidValue;
 }
 
-static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, void* rew, uint8_t* term, cudaStream_t st) {
+// One launch over envs [begin, end) (end < 0: all).  new_call: this launch starts a new API call (fresh RNG call id);
+// the chunks of one pipelined host step share the id.
+static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, void* rew, uint8_t* term, cudaStream_t st,
+                   int begin = 0, int end = -1, bool new_call = true) {
   if (!action) return fail(GEMB200_E_INVALID, "action is NULL");
-  h->gstep += 1;
+  if (new_call) { h->gstep += 1; h->n_steps += 1; }
+  if (end < 0) end = h->cfg.n_envs;
+  const int fifo_slot = h->cfg.dead_time_steps > 0 ? (int)((h->n_steps - 1) % (uint64_t)h->cfg.dead_time_steps) : 0;
   cudaError_t e;
   if (h->cfg.dtype == GEMB200_F32) {
     StepParams<float>& p = h->pf;
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
     e = launch_step<float>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   } else {
     StepParams<double>& p = h->pd;
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
     e = launch_step<double>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
@@ -490,6 +559,12 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   } while (0)
   h->W = state_words(d.nx, cfg->n_ref);
   ALLOC(h->d_st, n * h->W * h->rsz);
+  if (cfg->dead_time_steps > 0) {
+    // queue width: caller-side actions when the dead time wraps the dq transformation (or there is none), else abc(+e)
+    const int inner = cfg->finite ? d.n_act : (d.fam == kEESM ? 4 : (d.fam >= kSYNC ? 3 : d.n_act));
+    h->fifo_dim = (cfg->action_dq && !cfg->dead_time_outer) ? inner : d.n_act;
+    ALLOC(h->d_fifo, n * cfg->dead_time_steps * h->fifo_dim * h->rsz);
+  }
   if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
   if (h->two_segment) ALLOC(h->d_sw, n * sizeof(uint16_t));
 #undef ALLOC
@@ -510,9 +585,10 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_eps); cudaFree(h->d_sw);
+  cudaFree(h->d_st); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
+  for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -550,6 +626,7 @@ static int ensure_host_buffers(gemb200_handle* h) {
   if (h->hstream) return GEMB200_OK;
   const size_t n = (size_t)h->cfg.n_envs;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  for (int k = 0; k < 3; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&h->hpipe[k], cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&h->d_act, n * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz)));
   CUDA_TRY(cudaMalloc(&h->d_obs, n * h->n_state * h->rsz));
   CUDA_TRY(cudaMalloc(&h->d_ref, n * (h->n_ref > 0 ? h->n_ref : 1) * h->rsz));
@@ -566,11 +643,35 @@ int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void
   int rc = ensure_host_buffers(h);
   if (rc) return rc;
   const size_t n = (size_t)h->cfg.n_envs;
+  const size_t asz = (size_t)h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz);  // action bytes per env
+  // Row-per-env buffers are contiguous per env range, so a large batch is cut into chunks that flow through three
+  // streams: the D2H of chunk c overlaps the H2D + launch of chunk c+1 (PCIe is full duplex).  One API call = one RNG id.
+  const bool pipelined = h->cfg.layout == GEMB200_LAYOUT_AOS && n >= (size_t)1 << 16;
+  const int nchunk = pipelined ? 8 : 1;
+  const size_t per = pipelined ? ((n / nchunk + 255) / 256) * 256 : n;
+  bool first = true;
+  for (int c = 0; c < nchunk; ++c) {
+    const size_t b = (size_t)c * per, e = (b + per < n) ? b + per : n;
+    if (b >= e) break;
+    cudaStream_t st = pipelined ? h->hpipe[c % 3] : h->hstream;
+    CUDA_TRY(cudaMemcpyAsync((char*)h->d_act + b * asz, (const char*)action + b * asz, (e - b) * asz, cudaMemcpyHostToDevice, st));
+    rc = do_step(h, h->d_act, obs_out ? h->d_obs : nullptr, (ref_out && h->n_ref) ? h->d_ref : nullptr, reward_out ? h->d_rew : nullptr,
+                 terminated_out ? h->d_term : nullptr, st, (int)b, (int)e, first);
+    first = false;
+    if (rc) return rc;
+    if (pipelined) {
+      const size_t os = (size_t)h->n_state * h->rsz, rs = (size_t)h->n_ref * h->rsz;
+      if (obs_out) CUDA_TRY(cudaMemcpyAsync((char*)obs_out + b * os, (char*)h->d_obs + b * os, (e - b) * os, cudaMemcpyDeviceToHost, st));
+      if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync((char*)ref_out + b * rs, (char*)h->d_ref + b * rs, (e - b) * rs, cudaMemcpyDeviceToHost, st));
+      if (reward_out) CUDA_TRY(cudaMemcpyAsync((char*)reward_out + b * h->rsz, (char*)h->d_rew + b * h->rsz, (e - b) * h->rsz, cudaMemcpyDeviceToHost, st));
+      if (terminated_out) CUDA_TRY(cudaMemcpyAsync(terminated_out + b, h->d_term + b, e - b, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  if (pipelined) {
+    for (int k = 0; k < 3; ++k) CUDA_TRY(cudaStreamSynchronize(h->hpipe[k]));
+    return GEMB200_OK;
+  }
   cudaStream_t st = h->hstream;
-  CUDA_TRY(cudaMemcpyAsync(h->d_act, action, n * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz), cudaMemcpyHostToDevice, st));
-  rc = do_step(h, h->d_act, obs_out ? h->d_obs : nullptr, (ref_out && h->n_ref) ? h->d_ref : nullptr, reward_out ? h->d_rew : nullptr,
-               terminated_out ? h->d_term : nullptr, st);
-  if (rc) return rc;
   if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_state * h->rsz, cudaMemcpyDeviceToHost, st));
   if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(ref_out, h->d_ref, n * h->n_ref * h->rsz, cudaMemcpyDeviceToHost, st));
   if (reward_out) CUDA_TRY(cudaMemcpyAsync(reward_out, h->d_rew, n * h->rsz, cudaMemcpyDeviceToHost, st));
@@ -643,7 +744,7 @@ int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream)
   return GEMB200_OK;
 }
 
-// checkpoint blob: [gstep u64][packed records][eps][sw]
+// checkpoint blob: [gstep u64][n_steps u64][packed records][eps][sw][dead-time queue]
 struct Section { void* ptr; size_t bytes; };
 static int sections(gemb200_handle* h, Section* s) {
   const size_t n = (size_t)h->cfg.n_envs;
@@ -651,13 +752,14 @@ static int sections(gemb200_handle* h, Section* s) {
   s[k++] = {h->d_st, n * h->W * h->rsz};
   if (h->d_eps) s[k++] = {h->d_eps, n * sizeof(double)};
   if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
+  if (h->d_fifo) s[k++] = {h->d_fifo, n * h->cfg.dead_time_steps * h->fifo_dim * h->rsz};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {
   if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
   Section s[8];
   const int k = sections(h, s);
-  int64_t total = 8;
+  int64_t total = 16;
   for (int i = 0; i < k; ++i) total += (int64_t)s[i].bytes;
   return total;
 }
@@ -667,6 +769,7 @@ int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
   CUDA_TRY(cudaDeviceSynchronize());
   char* b = (char*)host_blob;
   std::memcpy(b, &h->gstep, 8); b += 8;
+  std::memcpy(b, &h->n_steps, 8); b += 8;
   Section s[8];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(b, s[i].ptr, s[i].bytes, cudaMemcpyDeviceToHost)); b += s[i].bytes; }
@@ -678,6 +781,7 @@ int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob) {
   CUDA_TRY(cudaDeviceSynchronize());
   const char* b = (const char*)host_blob;
   std::memcpy(&h->gstep, b, 8); b += 8;
+  std::memcpy(&h->n_steps, b, 8); b += 8;
   Section s[8];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(s[i].ptr, b, s[i].bytes, cudaMemcpyHostToDevice)); b += s[i].bytes; }

@@ -47,6 +47,7 @@ template <typename real>
 struct StepParams {
   // ---- batch ----
   int32_t n;              // envs in this handle
+  int32_t env_begin, env_end;  // sub-range of envs processed by this launch (chunked host-buffer pipeline); default [0, n)
   int64_t env_offset;     // global index of env 0 (sharding)
   uint32_t seed_lo, seed_hi;
   uint32_t gstep_lo, gstep_hi;  // unique id of this API call (reset or step): RNG counter words 0,1
@@ -57,6 +58,7 @@ struct StepParams {
   real* st;
   double* eps;            // [n]       electrical angle, wrapped to (-pi, pi]; nullptr for DC
   uint16_t* sw;           // [n] finite 2QC switching states, 2 bits per leg; nullptr unless finite && interlock
+  real* fifo;             // [dead_steps][fifo_dim][n] DeadTimeProcessor action queue (ring, slot fifo_slot is oldest = next to overwrite)
   // ---- I/O of this call (caller-owned) ----
   const void* action;
   real* obs;
@@ -74,23 +76,33 @@ struct StepParams {
   int32_t layout;         // gemb200_layout of the I/O tensors
   int32_t n_act;
   int32_t two_segment;    // finite && interlocking_time > 0
+  int32_t action_dq;      // action given in dq coordinates (see gemb200_config::action_dq)
+  int32_t dead_steps, dead_outer, fifo_dim, fifo_slot;
+  real adv_k;             // angle advance per (rad/s) of omega, in the stored angle unit: angle_advance * tau * p (/2pi in turns)
   real inv_nsteps;
   real tau;               // step
   real til;               // interlocking time
   real til_over_tau;
   real u_sup;
-  double pole_pairs;      // d eps / dt = p * omega, accumulated in double
+  // Electrical angle: d eps/dt = p * omega.  fp64 build: radians in a double.  fp32 build: TURNS as an unevaluated sum of two
+  // floats (hi, lo) — "double-float", ~48 bits — so that neither fp64 arithmetic nor fp64<->fp32 conversions (slow XU-pipe
+  // instructions on B200) are needed.  kang[m][s] = factor that turns the integrator's omega sum of segment s
+  // (0: whole tau, 1: interlock part, 2: rest) into the angle increment; m = 0: constant speed (sum = omega, factor = p*h_seg),
+  // m = 1: sum over sub-steps (factor = p*h or p*h/6 for RK4); units: turns (fp32 build) or radians (fp64 build); [..][2] = hi, lo.
+  real kang[2][3][2];
+  real eps_out_scale;     // normalised angle output = (hi + lo) * eps_out_scale  (2*pi/limit in turns, 1/limit in radians)
+  real init_ang[2];       // initial angle in the stored representation
   real c[20];             // motor model coefficients (sparse layout per family, see fill_motor_coeffs)
   real tq[4];             // torque coefficients
   real load_a, load_b, load_c, inv_j, omega_lim, omega_lin;
   real inv_lim[kMaxState];
   real init_x[kMaxX];
-  double init_eps;
   real reset_obs[kMaxState];  // observation right after a reset (constant initial state)
   // ---- constraint monitor ----
   int32_t n_constraints;
   int32_t con_kind[kMaxConstraints];
-  uint32_t con_mask[kMaxConstraints];
+  int32_t con_cnt[kMaxConstraints];
+  uint8_t con_idx[kMaxConstraints][kMaxState];  // observed state indices per constraint
   // ---- reward: sum over n_rw terms  w * (|s[idx] - ref| * inv_len)^pow ----
   int32_t n_rw;
   int32_t rw_state[kMaxState];

@@ -101,6 +101,35 @@ class SCMLSystem(PhysicalSystem):
         self._mechanical_load.check_initial_state(self._nominal_state, self._state_space.low, self._state_positions)
         self._sim = None
         self._owns_sim = False
+        self._action_dq, self._angle_advance, self._dead_steps, self._dead_outer = 0, 0.0, 0, 0
+
+    def apply_wrappers(self, wrappers):
+        """Fuse reference-style physical_system_wrappers into the kernel configuration (see physical_system_wrappers.py).
+        The list order has the reference's meaning: each entry wraps the system built from the previous ones."""
+        from ..physical_system_wrappers import CurrentSumProcessor, DeadTimeProcessor, DqToAbcActionProcessor
+        from .converters import FiniteConverter
+        from .electric_motors import DcShuntMotor, ExternallyExcitedSynchronousMotor, SynchronousMotor
+
+        for w in wrappers:
+            if isinstance(w, CurrentSumProcessor):
+                if not isinstance(self._electrical_motor, DcShuntMotor):
+                    raise NotImplementedError("CurrentSumProcessor is only built in for the shunt DC motor")
+            elif isinstance(w, DeadTimeProcessor):
+                if self._dead_steps:
+                    raise NotImplementedError("only one DeadTimeProcessor is supported")
+                self._dead_steps = w.dead_time
+                self._dead_outer = 1 if self._action_dq else 0  # it wraps an existing dq transformation -> queue of dq actions
+            elif isinstance(w, DqToAbcActionProcessor):
+                if not isinstance(self._electrical_motor, SynchronousMotor) or isinstance(self._converter, FiniteConverter):
+                    raise NotImplementedError("DqToAbcActionProcessor needs a PMSM/SynRM/EESM system with a continuous converter")
+                if self._action_dq:
+                    raise NotImplementedError("the system already takes dq actions")
+                self._action_dq = 1
+                self._angle_advance = 0.5 + self._dead_steps  # dq_to_abc_action_processor.py:69-72
+                self._action_space = w.action_space(isinstance(self._electrical_motor, ExternallyExcitedSynchronousMotor))
+            else:
+                raise NotImplementedError(f"{type(w).__name__} is not a device-side physical-system wrapper")
+        return self
 
     # ------------------------------------------------------------------ reference-compatible properties
     @property
@@ -179,6 +208,10 @@ class SCMLSystem(PhysicalSystem):
             cfg.limits[i] = float(v)
         for i, v in enumerate(self.initial_ode_state()):
             cfg.init_ode[i] = float(v)
+        cfg.action_dq = int(self._action_dq)
+        cfg.angle_advance = float(self._angle_advance)
+        cfg.dead_time_steps = int(self._dead_steps)
+        cfg.dead_time_outer = int(self._dead_outer)
         return cfg
 
     def attach(self, sim, owns=False):
@@ -280,10 +313,18 @@ class ThreePhaseMotorSystem(SCMLSystem):
     _NAMES = []
 
     def __init__(self, control_space="abc", **kwargs):
-        if control_space != "abc":
-            raise NotImplementedError("control_space='dq' (physical_systems.py:423-435) is not on the device path yet (SURVEY.md §8f row 2)")
+        assert control_space in ("abc", "dq")
         self.control_space = control_space
         super().__init__(**kwargs)
+        if control_space == "dq":  # physical_systems.py:423-435, :491-492 (SCIM :779-780): a_abc = T32 q(a_dq, angle), no advance
+            from .converters import FiniteConverter
+            from .electric_motors import ExternallyExcitedSynchronousMotor
+
+            assert not isinstance(self._converter, FiniteConverter), "dq-control space is only available for Continuous Controlled Converters"
+            if isinstance(self._electrical_motor, ExternallyExcitedSynchronousMotor):
+                raise NotImplementedError("the reference's EESM system ignores control_space='dq' in simulate (physical_systems.py:619-657)")
+            self._action_dq, self._angle_advance = 1, 0.0
+            self._action_space = Box(-1, 1, shape=(2,), dtype=np.float64)
 
     def _build_state_names(self):
         return self._mechanical_load.state_names + list(self._NAMES)

@@ -30,6 +30,7 @@ extern "C" {
 #define GEMB200_MAX_ODE 8      /* SCIM: omega + 4 + eps = 6 */
 #define GEMB200_MAX_ACT 4      /* EESM: 3 (B6) + 1 (4QC) */
 #define GEMB200_MAX_REF 4
+#define GEMB200_MAX_DEAD_TIME 8
 #define GEMB200_MAX_CONSTRAINTS 4
 #define GEMB200_MAX_MOTOR_PARAM 16
 
@@ -158,6 +159,17 @@ typedef struct gemb200_config {
 
   uint64_t seed;            /* Philox key; streams are keyed by (seed, global env index) */
   int64_t env_index_offset; /* global index of env 0 of this handle (rank*N_local when sharded) */
+
+  /* Action pre-processing of the three-phase systems (continuous converters only):
+   * action_dq = 1: the action is given in dq coordinates (2 values, EESM: + u_e) and transformed in the kernel with
+   *   a_abc = T32 * q(a_dq, eps + angle_advance * tau * omega * p)
+   * angle_advance = 0   : SynchronousMotorSystem(control_space='dq') physical_systems.py:423-435,:491-492 (SCIM: field angle :779-780)
+   * angle_advance = 0.5 (+ dead-time steps): physical_system_wrappers/dq_to_abc_action_processor.py:74-95 */
+  int32_t action_dq;
+  int32_t dead_time_steps;  /* DeadTimeProcessor(steps) physical_system_wrappers/dead_time_processor.py: action FIFO, 0 = off */
+  int32_t dead_time_outer;  /* 1: the dead-time FIFO holds the caller's (dq) actions, 0: the transformed (abc) ones */
+  int32_t reserved0;
+  double angle_advance;
 } gemb200_config;
 
 typedef struct gemb200_handle gemb200_handle;

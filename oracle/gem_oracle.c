@@ -51,6 +51,7 @@ typedef struct {
   double ref_value[GEMB200_MAX_REF];
   double ref_sigma[GEMB200_MAX_REF];
   int ref_left[GEMB200_MAX_REF];
+  double fifo[GEMB200_MAX_DEAD_TIME][GEMB200_MAX_ACT]; /* DeadTimeProcessor queue (ring; slot = call counter mod steps) */
 } env_t;
 
 typedef struct gem_oracle {
@@ -65,6 +66,7 @@ typedef struct gem_oracle {
   double l_M, i_k_rs;
   double tq0; /* SCIM torque factor */
   uint64_t gstep; /* id of the current API call (RNG counter) */
+  uint64_t n_steps; /* step calls so far (dead-time ring position) */
   env_t* env;
 } gem_oracle;
 
@@ -137,6 +139,7 @@ static int dims(gem_oracle* o) {
   o->slot_off[1] = o->n_sub[0];
   if (c->finite) o->n_act = (c->converter_kind[0] != 0) + (c->converter_kind[1] != 0);
   else o->n_act = slot_nvolt(c->converter_kind[0]) + slot_nvolt(c->converter_kind[1]);
+  if (c->action_dq) o->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2; /* dq_to_abc_action_processor.py:97-99,:143-145 */
   o->n_ref = c->n_ref;
   return 0;
 }
@@ -705,6 +708,7 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
   conv_reset(o, e, u_abc);
   for (int j = 0; j < 4; ++j) u_abc[j] *= c->u_sup;
   e->t = 0; e->k = 0;
+  memset(e->fifo, 0, sizeof(e->fifo)); /* DeadTimeProcessor.reset dead_time_processor.py:68-78: queue of zero actions */
   double tq = torque(o, y + 1);
   int n = 0;
   state[n++] = y[0];
@@ -880,6 +884,37 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
   double st[GEMB200_MAX_STATE], ref_full[GEMB200_MAX_STATE];
   const double* af = o->cfg.finite ? NULL : (const double*)action + i * o->n_act;
   const int32_t* ai = o->cfg.finite ? (const int32_t*)action + i * o->n_act : NULL;
+  /* physical-system wrappers (core.py:266-267): DeadTimeProcessor and DqToAbcActionProcessor in either order */
+  double abuf[GEMB200_MAX_ACT] = {0, 0, 0, 0};
+  int32_t ibuf[2] = {0, 0};
+  const gemb200_config* c = &o->cfg;
+  const int slot = c->dead_time_steps > 0 ? (int)((o->n_steps - 1) % (uint64_t)c->dead_time_steps) : 0;
+  if (c->finite) {
+    for (int j = 0; j < o->n_act; ++j) ibuf[j] = ai[j];
+    if (c->dead_time_steps > 0) /* dead_time_processor.py:80-90: apply the oldest action, store the new one */
+      for (int j = 0; j < o->n_act; ++j) { int32_t old = (int32_t)e->fifo[slot][j]; e->fifo[slot][j] = ibuf[j]; ibuf[j] = old; }
+    ai = ibuf;
+  } else {
+    int na = o->n_act;
+    for (int j = 0; j < na; ++j) abuf[j] = af[j];
+    if (c->dead_time_steps > 0 && c->dead_time_outer)
+      for (int j = 0; j < na; ++j) { double old = e->fifo[slot][j]; e->fifo[slot][j] = abuf[j]; abuf[j] = old; }
+    if (c->action_dq) {
+      /* _ClassicDqToAbcActionProcessor.simulate :100-106 / _EESM :147-153; angle from the last state vector:
+       * wrapped epsilon + angle_advance * tau * omega * p (:89-91).  control_space='dq' = same with advance 0
+       * (physical_systems.py:491-492); SCIM uses the field angle (:779-780). */
+      double ang, dq[2] = {abuf[0], abuf[1]}, ab[2], ue = abuf[2];
+      if (c->motor_kind == GEMB200_MOTOR_SCIM) ang = atan2(e->ode[4], e->ode[3]);
+      else ang = wrap_eps(e->ode[o->n_ode - 1]) + c->angle_advance * c->tau * e->ode[0] * c->motor_param[GEMB200_MP_P];
+      q_rot(dq, ang, ab);
+      t_32(ab, abuf);
+      na = 3;
+      if (c->motor_kind == GEMB200_MOTOR_EESM) { abuf[3] = ue; na = 4; }
+    }
+    if (c->dead_time_steps > 0 && !c->dead_time_outer)
+      for (int j = 0; j < na; ++j) { double old = e->fifo[slot][j]; e->fifo[slot][j] = abuf[j]; abuf[j] = old; }
+    af = abuf;
+  }
   simulate(o, e, af, ai, st);                                   /* core.py:344 */
   memset(ref_full, 0, sizeof(ref_full));
   for (int r = 0; r < o->n_ref; ++r) ref_full[o->cfg.ref_state[r]] = e->ref_value[r]; /* core.py:346 */
@@ -909,6 +944,7 @@ static void* step_range(void* arg) {
 void gem_oracle_step(gem_oracle* o, const void* action, double* obs, double* ref_next, double* rew, uint8_t* term, int nthreads) {
   int64_t n = o->cfg.n_envs;
   o->gstep += 1;
+  o->n_steps += 1;
   if (nthreads > n) nthreads = (int)n;
   if (nthreads <= 1) {
     job_t j = {o, action, obs, ref_next, rew, term, 0, n};

@@ -131,6 +131,7 @@ def describe(env, case):
     conv = p.converter
     meta = dict(
         case=case,
+        action_dim=int(np.prod(getattr(env.action_space, "shape", ()) or (1,))),
         state_names=list(p.state_names),
         limits=p.limits.tolist(),
         nominal_state=p.nominal_state.tolist(),
@@ -175,8 +176,13 @@ def record(case):
         kwargs["tau"] = case["tau"]
     if case.get("converter_cls") is not None:
         kwargs["converter"] = getattr(ps, case["converter_cls"])(**case.get("converter_args", {}))
-    if case.get("no_wrappers"):
-        kwargs["physical_system_wrappers"] = ()
+    if case.get("wrappers"):
+        from gym_electric_motor.physical_system_wrappers import DeadTimeProcessor, DqToAbcActionProcessor
+
+        ws = []
+        for kind, arg in case["wrappers"]:
+            ws.append(DeadTimeProcessor(steps=arg) if kind == "DeadTime" else DqToAbcActionProcessor.make(arg))
+        kwargs["physical_system_wrappers"] = ws
     env = gem.make(case["env_id"], visualization=NoViz(), ode_solver=make_solver(case["solver"]), **kwargs)
     K = case["steps"]
     actions = action_sequence(env, K, case["seed"], case.get("style", "mixed"))
@@ -285,6 +291,13 @@ CASES = [
     # non-default parameters: load polynomial with all terms, custom motor, non-zero constant initial state
     C("pmsm_sc_polyload_rk4", "Cont-SC-PMSM-v0", "rk4", steps=1500,
       load=dict(load_parameter=dict(a=0.5, b=0.02, c=1e-4, j_load=2e-3))),
+    # physical-system wrappers: dq actions with angle advance, dead time, both orders
+    C("pmsm_cc_dq_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500, wrappers=[("DqToAbc", "PMSM")]),
+    C("pmsm_sc_dq_dead2_rk4", "Cont-SC-PMSM-v0", "rk4", steps=1500, wrappers=[("DeadTime", 2), ("DqToAbc", "PMSM")]),
+    C("pmsm_cc_dead1_outer_dq_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500, wrappers=[("DqToAbc", "PMSM"), ("DeadTime", 1)]),
+    C("eesm_cc_dq_rk4", "Cont-CC-EESM-v0", "rk4", steps=1500, wrappers=[("DqToAbc", "EESM")]),
+    C("pmsm_fin_cc_dead3_rk4", "Finite-CC-PMSM-v0", "rk4", steps=1500, wrappers=[("DeadTime", 3)]),
+    C("permex_cc_dead2_rk4", "Cont-CC-PermExDc-v0", "rk4", steps=1000, wrappers=[("DeadTime", 2)]),
     C("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500,
       motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
                  motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0)))),

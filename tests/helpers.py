@@ -131,6 +131,14 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
         cfg.ref_kind[r] = ref_kind
         cfg.ref_state[r] = names.index(rn)
     cfg.seed = seed
+    # physical-system wrappers recorded with the golden (list order = reference order: later entries wrap earlier ones)
+    dq, dead, outer, adv = 0, 0, 0, 0.0
+    for kind, arg in meta["case"].get("wrappers", []) or []:
+        if kind == "DeadTime":
+            dead, outer = int(arg), (1 if dq else 0)
+        else:
+            dq, adv = 1, 0.5 + dead
+    cfg.action_dq, cfg.dead_time_steps, cfg.dead_time_outer, cfg.angle_advance = dq, dead, outer, adv
     return cfg
 
 

@@ -277,3 +277,71 @@ def test_full_size_replication_property(torch_cuda, oracle_lib):
         d = obs[:proto].double().cpu().numpy()
         assert col_rel_err(d, o_obs) < 1e-5 or np.abs(d - o_obs).max() < 1e-6
         assert np.abs(rew[:proto].double().cpu().numpy() - o_rew).max() < 1e-4
+
+
+def test_public_api_scalar_and_batched(torch_cuda):
+    """gem.make surface: scalar (num_envs=None) contract of the reference and the batched contract agree with each other and
+    with the recorded reference trajectory (Cont-CC-PMSM-v0, RK4 plugin golden)."""
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200.reference_generators import ExternalReferenceGenerator, MultipleReferenceGenerator
+
+    g = load_golden("pmsm_cc_rk4")
+
+    def mk(**kw):
+        rg = MultipleReferenceGenerator([ExternalReferenceGenerator("i_sd"), ExternalReferenceGenerator("i_sq")])
+        return gem.make("Cont-CC-PMSM-v0", ode_solver=gem.physical_systems.RK4Solver(), reference_generator=rg, dtype="float64", **kw)
+
+    env1, envn = mk(), mk(num_envs=5)
+    (s, r), info = env1.reset(seed=3)
+    assert s.shape == (14,) and r.shape == (2,) and info == {}
+    np.testing.assert_allclose(s, g["reset_state"], atol=1e-12)
+    (sb, rb), _ = envn.reset(seed=3)
+    assert tuple(sb.shape) == (5, 14) and tuple(rb.shape) == (5, 2)
+    ref_idx = [g["meta"]["state_names"].index(nm) for nm in g["meta"]["reference_names"]]
+    for k in range(40):
+        refs = g["refs_used"][k][ref_idx]
+        env1.set_reference(refs[None, :])
+        envn.set_reference(np.tile(refs, (5, 1)))
+        (s, r), rew, term, trunc, _ = env1.step(g["actions"][k])
+        (sb, rb), rewb, termb, truncb, _ = envn.step(np.tile(g["actions"][k], (5, 1)))
+        assert isinstance(rew, float) and isinstance(term, bool) and trunc is False
+        np.testing.assert_allclose(s, g["states"][k], rtol=0, atol=1e-9)
+        assert rew == pytest.approx(g["rewards"][k], abs=1e-9) and term == bool(g["terminated"][k])
+        np.testing.assert_allclose(sb.cpu().numpy(), np.tile(s, (5, 1)), atol=1e-12)
+        assert termb.dtype == torch_cuda.bool and bool(termb[0]) == term
+        if term:
+            with pytest.raises(AssertionError):
+                env1.step(g["actions"][k])  # core.py:341
+            env1.reset()
+            envn.reset()
+    env1.close()
+    envn.close()
+
+
+def test_mixed_motor_batch(torch_cuda, oracle_lib):
+    """configs[4]: PMSM + SynRM + EESM segmented per type, one launch per type on its own stream; each segment must equal
+    the same env stepped alone."""
+    import torch
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200.mixed import MixedEnvBatch
+
+    RK4 = gem.physical_systems.RK4Solver
+    ids = [("Cont-CC-PMSM-v0", dict(ode_solver=RK4())), ("Cont-CC-SynRM-v0", dict(ode_solver=RK4())), ("Cont-CC-EESM-v0", dict(ode_solver=RK4()))]
+    n = 3 * 700
+    mixed = MixedEnvBatch(ids, n, autoreset="same_step", seed=5)
+    solo = [gem.make(e, num_envs=700, autoreset="same_step", seed=5, env_index_offset=t * 700, **kw) for t, (e, kw) in enumerate(ids)]
+    mixed.reset()
+    for e in solo:
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for k in range(25):
+        acts = [torch.rand((700, 4 if t == 2 else 3), generator=gen, device="cuda") * 2 - 1 for t in range(3)]
+        res = mixed.step(acts)
+        torch.cuda.synchronize()
+        for t in range(3):
+            (s, r), rew, term, _, _ = solo[t].step(acts[t])
+            (sm, rm), rewm, termm, _, _ = res[t]
+            assert torch.equal(s, sm) and torch.equal(r, rm) and torch.equal(rew, rewm) and torch.equal(term, termm)
+    glob = torch.arange(n, device="cuda")
+    parts = mixed.split_interleaved(glob)
+    assert [int(p[1]) for p in parts] == [3, 4, 5]

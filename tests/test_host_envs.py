@@ -120,3 +120,34 @@ def test_kwargs_semantics():
         gem.make("Cont-CC-PMSM-v0", motor=object())
     # default (scipy) solver of the reference maps to RK4 with two sub-steps
     assert gem.make("Cont-CC-PMSM-v0").build_config().solver_nsteps == 2
+
+
+def test_wrapper_descriptors_compile_like_the_reference_stack():
+    """physical_system_wrappers=[...] (reference order semantics) -> kernel flags; compared with the independent translation
+    of the wrapper goldens in tests/helpers.py."""
+    from gym_electric_motor_b200.physical_system_wrappers import DeadTimeProcessor, DqToAbcActionProcessor
+
+    def build(spec):
+        return [DeadTimeProcessor(steps=a) if k == "DeadTime" else DqToAbcActionProcessor.make(a) for k, a in spec]
+
+    for name, env_id in [("pmsm_cc_dq_rk4", "Cont-CC-PMSM-v0"), ("pmsm_sc_dq_dead2_rk4", "Cont-SC-PMSM-v0"),
+                         ("pmsm_cc_dead1_outer_dq_rk4", "Cont-CC-PMSM-v0"), ("eesm_cc_dq_rk4", "Cont-CC-EESM-v0"),
+                         ("pmsm_fin_cc_dead3_rk4", "Finite-CC-PMSM-v0"), ("permex_cc_dead2_rk4", "Cont-CC-PermExDc-v0")]:
+        g = load_golden(name)
+        ref = config_from_meta(g["meta"], reset_ode=g["reset_ode"], solver="rk4")
+        env = gem.make(env_id, ode_solver=gem.physical_systems.RK4Solver(), physical_system_wrappers=build(g["meta"]["case"]["wrappers"]))
+        cfg = env.build_config()
+        for f in ("action_dq", "dead_time_steps", "dead_time_outer", "angle_advance"):
+            assert getattr(cfg, f) == getattr(ref, f), (name, f)
+        assert int(np.prod(getattr(env.action_space, "shape", ()) or (1,))) == g["meta"]["action_dim"]
+    with pytest.raises(NotImplementedError):
+        gem.make("Finite-CC-PMSM-v0", physical_system_wrappers=[DqToAbcActionProcessor.make("PMSM")])
+    with pytest.raises(NotImplementedError):
+        gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[gem.physical_system_wrappers.CosSinProcessor()])
+    # control_space='dq' (physical_systems.py:423-435): same transformation, no angle advance
+    ps_ = gem.physical_systems
+    sys_ = ps_.SynchronousMotorSystem(control_space="dq", supply=ps_.IdealVoltageSupply(300.0), converter=ps_.ContB6BridgeConverter(),
+                                      motor=ps_.PermanentMagnetSynchronousMotor(), load=ps_.ConstantSpeedLoad(omega_fixed=100.0),
+                                      ode_solver=ps_.RK4Solver())
+    c = sys_.fill_config(K.new_config())
+    assert (c.action_dq, c.angle_advance) == (1, 0.0) and sys_.action_space.shape == (2,)
