@@ -77,8 +77,10 @@ class GemB200Config(C.Structure):
         ("action_dq", C.c_int32),
         ("dead_time_steps", C.c_int32),
         ("dead_time_outer", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("init_random", C.c_int32),
         ("angle_advance", C.c_double),
+        ("init_lo", C.c_double * MAX_ODE),
+        ("init_hi", C.c_double * MAX_ODE),
     ]
 
 

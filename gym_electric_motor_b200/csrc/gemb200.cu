@@ -32,8 +32,9 @@ struct gemb200_handle {
   bool has_eps = false, any_wiener = false, two_segment = false;
   size_t rsz = 4;  // sizeof(real)
   // persistent device state
-  int W = 0;  // words per env in the packed record (state_words(nx, n_ref))
+  int NH = 0, NC = 0;  // words per env in the hot / cold record
   void* d_st = nullptr;
+  void* d_stc = nullptr;
   double* d_eps = nullptr;
   uint16_t* d_sw = nullptr;
   void* d_fifo = nullptr;
@@ -105,6 +106,9 @@ static int validate(const gemb200_config* c) {
   if (c->load_kind != GEMB200_LOAD_CONST_SPEED && c->load_kind != GEMB200_LOAD_POLY_STATIC) return fail(GEMB200_E_INVALID, "bad load_kind");
   if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
   if (c->dead_time_steps < 0 || c->dead_time_steps > GEMB200_MAX_DEAD_TIME) return fail(GEMB200_E_INVALID, "dead_time_steps out of range");
+  if (c->init_random && c->motor_kind == GEMB200_MOTOR_SCIM)
+    return fail(GEMB200_E_INVALID, "random initial states are not supported for the induction motor (the reference draws its flux limits "
+                                   "from the unseeded global numpy RNG, squirrel_cage_induction_motor.py:146-157)");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
   Dims d;
   int rc = derive_dims(c, &d);
@@ -117,14 +121,14 @@ static int validate(const gemb200_config* c) {
     if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_EXTERNAL) return fail(GEMB200_E_INVALID, "bad ref_kind");
     if (c->ref_kind[r] == GEMB200_REF_WIENER && (c->ref_len_lo[r] < 1 || c->ref_len_hi[r] < c->ref_len_lo[r] || !(c->ref_sigma_lo[r] > 0)))
       return fail(GEMB200_E_INVALID, "bad Wiener reference ranges");
-    if (c->ref_kind[r] == GEMB200_REF_WIENER && c->ref_len_hi[r] > 65535)
-      return fail(GEMB200_E_INVALID, "sub-episode lengths above 65535 steps are not supported (16-bit counters)");
+    if (c->ref_kind[r] == GEMB200_REF_WIENER && c->ref_len_hi[r] > (1 << 24))
+      return fail(GEMB200_E_INVALID, "sub-episode lengths above 2^24 steps are not supported");
   }
   for (int j = 0; j < d.n_state; ++j)
     if (!(c->limits[j] != 0.0) && !(c->motor_kind == GEMB200_MOTOR_SHUNT_DC && j == 6)) return fail(GEMB200_E_INVALID, "limits must be non-zero");
   const double j_total = c->load_param[GEMB200_LP_J_LOAD] + c->motor_param[GEMB200_MP_J_ROTOR];
   if (c->load_kind == GEMB200_LOAD_POLY_STATIC && !(j_total > 0)) return fail(GEMB200_E_INVALID, "total inertia must be positive");
-  if ((int64_t)c->n_envs * (int64_t)(state_words(d.nx, c->n_ref) > d.n_state ? state_words(d.nx, c->n_ref) : d.n_state) >= (int64_t)1 << 31)
+  if ((int64_t)c->n_envs * (int64_t)(hot_words(d.nx, c->n_ref) + cold_words(d.nx, c->n_ref) > d.n_state ? hot_words(d.nx, c->n_ref) + cold_words(d.nx, c->n_ref) : d.n_state) >= (int64_t)1 << 31)
     return fail(GEMB200_E_INVALID, "n_envs too large for 32-bit element indexing in one handle; shard the batch");
   return GEMB200_OK;
 }
@@ -257,6 +261,8 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->env_offset = c.env_index_offset;
   p->seed_lo = (uint32_t)c.seed; p->seed_hi = (uint32_t)(c.seed >> 32);
   p->st = static_cast<real*>(h->d_st);
+  p->stc = static_cast<real*>(h->d_stc);
+  p->kstep = 0;
   p->eps = h->d_eps;
   p->sw = h->d_sw;
   p->layout = c.layout;
@@ -311,6 +317,12 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     }
     p->inv_lim[eps_idx] = real(1);  // the angle entry is already normalised by eps_out_scale
   }
+  p->init_random = c.init_random;
+  for (int j = 0; j < dm.nx; ++j) { p->init_lo[j] = (real)c.init_lo[j]; p->init_span[j] = (real)(c.init_hi[j] - c.init_lo[j]); }
+  if (dm.has_eps) {
+    const double unit = sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0;
+    p->init_lo[dm.nx] = (real)(c.init_lo[dm.nx] * unit); p->init_span[dm.nx] = (real)((c.init_hi[dm.nx] - c.init_lo[dm.nx]) * unit);
+  }
   p->n_constraints = c.n_constraints;
   for (int i = 0; i < c.n_constraints; ++i) {
     p->con_kind[i] = c.constraint_kind[i];
@@ -359,7 +371,7 @@ constexpr int kBlock = GEMB200_BLOCK;
 
 // Persistent launch shape: at most as many CTAs as can be resident (SMs x occupancy), each thread looping over
 // ceil(range / resident threads) envs; the grid is then shrunk so that every thread gets the same trip count (no tail wave).
-template <int FAM, bool FINITE, typename real, int NREF>
+template <int FAM, bool FINITE, typename real, int NREF, bool SOA>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const size_t smem = ((size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD + (size_t)kBlock * kRefPad) * sizeof(real);
   const int range = p.env_end - p.env_begin;
@@ -370,7 +382,7 @@ static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<FAM, FINITE, real, NREF>, kBlock, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<FAM, FINITE, real, NREF, SOA>, kBlock, smem);
     resident = sms * (per_sm > 0 ? per_sm : 1);
   }
   if (grid > resident) {
@@ -378,7 +390,7 @@ static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
     grid = (grid + iters - 1) / iters;
   }
 #endif
-  step_kernel<FAM, FINITE, real, NREF><<<grid, kBlock, smem, st>>>(p);
+  step_kernel<FAM, FINITE, real, NREF, SOA><<<grid, kBlock, smem, st>>>(p);
   return cudaGetLastError();
 }
 template <int FAM, typename real, int NREF>
@@ -392,7 +404,8 @@ template <int FAM, typename real>
 static cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
 #define GEMB200_NREF(R)                                                                         \
   case R:                                                                                       \
-    return finite ? launch_step_t<FAM, true, real, R>(p, st) : launch_step_t<FAM, false, real, R>(p, st);
+    if (p.layout == GEMB200_LAYOUT_SOA) return finite ? launch_step_t<FAM, true, real, R, true>(p, st) : launch_step_t<FAM, false, real, R, true>(p, st); \
+    return finite ? launch_step_t<FAM, true, real, R, false>(p, st) : launch_step_t<FAM, false, real, R, false>(p, st);
   switch (nref) {
     GEMB200_NREF(0)
     GEMB200_NREF(1)
@@ -449,13 +462,13 @@ static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, 
   cudaError_t e;
   if (h->cfg.dtype == GEMB200_F32) {
     StepParams<float>& p = h->pf;
-    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot;
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)h->n_steps;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
     e = launch_step<float>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   } else {
     StepParams<double>& p = h->pd;
-    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot;
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)h->n_steps;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
     p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
     e = launch_step<double>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
@@ -471,13 +484,13 @@ static int do_reset(gemb200_handle* h, const uint8_t* mask, void* obs, void* ref
   if (h->cfg.dtype == GEMB200_F32) {
     StepParams<float>& p = h->pf;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
-    p.reset_mask = mask; p.obs = (float*)obs; p.ref_out = (float*)ref;
+    p.reset_mask = mask; p.obs = (float*)obs; p.ref_out = (float*)ref; p.kstep = (uint32_t)h->n_steps;
     e = launch_reset<float>(h->fam, h->n_ref, p, st);
     p.reset_mask = nullptr;
   } else {
     StepParams<double>& p = h->pd;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
-    p.reset_mask = mask; p.obs = (double*)obs; p.ref_out = (double*)ref;
+    p.reset_mask = mask; p.obs = (double*)obs; p.ref_out = (double*)ref; p.kstep = (uint32_t)h->n_steps;
     e = launch_reset<double>(h->fam, h->n_ref, p, st);
     p.reset_mask = nullptr;
   }
@@ -557,8 +570,9 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
     if (e_ != cudaSuccess) { gemb200_destroy(h); return fail(e_ == cudaErrorMemoryAllocation ? GEMB200_E_NOMEM : GEMB200_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e_)); } \
     cudaMemset((ptr), 0, (bytes));                                                                            \
   } while (0)
-  h->W = state_words(d.nx, cfg->n_ref);
-  ALLOC(h->d_st, n * h->W * h->rsz);
+  h->NH = hot_words(d.nx, cfg->n_ref); h->NC = cold_words(d.nx, cfg->n_ref);
+  ALLOC(h->d_st, n * (h->NH > 0 ? h->NH : 1) * h->rsz);
+  ALLOC(h->d_stc, n * h->NC * h->rsz);
   if (cfg->dead_time_steps > 0) {
     // queue width: caller-side actions when the dead time wraps the dq transformation (or there is none), else abc(+e)
     const int inner = cfg->finite ? d.n_act : (d.fam == kEESM ? 4 : (d.fam >= kSYNC ? 3 : d.n_act));
@@ -585,7 +599,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -705,8 +719,8 @@ int gemb200_get_ode_state(gemb200_handle* h, double* ode_out, void* stream) {
   if (!h || !ode_out) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) get_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_st, h->d_eps, ode_out, n, h->nx, h->W, h->has_eps);
-  else get_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_st, h->d_eps, ode_out, n, h->nx, h->W, h->has_eps);
+  if (h->cfg.dtype == GEMB200_F32) get_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_st, (const float*)h->d_stc, h->d_eps, ode_out, n, h->nx, h->n_ref, h->has_eps);
+  else get_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_st, (const double*)h->d_stc, h->d_eps, ode_out, n, h->nx, h->n_ref, h->has_eps);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
@@ -715,8 +729,8 @@ int gemb200_set_ode_state(gemb200_handle* h, const double* ode_in, void* stream)
   if (!h || !ode_in) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) set_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_st, h->d_eps, ode_in, n, h->nx, h->W, h->has_eps);
-  else set_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_st, h->d_eps, ode_in, n, h->nx, h->W, h->has_eps);
+  if (h->cfg.dtype == GEMB200_F32) set_ode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_st, (float*)h->d_stc, h->d_eps, ode_in, n, h->nx, h->n_ref, h->has_eps);
+  else set_ode_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_st, (double*)h->d_stc, h->d_eps, ode_in, n, h->nx, h->n_ref, h->has_eps);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
@@ -726,8 +740,8 @@ int gemb200_get_reference(gemb200_handle* h, double* ref_out, void* stream) {
   if (h->n_ref == 0) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) get_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_st, ref_out, n, h->nx, h->W, h->n_ref);
-  else get_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_st, ref_out, n, h->nx, h->W, h->n_ref);
+  if (h->cfg.dtype == GEMB200_F32) get_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)h->d_st, ref_out, n, h->nx, h->n_ref);
+  else get_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)h->d_st, ref_out, n, h->nx, h->n_ref);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
@@ -737,19 +751,20 @@ int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream)
   if (h->n_ref == 0) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
   const int n = h->cfg.n_envs, grid = (n + 255) / 256;
-  if (h->cfg.dtype == GEMB200_F32) set_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_st, ref_in, n, h->nx, h->W, h->n_ref);
-  else set_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_st, ref_in, n, h->nx, h->W, h->n_ref);
+  if (h->cfg.dtype == GEMB200_F32) set_ref_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)h->d_st, ref_in, n, h->nx, h->n_ref);
+  else set_ref_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)h->d_st, ref_in, n, h->nx, h->n_ref);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GEMB200_OK;
 }
 
-// checkpoint blob: [gstep u64][n_steps u64][packed records][eps][sw][dead-time queue]
+// checkpoint blob: [gstep u64][n_steps u64][hot records][cold records][eps][sw][dead-time queue]
 struct Section { void* ptr; size_t bytes; };
 static int sections(gemb200_handle* h, Section* s) {
   const size_t n = (size_t)h->cfg.n_envs;
   int k = 0;
-  s[k++] = {h->d_st, n * h->W * h->rsz};
+  s[k++] = {h->d_st, n * (h->NH > 0 ? h->NH : 1) * h->rsz};
+  s[k++] = {h->d_stc, n * h->NC * h->rsz};
   if (h->d_eps) s[k++] = {h->d_eps, n * sizeof(double)};
   if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
   if (h->d_fifo) s[k++] = {h->d_fifo, n * h->cfg.dead_time_steps * h->fifo_dim * h->rsz};
@@ -757,7 +772,7 @@ static int sections(gemb200_handle* h, Section* s) {
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {
   if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
-  Section s[8];
+  Section s[10];
   const int k = sections(h, s);
   int64_t total = 16;
   for (int i = 0; i < k; ++i) total += (int64_t)s[i].bytes;
@@ -770,7 +785,7 @@ int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
   char* b = (char*)host_blob;
   std::memcpy(b, &h->gstep, 8); b += 8;
   std::memcpy(b, &h->n_steps, 8); b += 8;
-  Section s[8];
+  Section s[10];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(b, s[i].ptr, s[i].bytes, cudaMemcpyDeviceToHost)); b += s[i].bytes; }
   return GEMB200_OK;
@@ -782,7 +797,7 @@ int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob) {
   const char* b = (const char*)host_blob;
   std::memcpy(&h->gstep, b, 8); b += 8;
   std::memcpy(&h->n_steps, b, 8); b += 8;
-  Section s[8];
+  Section s[10];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(s[i].ptr, b, s[i].bytes, cudaMemcpyHostToDevice)); b += s[i].bytes; }
   return GEMB200_OK;

@@ -15,7 +15,11 @@ constexpr int kMaxConstraints = 4;
 constexpr int kMaxX = 6;  // real-typed ODE states per env (omega + motor states without the angle): SCIM 5
 
 // words of persistent state per env and their placement (shared by host and device code)
-__host__ __device__ constexpr int state_words(int nx, int nref) { return nx + 2 * nref + (nref + 1) / 2; }
+// Two records per env: HOT (read and written every step): currents/fluxes x_1.. and the reference values;
+// COLD (read every step, written only when it changes): omega (constant-speed load), the Wiener sigmas and the absolute step
+// index at which each sub-episode ends.  Skipping the unchanged words saves 16 B of the 109 B written per PMSM env-step.
+__host__ __device__ constexpr int hot_words(int nx, int nref) { return nx - 1 + nref; }
+__host__ __device__ constexpr int cold_words(int nx, int nref) { (void)nx; return 1 + 2 * nref; }
 // element offset (in units of `real`) of word w of env i; vw = 16 / sizeof(real) words per 16-byte chunk
 __host__ __device__ inline size_t word_offset(int w, size_t i, size_t n, int W, int vw) {
   const int nfull = (W / vw) * vw;
@@ -40,7 +44,8 @@ enum MotorFamily : int {
 // RNG stream ids (word 3 of the Philox counter); shared convention with the test oracle.
 enum : uint32_t {
   kStreamWalk = 1, kStreamSubep = 2, kStreamInit = 3, kStreamSubepHi = 18,
-  kStreamWalkR = 5, kStreamSubepR = 6, kStreamSubepHiR = 22  // "R": draws made right after an in-kernel auto-reset
+  kStreamWalkR = 5, kStreamSubepR = 6, kStreamSubepHiR = 22,  // "R": draws made right after an in-kernel auto-reset
+  kStreamInitState = 7, kStreamInitState2 = 8                 // random initial ODE state
 };
 
 template <typename real>
@@ -52,10 +57,13 @@ struct StepParams {
   uint32_t seed_lo, seed_hi;
   uint32_t gstep_lo, gstep_hi;  // unique id of this API call (reset or step): RNG counter words 0,1
   // ---- persistent per-env state (owned by the handle) ----
-  // `st`: W = NX + 2*NREF + ceil(NREF/2) words per env: [x_0..x_{NX-1} | (ref value, sigma) per slot | sub-episode counters,
-  // two 16-bit counters per word].  Stored as SoA of VECTOR CHUNKS (16-byte chunks first, then an 8-byte, then a 4-byte chunk)
-  // so that a thread moves its record with W/4 fully coalesced 128-bit accesses (see word_offset()).
+  // `st`  (hot):  [x_1..x_{NX-1} | ref value per slot]            hot_words() words per env
+  // `stc` (cold): [omega | sigma per slot | sub-episode end per slot]  cold_words() words per env (ends are uint32 bit patterns)
+  // Each record is stored as SoA of VECTOR CHUNKS (16-byte chunks first, then an 8-byte, then a 4-byte chunk) so that a thread
+  // moves it with fully coalesced 128-bit accesses (see word_offset()).
   real* st;
+  real* stc;
+  uint32_t kstep;         // number of step calls so far: the clock of the sub-episode ends
   double* eps;            // [n]       electrical angle, wrapped to (-pi, pi]; nullptr for DC
   uint16_t* sw;           // [n] finite 2QC switching states, 2 bits per leg; nullptr unless finite && interlock
   real* fifo;             // [dead_steps][fifo_dim][n] DeadTimeProcessor action queue (ring, slot fifo_slot is oldest = next to overwrite)
@@ -98,6 +106,8 @@ struct StepParams {
   real inv_lim[kMaxState];
   real init_x[kMaxX];
   real reset_obs[kMaxState];  // observation right after a reset (constant initial state)
+  int32_t init_random;        // 1: uniform initial state per reset (init_lo + init_span * U); the angle entry [NX] is in the stored unit
+  real init_lo[kMaxX + 1], init_span[kMaxX + 1];
   // ---- constraint monitor ----
   int32_t n_constraints;
   int32_t con_kind[kMaxConstraints];

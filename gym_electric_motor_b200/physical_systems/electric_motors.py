@@ -37,9 +37,9 @@ class ElectricMotor:
         self._limits = update_parameter_dict(self._default_limits, limit_values or {})
         self._nominal_values = update_parameter_dict(self._default_nominal_values, nominal_values or {})
         self._initializer = update_parameter_dict(self._default_initializer, motor_initializer or {})
-        if self._initializer.get("random_init") is not None:
-            raise NotImplementedError("random motor initialisers (electric_motor.py:179-268) are not on the device path yet; "
-                                      "use constant 'states' (SURVEY.md §8f row 4)")
+        if self._initializer.get("random_init") not in (None, "uniform"):
+            raise NotImplementedError("only random_init=None / 'uniform' are on the device path (the truncated-normal initialiser of "
+                                      "electric_motor.py:245-258 is host code built on scipy.stats.truncnorm)")
         self._initial_states = dict(self._default_initializer["states"])
         if self._initializer["states"]:
             unknown = set(self._initializer["states"]) - set(self._initial_states)
@@ -73,9 +73,28 @@ class ElectricMotor:
         — a user's `i_sq=20` therefore initialises the d-current (pinned by tests/golden/pmsm_cc_custom_rk4.npz)."""
         return np.array([float(self._initial_states[k]) for k in self._default_initializer["states"]])
 
+    @property
+    def random_init(self):
+        return self._initializer.get("random_init") == "uniform"
+
+    def initial_bounds(self, state_low, state_positions):
+        """(lower, upper) per initial state in the initializer's key order (electric_motor.py:214-232): upper = the motor's
+        nominal value of the state, lower = upper * state_space.low, both clipped to `interval` when given."""
+        keys = list(self._default_initializer["states"])
+        upper = np.array([float(self._nominal_values[k]) for k in keys])
+        lower = upper * np.array([float(state_low[state_positions[k]]) for k in keys])
+        interval = self._initializer.get("interval")
+        if interval is not None:
+            iv = np.asarray(interval, dtype=float)
+            lower = np.clip(lower, a_min=iv.T[0], a_max=None)
+            upper = np.clip(upper, a_min=None, a_max=iv.T[1])
+        return lower, upper
+
     def check_initial_state(self, nominal_state, state_low, state_positions):
         """ElectricMotor.initialize constant branch (electric_motor.py:255-266): the value has to lie inside
         [nominal*low, nominal]."""
+        if self.random_init:
+            return
         for name, val in self._initial_states.items():
             if name not in state_positions:
                 continue
@@ -399,6 +418,9 @@ class InductionMotor(ThreePhaseMotor):
         return 1.5 * mp["p"] * mp["l_m"] ** 2 / (mp["l_m"] + mp["l_sigr"]) * self._limits["i_sd"] * self._limits["i_sq"] / 2
 
     def check_initial_state(self, nominal_state, state_low, state_positions):
+        if self.random_init:
+            raise NotImplementedError("random initial states of induction motors use flux limits drawn from the unseeded global numpy "
+                                      "RNG in the reference (squirrel_cage_induction_motor.py:146-157); not supported")
         # induction motors check against their own initial limits (electric_motor.py:197-213); zero always passes
         for name, val in self._initial_states.items():
             if name in ("psi_ralpha", "psi_rbeta") and val != 0.0:

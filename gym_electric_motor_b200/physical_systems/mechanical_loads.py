@@ -1,4 +1,6 @@
 """Mechanical-load descriptors (reference physical_systems/mechanical_loads/*.py); the ODE runs in the kernel (load_ode)."""
+import numpy as np
+
 from .. import _cabi as K
 from ..utils import update_parameter_dict
 
@@ -22,8 +24,8 @@ class MechanicalLoad:
         if "states" in li:
             li["states"] = dict(li["states"])
         self._initializer.update(li)
-        if self._initializer.get("random_init") is not None:
-            raise NotImplementedError("random load initialisers (mechanical_load.py:100-167) are not on the device path yet")
+        if self._initializer.get("random_init") not in (None, "uniform"):
+            raise NotImplementedError("only random_init=None / 'uniform' are on the device path (mechanical_load.py:138-150 uses scipy truncnorm)")
         self._initial_states = self._initializer.get("states", {s: 0.0 for s in self._state_names})
 
     @property
@@ -55,8 +57,25 @@ class MechanicalLoad:
     def initial_omega(self):
         return float(self._initial_states.get("omega", 0.0))
 
+    @property
+    def random_init(self):
+        return self._initializer.get("random_init") == "uniform"
+
+    def initial_bounds(self, nominal_state, state_low, state_positions):
+        """(lower, upper) of the initial omega (mechanical_load.py:118-128)."""
+        idx = state_positions["omega"]
+        upper = float(nominal_state[idx])
+        lower = upper * float(state_low[idx])
+        interval = self._initializer.get("interval")
+        if interval is not None:
+            iv = np.asarray(interval, dtype=float).reshape(-1, 2)
+            lower, upper = max(lower, iv[0, 0]), min(upper, iv[0, 1])
+        return lower, upper
+
     def check_initial_state(self, nominal_state, state_low, state_positions):
         """MechanicalLoad.initialize constant branch (mechanical_load.py:151-160)."""
+        if self.random_init:
+            return
         idx = state_positions["omega"]
         upper = nominal_state[idx]
         lower = upper * state_low[idx]

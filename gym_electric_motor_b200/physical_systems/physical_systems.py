@@ -208,6 +208,19 @@ class SCMLSystem(PhysicalSystem):
             cfg.limits[i] = float(v)
         for i, v in enumerate(self.initial_ode_state()):
             cfg.init_ode[i] = float(v)
+        # random initial states (uniform): bounds per ODE state; constant states get lo == hi
+        m, ld = self._electrical_motor, self._mechanical_load
+        if m.random_init or ld.random_init:
+            cfg.init_random = 1
+            init = self.initial_ode_state()
+            lo, hi = init.copy(), init.copy()
+            if ld.random_init:
+                lo[0], hi[0] = ld.initial_bounds(self._nominal_state, self._state_space.low, self._state_positions)
+            if m.random_init:
+                mlo, mhi = m.initial_bounds(self._state_space.low, self._state_positions)
+                lo[1:], hi[1:] = mlo, mhi  # initializer key order == reference's assignment order (see initial_ode_state)
+            for i in range(len(init)):
+                cfg.init_lo[i], cfg.init_hi[i] = float(lo[i]), float(hi[i])
         cfg.action_dq = int(self._action_dq)
         cfg.angle_advance = float(self._angle_advance)
         cfg.dead_time_steps = int(self._dead_steps)

@@ -168,8 +168,11 @@ typedef struct gemb200_config {
   int32_t action_dq;
   int32_t dead_time_steps;  /* DeadTimeProcessor(steps) physical_system_wrappers/dead_time_processor.py: action FIFO, 0 = off */
   int32_t dead_time_outer;  /* 1: the dead-time FIFO holds the caller's (dq) actions, 0: the transformed (abc) ones */
-  int32_t reserved0;
+  int32_t init_random;      /* 0: constant initial state init_ode[]; 1: uniform in [init_lo, init_hi] per ODE state at every reset
+                               (ElectricMotor.initialize / MechanicalLoad.initialize with random_init='uniform',
+                               electric_motor.py:179-268, mechanical_load.py:100-167) */
   double angle_advance;
+  double init_lo[GEMB200_MAX_ODE], init_hi[GEMB200_MAX_ODE]; /* ODE order [omega, motor states...]; lo == hi keeps a state constant */
 } gemb200_config;
 
 typedef struct gemb200_handle gemb200_handle;

@@ -99,7 +99,8 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
 /* Counter = (id of the API call lo, hi, global env index lo, (hi << 8) | stream id); key = seed.  Every reset/step
  * call of a handle gets a fresh call id, so no per-env RNG state exists.  Stream ids: */
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
-       STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */ };
+       STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
+       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */ };
 
 struct gem_oracle;
 static void rng4(const struct gem_oracle* o, int64_t env, uint32_t stream, uint32_t out[4]);
@@ -704,6 +705,16 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
   const int mk = c->motor_kind;
   double* y = e->ode;
   for (int j = 0; j < o->n_ode; ++j) y[j] = c->init_ode[j];
+  if (c->init_random) {
+    /* ElectricMotor.initialize / MechanicalLoad.initialize, random_init='uniform' (electric_motor.py:236-243,
+     * mechanical_load.py:131-137): value = (upper - lower) * U + lower per state; bounds derived on the host.
+     * (Philox stream instead of numpy's; one uniform per ODE state in ODE order.) */
+    uint32_t r0[4], r1[4];
+    int64_t idx = e - o->env;
+    rng4(o, idx, STREAM_INIT_STATE, r0);
+    rng4(o, idx, STREAM_INIT_STATE2, r1);
+    for (int j = 0; j < o->n_ode; ++j) y[j] = c->init_lo[j] + (c->init_hi[j] - c->init_lo[j]) * u01(j < 4 ? r0[j] : r1[j - 4]);
+  }
   double u_abc[5] = {0, 0, 0, 0, 0};
   conv_reset(o, e, u_abc);
   for (int j = 0; j < 4; ++j) u_abc[j] *= c->u_sup;

@@ -404,6 +404,25 @@ def _wrapper_chain(ps_):
     return chain
 
 
+def init_bounds():
+    """Empirical range of the reference's random initial ODE states (random_init='uniform'), 3000 resets per env."""
+    out = {}
+    for env_id, load_iv in [("Cont-CC-PMSM-v0", None), ("Cont-SC-PMSM-v0", [[-50.0, 120.0]]), ("Cont-CC-EESM-v0", None),
+                            ("Cont-CC-PermExDc-v0", None), ("Cont-SC-ExtExDc-v0", None), ("Cont-CC-SynRM-v0", None)]:
+        env = gem.make(env_id, visualization=NoViz(), ode_solver=make_solver("euler"), motor=dict(motor_initializer=dict(random_init="uniform")),
+                       load=dict(load_initializer=dict(random_init="uniform", interval=load_iv)))
+        ys = []
+        env.reset(seed=0)
+        for _ in range(3000):
+            env.reset()
+            ys.append(ode_state(env))
+        ys = np.array(ys)
+        out[env_id] = dict(load_interval=load_iv, min=ys.min(axis=0).tolist(), max=ys.max(axis=0).tolist(), mean=ys.mean(axis=0).tolist())
+        print(env_id, "ode min", np.round(ys.min(axis=0), 2), "max", np.round(ys.max(axis=0), 2))
+    with open(os.path.join(HERE, "init_bounds.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def regen_ref_data():
     """Re-run the reference's own integration test recipe (tests/integration_tests/test_integration.py:18-87)."""
     sys.path.insert(0, os.path.join(REF_ROOT, "examples", "classic_controllers"))
@@ -458,9 +477,11 @@ if __name__ == "__main__":
     ap.add_argument("--skip-table", action="store_true")
     args = ap.parse_args()
     for case in CASES:
-        if args.only == "ref_data" or (args.only and args.only not in case["name"]):
+        if args.only in ("ref_data", "init_bounds") or (args.only and args.only not in case["name"]):
             continue
         record(case)
+    if not args.only or args.only == "init_bounds":
+        init_bounds()
     if not args.only or args.only == "ref_data":
         if not args.skip_table and not args.only:
             env_table()

@@ -176,7 +176,13 @@ def _cfg(name, n, dtype=K.F32, **kw):
 @pytest.mark.parametrize("name", ["pmsm_cc_rk4", "eesm_cc_rk4", "permex_cc_rk4", "extex_cc_rk4", "scim_fin_sc_rk4"])
 @pytest.mark.parametrize("n", [1, 31, 33, 257, 4096 + 5])
 def test_layouts_and_host_path_agree_bitwise(torch_cuda, name, n):
-    """row-per-env (AoS, smem transpose + vector stores) vs field-major (SoA) vs the host-buffer entry point."""
+    """row-per-env (AoS, smem transpose + vector stores) vs the host-buffer entry point: bit-for-bit (same kernel).
+    Field-major (SoA) is a separate template instantiation of the same source, so the compiler may contract FMAs differently:
+    it has to agree to a few ulp (and terminations exactly)."""
+
+    def close(x, y):
+        return torch.allclose(x, y, rtol=2e-6, atol=2e-7)
+
     import torch
     from gym_electric_motor_b200.vector_sim import VectorSim
 
@@ -188,15 +194,15 @@ def test_layouts_and_host_path_agree_bitwise(torch_cuda, name, n):
     steps = 20
     acts = _random_actions(rng, g, n, steps)
     ra, rs, rh = sa.reset(), ss.reset(), sh.reset_host()
-    assert torch.equal(ra[0], rs[0].T) and torch.equal(ra[1], rs[1].T)
+    assert close(ra[0], rs[0].T) and close(ra[1], rs[1].T)
     assert np.array_equal(ra[0].cpu().numpy(), rh[0])
     for k in range(steps):
         a = acts[k]
         oa = sa.step(a)
         os_ = ss.step(np.ascontiguousarray(a.T) if not sa.finite else np.ascontiguousarray(a.reshape(n, -1).T))
         oh = sh.step_host(a)
-        assert torch.equal(oa[0], os_[0].T) and torch.equal(oa[1], os_[1].T)
-        assert torch.equal(oa[2], os_[2]) and torch.equal(oa[3], os_[3])
+        assert close(oa[0], os_[0].T) and close(oa[1], os_[1].T)
+        assert close(oa[2], os_[2]) and torch.equal(oa[3], os_[3])
         for x, y in zip(oa, oh):
             assert np.array_equal(x.cpu().numpy(), y)
 
@@ -345,3 +351,47 @@ def test_mixed_motor_batch(torch_cuda, oracle_lib):
     glob = torch.arange(n, device="cuda")
     parts = mixed.split_interleaved(glob)
     assert [int(p[1]) for p in parts] == [3, 4, 5]
+
+
+@pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("name", ["pmsm_sc_rk4", "eesm_cc_rk4", "extex_cc_rk4", "permex_cc_rk4"])
+def test_random_initial_states_match_oracle(torch_cuda, oracle_lib, name, dtype):
+    """random_init='uniform' on the device: same Philox draws as the oracle at reset and at every in-kernel auto-reset;
+    the reset observation is computed from the sampled state."""
+    g = load_golden(name)
+    n, steps = 777, 60
+    init = np.array(g["reset_ode"], dtype=float)
+    n_ode = len(init)
+    lim = np.array(g["meta"]["limits"])
+    names = g["meta"]["state_names"]
+    span = np.array([0.3 * lim[0]] + [0.6 * lim[names.index("i_sd" if "i_sd" in names else ("i_a" if "i_a" in names else "i"))]] * (n_ode - 1))
+    if "epsilon" in names:
+        span[-1] = np.pi
+
+    def mk(dt):
+        cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=init, dtype=dt, solver="rk4", ref_kind=K.REF_WIENER, autoreset=K.AUTORESET_SAME_STEP, seed=77)
+        cfg.init_random = 1
+        for j in range(n_ode):
+            cfg.init_lo[j], cfg.init_hi[j] = -span[j], span[j]
+        return cfg
+
+    dev = DeviceAdapter(mk(dtype))
+    ora = oracle_lib.Oracle(mk(K.F64), nthreads=8)
+    o_obs, o_ref = ora.reset()
+    d_obs, d_ref = dev.reset()
+    tol = TOL[dtype]
+    assert np.abs(d_obs - o_obs).max() < 20 * tol
+    y = dev.sim.get_ode_state().cpu().numpy()
+    assert np.abs(y - ora.get_ode_state()).max() / np.abs(span).max() < 20 * tol
+    assert np.unique(np.round(y[:, 1], 6)).size > n // 2  # really random per env
+    rng = np.random.default_rng(5)
+    acts = _random_actions(rng, g, n, steps)
+    alive = np.ones(n, dtype=bool)
+    n_term = 0
+    for k in range(steps):
+        o_obs, o_ref, o_rew, o_term = ora.step(acts[k])
+        d_obs, d_ref, d_rew, d_term = dev.step(acts[k])
+        alive &= ~(o_term != d_term)
+        assert np.abs(d_obs - o_obs)[alive].max() < 50 * tol, k
+        n_term += int(o_term[alive].sum())
+    assert alive.mean() > 0.99 and n_term > 0

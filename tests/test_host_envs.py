@@ -151,3 +151,25 @@ def test_wrapper_descriptors_compile_like_the_reference_stack():
                                       ode_solver=ps_.RK4Solver())
     c = sys_.fill_config(K.new_config())
     assert (c.action_dq, c.angle_advance) == (1, 0.0) and sys_.action_space.shape == (2,)
+
+
+def test_random_initialiser_bounds_match_reference():
+    """random_init='uniform': the [lower, upper] box per ODE state must be the one the reference samples from — compared with
+    the empirical range of 3000 reference resets per env (tests/golden/init_bounds.json, make_golden.py:init_bounds)."""
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "init_bounds.json")))
+    for env_id, e in ref.items():
+        env = gem.make(env_id, motor=dict(motor_initializer=dict(random_init="uniform")),
+                       load=dict(load_initializer=dict(random_init="uniform", interval=e["load_interval"])))
+        cfg = env.build_config()
+        assert cfg.init_random == 1
+        n = len(e["min"])
+        lo, hi = np.array(list(cfg.init_lo)[:n]), np.array(list(cfg.init_hi)[:n])
+        mn, mx, mean = np.array(e["min"]), np.array(e["max"]), np.array(e["mean"])
+        span = hi - lo
+        assert np.all(mn >= lo - 1e-9) and np.all(mx <= hi + 1e-9), (env_id, lo, hi, mn, mx)
+        assert np.all(mn - lo < 0.01 * span) and np.all(hi - mx < 0.01 * span), (env_id, lo, hi, mn, mx)
+        assert np.all(np.abs(mean - 0.5 * (lo + hi)) < 0.03 * span)
+    with pytest.raises(NotImplementedError):
+        gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(random_init="uniform")))
+    with pytest.raises(NotImplementedError):
+        gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="gaussian")))
