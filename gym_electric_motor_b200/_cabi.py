@@ -19,7 +19,7 @@ LOAD_CONST_SPEED, LOAD_POLY_STATIC = 0, 1
 LP_A, LP_B, LP_C, LP_J_LOAD, LP_TAU_DECAY = range(5)
 SOLVER_EULER, SOLVER_RK4 = 0, 1
 CONSTRAINT_LIMIT, CONSTRAINT_SQUARED = 0, 1
-REF_CONST, REF_WIENER, REF_EXTERNAL = 0, 1, 2
+REF_CONST, REF_WIENER, REF_EXTERNAL, REF_LAPLACE, REF_SINUS, REF_STEP, REF_SAWTOOTH, REF_TRIANGULAR = range(8)
 F32, F64 = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 AUTORESET_NONE, AUTORESET_SAME_STEP = 0, 1
@@ -81,6 +81,12 @@ class GemB200Config(C.Structure):
         ("angle_advance", C.c_double),
         ("init_lo", C.c_double * MAX_ODE),
         ("init_hi", C.c_double * MAX_ODE),
+        ("ref_amp_lo", C.c_double * MAX_REF),
+        ("ref_amp_hi", C.c_double * MAX_REF),
+        ("ref_freq_lo", C.c_double * MAX_REF),
+        ("ref_freq_hi", C.c_double * MAX_REF),
+        ("ref_off_lo", C.c_double * MAX_REF),
+        ("ref_off_hi", C.c_double * MAX_REF),
     ]
 
 

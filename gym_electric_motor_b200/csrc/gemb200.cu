@@ -118,11 +118,14 @@ static int validate(const gemb200_config* c) {
                                    "(physical_systems.py:632 slices u_in[:2]); not supported");
   for (int r = 0; r < c->n_ref; ++r) {
     if (c->ref_state[r] < 0 || c->ref_state[r] >= d.n_state) return fail(GEMB200_E_INVALID, "ref_state out of range");
-    if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_EXTERNAL) return fail(GEMB200_E_INVALID, "bad ref_kind");
-    if (c->ref_kind[r] == GEMB200_REF_WIENER && (c->ref_len_lo[r] < 1 || c->ref_len_hi[r] < c->ref_len_lo[r] || !(c->ref_sigma_lo[r] > 0)))
-      return fail(GEMB200_E_INVALID, "bad Wiener reference ranges");
-    if (c->ref_kind[r] == GEMB200_REF_WIENER && c->ref_len_hi[r] > (1 << 24))
-      return fail(GEMB200_E_INVALID, "sub-episode lengths above 2^24 steps are not supported");
+    if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_TRIANGULAR) return fail(GEMB200_E_INVALID, "bad ref_kind");
+    const bool subep = c->ref_kind[r] == GEMB200_REF_WIENER || c->ref_kind[r] >= GEMB200_REF_LAPLACE;
+    const bool walk = c->ref_kind[r] == GEMB200_REF_WIENER || c->ref_kind[r] == GEMB200_REF_LAPLACE;
+    if (subep && (c->ref_len_lo[r] < 1 || c->ref_len_hi[r] < c->ref_len_lo[r] || c->ref_len_hi[r] > (1 << 24)))
+      return fail(GEMB200_E_INVALID, "bad sub-episode length range");
+    if (walk && !(c->ref_sigma_lo[r] > 0 && c->ref_sigma_hi[r] >= c->ref_sigma_lo[r])) return fail(GEMB200_E_INVALID, "bad sigma range");
+    if (c->ref_kind[r] >= GEMB200_REF_SINUS && !(c->ref_freq_lo[r] > 0 && c->ref_freq_hi[r] >= c->ref_freq_lo[r] && c->ref_amp_lo[r] >= 0))
+      return fail(GEMB200_E_INVALID, "bad amplitude / frequency range of a periodic reference generator");
   }
   for (int j = 0; j < d.n_state; ++j)
     if (!(c->limits[j] != 0.0) && !(c->motor_kind == GEMB200_MOTOR_SHUNT_DC && j == 6)) return fail(GEMB200_E_INVALID, "limits must be non-zero");
@@ -347,12 +350,16 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->bias = (real)c.reward_bias; p->viol_reward = (real)c.violation_reward;
   p->n_ref = c.n_ref;
   p->any_wiener = h->any_wiener;
+  p->ref_tau = (real)c.tau;
   for (int r = 0; r < c.n_ref; ++r) {
     p->ref_kind[r] = c.ref_kind[r]; p->ref_state[r] = c.ref_state[r];
     p->ref_const[r] = (real)c.ref_value[r];
     p->ref_lo[r] = (real)c.ref_margin_lo[r]; p->ref_hi[r] = (real)c.ref_margin_hi[r];
     p->ref_init_lo[r] = (real)c.ref_init_lo[r]; p->ref_init_span[r] = (real)(c.ref_init_hi[r] - c.ref_init_lo[r]);
-    if (c.ref_kind[r] == GEMB200_REF_WIENER) {
+    p->ref_amp_lo[r] = (real)c.ref_amp_lo[r]; p->ref_amp_span[r] = (real)(c.ref_amp_hi[r] - c.ref_amp_lo[r]);
+    p->ref_freq_lo[r] = (real)c.ref_freq_lo[r]; p->ref_freq_span[r] = (real)(c.ref_freq_hi[r] - c.ref_freq_lo[r]);
+    p->ref_off_lo[r] = (real)c.ref_off_lo[r]; p->ref_off_hi[r] = (real)c.ref_off_hi[r];
+    if (c.ref_kind[r] == GEMB200_REF_WIENER || c.ref_kind[r] == GEMB200_REF_LAPLACE) {
       p->ref_lsig_lo[r] = (real)std::log10(c.ref_sigma_lo[r]);
       p->ref_lsig_span[r] = (real)(std::log10(c.ref_sigma_hi[r]) - std::log10(c.ref_sigma_lo[r]));
     }
@@ -562,7 +569,8 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   h->n_ref = cfg->n_ref;
   h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
   h->two_segment = cfg->finite && cfg->interlocking_time > 0;
-  for (int r = 0; r < cfg->n_ref; ++r) h->any_wiener = h->any_wiener || cfg->ref_kind[r] == GEMB200_REF_WIENER;
+  for (int r = 0; r < cfg->n_ref; ++r)  // any generator that advances by itself (Wiener, Laplace, periodic)
+    h->any_wiener = h->any_wiener || cfg->ref_kind[r] == GEMB200_REF_WIENER || cfg->ref_kind[r] >= GEMB200_REF_LAPLACE;
   const size_t n = (size_t)cfg->n_envs;
 #define ALLOC(ptr, bytes)                                                                                     \
   do {                                                                                                        \

@@ -45,7 +45,9 @@ enum MotorFamily : int {
 enum : uint32_t {
   kStreamWalk = 1, kStreamSubep = 2, kStreamInit = 3, kStreamSubepHi = 18,
   kStreamWalkR = 5, kStreamSubepR = 6, kStreamSubepHiR = 22,  // "R": draws made right after an in-kernel auto-reset
-  kStreamInitState = 7, kStreamInitState2 = 8                 // random initial ODE state
+  kStreamInitState = 7, kStreamInitState2 = 8,                // random initial ODE state
+  kStreamPeriodic = 32                                        // + 2*slot (+1): sub-episode parameters of the periodic generators,
+                                                              //   counter word 0 = step index of the sub-episode start
 };
 
 template <typename real>
@@ -132,6 +134,10 @@ struct StepParams {
   real ref_init_lo[kMaxRef], ref_init_span[kMaxRef];
   real ref_lsig_lo[kMaxRef], ref_lsig_span[kMaxRef];  // log10 sigma range
   int32_t ref_len_lo[kMaxRef], ref_len_span[kMaxRef];
+  // periodic generators (sinus / step / sawtooth / triangular): parameter ranges per slot, tau for the phase increment
+  real ref_amp_lo[kMaxRef], ref_amp_span[kMaxRef], ref_freq_lo[kMaxRef], ref_freq_span[kMaxRef], ref_off_lo[kMaxRef], ref_off_hi[kMaxRef];
+  real ref_tau;
+  int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
 };
 
 }  // namespace gemb200

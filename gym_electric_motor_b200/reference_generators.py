@@ -2,9 +2,10 @@
 kernel's epilogue with a counter-based Philox stream per (seed, env) — the reference's numpy PCG64 streams cannot be
 matched on a device; the distributions are (tests/test_oracle_golden.py::test_wiener_reference_statistics).
 
-On the device: Wiener, Const, Zero, Multiple (of those) and `ExternalReferenceGenerator` (values pushed by the caller
-each step).  The other sub-episoded generators (Step/Sinus/Sawtooth/Triangular/Laplace/Switched) are "next"
-(SURVEY.md §8f row 3)."""
+On the device: Wiener, Laplace, Sinusoidal, Step, Sawtooth, Triangular, Const, Zero, Multiple (of those) and
+`ExternalReferenceGenerator` (values pushed by the caller each step).  The periodic generators re-derive their sub-episode
+parameters from a Philox block addressed by the sub-episode's start step, so they need no extra per-env state.
+SwitchedReferenceGenerator is not available yet."""
 import numpy as np
 
 from . import _cabi as K
@@ -49,6 +50,9 @@ class ReferenceGenerator:
             cfg.ref_init_lo[r], cfg.ref_init_hi[r] = s.get("init", s.get("margin", (-1.0, 1.0)))
             cfg.ref_sigma_lo[r], cfg.ref_sigma_hi[r] = s.get("sigma", (1e-3, 1e-1))
             cfg.ref_len_lo[r], cfg.ref_len_hi[r] = s.get("length", (500, 2000))
+            cfg.ref_amp_lo[r], cfg.ref_amp_hi[r] = s.get("amp", (0.0, 0.0))
+            cfg.ref_freq_lo[r], cfg.ref_freq_hi[r] = s.get("freq", (1.0, 1.0))
+            cfg.ref_off_lo[r], cfg.ref_off_hi[r] = s.get("off", (0.0, 0.0))
 
     def close(self):
         pass
@@ -199,19 +203,70 @@ class MultipleReferenceGenerator(ReferenceGenerator):
         return out
 
 
-def _unsupported(name):
-    class _Unsupported(ReferenceGenerator):
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"{name} is not on the device path yet (SURVEY.md §8f row 3); available: Wiener, Const, Zero, "
-                                      "Multiple, ExternalReferenceGenerator")
+class LaplaceProcessReferenceGenerator(SubepisodedReferenceGenerator):
+    """reference laplace_process_reference_generator.py: random walk with Laplace(0, sigma) increments, starts at 0."""
 
-    _Unsupported.__name__ = name
-    return _Unsupported
+    def __init__(self, sigma_range=(1e-3, 1e-1), **kwargs):
+        super().__init__(**kwargs)
+        self._sigma_range = sigma_range
+
+    def slots(self):
+        sr = self._sigma_range
+        sigma = (float(sr), float(sr)) if type(sr) in (int, float) else (float(sr[0]), float(sr[1]))
+        return [dict(kind=K.REF_LAPLACE, state=self._physical_system.state_positions[self._reference_state], margin=self._limit_margin,
+                     sigma=sigma, length=self._length_range())]
 
 
-StepReferenceGenerator = _unsupported("StepReferenceGenerator")
-SinusoidalReferenceGenerator = _unsupported("SinusoidalReferenceGenerator")
-SawtoothReferenceGenerator = _unsupported("SawtoothReferenceGenerator")
-TriangularReferenceGenerator = _unsupported("TriangularReferenceGenerator")
-LaplaceProcessReferenceGenerator = _unsupported("LaplaceProcessReferenceGenerator")
-SwitchedReferenceGenerator = _unsupported("SwitchedReferenceGenerator")
+class _PeriodicReferenceGenerator(SubepisodedReferenceGenerator):
+    """Common part of the sinusoidal / step / sawtooth / triangular generators: per sub-episode a random amplitude, frequency,
+    offset and phase (sinusoidal_reference_generator.py:19-62 and siblings)."""
+
+    KIND = None
+
+    def __init__(self, amplitude_range=None, frequency_range=(1, 10), offset_range=None, *_, **kwargs):
+        super().__init__(**kwargs)
+        self._amplitude_range = amplitude_range or (0, np.inf)
+        self._frequency_range = frequency_range
+        self._offset_range = offset_range or (-np.inf, np.inf)
+
+    def set_modules(self, physical_system):
+        super().set_modules(physical_system)
+        self._amplitude_range = np.clip(self._amplitude_range, 0, (self._limit_margin[1] - self._limit_margin[0]) / 2)
+        self._offset_range = np.clip(self._offset_range, self._limit_margin[0], self._limit_margin[1])
+
+    def slots(self):
+        fr = self._frequency_range
+        freq = (float(fr), float(fr)) if type(fr) in (int, float) else (float(fr[0]), float(fr[1]))
+        return [dict(kind=self.KIND, state=self._physical_system.state_positions[self._reference_state], margin=self._limit_margin,
+                     amp=(float(self._amplitude_range[0]), float(self._amplitude_range[1])), freq=freq,
+                     off=(float(self._offset_range[0]), float(self._offset_range[1])), length=self._length_range())]
+
+
+class SinusoidalReferenceGenerator(_PeriodicReferenceGenerator):
+    """reference sinusoidal_reference_generator.py"""
+
+    KIND = K.REF_SINUS
+
+
+class StepReferenceGenerator(_PeriodicReferenceGenerator):
+    """reference step_reference_generator.py (incl. the roll of the whole sub-episode by int(steps_per_period * phase))"""
+
+    KIND = K.REF_STEP
+
+
+class SawtoothReferenceGenerator(_PeriodicReferenceGenerator):
+    """reference sawtooth_reference_generator.py"""
+
+    KIND = K.REF_SAWTOOTH
+
+
+class TriangularReferenceGenerator(_PeriodicReferenceGenerator):
+    """reference triangle_reference_generator.py"""
+
+    KIND = K.REF_TRIANGULAR
+
+
+class SwitchedReferenceGenerator(ReferenceGenerator):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("SwitchedReferenceGenerator (switched_reference_generator.py) is not on the device path yet; available: "
+                                  "Wiener, Laplace, Sinusoidal, Step, Sawtooth, Triangular, Const, Zero, Multiple, External")

@@ -96,8 +96,13 @@ enum gemb200_ref_kind {
   GEMB200_REF_CONST = 0,   /* reference_generators/const_reference_generator.py */
   GEMB200_REF_WIENER = 1,  /* reference_generators/wiener_process_reference_generator.py:7-49 on
                               subepisoded_reference_generator.py:9-119 */
-  GEMB200_REF_EXTERNAL = 2 /* value injected with gemb200_set_reference() before each step (oracle injection hook,
-                              user-side generators) */
+  GEMB200_REF_EXTERNAL = 2, /* value injected with gemb200_set_reference() before each step (oracle injection hook,
+                               user-side generators) */
+  GEMB200_REF_LAPLACE = 3,    /* reference_generators/laplace_process_reference_generator.py */
+  GEMB200_REF_SINUS = 4,      /* sinusoidal_reference_generator.py */
+  GEMB200_REF_STEP = 5,       /* step_reference_generator.py */
+  GEMB200_REF_SAWTOOTH = 6,   /* sawtooth_reference_generator.py */
+  GEMB200_REF_TRIANGULAR = 7  /* triangle_reference_generator.py */
 };
 
 enum gemb200_dtype { GEMB200_F32 = 0 /* fp32 state, fp64 rotor angle */, GEMB200_F64 = 1 };
@@ -173,6 +178,13 @@ typedef struct gemb200_config {
                                electric_motor.py:179-268, mechanical_load.py:100-167) */
   double angle_advance;
   double init_lo[GEMB200_MAX_ODE], init_hi[GEMB200_MAX_ODE]; /* ODE order [omega, motor states...]; lo == hi keeps a state constant */
+
+  /* periodic reference generators (SINUS/STEP/SAWTOOTH/TRIANGULAR): per sub-episode amplitude ~ U(amp), frequency ~ U(freq) [Hz],
+   * offset ~ U(clip(off, -margin_hi + A | margin_lo + A (STEP), margin_hi - A)); ranges already clipped to the limit margin
+   * as in the generators' set_modules() */
+  double ref_amp_lo[GEMB200_MAX_REF], ref_amp_hi[GEMB200_MAX_REF];
+  double ref_freq_lo[GEMB200_MAX_REF], ref_freq_hi[GEMB200_MAX_REF];
+  double ref_off_lo[GEMB200_MAX_REF], ref_off_hi[GEMB200_MAX_REF];
 } gemb200_config;
 
 typedef struct gemb200_handle gemb200_handle;

@@ -51,6 +51,7 @@ typedef struct {
   double ref_value[GEMB200_MAX_REF];
   double ref_sigma[GEMB200_MAX_REF];
   int ref_left[GEMB200_MAX_REF];
+  uint32_t ref_start[GEMB200_MAX_REF], ref_len[GEMB200_MAX_REF]; /* periodic generators: sub-episode start step and length */
   double fifo[GEMB200_MAX_DEAD_TIME][GEMB200_MAX_ACT]; /* DeadTimeProcessor queue (ring; slot = call counter mod steps) */
 } env_t;
 
@@ -100,7 +101,8 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
  * call of a handle gets a fresh call id, so no per-env RNG state exists.  Stream ids: */
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
-       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */ };
+       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */,
+       STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */ };
 
 struct gem_oracle;
 static void rng4(const struct gem_oracle* o, int64_t env, uint32_t stream, uint32_t out[4]);
@@ -805,12 +807,67 @@ static double reward(const gem_oracle* o, const double* s, const double* ref_ful
 
 /* SubepisodedReferenceGenerator.get_reference_observation :93-100 + WienerProcess._reset_reference :30-41, one value
  * per call instead of a pre-computed sub-episode (same distribution; RNG stream differs from numpy, see header) */
+static void rng4_at(const gem_oracle* o, int64_t env, uint32_t kstart, uint32_t stream, uint32_t out[4]) {
+  uint64_t g = (uint64_t)(env + o->cfg.env_index_offset);
+  out[0] = kstart; out[1] = 0xA5A5A5A5u; out[2] = (uint32_t)g; out[3] = ((uint32_t)(g >> 32) << 8) | stream;
+  philox4x32_10(out, (uint32_t)o->cfg.seed, (uint32_t)(o->cfg.seed >> 32));
+}
+static double frac1(double x) { return x - floor(x); }
+
+/* Value k steps into a sub-episode of Sinusoidal/Step/Sawtooth/TriangularReferenceGenerator._reset_reference
+ * (sinusoidal_reference_generator.py:44-62, step_reference_generator.py:47-76, sawtooth_reference_generator.py:47-64,
+ * triangle_reference_generator.py:51-77), parameters from the Philox block of the sub-episode instead of numpy draws. */
+static double periodic_value(const gem_oracle* o, int r, int kind, const uint32_t* b, const uint32_t* cw, uint32_t k, uint32_t len) {
+  const gemb200_config* c = &o->cfg;
+  double A = c->ref_amp_lo[r] + (c->ref_amp_hi[r] - c->ref_amp_lo[r]) * u01(b[1]);   /* _get_current_value(amplitude_range) */
+  double f = c->ref_freq_lo[r] + (c->ref_freq_hi[r] - c->ref_freq_lo[r]) * u01(b[2]);
+  double lo_c = (kind == GEMB200_REF_STEP ? c->ref_margin_lo[r] : -c->ref_margin_hi[r]) + A, hi_c = c->ref_margin_hi[r] - A;
+  double olo = fmin(fmax(c->ref_off_lo[r], lo_c), hi_c), ohi = fmin(fmax(c->ref_off_hi[r], lo_c), hi_c); /* np.clip(offset_range, ., .) */
+  double off = olo + (ohi - olo) * u01(b[3]);
+  double ph = u01(cw[0]); /* phase / 2pi */
+  double wave;
+  if (kind == GEMB200_REF_STEP) {
+    double u = u01(cw[1]);
+    double ratio = u < 0.5 ? sqrt(0.5 * u) : 1.0 - sqrt(0.5 * (1.0 - u)); /* random_generator.triangular(0, 0.5, 1) */
+    uint32_t shift = (uint32_t)((1.0 / (f * c->tau)) * ph);               /* int(steps_per_period * phase) */
+    uint32_t kk = (k + len - shift % len) % len;                          /* np.roll over the sub-episode */
+    double x = frac1(f * c->tau * (double)kk) - ratio;                    /* f * (t % (1/f)) - high_low_ratio */
+    wave = x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0);
+  } else {
+    double t = frac1(f * c->tau * (double)k + ph);
+    if (kind == GEMB200_REF_SINUS) wave = sin(2 * M_PI * t);
+    else if (kind == GEMB200_REF_SAWTOOTH) wave = 2.0 * t - 1.0;             /* scipy.signal.sawtooth(x) */
+    else { double w = u01(cw[1]); wave = t < w ? 2.0 * t / w - 1.0 : (w + 1.0 - 2.0 * t) / (1.0 - w); } /* sawtooth(x, width) */
+  }
+  double v = A * wave + off;
+  if (v > c->ref_margin_hi[r]) v = c->ref_margin_hi[r];
+  if (v < c->ref_margin_lo[r]) v = c->ref_margin_lo[r];
+  return v;
+}
+
 static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_reset) {
   const gemb200_config* c = &o->cfg;
-  uint32_t rw[4], rs[4], rs2[4];
-  int have_w = 0, have_s = 0, have_s2 = 0;
+  uint32_t rw[4], rs[4], rs2[4], rlap[4];
+  int have_w = 0, have_s = 0, have_s2 = 0, have_lap = 0;
+  uint32_t kstep = (uint32_t)o->n_steps;
   for (int r = 0; r < c->n_ref; ++r) {
-    if (c->ref_kind[r] != GEMB200_REF_WIENER) continue;
+    int kind = c->ref_kind[r];
+    if (kind >= GEMB200_REF_SINUS) {
+      uint32_t b[4], cw[4];
+      if (e->ref_left[r] <= 0) { /* new sub-episode (subepisoded_reference_generator.py:93-100) */
+        e->ref_start[r] = kstep;
+        rng4_at(o, idx, kstep, STREAM_PERIODIC + 2 * r, b);
+        e->ref_len[r] = (uint32_t)((double)(c->ref_len_hi[r] - c->ref_len_lo[r]) * ((double)b[0] / 4294967296.0) + c->ref_len_lo[r]);
+        e->ref_left[r] = (int)e->ref_len[r];
+      } else {
+        rng4_at(o, idx, e->ref_start[r], STREAM_PERIODIC + 2 * r, b);
+      }
+      rng4_at(o, idx, e->ref_start[r], STREAM_PERIODIC + 2 * r + 1, cw);
+      e->ref_value[r] = periodic_value(o, r, kind, b, cw, kstep - e->ref_start[r], e->ref_len[r]);
+      e->ref_left[r] -= 1;
+      continue;
+    }
+    if (kind != GEMB200_REF_WIENER && kind != GEMB200_REF_LAPLACE) continue;
     if (e->ref_left[r] <= 0) {
       /* two uniforms per slot: slots 0,1 share one Philox block, slots 2,3 a second one */
       uint32_t a, b;
@@ -826,11 +883,18 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
       double l0 = log10(c->ref_sigma_lo[r]), l1 = log10(c->ref_sigma_hi[r]);
       e->ref_sigma[r] = pow(10.0, (l1 - l0) * u01(b) + l0); /* wiener_process_reference_generator.py:31 */
     }
-    if (!have_w) { rng4(o, idx, after_reset ? STREAM_WALK_R : STREAM_WALK, rw); have_w = 1; }
-    /* Box-Muller: slots (0,1) from words (0,1), slots (2,3) from words (2,3) */
-    double u1 = u01(rw[2 * (r >> 1)]), u2 = u01(rw[2 * (r >> 1) + 1]);
-    double rad = sqrt(-2.0 * log(u1));
-    double z = (r & 1) ? rad * sin(2 * M_PI * u2) : rad * cos(2 * M_PI * u2);
+    double z;
+    if (kind == GEMB200_REF_LAPLACE) { /* random_generator.laplace(0, sigma): inverse CDF, laplace_process_reference_generator.py:25-28 */
+      if (!have_lap) { rng4(o, idx, (after_reset ? STREAM_WALK_R : STREAM_WALK) + 8, rlap); have_lap = 1; }
+      double u = u01(rlap[r]);
+      z = u < 0.5 ? log(2.0 * u) : -log(2.0 * (1.0 - u));
+    } else {
+      if (!have_w) { rng4(o, idx, after_reset ? STREAM_WALK_R : STREAM_WALK, rw); have_w = 1; }
+      /* Box-Muller: slots (0,1) from words (0,1), slots (2,3) from words (2,3) */
+      double u1 = u01(rw[2 * (r >> 1)]), u2 = u01(rw[2 * (r >> 1) + 1]);
+      double rad = sqrt(-2.0 * log(u1));
+      z = (r & 1) ? rad * sin(2 * M_PI * u2) : rad * cos(2 * M_PI * u2);
+    }
     double v = e->ref_value[r] + e->ref_sigma[r] * z; /* :35-40 */
     if (v > c->ref_margin_hi[r]) v = c->ref_margin_hi[r];
     if (v < c->ref_margin_lo[r]) v = c->ref_margin_lo[r];
@@ -849,6 +913,8 @@ static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
       e->ref_value[r] = c->ref_init_lo[r] + (c->ref_init_hi[r] - c->ref_init_lo[r]) * u01(ri[r]);
       e->ref_left[r] = 0; /* _current_episode_length = -1 forces a new sub-episode */
       e->ref_sigma[r] = 0;
+    } else if (c->ref_kind[r] >= GEMB200_REF_LAPLACE) { /* SubepisodedReferenceGenerator.reset :71-91: value 0, new sub-episode */
+      e->ref_value[r] = 0.0; e->ref_left[r] = 0; e->ref_sigma[r] = 0;
     } else {
       e->ref_value[r] = c->ref_value[r];
     }
@@ -987,6 +1053,17 @@ void gem_oracle_set_reference(gem_oracle* o, const double* in) {
 /* sub-episode bookkeeping, exposed so that the device generator can be compared slot by slot */
 void gem_oracle_get_ref_aux(const gem_oracle* o, double* sigma, int32_t* left) {
   for (int64_t i = 0; i < o->cfg.n_envs; ++i) for (int r = 0; r < o->n_ref; ++r) { sigma[i * o->n_ref + r] = o->env[i].ref_sigma[r]; left[i * o->n_ref + r] = o->env[i].ref_left[r]; }
+}
+/* whole sub-episode of a periodic generator from raw Philox words (pinned against numpy/scipy formulas of the reference in
+ * tests/test_oracle_golden.py); params_out = [A, f, offset, phase/2pi, width-or-ratio uniform] */
+void gem_oracle_periodic_block(const gem_oracle* o, int r, int kind, const uint32_t* b, const uint32_t* cw, uint32_t len, double* values, double* params_out) {
+  const gemb200_config* c = &o->cfg;
+  double A = c->ref_amp_lo[r] + (c->ref_amp_hi[r] - c->ref_amp_lo[r]) * u01(b[1]);
+  double f = c->ref_freq_lo[r] + (c->ref_freq_hi[r] - c->ref_freq_lo[r]) * u01(b[2]);
+  double lo_c = (kind == GEMB200_REF_STEP ? c->ref_margin_lo[r] : -c->ref_margin_hi[r]) + A, hi_c = c->ref_margin_hi[r] - A;
+  double olo = fmin(fmax(c->ref_off_lo[r], lo_c), hi_c), ohi = fmin(fmax(c->ref_off_hi[r], lo_c), hi_c);
+  params_out[0] = A; params_out[1] = f; params_out[2] = olo + (ohi - olo) * u01(b[3]); params_out[3] = u01(cw[0]); params_out[4] = u01(cw[1]);
+  for (uint32_t k = 0; k < len; ++k) values[k] = periodic_value(o, r, kind, b, cw, k, len);
 }
 /* exposed for the known-answer tests of the reference's converter tables / solver vectors */
 void gem_oracle_philox(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_10(ctr, k0, k1); }

@@ -39,6 +39,7 @@ def lib():
             getattr(_lib, "gem_oracle_" + n).argtypes = [C.c_void_p, C.c_void_p]
         _lib.gem_oracle_get_ref_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.gem_oracle_philox.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.gem_oracle_periodic_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -105,6 +106,13 @@ class Oracle:
     def set_reference(self, r):
         r = np.ascontiguousarray(np.asarray(r, dtype=np.float64).reshape(self.n, self.n_ref))
         self._lib.gem_oracle_set_reference(self._h, _p(r))
+
+    def periodic_block(self, slot, kind, b, c, length):
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        vals, par = np.zeros(length), np.zeros(5)
+        self._lib.gem_oracle_periodic_block(self._h, slot, kind, _p(b), _p(c), length, _p(vals), _p(par))
+        return vals, par
 
     def get_ref_aux(self):
         sigma = np.zeros((self.n, self.n_ref))

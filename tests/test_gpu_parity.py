@@ -395,3 +395,42 @@ def test_random_initial_states_match_oracle(torch_cuda, oracle_lib, name, dtype)
         assert np.abs(d_obs - o_obs)[alive].max() < 50 * tol, k
         n_term += int(o_term[alive].sum())
     assert alive.mean() > 0.99 and n_term > 0
+
+
+@pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kinds", [(K.REF_LAPLACE, K.REF_WIENER), (K.REF_SINUS, K.REF_STEP), (K.REF_SAWTOOTH, K.REF_TRIANGULAR)])
+def test_more_reference_generators_match_oracle(torch_cuda, oracle_lib, kinds, dtype):
+    """Laplace / sinusoidal / step / sawtooth / triangular generators in the fused epilogue vs the oracle (same Philox blocks)."""
+    g = load_golden("pmsm_cc_rk4")
+    n, steps = 600, 160
+
+    def mk(dt):
+        cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=dt, solver="rk4", ref_kind=K.REF_WIENER,
+                               autoreset=K.AUTORESET_SAME_STEP, seed=4242)
+        for r in range(2):
+            cfg.ref_kind[r] = kinds[r]
+            cfg.ref_margin_lo[r], cfg.ref_margin_hi[r] = -0.6, 0.6
+            cfg.ref_init_lo[r], cfg.ref_init_hi[r] = -0.6, 0.6
+            cfg.ref_amp_lo[r], cfg.ref_amp_hi[r] = 0.05, 0.6
+            cfg.ref_freq_lo[r], cfg.ref_freq_hi[r] = 20.0, 400.0
+            cfg.ref_off_lo[r], cfg.ref_off_hi[r] = -0.6, 0.6
+            cfg.ref_len_lo[r], cfg.ref_len_hi[r] = 7, 45
+        return cfg
+
+    dev = DeviceAdapter(mk(dtype))
+    ora = oracle_lib.Oracle(mk(K.F64), nthreads=8)
+    _, o_ref = ora.reset()
+    _, d_ref = dev.reset()
+    tol = 1e-9 if dtype == K.F64 else 2e-4
+    bad = int((np.abs(d_ref - o_ref) > tol).sum())
+    total = d_ref.size
+    rng = np.random.default_rng(1)
+    for k in range(steps):
+        a = rng.uniform(-0.3, 0.3, size=(n, 3))
+        _, o_ref, o_rew, o_term = ora.step(a)
+        _, d_ref, d_rew, d_term = dev.step(a)
+        assert not o_term.any() and not d_term.any()
+        bad += int((np.abs(d_ref - o_ref) > tol).sum())
+        total += d_ref.size
+    # discontinuous waves may differ exactly at an edge in fp32 (phase rounding); everything else has to agree
+    assert bad <= (0 if dtype == K.F64 else 0.004 * total), (bad, total)
