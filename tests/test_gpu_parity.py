@@ -436,3 +436,15 @@ def test_more_reference_generators_match_oracle(torch_cuda, oracle_lib, kinds, d
     assert alive.mean() > 0.99
     # discontinuous waves may differ exactly at an edge in fp32 (phase rounding); everything else has to agree
     assert bad <= (0 if dtype == K.F64 else 0.004 * total), (bad, total)
+
+
+def test_vector_facade_steps(torch_cuda):
+    import gym_electric_motor_b200 as gem
+
+    venv = gem.vector.make_vec("Cont-CC-PMSM-v0", num_envs=64, flatten_obs=True, ode_solver=gem.physical_systems.RK4Solver())
+    obs, info = venv.reset(seed=1)
+    assert tuple(obs.shape) == (64, 16)
+    for _ in range(5):
+        obs, rew, term, trunc, info = venv.step(torch_cuda.zeros((64, 3), device="cuda"))
+    assert tuple(rew.shape) == (64,) and term.dtype == torch_cuda.bool and not trunc.any()
+    venv.close()

@@ -173,3 +173,11 @@ def test_random_initialiser_bounds_match_reference():
         gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(random_init="uniform")))
     with pytest.raises(NotImplementedError):
         gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="gaussian")))
+
+
+def test_vector_facade_spaces():
+    venv = gem.vector.make_vec("Cont-CC-PMSM-v0", num_envs=8, flatten_obs=True)
+    assert venv.num_envs == 8 and venv.single_observation_space.shape == (16,) and venv.observation_space.shape == (8, 16)
+    assert venv.single_action_space.shape == (3,) and venv.action_space.shape == (8, 3)
+    v2 = gem.vector.make_vec("Finite-CC-PMSM-v0", num_envs=4)
+    assert v2.single_action_space.n == 8 and len(v2.observation_space.spaces) == 2
