@@ -1,17 +1,26 @@
 """Build libgemb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python -m gym_electric_motor_b200.build [--force] [--verbose]
+
+The step kernel's 200 instantiations are spread over ten translation units (motor family x real, csrc/gemb200_step_tu.cu)
+that compile in parallel; objects go to build/ (git- and gpurun-ignored), only the linked .so stays in the package.
 """
+import hashlib
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "gemb200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "gemb200_kernels.cuh"), os.path.join(HERE, "csrc", "gemb200_params.h"),
-        os.path.join(HERE, "..", "include", "gemb200.h")]
+CSRC = os.path.join(HERE, "csrc")
+HEADERS = [os.path.join(CSRC, "gemb200_kernels.cuh"), os.path.join(CSRC, "gemb200_params.h"), os.path.join(CSRC, "gemb200_launch.cuh"),
+           os.path.join(HERE, "..", "include", "gemb200.h")]
+SOURCES = [os.path.join(CSRC, "gemb200.cu"), os.path.join(CSRC, "gemb200_step_tu.cu")]
 OUT = os.path.join(HERE, "libgemb200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+OBJ_DIR = os.path.join(HERE, "..", "build", "gemb200")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+FAMILIES = (0, 1, 2, 3, 4)  # gemb200_params.h: MotorFamily
+REALS = ("float", "double")
 
 
 def nvcc_path():
@@ -21,23 +30,59 @@ def nvcc_path():
     return "nvcc"
 
 
-def is_stale():
-    if not os.path.exists(OUT):
+def is_stale(out=OUT):
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in HEADERS + SOURCES if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
-        return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
-        sys.stdout.write(res.stdout)
+def _units(only=None):
+    units = [("host", SOURCES[0], [])]
+    for fam in FAMILIES:
+        for real in REALS:
+            if only and (fam, real) not in only:
+                continue
+            units.append((f"step_f{fam}_{real}", SOURCES[1], [f"-DGEMB200_TU_FAM={fam}", f"-DGEMB200_TU_REAL={real}"]))
+    return units
+
+
+def build(force=False, verbose=False, out=OUT, defines=(), only=None, jobs=None):
+    """Compile and link.  `defines`/`only`/`out` are for experiment builds (tools/variant_bench.py): extra -D flags, a subset of
+    (family, real) units (a missing unit makes the library fail to LOAD, on purpose: no silent holes), another output path."""
+    if not force and not is_stale(out):
+        return out
+    tag = hashlib.sha1(("|".join(defines) + "|" + os.path.abspath(out)).encode()).hexdigest()[:10]
+    obj_dir = os.path.join(OBJ_DIR, tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = nvcc_path()
+    extra = list(defines) + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(unit):
+        name, src, flags = unit
+        obj = os.path.join(obj_dir, name + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + flags + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return obj, res
+
+    units = _units(only)
+    with ThreadPoolExecutor(max_workers=jobs or min(len(units), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, units))
+    objs = []
+    for obj, res in results:
+        if verbose or res.returncode != 0:
+            sys.stdout.write(res.stdout)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed building libgemb200.so")
+        objs.append(obj)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
+    if only:
+        link += ["-Xlinker", "--unresolved-symbols=ignore-all"]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libgemb200.so")
-    return OUT
+        sys.stdout.write(res.stdout)
+        raise RuntimeError("link of libgemb200.so failed")
+    return out
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@
 #include <new>
 #include <string>
 
-#include "gemb200_kernels.cuh"
+#include "gemb200_launch.cuh"
 
 using namespace gemb200;
 
@@ -263,6 +263,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->env_begin = 0; p->env_end = c.n_envs;
   p->env_offset = c.env_index_offset;
   p->seed_lo = (uint32_t)c.seed; p->seed_hi = (uint32_t)(c.seed >> 32);
+  for (int r = 0; r < 10; ++r) { p->rk[r][0] = p->seed_lo + (uint32_t)r * 0x9E3779B9u; p->rk[r][1] = p->seed_hi + (uint32_t)r * 0xBB67AE85u; }
   p->st = static_cast<real*>(h->d_st);
   p->stc = static_cast<real*>(h->d_stc);
   p->kstep = 0;
@@ -326,20 +327,34 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     const double unit = sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0;
     p->init_lo[dm.nx] = (real)(c.init_lo[dm.nx] * unit); p->init_span[dm.nx] = (real)((c.init_hi[dm.nx] - c.init_lo[dm.nx]) * unit);
   }
-  p->n_constraints = c.n_constraints;
   for (int i = 0; i < c.n_constraints; ++i) {
-    p->con_kind[i] = c.constraint_kind[i];
-    int cnt = 0;
-    for (int j = 0; j < dm.n_state; ++j) if ((c.constraint_mask[i] >> j) & 1u) p->con_idx[i][cnt++] = (uint8_t)j;
-    p->con_cnt[i] = cnt;
+    if (c.constraint_kind[i] == GEMB200_CONSTRAINT_SQUARED) {
+      int cnt = 0;
+      for (int j = 0; j < dm.n_state; ++j) if ((c.constraint_mask[i] >> j) & 1u) p->sq_idx[p->n_sq][cnt++] = j;
+      p->sq_cnt[p->n_sq++] = cnt;
+    } else {
+      for (int j = 0; j < dm.n_state; ++j) {
+        if (!((c.constraint_mask[i] >> j) & 1u)) continue;
+        bool seen = false;
+        for (int q = 0; q < p->n_lim; ++q) seen = seen || p->lim_idx[q] == j;
+        if (!seen) p->lim_idx[p->n_lim++] = j;
+      }
+    }
   }
   // WeightedSumOfErrors: only non-zero weights become terms (weighted_sum_of_errors.py:128-129)
   int t = 0;
   for (int j = 0; j < dm.n_state; ++j) {
     if (c.reward_weight[j] == 0.0) continue;
+    int slot = -1;
+    for (int r = 0; r < c.n_ref; ++r) if (c.ref_state[r] == j) slot = r;  // the last generator of a state wins (multiple_reference_generator.py:70-78)
+    if (slot >= 0) {
+      p->rwr_w[slot] = (real)c.reward_weight[j];
+      p->rwr_inv_len[slot] = (real)(1.0 / c.state_length[j]);
+      p->rwr_pow[slot] = (real)c.reward_power[j];
+      p->rwr_pow1[slot] = c.reward_power[j] == 1.0;
+      continue;
+    }
     p->rw_state[t] = j;
-    p->rw_ref[t] = kMaxRef;
-    for (int r = 0; r < c.n_ref; ++r) if (c.ref_state[r] == j) p->rw_ref[t] = r;
     p->rw_w[t] = (real)c.reward_weight[j];
     p->rw_inv_len[t] = (real)(1.0 / c.state_length[j]);
     p->rw_pow[t] = (real)c.reward_power[j];
@@ -347,6 +362,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     ++t;
   }
   p->n_rw = t;
+  for (int r = 0; r < kMaxRef; ++r) if (p->rwr_w[r] == real(0)) p->rwr_pow1[r] = 1;  // unused slots: no pow()
   p->bias = (real)c.reward_bias; p->viol_reward = (real)c.violation_reward;
   p->n_ref = c.n_ref;
   p->any_wiener = h->any_wiener;
@@ -368,73 +384,8 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// kernel dispatch
+// kernel dispatch (the instantiations live in gemb200_step_tu.cu, one TU per family x real)
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int kBlock = GEMB200_BLOCK;
-
-#ifndef GEMB200_PERSISTENT
-#define GEMB200_PERSISTENT 0  /* measured slower, see the note in step_kernel */
-#endif
-
-// Persistent launch shape: at most as many CTAs as can be resident (SMs x occupancy), each thread looping over
-// ceil(range / resident threads) envs; the grid is then shrunk so that every thread gets the same trip count (no tail wave).
-template <int FAM, bool FINITE, typename real, int NREF, bool SOA>
-static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
-  const size_t smem = ((size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD + (size_t)kBlock * kRefPad) * sizeof(real);
-  const int range = p.env_end - p.env_begin;
-  int grid = (range + kBlock - 1) / kBlock;
-#if GEMB200_PERSISTENT
-  static int resident = 0;  // per template instantiation
-  if (resident == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<FAM, FINITE, real, NREF, SOA>, kBlock, smem);
-    resident = sms * (per_sm > 0 ? per_sm : 1);
-  }
-  if (grid > resident) {
-    const int iters = (grid + resident - 1) / resident;
-    grid = (grid + iters - 1) / iters;
-  }
-#endif
-  step_kernel<FAM, FINITE, real, NREF, SOA><<<grid, kBlock, smem, st>>>(p);
-  return cudaGetLastError();
-}
-template <int FAM, typename real, int NREF>
-static cudaError_t launch_reset_t(const StepParams<real>& p, cudaStream_t st) {
-  const int grid = (p.n + 255) / 256;
-  reset_kernel<FAM, real, NREF><<<grid, 256, 0, st>>>(p);
-  return cudaGetLastError();
-}
-
-template <int FAM, typename real>
-static cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
-#define GEMB200_NREF(R)                                                                         \
-  case R:                                                                                       \
-    if (p.layout == GEMB200_LAYOUT_SOA) return finite ? launch_step_t<FAM, true, real, R, true>(p, st) : launch_step_t<FAM, false, real, R, true>(p, st); \
-    return finite ? launch_step_t<FAM, true, real, R, false>(p, st) : launch_step_t<FAM, false, real, R, false>(p, st);
-  switch (nref) {
-    GEMB200_NREF(0)
-    GEMB200_NREF(1)
-    GEMB200_NREF(2)
-    GEMB200_NREF(3)
-    GEMB200_NREF(4)
-  }
-#undef GEMB200_NREF
-  return cudaErrorInvalidValue;
-}
-template <int FAM, typename real>
-static cudaError_t launch_reset_f(int nref, const StepParams<real>& p, cudaStream_t st) {
-  switch (nref) {
-    case 0: return launch_reset_t<FAM, real, 0>(p, st);
-    case 1: return launch_reset_t<FAM, real, 1>(p, st);
-    case 2: return launch_reset_t<FAM, real, 2>(p, st);
-    case 3: return launch_reset_t<FAM, real, 3>(p, st);
-    case 4: return launch_reset_t<FAM, real, 4>(p, st);
-  }
-  return cudaErrorInvalidValue;
-}
-
 template <typename real>
 static cudaError_t launch_step(int fam, bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
   switch (fam) {

@@ -1,0 +1,65 @@
+// gemb200_launch.cuh — step/reset kernel dispatch for ONE (motor family, real) pair.
+//
+// The step kernel has 5 families x {cont, finite} x {fp32, fp64} x NREF 0..4 x {AoS, SoA} = 200 instantiations; each
+// (family, real) pair is compiled in its own translation unit (gemb200_step_tu.cu with -DGEMB200_TU_FAM / -DGEMB200_TU_REAL) so that
+// the library builds in parallel.  gemb200.cu only sees the declarations below.
+#pragma once
+#include "gemb200_kernels.cuh"
+
+namespace gemb200 {
+
+template <int FAM, typename real> cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st);
+template <int FAM, typename real> cudaError_t launch_reset_f(int nref, const StepParams<real>& p, cudaStream_t st);
+
+#ifdef GEMB200_TU_FAM
+constexpr int kBlock = GEMB200_BLOCK;
+
+template <int FAM, bool FINITE, typename real, int NREF, bool SOA>
+static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
+  const size_t smem = (size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD * sizeof(real);
+  const int range = p.env_end - p.env_begin;
+  const int grid = (range + kBlock - 1) / kBlock;
+  step_kernel<FAM, FINITE, real, NREF, SOA><<<grid, kBlock, smem, st>>>(p);
+  return cudaGetLastError();
+}
+template <int FAM, typename real, int NREF>
+static cudaError_t launch_reset_t(const StepParams<real>& p, cudaStream_t st) {
+  const int grid = (p.n + 255) / 256;
+  reset_kernel<FAM, real, NREF><<<grid, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int FAM, typename real>
+cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
+#define GEMB200_NREF(R)                                                                         \
+  case R:                                                                                       \
+    if (p.layout == GEMB200_LAYOUT_SOA) return finite ? launch_step_t<FAM, true, real, R, true>(p, st) : launch_step_t<FAM, false, real, R, true>(p, st); \
+    return finite ? launch_step_t<FAM, true, real, R, false>(p, st) : launch_step_t<FAM, false, real, R, false>(p, st);
+  switch (nref) {
+    GEMB200_NREF(0)
+    GEMB200_NREF(1)
+    GEMB200_NREF(2)
+    GEMB200_NREF(3)
+    GEMB200_NREF(4)
+  }
+#undef GEMB200_NREF
+  return cudaErrorInvalidValue;
+}
+template <int FAM, typename real>
+cudaError_t launch_reset_f(int nref, const StepParams<real>& p, cudaStream_t st) {
+  switch (nref) {
+    case 0: return launch_reset_t<FAM, real, 0>(p, st);
+    case 1: return launch_reset_t<FAM, real, 1>(p, st);
+    case 2: return launch_reset_t<FAM, real, 2>(p, st);
+    case 3: return launch_reset_t<FAM, real, 3>(p, st);
+    case 4: return launch_reset_t<FAM, real, 4>(p, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+
+template cudaError_t launch_step_f<GEMB200_TU_FAM, GEMB200_TU_REAL>(bool, int, const StepParams<GEMB200_TU_REAL>&, cudaStream_t);
+template cudaError_t launch_reset_f<GEMB200_TU_FAM, GEMB200_TU_REAL>(int, const StepParams<GEMB200_TU_REAL>&, cudaStream_t);
+#endif
+
+}  // namespace gemb200

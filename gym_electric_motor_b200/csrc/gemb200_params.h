@@ -57,6 +57,7 @@ struct StepParams {
   int32_t env_begin, env_end;  // sub-range of envs processed by this launch (chunked host-buffer pipeline); default [0, n)
   int64_t env_offset;     // global index of env 0 (sharding)
   uint32_t seed_lo, seed_hi;
+  uint32_t rk[10][2];     // Philox4x32-10 round keys: seed + r * (0x9E3779B9, 0xBB67AE85)
   uint32_t gstep_lo, gstep_hi;  // unique id of this API call (reset or step): RNG counter words 0,1
   // ---- persistent per-env state (owned by the handle) ----
   // `st`  (hot):  [x_1..x_{NX-1} | ref value per slot]            hot_words() words per env
@@ -110,15 +111,19 @@ struct StepParams {
   real reset_obs[kMaxState];  // observation right after a reset (constant initial state)
   int32_t init_random;        // 1: uniform initial state per reset (init_lo + init_span * U); the angle entry [NX] is in the stored unit
   real init_lo[kMaxX + 1], init_span[kMaxX + 1];
-  // ---- constraint monitor ----
-  int32_t n_constraints;
-  int32_t con_kind[kMaxConstraints];
-  int32_t con_cnt[kMaxConstraints];
-  uint8_t con_idx[kMaxConstraints][kMaxState];  // observed state indices per constraint
-  // ---- reward: sum over n_rw terms  w * (|s[idx] - ref| * inv_len)^pow ----
+  // ---- constraint monitor: merge = max, so all LimitConstraints collapse into ONE list of observed states; every
+  //      SquaredConstraint keeps its own list ----
+  int32_t n_lim;
+  int32_t lim_idx[kMaxState];
+  int32_t n_sq;
+  int32_t sq_cnt[kMaxConstraints];
+  int32_t sq_idx[kMaxConstraints][kMaxState];
+  // ---- reward: sum of  w * (|s[idx] - ref| * inv_len)^pow.  Terms of referenced states are indexed by reference slot (the
+  //      reference value is then a register); rw_* are the weighted states WITHOUT a reference (compared with 0) ----
+  real rwr_w[kMaxRef], rwr_inv_len[kMaxRef], rwr_pow[kMaxRef];
+  int32_t rwr_pow1[kMaxRef];
   int32_t n_rw;
   int32_t rw_state[kMaxState];
-  int32_t rw_ref[kMaxState];   // reference slot, or kMaxRef for "no reference" (value 0)
   int32_t rw_pow1[kMaxState];  // 1 if power == 1
   real rw_w[kMaxState];
   real rw_inv_len[kMaxState];
