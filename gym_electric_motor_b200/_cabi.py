@@ -7,8 +7,8 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 1
-MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM = 24, 8, 4, 4, 4, 16
+ABI_VERSION = 2
+MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 24, 8, 4, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
 MOTOR_PERMEX_DC, MOTOR_SERIES_DC, MOTOR_SHUNT_DC, MOTOR_EXTEX_DC, MOTOR_PMSM, MOTOR_SYNRM, MOTOR_EESM, MOTOR_SCIM = range(8)
@@ -23,6 +23,8 @@ REF_CONST, REF_WIENER, REF_EXTERNAL, REF_LAPLACE, REF_SINUS, REF_STEP, REF_SAWTO
 F32, F64 = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 AUTORESET_NONE, AUTORESET_SAME_STEP = 0, 1
+SOP_NONE, SOP_COS_SIN, SOP_FLUX_OBSERVER, SOP_NOISE = range(4)
+NOISE_NORMAL, NOISE_UNIFORM, NOISE_LAPLACE = range(3)
 
 E_INVALID, E_CUDA, E_NOMEM, E_ABI = -1, -2, -3, -4
 
@@ -87,6 +89,11 @@ class GemB200Config(C.Structure):
         ("ref_freq_hi", C.c_double * MAX_REF),
         ("ref_off_lo", C.c_double * MAX_REF),
         ("ref_off_hi", C.c_double * MAX_REF),
+        ("n_state_ops", C.c_int32),
+        ("sop_kind", C.c_int32 * MAX_STATE_OPS),
+        ("sop_idx", (C.c_int32 * 4) * MAX_STATE_OPS),
+        ("sop_mask", C.c_uint32 * MAX_STATE_OPS),
+        ("sop_param", (C.c_double * 8) * MAX_STATE_OPS),
     ]
 
 

@@ -39,6 +39,8 @@ struct gemb200_handle {
   uint16_t* d_sw = nullptr;
   void* d_fifo = nullptr;
   int fifo_dim = 0;
+  void* d_obsv = nullptr;  // FluxObserver integrator [2][n]
+  int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
   StepParams<double> pd;
   uint64_t gstep = 0;
@@ -57,7 +59,7 @@ struct gemb200_handle {
 // ----------------------------------------------------------------------------------------------------------------
 static bool is_qc(int k) { return k == GEMB200_CONV_1QC || k == GEMB200_CONV_2QC || k == GEMB200_CONV_4QC; }
 
-struct Dims { int fam, n_state, n_ode, n_act, nx; bool has_eps; };
+struct Dims { int fam, n_state, n_ode, n_act, nx; bool has_eps; int n_obs = 0; bool has_observer = false; };  // n_state: the system's own vector, n_obs: after the wrappers
 
 static int derive_dims(const gemb200_config* c, Dims* d) {
   const int k0 = c->converter_kind[0], k1 = c->converter_kind[1];
@@ -77,6 +79,34 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
     if (!three_phase || c->finite) return fail(GEMB200_E_INVALID, "dq actions need a three-phase motor with a continuous converter");
     d->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2;
   }
+  // state-vector wrappers (gemb200_state_op): width bookkeeping as in the wrappers' set_physical_system
+  d->n_obs = d->n_state;
+  if (c->n_state_ops < 0 || c->n_state_ops > GEMB200_MAX_STATE_OPS) return fail(GEMB200_E_INVALID, "n_state_ops out of range");
+  for (int k = 0; k < c->n_state_ops; ++k) {
+    switch (c->sop_kind[k]) {
+      case GEMB200_SOP_COS_SIN:
+        if (c->sop_idx[k][0] < 0 || c->sop_idx[k][0] >= d->n_obs) return fail(GEMB200_E_INVALID, "CosSinProcessor: angle index out of range");
+        d->n_obs += c->sop_idx[k][1] ? 1 : 2;
+        break;
+      case GEMB200_SOP_FLUX_OBSERVER:
+        if (c->motor_kind != GEMB200_MOTOR_SCIM) return fail(GEMB200_E_INVALID, "FluxObserver needs an induction motor (flux_observer.py:57-60)");
+        if (d->has_observer) return fail(GEMB200_E_INVALID, "only one FluxObserver per system");
+        for (int q = 0; q < 4; ++q)
+          if (c->sop_idx[k][q] < 0 || c->sop_idx[k][q] >= d->n_obs) return fail(GEMB200_E_INVALID, "FluxObserver: state index out of range");
+        if (!(c->sop_param[k][3] > 0)) return fail(GEMB200_E_INVALID, "FluxObserver: psi_limit must be positive");
+        d->has_observer = true;
+        d->n_obs += 2;
+        break;
+      case GEMB200_SOP_NOISE:
+        if (c->sop_idx[k][0] < GEMB200_NOISE_NORMAL || c->sop_idx[k][0] > GEMB200_NOISE_LAPLACE) return fail(GEMB200_E_INVALID, "StateNoiseProcessor: unknown distribution");
+        if (d->n_obs < 32 && (c->sop_mask[k] >> d->n_obs) != 0) return fail(GEMB200_E_INVALID, "StateNoiseProcessor: state index out of range");
+        break;
+      default: return fail(GEMB200_E_INVALID, "unknown state op");
+    }
+    if (d->n_obs > GEMB200_MAX_STATE) return fail(GEMB200_E_INVALID, "state vector too long");
+  }
+  if (c->action_dq == 2 && !(c->motor_kind == GEMB200_MOTOR_SCIM && d->has_observer))
+    return fail(GEMB200_E_INVALID, "action_dq = 2 (observer angle) needs a SCIM with a FluxObserver");
   if (three_phase) {
     if (k0 != GEMB200_CONV_B6) return fail(GEMB200_E_INVALID, "three-phase motors need a B6 bridge in converter slot 0");
     if (c->motor_kind == GEMB200_MOTOR_EESM) {
@@ -117,7 +147,7 @@ static int validate(const gemb200_config* c) {
     return fail(GEMB200_E_INVALID, "finite EESM with interlocking time: the reference raises in this configuration "
                                    "(physical_systems.py:632 slices u_in[:2]); not supported");
   for (int r = 0; r < c->n_ref; ++r) {
-    if (c->ref_state[r] < 0 || c->ref_state[r] >= d.n_state) return fail(GEMB200_E_INVALID, "ref_state out of range");
+    if (c->ref_state[r] < 0 || c->ref_state[r] >= d.n_obs) return fail(GEMB200_E_INVALID, "ref_state out of range");
     if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_TRIANGULAR) return fail(GEMB200_E_INVALID, "bad ref_kind");
     const bool subep = c->ref_kind[r] == GEMB200_REF_WIENER || c->ref_kind[r] >= GEMB200_REF_LAPLACE;
     const bool walk = c->ref_kind[r] == GEMB200_REF_WIENER || c->ref_kind[r] == GEMB200_REF_LAPLACE;
@@ -131,7 +161,7 @@ static int validate(const gemb200_config* c) {
     if (!(c->limits[j] != 0.0) && !(c->motor_kind == GEMB200_MOTOR_SHUNT_DC && j == 6)) return fail(GEMB200_E_INVALID, "limits must be non-zero");
   const double j_total = c->load_param[GEMB200_LP_J_LOAD] + c->motor_param[GEMB200_MP_J_ROTOR];
   if (c->load_kind == GEMB200_LOAD_POLY_STATIC && !(j_total > 0)) return fail(GEMB200_E_INVALID, "total inertia must be positive");
-  if ((int64_t)c->n_envs * (int64_t)(hot_words(d.nx, c->n_ref) + cold_words(d.nx, c->n_ref) > d.n_state ? hot_words(d.nx, c->n_ref) + cold_words(d.nx, c->n_ref) : d.n_state) >= (int64_t)1 << 31)
+  if ((int64_t)c->n_envs * (int64_t)(hot_words(d.nx, c->n_ref) + cold_words(d.nx, c->n_ref) > d.n_obs ? hot_words(d.nx, c->n_ref) + cold_words(d.nx, c->n_ref) : d.n_obs) >= (int64_t)1 << 31)
     return fail(GEMB200_E_INVALID, "n_envs too large for 32-bit element indexing in one handle; shard the batch");
   return GEMB200_OK;
 }
@@ -330,10 +360,10 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   for (int i = 0; i < c.n_constraints; ++i) {
     if (c.constraint_kind[i] == GEMB200_CONSTRAINT_SQUARED) {
       int cnt = 0;
-      for (int j = 0; j < dm.n_state; ++j) if ((c.constraint_mask[i] >> j) & 1u) p->sq_idx[p->n_sq][cnt++] = j;
+      for (int j = 0; j < dm.n_obs; ++j) if ((c.constraint_mask[i] >> j) & 1u) p->sq_idx[p->n_sq][cnt++] = j;
       p->sq_cnt[p->n_sq++] = cnt;
     } else {
-      for (int j = 0; j < dm.n_state; ++j) {
+      for (int j = 0; j < dm.n_obs; ++j) {
         if (!((c.constraint_mask[i] >> j) & 1u)) continue;
         bool seen = false;
         for (int q = 0; q < p->n_lim; ++q) seen = seen || p->lim_idx[q] == j;
@@ -343,7 +373,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   }
   // WeightedSumOfErrors: only non-zero weights become terms (weighted_sum_of_errors.py:128-129)
   int t = 0;
-  for (int j = 0; j < dm.n_state; ++j) {
+  for (int j = 0; j < dm.n_obs; ++j) {
     if (c.reward_weight[j] == 0.0) continue;
     int slot = -1;
     for (int r = 0; r < c.n_ref; ++r) if (c.ref_state[r] == j) slot = r;  // the last generator of a state wins (multiple_reference_generator.py:70-78)
@@ -364,6 +394,16 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->n_rw = t;
   for (int r = 0; r < kMaxRef; ++r) if (p->rwr_w[r] == real(0)) p->rwr_pow1[r] = 1;  // unused slots: no pow()
   p->bias = (real)c.reward_bias; p->viol_reward = (real)c.violation_reward;
+  p->n_sops = c.n_state_ops;
+  p->n_obs = dm.n_obs;
+  p->row_stride = h->row_stride;
+  p->obsv = static_cast<real*>(h->d_obsv);
+  for (int k = 0; k < c.n_state_ops; ++k) {
+    p->sop_kind[k] = c.sop_kind[k];
+    p->sop_mask[k] = c.sop_mask[k];
+    for (int q = 0; q < 4; ++q) p->sop_idx[k][q] = c.sop_idx[k][q];
+    for (int q = 0; q < 8; ++q) p->sop_param[k][q] = (real)c.sop_param[k][q];
+  }
   p->n_ref = c.n_ref;
   p->any_wiener = h->any_wiener;
   p->ref_tau = (real)c.tau;
@@ -495,7 +535,7 @@ int gemb200_query_dims(const gemb200_config* cfg, int32_t* n_state, int32_t* n_o
   Dims d;
   int rc = derive_dims(cfg, &d);
   if (rc) return rc;
-  if (n_state) *n_state = d.n_state;
+  if (n_state) *n_state = d.n_obs;
   if (n_ode) *n_ode = d.n_ode;
   if (n_act) *n_act = d.n_act;
   if (n_ref) *n_ref = cfg->n_ref;
@@ -517,6 +557,8 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   Dims d;
   derive_dims(cfg, &d);
   h->fam = d.fam; h->n_state = d.n_state; h->n_ode = d.n_ode; h->n_act = d.n_act; h->nx = d.nx; h->has_eps = d.has_eps;
+  h->n_obs = d.n_obs;
+  h->row_stride = cfg->n_state_ops > 0 ? (d.n_obs | 1) : (d.fam == kEESM ? 17 : d.n_state);  // Fam<>::PAD without wrappers
   h->n_ref = cfg->n_ref;
   h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
   h->two_segment = cfg->finite && cfg->interlocking_time > 0;
@@ -540,6 +582,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   }
   if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
   if (h->two_segment) ALLOC(h->d_sw, n * sizeof(uint16_t));
+  if (d.has_observer) ALLOC(h->d_obsv, n * 2 * h->rsz);
 #undef ALLOC
   Derived dv;
   derive_model(cfg, d, &dv);
@@ -558,7 +601,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -601,7 +644,7 @@ static int ensure_host_buffers(gemb200_handle* h) {
   CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
   for (int k = 0; k < 3; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&h->hpipe[k], cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&h->d_act, n * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz)));
-  CUDA_TRY(cudaMalloc(&h->d_obs, n * h->n_state * h->rsz));
+  CUDA_TRY(cudaMalloc(&h->d_obs, n * h->n_obs * h->rsz));
   CUDA_TRY(cudaMalloc(&h->d_ref, n * (h->n_ref > 0 ? h->n_ref : 1) * h->rsz));
   CUDA_TRY(cudaMalloc(&h->d_rew, n * h->rsz));
   CUDA_TRY(cudaMalloc((void**)&h->d_term, n));
@@ -633,7 +676,7 @@ int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void
     first = false;
     if (rc) return rc;
     if (pipelined) {
-      const size_t os = (size_t)h->n_state * h->rsz, rs = (size_t)h->n_ref * h->rsz;
+      const size_t os = (size_t)h->n_obs * h->rsz, rs = (size_t)h->n_ref * h->rsz;
       if (obs_out) CUDA_TRY(cudaMemcpyAsync((char*)obs_out + b * os, (char*)h->d_obs + b * os, (e - b) * os, cudaMemcpyDeviceToHost, st));
       if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync((char*)ref_out + b * rs, (char*)h->d_ref + b * rs, (e - b) * rs, cudaMemcpyDeviceToHost, st));
       if (reward_out) CUDA_TRY(cudaMemcpyAsync((char*)reward_out + b * h->rsz, (char*)h->d_rew + b * h->rsz, (e - b) * h->rsz, cudaMemcpyDeviceToHost, st));
@@ -645,7 +688,7 @@ int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void
     return GEMB200_OK;
   }
   cudaStream_t st = h->hstream;
-  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_state * h->rsz, cudaMemcpyDeviceToHost, st));
+  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_obs * h->rsz, cudaMemcpyDeviceToHost, st));
   if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(ref_out, h->d_ref, n * h->n_ref * h->rsz, cudaMemcpyDeviceToHost, st));
   if (reward_out) CUDA_TRY(cudaMemcpyAsync(reward_out, h->d_rew, n * h->rsz, cudaMemcpyDeviceToHost, st));
   if (terminated_out) CUDA_TRY(cudaMemcpyAsync(terminated_out, h->d_term, n, cudaMemcpyDeviceToHost, st));
@@ -663,12 +706,12 @@ int gemb200_reset_host(gemb200_handle* h, const uint8_t* reset_mask, void* obs_o
   if (reset_mask) CUDA_TRY(cudaMemcpyAsync(h->d_mask, reset_mask, n, cudaMemcpyHostToDevice, st));
   if (reset_mask && (obs_out || ref_out)) {
     // unmasked envs keep the caller's previous values: pre-load the device staging buffers with them
-    if (obs_out) CUDA_TRY(cudaMemcpyAsync(h->d_obs, obs_out, n * h->n_state * h->rsz, cudaMemcpyHostToDevice, st));
+    if (obs_out) CUDA_TRY(cudaMemcpyAsync(h->d_obs, obs_out, n * h->n_obs * h->rsz, cudaMemcpyHostToDevice, st));
     if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(h->d_ref, ref_out, n * h->n_ref * h->rsz, cudaMemcpyHostToDevice, st));
   }
   rc = do_reset(h, reset_mask ? h->d_mask : nullptr, obs_out ? h->d_obs : nullptr, (ref_out && h->n_ref) ? h->d_ref : nullptr, st);
   if (rc) return rc;
-  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_state * h->rsz, cudaMemcpyDeviceToHost, st));
+  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->d_obs, n * h->n_obs * h->rsz, cudaMemcpyDeviceToHost, st));
   if (ref_out && h->n_ref) CUDA_TRY(cudaMemcpyAsync(ref_out, h->d_ref, n * h->n_ref * h->rsz, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return GEMB200_OK;
@@ -727,6 +770,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_eps) s[k++] = {h->d_eps, n * sizeof(double)};
   if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
   if (h->d_fifo) s[k++] = {h->d_fifo, n * h->cfg.dead_time_steps * h->fifo_dim * h->rsz};
+  if (h->d_obsv) s[k++] = {h->d_obsv, n * 2 * h->rsz};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {

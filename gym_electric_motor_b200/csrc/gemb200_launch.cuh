@@ -16,7 +16,7 @@ constexpr int kBlock = GEMB200_BLOCK;
 
 template <int FAM, bool FINITE, typename real, int NREF, bool SOA>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
-  const size_t smem = (size_t)(kBlock / 32) * 32 * Fam<FAM>::PAD * sizeof(real);
+  const size_t smem = (size_t)kBlock * (size_t)p.row_stride * sizeof(real);
   const int range = p.env_end - p.env_begin;
   const int grid = (range + kBlock - 1) / kBlock;
   step_kernel<FAM, FINITE, real, NREF, SOA><<<grid, kBlock, smem, st>>>(p);

@@ -12,6 +12,7 @@ namespace gemb200 {
 constexpr int kMaxState = 24;
 constexpr int kMaxRef = 4;
 constexpr int kMaxConstraints = 4;
+constexpr int kMaxStateOps = 4;
 constexpr int kMaxX = 6;  // real-typed ODE states per env (omega + motor states without the angle): SCIM 5
 
 // words of persistent state per env and their placement (shared by host and device code)
@@ -46,8 +47,10 @@ enum : uint32_t {
   kStreamWalk = 1, kStreamSubep = 2, kStreamInit = 3, kStreamSubepHi = 18,
   kStreamWalkR = 5, kStreamSubepR = 6, kStreamSubepHiR = 22,  // "R": draws made right after an in-kernel auto-reset
   kStreamInitState = 7, kStreamInitState2 = 8,                // random initial ODE state
-  kStreamPeriodic = 32                                        // + 2*slot (+1): sub-episode parameters of the periodic generators,
+  kStreamPeriodic = 32,                                       // + 2*slot (+1): sub-episode parameters of the periodic generators,
                                                               //   counter word 0 = step index of the sub-episode start
+  kStreamNoise = 64,                                          // + 8*op + (state index >> 2): StateNoiseProcessor draws
+  kStreamNoiseR = 128                                         //   ... right after an in-kernel auto-reset
 };
 
 template <typename real>
@@ -142,6 +145,15 @@ struct StepParams {
   // periodic generators (sinus / step / sawtooth / triangular): parameter ranges per slot, tau for the phase increment
   real ref_amp_lo[kMaxRef], ref_amp_span[kMaxRef], ref_freq_lo[kMaxRef], ref_freq_span[kMaxRef], ref_off_lo[kMaxRef], ref_off_hi[kMaxRef];
   real ref_tau;
+  // ---- state-vector wrappers (gemb200.h: gemb200_state_op), applied in order after the system's own vector is assembled ----
+  int32_t n_sops;
+  int32_t row_stride;      // shared-memory words per staged row: Fam::PAD without wrappers, else (final width | 1)
+  int32_t n_obs;           // final width of the observation
+  int32_t sop_kind[kMaxStateOps];
+  int32_t sop_idx[kMaxStateOps][4];
+  uint32_t sop_mask[kMaxStateOps];
+  real sop_param[kMaxStateOps][8];
+  real* obsv;              // [2][n] FluxObserver integrator (re, im); nullptr without one
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
 };
 

@@ -3,9 +3,10 @@
 On the device path a wrapper is a DESCRIPTOR: passing it in `physical_system_wrappers=[...]` switches on the matching
 pre-processing inside the kernel (the order of the list has the reference's meaning: later entries wrap earlier ones).
 
-Available: `DqToAbcActionProcessor` (dq_to_abc_action_processor.py), `DeadTimeProcessor` (dead_time_processor.py) and
-`CurrentSumProcessor` (built into every ShuntDc system, current_sum_processor.py).  CosSinProcessor, StateNoiseProcessor and
-FluxObserver are "next" (SURVEY.md §8f row 1).
+Available: `DqToAbcActionProcessor` (dq_to_abc_action_processor.py), `DeadTimeProcessor` (dead_time_processor.py),
+`CurrentSumProcessor` (built into every ShuntDc system, current_sum_processor.py) and the state-vector wrappers
+`CosSinProcessor` (cos_sin_processor.py), `FluxObserver` (flux_observer.py) and `StateNoiseProcessor`
+(state_noise_processor.py), which run as "state ops" at the end of the step kernel (include/gemb200.h: gemb200_state_op).
 """
 import numpy as np
 
@@ -19,16 +20,18 @@ class PhysicalSystemWrapper:
 class DqToAbcActionProcessor(PhysicalSystemWrapper):
     """Actions in dq coordinates: a_abc = T32 * q(a_dq, epsilon + angle_advance * tau * omega * p) with angle_advance = 0.5
     (+ the dead time of an inner DeadTimeProcessor), dq_to_abc_action_processor.py:74-95.  PMSM / SynRM: 2 actions; EESM: 3
-    (d, q, u_e).  The SCIM variant needs the FluxObserver state 'psi_angle' and is not available yet."""
+    (d, q, u_e); SCIM: 2 actions, transformation angle = the FluxObserver state psi_angle (the observer must come first in the list)."""
 
     def __init__(self, angle_name="epsilon"):
-        if angle_name != "epsilon":
-            raise NotImplementedError("only the rotor angle 'epsilon' is available as transformation angle (no FluxObserver yet)")
+        if angle_name not in ("epsilon", "psi_angle"):
+            raise NotImplementedError("transformation angles on the device path: 'epsilon' (PMSM/SynRM/EESM) or the FluxObserver's 'psi_angle' (SCIM)")
         self.angle_name = angle_name
 
     @classmethod
     def make(cls, motor_type, *args, **kwargs):
-        assert motor_type in ("PMSM", "SynRM", "EESM"), f"Not supported motor_type {motor_type}."
+        assert motor_type in ("PMSM", "SynRM", "EESM", "SCIM"), f"Not supported motor_type {motor_type}."
+        if motor_type == "SCIM":  # dq_to_abc_action_processor.py:103-105
+            kwargs.setdefault("angle_name", "psi_angle")
         return cls(*args, **kwargs)
 
     def action_space(self, motor_kind_is_eesm):
@@ -58,15 +61,49 @@ class CurrentSumProcessor(PhysicalSystemWrapper):
             raise NotImplementedError("only CurrentSumProcessor(('i_a','i_e'), limit='max') — the ShuntDc default — is built in")
 
 
-def _unsupported(name):
-    class _Unsupported(PhysicalSystemWrapper):
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"{name} is not on the device path yet (SURVEY.md §8f row 1)")
+class CosSinProcessor(PhysicalSystemWrapper):
+    """Appends cos and sin of an angle state (normalised angle * pi) to the state vector, optionally removing the angle
+    (cos_sin_processor.py:9-89)."""
 
-    _Unsupported.__name__ = name
-    return _Unsupported
+    def __init__(self, angle="epsilon", physical_system=None, remove_angle=False):
+        self._angle = angle
+        self._remove_angle = bool(remove_angle)
+
+    @property
+    def angle(self):
+        return self._angle
 
 
-CosSinProcessor = _unsupported("CosSinProcessor")
-StateNoiseProcessor = _unsupported("StateNoiseProcessor")
-FluxObserver = _unsupported("FluxObserver")
+class FluxObserver(PhysicalSystemWrapper):
+    """Rotor-flux estimate of an induction motor, appended as `psi_abs`, `psi_angle` (flux_observer.py:9-102)."""
+
+    def __init__(self, current_names=("i_sa", "i_sb", "i_sc"), physical_system=None):
+        self._current_names = tuple(current_names)
+
+
+class StateNoiseProcessor(PhysicalSystemWrapper):
+    """Adds i.i.d. noise to the listed states (state_noise_processor.py:4-98).  Distributions on the device path: 'normal'
+    (loc, scale), 'uniform' (low, high), 'laplace' (loc, scale); the reference draws blocks of `random_length` samples from numpy,
+    the kernel draws one Philox sample per step (same distribution, different stream)."""
+
+    _DISTS = {"normal": ("loc", "scale", 0.0, 1.0), "uniform": ("low", "high", 0.0, 1.0), "laplace": ("loc", "scale", 0.0, 1.0)}
+
+    def __init__(self, states, random_dist="normal", random_kwargs=(), random_length=1000, physical_system=None):
+        assert hasattr(np.random.default_rng(), random_dist), (
+            f"The numpy random number generator has no distribution {random_dist}."
+            "Check https://numpy.org/doc/stable/reference/random/generator.html#distributions for distributions.")
+        if random_dist not in self._DISTS:
+            raise NotImplementedError(f"random_dist={random_dist!r}: the device path has 'normal', 'uniform' and 'laplace'")
+        self._states = states
+        self._random_dist = random_dist
+        self._random_kwargs = dict(random_kwargs)
+        self._random_length = int(random_length)
+        k0, k1, d0, d1 = self._DISTS[random_dist]
+        unknown = set(self._random_kwargs) - {k0, k1}
+        if unknown:
+            raise TypeError(f"unexpected random_kwargs {sorted(unknown)} for distribution {random_dist!r}")
+        self.params = (float(self._random_kwargs.get(k0, d0)), float(self._random_kwargs.get(k1, d1)))
+
+    @property
+    def random_kwargs(self):
+        return self._random_kwargs

@@ -102,13 +102,16 @@ class SCMLSystem(PhysicalSystem):
         self._sim = None
         self._owns_sim = False
         self._action_dq, self._angle_advance, self._dead_steps, self._dead_outer = 0, 0.0, 0, 0
+        self._state_ops = []
+        self._base_limits = self._limits.copy()  # limits of the system's own state vector (normalisation inside the kernel)
 
     def apply_wrappers(self, wrappers):
         """Fuse reference-style physical_system_wrappers into the kernel configuration (see physical_system_wrappers.py).
         The list order has the reference's meaning: each entry wraps the system built from the previous ones."""
-        from ..physical_system_wrappers import CurrentSumProcessor, DeadTimeProcessor, DqToAbcActionProcessor
+        from ..physical_system_wrappers import (CosSinProcessor, CurrentSumProcessor, DeadTimeProcessor, DqToAbcActionProcessor, FluxObserver,
+                                                StateNoiseProcessor)
         from .converters import FiniteConverter
-        from .electric_motors import DcShuntMotor, ExternallyExcitedSynchronousMotor, SynchronousMotor
+        from .electric_motors import DcShuntMotor, ExternallyExcitedSynchronousMotor, InductionMotor, SynchronousMotor
 
         for w in wrappers:
             if isinstance(w, CurrentSumProcessor):
@@ -120,16 +123,66 @@ class SCMLSystem(PhysicalSystem):
                 self._dead_steps = w.dead_time
                 self._dead_outer = 1 if self._action_dq else 0  # it wraps an existing dq transformation -> queue of dq actions
             elif isinstance(w, DqToAbcActionProcessor):
-                if not isinstance(self._electrical_motor, SynchronousMotor) or isinstance(self._converter, FiniteConverter):
-                    raise NotImplementedError("DqToAbcActionProcessor needs a PMSM/SynRM/EESM system with a continuous converter")
+                scim = isinstance(self._electrical_motor, InductionMotor)
+                if not isinstance(self._electrical_motor, (SynchronousMotor, InductionMotor)) or isinstance(self._converter, FiniteConverter):
+                    raise NotImplementedError("DqToAbcActionProcessor needs a PMSM/SynRM/EESM/SCIM system with a continuous converter")
                 if self._action_dq:
                     raise NotImplementedError("the system already takes dq actions")
-                self._action_dq = 1
+                assert w.angle_name in self._state_names, (
+                    f"Angle {w.angle_name} not in the states of the physical system. Probably a flux observer is required.")
+                if scim != (w.angle_name == "psi_angle"):
+                    raise NotImplementedError("angle 'psi_angle' goes with the induction motor, 'epsilon' with the synchronous motors")
+                self._action_dq = 2 if scim else 1
                 self._angle_advance = 0.5 + self._dead_steps  # dq_to_abc_action_processor.py:69-72
                 self._action_space = w.action_space(isinstance(self._electrical_motor, ExternallyExcitedSynchronousMotor))
+            elif isinstance(w, (CosSinProcessor, FluxObserver, StateNoiseProcessor)):
+                self._add_state_op(w)
             else:
                 raise NotImplementedError(f"{type(w).__name__} is not a device-side physical-system wrapper")
         return self
+
+    def _add_state_op(self, w):
+        """State-vector wrappers: the bookkeeping of their set_physical_system (names, positions, limits, nominal state, space);
+        the arithmetic runs in the kernel (gemb200_state_op)."""
+        from ..physical_system_wrappers import CosSinProcessor, FluxObserver
+        from .electric_motors import InductionMotor
+
+        if len(self._state_ops) >= K.MAX_STATE_OPS:
+            raise NotImplementedError(f"at most {K.MAX_STATE_OPS} state-vector wrappers per system")
+        names, low, high = list(self._state_names), self._state_space.low, self._state_space.high
+        if isinstance(w, CosSinProcessor):  # cos_sin_processor.py:39-58
+            idx = self._state_positions[w.angle]
+            rm = [idx] if w._remove_angle else []
+            low = np.concatenate((np.delete(low, rm), [-1.0, -1.0]))
+            high = np.concatenate((np.delete(high, rm), [1.0, 1.0]))
+            self._limits = np.concatenate((np.delete(self._limits, rm), [1.0, 1.0]))
+            self._nominal_state = np.concatenate((np.delete(self._nominal_state, rm), [1.0, 1.0]))
+            names = list(np.delete(names, rm)) + [f"cos({w.angle})", f"sin({w.angle})"]
+            self._state_ops.append(dict(kind=K.SOP_COS_SIN, idx=[idx, int(w._remove_angle), 0, 0], mask=0, param=[]))
+        elif isinstance(w, FluxObserver):  # flux_observer.py:56-79
+            assert isinstance(self._electrical_motor, InductionMotor)
+            mp = self._electrical_motor.motor_parameter
+            l_m, l_r, r_r, p = mp["l_m"], mp["l_m"] + mp["l_sigr"], mp["r_r"], mp["p"]
+            psi_limit = l_m * self._limits[names.index("i_sd")]
+            ci = [self._state_positions[n] for n in w._current_names]
+            oi = self._state_positions["omega"]
+            param = [r_r * l_m / l_r, r_r / l_r, p, psi_limit] + [self._limits[j] for j in ci] + [self._limits[oi]]
+            low = np.concatenate((low, [-psi_limit, -np.pi]))  # (sic) the reference's space is in physical units here
+            high = np.concatenate((high, [psi_limit, np.pi]))
+            self._limits = np.concatenate((self._limits, [psi_limit, np.pi]))
+            self._nominal_state = np.concatenate((self._nominal_state, [psi_limit, np.pi]))
+            names = names + ["psi_abs", "psi_angle"]
+            self._state_ops.append(dict(kind=K.SOP_FLUX_OBSERVER, idx=ci + [oi], mask=0, param=param))
+        else:  # StateNoiseProcessor: state_noise_processor.py:69-72
+            sel = names if (isinstance(w._states, str) and w._states == "all") else list(w._states)
+            mask = 0
+            for n in sel:
+                mask |= 1 << self._state_positions[n]
+            dist = {"normal": K.NOISE_NORMAL, "uniform": K.NOISE_UNIFORM, "laplace": K.NOISE_LAPLACE}[w._random_dist]
+            self._state_ops.append(dict(kind=K.SOP_NOISE, idx=[dist, 0, 0, 0], mask=mask, param=list(w.params)))
+        self._state_names = names
+        self._state_positions = {key: index for index, key in enumerate(names)}
+        self._state_space = Box(low, high, dtype=np.float64)
 
     # ------------------------------------------------------------------ reference-compatible properties
     @property
@@ -204,7 +257,7 @@ class SCMLSystem(PhysicalSystem):
         self._electrical_motor.fill_config(cfg)
         self._mechanical_load.fill_config(cfg)
         self._ode_solver.fill_config(cfg)
-        for i, v in enumerate(self._limits):
+        for i, v in enumerate(self._base_limits):
             cfg.limits[i] = float(v)
         for i, v in enumerate(self.initial_ode_state()):
             cfg.init_ode[i] = float(v)
@@ -225,6 +278,14 @@ class SCMLSystem(PhysicalSystem):
         cfg.angle_advance = float(self._angle_advance)
         cfg.dead_time_steps = int(self._dead_steps)
         cfg.dead_time_outer = int(self._dead_outer)
+        cfg.n_state_ops = len(self._state_ops)
+        for k, op in enumerate(self._state_ops):
+            cfg.sop_kind[k] = op["kind"]
+            cfg.sop_mask[k] = op["mask"]
+            for q, v in enumerate(op["idx"]):
+                cfg.sop_idx[k][q] = int(v)
+            for q, v in enumerate(op["param"]):
+                cfg.sop_param[k][q] = float(v)
         return cfg
 
     def attach(self, sim, owns=False):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 1
+#define GEMB200_ABI_VERSION 2
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 24   /* longest state vector in scope: EESM 16 */
@@ -33,6 +33,7 @@ extern "C" {
 #define GEMB200_MAX_DEAD_TIME 8
 #define GEMB200_MAX_CONSTRAINTS 4
 #define GEMB200_MAX_MOTOR_PARAM 16
+#define GEMB200_MAX_STATE_OPS 4 /* state-vector wrappers stacked on one system */
 
 /* error codes */
 #define GEMB200_OK 0
@@ -104,6 +105,21 @@ enum gemb200_ref_kind {
   GEMB200_REF_SAWTOOTH = 6,   /* sawtooth_reference_generator.py */
   GEMB200_REF_TRIANGULAR = 7  /* triangle_reference_generator.py */
 };
+
+/* State-vector wrappers of the reference (physical_system_wrappers/*.py) that run in the kernel after the system's own state
+ * vector has been assembled, in list order (each one sees the vector produced by the previous ones).  n_state reported by
+ * gemb200_query_dims, limits[], constraint masks, reward weights and ref_state[] all refer to the FINAL vector. */
+enum gemb200_state_op {
+  GEMB200_SOP_NONE = 0,
+  GEMB200_SOP_COS_SIN = 1,       /* cos_sin_processor.py: append cos(pi*s[angle]), sin(pi*s[angle]); optionally drop the angle.
+                                    sop_idx = {angle index, remove_angle} */
+  GEMB200_SOP_FLUX_OBSERVER = 2, /* flux_observer.py:85-101 (induction motor): rotor-flux estimate integrated with explicit Euler,
+                                    appends |psi|/psi_limit and angle(psi)/pi.  sop_idx = {i_sa, i_sb, i_sc, omega} indices,
+                                    sop_param = {r_r*l_m/l_r, r_r/l_r, p, psi_limit, limit of i_sa, i_sb, i_sc, omega} */
+  GEMB200_SOP_NOISE = 3          /* state_noise_processor.py: s[j] += noise for the states in sop_mask, i.i.d. per step and env.
+                                    sop_idx[0] = gemb200_noise_dist, sop_param = {loc, scale} (normal, laplace) or {low, high} */
+};
+enum gemb200_noise_dist { GEMB200_NOISE_NORMAL = 0, GEMB200_NOISE_UNIFORM = 1, GEMB200_NOISE_LAPLACE = 2 };
 
 enum gemb200_dtype { GEMB200_F32 = 0 /* fp32 state, fp64 rotor angle */, GEMB200_F64 = 1 };
 enum gemb200_layout {
@@ -185,6 +201,16 @@ typedef struct gemb200_config {
   double ref_amp_lo[GEMB200_MAX_REF], ref_amp_hi[GEMB200_MAX_REF];
   double ref_freq_lo[GEMB200_MAX_REF], ref_freq_hi[GEMB200_MAX_REF];
   double ref_off_lo[GEMB200_MAX_REF], ref_off_hi[GEMB200_MAX_REF];
+
+  /* state-vector wrappers (see gemb200_state_op).  limits[] above stays the INNER system's limits (they normalise the assembled
+   * vector); the ops carry their own scaling in sop_param. */
+  int32_t n_state_ops;
+  int32_t sop_kind[GEMB200_MAX_STATE_OPS];
+  int32_t sop_idx[GEMB200_MAX_STATE_OPS][4];
+  uint32_t sop_mask[GEMB200_MAX_STATE_OPS];
+  double sop_param[GEMB200_MAX_STATE_OPS][8];
+  /* action_dq = 2: SCIM with a FluxObserver — the transformation angle is the observer's psi_angle (+ angle_advance*tau*omega*p),
+   * dq_to_abc_action_processor.py:103-105; requires a GEMB200_SOP_FLUX_OBSERVER op */
 } gemb200_config;
 
 typedef struct gemb200_handle gemb200_handle;

@@ -53,11 +53,13 @@ typedef struct {
   int ref_left[GEMB200_MAX_REF];
   uint32_t ref_start[GEMB200_MAX_REF], ref_len[GEMB200_MAX_REF]; /* periodic generators: sub-episode start step and length */
   double fifo[GEMB200_MAX_DEAD_TIME][GEMB200_MAX_ACT]; /* DeadTimeProcessor queue (ring; slot = call counter mod steps) */
+  double psi_re, psi_im; /* FluxObserver._integrated flux_observer.py:46 */
 } env_t;
 
 typedef struct gem_oracle {
   gemb200_config cfg;
   int n_state, n_ode, n_act, n_ref, n_motor, n_cur, n_volt;
+  int n_obs; /* width of the state vector after the physical_system_wrappers (n_state: the inner system's own) */
   int n_sub[2];     /* 2QC sub-converters per slot */
   int slot_off[2];  /* first sub index per slot */
   double mc[MAXM][MAXF]; /* _model_constants */
@@ -102,7 +104,8 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
        STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */,
-       STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */ };
+       STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */,
+       STREAM_NOISE = 64 /* + 8*op + (state >> 2): StateNoiseProcessor */, STREAM_NOISE_R = 128 /* ... right after an auto-reset */ };
 
 struct gem_oracle;
 static void rng4(const struct gem_oracle* o, int64_t env, uint32_t stream, uint32_t out[4]);
@@ -144,6 +147,12 @@ static int dims(gem_oracle* o) {
   else o->n_act = slot_nvolt(c->converter_kind[0]) + slot_nvolt(c->converter_kind[1]);
   if (c->action_dq) o->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2; /* dq_to_abc_action_processor.py:97-99,:143-145 */
   o->n_ref = c->n_ref;
+  /* widths after the wrappers: cos_sin_processor.py:44-58, flux_observer.py:66-75 */
+  o->n_obs = o->n_state;
+  for (int k = 0; k < c->n_state_ops; ++k) {
+    if (c->sop_kind[k] == GEMB200_SOP_COS_SIN) o->n_obs += c->sop_idx[k][1] ? 1 : 2;
+    else if (c->sop_kind[k] == GEMB200_SOP_FLUX_OBSERVER) o->n_obs += 2;
+  }
   return 0;
 }
 
@@ -773,6 +782,59 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
+/* state-vector wrappers, applied in list order to the (normalised) vector of the inner system                  */
+/* ------------------------------------------------------------------------------------------------------------ */
+static void apply_state_ops(const gem_oracle* o, env_t* e, int64_t idx, double* st, int is_reset, int after_autoreset) {
+  const gemb200_config* c = &o->cfg;
+  int w = o->n_state;
+  for (int k = 0; k < c->n_state_ops; ++k) {
+    const double* q = c->sop_param[k];
+    switch (c->sop_kind[k]) {
+      case GEMB200_SOP_COS_SIN: { /* cos_sin_processor.py:60-89 */
+        const int a = c->sop_idx[k][0];
+        const double cs = cos(st[a] * M_PI), sn = sin(st[a] * M_PI);
+        if (c->sop_idx[k][1]) { for (int j = a; j < w - 1; ++j) st[j] = st[j + 1]; --w; } /* np.delete(state, angle) :68 */
+        st[w++] = cs; st[w++] = sn;
+      } break;
+      case GEMB200_SOP_FLUX_OBSERVER: { /* flux_observer.py:81-101 */
+        if (is_reset) { e->psi_re = 0.0; e->psi_im = 0.0; st[w++] = 0.0; st[w++] = 0.0; break; } /* :81-83 */
+        double i_s[3], ab[2];
+        for (int j = 0; j < 3; ++j) i_s[j] = st[c->sop_idx[k][j]] * q[4 + j]; /* state = state_norm * limits :87-88 */
+        const double omega = st[c->sop_idx[k][3]] * q[7] * q[2];              /* :89 */
+        t_23(i_s, ab);
+        /* delta_psi = i_ab r_r l_m / l_r - psi * complex(r_r / l_r, -omega)  :93-95 */
+        const double dre = ab[0] * q[0] - (e->psi_re * q[1] + e->psi_im * omega);
+        const double dim = ab[1] * q[0] - (e->psi_im * q[1] - e->psi_re * omega);
+        e->psi_re += dre * c->tau; e->psi_im += dim * c->tau;                  /* :97 */
+        st[w++] = sqrt(e->psi_re * e->psi_re + e->psi_im * e->psi_im) / q[3];
+        st[w++] = atan2(e->psi_im, e->psi_re) / M_PI;                          /* limits [psi_limit, pi] :69,:98 */
+      } break;
+      case GEMB200_SOP_NOISE: { /* state_noise_processor.py:74-98; one i.i.d. draw per step (Philox instead of numpy) */
+        const uint32_t mask = c->sop_mask[k];
+        for (int b = 0; b * 4 < w; ++b) {
+          if (((mask >> (4 * b)) & 15u) == 0) continue;
+          uint32_t r[4];
+          rng4(o, idx, (after_autoreset ? STREAM_NOISE_R : STREAM_NOISE) + 8 * k + b, r);
+          for (int m = 0; m < 4 && 4 * b + m < w; ++m) {
+            if (!((mask >> (4 * b + m)) & 1u)) continue;
+            double z;
+            if (c->sop_idx[k][0] == GEMB200_NOISE_UNIFORM) z = q[0] + (q[1] - q[0]) * u01(r[m]);
+            else if (c->sop_idx[k][0] == GEMB200_NOISE_LAPLACE) {
+              const double u = u01(r[m]);
+              z = q[0] + q[1] * (u < 0.5 ? log(2 * u) : -log(2 * (1 - u)));
+            } else { /* Box-Muller on the word pair (0,1) / (2,3); even state: cos branch, odd: sin branch */
+              const double rad = sqrt(-2.0 * log(u01(r[m & 2]))), ang = 2.0 * M_PI * u01(r[(m & 2) + 1]);
+              z = q[0] + q[1] * rad * ((m & 1) ? sin(ang) : cos(ang));
+            }
+            st[4 * b + m] += z;
+          }
+        }
+      } break;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
 /* epilogue: constraints, reward, reference generators                                                           */
 /* ------------------------------------------------------------------------------------------------------------ */
 /* ConstraintMonitor.check_constraints core.py:834-844 with merge 'max'; constraints.py:55-58, :96-98 */
@@ -782,10 +844,10 @@ static double check_constraints(const gem_oracle* o, const double* s) {
     uint32_t mask = o->cfg.constraint_mask[ci];
     double vi = 0.0;
     if (o->cfg.constraint_kind[ci] == GEMB200_CONSTRAINT_LIMIT) {
-      for (int j = 0; j < o->n_state; ++j) if ((mask >> j) & 1u) if (fabs(s[j]) > 1.0) vi = 1.0;
+      for (int j = 0; j < o->n_obs; ++j) if ((mask >> j) & 1u) if (fabs(s[j]) > 1.0) vi = 1.0;
     } else {
       double sum = 0.0;
-      for (int j = 0; j < o->n_state; ++j) if ((mask >> j) & 1u) sum += s[j] * s[j];
+      for (int j = 0; j < o->n_obs; ++j) if ((mask >> j) & 1u) sum += s[j] * s[j];
       vi = sum > 1.0 ? 1.0 : 0.0;
     }
     if (vi > v) v = vi;
@@ -796,7 +858,7 @@ static double check_constraints(const gem_oracle* o, const double* s) {
 /* WeightedSumOfErrors.reward weighted_sum_of_errors.py:125-129 */
 static double reward(const gem_oracle* o, const double* s, const double* ref_full, double violation) {
   double sum = 0.0;
-  for (int j = 0; j < o->n_state; ++j) {
+  for (int j = 0; j < o->n_obs; ++j) {
     double w = o->cfg.reward_weight[j];
     if (w == 0.0) continue; /* 0 * x = 0 for the finite x met here */
     sum += w * pow(fabs(s[j] - ref_full[j]) / o->cfg.state_length[j], o->cfg.reward_power[j]);
@@ -939,7 +1001,7 @@ int gem_oracle_create(const gemb200_config* cfg, gem_oracle** out) {
 }
 void gem_oracle_destroy(gem_oracle* o) { if (o) { free(o->env); free(o); } }
 void gem_oracle_dims(const gem_oracle* o, int32_t* n_state, int32_t* n_ode, int32_t* n_act, int32_t* n_ref) {
-  *n_state = o->n_state; *n_ode = o->n_ode; *n_act = o->n_act; *n_ref = o->n_ref;
+  *n_state = o->n_obs; *n_ode = o->n_ode; *n_act = o->n_act; *n_ref = o->n_ref;
 }
 
 /* env.reset (core.py:300-319). mask NULL = all. obs [N][n_state], ref_next [N][n_ref] (may be NULL). */
@@ -950,8 +1012,9 @@ void gem_oracle_reset(gem_oracle* o, const uint8_t* mask, double* obs, double* r
     if (mask && !mask[i]) continue;
     env_t* e = o->env + i;
     ps_reset(o, e, st);
+    apply_state_ops(o, e, i, st, 1, 0);
     ref_reset(o, e, i);
-    if (obs) memcpy(obs + i * o->n_state, st, sizeof(double) * o->n_state);
+    if (obs) memcpy(obs + i * o->n_obs, st, sizeof(double) * o->n_obs);
     if (ref_next) for (int r = 0; r < o->n_ref; ++r) ref_next[i * o->n_ref + r] = e->ref_value[r];
   }
 }
@@ -981,7 +1044,9 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
        * wrapped epsilon + angle_advance * tau * omega * p (:89-91).  control_space='dq' = same with advance 0
        * (physical_systems.py:491-492); SCIM uses the field angle (:779-780). */
       double ang, dq[2] = {abuf[0], abuf[1]}, ab[2], ue = abuf[2];
-      if (c->motor_kind == GEMB200_MOTOR_SCIM) ang = atan2(e->ode[4], e->ode[3]);
+      if (c->motor_kind == GEMB200_MOTOR_SCIM && c->action_dq == 2) /* observer angle: dq_to_abc_action_processor.py:89-91,:103-105 */
+        ang = atan2(e->psi_im, e->psi_re) + c->angle_advance * c->tau * e->ode[0] * c->motor_param[GEMB200_MP_P];
+      else if (c->motor_kind == GEMB200_MOTOR_SCIM) ang = atan2(e->ode[4], e->ode[3]);
       else ang = wrap_eps(e->ode[o->n_ode - 1]) + c->angle_advance * c->tau * e->ode[0] * c->motor_param[GEMB200_MP_P];
       q_rot(dq, ang, ab);
       t_32(ab, abuf);
@@ -993,6 +1058,7 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
     af = abuf;
   }
   simulate(o, e, af, ai, st);                                   /* core.py:344 */
+  apply_state_ops(o, e, i, st, 0, 0);                           /* wrappers' simulate() */
   memset(ref_full, 0, sizeof(ref_full));
   for (int r = 0; r < o->n_ref; ++r) ref_full[o->cfg.ref_state[r]] = e->ref_value[r]; /* core.py:346 */
   double v = check_constraints(o, st);                          /* core.py:348 */
@@ -1001,9 +1067,10 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
   ref_advance(o, e, i, 0);                                      /* core.py:351 */
   if (terminated && o->cfg.autoreset == GEMB200_AUTORESET_SAME_STEP) {
     ps_reset(o, e, st);
+    apply_state_ops(o, e, i, st, 1, 1);
     ref_reset(o, e, i);
   }
-  if (obs) memcpy(obs + i * o->n_state, st, sizeof(double) * o->n_state);
+  if (obs) memcpy(obs + i * o->n_obs, st, sizeof(double) * o->n_obs);
   if (ref_next) for (int r = 0; r < o->n_ref; ++r) ref_next[i * o->n_ref + r] = e->ref_value[r];
   if (rew) rew[i] = rw;
   if (term) term[i] = (uint8_t)terminated;

@@ -133,7 +133,9 @@ def describe(env, case):
         case=case,
         action_dim=int(np.prod(getattr(env.action_space, "shape", ()) or (1,))),
         state_names=list(p.state_names),
-        limits=p.limits.tolist(),
+        base_state_names=list(p.unwrapped.state_names),  # the inner system's own vector (before state-vector wrappers)
+        base_limits=np.asarray(p.unwrapped.limits, dtype=float).tolist(),
+        limits=np.asarray(p.limits, dtype=float).tolist(),
         nominal_state=p.nominal_state.tolist(),
         state_low=p.state_space.low.tolist(),
         state_high=p.state_space.high.tolist(),
@@ -177,11 +179,19 @@ def record(case):
     if case.get("converter_cls") is not None:
         kwargs["converter"] = getattr(ps, case["converter_cls"])(**case.get("converter_args", {}))
     if case.get("wrappers"):
-        from gym_electric_motor.physical_system_wrappers import DeadTimeProcessor, DqToAbcActionProcessor
+        from gym_electric_motor.physical_system_wrappers import (CosSinProcessor, DeadTimeProcessor, DqToAbcActionProcessor,
+                                                                 FluxObserver)
 
         ws = []
         for kind, arg in case["wrappers"]:
-            ws.append(DeadTimeProcessor(steps=arg) if kind == "DeadTime" else DqToAbcActionProcessor.make(arg))
+            if kind == "DeadTime":
+                ws.append(DeadTimeProcessor(steps=arg))
+            elif kind == "CosSin":  # arg = [angle name, remove_angle]
+                ws.append(CosSinProcessor(angle=arg[0], remove_angle=bool(arg[1])))
+            elif kind == "FluxObserver":
+                ws.append(FluxObserver())
+            else:
+                ws.append(DqToAbcActionProcessor.make(arg))
         kwargs["physical_system_wrappers"] = ws
     env = gem.make(case["env_id"], visualization=NoViz(), ode_solver=make_solver(case["solver"]), **kwargs)
     K = case["steps"]
@@ -298,6 +308,13 @@ CASES = [
     C("eesm_cc_dq_rk4", "Cont-CC-EESM-v0", "rk4", steps=1500, wrappers=[("DqToAbc", "EESM")]),
     C("pmsm_fin_cc_dead3_rk4", "Finite-CC-PMSM-v0", "rk4", steps=1500, wrappers=[("DeadTime", 3)]),
     C("permex_cc_dead2_rk4", "Cont-CC-PermExDc-v0", "rk4", steps=1000, wrappers=[("DeadTime", 2)]),
+    # state-vector wrappers: CosSinProcessor (with and without removing the angle), FluxObserver, FluxObserver + dq actions (SCIM)
+    C("pmsm_cc_cossin_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1000, wrappers=[("CosSin", ["epsilon", 0])]),
+    C("pmsm_sc_cossin_rm_rk4", "Cont-SC-PMSM-v0", "rk4", steps=1000, wrappers=[("CosSin", ["epsilon", 1])]),
+    C("scim_cc_flux_rk4", "Cont-CC-SCIM-v0", "rk4", steps=1500, wrappers=[("FluxObserver", None)]),
+    C("scim_cc_flux_dq_rk4", "Cont-CC-SCIM-v0", "rk4", steps=1500, wrappers=[("FluxObserver", None), ("DqToAbc", "SCIM")]),
+    C("scim_sc_flux_cossin_dead1_rk4", "Cont-SC-SCIM-v0", "rk4", steps=1500,
+      wrappers=[("DeadTime", 1), ("FluxObserver", None), ("CosSin", ["psi_angle", 0]), ("DqToAbc", "SCIM")]),
     C("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500,
       motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
                  motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0)))),

@@ -106,8 +106,10 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
     cfg.load_param[K.LP_J_LOAD] = meta["j_total"] - meta["motor_parameter"]["j_rotor"]
     cfg.load_param[K.LP_TAU_DECAY] = 1e-3
     n_state = len(meta["state_names"])
+    # cfg.limits normalises the inner system's own vector; weights / lengths refer to the final (wrapped) vector
+    for i, v in enumerate(meta.get("base_limits", meta["limits"])):
+        cfg.limits[i] = v
     for i in range(n_state):
-        cfg.limits[i] = meta["limits"][i]
         cfg.reward_weight[i] = meta["reward_weights"][i]
         cfg.reward_power[i] = meta["reward_power"][i]
         cfg.state_length[i] = meta["state_length"][i]
@@ -133,11 +135,38 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
     cfg.seed = seed
     # physical-system wrappers recorded with the golden (list order = reference order: later entries wrap earlier ones)
     dq, dead, outer, adv = 0, 0, 0, 0.0
+    cur_names = list(meta.get("base_state_names", names))  # state vector as seen by the next wrapper
+    cur_limits = list(meta.get("base_limits", meta["limits"]))
+    nops = 0
     for kind, arg in meta["case"].get("wrappers", []) or []:
         if kind == "DeadTime":
             dead, outer = int(arg), (1 if dq else 0)
+        elif kind == "CosSin":  # cos_sin_processor.py:39-58
+            idx, rm = cur_names.index(arg[0]), int(arg[1])
+            cfg.sop_kind[nops] = K.SOP_COS_SIN
+            cfg.sop_idx[nops][0], cfg.sop_idx[nops][1] = idx, rm
+            if rm:
+                del cur_names[idx], cur_limits[idx]
+            cur_names += [f"cos({arg[0]})", f"sin({arg[0]})"]
+            cur_limits += [1.0, 1.0]
+            nops += 1
+        elif kind == "FluxObserver":  # flux_observer.py:56-79
+            mp = meta["motor_parameter"]
+            l_r = mp["l_m"] + mp["l_sigr"]
+            psi_limit = mp["l_m"] * cur_limits[cur_names.index("i_sd")]
+            idx = [cur_names.index(n) for n in ("i_sa", "i_sb", "i_sc", "omega")]
+            cfg.sop_kind[nops] = K.SOP_FLUX_OBSERVER
+            for q, v in enumerate(idx):
+                cfg.sop_idx[nops][q] = v
+            for q, v in enumerate([mp["r_r"] * mp["l_m"] / l_r, mp["r_r"] / l_r, mp["p"], psi_limit] + [cur_limits[j] for j in idx]):
+                cfg.sop_param[nops][q] = v
+            cur_names += ["psi_abs", "psi_angle"]
+            cur_limits += [psi_limit, np.pi]
+            nops += 1
         else:
-            dq, adv = 1, 0.5 + dead
+            dq, adv = (2 if arg == "SCIM" else 1), 0.5 + dead
+    cfg.n_state_ops = nops
+    assert cur_names == names or not nops, (cur_names, names)
     cfg.action_dq, cfg.dead_time_steps, cfg.dead_time_outer, cfg.angle_advance = dq, dead, outer, adv
     return cfg
 
@@ -161,6 +190,25 @@ def replay_golden(sim, g, inject_refs=True):
         if g["terminated"][k]:
             sim.reset()
     return out
+
+
+def golden_reset_state(g):
+    """Reset observation of a golden.  Reference quirk: CosSinProcessor(remove_angle=True).reset() returns the vector WITH the
+    angle it removes in simulate() (cos_sin_processor.py:60-63 vs :65-70); a batched tensor has one width, so the device path
+    and the oracle remove it at reset too — compare against the golden with that column deleted."""
+    rs = np.asarray(g["reset_state"], dtype=np.float64)
+    names = list(g["meta"].get("base_state_names", g["meta"]["state_names"]))
+    for kind, arg in g["meta"]["case"].get("wrappers", []) or []:
+        if kind == "CosSin":
+            if int(arg[1]):  # env.reset() then cuts the un-shortened vector with its state filter: [..., angle, ..., cos] — sin is lost
+                a = names.index(arg[0])
+                rs = np.delete(np.concatenate((rs, [np.sin(np.pi * rs[a])])), a)
+            if int(arg[1]):
+                names.remove(arg[0])
+            names += [f"cos({arg[0]})", f"sin({arg[0]})"]
+        elif kind == "FluxObserver":
+            names += ["psi_abs", "psi_angle"]
+    return rs
 
 
 def col_rel_err(a, b):

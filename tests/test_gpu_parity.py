@@ -8,7 +8,7 @@ column-relative — the bar BASELINE.json's north_star sets for state trajectori
 import numpy as np
 import pytest
 
-from helpers import col_rel_err, config_from_meta, golden_names, load_golden, replay_golden
+from helpers import golden_reset_state, col_rel_err, config_from_meta, golden_names, load_golden, replay_golden
 from gym_electric_motor_b200 import _cabi as K
 
 pytestmark = pytest.mark.gpu
@@ -67,7 +67,7 @@ def test_device_reproduces_reference_trajectory(torch_cuda, name, dtype):
     sim = DeviceAdapter(cfg)
     out = replay_golden(sim, g)
     tol = (TOL_DOPRI if is_dopri else TOL)[dtype]
-    assert np.abs(out["reset_state"] - g["reset_state"]).max() < 1e-6
+    assert np.abs(out["reset_state"] - golden_reset_state(g)).max() < 1e-6
     if g["meta"]["motor_class"] == "SquirrelCageInductionMotor":
         # i_sd/i_sq/u_sd/u_sq are expressed in the rotor-flux frame, angle = atan2(psi_b, psi_a)
         # (physical_systems.py:765-769).  While the flux is still (numerically) zero after a reset that angle is
@@ -94,6 +94,8 @@ BATCH_CASES = [
     ("synrm_cc_rk4", "rk4x2"), ("eesm_cc_rk4", "rk4"), ("eesm_fin_cc_rk4", "rk4"), ("scim_cc_rk4", "rk4"),
     ("scim_fin_cc_interlock_rk4", "rk4"), ("permex_cc_euler_10k", "euler"), ("permex_fin4qc_interlock_rk4", "rk4"),
     ("series_cc_rk4", "rk4"), ("shunt_cc_rk4", "rk4"), ("extex_cc_rk4", "rk4"),
+    # state-vector wrappers (CosSinProcessor, FluxObserver, FluxObserver angle for dq actions, dead time in front)
+    ("pmsm_cc_cossin_rk4", "rk4"), ("pmsm_sc_cossin_rm_rk4", "rk4"), ("scim_cc_flux_dq_rk4", "rk4"), ("scim_sc_flux_cossin_dead1_rk4", "rk4"),
 ]
 
 
@@ -150,6 +152,7 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
     assert np.abs(d_ref - o_ref).max() < max(tol, 1e-12) * 10
     alive = np.ones(n, dtype=bool)  # envs whose device/oracle episodes are still aligned
     scale = np.maximum(np.abs(o_obs).max(axis=0), 1e-3)
+    ang_cols = [j for j, nm in enumerate(g["meta"]["state_names"]) if nm in ("epsilon", "psi_angle")]
     n_term = 0
     for k in range(steps):
         o_obs, o_ref, o_rew, o_term = ora.step(actions[k])
@@ -157,7 +160,10 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
         split = alive & (o_term != d_term)
         alive &= ~split  # a constraint within rounding of its threshold: episodes diverge from here on
         scale = np.maximum(scale, np.abs(o_obs[alive]).max(axis=0))
-        err = (np.abs(d_obs - o_obs)[alive] / scale).max()
+        diff = np.abs(d_obs - o_obs)
+        for j in ang_cols:  # normalised angles live on a circle of circumference 2: +1 and -1 are the same point
+            diff[:, j] = np.abs((d_obs[:, j] - o_obs[:, j] + 1.0) % 2.0 - 1.0)
+        err = (diff[alive] / scale).max()
         assert err < tol, f"step {k}: state error {err:.3e}"
         assert np.abs(d_ref - o_ref)[alive].max() < 20 * tol if d_ref.size else True
         assert np.abs(d_rew - o_rew)[alive].max() < 20 * tol
@@ -165,6 +171,62 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
     assert alive.mean() > 0.995, f"too many diverged envs: {n - alive.sum()}"
     if name not in ("series_cc_rk4",) and "_fin" not in name:  # finite envs: tau = 1e-5, 150 steps are too short to trip
         assert n_term > 0, "test is meant to exercise termination + auto-reset"
+
+
+@pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("dist,params", [(K.NOISE_NORMAL, (0.01, 0.05)), (K.NOISE_UNIFORM, (-0.02, 0.04)), (K.NOISE_LAPLACE, (0.0, 0.03))])
+def test_state_noise_processor_matches_oracle_and_distribution(torch_cuda, oracle_lib, dist, params, dtype):
+    """StateNoiseProcessor (state_noise_processor.py:74-98) as a state op: device == oracle value for value (same Philox
+    convention), and the noise itself has the requested distribution (moments checked against numpy's definitions)."""
+    g = load_golden("pmsm_cc_rk4")
+    n, steps = 2048, 12
+    names = g["meta"]["state_names"]
+    noisy = [names.index(s) for s in ("omega", "i_sd", "i_sq", "u_sup")]
+
+    def mk(dt, with_noise=True):
+        cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=dt, solver="rk4", ref_kind=K.REF_WIENER,
+                               autoreset=K.AUTORESET_SAME_STEP, seed=99)
+        cfg.n_constraints = 0  # keep episodes running: the clean twin must stay aligned
+        if with_noise:
+            cfg.n_state_ops = 1
+            cfg.sop_kind[0] = K.SOP_NOISE
+            cfg.sop_idx[0][0] = dist
+            cfg.sop_mask[0] = sum(1 << j for j in noisy)
+            cfg.sop_param[0][0], cfg.sop_param[0][1] = params
+        return cfg
+
+    dev, ora, clean = DeviceAdapter(mk(dtype)), oracle_lib.Oracle(mk(K.F64), nthreads=8), oracle_lib.Oracle(mk(K.F64, False), nthreads=8)
+    rng = np.random.default_rng(3)
+    d0, _ = dev.reset()
+    o0, _ = ora.reset()
+    c0, _ = clean.reset()
+    tol = 1e-9 if dtype == K.F64 else 2e-6
+    assert np.abs(d0 - o0).max() < tol  # the noise is added at reset as well (:74-78)
+    samples = [(o0 - c0)[:, noisy]]
+    for k in range(steps):
+        a = rng.uniform(-0.3, 0.3, size=(n, 3))
+        d_obs, _, d_rew, _ = dev.step(a)
+        o_obs, _, o_rew, _ = ora.step(a)
+        c_obs, _, _, _ = clean.step(a)
+        assert np.abs(d_obs - o_obs).max() < tol, k
+        assert np.abs(d_rew - o_rew).max() < 10 * tol  # the reward sees the noisy state (it is computed on the wrapped system)
+        others = [j for j in range(len(names)) if j not in noisy]
+        assert np.abs(o_obs[:, others] - c_obs[:, others]).max() == 0.0
+        samples.append((o_obs - c_obs)[:, noisy])
+    z = np.concatenate(samples).ravel()
+    a0, a1 = params
+    if dist == K.NOISE_NORMAL:
+        mean, std, kurt = a0, a1, 3.0
+    elif dist == K.NOISE_UNIFORM:
+        mean, std, kurt = 0.5 * (a0 + a1), (a1 - a0) / np.sqrt(12.0), 1.8
+    else:
+        mean, std, kurt = a0, a1 * np.sqrt(2.0), 6.0
+    m = len(z)
+    assert abs(z.mean() - mean) < 5 * std / np.sqrt(m)
+    assert abs(z.std() / std - 1) < 0.02
+    assert abs(((z - z.mean()) ** 4).mean() / z.var() ** 2 / kurt - 1) < 0.1
+    if dist == K.NOISE_UNIFORM:
+        assert z.min() >= a0 and z.max() <= a1
 
 
 def _cfg(name, n, dtype=K.F32, **kw):
@@ -300,7 +362,7 @@ def test_public_api_scalar_and_batched(torch_cuda):
     env1, envn = mk(), mk(num_envs=5)
     (s, r), info = env1.reset(seed=3)
     assert s.shape == (14,) and r.shape == (2,) and info == {}
-    np.testing.assert_allclose(s, g["reset_state"], atol=1e-12)
+    np.testing.assert_allclose(s, golden_reset_state(g), atol=1e-12)
     (sb, rb), _ = envn.reset(seed=3)
     assert tuple(sb.shape) == (5, 14) and tuple(rb.shape) == (5, 2)
     ref_idx = [g["meta"]["state_names"].index(nm) for nm in g["meta"]["reference_names"]]

@@ -142,8 +142,8 @@ def test_wrapper_descriptors_compile_like_the_reference_stack():
         assert int(np.prod(getattr(env.action_space, "shape", ()) or (1,))) == g["meta"]["action_dim"]
     with pytest.raises(NotImplementedError):
         gem.make("Finite-CC-PMSM-v0", physical_system_wrappers=[DqToAbcActionProcessor.make("PMSM")])
-    with pytest.raises(NotImplementedError):
-        gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[gem.physical_system_wrappers.CosSinProcessor()])
+    with pytest.raises(AssertionError):  # 'psi_angle' needs a FluxObserver first (dq_to_abc_action_processor.py:62-64)
+        gem.make("Cont-CC-SCIM-v0", physical_system_wrappers=[DqToAbcActionProcessor.make("SCIM")])
     # control_space='dq' (physical_systems.py:423-435): same transformation, no angle advance
     ps_ = gem.physical_systems
     sys_ = ps_.SynchronousMotorSystem(control_space="dq", supply=ps_.IdealVoltageSupply(300.0), converter=ps_.ContB6BridgeConverter(),
@@ -151,6 +151,54 @@ def test_wrapper_descriptors_compile_like_the_reference_stack():
                                       ode_solver=ps_.RK4Solver())
     c = sys_.fill_config(K.new_config())
     assert (c.action_dq, c.angle_advance) == (1, 0.0) and sys_.action_space.shape == (2,)
+
+
+def test_state_vector_wrappers_bookkeeping_matches_reference():
+    """CosSinProcessor / FluxObserver / StateNoiseProcessor: names, limits, state space and the kernel's op list must equal what the
+    reference's wrappers derived when the goldens were recorded (meta) and the independent translation in tests/helpers.py."""
+    psw = gem.physical_system_wrappers
+
+    def build(spec):
+        out = []
+        for k, a in spec:
+            out.append(psw.DeadTimeProcessor(steps=a) if k == "DeadTime" else psw.CosSinProcessor(angle=a[0], remove_angle=bool(a[1])) if k == "CosSin"
+                       else psw.FluxObserver() if k == "FluxObserver" else psw.DqToAbcActionProcessor.make(a))
+        return out
+
+    for name, env_id in [("pmsm_cc_cossin_rk4", "Cont-CC-PMSM-v0"), ("pmsm_sc_cossin_rm_rk4", "Cont-SC-PMSM-v0"), ("scim_cc_flux_rk4", "Cont-CC-SCIM-v0"),
+                         ("scim_cc_flux_dq_rk4", "Cont-CC-SCIM-v0"), ("scim_sc_flux_cossin_dead1_rk4", "Cont-SC-SCIM-v0")]:
+        g = load_golden(name)
+        meta = g["meta"]
+        ref = config_from_meta(meta, reset_ode=g["reset_ode"], solver="rk4", ref_kind=K.REF_WIENER)
+        env = gem.make(env_id, ode_solver=gem.physical_systems.RK4Solver(), physical_system_wrappers=build(meta["case"]["wrappers"]))
+        ps_ = env.physical_system
+        assert ps_.state_names == meta["state_names"], name
+        assert np.allclose(ps_.limits, meta["limits"], rtol=1e-12)
+        assert np.allclose(ps_.nominal_state, g["meta"]["nominal_state"], rtol=1e-12)
+        assert np.allclose(ps_.state_space.low, meta["state_low"]) and np.allclose(ps_.state_space.high, meta["state_high"])
+        assert int(np.prod(env.action_space.shape)) == meta["action_dim"]
+        cfg = env.build_config()
+        assert cfg.n_state_ops == ref.n_state_ops and cfg.action_dq == ref.action_dq and cfg.angle_advance == ref.angle_advance
+        for k in range(cfg.n_state_ops):
+            assert cfg.sop_kind[k] == ref.sop_kind[k] and list(cfg.sop_idx[k]) == list(ref.sop_idx[k])
+            assert list(cfg.sop_param[k]) == pytest.approx(list(ref.sop_param[k]), rel=1e-12)
+        for f, n in (("limits", 24), ("reward_weight", 24), ("state_length", 24), ("constraint_mask", 4), ("ref_state", 4)):
+            assert list(getattr(cfg, f))[:n] == pytest.approx(list(getattr(ref, f))[:n], rel=1e-12), (name, f)
+        n_state = K.C.c_int32()
+        K.load_library().gemb200_query_dims(K.C.byref(cfg), K.C.byref(n_state), None, None, None)
+        assert n_state.value == len(meta["state_names"])
+    # StateNoiseProcessor: descriptor -> op
+    env = gem.make("Cont-SC-PermExDc-v0", physical_system_wrappers=[psw.StateNoiseProcessor(states=["omega", "torque"], random_dist="laplace",
+                                                                                           random_kwargs=dict(loc=0.0, scale=0.1))])
+    cfg = env.build_config()
+    assert (cfg.n_state_ops, cfg.sop_kind[0], cfg.sop_idx[0][0], cfg.sop_mask[0]) == (1, K.SOP_NOISE, K.NOISE_LAPLACE, 0b11)
+    assert list(cfg.sop_param[0])[:2] == [0.0, 0.1]
+    env = gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.StateNoiseProcessor(states="all")])
+    assert env.build_config().sop_mask[0] == (1 << 14) - 1
+    with pytest.raises(AssertionError):
+        psw.StateNoiseProcessor(states="all", random_dist="not_a_distribution")
+    with pytest.raises(NotImplementedError):
+        psw.StateNoiseProcessor(states="all", random_dist="gamma")
 
 
 def test_random_initialiser_bounds_match_reference():
