@@ -39,7 +39,7 @@ struct gemb200_handle {
   uint16_t* d_sw = nullptr;
   void* d_fifo = nullptr;
   int fifo_dim = 0;
-  void* d_obsv = nullptr;  // FluxObserver integrator [2][n]
+  void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
   int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
   StepParams<double> pd;
@@ -582,7 +582,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   }
   if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
   if (h->two_segment) ALLOC(h->d_sw, n * sizeof(uint16_t));
-  if (d.has_observer) ALLOC(h->d_obsv, n * 2 * h->rsz);
+  if (d.has_observer) ALLOC(h->d_obsv, n * 4 * h->rsz);
 #undef ALLOC
   Derived dv;
   derive_model(cfg, d, &dv);
@@ -770,7 +770,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_eps) s[k++] = {h->d_eps, n * sizeof(double)};
   if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
   if (h->d_fifo) s[k++] = {h->d_fifo, n * h->cfg.dead_time_steps * h->fifo_dim * h->rsz};
-  if (h->d_obsv) s[k++] = {h->d_obsv, n * 2 * h->rsz};
+  if (h->d_obsv) s[k++] = {h->d_obsv, n * 4 * h->rsz};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {

@@ -153,7 +153,7 @@ struct StepParams {
   int32_t sop_idx[kMaxStateOps][4];
   uint32_t sop_mask[kMaxStateOps];
   real sop_param[kMaxStateOps][8];
-  real* obsv;              // [2][n] FluxObserver integrator (re, im); nullptr without one
+  real* obsv;              // [4][n] FluxObserver integrator (re, im, compensation terms); nullptr without one
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
 };
 

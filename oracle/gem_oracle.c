@@ -819,9 +819,9 @@ static void apply_state_ops(const gem_oracle* o, env_t* e, int64_t idx, double* 
             if (!((mask >> (4 * b + m)) & 1u)) continue;
             double z;
             if (c->sop_idx[k][0] == GEMB200_NOISE_UNIFORM) z = q[0] + (q[1] - q[0]) * u01(r[m]);
-            else if (c->sop_idx[k][0] == GEMB200_NOISE_LAPLACE) {
-              const double u = u01(r[m]);
-              z = q[0] + q[1] * (u < 0.5 ? log(2 * u) : -log(2 * (1 - u)));
+            else if (c->sop_idx[k][0] == GEMB200_NOISE_LAPLACE) { /* sign from bit 0, magnitude -log(V), V ~ U(0,1) from the other 31 bits */
+              const double v = u01(r[m] | 1u);
+              z = q[0] + q[1] * ((r[m] & 1u) ? log(v) : -log(v));
             } else { /* Box-Muller on the word pair (0,1) / (2,3); even state: cos branch, odd: sin branch */
               const double rad = sqrt(-2.0 * log(u01(r[m & 2]))), ang = 2.0 * M_PI * u01(r[(m & 2) + 1]);
               z = q[0] + q[1] * rad * ((m & 1) ? sin(ang) : cos(ang));
