@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -394,6 +395,16 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->n_rw = t;
   for (int r = 0; r < kMaxRef; ++r) if (p->rwr_w[r] == real(0)) p->rwr_pow1[r] = 1;  // unused slots: no pow()
   p->bias = (real)c.reward_bias; p->viol_reward = (real)c.violation_reward;
+  // PLAIN shape (step_kernel): decided here once; GEMB200_NO_PLAIN=1 in the environment forces the general instantiation (A/B runs)
+  {
+    bool plain = !c.finite && c.load_kind == GEMB200_LOAD_CONST_SPEED && c.solver_kind == GEMB200_SOLVER_RK4 && c.solver_nsteps == 1 &&
+                 c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
+                 c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
+                 p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
+    for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r];
+    const char* off = std::getenv("GEMB200_NO_PLAIN");
+    p->plain = plain && !(off && off[0] == '1');
+  }
   p->n_sops = c.n_state_ops;
   p->n_obs = dm.n_obs;
   p->row_stride = h->row_stride;

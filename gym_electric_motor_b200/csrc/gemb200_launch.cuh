@@ -14,12 +14,12 @@ template <int FAM, typename real> cudaError_t launch_reset_f(int nref, const Ste
 #ifdef GEMB200_TU_FAM
 constexpr int kBlock = GEMB200_BLOCK;
 
-template <int FAM, bool FINITE, typename real, int NREF, bool SOA>
+template <int FAM, bool FINITE, typename real, int NREF, bool SOA, bool PLAIN = false>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const size_t smem = (size_t)kBlock * (size_t)p.row_stride * sizeof(real);
   const int range = p.env_end - p.env_begin;
   const int grid = (range + kBlock - 1) / kBlock;
-  step_kernel<FAM, FINITE, real, NREF, SOA><<<grid, kBlock, smem, st>>>(p);
+  step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN><<<grid, kBlock, smem, st>>>(p);
   return cudaGetLastError();
 }
 template <int FAM, typename real, int NREF>
@@ -33,6 +33,9 @@ template <int FAM, typename real>
 cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
 #define GEMB200_NREF(R)                                                                         \
   case R:                                                                                       \
+    if constexpr (std::is_same<real, float>::value) {                                           \
+      if (p.plain && !finite) return p.layout == GEMB200_LAYOUT_SOA ? launch_step_t<FAM, false, real, R, true, true>(p, st) : launch_step_t<FAM, false, real, R, false, true>(p, st); \
+    }                                                                                           \
     if (p.layout == GEMB200_LAYOUT_SOA) return finite ? launch_step_t<FAM, true, real, R, true>(p, st) : launch_step_t<FAM, false, real, R, true>(p, st); \
     return finite ? launch_step_t<FAM, true, real, R, false>(p, st) : launch_step_t<FAM, false, real, R, false>(p, st);
   switch (nref) {
