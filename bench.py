@@ -86,29 +86,47 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
+        """Start early (nvidia-smi needs ~100 ms before its first row); rows are stamped on arrival, mark()/stop() bracket the timed region."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
+        time.sleep(0.03)  # let the last row of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t_begin = getattr(self, "t_begin", 0.0)
+        inside = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.03]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: take the rows closest to it
+            inside = [r for (t, r) in self.rows if t_begin - 0.25 <= t <= t_end + 0.25]
+            window = "timed region +-250 ms"
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -121,7 +139,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_arm(n_envs, steps, warmup, budget_s=None):
@@ -198,6 +216,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     n = args.envs_per_gpu
     R = 4  # replicas of the env batch that the timed steps rotate over (working set >> L2)
     envs = [make_env(n, device=local_rank, rank=rank * R + r) for r in range(R)]
@@ -218,10 +239,10 @@ def main():
     # ---------------- device-resident arm: K back-to-back launches rotating over R replicas, one event pair ----------------
     for k in range(max(W, R)):
         envs[k % R].step(pool[k % 8])
-    sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
+        sampler.mark()
     l0 = sum(e.sim.launch_count for e in envs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()

@@ -2,7 +2,7 @@
 
     python -m gym_electric_motor_b200.build [--force] [--verbose]
 
-The step kernel's 200 instantiations are spread over ten translation units (motor family x real, csrc/gemb200_step_tu.cu)
+The step kernel's 200 instantiations are spread over twelve translation units (motor family x real, csrc/gemb200_step_tu.cu)
 that compile in parallel; objects go to build/ (git- and gpurun-ignored), only the linked .so stays in the package.
 """
 import hashlib
@@ -19,7 +19,7 @@ SOURCES = [os.path.join(CSRC, "gemb200.cu"), os.path.join(CSRC, "gemb200_step_tu
 OUT = os.path.join(HERE, "libgemb200.so")
 OBJ_DIR = os.path.join(HERE, "..", "build", "gemb200")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-FAMILIES = (0, 1, 2, 3, 4)  # gemb200_params.h: MotorFamily
+FAMILIES = (0, 1, 2, 3, 4, 5)  # gemb200_params.h: MotorFamily
 REALS = ("float", "double")
 
 

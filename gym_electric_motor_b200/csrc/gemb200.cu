@@ -73,11 +73,13 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
     case GEMB200_MOTOR_SYNRM: *d = {kSYNC, 14, 4, c->finite ? 1 : 3, 3, true}; break;
     case GEMB200_MOTOR_EESM: *d = {kEESM, 16, 5, c->finite ? 2 : 4, 4, true}; break;
     case GEMB200_MOTOR_SCIM: *d = {kSCIM, 14, 6, c->finite ? 1 : 3, 5, true}; break;
+    case GEMB200_MOTOR_DFIM: *d = {kDFIM, 24, 6, c->finite ? 2 : 6, 5, true}; break;
     default: return fail(GEMB200_E_INVALID, "unknown motor_kind");
   }
   const bool three_phase = d->fam >= kSYNC;
   if (c->action_dq) {
     if (!three_phase || c->finite) return fail(GEMB200_E_INVALID, "dq actions need a three-phase motor with a continuous converter");
+    if (c->motor_kind == GEMB200_MOTOR_DFIM) return fail(GEMB200_E_INVALID, "dq actions for the DFIM (4 actions, dq_to_abc_action_processor.py:108-137) are not supported");
     d->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2;
   }
   // state-vector wrappers (gemb200_state_op): width bookkeeping as in the wrappers' set_physical_system
@@ -112,6 +114,8 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
     if (k0 != GEMB200_CONV_B6) return fail(GEMB200_E_INVALID, "three-phase motors need a B6 bridge in converter slot 0");
     if (c->motor_kind == GEMB200_MOTOR_EESM) {
       if (!is_qc(k1)) return fail(GEMB200_E_INVALID, "EESM needs a 1QC/2QC/4QC excitation converter in slot 1");
+    } else if (c->motor_kind == GEMB200_MOTOR_DFIM) {
+      if (k1 != GEMB200_CONV_B6) return fail(GEMB200_E_INVALID, "DFIM needs a second B6 bridge (rotor) in converter slot 1");
     } else if (k1 != GEMB200_CONV_NONE) return fail(GEMB200_E_INVALID, "converter slot 1 must be NONE for this motor");
   } else {
     if (!is_qc(k0)) return fail(GEMB200_E_INVALID, "DC motors need a 1QC/2QC/4QC converter in slot 0");
@@ -137,7 +141,7 @@ static int validate(const gemb200_config* c) {
   if (c->load_kind != GEMB200_LOAD_CONST_SPEED && c->load_kind != GEMB200_LOAD_POLY_STATIC) return fail(GEMB200_E_INVALID, "bad load_kind");
   if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
   if (c->dead_time_steps < 0 || c->dead_time_steps > GEMB200_MAX_DEAD_TIME) return fail(GEMB200_E_INVALID, "dead_time_steps out of range");
-  if (c->init_random && c->motor_kind == GEMB200_MOTOR_SCIM)
+  if (c->init_random && (c->motor_kind == GEMB200_MOTOR_SCIM || c->motor_kind == GEMB200_MOTOR_DFIM))
     return fail(GEMB200_E_INVALID, "random initial states are not supported for the induction motor (the reference draws its flux limits "
                                    "from the unseeded global numpy RNG, squirrel_cage_induction_motor.py:146-157)");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
@@ -218,6 +222,7 @@ static void derive_model(const gemb200_config* cfg, const Dims& dm, Derived* o) 
       c[12] = (k / sigma) / s2; c[13] = (-p * l_M * l_q / (sigma * l_d)) / s2;
       o->tq[0] = 1.5 * p * l_M * ik; o->tq[1] = 1.5 * p * (l_d - l_q);
     } break;
+    case GEMB200_MOTOR_DFIM:
     case GEMB200_MOTOR_SCIM: {  // induction_motor.py:287-310, :236-249
       const double l_m = mp[GEMB200_MP_L_M], r_r = mp[GEMB200_MP_R_E];
       const double l_s = l_m + mp[GEMB200_MP_L_SIGS], l_r = l_m + mp[GEMB200_MP_L_SIGR];
@@ -225,6 +230,8 @@ static void derive_model(const gemb200_config* cfg, const Dims& dm, Derived* o) 
       const double tau_r = l_r / r_r, tau_sig = sigma * l_s / (r_s + r_r * (l_m * l_m) / (l_r * l_r));
       c[0] = -1.0 / tau_sig; c[1] = l_m * r_r / (sigma * l_s * l_r * l_r); c[2] = l_m * p / (sigma * l_r * l_s);
       c[3] = 1.0 / (sigma * l_s); c[4] = l_m / tau_r; c[5] = -1.0 / tau_r; c[6] = p;
+      c[7] = -l_m / (sigma * l_r * l_s);  // rotor-voltage column of the current rows (DFIM)
+      c[8] = 1.0 / l_r; c[9] = l_m / l_r;  // rotor current i_r = psi_r / l_r - l_m / l_r * i_s (physical_systems.py:946-956)
       o->tq[0] = 1.5 * p * l_m / l_r;
     } break;
   }
@@ -255,7 +262,7 @@ static void derive_model(const gemb200_config* cfg, const Dims& dm, Derived* o) 
       // abc -> alpha/beta of (ua,ua,ua) is mathematically 0 (the reference shows ~1e-17 round-off here)
       const double ualpha = 2.0 / 3.0 * (ua - 0.5 * ua - 0.5 * ua), ubeta = 2.0 / 3.0 * (0.5 * std::sqrt(3.0) * ua - 0.5 * std::sqrt(3.0) * ua);
       double cs, sn, tqv, ia, ib;
-      if (dm.fam == kSCIM) {
+      if (dm.fam == kSCIM || dm.fam == kDFIM) {
         const double ef = std::atan2(y[4], y[3]);
         cs = std::cos(ef); sn = std::sin(ef);
         tqv = o->tq[0] * (y[3] * y[2] - y[4] * y[1]);
@@ -268,6 +275,19 @@ static void derive_model(const gemb200_config* cfg, const Dims& dm, Derived* o) 
       const double ud = cs * ualpha + sn * ubeta, uq = -sn * ualpha + cs * ubeta;
       s[n++] = tqv;
       s[n++] = ia; s[n++] = -0.5 * ia + 0.5 * std::sqrt(3.0) * ib; s[n++] = -0.5 * ia - 0.5 * std::sqrt(3.0) * ib;
+      if (dm.fam == kDFIM) {
+        // physical_systems.py:1062-1113: i_sdq in the field frame; i_rdq (sic) with the angle eps_field - eps_el, i_rdef = its inverse;
+        // all six bridge legs at -0.5 u_sup, whose alpha-beta image is 0
+        const double ira = o->c[8] * y[3] - o->c[9] * y[1], irb = o->c[8] * y[4] - o->c[9] * y[2];
+        const double cfe = std::cos(std::atan2(y[4], y[3]) - eps), sfe = std::sin(std::atan2(y[4], y[3]) - eps);
+        s[n++] = cs * y[1] + sn * y[2]; s[n++] = -sn * y[1] + cs * y[2];
+        s[n++] = ira; s[n++] = -0.5 * ira + 0.5 * std::sqrt(3.0) * irb; s[n++] = -0.5 * ira - 0.5 * std::sqrt(3.0) * irb;
+        s[n++] = cfe * ira + sfe * irb; s[n++] = -sfe * ira + cfe * irb;
+        s[n++] = ua; s[n++] = ua; s[n++] = ua; s[n++] = ud; s[n++] = uq;
+        s[n++] = ua; s[n++] = ua; s[n++] = ua; s[n++] = cfe * ualpha + sfe * ubeta; s[n++] = -sfe * ualpha + cfe * ubeta;
+        s[n++] = eps;
+        break;
+      }
       if (dm.fam == kSCIM) { s[n++] = cs * y[1] + sn * y[2]; s[n++] = -sn * y[1] + cs * y[2]; }
       else { s[n++] = y[1]; s[n++] = y[2]; }
       if (dm.fam == kEESM) {
@@ -397,7 +417,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->bias = (real)c.reward_bias; p->viol_reward = (real)c.violation_reward;
   // PLAIN shape (step_kernel): decided here once; GEMB200_NO_PLAIN=1 in the environment forces the general instantiation (A/B runs)
   {
-    bool plain = !c.finite && c.load_kind == GEMB200_LOAD_CONST_SPEED && c.solver_kind == GEMB200_SOLVER_RK4 && c.solver_nsteps == 1 &&
+    bool plain =
                  c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
@@ -445,6 +465,7 @@ static cudaError_t launch_step(int fam, bool finite, int nref, const StepParams<
     case kSYNC: return launch_step_f<kSYNC, real>(finite, nref, p, st);
     case kEESM: return launch_step_f<kEESM, real>(finite, nref, p, st);
     case kSCIM: return launch_step_f<kSCIM, real>(finite, nref, p, st);
+    case kDFIM: return launch_step_f<kDFIM, real>(finite, nref, p, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -456,6 +477,7 @@ static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cu
     case kSYNC: return launch_reset_f<kSYNC, real>(nref, p, st);
     case kEESM: return launch_reset_f<kEESM, real>(nref, p, st);
     case kSCIM: return launch_reset_f<kSCIM, real>(nref, p, st);
+    case kDFIM: return launch_reset_f<kDFIM, real>(nref, p, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -569,7 +591,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   derive_dims(cfg, &d);
   h->fam = d.fam; h->n_state = d.n_state; h->n_ode = d.n_ode; h->n_act = d.n_act; h->nx = d.nx; h->has_eps = d.has_eps;
   h->n_obs = d.n_obs;
-  h->row_stride = cfg->n_state_ops > 0 ? (d.n_obs | 1) : (d.fam == kEESM ? 17 : d.n_state);  // Fam<>::PAD without wrappers
+  h->row_stride = cfg->n_state_ops > 0 ? (d.n_obs | 1) : (d.fam == kEESM ? 17 : (d.fam == kDFIM ? 25 : d.n_state));  // Fam<>::PAD without wrappers
   h->n_ref = cfg->n_ref;
   h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
   h->two_segment = cfg->finite && cfg->interlocking_time > 0;
@@ -587,7 +609,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   ALLOC(h->d_stc, n * h->NC * h->rsz);
   if (cfg->dead_time_steps > 0) {
     // queue width: caller-side actions when the dead time wraps the dq transformation (or there is none), else abc(+e)
-    const int inner = cfg->finite ? d.n_act : (d.fam == kEESM ? 4 : (d.fam >= kSYNC ? 3 : d.n_act));
+    const int inner = cfg->finite ? d.n_act : (d.fam == kDFIM ? 6 : (d.fam == kEESM ? 4 : (d.fam >= kSYNC ? 3 : d.n_act)));
     h->fifo_dim = (cfg->action_dq && !cfg->dead_time_outer) ? inner : d.n_act;
     ALLOC(h->d_fifo, n * cfg->dead_time_steps * h->fifo_dim * h->rsz);
   }

@@ -14,13 +14,27 @@ template <int FAM, typename real> cudaError_t launch_reset_f(int nref, const Ste
 #ifdef GEMB200_TU_FAM
 constexpr int kBlock = GEMB200_BLOCK;
 
-template <int FAM, bool FINITE, typename real, int NREF, bool SOA, bool PLAIN = false>
+template <int FAM, bool FINITE, typename real, int NREF, bool SOA, bool PLAIN = false, bool MECH = false>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const size_t smem = (size_t)kBlock * (size_t)p.row_stride * sizeof(real);
   const int range = p.env_end - p.env_begin;
   const int grid = (range + kBlock - 1) / kBlock;
-  step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN><<<grid, kBlock, smem, st>>>(p);
+  step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);
   return cudaGetLastError();
+}
+// PLAIN instantiations (fp32): {cont, finite} x {constant speed, integrating load} x {AoS, SoA}
+template <int FAM, typename real, int NREF>
+static cudaError_t launch_plain_t(bool finite, const StepParams<real>& p, cudaStream_t st) {
+  const bool soa = p.layout == GEMB200_LAYOUT_SOA, mech = p.load_kind != GEMB200_LOAD_CONST_SPEED;
+#define GEMB200_PLAIN(F, M)                                                                                   \
+  if (finite == F && mech == M)                                                                               \
+    return soa ? launch_step_t<FAM, F, real, NREF, true, true, M>(p, st) : launch_step_t<FAM, F, real, NREF, false, true, M>(p, st);
+  GEMB200_PLAIN(false, false)
+  GEMB200_PLAIN(false, true)
+  GEMB200_PLAIN(true, false)
+  GEMB200_PLAIN(true, true)
+#undef GEMB200_PLAIN
+  return cudaErrorInvalidValue;
 }
 template <int FAM, typename real, int NREF>
 static cudaError_t launch_reset_t(const StepParams<real>& p, cudaStream_t st) {
@@ -34,7 +48,7 @@ cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cuda
 #define GEMB200_NREF(R)                                                                         \
   case R:                                                                                       \
     if constexpr (std::is_same<real, float>::value) {                                           \
-      if (p.plain && !finite) return p.layout == GEMB200_LAYOUT_SOA ? launch_step_t<FAM, false, real, R, true, true>(p, st) : launch_step_t<FAM, false, real, R, false, true>(p, st); \
+      if (p.plain) return launch_plain_t<FAM, real, R>(finite, p, st);                         \
     }                                                                                           \
     if (p.layout == GEMB200_LAYOUT_SOA) return finite ? launch_step_t<FAM, true, real, R, true>(p, st) : launch_step_t<FAM, false, real, R, true>(p, st); \
     return finite ? launch_step_t<FAM, true, real, R, false>(p, st) : launch_step_t<FAM, false, real, R, false>(p, st);

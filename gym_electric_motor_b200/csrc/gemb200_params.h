@@ -9,7 +9,7 @@
 
 namespace gemb200 {
 
-constexpr int kMaxState = 24;
+constexpr int kMaxState = 28;
 constexpr int kMaxRef = 4;
 constexpr int kMaxConstraints = 4;
 constexpr int kMaxStateOps = 4;
@@ -39,7 +39,8 @@ enum MotorFamily : int {
   kDC2 = 1,   // two currents: Shunt (+i_sum), ExtEx         state [omega, torque, i_a, i_e, u(_a), (u_e,) u_sup(, i_sum)]
   kSYNC = 2,  // PMSM, SynRM                                 14 states
   kEESM = 3,  // 16 states
-  kSCIM = 4   // 14 states
+  kSCIM = 4,  // 14 states
+  kDFIM = 5   // 24 states: SCIM model + rotor voltages from a second B6 bridge
 };
 
 // RNG stream ids (word 3 of the Philox counter); shared convention with the test oracle.

@@ -3,7 +3,7 @@ from .converters import (ContB6BridgeConverter, ContDynamicallyAveragedConverter
                          ContOneQuadrantConverter, ContTwoQuadrantConverter, FiniteB6BridgeConverter, FiniteConverter,
                          FiniteFourQuadrantConverter, FiniteMultiConverter, FiniteOneQuadrantConverter, FiniteTwoQuadrantConverter,
                          PowerElectronicConverter)
-from .electric_motors import (DcExternallyExcitedMotor, DcMotor, DcPermanentlyExcitedMotor, DcSeriesMotor, DcShuntMotor, ElectricMotor,
+from .electric_motors import (DcExternallyExcitedMotor, DcMotor, DcPermanentlyExcitedMotor, DcSeriesMotor, DcShuntMotor, DoublyFedInductionMotor, ElectricMotor,
                               ExternallyExcitedSynchronousMotor, InductionMotor, PermanentMagnetSynchronousMotor,
                               SquirrelCageInductionMotor, SynchronousMotor, SynchronousReluctanceMotor, ThreePhaseMotor)
 from .mechanical_loads import ConstantSpeedLoad, ExternalSpeedLoad, MechanicalLoad, OrnsteinUhlenbeckLoad, PolynomialStaticLoad

@@ -122,7 +122,7 @@ class _MultiMixin:
                 raise TypeError("cannot mix finite and continuous sub-converters")
             self._sub_converters.append(sub)
         if len(self._sub_converters) > 2:
-            raise NotImplementedError("at most two sub-converters are supported on the device (DFIM is out of scope, SURVEY.md §8f)")
+            raise NotImplementedError("at most two sub-converters are supported on the device")
         ils = {s.interlocking_time for s in self._sub_converters}
         if len(ils) > 1:
             raise NotImplementedError("sub-converters with different interlocking times are not supported")

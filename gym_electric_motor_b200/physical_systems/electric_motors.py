@@ -432,3 +432,31 @@ class SquirrelCageInductionMotor(InductionMotor):
     """reference squirrel_cage_induction_motor.py"""
 
     KIND = K.MOTOR_SCIM
+
+
+class DoublyFedInductionMotor(InductionMotor):
+    """reference doubly_fed_induction_motor.py: the induction model with accessible rotor windings (second B6 bridge)."""
+
+    KIND = K.MOTOR_DFIM
+    ROTOR_VOLTAGES = ["u_ralpha", "u_rbeta"]
+    ROTOR_CURRENTS = ["i_ralpha", "i_rbeta"]
+    IO_VOLTAGES = InductionMotor.IO_VOLTAGES + ["u_ra", "u_rb", "u_rc", "u_rd", "u_rq"]
+    IO_CURRENTS = InductionMotor.IO_CURRENTS + ["i_ra", "i_rb", "i_rc", "i_rd", "i_rq"]
+    _default_motor_parameter = {"p": 2, "l_m": 297.5e-3, "l_sigs": 25.71e-3, "l_sigr": 25.71e-3, "j_rotor": 13.695e-3, "r_s": 4.42, "r_r": 3.51}
+    _default_limits = dict(omega=1800 * np.pi / 30, torque=0.0, i=9, epsilon=math.pi, u=720)
+    _default_nominal_values = dict(omega=1650 * np.pi / 30, torque=0.0, i=7.5, epsilon=math.pi, u=720)
+
+    def _three_phase_update_limits(self):
+        """DoublyFedInductionMotor._update_limits (doubly_fed_induction_motor.py:126-147): rotor quantities included, current fallback
+        u / r_r; then ThreePhaseMotor._update_limits."""
+        voltage_limit = 0.5 * self._limits["u"]
+        voltage_nominal = 0.5 * self._nominal_values["u"]
+        limits_agenda, nominal_agenda = {}, {}
+        for u, i in zip(self.IO_VOLTAGES + self.ROTOR_VOLTAGES, self.IO_CURRENTS + self.ROTOR_CURRENTS):
+            limits_agenda[u] = voltage_limit
+            nominal_agenda[u] = voltage_nominal
+            limits_agenda[i] = self._limits.get("i", None) or self._limits[u] / self._motor_parameter["r_r"]
+            nominal_agenda[i] = self._nominal_values.get("i", None) or self._nominal_values[u] / self._motor_parameter["r_r"]
+        self._base_update_limits(limits_agenda, nominal_agenda)
+        self._base_update_limits(dict(torque=self._torque_limit()))
+

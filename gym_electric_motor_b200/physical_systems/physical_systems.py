@@ -12,7 +12,7 @@ from .. import _cabi as K
 from ..spaces import Box
 from ..utils import set_state_array
 from .converters import ContDynamicallyAveragedConverter, FiniteConverter, PowerElectronicConverter
-from .electric_motors import (DcExternallyExcitedMotor, DcMotor, DcPermanentlyExcitedMotor, DcSeriesMotor, DcShuntMotor, ElectricMotor,
+from .electric_motors import (DcExternallyExcitedMotor, DcMotor, DcPermanentlyExcitedMotor, DcSeriesMotor, DcShuntMotor, DoublyFedInductionMotor, ElectricMotor,
                               ExternallyExcitedSynchronousMotor, InductionMotor, SynchronousMotor)
 from .mechanical_loads import MechanicalLoad
 from .solvers import OdeSolver
@@ -430,8 +430,17 @@ class SquirrelCageInductionMotorSystem(ThreePhaseMotorSystem):
     _NAMES = ["torque", "i_sa", "i_sb", "i_sc", "i_sd", "i_sq", "u_sa", "u_sb", "u_sc", "u_sd", "u_sq", "epsilon", "u_sup"]
 
 
-def _dfim(*a, **k):
-    raise NotImplementedError("DoublyFedInductionMotorSystem (physical_systems.py:850-1113) is out of scope this round (SURVEY.md §8f row 2)")
+class DoublyFedInductionMotorSystem(ThreePhaseMotorSystem):
+    """reference physical_systems.py:850-1113: stator and rotor each fed by a B6 bridge (Cont/FiniteMultiConverter of two B6)."""
 
+    _MOTOR_BASE = DoublyFedInductionMotor
+    _NAMES = ["torque", "i_sa", "i_sb", "i_sc", "i_sd", "i_sq", "i_ra", "i_rb", "i_rc", "i_rd", "i_rq", "u_sa", "u_sb", "u_sc", "u_sd", "u_sq",
+              "u_ra", "u_rb", "u_rc", "u_rd", "u_rq", "epsilon", "u_sup"]
 
-DoublyFedInductionMotorSystem = _dfim
+    def __init__(self, control_space="abc", **kwargs):
+        if control_space != "abc":
+            raise NotImplementedError("dq actions for the DFIM need the 4-action DqToAbcActionProcessor (dq_to_abc_action_processor.py:108-137); "
+                                      "not on the device path")
+        super().__init__(control_space=control_space, **kwargs)
+        if self._converter.slots() != [K.CONV_B6, K.CONV_B6]:
+            raise ValueError("the DFIM system needs a multi converter of two B6 bridges (stator, rotor)")

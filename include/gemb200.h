@@ -23,12 +23,12 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 2
+#define GEMB200_ABI_VERSION 3
 
 /* limits of the POD config */
-#define GEMB200_MAX_STATE 24   /* longest state vector in scope: EESM 16 */
+#define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
 #define GEMB200_MAX_ODE 8      /* SCIM: omega + 4 + eps = 6 */
-#define GEMB200_MAX_ACT 4      /* EESM: 3 (B6) + 1 (4QC) */
+#define GEMB200_MAX_ACT 6      /* DFIM: two B6 bridges; EESM: 3 (B6) + 1 (4QC) */
 #define GEMB200_MAX_REF 4
 #define GEMB200_MAX_DEAD_TIME 8
 #define GEMB200_MAX_CONSTRAINTS 4
@@ -51,8 +51,10 @@ enum gemb200_motor_kind {
   GEMB200_MOTOR_PMSM = 4,      /* permanent_magnet_synchronous_motor.py:107-139 params: p l_d l_q r_s psi_p j_rotor */
   GEMB200_MOTOR_SYNRM = 5,     /* synchronous_reluctance_motor.py:117-139      params: p l_d l_q r_s j_rotor */
   GEMB200_MOTOR_EESM = 6,      /* externally_excited_synchronous_motor.py:125-203 params: p l_d l_q l_m l_e r_s r_e k j_rotor */
-  GEMB200_MOTOR_SCIM = 7       /* induction_motor.py:187-310, squirrel_cage_induction_motor.py:121-129
+  GEMB200_MOTOR_SCIM = 7,      /* induction_motor.py:187-310, squirrel_cage_induction_motor.py:121-129
                                   params: p l_m l_sigs l_sigr r_s r_r j_rotor */
+  GEMB200_MOTOR_DFIM = 8       /* doubly_fed_induction_motor.py + physical_systems.py:850-1113: the induction model with the rotor fed
+                                  by a second B6 bridge (converter slot 1); same parameters as SCIM */
 };
 
 /* motor_param[] slots (physical parameters exactly as in the reference's motor_parameter dicts) */
@@ -67,7 +69,8 @@ enum gemb200_motor_param {
 
 /* converter slots — reference physical_systems/converters.py.  A converter is 1 or 2 slots:
  * DC motors: slot0 in {1QC,2QC,4QC}; ExtEx: slot0 (armature) + slot1 (excitation);
- * PMSM/SynRM/SCIM: slot0 = B6; EESM: slot0 = B6, slot1 in {1QC,2QC,4QC}  (Cont/FiniteMultiConverter :498-740). */
+ * PMSM/SynRM/SCIM: slot0 = B6; EESM: slot0 = B6, slot1 in {1QC,2QC,4QC}; DFIM: slot0 = B6 (stator), slot1 = B6 (rotor)
+ * (Cont/FiniteMultiConverter :498-740). */
 enum gemb200_converter_kind {
   GEMB200_CONV_NONE = 0,
   GEMB200_CONV_1QC = 1, /* :218-245 finite, :371-401 continuous */

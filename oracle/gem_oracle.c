@@ -45,7 +45,7 @@ typedef struct {
   double ode[GEMB200_MAX_ODE]; /* [mechanical | motor] physical_systems.py:270 */
   double t;
   long k;
-  sub2qc_t sub[5]; /* slot0: up to 3 legs (B6) or 2 (4QC) ; slot1: up to 2 */
+  sub2qc_t sub[6]; /* slot0: up to 3 legs (B6) or 2 (4QC) ; slot1: up to 3 (the DFIM's rotor bridge) */
   int cur_action1qc[2];
   /* reference generator slots (subepisoded_reference_generator.py) */
   double ref_value[GEMB200_MAX_REF];
@@ -136,6 +136,7 @@ static int dims(gem_oracle* o) {
     case GEMB200_MOTOR_SYNRM: o->n_motor = 3; o->n_cur = 2; o->n_volt = 2; o->n_state = 14; break;
     case GEMB200_MOTOR_EESM: o->n_motor = 4; o->n_cur = 3; o->n_volt = 3; o->n_state = 16; break;
     case GEMB200_MOTOR_SCIM: o->n_motor = 5; o->n_cur = 2; o->n_volt = 2; o->n_state = 14; break;
+    case GEMB200_MOTOR_DFIM: o->n_motor = 5; o->n_cur = 2; o->n_volt = 4; o->n_state = 24; break; /* physical_systems.py:891-916 */
     default: return -1;
   }
   o->n_ode = 1 + o->n_motor;
@@ -214,6 +215,7 @@ static void update_model(gem_oracle* o) {
       m[3][0] = p;
       for (int j = 0; j < 10; ++j) { m[0][j] = m[0][j] / l_d; m[1][j] = m[1][j] / l_q; m[2][j] = m[2][j] / l_E / i_k_rs; }
     } break;
+    case GEMB200_MOTOR_DFIM:
     case GEMB200_MOTOR_SCIM: { /* induction_motor.py:287-310
         features [omega, i_a, i_b, psi_a, psi_b, omega*psi_a, omega*psi_b, u_sa, u_sb, u_ra, u_rb] */
       double l_m = mp[GEMB200_MP_L_M], r_r = mp[GEMB200_MP_R_E];
@@ -260,6 +262,9 @@ static void electrical_ode(const gem_oracle* o, const double* ms, const double* 
     case GEMB200_MOTOR_SCIM: /* induction_motor.py:187-217 with rotor voltages 0 (squirrel_cage_induction_motor.py:121-129) */
       f[0] = omega; f[1] = ms[0]; f[2] = ms[1]; f[3] = ms[2]; f[4] = ms[3]; f[5] = omega * ms[2]; f[6] = omega * ms[3];
       f[7] = u[0]; f[8] = u[1]; f[9] = 0.0; f[10] = 0.0; n = 11; break;
+    case GEMB200_MOTOR_DFIM: /* induction_motor.py:187-217, u = [u_salpha, u_sbeta, u_ralpha, u_rbeta] */
+      f[0] = omega; f[1] = ms[0]; f[2] = ms[1]; f[3] = ms[2]; f[4] = ms[3]; f[5] = omega * ms[2]; f[6] = omega * ms[3];
+      f[7] = u[0]; f[8] = u[1]; f[9] = u[2]; f[10] = u[3]; n = 11; break;
   }
   for (int i = 0; i < o->mc_rows; ++i) {
     double s = 0.0;
@@ -281,6 +286,7 @@ static double torque(const gem_oracle* o, const double* ms) {
       return 1.5 * mp[GEMB200_MP_P] * ((mp[GEMB200_MP_L_D] - mp[GEMB200_MP_L_Q]) * ms[0]) * ms[1];
     case GEMB200_MOTOR_EESM: /* externally_excited_synchronous_motor.py:200-203 */
       return 1.5 * mp[GEMB200_MP_P] * (o->l_M * ms[2] * o->i_k_rs + (mp[GEMB200_MP_L_D] - mp[GEMB200_MP_L_Q]) * ms[0]) * ms[1];
+    case GEMB200_MOTOR_DFIM:
     case GEMB200_MOTOR_SCIM: /* induction_motor.py:236-249 */
       return o->tq0 * (ms[2] * ms[1] - ms[3] * ms[0]);
   }
@@ -621,6 +627,14 @@ static double wrap_eps(double eps) { /* physical_systems.py:520-522: python floa
   return r;
 }
 
+/* DoublyFedInductionMotorSystem.calculate_rotor_current physical_systems.py:946-956; y = [omega, i_sa, i_sb, psi_ra, psi_rb, eps] */
+static void dfim_rotor_current(const gem_oracle* o, const double* y, double* i_r) {
+  const double* mp = o->cfg.motor_param;
+  const double l_r = mp[GEMB200_MP_L_M] + mp[GEMB200_MP_L_SIGR];
+  i_r[0] = 1 / l_r * y[3] - mp[GEMB200_MP_L_M] / l_r * y[1];
+  i_r[1] = 1 / l_r * y[4] - mp[GEMB200_MP_L_M] / l_r * y[2];
+}
+
 /* ------------------------------------------------------------------------------------------------------------ */
 /* simulate                                                                                                      */
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -629,7 +643,7 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
   const int mk = c->motor_kind;
   const double u_sup = c->u_sup; /* IdealVoltageSupply.get_voltage voltage_supplies.py:70-72 */
   double* y = e->ode;
-  double i_in[4], u_in[4], u_solver[4];
+  double i_in[6], u_in[6], u_solver[4];
   double t0 = e->t;
   int nseg = conv_set_action(o, e, act_f, act_i, t0);
   double seg_end[2];
@@ -648,15 +662,28 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
       case GEMB200_MOTOR_SYNRM: eps = y[3]; dq_to_abc(y + 1, eps, i_in); break; /* :489-493, :505 */
       case GEMB200_MOTOR_EESM: eps = y[4]; dq_to_abc(y + 1, eps, i_in); i_in[3] = y[3]; break; /* :621-624 */
       case GEMB200_MOTOR_SCIM: eps_fs = atan2(y[4], y[3]); t_32(y + 1, i_in); break; /* :775-782, :765-769 */
+      case GEMB200_MOTOR_DFIM: { /* :958-963 / :975-981 */
+        double i_r[2];
+        eps_fs = atan2(y[4], y[3]); eps = y[5];
+        t_32(y + 1, i_in);
+        dfim_rotor_current(o, y, i_r);
+        t_32(i_r, i_in + 3); /* alphabeta_to_abc_space(calculate_rotor_current(.)) */
+      } break;
     }
     (void)conv_i_sup(o, e, i_in);             /* :507 */
     conv_convert(o, e, i_in, t_solver, u_in); /* :509 */
-    for (int j = 0; j < 4; ++j) u_in[j] *= u_sup; /* :510 */
+    for (int j = 0; j < 6; ++j) u_in[j] *= u_sup; /* :510 */
     switch (mk) {
       case GEMB200_MOTOR_PMSM:
       case GEMB200_MOTOR_SYNRM: abc_to_dq(u_in, eps, u_solver); break;                  /* :511 */
       case GEMB200_MOTOR_EESM: abc_to_dq(u_in, eps, u_solver); u_solver[2] = u_in[3]; break; /* :642 */
       case GEMB200_MOTOR_SCIM: t_23(u_in, u_solver); break;                             /* :797-799 */
+      case GEMB200_MOTOR_DFIM: { /* :969-973 */
+        double u_rdq[2];
+        abc_to_dq(u_in + 3, eps_fs - eps, u_rdq);
+        t_23(u_in, u_solver);
+        q_rot(u_rdq, eps_fs, u_solver + 2);
+      } break;
       default: u_solver[0] = u_in[0]; u_solver[1] = u_in[1]; break;
     }
     t_solver = integrate(o, y, t_solver, seg_end[seg], u_solver); /* :513 */
@@ -692,6 +719,25 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
       state[n++] = u_solver[0]; state[n++] = u_solver[1]; state[n++] = u_solver[2];
       state[n++] = wrap_eps(y[4]);
     } break;
+    case GEMB200_MOTOR_DFIM: { /* :1000-1035: eps_fs / eps are still the angles at the start of the last segment */
+      double u_sdq[2], u_rdq[2], i_sdq[2], i_sabc[3], i_r[2], i_rdq[2], i_rdef[3];
+      abc_to_dq(u_in, eps_fs, u_sdq);
+      abc_to_dq(u_in + 3, eps_fs - eps, u_rdq);
+      q_rot(y + 1, -eps_fs, i_sdq);
+      dq_to_abc(i_sdq, eps_fs, i_sabc);
+      dfim_rotor_current(o, y, i_r);
+      q_rot(i_r, -eps_fs, i_rdq);
+      dq_to_abc(i_rdq, eps_fs - eps, i_rdef);
+      for (int j = 0; j < 3; ++j) state[n++] = i_sabc[j];
+      state[n++] = i_sdq[0]; state[n++] = i_sdq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = i_rdef[j];
+      state[n++] = i_rdq[0]; state[n++] = i_rdq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = u_in[j];
+      state[n++] = u_sdq[0]; state[n++] = u_sdq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = u_in[3 + j];
+      state[n++] = u_rdq[0]; state[n++] = u_rdq[1];
+      state[n++] = wrap_eps(y[5]);
+    } break;
     case GEMB200_MOTOR_SCIM: { /* :794-814: u_dq and i_dq use the field angle at the start of the last segment */
       double u_dq[2], i_dq[2], i_abc[3];
       abc_to_dq(u_in, eps_fs, u_dq);
@@ -726,9 +772,9 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
     rng4(o, idx, STREAM_INIT_STATE2, r1);
     for (int j = 0; j < o->n_ode; ++j) y[j] = c->init_lo[j] + (c->init_hi[j] - c->init_lo[j]) * u01(j < 4 ? r0[j] : r1[j - 4]);
   }
-  double u_abc[5] = {0, 0, 0, 0, 0};
+  double u_abc[6] = {0, 0, 0, 0, 0, 0};
   conv_reset(o, e, u_abc);
-  for (int j = 0; j < 4; ++j) u_abc[j] *= c->u_sup;
+  for (int j = 0; j < 6; ++j) u_abc[j] *= c->u_sup;
   e->t = 0; e->k = 0;
   memset(e->fifo, 0, sizeof(e->fifo)); /* DeadTimeProcessor.reset dead_time_processor.py:68-78: queue of zero actions */
   double tq = torque(o, y + 1);
@@ -761,6 +807,27 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
       state[n++] = y[1]; state[n++] = y[2]; state[n++] = y[3];
       for (int j = 0; j < 4; ++j) state[n++] = u_abc[j];
       state[n++] = u_dq[0]; state[n++] = u_dq[1];
+      state[n++] = eps;
+    } break;
+    case GEMB200_MOTOR_DFIM: { /* :1062-1113 */
+      double eps = y[5], eps_fs = atan2(y[4], y[3]), u_sdq[2], u_rdq[2], i_sdq[2], i_sabc[3], i_r[2], i_rdq[2], i_rdef[3];
+      if (eps > M_PI) eps -= 2 * M_PI;
+      if (eps_fs > M_PI) eps_fs -= 2 * M_PI;
+      abc_to_dq(u_abc, eps_fs, u_sdq);
+      abc_to_dq(u_abc + 3, eps_fs - eps, u_rdq);
+      q_rot(y + 1, -eps_fs, i_sdq);
+      dq_to_abc(i_sdq, eps_fs, i_sabc);
+      dfim_rotor_current(o, y, i_r);
+      q_rot(i_r, -(eps_fs - eps), i_rdq); /* (sic) the reset uses eps_field - eps_el here, simulate uses eps_field */
+      dq_to_abc(i_rdq, eps_fs - eps, i_rdef);
+      for (int j = 0; j < 3; ++j) state[n++] = i_sabc[j];
+      state[n++] = i_sdq[0]; state[n++] = i_sdq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = i_rdef[j];
+      state[n++] = i_rdq[0]; state[n++] = i_rdq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = u_abc[j];
+      state[n++] = u_sdq[0]; state[n++] = u_sdq[1];
+      for (int j = 0; j < 3; ++j) state[n++] = u_abc[3 + j];
+      state[n++] = u_rdq[0]; state[n++] = u_rdq[1];
       state[n++] = eps;
     } break;
     case GEMB200_MOTOR_SCIM: {
@@ -1025,7 +1092,7 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
   const double* af = o->cfg.finite ? NULL : (const double*)action + i * o->n_act;
   const int32_t* ai = o->cfg.finite ? (const int32_t*)action + i * o->n_act : NULL;
   /* physical-system wrappers (core.py:266-267): DeadTimeProcessor and DqToAbcActionProcessor in either order */
-  double abuf[GEMB200_MAX_ACT] = {0, 0, 0, 0};
+  double abuf[GEMB200_MAX_ACT] = {0, 0, 0, 0, 0, 0};
   int32_t ibuf[2] = {0, 0};
   const gemb200_config* c = &o->cfg;
   const int slot = c->dead_time_steps > 0 ? (int)((o->n_steps - 1) % (uint64_t)c->dead_time_steps) : 0;

@@ -149,7 +149,9 @@ def describe(env, case):
         supply_class=type(p.supply).__name__,
         u_sup=float(p.supply.u_nominal),
         converter_class=type(conv).__name__,
-        interlocking_time=float(conv._interlocking_time),
+        # a multi converter keeps its own (unused) copy; the sub-converters' value is the one in force
+        interlocking_time=float(max([conv._interlocking_time] + [sc._interlocking_time for sc in getattr(conv, "_sub_converters", [])])
+                                if case.get("multi") is not None else conv._interlocking_time),
         reference_names=list(env.reference_generator.reference_names),
         referenced_states=np.asarray(env.reference_generator.referenced_states).astype(int).tolist(),
         reward_weights=np.asarray(env.reward_function._reward_weights, dtype=float).tolist(),
@@ -178,6 +180,9 @@ def record(case):
         kwargs["tau"] = case["tau"]
     if case.get("converter_cls") is not None:
         kwargs["converter"] = getattr(ps, case["converter_cls"])(**case.get("converter_args", {}))
+    if case.get("multi") is not None:  # multi converter built from INSTANCES, as the reference's env defaults do
+        subs = [getattr(ps, c)(**a) for c, a in case["multi"]]
+        kwargs["converter"] = (ps.FiniteMultiConverter if case["env_id"].startswith("Finite") else ps.ContMultiConverter)(subconverters=subs)
     if case.get("wrappers"):
         from gym_electric_motor.physical_system_wrappers import (CosSinProcessor, DeadTimeProcessor, DqToAbcActionProcessor,
                                                                  FluxObserver)
@@ -280,6 +285,16 @@ CASES = [
     C("scim_cc_dopri5", "Cont-CC-SCIM-v0", "dopri5", steps=1500),
     C("scim_sc_rk4", "Cont-SC-SCIM-v0", "rk4", steps=1500),
     C("scim_fin_sc_rk4", "Finite-SC-SCIM-v0", "rk4", steps=2000),
+    # doubly fed induction motor: two B6 bridges (stator, rotor)
+    C("dfim_cc_rk4", "Cont-CC-DFIM-v0", "rk4", steps=2000),
+    C("dfim_cc_euler", "Cont-CC-DFIM-v0", "euler", steps=1500),
+    C("dfim_cc_dopri5", "Cont-CC-DFIM-v0", "dopri5", steps=1500),
+    C("dfim_sc_rk4", "Cont-SC-DFIM-v0", "rk4", steps=1500),
+    C("dfim_cc_interlock_rk4", "Cont-CC-DFIM-v0", "rk4", steps=1500,
+      multi=[("ContB6BridgeConverter", dict(interlocking_time=2e-6)), ("ContB6BridgeConverter", dict(interlocking_time=2e-6))]),
+    C("dfim_fin_cc_rk4", "Finite-CC-DFIM-v0", "rk4", steps=2000),
+    C("dfim_fin_sc_interlock_rk4", "Finite-SC-DFIM-v0", "rk4", steps=2000,
+      multi=[("FiniteB6BridgeConverter", dict(interlocking_time=1e-6)), ("FiniteB6BridgeConverter", dict(interlocking_time=1e-6))]),
     # remaining DC family
     C("series_cc_rk4", "Cont-CC-SeriesDc-v0", "rk4", steps=1500),
     C("series_sc_dopri5", "Cont-SC-SeriesDc-v0", "dopri5", steps=1500),

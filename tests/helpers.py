@@ -28,6 +28,7 @@ MOTOR_KIND = {
     "SynchronousReluctanceMotor": K.MOTOR_SYNRM,
     "ExternallyExcitedSynchronousMotor": K.MOTOR_EESM,
     "SquirrelCageInductionMotor": K.MOTOR_SCIM,
+    "DoublyFedInductionMotor": K.MOTOR_DFIM,
 }
 MP_SLOT = dict(
     p=K.MP_P, r_s=K.MP_R_S, l_d=K.MP_L_D, l_q=K.MP_L_Q, psi_p=K.MP_PSI_P, j_rotor=K.MP_J_ROTOR, r_a=K.MP_R_A,
@@ -45,7 +46,7 @@ CONV = {
     "FiniteB6BridgeConverter": (1, [K.CONV_B6]),
 }
 N_MOTOR_ODE = {K.MOTOR_PERMEX_DC: 1, K.MOTOR_SERIES_DC: 1, K.MOTOR_SHUNT_DC: 2, K.MOTOR_EXTEX_DC: 2, K.MOTOR_PMSM: 3,
-               K.MOTOR_SYNRM: 3, K.MOTOR_EESM: 4, K.MOTOR_SCIM: 5}
+               K.MOTOR_SYNRM: 3, K.MOTOR_EESM: 4, K.MOTOR_SCIM: 5, K.MOTOR_DFIM: 5}
 
 
 def golden_names():
@@ -84,7 +85,7 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
         cfg.finite, kinds = CONV[cc]
     elif cc in ("ContMultiConverter", "FiniteMultiConverter"):
         cfg.finite = int(cc.startswith("Finite"))
-        kinds = [K.CONV_B6, K.CONV_4QC] if mk == K.MOTOR_EESM else [K.CONV_4QC, K.CONV_4QC]
+        kinds = [K.CONV_B6, K.CONV_4QC] if mk == K.MOTOR_EESM else ([K.CONV_B6, K.CONV_B6] if mk == K.MOTOR_DFIM else [K.CONV_4QC, K.CONV_4QC])
     else:
         raise ValueError(cc)
     for i, kd in enumerate(kinds):

@@ -11,13 +11,11 @@ from gym_electric_motor_b200 import _cabi as K
 from helpers import GOLDEN_DIR, config_from_meta, load_golden
 
 TABLE = json.load(open(os.path.join(GOLDEN_DIR, "env_table.json")))
-IDS = [k for k in sorted(TABLE) if "DFIM" not in k]
+IDS = sorted(TABLE)  # all 54 registered ids of the reference
 
 
 def test_registry_covers_reference_ids():
-    assert sorted(gem.env_ids()) == IDS
-    with pytest.raises(NotImplementedError):
-        gem.make("Cont-CC-DFIM-v0")
+    assert sorted(gem.env_ids()) == IDS and len(IDS) == 54
     with pytest.raises(KeyError):
         gem.make("Cont-CC-Nope-v0")
 

@@ -69,6 +69,7 @@ def main():
         ("Cont-CC-EESM-v0 rk4x1 f32", "Cont-CC-EESM-v0", dict(ode_solver=RK4()), 161),
         ("Cont-CC-SynRM-v0 rk4x1 f32", "Cont-CC-SynRM-v0", dict(ode_solver=RK4()), 129),
         ("Cont-SC-PMSM-v0 rk4x1 f32 (PolynomialStaticLoad)", "Cont-SC-PMSM-v0", dict(ode_solver=RK4()), 117),
+        ("Cont-CC-DFIM-v0 rk4x1 f32", "Cont-CC-DFIM-v0", dict(ode_solver=RK4()), 4 * 6 + 2 * 4 * 6 + 4 * 24 + 4 * 2 + 2 * 4 * 2 + 5),
         ("Cont-CC-PermExDc-v0 euler f32", "Cont-CC-PermExDc-v0", dict(ode_solver=gem.physical_systems.EulerSolver()), 4 + 2 * 4 * 2 + 4 * 5 + 4 + 2 * 4 + 5),
     ]
     for label, env_id, kw, balg in cases:
