@@ -425,6 +425,12 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     const char* off = std::getenv("GEMB200_NO_PLAIN");
     p->plain = plain && !(off && off[0] == '1');
   }
+  {  // L2 prefetch distance: one wave of resident threads (SMs x blocks/SM x block size); GEMB200_PF_DIST overrides (0 = off)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+    p->pf_dist = sms * 4 * GEMB200_BLOCK;  // measured optimum 0.25-1 wave, flat (profiles/r01_variants.md)
+    if (const char* e = std::getenv("GEMB200_PF_DIST")) p->pf_dist = std::atoi(e);
+  }
   p->n_sops = c.n_state_ops;
   p->n_obs = dm.n_obs;
   p->row_stride = h->row_stride;

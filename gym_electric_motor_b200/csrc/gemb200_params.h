@@ -155,6 +155,7 @@ struct StepParams {
   uint32_t sop_mask[kMaxStateOps];
   real sop_param[kMaxStateOps][8];
   real* obsv;              // [4][n] FluxObserver integrator (re, im, compensation terms); nullptr without one
+  int32_t pf_dist;         // envs between a thread's env and the one it prefetches into L2 (0: off); ~ one wave of resident threads
   int32_t plain;           // 1: this configuration has the PLAIN shape (see step_kernel) -> specialised instantiation
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
 };
