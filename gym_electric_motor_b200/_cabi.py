@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
@@ -25,6 +25,7 @@ LAYOUT_AOS, LAYOUT_SOA = 0, 1
 AUTORESET_NONE, AUTORESET_SAME_STEP = 0, 1
 SOP_NONE, SOP_COS_SIN, SOP_FLUX_OBSERVER, SOP_NOISE = range(4)
 NOISE_NORMAL, NOISE_UNIFORM, NOISE_LAPLACE = range(3)
+SUPPLY_IDEAL, SUPPLY_RC = 0, 1
 
 E_INVALID, E_CUDA, E_NOMEM, E_ABI = -1, -2, -3, -4
 
@@ -94,6 +95,8 @@ class GemB200Config(C.Structure):
         ("sop_idx", (C.c_int32 * 4) * MAX_STATE_OPS),
         ("sop_mask", C.c_uint32 * MAX_STATE_OPS),
         ("sop_param", (C.c_double * 8) * MAX_STATE_OPS),
+        ("supply_kind", C.c_int32),
+        ("supply_param", C.c_double * 4),
     ]
 
 

@@ -40,6 +40,7 @@ struct gemb200_handle {
   uint16_t* d_sw = nullptr;
   void* d_fifo = nullptr;
   int fifo_dim = 0;
+  void* d_sup = nullptr;   // RC supply state [2][n]
   void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
   int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
@@ -144,6 +145,8 @@ static int validate(const gemb200_config* c) {
   if (c->init_random && (c->motor_kind == GEMB200_MOTOR_SCIM || c->motor_kind == GEMB200_MOTOR_DFIM))
     return fail(GEMB200_E_INVALID, "random initial states are not supported for the induction motor (the reference draws its flux limits "
                                    "from the unseeded global numpy RNG, squirrel_cage_induction_motor.py:146-157)");
+  if (c->supply_kind != GEMB200_SUPPLY_IDEAL && c->supply_kind != GEMB200_SUPPLY_RC) return fail(GEMB200_E_INVALID, "bad supply_kind");
+  if (c->supply_kind == GEMB200_SUPPLY_RC && !(c->supply_param[0] > 0 && c->supply_param[1] > 0)) return fail(GEMB200_E_INVALID, "RC supply needs R > 0 and C > 0");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
   Dims d;
   int rc = derive_dims(c, &d);
@@ -418,7 +421,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   // PLAIN shape (step_kernel): decided here once; GEMB200_NO_PLAIN=1 in the environment forces the general instantiation (A/B runs)
   {
     bool plain =
-                 c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
+                 c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
     for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r];
@@ -431,6 +434,10 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     p->pf_dist = sms * 4 * GEMB200_BLOCK;  // measured optimum 0.25-1 wave, flat (profiles/r01_variants.md)
     if (const char* e = std::getenv("GEMB200_PF_DIST")) p->pf_dist = std::atoi(e);
   }
+  p->supply_kind = c.supply_kind;
+  p->sup = static_cast<real*>(h->d_sup);
+  p->sup_k1 = c.supply_kind == GEMB200_SUPPLY_RC ? (real)(c.tau / (c.supply_param[0] * c.supply_param[1])) : real(0);
+  p->sup_k2 = (real)c.supply_param[0];
   p->n_sops = c.n_state_ops;
   p->n_obs = dm.n_obs;
   p->row_stride = h->row_stride;
@@ -620,7 +627,8 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
     ALLOC(h->d_fifo, n * cfg->dead_time_steps * h->fifo_dim * h->rsz);
   }
   if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
-  if (h->two_segment) ALLOC(h->d_sw, n * sizeof(uint16_t));
+  if (h->two_segment || (cfg->finite && cfg->supply_kind == GEMB200_SUPPLY_RC)) ALLOC(h->d_sw, n * sizeof(uint16_t));
+  if (cfg->supply_kind == GEMB200_SUPPLY_RC) ALLOC(h->d_sup, n * 2 * h->rsz);
   if (d.has_observer) ALLOC(h->d_obsv, n * 4 * h->rsz);
 #undef ALLOC
   Derived dv;
@@ -640,7 +648,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -810,6 +818,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_sw) s[k++] = {h->d_sw, n * sizeof(uint16_t)};
   if (h->d_fifo) s[k++] = {h->d_fifo, n * h->cfg.dead_time_steps * h->fifo_dim * h->rsz};
   if (h->d_obsv) s[k++] = {h->d_obsv, n * 4 * h->rsz};
+  if (h->d_sup) s[k++] = {h->d_sup, n * 2 * h->rsz};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {

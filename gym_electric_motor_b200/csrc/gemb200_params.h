@@ -154,6 +154,9 @@ struct StepParams {
   int32_t sop_idx[kMaxStateOps][4];
   uint32_t sop_mask[kMaxStateOps];
   real sop_param[kMaxStateOps][8];
+  int32_t supply_kind;     // gemb200_supply_kind
+  real sup_k1, sup_k2;     // RC supply: tau / (R C), R
+  real* sup;               // [2][n] RC supply: u_sup, 'has a previous call' flag (0 right after a reset); nullptr for the ideal supply
   real* obsv;              // [4][n] FluxObserver integrator (re, im, compensation terms); nullptr without one
   int32_t pf_dist;         // envs between a thread's env and the one it prefetches into L2 (0: off); ~ one wave of resident threads
   int32_t plain;           // 1: this configuration has the PLAIN shape (see step_kernel) -> specialised instantiation

@@ -77,8 +77,6 @@ class SCMLSystem(PhysicalSystem):
             if not isinstance(obj, base):
                 raise TypeError(f"{what}={type(obj).__name__} is not a built-in {base.__name__} of gym_electric_motor_b200; "
                                 "user-defined Python components cannot run inside the CUDA kernel (INTEGRATION.md)")
-        if not isinstance(supply, IdealVoltageSupply):
-            raise NotImplementedError("only IdealVoltageSupply is on the device path in this round")
         self._converter, self._electrical_motor, self._mechanical_load, self._supply, self._ode_solver = converter, motor, load, supply, ode_solver
         self.num_envs = int(num_envs)
         self._device = _device_index(device)
@@ -253,7 +251,7 @@ class SCMLSystem(PhysicalSystem):
             cfg.converter_kind[i] = slots[i] if i < len(slots) else K.CONV_NONE
         cfg.tau = float(self.tau)
         cfg.interlocking_time = float(self._converter.interlocking_time)
-        cfg.u_sup = float(self._supply.u_nominal)
+        self._supply.fill_config(cfg)
         self._electrical_motor.fill_config(cfg)
         self._mechanical_load.fill_config(cfg)
         self._ode_solver.fill_config(cfg)

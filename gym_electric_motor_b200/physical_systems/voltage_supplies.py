@@ -1,5 +1,9 @@
-"""Voltage-supply descriptors (reference physical_systems/voltage_supplies.py).  Only the ideal supply is on the device
-path in this round (all 54 registered envs use it); RC / AC supplies are listed under "next" in DESIGN.md."""
+"""Voltage-supply descriptors (reference physical_systems/voltage_supplies.py).  On the device path: the ideal supply (all 54
+registered envs use it) and the RC supply (a DC link fed through a resistor, advanced inside the step kernel from the converter's
+supply current).  The AC supplies draw their phase from the unseeded global numpy RNG in the reference and are not available."""
+import warnings
+
+from .. import _cabi as K
 
 
 class VoltageSupply:
@@ -16,6 +20,11 @@ class VoltageSupply:
         return self._u_nominal
 
 
+    def fill_config(self, cfg):
+        cfg.u_sup = float(self._u_nominal)
+        cfg.supply_kind = K.SUPPLY_IDEAL
+
+
 class IdealVoltageSupply(VoltageSupply):
     """reference voltage_supplies.py:60-72"""
 
@@ -24,15 +33,36 @@ class IdealVoltageSupply(VoltageSupply):
         self.supply_range = (u_nominal, u_nominal)
 
 
+class RCVoltageSupply(VoltageSupply):
+    """reference voltage_supplies.py:75-123: ideal source u_0 = u_nominal behind an RC element,
+    d u_sup / dt = (u_0 - u_sup - R i_sup) / (R C), one explicit Euler step per control step."""
+
+    def __init__(self, u_nominal=600.0, supply_parameter=None):
+        super().__init__(u_nominal)
+        supply_parameter = supply_parameter or {"R": 1, "C": 4e-3}
+        assert "R" in supply_parameter.keys(), "Pass key 'R' for Resistance in your dict"
+        assert "C" in supply_parameter.keys(), "Pass key 'C' for Capacitance in your dict"
+        self.supply_range = (0, u_nominal)
+        self._r = supply_parameter["R"]
+        self._c = supply_parameter["C"]
+        if self._r * self._c < 1e-4:
+            warnings.warn("The product of R and C might be too small for the correct calculation of the supply voltage. "
+                          "You might want to consider R*C as a time constant.")
+
+    def fill_config(self, cfg):
+        cfg.u_sup = float(self._u_nominal)
+        cfg.supply_kind = K.SUPPLY_RC
+        cfg.supply_param[0], cfg.supply_param[1] = float(self._r), float(self._c)
+
+
 def _unsupported(name, where):
     class _Unsupported(VoltageSupply):
         def __init__(self, *a, **k):
-            raise NotImplementedError(f"{name} ({where}) is not on the device path yet (SURVEY.md §8f row 3); use IdealVoltageSupply")
+            raise NotImplementedError(f"{name} ({where}) is not on the device path (its phase comes from the unseeded global numpy RNG, voltage_supplies.py:152-166); use IdealVoltageSupply or RCVoltageSupply")
 
     _Unsupported.__name__ = name
     return _Unsupported
 
 
-RCVoltageSupply = _unsupported("RCVoltageSupply", "voltage_supplies.py:75-123")
 AC1PhaseSupply = _unsupported("AC1PhaseSupply", "voltage_supplies.py:126-166")
 AC3PhaseSupply = _unsupported("AC3PhaseSupply", "voltage_supplies.py:169-213")

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 3
+#define GEMB200_ABI_VERSION 4
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -84,6 +84,13 @@ enum gemb200_load_kind {
   GEMB200_LOAD_POLY_STATIC = 1  /* mechanical_loads/polynomial_static_load.py:87-99 */
 };
 enum gemb200_load_param { GEMB200_LP_A = 0, GEMB200_LP_B = 1, GEMB200_LP_C = 2, GEMB200_LP_J_LOAD = 3, GEMB200_LP_TAU_DECAY = 4 };
+
+enum gemb200_supply_kind {
+  GEMB200_SUPPLY_IDEAL = 0, /* voltage_supplies.py:60-72: u_sup = u_nominal */
+  GEMB200_SUPPLY_RC = 1     /* voltage_supplies.py:75-123: DC link behind an RC element, u_sup' = (u_0 - u_sup - R i_sup) / (R C), advanced once
+                               per step with explicit Euler from the supply current of the converter (converters.py i_sup);
+                               supply_param = {R, C} */
+};
 
 enum gemb200_solver_kind {
   GEMB200_SOLVER_EULER = 0, /* physical_systems/solvers.py:79-136 (incl. the n-step time quirk :113-119) */
@@ -212,6 +219,8 @@ typedef struct gemb200_config {
   int32_t sop_idx[GEMB200_MAX_STATE_OPS][4];
   uint32_t sop_mask[GEMB200_MAX_STATE_OPS];
   double sop_param[GEMB200_MAX_STATE_OPS][8];
+  int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */
+  double supply_param[4];
   /* action_dq = 2: SCIM with a FluxObserver — the transformation angle is the observer's psi_angle (+ angle_advance*tau*omega*p),
    * dq_to_abc_action_processor.py:103-105; requires a GEMB200_SOP_FLUX_OBSERVER op */
 } gemb200_config;

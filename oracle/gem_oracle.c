@@ -54,6 +54,7 @@ typedef struct {
   uint32_t ref_start[GEMB200_MAX_REF], ref_len[GEMB200_MAX_REF]; /* periodic generators: sub-episode start step and length */
   double fifo[GEMB200_MAX_DEAD_TIME][GEMB200_MAX_ACT]; /* DeadTimeProcessor queue (ring; slot = call counter mod steps) */
   double psi_re, psi_im; /* FluxObserver._integrated flux_observer.py:46 */
+  double u_rc; int rc_started; /* RCVoltageSupply: solver state and 'a previous get_voltage call exists' (voltage_supplies.py:110-123) */
 } env_t;
 
 typedef struct gem_oracle {
@@ -641,7 +642,7 @@ static void dfim_rotor_current(const gem_oracle* o, const double* y, double* i_r
 static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const int32_t* act_i, double* state) {
   const gemb200_config* c = &o->cfg;
   const int mk = c->motor_kind;
-  const double u_sup = c->u_sup; /* IdealVoltageSupply.get_voltage voltage_supplies.py:70-72 */
+  double u_sup = c->u_sup; /* IdealVoltageSupply.get_voltage voltage_supplies.py:70-72 */
   double* y = e->ode;
   double i_in[6], u_in[6], u_solver[4];
   double t0 = e->t;
@@ -670,7 +671,15 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
         t_32(i_r, i_in + 3); /* alphabeta_to_abc_space(calculate_rotor_current(.)) */
       } break;
     }
-    (void)conv_i_sup(o, e, i_in);             /* :507 */
+    double i_sup = conv_i_sup(o, e, i_in);    /* :507 */
+    if (c->supply_kind == GEMB200_SUPPLY_RC) { /* RCVoltageSupply.get_voltage(self._t, i_sup) :115-123: one Euler step from the previous
+                                                  call's time to this step's start time; a second segment sees dt = 0 */
+      if (seg == 0) {
+        if (e->rc_started) e->u_rc += (c->u_sup - e->u_rc - c->supply_param[0] * i_sup) / (c->supply_param[0] * c->supply_param[1]) * c->tau;
+        e->rc_started = 1;
+      }
+      u_sup = e->u_rc;
+    }
     conv_convert(o, e, i_in, t_solver, u_in); /* :509 */
     for (int j = 0; j < 6; ++j) u_in[j] *= u_sup; /* :510 */
     switch (mk) {
@@ -774,6 +783,7 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
   }
   double u_abc[6] = {0, 0, 0, 0, 0, 0};
   conv_reset(o, e, u_abc);
+  e->u_rc = c->u_sup; e->rc_started = 0; /* supply.reset() -> [u_0] */
   for (int j = 0; j < 6; ++j) u_abc[j] *= c->u_sup;
   e->t = 0; e->k = 0;
   memset(e->fifo, 0, sizeof(e->fifo)); /* DeadTimeProcessor.reset dead_time_processor.py:68-78: queue of zero actions */

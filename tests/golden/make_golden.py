@@ -148,6 +148,7 @@ def describe(env, case):
         omega_fixed=float(getattr(load, "omega_fixed", 0.0) or 0.0),
         supply_class=type(p.supply).__name__,
         u_sup=float(p.supply.u_nominal),
+        supply_parameter=dict(R=float(getattr(p.supply, "_r", 0.0)), C=float(getattr(p.supply, "_c", 0.0))),
         converter_class=type(conv).__name__,
         # a multi converter keeps its own (unused) copy; the sub-converters' value is the one in force
         interlocking_time=float(max([conv._interlocking_time] + [sc._interlocking_time for sc in getattr(conv, "_sub_converters", [])])
@@ -180,6 +181,9 @@ def record(case):
         kwargs["tau"] = case["tau"]
     if case.get("converter_cls") is not None:
         kwargs["converter"] = getattr(ps, case["converter_cls"])(**case.get("converter_args", {}))
+    if case.get("supply_rc") is not None:  # [u_nominal, R, C]
+        u0, r, c = case["supply_rc"]
+        kwargs["supply"] = ps.RCVoltageSupply(u_nominal=u0, supply_parameter=dict(R=r, C=c))
     if case.get("multi") is not None:  # multi converter built from INSTANCES, as the reference's env defaults do
         subs = [getattr(ps, c)(**a) for c, a in case["multi"]]
         kwargs["converter"] = (ps.FiniteMultiConverter if case["env_id"].startswith("Finite") else ps.ContMultiConverter)(subconverters=subs)
@@ -295,6 +299,15 @@ CASES = [
     C("dfim_fin_cc_rk4", "Finite-CC-DFIM-v0", "rk4", steps=2000),
     C("dfim_fin_sc_interlock_rk4", "Finite-SC-DFIM-v0", "rk4", steps=2000,
       multi=[("FiniteB6BridgeConverter", dict(interlocking_time=1e-6)), ("FiniteB6BridgeConverter", dict(interlocking_time=1e-6))]),
+    # RC voltage supply (voltage_supplies.py:75-123) behind every converter family
+    C("permex_sc_rc_rk4", "Cont-SC-PermExDc-v0", "rk4", steps=1500, supply_rc=[60.0, 0.5, 4e-3]),
+    C("permex_fin_sc_rc_interlock_rk4", "Finite-SC-PermExDc-v0", "rk4", steps=2000, supply_rc=[60.0, 0.5, 4e-3], converter=dict(interlocking_time=1e-6)),
+    C("extex_cc_rc_rk4", "Cont-CC-ExtExDc-v0", "rk4", steps=1500, supply_rc=[60.0, 0.2, 2e-3]),
+    C("pmsm_sc_rc_rk4", "Cont-SC-PMSM-v0", "rk4", steps=1500, supply_rc=[420.0, 1.0, 4e-3]),
+    C("pmsm_fin_cc_rc_rk4", "Finite-CC-PMSM-v0", "rk4", steps=2000, supply_rc=[420.0, 1.0, 1e-3]),
+    C("pmsm_cc_rc_interlock_euler3", "Cont-CC-PMSM-v0", "euler3", steps=1500, supply_rc=[300.0, 0.3, 4e-3], converter=dict(interlocking_time=2e-6)),
+    C("eesm_fin_cc_rc_rk4", "Finite-CC-EESM-v0", "rk4", steps=2000, supply_rc=[300.0, 1.0, 2e-3]),
+    C("dfim_cc_rc_rk4", "Cont-CC-DFIM-v0", "rk4", steps=1500, supply_rc=[420.0, 1.0, 4e-3]),
     # remaining DC family
     C("series_cc_rk4", "Cont-CC-SeriesDc-v0", "rk4", steps=1500),
     C("series_sc_dopri5", "Cont-SC-SeriesDc-v0", "dopri5", steps=1500),

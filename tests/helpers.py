@@ -96,6 +96,9 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
     cfg.tau = meta["tau"]
     cfg.interlocking_time = meta["interlocking_time"]
     cfg.u_sup = meta["u_sup"]
+    if meta.get("supply_class") == "RCVoltageSupply":
+        cfg.supply_kind = K.SUPPLY_RC
+        cfg.supply_param[0], cfg.supply_param[1] = meta["supply_parameter"]["R"], meta["supply_parameter"]["C"]
     for k, v in meta["motor_parameter"].items():
         if k in MP_SLOT:
             cfg.motor_param[MP_SLOT[k]] = v

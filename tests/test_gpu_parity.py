@@ -109,6 +109,9 @@ BATCH_CASES = [
     ("synrm_cc_rk4", "rk4x2"), ("eesm_cc_rk4", "rk4"), ("eesm_fin_cc_rk4", "rk4"), ("scim_cc_rk4", "rk4"),
     ("scim_fin_cc_interlock_rk4", "rk4"), ("permex_cc_euler_10k", "euler"), ("permex_fin4qc_interlock_rk4", "rk4"),
     ("series_cc_rk4", "rk4"), ("shunt_cc_rk4", "rk4"), ("extex_cc_rk4", "rk4"),
+    # RC voltage supply behind continuous / finite, single / multi converters
+    ("permex_sc_rc_rk4", "rk4"), ("permex_fin_sc_rc_interlock_rk4", "rk4"), ("pmsm_fin_cc_rc_rk4", "rk4"), ("eesm_fin_cc_rc_rk4", "rk4"),
+    ("pmsm_cc_rc_interlock_euler3", "euler3"), ("dfim_cc_rc_rk4", "rk4"),
     ("dfim_cc_rk4", "rk4"), ("dfim_sc_rk4", "rk4x2"), ("dfim_fin_sc_interlock_rk4", "rk4"), ("dfim_cc_interlock_rk4", "euler3"),
     # state-vector wrappers (CosSinProcessor, FluxObserver, FluxObserver angle for dq actions, dead time in front)
     ("pmsm_cc_cossin_rk4", "rk4"), ("pmsm_sc_cossin_rm_rk4", "rk4"), ("scim_cc_flux_dq_rk4", "rk4"), ("scim_sc_flux_cossin_dead1_rk4", "rk4"),

@@ -83,6 +83,10 @@ def test_config_equals_golden_meta_translation():
         ("permex_cc_rk4", "Cont-CC-PermExDc-v0", {}),
         ("shunt_cc_rk4", "Cont-CC-ShuntDc-v0", {}),
         ("pmsm_sc_polyload_rk4", "Cont-SC-PMSM-v0", dict(load=dict(load_parameter=dict(a=0.5, b=0.02, c=1e-4, j_load=2e-3)))),
+        ("dfim_cc_rk4", "Cont-CC-DFIM-v0", {}),
+        ("dfim_fin_cc_rk4", "Finite-CC-DFIM-v0", {}),
+        ("pmsm_sc_rc_rk4", "Cont-SC-PMSM-v0", dict(supply=gem.physical_systems.RCVoltageSupply(420.0, dict(R=1.0, C=4e-3)))),
+        ("extex_cc_rc_rk4", "Cont-CC-ExtExDc-v0", dict(supply=gem.physical_systems.RCVoltageSupply(60.0, dict(R=0.2, C=2e-3)))),
         ("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", dict(motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
                                                               motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0))))),
     ]:
@@ -91,10 +95,10 @@ def test_config_equals_golden_meta_translation():
         env = gem.make(env_id, ode_solver=gem.physical_systems.RK4Solver(), **kw)
         cfg = env.build_config()
         for f in ("motor_kind", "finite", "load_kind", "solver_kind", "solver_nsteps", "tau", "interlocking_time", "u_sup", "n_ref",
-                  "n_constraints", "reward_bias", "violation_reward"):
+                  "n_constraints", "reward_bias", "violation_reward", "supply_kind"):
             assert getattr(cfg, f) == pytest.approx(getattr(ref, f)), (name, f)
-        for f, n in (("converter_kind", 2), ("motor_param", 16), ("load_param", 5), ("limits", 24), ("init_ode", 8), ("reward_weight", 24),
-                     ("state_length", 24), ("constraint_mask", 4), ("ref_state", 4)):
+        for f, n in (("converter_kind", 2), ("motor_param", 16), ("load_param", 5), ("limits", 28), ("init_ode", 8), ("reward_weight", 28),
+                     ("state_length", 28), ("constraint_mask", 4), ("ref_state", 4), ("supply_param", 2)):
             a, b = list(getattr(cfg, f))[:n], list(getattr(ref, f))[:n]
             assert a == pytest.approx(b, rel=1e-12), (name, f, a, b)
 
@@ -180,7 +184,7 @@ def test_state_vector_wrappers_bookkeeping_matches_reference():
         for k in range(cfg.n_state_ops):
             assert cfg.sop_kind[k] == ref.sop_kind[k] and list(cfg.sop_idx[k]) == list(ref.sop_idx[k])
             assert list(cfg.sop_param[k]) == pytest.approx(list(ref.sop_param[k]), rel=1e-12)
-        for f, n in (("limits", 24), ("reward_weight", 24), ("state_length", 24), ("constraint_mask", 4), ("ref_state", 4)):
+        for f, n in (("limits", 28), ("reward_weight", 28), ("state_length", 28), ("constraint_mask", 4), ("ref_state", 4)):
             assert list(getattr(cfg, f))[:n] == pytest.approx(list(getattr(ref, f))[:n], rel=1e-12), (name, f)
         n_state = K.C.c_int32()
         K.load_library().gemb200_query_dims(K.C.byref(cfg), K.C.byref(n_state), None, None, None)
