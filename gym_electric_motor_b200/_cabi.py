@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
@@ -95,6 +95,9 @@ class GemB200Config(C.Structure):
         ("sop_idx", (C.c_int32 * 4) * MAX_STATE_OPS),
         ("sop_mask", C.c_uint32 * MAX_STATE_OPS),
         ("sop_param", (C.c_double * 8) * MAX_STATE_OPS),
+        ("init_dist", C.c_int32 * MAX_ODE),
+        ("init_mu", C.c_double * MAX_ODE),
+        ("init_sigma", C.c_double * MAX_ODE),
         ("supply_kind", C.c_int32),
         ("supply_param", C.c_double * 4),
     ]

@@ -145,6 +145,9 @@ static int validate(const gemb200_config* c) {
   if (c->init_random && (c->motor_kind == GEMB200_MOTOR_SCIM || c->motor_kind == GEMB200_MOTOR_DFIM))
     return fail(GEMB200_E_INVALID, "random initial states are not supported for the induction motor (the reference draws its flux limits "
                                    "from the unseeded global numpy RNG, squirrel_cage_induction_motor.py:146-157)");
+  for (int j = 0; j < GEMB200_MAX_ODE; ++j)
+    if (c->init_random && c->init_dist[j] && !(c->init_sigma[j] > 0 && c->init_hi[j] > c->init_lo[j]))
+      return fail(GEMB200_E_INVALID, "truncated-normal initial state needs sigma > 0 and a non-empty interval");
   if (c->supply_kind != GEMB200_SUPPLY_IDEAL && c->supply_kind != GEMB200_SUPPLY_RC) return fail(GEMB200_E_INVALID, "bad supply_kind");
   if (c->supply_kind == GEMB200_SUPPLY_RC && !(c->supply_param[0] > 0 && c->supply_param[1] > 0)) return fail(GEMB200_E_INVALID, "RC supply needs R > 0 and C > 0");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
@@ -376,6 +379,18 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     p->inv_lim[eps_idx] = real(1);  // the angle entry is already normalised by eps_out_scale
   }
   p->init_random = c.init_random;
+  {  // truncated-normal states: CDF bounds prepared in double; the angle entry is converted to the stored unit like init_lo
+    const int nst = dm.nx + (dm.has_eps ? 1 : 0);
+    for (int j = 0; j < nst; ++j) {
+      if (!c.init_random || !c.init_dist[j]) continue;
+      const double unit = (j == dm.nx && sizeof(real) == 4) ? 1.0 / (2 * M_PI) : 1.0;
+      const double mu = c.init_mu[j], sg = c.init_sigma[j];
+      const double ca = 0.5 * std::erfc(-(c.init_lo[j] - mu) / sg * M_SQRT1_2), cb = 0.5 * std::erfc(-(c.init_hi[j] - mu) / sg * M_SQRT1_2);
+      p->init_gauss = 1; p->init_dist[j] = 1;
+      p->init_mu[j] = (real)(mu * unit); p->init_sigma[j] = (real)(sg * unit);
+      p->init_ca[j] = (real)ca; p->init_cspan[j] = (real)(cb - ca);
+    }
+  }
   for (int j = 0; j < dm.nx; ++j) { p->init_lo[j] = (real)c.init_lo[j]; p->init_span[j] = (real)(c.init_hi[j] - c.init_lo[j]); }
   if (dm.has_eps) {
     const double unit = sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0;

@@ -115,6 +115,9 @@ struct StepParams {
   real reset_obs[kMaxState];  // observation right after a reset (constant initial state)
   int32_t init_random;        // 1: uniform initial state per reset (init_lo + init_span * U); the angle entry [NX] is in the stored unit
   real init_lo[kMaxX + 1], init_span[kMaxX + 1];
+  // truncated-normal initial states: x = mu + sigma * Phi^-1(ca + U * cspan), ca = Phi((lo - mu) / sigma); init_gauss = any such state
+  int32_t init_gauss, init_dist[kMaxX + 1];
+  real init_mu[kMaxX + 1], init_sigma[kMaxX + 1], init_ca[kMaxX + 1], init_cspan[kMaxX + 1];
   // ---- constraint monitor: merge = max, so all LimitConstraints collapse into ONE list of observed states; every
   //      SquaredConstraint keeps its own list ----
   int32_t n_lim;

@@ -37,9 +37,8 @@ class ElectricMotor:
         self._limits = update_parameter_dict(self._default_limits, limit_values or {})
         self._nominal_values = update_parameter_dict(self._default_nominal_values, nominal_values or {})
         self._initializer = update_parameter_dict(self._default_initializer, motor_initializer or {})
-        if self._initializer.get("random_init") not in (None, "uniform"):
-            raise NotImplementedError("only random_init=None / 'uniform' are on the device path (the truncated-normal initialiser of "
-                                      "electric_motor.py:245-258 is host code built on scipy.stats.truncnorm)")
+        if self._initializer.get("random_init") not in (None, "uniform", "normal", "gaussian"):
+            raise NotImplementedError(f"random_init={self._initializer.get('random_init')!r} (electric_motor.py:233-262 knows uniform / normal / gaussian)")
         self._initial_states = dict(self._default_initializer["states"])
         if self._initializer["states"]:
             unknown = set(self._initializer["states"]) - set(self._initial_states)
@@ -75,7 +74,20 @@ class ElectricMotor:
 
     @property
     def random_init(self):
-        return self._initializer.get("random_init") == "uniform"
+        return self._initializer.get("random_init") in ("uniform", "normal", "gaussian")
+
+    @property
+    def gaussian_init(self):
+        return self._initializer.get("random_init") in ("normal", "gaussian")
+
+    def gaussian_params(self, lower, upper):
+        """(mue, sigma) per initial state of the truncated normal (electric_motor.py:245-248): a given scalar, else the middle of
+        the interval / 1."""
+        rp = self._initializer.get("random_params") or (None, None)
+        lower, upper = np.asarray(lower, dtype=float), np.asarray(upper, dtype=float)
+        mue = np.broadcast_to(rp[0] or (upper - lower) / 2 + lower, lower.shape).astype(float)
+        sigma = np.broadcast_to(rp[1] or 1, lower.shape).astype(float)
+        return mue, sigma
 
     def initial_bounds(self, state_low, state_positions):
         """(lower, upper) per initial state in the initializer's key order (electric_motor.py:214-232): upper = the motor's

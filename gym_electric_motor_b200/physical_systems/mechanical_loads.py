@@ -24,8 +24,8 @@ class MechanicalLoad:
         if "states" in li:
             li["states"] = dict(li["states"])
         self._initializer.update(li)
-        if self._initializer.get("random_init") not in (None, "uniform"):
-            raise NotImplementedError("only random_init=None / 'uniform' are on the device path (mechanical_load.py:138-150 uses scipy truncnorm)")
+        if self._initializer.get("random_init") not in (None, "uniform", "normal", "gaussian"):
+            raise NotImplementedError(f"random_init={self._initializer.get('random_init')!r} (mechanical_load.py:131-152 knows uniform / normal / gaussian)")
         self._initial_states = self._initializer.get("states", {s: 0.0 for s in self._state_names})
 
     @property
@@ -59,7 +59,16 @@ class MechanicalLoad:
 
     @property
     def random_init(self):
-        return self._initializer.get("random_init") == "uniform"
+        return self._initializer.get("random_init") in ("uniform", "normal", "gaussian")
+
+    @property
+    def gaussian_init(self):
+        return self._initializer.get("random_init") in ("normal", "gaussian")
+
+    def gaussian_params(self, lower, upper):
+        """(mue, sigma) of the truncated normal (mechanical_load.py:138-141)"""
+        rp = self._initializer.get("random_params") or (None, None)
+        return float(rp[0] or (upper - lower) / 2 + lower), float(rp[1] or 1)
 
     def initial_bounds(self, nominal_state, state_low, state_positions):
         """(lower, upper) of the initial omega (mechanical_load.py:118-128)."""

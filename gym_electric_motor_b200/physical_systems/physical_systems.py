@@ -272,6 +272,16 @@ class SCMLSystem(PhysicalSystem):
                 lo[1:], hi[1:] = mlo, mhi  # initializer key order == reference's assignment order (see initial_ode_state)
             for i in range(len(init)):
                 cfg.init_lo[i], cfg.init_hi[i] = float(lo[i]), float(hi[i])
+            # truncated normal (random_init='normal' / 'gaussian'): per-state mue / sigma; degenerate intervals stay constant
+            if ld.random_init and ld.gaussian_init and hi[0] > lo[0]:
+                cfg.init_dist[0] = 1
+                cfg.init_mu[0], cfg.init_sigma[0] = ld.gaussian_params(lo[0], hi[0])
+            if m.random_init and m.gaussian_init:
+                mu, sg = m.gaussian_params(lo[1:], hi[1:])
+                for j in range(len(mu)):
+                    if hi[1 + j] > lo[1 + j]:
+                        cfg.init_dist[1 + j] = 1
+                        cfg.init_mu[1 + j], cfg.init_sigma[1 + j] = float(mu[j]), float(sg[j])
         cfg.action_dq = int(self._action_dq)
         cfg.angle_advance = float(self._angle_advance)
         cfg.dead_time_steps = int(self._dead_steps)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 4
+#define GEMB200_ABI_VERSION 5
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -219,6 +219,10 @@ typedef struct gemb200_config {
   int32_t sop_idx[GEMB200_MAX_STATE_OPS][4];
   uint32_t sop_mask[GEMB200_MAX_STATE_OPS];
   double sop_param[GEMB200_MAX_STATE_OPS][8];
+  /* random_init = 'normal' / 'gaussian' (electric_motor.py:245-258, mechanical_load.py:138-150): truncated normal on [init_lo, init_hi]
+   * per state; init_dist[j] = 0 uniform (lo == hi: constant), 1 truncated normal with init_mu[j], init_sigma[j]; needs init_random = 1 */
+  int32_t init_dist[GEMB200_MAX_ODE];
+  double init_mu[GEMB200_MAX_ODE], init_sigma[GEMB200_MAX_ODE];
   int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */
   double supply_param[4];
   /* action_dq = 2: SCIM with a FluxObserver — the transformation angle is the observer's psi_angle (+ angle_advance*tau*omega*p),

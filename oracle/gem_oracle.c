@@ -628,6 +628,36 @@ static double wrap_eps(double eps) { /* physical_systems.py:520-522: python floa
   return r;
 }
 
+/* standard normal CDF and its inverse (Wichura's AS 241, PPND16: relative accuracy 1e-16) for the truncated-normal initialiser */
+static double norm_cdf(double x) { return 0.5 * erfc(-x * M_SQRT1_2); }
+static double norm_ppf(double p) {
+  static const double a[8] = {3.3871328727963666080e0, 1.3314166789178437745e+2, 1.9715909503065514427e+3, 1.3731693765509461125e+4,
+                              4.5921953931549871457e+4, 6.7265770927008700853e+4, 3.3430575583588128105e+4, 2.5090809287301226727e+3};
+  static const double b[8] = {1.0, 4.2313330701600911252e+1, 6.8718700749205790830e+2, 5.3941960214247511077e+3, 2.1213794301586595867e+4,
+                              3.9307895800092710610e+4, 2.8729085735721942674e+4, 5.2264952788528545610e+3};
+  static const double cc[8] = {1.42343711074968357734e0, 4.63033784615654529590e0, 5.76949722146069140550e0, 3.64784832476320460504e0,
+                               1.27045825245236838258e0, 2.41780725177450611770e-1, 2.27238449892691845833e-2, 7.74545014278341407640e-4};
+  static const double d[8] = {1.0, 2.05319162663775882187e0, 1.67638483018380384940e0, 6.89767334985100004550e-1, 1.48103976427480074590e-1,
+                              1.51986665636164571966e-2, 5.47593808499534494600e-4, 1.05075007164441684324e-9};
+  static const double e[8] = {6.65790464350110377720e0, 5.46378491116411436990e0, 1.78482653991729133580e0, 2.96560571828504891230e-1,
+                              2.65321895265761230930e-2, 1.24266094738807843860e-3, 2.71155556874348757815e-5, 2.01033439929228813265e-7};
+  static const double f[8] = {1.0, 5.99832206555887937690e-1, 1.36929880922735805310e-1, 1.48753612908506148525e-2, 7.86869131145613259100e-4,
+                              1.84631831751005468180e-5, 1.42151175831644588870e-7, 2.04426310338993978564e-15};
+  const double q = p - 0.5;
+  double r, num = 0, den = 0;
+  if (fabs(q) <= 0.425) {
+    r = 0.180625 - q * q;
+    for (int i = 7; i >= 0; --i) { num = num * r + a[i]; den = den * r + b[i]; }
+    return q * num / den;
+  }
+  r = q < 0 ? p : 1 - p;
+  if (r <= 0) return q < 0 ? -INFINITY : INFINITY;
+  r = sqrt(-log(r));
+  if (r <= 5) { r -= 1.6; for (int i = 7; i >= 0; --i) { num = num * r + cc[i]; den = den * r + d[i]; } }
+  else { r -= 5; for (int i = 7; i >= 0; --i) { num = num * r + e[i]; den = den * r + f[i]; } }
+  return q < 0 ? -num / den : num / den;
+}
+
 /* DoublyFedInductionMotorSystem.calculate_rotor_current physical_systems.py:946-956; y = [omega, i_sa, i_sb, psi_ra, psi_rb, eps] */
 static void dfim_rotor_current(const gem_oracle* o, const double* y, double* i_r) {
   const double* mp = o->cfg.motor_param;
@@ -779,7 +809,16 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
     int64_t idx = e - o->env;
     rng4(o, idx, STREAM_INIT_STATE, r0);
     rng4(o, idx, STREAM_INIT_STATE2, r1);
-    for (int j = 0; j < o->n_ode; ++j) y[j] = c->init_lo[j] + (c->init_hi[j] - c->init_lo[j]) * u01(j < 4 ? r0[j] : r1[j - 4]);
+    for (int j = 0; j < o->n_ode; ++j) {
+      const double u = u01(j < 4 ? r0[j] : r1[j - 4]);
+      y[j] = c->init_lo[j] + (c->init_hi[j] - c->init_lo[j]) * u;
+      if (c->init_dist[j]) { /* random_init='gaussian': scipy.stats.truncnorm(a, b, loc=mue, scale=sigma) electric_motor.py:245-258, by inversion */
+        const double mu = c->init_mu[j], sg = c->init_sigma[j];
+        const double ca = norm_cdf((c->init_lo[j] - mu) / sg), cb = norm_cdf((c->init_hi[j] - mu) / sg);
+        const double g = mu + sg * norm_ppf(ca + u * (cb - ca));
+        y[j] = fmin(fmax(g, c->init_lo[j]), c->init_hi[j]);
+      }
+    }
   }
   double u_abc[6] = {0, 0, 0, 0, 0, 0};
   conv_reset(o, e, u_abc);

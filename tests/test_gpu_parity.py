@@ -440,10 +440,11 @@ def test_mixed_motor_batch(torch_cuda, oracle_lib):
 
 
 @pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("dist", ["uniform", "gaussian"])
 @pytest.mark.parametrize("name", ["pmsm_sc_rk4", "eesm_cc_rk4", "extex_cc_rk4", "permex_cc_rk4"])
-def test_random_initial_states_match_oracle(torch_cuda, oracle_lib, name, dtype):
-    """random_init='uniform' on the device: same Philox draws as the oracle at reset and at every in-kernel auto-reset;
-    the reset observation is computed from the sampled state."""
+def test_random_initial_states_match_oracle(torch_cuda, oracle_lib, name, dist, dtype):
+    """random_init='uniform' / 'gaussian' (truncated normal) on the device: same Philox draws as the oracle at reset and at every
+    in-kernel auto-reset; the reset observation is computed from the sampled state."""
     g = load_golden(name)
     n, steps = 777, 60
     init = np.array(g["reset_ode"], dtype=float)
@@ -459,6 +460,8 @@ def test_random_initial_states_match_oracle(torch_cuda, oracle_lib, name, dtype)
         cfg.init_random = 1
         for j in range(n_ode):
             cfg.init_lo[j], cfg.init_hi[j] = -span[j], span[j]
+            if dist == "gaussian":  # off-centre mean, sigma comparable to the interval: both truncation tails matter
+                cfg.init_dist[j], cfg.init_mu[j], cfg.init_sigma[j] = 1, 0.3 * span[j], 0.8 * span[j]
         return cfg
 
     dev = DeviceAdapter(mk(dtype))

@@ -221,8 +221,23 @@ def test_random_initialiser_bounds_match_reference():
         assert np.all(np.abs(mean - 0.5 * (lo + hi)) < 0.03 * span)
     with pytest.raises(NotImplementedError):
         gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(random_init="uniform")))
+
+
+def test_gaussian_initialiser_config():
+    """random_init='gaussian': mue defaults to the middle of [lower, upper], sigma to 1 (electric_motor.py:246-247); given scalars are
+    used for every state; the bounds are those of the uniform case."""
+    env = gem.make("Cont-SC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="gaussian")),
+                   load=dict(load_initializer=dict(random_init="normal", random_params=(20.0, 15.0), interval=[[-50.0, 120.0]])))
+    cfg = env.build_config()
+    ref = gem.make("Cont-SC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="uniform")),
+                   load=dict(load_initializer=dict(random_init="uniform", interval=[[-50.0, 120.0]]))).build_config()
+    assert cfg.init_random == 1 and list(cfg.init_lo)[:4] == list(ref.init_lo)[:4] and list(cfg.init_hi)[:4] == list(ref.init_hi)[:4]
+    assert list(cfg.init_dist)[:4] == [1, 1, 1, 1] and list(ref.init_dist)[:4] == [0, 0, 0, 0]
+    assert (cfg.init_mu[0], cfg.init_sigma[0]) == (20.0, 15.0)
+    for j in (1, 2, 3):
+        assert cfg.init_mu[j] == pytest.approx(0.5 * (cfg.init_lo[j] + cfg.init_hi[j])) and cfg.init_sigma[j] == 1.0
     with pytest.raises(NotImplementedError):
-        gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="gaussian")))
+        gem.make("Cont-SC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="cauchy")))
 
 
 def test_vector_facade_spaces():
