@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
@@ -25,7 +25,7 @@ LAYOUT_AOS, LAYOUT_SOA = 0, 1
 AUTORESET_NONE, AUTORESET_SAME_STEP = 0, 1
 SOP_NONE, SOP_COS_SIN, SOP_FLUX_OBSERVER, SOP_NOISE = range(4)
 NOISE_NORMAL, NOISE_UNIFORM, NOISE_LAPLACE = range(3)
-SUPPLY_IDEAL, SUPPLY_RC = 0, 1
+SUPPLY_IDEAL, SUPPLY_RC, SUPPLY_AC1 = 0, 1, 2
 
 E_INVALID, E_CUDA, E_NOMEM, E_ABI = -1, -2, -3, -4
 

@@ -41,6 +41,7 @@ struct gemb200_handle {
   void* d_fifo = nullptr;
   int fifo_dim = 0;
   void* d_sup = nullptr;   // RC supply state [2][n]
+  double* d_supph = nullptr;  // AC supply phase [n]
   void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
   int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
@@ -148,7 +149,8 @@ static int validate(const gemb200_config* c) {
   for (int j = 0; j < GEMB200_MAX_ODE; ++j)
     if (c->init_random && c->init_dist[j] && !(c->init_sigma[j] > 0 && c->init_hi[j] > c->init_lo[j]))
       return fail(GEMB200_E_INVALID, "truncated-normal initial state needs sigma > 0 and a non-empty interval");
-  if (c->supply_kind != GEMB200_SUPPLY_IDEAL && c->supply_kind != GEMB200_SUPPLY_RC) return fail(GEMB200_E_INVALID, "bad supply_kind");
+  if (c->supply_kind < GEMB200_SUPPLY_IDEAL || c->supply_kind > GEMB200_SUPPLY_AC1) return fail(GEMB200_E_INVALID, "bad supply_kind");
+  if (c->supply_kind == GEMB200_SUPPLY_AC1 && !(c->supply_param[0] > 0)) return fail(GEMB200_E_INVALID, "AC supply needs a positive frequency");
   if (c->supply_kind == GEMB200_SUPPLY_RC && !(c->supply_param[0] > 0 && c->supply_param[1] > 0)) return fail(GEMB200_E_INVALID, "RC supply needs R > 0 and C > 0");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
   Dims d;
@@ -184,6 +186,7 @@ struct Derived {
   double c[20] = {0};
   double tq[4] = {0};
   double reset_obs[GEMB200_MAX_STATE] = {0};
+  double reset_obs_du[GEMB200_MAX_STATE] = {0};  // d reset_obs / d u_sup (the voltage entries are linear in u_sup)
   double inv_j = 0, omega_lim = 0, omega_lin = 0;
 };
 
@@ -453,6 +456,19 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->sup = static_cast<real*>(h->d_sup);
   p->sup_k1 = c.supply_kind == GEMB200_SUPPLY_RC ? (real)(c.tau / (c.supply_param[0] * c.supply_param[1])) : real(0);
   p->sup_k2 = (real)c.supply_param[0];
+  p->sup_phase = h->d_supph;
+  if (c.supply_kind == GEMB200_SUPPLY_AC1) {
+    const double unit = sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0;  // fp32 build: turns as double-float
+    const double kph = 2 * M_PI * c.supply_param[0] * c.tau * unit;
+    double ph0 = c.supply_param[1];
+    ph0 = ph0 - 2 * M_PI * std::rint(ph0 / (2 * M_PI));
+    ph0 *= unit;
+    p->sup_amp = (real)(std::sqrt(2.0) * c.u_sup);
+    p->sup_kph[0] = (real)kph; p->sup_kph[1] = sizeof(real) == 4 ? (real)(kph - (double)p->sup_kph[0]) : real(0);
+    p->sup_ph0[0] = (real)ph0; p->sup_ph0[1] = sizeof(real) == 4 ? (real)(ph0 - (double)p->sup_ph0[0]) : real(0);
+    p->sup_fixed = c.supply_param[2] != 0.0;
+  }
+  for (int j = 0; j < dm.n_state; ++j) p->reset_obs_du[j] = (real)dv.reset_obs_du[j];
   p->n_sops = c.n_state_ops;
   p->n_obs = dm.n_obs;
   p->row_stride = h->row_stride;
@@ -644,10 +660,18 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   if (d.has_eps) ALLOC(h->d_eps, n * sizeof(double));
   if (h->two_segment || (cfg->finite && cfg->supply_kind == GEMB200_SUPPLY_RC)) ALLOC(h->d_sw, n * sizeof(uint16_t));
   if (cfg->supply_kind == GEMB200_SUPPLY_RC) ALLOC(h->d_sup, n * 2 * h->rsz);
+  if (cfg->supply_kind == GEMB200_SUPPLY_AC1) ALLOC(h->d_supph, n * sizeof(double));
   if (d.has_observer) ALLOC(h->d_obsv, n * 4 * h->rsz);
 #undef ALLOC
   Derived dv;
   derive_model(cfg, d, &dv);
+  {  // same derivation one volt higher: the difference is the u_sup-proportional part of the reset observation
+    gemb200_config c1 = *cfg;
+    c1.u_sup += 1.0;
+    Derived dv1;
+    derive_model(&c1, d, &dv1);
+    for (int j = 0; j < d.n_state; ++j) dv.reset_obs_du[j] = dv1.reset_obs[j] - dv.reset_obs[j];
+  }
   fill_params<float>(h, d, dv, &h->pf);
   fill_params<double>(h, d, dv, &h->pd);
   cudaEventCreate(&h->ev0);
@@ -663,7 +687,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -834,6 +858,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_fifo) s[k++] = {h->d_fifo, n * h->cfg.dead_time_steps * h->fifo_dim * h->rsz};
   if (h->d_obsv) s[k++] = {h->d_obsv, n * 4 * h->rsz};
   if (h->d_sup) s[k++] = {h->d_sup, n * 2 * h->rsz};
+  if (h->d_supph) s[k++] = {h->d_supph, n * sizeof(double)};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {

@@ -48,6 +48,7 @@ enum : uint32_t {
   kStreamWalk = 1, kStreamSubep = 2, kStreamInit = 3, kStreamSubepHi = 18,
   kStreamWalkR = 5, kStreamSubepR = 6, kStreamSubepHiR = 22,  // "R": draws made right after an in-kernel auto-reset
   kStreamInitState = 7, kStreamInitState2 = 8,                // random initial ODE state
+  kStreamSupply = 9,                                          // AC supply phase at reset
   kStreamPeriodic = 32,                                       // + 2*slot (+1): sub-episode parameters of the periodic generators,
                                                               //   counter word 0 = step index of the sub-episode start
   kStreamNoise = 64,                                          // + 8*op + (state index >> 2): StateNoiseProcessor draws
@@ -159,6 +160,12 @@ struct StepParams {
   real sop_param[kMaxStateOps][8];
   int32_t supply_kind;     // gemb200_supply_kind
   real sup_k1, sup_k2;     // RC supply: tau / (R C), R
+  // AC supply: phase kept like the electrical angle (Ang<real>: turns as double-float in fp32, radians in a double), advanced by
+  // f * tau per step; amplitude sqrt(2) * u_nominal; sup_ph0 = fixed phase in the stored unit, sup_fixed = 0: random per reset
+  real sup_amp, sup_kph[2], sup_ph0[2];
+  int32_t sup_fixed;
+  double* sup_phase;       // [n]; nullptr unless AC supply
+  real reset_obs_du[kMaxState];  // d reset_obs / d u_sup (supplies whose voltage at reset differs per env)
   real* sup;               // [2][n] RC supply: u_sup, 'has a previous call' flag (0 right after a reset); nullptr for the ideal supply
   real* obsv;              // [4][n] FluxObserver integrator (re, im, compensation terms); nullptr without one
   int32_t pf_dist;         // envs between a thread's env and the one it prefetches into L2 (0: off); ~ one wave of resident threads

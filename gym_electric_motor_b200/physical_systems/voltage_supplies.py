@@ -1,7 +1,10 @@
 """Voltage-supply descriptors (reference physical_systems/voltage_supplies.py).  On the device path: the ideal supply (all 54
 registered envs use it) and the RC supply (a DC link fed through a resistor, advanced inside the step kernel from the converter's
-supply current).  The AC supplies draw their phase from the unseeded global numpy RNG in the reference and are not available."""
+supply current).  and the single-phase AC supply (phase per env from the Philox stream unless fixed).  The three-phase AC supply
+changes the shape of the state vector (three u_sup entries) and is not available."""
 import warnings
+
+import numpy as np
 
 from .. import _cabi as K
 
@@ -55,14 +58,42 @@ class RCVoltageSupply(VoltageSupply):
         cfg.supply_param[0], cfg.supply_param[1] = float(self._r), float(self._c)
 
 
+class AC1PhaseSupply(VoltageSupply):
+    """reference voltage_supplies.py:126-166: u_sup(t) = sqrt(2) u_nominal sin(2 pi f t + phi).  Without a 'phase' entry the phase is
+    drawn per env at every reset — from the device's Philox stream here, from the unseeded global numpy RNG in the reference."""
+
+    def __init__(self, u_nominal=230, supply_parameter=None):
+        super().__init__(u_nominal)
+        self._fixed_phi = False
+        if supply_parameter is not None:
+            assert isinstance(supply_parameter, dict), "supply_parameter should be a dict"
+            assert "frequency" in supply_parameter.keys(), "Pass key 'frequency' for frequency f in Hz in your dict"
+            supply_parameter = dict(supply_parameter)
+            if "phase" in supply_parameter.keys():
+                assert 0 <= supply_parameter["phase"] < 2 * np.pi, "The phase angle has to be given in rad in range [0,2*pi)"
+                self._fixed_phi = True
+            else:
+                supply_parameter["phase"] = 0.0
+        else:
+            supply_parameter = {"frequency": 50, "phase": 0.0}
+        self._f = supply_parameter["frequency"]
+        self._phi = supply_parameter["phase"]
+        self._max_amp = self._u_nominal * np.sqrt(2)
+        self.supply_range = [-1 * self._max_amp, self._max_amp]
+
+    def fill_config(self, cfg):
+        cfg.u_sup = float(self._u_nominal)
+        cfg.supply_kind = K.SUPPLY_AC1
+        cfg.supply_param[0], cfg.supply_param[1], cfg.supply_param[2] = float(self._f), float(self._phi), float(self._fixed_phi)
+
+
 def _unsupported(name, where):
     class _Unsupported(VoltageSupply):
         def __init__(self, *a, **k):
-            raise NotImplementedError(f"{name} ({where}) is not on the device path (its phase comes from the unseeded global numpy RNG, voltage_supplies.py:152-166); use IdealVoltageSupply or RCVoltageSupply")
+            raise NotImplementedError(f"{name} ({where}) is not on the device path (voltage_len = 3 changes the state vector and the voltage product of physical_systems.py:184, which no registered env or reference test exercises)")
 
     _Unsupported.__name__ = name
     return _Unsupported
 
 
-AC1PhaseSupply = _unsupported("AC1PhaseSupply", "voltage_supplies.py:126-166")
 AC3PhaseSupply = _unsupported("AC3PhaseSupply", "voltage_supplies.py:169-213")

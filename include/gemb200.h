@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 5
+#define GEMB200_ABI_VERSION 6
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -87,9 +87,12 @@ enum gemb200_load_param { GEMB200_LP_A = 0, GEMB200_LP_B = 1, GEMB200_LP_C = 2, 
 
 enum gemb200_supply_kind {
   GEMB200_SUPPLY_IDEAL = 0, /* voltage_supplies.py:60-72: u_sup = u_nominal */
-  GEMB200_SUPPLY_RC = 1     /* voltage_supplies.py:75-123: DC link behind an RC element, u_sup' = (u_0 - u_sup - R i_sup) / (R C), advanced once
+  GEMB200_SUPPLY_RC = 1,    /* voltage_supplies.py:75-123: DC link behind an RC element, u_sup' = (u_0 - u_sup - R i_sup) / (R C), advanced once
                                per step with explicit Euler from the supply current of the converter (converters.py i_sup);
                                supply_param = {R, C} */
+  GEMB200_SUPPLY_AC1 = 2    /* voltage_supplies.py:126-166: u_sup(t) = sqrt(2) u_nominal sin(2 pi f t + phi), t = time since the reset;
+                               supply_param = {f [Hz], phi [rad], fixed}: fixed = 0 draws phi ~ U[0, 2 pi) per env at every reset (the
+                               reference uses the unseeded global numpy RNG here, the device its Philox stream) */
 };
 
 enum gemb200_solver_kind {

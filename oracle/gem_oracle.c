@@ -54,6 +54,7 @@ typedef struct {
   uint32_t ref_start[GEMB200_MAX_REF], ref_len[GEMB200_MAX_REF]; /* periodic generators: sub-episode start step and length */
   double fifo[GEMB200_MAX_DEAD_TIME][GEMB200_MAX_ACT]; /* DeadTimeProcessor queue (ring; slot = call counter mod steps) */
   double psi_re, psi_im; /* FluxObserver._integrated flux_observer.py:46 */
+  double ac_phase; /* AC1PhaseSupply._phi */
   double u_rc; int rc_started; /* RCVoltageSupply: solver state and 'a previous get_voltage call exists' (voltage_supplies.py:110-123) */
 } env_t;
 
@@ -104,7 +105,7 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
  * call of a handle gets a fresh call id, so no per-env RNG state exists.  Stream ids: */
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
-       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */,
+       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */,
        STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */,
        STREAM_NOISE = 64 /* + 8*op + (state >> 2): StateNoiseProcessor */, STREAM_NOISE_R = 128 /* ... right after an auto-reset */ };
 
@@ -702,6 +703,8 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
       } break;
     }
     double i_sup = conv_i_sup(o, e, i_in);    /* :507 */
+    if (c->supply_kind == GEMB200_SUPPLY_AC1) /* AC1PhaseSupply.get_voltage(self._t) :163-166: the step's START time for all segments */
+      u_sup = sqrt(2.0) * c->u_sup * sin(2 * M_PI * c->supply_param[0] * t0 + e->ac_phase);
     if (c->supply_kind == GEMB200_SUPPLY_RC) { /* RCVoltageSupply.get_voltage(self._t, i_sup) :115-123: one Euler step from the previous
                                                   call's time to this step's start time; a second segment sees dt = 0 */
       if (seg == 0) {
@@ -823,7 +826,13 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
   double u_abc[6] = {0, 0, 0, 0, 0, 0};
   conv_reset(o, e, u_abc);
   e->u_rc = c->u_sup; e->rc_started = 0; /* supply.reset() -> [u_0] */
-  for (int j = 0; j < 6; ++j) u_abc[j] *= c->u_sup;
+  double u_sup0 = c->u_sup;
+  if (c->supply_kind == GEMB200_SUPPLY_AC1) { /* AC1PhaseSupply.reset :157-161 */
+    e->ac_phase = c->supply_param[1];
+    if (c->supply_param[2] == 0.0) { uint32_t r[4]; rng4(o, e - o->env, STREAM_SUPPLY, r); e->ac_phase = u01(r[0]) * 2 * M_PI; }
+    u_sup0 = sqrt(2.0) * c->u_sup * sin(e->ac_phase);
+  }
+  for (int j = 0; j < 6; ++j) u_abc[j] *= u_sup0;
   e->t = 0; e->k = 0;
   memset(e->fifo, 0, sizeof(e->fifo)); /* DeadTimeProcessor.reset dead_time_processor.py:68-78: queue of zero actions */
   double tq = torque(o, y + 1);
@@ -892,7 +901,7 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
       state[n++] = eps;
     } break;
   }
-  state[n++] = c->u_sup;
+  state[n++] = u_sup0;
   for (int j = 0; j < n; ++j) state[j] = state[j] / c->limits[j];
   if (mk == GEMB200_MOTOR_SHUNT_DC) state[n] = state[2] + state[3]; /* current_sum_processor.py:47-50 */
 }

@@ -148,7 +148,8 @@ def describe(env, case):
         omega_fixed=float(getattr(load, "omega_fixed", 0.0) or 0.0),
         supply_class=type(p.supply).__name__,
         u_sup=float(p.supply.u_nominal),
-        supply_parameter=dict(R=float(getattr(p.supply, "_r", 0.0)), C=float(getattr(p.supply, "_c", 0.0))),
+        supply_parameter=dict(R=float(getattr(p.supply, "_r", 0.0)), C=float(getattr(p.supply, "_c", 0.0)), f=float(getattr(p.supply, "_f", 0.0)),
+                              phase=float(getattr(p.supply, "_phi", 0.0))),
         converter_class=type(conv).__name__,
         # a multi converter keeps its own (unused) copy; the sub-converters' value is the one in force
         interlocking_time=float(max([conv._interlocking_time] + [sc._interlocking_time for sc in getattr(conv, "_sub_converters", [])])
@@ -184,6 +185,9 @@ def record(case):
     if case.get("supply_rc") is not None:  # [u_nominal, R, C]
         u0, r, c = case["supply_rc"]
         kwargs["supply"] = ps.RCVoltageSupply(u_nominal=u0, supply_parameter=dict(R=r, C=c))
+    if case.get("supply_ac") is not None:  # [u_nominal, f, phase]
+        u0, f, ph = case["supply_ac"]
+        kwargs["supply"] = ps.AC1PhaseSupply(u_nominal=u0, supply_parameter=dict(frequency=f, phase=ph))
     if case.get("multi") is not None:  # multi converter built from INSTANCES, as the reference's env defaults do
         subs = [getattr(ps, c)(**a) for c, a in case["multi"]]
         kwargs["converter"] = (ps.FiniteMultiConverter if case["env_id"].startswith("Finite") else ps.ContMultiConverter)(subconverters=subs)
@@ -308,6 +312,10 @@ CASES = [
     C("pmsm_cc_rc_interlock_euler3", "Cont-CC-PMSM-v0", "euler3", steps=1500, supply_rc=[300.0, 0.3, 4e-3], converter=dict(interlocking_time=2e-6)),
     C("eesm_fin_cc_rc_rk4", "Finite-CC-EESM-v0", "rk4", steps=2000, supply_rc=[300.0, 1.0, 2e-3]),
     C("dfim_cc_rc_rk4", "Cont-CC-DFIM-v0", "rk4", steps=1500, supply_rc=[420.0, 1.0, 4e-3]),
+    # single-phase AC supply with a fixed phase (voltage_supplies.py:126-166)
+    C("permex_sc_ac_rk4", "Cont-SC-PermExDc-v0", "rk4", steps=1500, supply_ac=[42.0, 50.0, 0.7]),
+    C("series_fin_cc_ac_interlock_rk4", "Finite-CC-SeriesDc-v0", "rk4", steps=2000, supply_ac=[230.0, 400.0, 2.5], converter=dict(interlocking_time=1e-6)),
+    C("pmsm_cc_ac_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500, supply_ac=[230.0, 50.0, 4.0]),
     # remaining DC family
     C("series_cc_rk4", "Cont-CC-SeriesDc-v0", "rk4", steps=1500),
     C("series_sc_dopri5", "Cont-SC-SeriesDc-v0", "dopri5", steps=1500),

@@ -96,6 +96,9 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
     cfg.tau = meta["tau"]
     cfg.interlocking_time = meta["interlocking_time"]
     cfg.u_sup = meta["u_sup"]
+    if meta.get("supply_class") == "AC1PhaseSupply":
+        cfg.supply_kind = K.SUPPLY_AC1
+        cfg.supply_param[0], cfg.supply_param[1], cfg.supply_param[2] = meta["supply_parameter"]["f"], meta["supply_parameter"]["phase"], 1.0
     if meta.get("supply_class") == "RCVoltageSupply":
         cfg.supply_kind = K.SUPPLY_RC
         cfg.supply_param[0], cfg.supply_param[1] = meta["supply_parameter"]["R"], meta["supply_parameter"]["C"]

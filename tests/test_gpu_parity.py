@@ -112,6 +112,8 @@ BATCH_CASES = [
     # RC voltage supply behind continuous / finite, single / multi converters
     ("permex_sc_rc_rk4", "rk4"), ("permex_fin_sc_rc_interlock_rk4", "rk4"), ("pmsm_fin_cc_rc_rk4", "rk4"), ("eesm_fin_cc_rc_rk4", "rk4"),
     ("pmsm_cc_rc_interlock_euler3", "euler3"), ("dfim_cc_rc_rk4", "rk4"),
+    # single-phase AC supply; the batch test draws a random phase per env and reset (goldens: fixed phase)
+    ("permex_sc_ac_rk4", "rk4"), ("series_fin_cc_ac_interlock_rk4", "rk4"), ("pmsm_cc_ac_rk4", "rk4"),
     ("dfim_cc_rk4", "rk4"), ("dfim_sc_rk4", "rk4x2"), ("dfim_fin_sc_interlock_rk4", "rk4"), ("dfim_cc_interlock_rk4", "euler3"),
     # state-vector wrappers (CosSinProcessor, FluxObserver, FluxObserver angle for dq actions, dead time in front)
     ("pmsm_cc_cossin_rk4", "rk4"), ("pmsm_sc_cossin_rm_rk4", "rk4"), ("scim_cc_flux_dq_rk4", "rk4"), ("scim_sc_flux_cossin_dead1_rk4", "rk4"),
@@ -160,6 +162,8 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
             cfg.ref_init_lo[r], cfg.ref_init_hi[r] = -0.7, 0.7
             cfg.ref_len_lo[r], cfg.ref_len_hi[r] = 5, 40  # many sub-episode changes inside the test
         cfg.env_index_offset = 7 * n
+        if cfg.supply_kind == K.SUPPLY_AC1:
+            cfg.supply_param[2] = 0.0  # phase ~ U[0, 2 pi) per env at every reset (Philox stream 9 on both sides)
         return cfg
 
     dev = DeviceAdapter(mk(dtype))

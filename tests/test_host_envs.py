@@ -87,6 +87,7 @@ def test_config_equals_golden_meta_translation():
         ("dfim_fin_cc_rk4", "Finite-CC-DFIM-v0", {}),
         ("pmsm_sc_rc_rk4", "Cont-SC-PMSM-v0", dict(supply=gem.physical_systems.RCVoltageSupply(420.0, dict(R=1.0, C=4e-3)))),
         ("extex_cc_rc_rk4", "Cont-CC-ExtExDc-v0", dict(supply=gem.physical_systems.RCVoltageSupply(60.0, dict(R=0.2, C=2e-3)))),
+        ("permex_sc_ac_rk4", "Cont-SC-PermExDc-v0", dict(supply=gem.physical_systems.AC1PhaseSupply(42.0, dict(frequency=50.0, phase=0.7)))),
         ("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", dict(motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
                                                               motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0))))),
     ]:
@@ -98,7 +99,7 @@ def test_config_equals_golden_meta_translation():
                   "n_constraints", "reward_bias", "violation_reward", "supply_kind"):
             assert getattr(cfg, f) == pytest.approx(getattr(ref, f)), (name, f)
         for f, n in (("converter_kind", 2), ("motor_param", 16), ("load_param", 5), ("limits", 28), ("init_ode", 8), ("reward_weight", 28),
-                     ("state_length", 28), ("constraint_mask", 4), ("ref_state", 4), ("supply_param", 2)):
+                     ("state_length", 28), ("constraint_mask", 4), ("ref_state", 4), ("supply_param", 3)):
             a, b = list(getattr(cfg, f))[:n], list(getattr(ref, f))[:n]
             assert a == pytest.approx(b, rel=1e-12), (name, f, a, b)
 
