@@ -81,8 +81,7 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
   const bool three_phase = d->fam >= kSYNC;
   if (c->action_dq) {
     if (!three_phase || c->finite) return fail(GEMB200_E_INVALID, "dq actions need a three-phase motor with a continuous converter");
-    if (c->motor_kind == GEMB200_MOTOR_DFIM) return fail(GEMB200_E_INVALID, "dq actions for the DFIM (4 actions, dq_to_abc_action_processor.py:108-137) are not supported");
-    d->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2;
+    d->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : (c->motor_kind == GEMB200_MOTOR_DFIM ? 4 : 2);
   }
   // state-vector wrappers (gemb200_state_op): width bookkeeping as in the wrappers' set_physical_system
   d->n_obs = d->n_state;
@@ -94,7 +93,7 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
         d->n_obs += c->sop_idx[k][1] ? 1 : 2;
         break;
       case GEMB200_SOP_FLUX_OBSERVER:
-        if (c->motor_kind != GEMB200_MOTOR_SCIM) return fail(GEMB200_E_INVALID, "FluxObserver needs an induction motor (flux_observer.py:57-60)");
+        if (c->motor_kind != GEMB200_MOTOR_SCIM && c->motor_kind != GEMB200_MOTOR_DFIM) return fail(GEMB200_E_INVALID, "FluxObserver needs an induction motor (flux_observer.py:57-60)");
         if (d->has_observer) return fail(GEMB200_E_INVALID, "only one FluxObserver per system");
         for (int q = 0; q < 4; ++q)
           if (c->sop_idx[k][q] < 0 || c->sop_idx[k][q] >= d->n_obs) return fail(GEMB200_E_INVALID, "FluxObserver: state index out of range");
@@ -112,6 +111,9 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
   }
   if (c->action_dq == 2 && !(c->motor_kind == GEMB200_MOTOR_SCIM && d->has_observer))
     return fail(GEMB200_E_INVALID, "action_dq = 2 (observer angle) needs a SCIM with a FluxObserver");
+  if (c->motor_kind == GEMB200_MOTOR_DFIM && c->action_dq && !(c->action_dq == 3 && d->has_observer))
+    return fail(GEMB200_E_INVALID, "DFIM dq actions are action_dq = 3 and need a FluxObserver (dq_to_abc_action_processor.py:108-137)");
+  if (c->action_dq == 3 && c->motor_kind != GEMB200_MOTOR_DFIM) return fail(GEMB200_E_INVALID, "action_dq = 3 is the DFIM processor");
   if (three_phase) {
     if (k0 != GEMB200_CONV_B6) return fail(GEMB200_E_INVALID, "three-phase motors need a B6 bridge in converter slot 0");
     if (c->motor_kind == GEMB200_MOTOR_EESM) {

@@ -29,13 +29,17 @@ class DqToAbcActionProcessor(PhysicalSystemWrapper):
 
     @classmethod
     def make(cls, motor_type, *args, **kwargs):
-        assert motor_type in ("PMSM", "SynRM", "EESM", "SCIM"), f"Not supported motor_type {motor_type}."
+        assert motor_type in ("PMSM", "SynRM", "EESM", "SCIM", "DFIM"), f"Not supported motor_type {motor_type}."
         if motor_type == "SCIM":  # dq_to_abc_action_processor.py:103-105
             kwargs.setdefault("angle_name", "psi_angle")
-        return cls(*args, **kwargs)
+        inst = cls(*args, **kwargs)
+        inst.dfim = motor_type == "DFIM"  # 4 actions: stator dq + rotor dq (:108-137), needs the FluxObserver's psi_angle as well
+        return inst
+
+    dfim = False
 
     def action_space(self, motor_kind_is_eesm):
-        return Box(-1, 1, shape=(3 if motor_kind_is_eesm else 2,), dtype=np.float64)
+        return Box(-1, 1, shape=(4 if self.dfim else (3 if motor_kind_is_eesm else 2),), dtype=np.float64)
 
 
 class DeadTimeProcessor(PhysicalSystemWrapper):

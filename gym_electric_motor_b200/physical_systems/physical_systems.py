@@ -109,7 +109,7 @@ class SCMLSystem(PhysicalSystem):
         from ..physical_system_wrappers import (CosSinProcessor, CurrentSumProcessor, DeadTimeProcessor, DqToAbcActionProcessor, FluxObserver,
                                                 StateNoiseProcessor)
         from .converters import FiniteConverter
-        from .electric_motors import DcShuntMotor, ExternallyExcitedSynchronousMotor, InductionMotor, SynchronousMotor
+        from .electric_motors import DcShuntMotor, DoublyFedInductionMotor, ExternallyExcitedSynchronousMotor, InductionMotor, SynchronousMotor
 
         for w in wrappers:
             if isinstance(w, CurrentSumProcessor):
@@ -121,7 +121,12 @@ class SCMLSystem(PhysicalSystem):
                 self._dead_steps = w.dead_time
                 self._dead_outer = 1 if self._action_dq else 0  # it wraps an existing dq transformation -> queue of dq actions
             elif isinstance(w, DqToAbcActionProcessor):
-                scim = isinstance(self._electrical_motor, InductionMotor)
+                dfim = isinstance(self._electrical_motor, DoublyFedInductionMotor)
+                scim = isinstance(self._electrical_motor, InductionMotor) and not dfim
+                if dfim != bool(w.dfim):
+                    raise NotImplementedError("DqToAbcActionProcessor.make('DFIM') goes with the DFIM system and only with it")
+                if dfim:
+                    assert "psi_angle" in self._state_names, "Angle psi_angle not in the states of the physical system. Probably a flux observer is required."
                 if not isinstance(self._electrical_motor, (SynchronousMotor, InductionMotor)) or isinstance(self._converter, FiniteConverter):
                     raise NotImplementedError("DqToAbcActionProcessor needs a PMSM/SynRM/EESM/SCIM system with a continuous converter")
                 if self._action_dq:
@@ -130,7 +135,7 @@ class SCMLSystem(PhysicalSystem):
                     f"Angle {w.angle_name} not in the states of the physical system. Probably a flux observer is required.")
                 if scim != (w.angle_name == "psi_angle"):
                     raise NotImplementedError("angle 'psi_angle' goes with the induction motor, 'epsilon' with the synchronous motors")
-                self._action_dq = 2 if scim else 1
+                self._action_dq = 3 if dfim else (2 if scim else 1)
                 self._angle_advance = 0.5 + self._dead_steps  # dq_to_abc_action_processor.py:69-72
                 self._action_space = w.action_space(isinstance(self._electrical_motor, ExternallyExcitedSynchronousMotor))
             elif isinstance(w, (CosSinProcessor, FluxObserver, StateNoiseProcessor)):

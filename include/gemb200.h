@@ -228,6 +228,8 @@ typedef struct gemb200_config {
   double init_mu[GEMB200_MAX_ODE], init_sigma[GEMB200_MAX_ODE];
   int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */
   double supply_param[4];
+  /* action_dq = 3: DFIM, 4 actions (stator dq, rotor dq): stator with eps + angle_advance*tau*omega*p, rotor with the FluxObserver's
+   * psi_angle minus that angle (dq_to_abc_action_processor.py:108-137); requires a GEMB200_SOP_FLUX_OBSERVER op */
   /* action_dq = 2: SCIM with a FluxObserver — the transformation angle is the observer's psi_angle (+ angle_advance*tau*omega*p),
    * dq_to_abc_action_processor.py:103-105; requires a GEMB200_SOP_FLUX_OBSERVER op */
 } gemb200_config;

@@ -148,7 +148,7 @@ static int dims(gem_oracle* o) {
   o->slot_off[1] = o->n_sub[0];
   if (c->finite) o->n_act = (c->converter_kind[0] != 0) + (c->converter_kind[1] != 0);
   else o->n_act = slot_nvolt(c->converter_kind[0]) + slot_nvolt(c->converter_kind[1]);
-  if (c->action_dq) o->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : 2; /* dq_to_abc_action_processor.py:97-99,:143-145 */
+  if (c->action_dq) o->n_act = c->motor_kind == GEMB200_MOTOR_EESM ? 3 : (c->motor_kind == GEMB200_MOTOR_DFIM ? 4 : 2); /* dq_to_abc_action_processor.py:97-99,:110-111,:143-145 */
   o->n_ref = c->n_ref;
   /* widths after the wrappers: cos_sin_processor.py:44-58, flux_observer.py:66-75 */
   o->n_obs = o->n_state;
@@ -1164,7 +1164,14 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
     for (int j = 0; j < na; ++j) abuf[j] = af[j];
     if (c->dead_time_steps > 0 && c->dead_time_outer)
       for (int j = 0; j < na; ++j) { double old = e->fifo[slot][j]; e->fifo[slot][j] = abuf[j]; abuf[j] = old; }
-    if (c->action_dq) {
+    if (c->action_dq == 3) { /* _DFIMDqToAbcActionProcessor.simulate :119-131 */
+      const double adv = wrap_eps(e->ode[o->n_ode - 1]) + c->angle_advance * c->tau * e->ode[0] * c->motor_param[GEMB200_MP_P];
+      const double psi_angle = atan2(e->psi_im, e->psi_re);
+      double dqs[2] = {abuf[0], abuf[1]}, dqr[2] = {abuf[2], abuf[3]}, ab[2];
+      q_rot(dqs, adv, ab); t_32(ab, abuf);
+      q_rot(dqr, psi_angle - adv, ab); t_32(ab, abuf + 3);
+      na = 6;
+    } else if (c->action_dq) {
       /* _ClassicDqToAbcActionProcessor.simulate :100-106 / _EESM :147-153; angle from the last state vector:
        * wrapped epsilon + angle_advance * tau * omega * p (:89-91).  control_space='dq' = same with advance 0
        * (physical_systems.py:491-492); SCIM uses the field angle (:779-780). */

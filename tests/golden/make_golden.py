@@ -351,6 +351,8 @@ CASES = [
     C("scim_cc_flux_dq_rk4", "Cont-CC-SCIM-v0", "rk4", steps=1500, wrappers=[("FluxObserver", None), ("DqToAbc", "SCIM")]),
     C("scim_sc_flux_cossin_dead1_rk4", "Cont-SC-SCIM-v0", "rk4", steps=1500,
       wrappers=[("DeadTime", 1), ("FluxObserver", None), ("CosSin", ["psi_angle", 0]), ("DqToAbc", "SCIM")]),
+    C("dfim_cc_flux_dq_rk4", "Cont-CC-DFIM-v0", "rk4", steps=1500, wrappers=[("FluxObserver", None), ("DqToAbc", "DFIM")]),
+    C("dfim_sc_dead1_flux_dq_rk4", "Cont-SC-DFIM-v0", "rk4", steps=1500, wrappers=[("DeadTime", 1), ("FluxObserver", None), ("DqToAbc", "DFIM")]),
     C("pmsm_cc_custom_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500,
       motor=dict(motor_parameter=dict(p=4, l_d=0.5e-3, l_q=0.9e-3, r_s=25e-3, psi_p=50e-3),
                  motor_initializer=dict(states=dict(i_sq=20.0, i_sd=-10.0, epsilon=1.0)))),

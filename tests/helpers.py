@@ -171,7 +171,7 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
             cur_limits += [psi_limit, np.pi]
             nops += 1
         else:
-            dq, adv = (2 if arg == "SCIM" else 1), 0.5 + dead
+            dq, adv = (3 if arg == "DFIM" else (2 if arg == "SCIM" else 1)), 0.5 + dead
     cfg.n_state_ops = nops
     assert cur_names == names or not nops, (cur_names, names)
     cfg.action_dq, cfg.dead_time_steps, cfg.dead_time_outer, cfg.angle_advance = dq, dead, outer, adv

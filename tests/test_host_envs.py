@@ -169,7 +169,8 @@ def test_state_vector_wrappers_bookkeeping_matches_reference():
         return out
 
     for name, env_id in [("pmsm_cc_cossin_rk4", "Cont-CC-PMSM-v0"), ("pmsm_sc_cossin_rm_rk4", "Cont-SC-PMSM-v0"), ("scim_cc_flux_rk4", "Cont-CC-SCIM-v0"),
-                         ("scim_cc_flux_dq_rk4", "Cont-CC-SCIM-v0"), ("scim_sc_flux_cossin_dead1_rk4", "Cont-SC-SCIM-v0")]:
+                         ("scim_cc_flux_dq_rk4", "Cont-CC-SCIM-v0"), ("scim_sc_flux_cossin_dead1_rk4", "Cont-SC-SCIM-v0"),
+                         ("dfim_cc_flux_dq_rk4", "Cont-CC-DFIM-v0"), ("dfim_sc_dead1_flux_dq_rk4", "Cont-SC-DFIM-v0")]:
         g = load_golden(name)
         meta = g["meta"]
         ref = config_from_meta(meta, reset_ode=g["reset_ode"], solver="rk4", ref_kind=K.REF_WIENER)
