@@ -257,6 +257,45 @@ def test_state_noise_processor_matches_oracle_and_distribution(torch_cuda, oracl
         assert z.min() >= a0 and z.max() <= a1
 
 
+@pytest.mark.parametrize("dev_solver,ora_solver,dtype,n,tol", [
+    ("rk4", "rk4", K.F32, 1024, 1e-5), ("rk4", "rk4", K.F64, 1024, 1e-9), ("rk4x2", "rk4x2", K.F32, 1024, 1e-5),
+    ("rk4x2", "dopri5", K.F64, 256, 2e-6), ("rk4x2", "dopri5", K.F32, 256, 1e-5)])
+def test_headline_config_long_horizon(torch_cuda, oracle_lib, dev_solver, ora_solver, dtype, n, tol):
+    """Cont-CC-PMSM-v0, zero-initialised, omega = 100 rad/s, U(-1,1)^3 actions, 1000 steps; the CUDA path
+    (RK4 x1 / x2) against the oracle driven by the algorithm-identical RK4 and by the reference's default dopri5, auto-reset on.
+    State, reward and termination are compared for every env and step; an env whose termination differs (a constraint within
+    rounding of its threshold) is dropped from then on — at most 0.5 % may."""
+    g = load_golden("pmsm_cc_rk4")
+    steps = 1000
+    rng = np.random.default_rng(2024)
+
+    def mk(dt, solver):
+        return config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=dt, solver=solver, ref_kind=K.REF_WIENER,
+                                autoreset=K.AUTORESET_SAME_STEP, seed=7)
+
+    dev, ora = DeviceAdapter(mk(dtype, dev_solver)), oracle_lib.Oracle(mk(K.F64, ora_solver), nthreads=16)
+    d_obs, d_ref = dev.reset()
+    o_obs, o_ref = ora.reset()
+    assert np.abs(d_obs - o_obs).max() < 1e-6 and np.abs(d_ref - o_ref).max() < 1e-5
+    alive = np.ones(n, dtype=bool)
+    scale = np.maximum(np.abs(o_obs).max(axis=0), 1e-3)
+    worst, n_term = 0.0, 0
+    for k in range(steps):
+        a = rng.uniform(-1, 1, size=(n, 3))
+        d_obs, d_ref, d_rew, d_term = dev.step(a)
+        o_obs, o_ref, o_rew, o_term = ora.step(a)
+        alive &= ~(o_term != d_term)
+        scale = np.maximum(scale, np.abs(o_obs[alive]).max(axis=0))
+        diff = np.abs(d_obs - o_obs)
+        diff[:, 12] = np.abs((d_obs[:, 12] - o_obs[:, 12] + 1.0) % 2.0 - 1.0)  # epsilon lives on a circle
+        err = (diff[alive] / scale).max()
+        worst = max(worst, err)
+        assert err < tol, f"step {k}: state error {err:.3e}"
+        assert np.abs(d_rew - o_rew)[alive].max() < 20 * tol and np.abs(d_ref - o_ref)[alive].max() < 20 * max(tol, 1e-7)
+        n_term += int(o_term[alive].sum())
+    assert alive.mean() > 0.995 and n_term > n // 4, (alive.mean(), n_term)  # random actions do trip the current limit
+
+
 def _cfg(name, n, dtype=K.F32, **kw):
     g = load_golden(name)
     return g, config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=dtype, solver="rk4", ref_kind=K.REF_WIENER,
