@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
@@ -98,6 +98,11 @@ class GemB200Config(C.Structure):
         ("init_dist", C.c_int32 * MAX_ODE),
         ("init_mu", C.c_double * MAX_ODE),
         ("init_sigma", C.c_double * MAX_ODE),
+        ("ref_sw_count", C.c_int32 * MAX_REF),
+        ("ref_sw_first", C.c_int32 * MAX_REF),
+        ("ref_sw_len_lo", C.c_int32 * MAX_REF),
+        ("ref_sw_len_hi", C.c_int32 * MAX_REF),
+        ("ref_sw_cdf", C.c_double * MAX_REF),
         ("supply_kind", C.c_int32),
         ("supply_param", C.c_double * 4),
     ]

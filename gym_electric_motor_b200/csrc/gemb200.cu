@@ -30,7 +30,7 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
 struct gemb200_handle {
   gemb200_config cfg;
   int fam = 0, n_state = 0, n_ode = 0, n_act = 0, n_ref = 0, nx = 0;
-  bool has_eps = false, any_wiener = false, two_segment = false;
+  bool has_eps = false, any_wiener = false, two_segment = false, any_switched = false;
   size_t rsz = 4;  // sizeof(real)
   // persistent device state
   int NH = 0, NC = 0;  // words per env in the hot / cold record
@@ -42,6 +42,7 @@ struct gemb200_handle {
   int fifo_dim = 0;
   void* d_sup = nullptr;   // RC supply state [2][n]
   double* d_supph = nullptr;  // AC supply phase [n]
+  uint32_t* d_swst = nullptr;  // switched reference generators [n_ref][2][n]
   void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
   int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
@@ -161,8 +162,22 @@ static int validate(const gemb200_config* c) {
   if (c->finite && c->interlocking_time > 0 && c->motor_kind == GEMB200_MOTOR_EESM)
     return fail(GEMB200_E_INVALID, "finite EESM with interlocking time: the reference raises in this configuration "
                                    "(physical_systems.py:632 slices u_in[:2]); not supported");
+  int n_entries = c->n_ref;  // parameter entries in use: the output slots plus the extra sub-generators of switched slots
   for (int r = 0; r < c->n_ref; ++r) {
+    if (c->ref_sw_count[r] <= 1) continue;
+    const int first = c->ref_sw_first[r], cnt = c->ref_sw_count[r];
+    if (first < 0 || first + cnt > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "switched reference generator: parameter entries out of range");
+    if (first + cnt > n_entries) n_entries = first + cnt;
+    if (c->ref_sw_len_lo[r] < 1 || c->ref_sw_len_hi[r] <= c->ref_sw_len_lo[r]) return fail(GEMB200_E_INVALID, "switched reference generator: bad super-episode length range");
+    for (int m = 0; m < cnt; ++m) {
+      const int k = c->ref_kind[first + m];
+      if (k == GEMB200_REF_EXTERNAL) return fail(GEMB200_E_INVALID, "switched reference generator: external sub-generators are not supported");
+      if (!(c->ref_sw_cdf[first + m] > 0 && c->ref_sw_cdf[first + m] <= 1.0 + 1e-12)) return fail(GEMB200_E_INVALID, "switched reference generator: bad probabilities");
+    }
+  }
+  for (int r = 0; r < c->n_ref; ++r)
     if (c->ref_state[r] < 0 || c->ref_state[r] >= d.n_obs) return fail(GEMB200_E_INVALID, "ref_state out of range");
+  for (int r = 0; r < n_entries; ++r) {
     if (c->ref_kind[r] < GEMB200_REF_CONST || c->ref_kind[r] > GEMB200_REF_TRIANGULAR) return fail(GEMB200_E_INVALID, "bad ref_kind");
     const bool subep = c->ref_kind[r] == GEMB200_REF_WIENER || c->ref_kind[r] >= GEMB200_REF_LAPLACE;
     const bool walk = c->ref_kind[r] == GEMB200_REF_WIENER || c->ref_kind[r] == GEMB200_REF_LAPLACE;
@@ -444,7 +459,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
                  c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
-    for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r];
+    for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r] && c.ref_sw_count[r] <= 1;
     const char* off = std::getenv("GEMB200_NO_PLAIN");
     p->plain = plain && !(off && off[0] == '1');
   }
@@ -482,9 +497,16 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     for (int q = 0; q < 8; ++q) p->sop_param[k][q] = (real)c.sop_param[k][q];
   }
   p->n_ref = c.n_ref;
+  p->swst = h->d_swst;
+  for (int r = 0; r < c.n_ref; ++r) {
+    p->sw_count[r] = c.ref_sw_count[r] > 1 ? c.ref_sw_count[r] : 0;
+    p->sw_first[r] = c.ref_sw_first[r];
+    p->sw_len_lo[r] = c.ref_sw_len_lo[r]; p->sw_len_span[r] = c.ref_sw_len_hi[r] - c.ref_sw_len_lo[r];
+  }
+  for (int r = 0; r < GEMB200_MAX_REF; ++r) p->sw_cdf[r] = (real)c.ref_sw_cdf[r];
   p->any_wiener = h->any_wiener;
   p->ref_tau = (real)c.tau;
-  for (int r = 0; r < c.n_ref; ++r) {
+  for (int r = 0; r < GEMB200_MAX_REF; ++r) {  // all parameter entries (switched sub-generators live beyond n_ref)
     p->ref_kind[r] = c.ref_kind[r]; p->ref_state[r] = c.ref_state[r];
     p->ref_const[r] = (real)c.ref_value[r];
     p->ref_lo[r] = (real)c.ref_margin_lo[r]; p->ref_hi[r] = (real)c.ref_margin_hi[r];
@@ -641,8 +663,12 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   h->n_ref = cfg->n_ref;
   h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
   h->two_segment = cfg->finite && cfg->interlocking_time > 0;
-  for (int r = 0; r < cfg->n_ref; ++r)  // any generator that advances by itself (Wiener, Laplace, periodic)
-    h->any_wiener = h->any_wiener || cfg->ref_kind[r] == GEMB200_REF_WIENER || cfg->ref_kind[r] >= GEMB200_REF_LAPLACE;
+  for (int r = 0; r < GEMB200_MAX_REF; ++r) {  // any generator that advances by itself (Wiener, Laplace, periodic), incl. switched subs
+    bool used = r < cfg->n_ref;
+    for (int q = 0; q < cfg->n_ref; ++q) used = used || (cfg->ref_sw_count[q] > 1 && r >= cfg->ref_sw_first[q] && r < cfg->ref_sw_first[q] + cfg->ref_sw_count[q]);
+    if (used) h->any_wiener = h->any_wiener || cfg->ref_kind[r] == GEMB200_REF_WIENER || cfg->ref_kind[r] >= GEMB200_REF_LAPLACE;
+    if (r < cfg->n_ref && cfg->ref_sw_count[r] > 1) h->any_switched = true;
+  }
   const size_t n = (size_t)cfg->n_envs;
 #define ALLOC(ptr, bytes)                                                                                     \
   do {                                                                                                        \
@@ -663,6 +689,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   if (h->two_segment || (cfg->finite && cfg->supply_kind == GEMB200_SUPPLY_RC)) ALLOC(h->d_sw, n * sizeof(uint16_t));
   if (cfg->supply_kind == GEMB200_SUPPLY_RC) ALLOC(h->d_sup, n * 2 * h->rsz);
   if (cfg->supply_kind == GEMB200_SUPPLY_AC1) ALLOC(h->d_supph, n * sizeof(double));
+  if (h->any_switched) ALLOC(h->d_swst, n * 2 * cfg->n_ref * sizeof(uint32_t));
   if (d.has_observer) ALLOC(h->d_obsv, n * 4 * h->rsz);
 #undef ALLOC
   Derived dv;
@@ -689,7 +716,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -861,6 +888,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_obsv) s[k++] = {h->d_obsv, n * 4 * h->rsz};
   if (h->d_sup) s[k++] = {h->d_sup, n * 2 * h->rsz};
   if (h->d_supph) s[k++] = {h->d_supph, n * sizeof(double)};
+  if (h->d_swst) s[k++] = {h->d_swst, n * 2 * h->cfg.n_ref * sizeof(uint32_t)};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {

@@ -48,6 +48,7 @@ enum : uint32_t {
   kStreamWalk = 1, kStreamSubep = 2, kStreamInit = 3, kStreamSubepHi = 18,
   kStreamWalkR = 5, kStreamSubepR = 6, kStreamSubepHiR = 22,  // "R": draws made right after an in-kernel auto-reset
   kStreamInitState = 7, kStreamInitState2 = 8,                // random initial ODE state
+  kStreamSwitch = 10, kStreamSwitchR = 14,                    // + slot: SwitchedReferenceGenerator super-episode (R: at a reset)
   kStreamSupply = 9,                                          // AC supply phase at reset
   kStreamPeriodic = 32,                                       // + 2*slot (+1): sub-episode parameters of the periodic generators,
                                                               //   counter word 0 = step index of the sub-episode start
@@ -150,6 +151,10 @@ struct StepParams {
   // periodic generators (sinus / step / sawtooth / triangular): parameter ranges per slot, tau for the phase increment
   real ref_amp_lo[kMaxRef], ref_amp_span[kMaxRef], ref_freq_lo[kMaxRef], ref_freq_span[kMaxRef], ref_off_lo[kMaxRef], ref_off_hi[kMaxRef];
   real ref_tau;
+  // SwitchedReferenceGenerator: output slot r switches between the parameter entries sw_first[r] .. +sw_count[r]-1 of the arrays above
+  int32_t sw_count[kMaxRef], sw_first[kMaxRef], sw_len_lo[kMaxRef], sw_len_span[kMaxRef];
+  real sw_cdf[kMaxRef];
+  uint32_t* swst;          // [n_ref][2][n]: current parameter entry, step at which the super-episode ends; nullptr unless switched
   // ---- state-vector wrappers (gemb200.h: gemb200_state_op), applied in order after the system's own vector is assembled ----
   int32_t n_sops;
   int32_t row_stride;      // shared-memory words per staged row: Fam::PAD without wrappers, else (final width | 1)

@@ -2,10 +2,10 @@
 kernel's epilogue with a counter-based Philox stream per (seed, env) — the reference's numpy PCG64 streams cannot be
 matched on a device; the distributions are (tests/test_oracle_golden.py::test_wiener_reference_statistics).
 
-On the device: Wiener, Laplace, Sinusoidal, Step, Sawtooth, Triangular, Const, Zero, Multiple (of those) and
+On the device: Wiener, Laplace, Sinusoidal, Step, Sawtooth, Triangular, Const, Zero, Multiple and Switched (of those) and
 `ExternalReferenceGenerator` (values pushed by the caller each step).  The periodic generators re-derive their sub-episode
 parameters from a Philox block addressed by the sub-episode's start step, so they need no extra per-env state.
-SwitchedReferenceGenerator is not available yet."""
+SwitchedReferenceGenerator keeps (current sub-generator, super-episode end) per env."""
 import numpy as np
 
 from . import _cabi as K
@@ -42,7 +42,8 @@ class ReferenceGenerator:
         if len(slots) > K.MAX_REF:
             raise ValueError(f"at most {K.MAX_REF} referenced states")
         cfg.n_ref = len(slots)
-        for r, s in enumerate(slots):
+
+        def put(r, s):
             cfg.ref_kind[r] = s["kind"]
             cfg.ref_state[r] = s["state"]
             cfg.ref_value[r] = s.get("value", 0.0)
@@ -53,6 +54,26 @@ class ReferenceGenerator:
             cfg.ref_amp_lo[r], cfg.ref_amp_hi[r] = s.get("amp", (0.0, 0.0))
             cfg.ref_freq_lo[r], cfg.ref_freq_hi[r] = s.get("freq", (1.0, 1.0))
             cfg.ref_off_lo[r], cfg.ref_off_hi[r] = s.get("off", (0.0, 0.0))
+
+        for r, s in enumerate(slots):
+            put(r, s)
+        # switched slots: their sub-generators become extra parameter entries behind the output slots (gemb200.h: ref_sw_*)
+        nxt = len(slots)
+        for r, s in enumerate(slots):
+            sw = s.get("switch")
+            if not sw or len(sw["subs"]) < 2:
+                continue
+            m = len(sw["subs"])
+            if nxt + m > K.MAX_REF:
+                raise NotImplementedError(f"referenced states + switched sub-generators exceed the {K.MAX_REF} generator entries of the kernel")
+            cfg.ref_sw_count[r], cfg.ref_sw_first[r] = m, nxt
+            cfg.ref_sw_len_lo[r], cfg.ref_sw_len_hi[r] = sw["length"]
+            acc = 0.0
+            for j, sub in enumerate(sw["subs"]):
+                put(nxt + j, sub)
+                acc += sw["p"][j] / sum(sw["p"])
+                cfg.ref_sw_cdf[nxt + j] = min(acc, 1.0) if j < m - 1 else 1.0
+            nxt += m
 
     def close(self):
         pass
@@ -267,6 +288,45 @@ class TriangularReferenceGenerator(_PeriodicReferenceGenerator):
 
 
 class SwitchedReferenceGenerator(ReferenceGenerator):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("SwitchedReferenceGenerator (switched_reference_generator.py) is not on the device path yet; available: "
-                                  "Wiener, Laplace, Sinusoidal, Step, Sawtooth, Triangular, Const, Zero, Multiple, External")
+    """reference switched_reference_generator.py: switches randomly (probabilities `p`) between sub-generators of the SAME referenced
+    state; each one is used for a super-episode of integers(*super_episode_length) steps, and a newly selected sub-generator starts a
+    fresh sub-episode from the current reference value.  On the device the sub-generators' parameters occupy additional parameter
+    entries of the kernel's generator table (include/gemb200.h: ref_sw_*), so referenced states + extra sub-generators <= 4."""
+
+    def __init__(self, sub_generators, p=None, super_episode_length=(100, 10000)):
+        super().__init__()
+        self.reference_space = Box(-1, 1, shape=(1,), dtype=np.float64)
+        self._sub_generators = list(sub_generators)
+        assert len(self._sub_generators) > 0, "No sub generator was passed."
+        ref_names = self._sub_generators[0].reference_names
+        assert all(sub_gen.reference_names == ref_names for sub_gen in self._sub_generators), \
+            "The passed sub generators have different referenced states."
+        self._reference_names = ref_names
+        self._probabilities = p or [1 / len(sub_generators)] * len(sub_generators)
+        if type(super_episode_length) in [float, int]:
+            super_episode_length = super_episode_length, super_episode_length + 1
+        self._super_episode_length = super_episode_length
+
+    def set_modules(self, physical_system):
+        super().set_modules(physical_system)
+        for sub_generator in self._sub_generators:
+            sub_generator.set_modules(physical_system)
+        ref_space_low = np.min([sub.reference_space.low for sub in self._sub_generators], axis=0)
+        ref_space_high = np.max([sub.reference_space.high for sub in self._sub_generators], axis=0)
+        self.reference_space = Box(ref_space_low, ref_space_high, dtype=np.float64)
+        self._referenced_states = self._sub_generators[0].referenced_states
+        for sub_generator in self._sub_generators:
+            assert np.all(sub_generator.referenced_states == self._referenced_states), "Reference Generators reference different state variables"
+            assert sub_generator.reference_space.shape == self.reference_space.shape, "Reference Generators have differently shaped reference spaces"
+
+    def slots(self):
+        subs = []
+        for sub in self._sub_generators:
+            sl = sub.slots()
+            if len(sl) != 1 or sl[0]["kind"] == K.REF_EXTERNAL or "switch" in sl[0]:
+                raise NotImplementedError("sub-generators of a SwitchedReferenceGenerator must be single-state built-in generators")
+            subs.append(sl[0])
+        out = dict(subs[0])
+        out["switch"] = dict(subs=subs, p=[float(v) for v in self._probabilities],
+                             length=(int(self._super_episode_length[0]), int(self._super_episode_length[1])))
+        return [out]

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 6
+#define GEMB200_ABI_VERSION 7
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -226,6 +226,12 @@ typedef struct gemb200_config {
    * per state; init_dist[j] = 0 uniform (lo == hi: constant), 1 truncated normal with init_mu[j], init_sigma[j]; needs init_random = 1 */
   int32_t init_dist[GEMB200_MAX_ODE];
   double init_mu[GEMB200_MAX_ODE], init_sigma[GEMB200_MAX_ODE];
+  /* SwitchedReferenceGenerator (reference_generators/switched_reference_generator.py): output slot r (r < n_ref) switches between
+   * ref_sw_count[r] generators (0 or 1: not switched) whose parameters occupy the entries ref_sw_first[r] .. +count-1 of the per-slot
+   * arrays above; entries >= n_ref are parameter-only entries, so n_ref + extra entries <= GEMB200_MAX_REF.  ref_sw_cdf[entry] is the
+   * cumulative probability inside its group; the super-episode length is integers(ref_sw_len_lo[r], ref_sw_len_hi[r]). */
+  int32_t ref_sw_count[GEMB200_MAX_REF], ref_sw_first[GEMB200_MAX_REF], ref_sw_len_lo[GEMB200_MAX_REF], ref_sw_len_hi[GEMB200_MAX_REF];
+  double ref_sw_cdf[GEMB200_MAX_REF];
   int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */
   double supply_param[4];
   /* action_dq = 3: DFIM, 4 actions (stator dq, rotor dq): stator with eps + angle_advance*tau*omega*p, rotor with the FluxObserver's

@@ -54,6 +54,7 @@ typedef struct {
   uint32_t ref_start[GEMB200_MAX_REF], ref_len[GEMB200_MAX_REF]; /* periodic generators: sub-episode start step and length */
   double fifo[GEMB200_MAX_DEAD_TIME][GEMB200_MAX_ACT]; /* DeadTimeProcessor queue (ring; slot = call counter mod steps) */
   double psi_re, psi_im; /* FluxObserver._integrated flux_observer.py:46 */
+  int sw_cur[GEMB200_MAX_REF], sw_k[GEMB200_MAX_REF], sw_len[GEMB200_MAX_REF]; /* SwitchedReferenceGenerator: current entry, _k, _current_episode_length */
   double ac_phase; /* AC1PhaseSupply._phi */
   double u_rc; int rc_started; /* RCVoltageSupply: solver state and 'a previous get_voltage call exists' (voltage_supplies.py:110-123) */
 } env_t;
@@ -105,6 +106,7 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
  * call of a handle gets a fresh call id, so no per-env RNG state exists.  Stream ids: */
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
+       STREAM_SWITCH = 10, STREAM_SWITCH_R = 14 /* + slot: SwitchedReferenceGenerator super-episodes (R: at a reset) */,
        STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */,
        STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */,
        STREAM_NOISE = 64 /* + 8*op + (state >> 2): StateNoiseProcessor */, STREAM_NOISE_R = 128 /* ... right after an auto-reset */ };
@@ -1032,25 +1034,49 @@ static double periodic_value(const gem_oracle* o, int r, int kind, const uint32_
   return v;
 }
 
+/* SwitchedReferenceGenerator._reset_reference switched_reference_generator.py:96-101: super-episode length ~ integers(lo, hi),
+ * generator ~ choice(sub_generators, p) */
+static void switch_generator(const gem_oracle* o, env_t* e, int64_t idx, int r, int at_reset) {
+  const gemb200_config* c = &o->cfg;
+  uint32_t w[4];
+  rng4(o, idx, (at_reset ? STREAM_SWITCH_R : STREAM_SWITCH) + r, w);
+  e->sw_len[r] = c->ref_sw_len_lo[r] + (int)(((uint64_t)w[0] * (uint64_t)(uint32_t)(c->ref_sw_len_hi[r] - c->ref_sw_len_lo[r])) >> 32);
+  const double u = u01(w[1]);
+  int g = c->ref_sw_first[r];
+  for (int m = 1; m < c->ref_sw_count[r]; ++m) if (u >= c->ref_sw_cdf[c->ref_sw_first[r] + m - 1]) g = c->ref_sw_first[r] + m;
+  e->sw_cur[r] = g;
+  e->sw_k[r] = 0;
+}
+
 static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_reset) {
   const gemb200_config* c = &o->cfg;
   uint32_t rw[4], rs[4], rs2[4], rlap[4];
   int have_w = 0, have_s = 0, have_s2 = 0, have_lap = 0;
   uint32_t kstep = (uint32_t)o->n_steps;
   for (int r = 0; r < c->n_ref; ++r) {
-    int kind = c->ref_kind[r];
+    int g = r; /* parameter entry: r itself, or the sub-generator a SwitchedReferenceGenerator currently uses */
+    if (c->ref_sw_count[r] > 1) { /* switched_reference_generator.py:80-94 */
+      if (!after_reset && e->sw_k[r] >= e->sw_len[r]) {
+        switch_generator(o, e, idx, r, 0);
+        e->ref_left[r] = 0; /* sub.reset(state, self._reference): value kept (:73-76 of the subepisoded class), new sub-episode */
+        if (c->ref_kind[e->sw_cur[r]] == GEMB200_REF_CONST) e->ref_value[r] = c->ref_value[e->sw_cur[r]];
+      }
+      g = e->sw_cur[r];
+      if (!after_reset) e->sw_k[r] += 1;
+    }
+    int kind = c->ref_kind[g];
     if (kind >= GEMB200_REF_SINUS) {
       uint32_t b[4], cw[4];
       if (e->ref_left[r] <= 0) { /* new sub-episode (subepisoded_reference_generator.py:93-100) */
         e->ref_start[r] = kstep;
         rng4_at(o, idx, kstep, STREAM_PERIODIC + 2 * r, b);
-        e->ref_len[r] = (uint32_t)((double)(c->ref_len_hi[r] - c->ref_len_lo[r]) * ((double)b[0] / 4294967296.0) + c->ref_len_lo[r]);
+        e->ref_len[r] = (uint32_t)((double)(c->ref_len_hi[g] - c->ref_len_lo[g]) * ((double)b[0] / 4294967296.0) + c->ref_len_lo[g]);
         e->ref_left[r] = (int)e->ref_len[r];
       } else {
         rng4_at(o, idx, e->ref_start[r], STREAM_PERIODIC + 2 * r, b);
       }
       rng4_at(o, idx, e->ref_start[r], STREAM_PERIODIC + 2 * r + 1, cw);
-      e->ref_value[r] = periodic_value(o, r, kind, b, cw, kstep - e->ref_start[r], e->ref_len[r]);
+      e->ref_value[r] = periodic_value(o, g, kind, b, cw, kstep - e->ref_start[r], e->ref_len[r]);
       e->ref_left[r] -= 1;
       continue;
     }
@@ -1066,8 +1092,8 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
         a = rs2[2 * (r & 1)]; b = rs2[2 * (r & 1) + 1];
       }
       /* int(U[0,1)*(hi-lo) + lo) subepisoded_reference_generator.py:37,:115-119 with U = a / 2^32 */
-      e->ref_left[r] = (int)((double)(c->ref_len_hi[r] - c->ref_len_lo[r]) * ((double)a / 4294967296.0) + c->ref_len_lo[r]);
-      double l0 = log10(c->ref_sigma_lo[r]), l1 = log10(c->ref_sigma_hi[r]);
+      e->ref_left[r] = (int)((double)(c->ref_len_hi[g] - c->ref_len_lo[g]) * ((double)a / 4294967296.0) + c->ref_len_lo[g]);
+      double l0 = log10(c->ref_sigma_lo[g]), l1 = log10(c->ref_sigma_hi[g]);
       e->ref_sigma[r] = pow(10.0, (l1 - l0) * u01(b) + l0); /* wiener_process_reference_generator.py:31 */
     }
     double z;
@@ -1083,8 +1109,8 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
       z = (r & 1) ? rad * sin(2 * M_PI * u2) : rad * cos(2 * M_PI * u2);
     }
     double v = e->ref_value[r] + e->ref_sigma[r] * z; /* :35-40 */
-    if (v > c->ref_margin_hi[r]) v = c->ref_margin_hi[r];
-    if (v < c->ref_margin_lo[r]) v = c->ref_margin_lo[r];
+    if (v > c->ref_margin_hi[g]) v = c->ref_margin_hi[g];
+    if (v < c->ref_margin_lo[g]) v = c->ref_margin_lo[g];
     e->ref_value[r] = v;
     e->ref_left[r] -= 1;
   }
@@ -1096,14 +1122,16 @@ static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
   uint32_t ri[4];
   rng4(o, idx, STREAM_INIT, ri);
   for (int r = 0; r < c->n_ref; ++r) {
-    if (c->ref_kind[r] == GEMB200_REF_WIENER) {
-      e->ref_value[r] = c->ref_init_lo[r] + (c->ref_init_hi[r] - c->ref_init_lo[r]) * u01(ri[r]);
+    int g = r;
+    if (c->ref_sw_count[r] > 1) { switch_generator(o, e, idx, r, 1); g = e->sw_cur[r]; } /* switched_reference_generator.py:64-68 */
+    if (c->ref_kind[g] == GEMB200_REF_WIENER) {
+      e->ref_value[r] = c->ref_init_lo[g] + (c->ref_init_hi[g] - c->ref_init_lo[g]) * u01(ri[r]);
       e->ref_left[r] = 0; /* _current_episode_length = -1 forces a new sub-episode */
       e->ref_sigma[r] = 0;
-    } else if (c->ref_kind[r] >= GEMB200_REF_LAPLACE) { /* SubepisodedReferenceGenerator.reset :71-91: value 0, new sub-episode */
+    } else if (c->ref_kind[g] >= GEMB200_REF_LAPLACE) { /* SubepisodedReferenceGenerator.reset :71-91: value 0, new sub-episode */
       e->ref_value[r] = 0.0; e->ref_left[r] = 0; e->ref_sigma[r] = 0;
     } else {
-      e->ref_value[r] = c->ref_value[r];
+      e->ref_value[r] = c->ref_value[g]; e->ref_left[r] = 0;
     }
   }
   ref_advance(o, e, idx, 1); /* reset() returns get_reference_observation() :82-91 via core.py:499-503 */

@@ -478,6 +478,39 @@ def init_bounds():
         json.dump(out, f, indent=1)
 
 
+def switched_stats():
+    """SwitchedReferenceGenerator semantics as statistics (its numpy streams cannot be matched on a device): three constant
+    sub-generators with probabilities (.5, .3, .2), super-episodes of integers(5, 12) steps, 200 000 steps of the reference; recorded:
+    the histogram of run lengths of equal reference values, the value frequencies, the length of the first run after the reset."""
+    from gym_electric_motor.reference_generators import ConstReferenceGenerator, SwitchedReferenceGenerator
+
+    vals, probs, length = [0.3, -0.2, 0.6], [0.5, 0.3, 0.2], (5, 12)
+    runs, first_runs, counts = [], [], {v: 0 for v in vals}
+    for seed in range(40):
+        env = gem.make("Cont-SC-PermExDc-v0", visualization=NoViz(), ode_solver=make_solver("euler"), constraints=(),
+                       reference_generator=SwitchedReferenceGenerator([ConstReferenceGenerator("omega", v) for v in vals], p=probs,
+                                                                      super_episode_length=length))
+        (_, r0), _ = env.reset(seed=seed)
+        seq = [float(r0[0])]
+        for _ in range(5000):
+            (_, rn), _, term, _, _ = env.step(np.zeros(1))
+            assert not term
+            seq.append(float(rn[0]))
+        seq = np.array(seq)
+        edges = np.nonzero(np.diff(seq) != 0)[0] + 1
+        rl = np.diff(np.concatenate(([0], edges)))  # complete runs only (the last, unfinished one is dropped)
+        first_runs.append(int(rl[0]))
+        runs += rl[1:].tolist()
+        for v in vals:
+            counts[v] += int(np.isclose(seq, v).sum())
+    hist = np.bincount(np.array(runs, dtype=int), minlength=80)[:80]
+    out = dict(values=vals, p=probs, super_episode_length=list(length), run_length_hist=hist.tolist(), first_runs=first_runs,
+               value_frequency=[counts[v] / sum(counts.values()) for v in vals], n_runs=len(runs))
+    with open(os.path.join(HERE, "switched_stats.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("switched_stats: runs", len(runs), "min/max run", min(runs), max(runs), "first runs", sorted(set(first_runs)), "freq", out["value_frequency"])
+
+
 def regen_ref_data():
     """Re-run the reference's own integration test recipe (tests/integration_tests/test_integration.py:18-87)."""
     sys.path.insert(0, os.path.join(REF_ROOT, "examples", "classic_controllers"))
@@ -532,11 +565,13 @@ if __name__ == "__main__":
     ap.add_argument("--skip-table", action="store_true")
     args = ap.parse_args()
     for case in CASES:
-        if args.only in ("ref_data", "init_bounds") or (args.only and args.only not in case["name"]):
+        if args.only in ("ref_data", "init_bounds", "switched_stats") or (args.only and args.only not in case["name"]):
             continue
         record(case)
     if not args.only or args.only == "init_bounds":
         init_bounds()
+    if not args.only or args.only == "switched_stats":
+        switched_stats()
     if not args.only or args.only == "ref_data":
         if not args.skip_table and not args.only:
             env_table()

@@ -199,6 +199,34 @@ def replay_golden(sim, g, inject_refs=True):
     return out
 
 
+def switched_config(n, kinds_cfg, p, length, name="permex_sc_euler3", seed=3, dtype=K.F64):
+    """config with ONE switched reference slot on the golden's referenced state; kinds_cfg = list of dicts written into the extra
+    parameter entries 1.. (entry 0 is the output slot itself)."""
+    g = load_golden(name)
+    cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], solver="rk4", ref_kind=K.REF_WIENER, seed=seed, dtype=dtype,
+                           autoreset=K.AUTORESET_SAME_STEP)
+    assert cfg.n_ref == 1
+    cfg.n_constraints = 0
+    cfg.ref_sw_count[0], cfg.ref_sw_first[0] = len(kinds_cfg), 1
+    cfg.ref_sw_len_lo[0], cfg.ref_sw_len_hi[0] = length
+    acc = 0.0
+    for j, kc in enumerate(kinds_cfg):
+        e = 1 + j
+        cfg.ref_state[e] = cfg.ref_state[0]
+        cfg.ref_kind[e] = kc["kind"]
+        cfg.ref_value[e] = kc.get("value", 0.0)
+        cfg.ref_margin_lo[e], cfg.ref_margin_hi[e] = kc.get("margin", (-0.8, 0.8))
+        cfg.ref_init_lo[e], cfg.ref_init_hi[e] = kc.get("margin", (-0.8, 0.8))
+        cfg.ref_sigma_lo[e], cfg.ref_sigma_hi[e] = kc.get("sigma", (1e-3, 1e-2))
+        cfg.ref_len_lo[e], cfg.ref_len_hi[e] = kc.get("length", (8, 30))
+        cfg.ref_amp_lo[e], cfg.ref_amp_hi[e] = kc.get("amp", (0.1, 0.4))
+        cfg.ref_freq_lo[e], cfg.ref_freq_hi[e] = kc.get("freq", (50.0, 400.0))
+        cfg.ref_off_lo[e], cfg.ref_off_hi[e] = kc.get("off", (-0.3, 0.3))
+        acc += p[j]
+        cfg.ref_sw_cdf[e] = acc if j < len(kinds_cfg) - 1 else 1.0
+    return cfg
+
+
 def golden_reset_state(g):
     """Reset observation of a golden.  Reference quirk: CosSinProcessor(remove_angle=True).reset() returns the vector WITH the
     angle it removes in simulate() (cos_sin_processor.py:60-63 vs :65-70); a batched tensor has one width, so the device path

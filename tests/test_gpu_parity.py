@@ -8,7 +8,7 @@ column-relative — the bar BASELINE.json's north_star sets for state trajectori
 import numpy as np
 import pytest
 
-from helpers import golden_reset_state, col_rel_err, config_from_meta, golden_names, load_golden, replay_golden
+from helpers import golden_reset_state, switched_config, col_rel_err, config_from_meta, golden_names, load_golden, replay_golden
 from gym_electric_motor_b200 import _cabi as K
 
 pytestmark = pytest.mark.gpu
@@ -527,6 +527,42 @@ def test_random_initial_states_match_oracle(torch_cuda, oracle_lib, name, dist, 
         assert np.abs(d_obs - o_obs)[alive].max() < 50 * tol, k
         n_term += int(o_term[alive].sum())
     assert alive.mean() > 0.99 and n_term > 0
+
+
+@pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", ["wiener_sinus_step", "const_laplace_triangular", "two_const"])
+def test_switched_reference_generator_matches_oracle(torch_cuda, oracle_lib, case, dtype):
+    """SwitchedReferenceGenerator in the fused epilogue vs the oracle (same Philox convention): every reference value, reward and
+    the reset references of auto-reset envs, with super-episodes short enough for dozens of switches per env."""
+    kinds = dict(
+        wiener_sinus_step=[dict(kind=K.REF_WIENER, margin=(-0.5, 0.5)), dict(kind=K.REF_SINUS), dict(kind=K.REF_STEP, amp=(0.05, 0.2))],
+        const_laplace_triangular=[dict(kind=K.REF_CONST, value=0.25), dict(kind=K.REF_LAPLACE, sigma=(1e-3, 5e-3)), dict(kind=K.REF_TRIANGULAR)],
+        two_const=[dict(kind=K.REF_CONST, value=-0.4), dict(kind=K.REF_CONST, value=0.7)])[case]
+    n, steps = 700, 300
+    p = [1.0 / len(kinds)] * len(kinds)
+
+    def mk(dt):
+        cfg = switched_config(n, kinds, p, (7, 25), seed=21, dtype=dt)
+        cfg.n_constraints = 1  # terminations + in-kernel auto-reset: the generator is re-chosen at the reset
+        return cfg
+
+    dev, ora = DeviceAdapter(mk(dtype)), oracle_lib.Oracle(mk(K.F64), nthreads=8)
+    d_obs, d_ref = dev.reset()
+    o_obs, o_ref = ora.reset()
+    tol = 1e-9 if dtype == K.F64 else 2e-5
+    assert np.abs(d_ref - o_ref).max() < tol
+    rng = np.random.default_rng(8)
+    alive = np.ones(n, dtype=bool)
+    distinct = set()
+    for k in range(steps):
+        a = rng.uniform(-1, 1, size=(n, 1))
+        d_obs, d_ref, d_rew, d_term = dev.step(a)
+        o_obs, o_ref, o_rew, o_term = ora.step(a)
+        alive &= ~(o_term != d_term)
+        assert np.abs(d_ref - o_ref)[alive].max() < tol, k
+        assert np.abs(d_rew - o_rew)[alive].max() < 20 * tol, k
+        distinct.update(np.round(o_ref[:5, 0], 3).tolist())
+    assert alive.mean() > 0.99 and len(distinct) > (1 if case == "two_const" else 20)
 
 
 @pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])

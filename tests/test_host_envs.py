@@ -242,6 +242,24 @@ def test_gaussian_initialiser_config():
         gem.make("Cont-SC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="cauchy")))
 
 
+def test_switched_reference_generator_config():
+    """SwitchedReferenceGenerator -> generator-table entries: the output slot plus one parameter entry per sub-generator, cumulative
+    probabilities, super-episode range; reference_space = union of the sub-generators' spaces (switched :49-56)."""
+    rg = gem.reference_generators
+    subs = [rg.WienerProcessReferenceGenerator(reference_state="omega", sigma_range=(1e-3, 1e-2)), rg.SinusoidalReferenceGenerator(reference_state="omega"),
+            rg.ConstReferenceGenerator(reference_state="omega", reference_value=0.3)]
+    env = gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator(subs, p=[0.5, 0.3, 0.2], super_episode_length=(50, 200)))
+    c = env.build_config()
+    assert c.n_ref == 1 and (c.ref_sw_count[0], c.ref_sw_first[0], c.ref_sw_len_lo[0], c.ref_sw_len_hi[0]) == (3, 1, 50, 200)
+    assert list(c.ref_kind)[1:4] == [K.REF_WIENER, K.REF_SINUS, K.REF_CONST] and c.ref_value[3] == 0.3
+    assert list(c.ref_sw_cdf)[1:4] == pytest.approx([0.5, 0.8, 1.0])
+    assert env.reference_names == ["omega"] and env.reference_generator.reference_space.shape == (1,)
+    with pytest.raises(AssertionError):
+        rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega"), rg.WienerProcessReferenceGenerator(reference_state="torque")])
+    with pytest.raises(NotImplementedError):  # 1 output + 4 sub-generators > 4 entries
+        gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega")] * 4)).build_config()
+
+
 def test_vector_facade_spaces():
     venv = gem.vector.make_vec("Cont-CC-PMSM-v0", num_envs=8, flatten_obs=True)
     assert venv.num_envs == 8 and venv.single_observation_space.shape == (16,) and venv.observation_space.shape == (8, 16)
