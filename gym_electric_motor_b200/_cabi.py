@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
@@ -15,8 +15,8 @@ MOTOR_PERMEX_DC, MOTOR_SERIES_DC, MOTOR_SHUNT_DC, MOTOR_EXTEX_DC, MOTOR_PMSM, MO
 (MP_P, MP_R_S, MP_L_D, MP_L_Q, MP_PSI_P, MP_J_ROTOR, MP_R_A, MP_L_A, MP_PSI_E, MP_R_E, MP_L_E, MP_L_E_PRIME, MP_L_M,
  MP_K, MP_L_SIGS, MP_L_SIGR) = range(16)
 CONV_NONE, CONV_1QC, CONV_2QC, CONV_4QC, CONV_B6 = range(5)
-LOAD_CONST_SPEED, LOAD_POLY_STATIC = 0, 1
-LP_A, LP_B, LP_C, LP_J_LOAD, LP_TAU_DECAY = range(5)
+LOAD_CONST_SPEED, LOAD_POLY_STATIC, LOAD_EXT_SPEED = 0, 1, 2
+LP_A, LP_B, LP_C, LP_J_LOAD, LP_TAU_DECAY, LP_TAU_LOAD = range(6)
 SOLVER_EULER, SOLVER_RK4 = 0, 1
 CONSTRAINT_LIMIT, CONSTRAINT_SQUARED = 0, 1
 REF_CONST, REF_WIENER, REF_EXTERNAL, REF_LAPLACE, REF_SINUS, REF_STEP, REF_SAWTOOTH, REF_TRIANGULAR = range(8)
@@ -103,6 +103,8 @@ class GemB200Config(C.Structure):
         ("ref_sw_len_lo", C.c_int32 * MAX_REF),
         ("ref_sw_len_hi", C.c_int32 * MAX_REF),
         ("ref_sw_cdf", C.c_double * MAX_REF),
+        ("ext_speed_table", C.c_void_p),
+        ("ext_speed_len", C.c_int32),
         ("supply_kind", C.c_int32),
         ("supply_param", C.c_double * 4),
     ]

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "gemb200_launch.cuh"
 
@@ -42,6 +43,8 @@ struct gemb200_handle {
   int fifo_dim = 0;
   void* d_sup = nullptr;   // RC supply state [2][n]
   double* d_supph = nullptr;  // AC supply phase [n]
+  void* d_ext = nullptr;       // external speed profile table (real)
+  uint32_t* d_kenv = nullptr;  // steps since the reset per env (external speed profile)
   uint32_t* d_swst = nullptr;  // switched reference generators [n_ref][2][n]
   void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
   int n_obs = 0, row_stride = 0;
@@ -143,7 +146,12 @@ static int validate(const gemb200_config* c) {
   if (c->solver_nsteps < 1 || c->solver_nsteps > 1024) return fail(GEMB200_E_INVALID, "solver_nsteps out of range");
   if (!(c->tau > 0)) return fail(GEMB200_E_INVALID, "tau must be positive");
   if (c->interlocking_time < 0 || c->interlocking_time >= c->tau) return fail(GEMB200_E_INVALID, "interlocking_time must be in [0, tau)");
-  if (c->load_kind != GEMB200_LOAD_CONST_SPEED && c->load_kind != GEMB200_LOAD_POLY_STATIC) return fail(GEMB200_E_INVALID, "bad load_kind");
+  if (c->load_kind < GEMB200_LOAD_CONST_SPEED || c->load_kind > GEMB200_LOAD_EXT_SPEED) return fail(GEMB200_E_INVALID, "bad load_kind");
+  if (c->load_kind == GEMB200_LOAD_EXT_SPEED) {
+    if (!c->ext_speed_table || c->ext_speed_len < 4 * c->solver_nsteps + 2) return fail(GEMB200_E_INVALID, "external speed load: table missing or shorter than two steps");
+    if (!(c->load_param[GEMB200_LP_TAU_LOAD] > 0)) return fail(GEMB200_E_INVALID, "external speed load: tau_load must be positive");
+    if (c->finite && c->interlocking_time > 0) return fail(GEMB200_E_INVALID, "external speed load with two-segment steps (finite converter + interlocking time) is not supported: the segment times are off the table grid");
+  }
   if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
   if (c->dead_time_steps < 0 || c->dead_time_steps > GEMB200_MAX_DEAD_TIME) return fail(GEMB200_E_INVALID, "dead_time_steps out of range");
   if (c->init_random && (c->motor_kind == GEMB200_MOTOR_SCIM || c->motor_kind == GEMB200_MOTOR_DFIM))
@@ -456,7 +464,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   // PLAIN shape (step_kernel): decided here once; GEMB200_NO_PLAIN=1 in the environment forces the general instantiation (A/B runs)
   {
     bool plain =
-                 c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
+                 c.load_kind != GEMB200_LOAD_EXT_SPEED && c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
     for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r] && c.ref_sw_count[r] <= 1;
@@ -469,6 +477,10 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     p->pf_dist = sms * 4 * GEMB200_BLOCK;  // measured optimum 0.25-1 wave, flat (profiles/r01_variants.md)
     if (const char* e = std::getenv("GEMB200_PF_DIST")) p->pf_dist = std::atoi(e);
   }
+  p->ext_tab = static_cast<const real*>(h->d_ext);
+  p->ext_len = c.ext_speed_len;
+  p->ext_inv_tau = c.load_kind == GEMB200_LOAD_EXT_SPEED ? (real)(1.0 / c.load_param[GEMB200_LP_TAU_LOAD]) : real(0);
+  p->kenv = h->d_kenv;
   p->supply_kind = c.supply_kind;
   p->sup = static_cast<real*>(h->d_sup);
   p->sup_k1 = c.supply_kind == GEMB200_SUPPLY_RC ? (real)(c.tau / (c.supply_param[0] * c.supply_param[1])) : real(0);
@@ -689,6 +701,17 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   if (h->two_segment || (cfg->finite && cfg->supply_kind == GEMB200_SUPPLY_RC)) ALLOC(h->d_sw, n * sizeof(uint16_t));
   if (cfg->supply_kind == GEMB200_SUPPLY_RC) ALLOC(h->d_sup, n * 2 * h->rsz);
   if (cfg->supply_kind == GEMB200_SUPPLY_AC1) ALLOC(h->d_supph, n * sizeof(double));
+  if (cfg->load_kind == GEMB200_LOAD_EXT_SPEED) {
+    ALLOC(h->d_kenv, n * sizeof(uint32_t));
+    ALLOC(h->d_ext, (size_t)cfg->ext_speed_len * h->rsz);
+    if (cfg->dtype == GEMB200_F32) {
+      std::vector<float> tmp(cfg->ext_speed_table, cfg->ext_speed_table + cfg->ext_speed_len);
+      cudaMemcpy(h->d_ext, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice);
+    } else {
+      cudaMemcpy(h->d_ext, cfg->ext_speed_table, (size_t)cfg->ext_speed_len * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    h->cfg.ext_speed_table = nullptr;  // the caller's buffer is not referenced after create
+  }
   if (h->any_switched) ALLOC(h->d_swst, n * 2 * cfg->n_ref * sizeof(uint32_t));
   if (d.has_observer) ALLOC(h->d_obsv, n * 4 * h->rsz);
 #undef ALLOC
@@ -716,7 +739,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -889,11 +912,12 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_sup) s[k++] = {h->d_sup, n * 2 * h->rsz};
   if (h->d_supph) s[k++] = {h->d_supph, n * sizeof(double)};
   if (h->d_swst) s[k++] = {h->d_swst, n * 2 * h->cfg.n_ref * sizeof(uint32_t)};
+  if (h->d_kenv) s[k++] = {h->d_kenv, n * sizeof(uint32_t)};
   return k;
 }
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {
   if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
-  Section s[10];
+  Section s[16];
   const int k = sections(h, s);
   int64_t total = 16;
   for (int i = 0; i < k; ++i) total += (int64_t)s[i].bytes;
@@ -906,7 +930,7 @@ int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
   char* b = (char*)host_blob;
   std::memcpy(b, &h->gstep, 8); b += 8;
   std::memcpy(b, &h->n_steps, 8); b += 8;
-  Section s[10];
+  Section s[16];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(b, s[i].ptr, s[i].bytes, cudaMemcpyDeviceToHost)); b += s[i].bytes; }
   return GEMB200_OK;
@@ -918,7 +942,7 @@ int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob) {
   const char* b = (const char*)host_blob;
   std::memcpy(&h->gstep, b, 8); b += 8;
   std::memcpy(&h->n_steps, b, 8); b += 8;
-  Section s[10];
+  Section s[16];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(s[i].ptr, b, s[i].bytes, cudaMemcpyHostToDevice)); b += s[i].bytes; }
   return GEMB200_OK;

@@ -163,6 +163,11 @@ struct StepParams {
   int32_t sop_idx[kMaxStateOps][4];
   uint32_t sop_mask[kMaxStateOps];
   real sop_param[kMaxStateOps][8];
+  // external speed profile (GEMB200_LOAD_EXT_SPEED): table of f(j * tau / (2 nsteps) + tau_load), per-env steps since the reset
+  const real* ext_tab;
+  int32_t ext_len;
+  real ext_inv_tau;
+  uint32_t* kenv;
   int32_t supply_kind;     // gemb200_supply_kind
   real sup_k1, sup_k2;     // RC supply: tau / (R C), R
   // AC supply: phase kept like the electrical angle (Ang<real>: turns as double-float in fp32, radians in a double), advanced by

@@ -147,5 +147,55 @@ def _unsupported(name, why):
     return _Unsupported
 
 
-ExternalSpeedLoad = _unsupported("ExternalSpeedLoad", "it calls a user Python function per step (host callback), out of scope (SURVEY.md §2 row 5)")
+class ExternalSpeedLoad(MechanicalLoad):
+    """reference external_speed_load.py: the speed follows a user profile f(t) through d omega/dt = (f(t + tau) - omega) / tau.
+
+    A Python callable cannot run inside the kernel, so the profile is TABULATED when the environment is built: f is evaluated at
+    every time a fixed-step Euler / RK4 stage can fall on (multiples of tau_system / (2 nsteps)) for `horizon_steps` control steps
+    after a reset (t restarts at every reset, as in the reference); past the horizon the last tabulated step repeats.  The scipy
+    solvers' adaptive stage times have no table: use EulerSolver / RK4Solver."""
+
+    KIND = K.LOAD_EXT_SPEED
+    HAS_JACOBIAN = False
+
+    def __init__(self, speed_profile, load_initializer=None, tau=1e-4, speed_profile_kwargs=None, horizon_steps=100000, **kwargs):
+        super().__init__(**kwargs)
+        if load_initializer is not None:
+            import warnings
+
+            warnings.warn("Given initializer will be overwritten with starting value from speed-profile, to avoid complications at the load "
+                          "reset. It is recommended to choose starting value of load by the defined speed-profile.", UserWarning)
+        self.speed_profile_kwargs = speed_profile_kwargs or {}
+        self._speed_profile = speed_profile
+        self._tau = tau
+        self._horizon = int(horizon_steps)
+        self._omega_initial = float(self._speed_profile(t=0, **self.speed_profile_kwargs))
+        self._initializer["states"]["omega"] = self._omega_initial
+        self._initial_states = self._initializer["states"]
+        self._table = None
+
+    @property
+    def omega(self):
+        return self._omega_initial
+
+    def fill_config(self, cfg):
+        """needs cfg.tau and cfg.solver_nsteps (SCMLSystem.fill_config fills the solver first)"""
+        cfg.load_kind = self.KIND
+        cfg.load_param[K.LP_J_LOAD] = float(self._j_load)
+        cfg.load_param[K.LP_TAU_LOAD] = float(self._tau)
+        per = 2 * int(cfg.solver_nsteps)
+        dt = float(cfg.tau) / per
+        n = per * self._horizon + 2 * per + 1  # two steps of margin: EulerSolver(nsteps > 1) evaluates the profile late (solvers.py:113-119)
+        kw = self.speed_profile_kwargs
+        try:  # vectorised profiles (numpy expressions) are evaluated in one call
+            tab = np.asarray(self._speed_profile(t=np.arange(n) * dt + self._tau, **kw), dtype=np.float64)
+            if tab.shape != (n,):
+                raise ValueError
+        except Exception:
+            tab = np.array([float(self._speed_profile(t=j * dt + self._tau, **kw)) for j in range(n)], dtype=np.float64)
+        self._table = np.ascontiguousarray(tab)
+        cfg.ext_speed_table = self._table.ctypes.data
+        cfg.ext_speed_len = n
+        cfg._keepalive = self._table  # the C side copies the table in gemb200_create
+
 OrnsteinUhlenbeckLoad = _unsupported("OrnsteinUhlenbeckLoad", "the reference's own constructor raises AttributeError (ornstein_uhlenbeck_load.py:22-27)")

@@ -258,8 +258,8 @@ class SCMLSystem(PhysicalSystem):
         cfg.interlocking_time = float(self._converter.interlocking_time)
         self._supply.fill_config(cfg)
         self._electrical_motor.fill_config(cfg)
-        self._mechanical_load.fill_config(cfg)
         self._ode_solver.fill_config(cfg)
+        self._mechanical_load.fill_config(cfg)  # after the solver: a tabulated speed profile needs the sub-step grid
         for i, v in enumerate(self._base_limits):
             cfg.limits[i] = float(v)
         for i, v in enumerate(self.initial_ode_state()):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 7
+#define GEMB200_ABI_VERSION 8
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -81,9 +81,13 @@ enum gemb200_converter_kind {
 
 enum gemb200_load_kind {
   GEMB200_LOAD_CONST_SPEED = 0, /* mechanical_loads/constant_speed_load.py:40-42 */
-  GEMB200_LOAD_POLY_STATIC = 1  /* mechanical_loads/polynomial_static_load.py:87-99 */
+  GEMB200_LOAD_POLY_STATIC = 1, /* mechanical_loads/polynomial_static_load.py:87-99 */
+  GEMB200_LOAD_EXT_SPEED = 2    /* mechanical_loads/external_speed_load.py:62-68: d omega/dt = (f(t + tau_load) - omega) / tau_load with the
+                                   user's speed profile f TABULATED on the host: ext_speed_table[j] = f(j * tau / (2 * solver_nsteps) + tau_load),
+                                   i.e. at every time a fixed-step Euler / RK4 stage can fall on; load_param[GEMB200_LP_TAU_LOAD] = tau_load;
+                                   t restarts at every reset; beyond the table the last step repeats */
 };
-enum gemb200_load_param { GEMB200_LP_A = 0, GEMB200_LP_B = 1, GEMB200_LP_C = 2, GEMB200_LP_J_LOAD = 3, GEMB200_LP_TAU_DECAY = 4 };
+enum gemb200_load_param { GEMB200_LP_A = 0, GEMB200_LP_B = 1, GEMB200_LP_C = 2, GEMB200_LP_J_LOAD = 3, GEMB200_LP_TAU_DECAY = 4, GEMB200_LP_TAU_LOAD = 5 };
 
 enum gemb200_supply_kind {
   GEMB200_SUPPLY_IDEAL = 0, /* voltage_supplies.py:60-72: u_sup = u_nominal */
@@ -232,6 +236,8 @@ typedef struct gemb200_config {
    * cumulative probability inside its group; the super-episode length is integers(ref_sw_len_lo[r], ref_sw_len_hi[r]). */
   int32_t ref_sw_count[GEMB200_MAX_REF], ref_sw_first[GEMB200_MAX_REF], ref_sw_len_lo[GEMB200_MAX_REF], ref_sw_len_hi[GEMB200_MAX_REF];
   double ref_sw_cdf[GEMB200_MAX_REF];
+  const double* ext_speed_table; /* HOST pointer, copied at gemb200_create (GEMB200_LOAD_EXT_SPEED only) */
+  int32_t ext_speed_len;
   int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */
   double supply_param[4];
   /* action_dq = 3: DFIM, 4 actions (stator dq, rotor dq): stator with eps + angle_advance*tau*omega*p, rotor with the FluxObserver's

@@ -298,8 +298,10 @@ static double torque(const gem_oracle* o, const double* ms) {
 }
 
 /* MechanicalLoad.mechanical_ode */
-static double mechanical_ode(const gem_oracle* o, double omega, double tq) {
+static double mechanical_ode(const gem_oracle* o, double omega, double tq, double g) {
   if (o->cfg.load_kind == GEMB200_LOAD_CONST_SPEED) return 0.0; /* constant_speed_load.py:40-42 */
+  if (o->cfg.load_kind == GEMB200_LOAD_EXT_SPEED) /* external_speed_load.py:62-68; g = speed_profile(t + tau_load) at this stage's time */
+    return (g - omega) / o->cfg.load_param[GEMB200_LP_TAU_LOAD];
   /* polynomial_static_load.py:87-99 */
   const double* lp = o->cfg.load_param;
   double sign = omega > 0 ? 1.0 : (omega < 0 ? -1.0 : 0.0);
@@ -309,45 +311,47 @@ static double mechanical_ode(const gem_oracle* o, double omega, double tq) {
 }
 
 /* SCMLSystem._system_equation physical_systems.py:205-236 */
-static void system_equation(const gem_oracle* o, const double* y, const double* u, double* dy) {
+static void system_equation(const gem_oracle* o, const double* y, const double* u, double* dy, double g) {
   double tq = torque(o, y + 1);
-  dy[0] = mechanical_ode(o, y[0], tq);
+  dy[0] = mechanical_ode(o, y[0], tq, g);
   electrical_ode(o, y + 1, u, y[0], dy + 1);
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* solvers                                                                                                       */
 /* ------------------------------------------------------------------------------------------------------------ */
-static void integrate_euler(const gem_oracle* o, double* y, double dt, int nsteps, const double* u) {
+/* gt: external speed profile samples f(t_stage + tau_load) on the grid of half sub-steps of THIS step (NULL otherwise) */
+static void integrate_euler(const gem_oracle* o, double* y, double dt, int nsteps, const double* u, const double* gt) {
   int n = o->n_ode;
   double dy[GEMB200_MAX_ODE];
   if (nsteps <= 1) { /* solvers.py:124-136 */
-    system_equation(o, y, u, dy);
+    system_equation(o, y, u, dy, gt ? gt[0] : 0.0);
     for (int i = 0; i < n; ++i) y[i] = y[i] + dy[i] * dt;
     return;
   }
-  /* solvers.py:103-122 (the time argument quirk is irrelevant: the RHS is autonomous) */
+  /* solvers.py:103-122; the time quirk (RHS evaluated one step + one sub-step late) only matters for the external speed load */
   double tau = dt / nsteps;
   for (int s = 0; s < nsteps; ++s) {
-    system_equation(o, y, u, dy);
+    system_equation(o, y, u, dy, gt ? gt[2 * nsteps + 2 * (s + 1)] : 0.0); /* current_t = t (the END time), RHS at current_t + tau :113-118 */
     for (int i = 0; i < n; ++i) y[i] = y[i] + dy[i] * tau;
   }
 }
 
-static void integrate_rk4(const gem_oracle* o, double* y, double dt, int nsteps, const double* u) {
+static void integrate_rk4(const gem_oracle* o, double* y, double dt, int nsteps, const double* u, const double* gt) {
   /* classic RK4; mirrors the test-side RK4Solver plugin in tests/golden/make_golden.py that produced the goldens */
   int n = o->n_ode;
   if (nsteps < 1) nsteps = 1;
   double h = dt / nsteps;
   double k1[GEMB200_MAX_ODE], k2[GEMB200_MAX_ODE], k3[GEMB200_MAX_ODE], k4[GEMB200_MAX_ODE], yt[GEMB200_MAX_ODE];
   for (int s = 0; s < nsteps; ++s) {
-    system_equation(o, y, u, k1);
+    const double g0 = gt ? gt[2 * s] : 0.0, g1 = gt ? gt[2 * s + 1] : 0.0, g2 = gt ? gt[2 * s + 2] : 0.0; /* t, t + h/2, t + h */
+    system_equation(o, y, u, k1, g0);
     for (int i = 0; i < n; ++i) yt[i] = y[i] + 0.5 * h * k1[i];
-    system_equation(o, yt, u, k2);
+    system_equation(o, yt, u, k2, g1);
     for (int i = 0; i < n; ++i) yt[i] = y[i] + 0.5 * h * k2[i];
-    system_equation(o, yt, u, k3);
+    system_equation(o, yt, u, k3, g1);
     for (int i = 0; i < n; ++i) yt[i] = y[i] + h * k3[i];
-    system_equation(o, yt, u, k4);
+    system_equation(o, yt, u, k4, g2);
     for (int i = 0; i < n; ++i) y[i] = y[i] + h / 6.0 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
   }
 }
@@ -371,7 +375,7 @@ static double integrate_dopri5(const gem_oracle* o, double* y, double t_start, d
   double y1[GEMB200_MAX_ODE], ysti[GEMB200_MAX_ODE];
   double x = t_start, xend = t_end, posneg = dt >= 0 ? 1.0 : -1.0, hmax = fabs(dt);
   double facold = 1e-4;
-  system_equation(o, y, u, k1);
+  system_equation(o, y, u, k1, 0.0);
   /* HINIT */
   double h;
   {
@@ -380,7 +384,7 @@ static double integrate_dopri5(const gem_oracle* o, double* y, double t_start, d
     h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
     h = fmin(h, hmax) * posneg;
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * k1[i];
-    system_equation(o, y1, u, k2);
+    system_equation(o, y1, u, k2, 0.0);
     double der2 = 0;
     for (int i = 0; i < n; ++i) { double sk = atol + rtol * fabs(y[i]); double d = (k2[i] - k1[i]) / sk; der2 += d * d; }
     der2 = sqrt(der2) / h;
@@ -396,17 +400,17 @@ static double integrate_dopri5(const gem_oracle* o, double* y, double t_start, d
     if (0.1 * fabs(h) <= fabs(x) * uround) return x;
     if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = 1; }
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * a21 * k1[i];
-    system_equation(o, y1, u, k2);
+    system_equation(o, y1, u, k2, 0.0);
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a31 * k1[i] + a32 * k2[i]);
-    system_equation(o, y1, u, k3);
+    system_equation(o, y1, u, k3, 0.0);
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
-    system_equation(o, y1, u, k4);
+    system_equation(o, y1, u, k4, 0.0);
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
-    system_equation(o, y1, u, k5);
+    system_equation(o, y1, u, k5, 0.0);
     for (int i = 0; i < n; ++i) ysti[i] = y[i] + h * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
-    system_equation(o, ysti, u, k6);
+    system_equation(o, ysti, u, k6, 0.0);
     for (int i = 0; i < n; ++i) y1[i] = y[i] + h * (a71 * k1[i] + a73 * k3[i] + a74 * k4[i] + a75 * k5[i] + a76 * k6[i]);
-    system_equation(o, y1, u, k2);
+    system_equation(o, y1, u, k2, 0.0);
     double err = 0;
     for (int i = 0; i < n; ++i) {
       k4[i] = (e1 * k1[i] + e3 * k3[i] + e4 * k4[i] + e5 * k5[i] + e6 * k6[i] + e7 * k2[i]) * h;
@@ -437,11 +441,11 @@ static double integrate_dopri5(const gem_oracle* o, double* y, double t_start, d
 }
 
 /* OdeSolver.integrate(t): returns the time actually reached (== t_end except for a failing dopri5) */
-static double integrate(const gem_oracle* o, double* y, double t_start, double t_end, const double* u) {
+static double integrate(const gem_oracle* o, double* y, double t_start, double t_end, const double* u, const double* gt) {
   switch (o->cfg.solver_kind) {
-    case GEMB200_SOLVER_EULER: integrate_euler(o, y, t_end - t_start, o->cfg.solver_nsteps, u); return t_end;
-    case GEMB200_SOLVER_RK4: integrate_rk4(o, y, t_end - t_start, o->cfg.solver_nsteps, u); return t_end;
-    default: return integrate_dopri5(o, y, t_start, t_end, u);
+    case GEMB200_SOLVER_EULER: integrate_euler(o, y, t_end - t_start, o->cfg.solver_nsteps, u, gt); return t_end;
+    case GEMB200_SOLVER_RK4: integrate_rk4(o, y, t_end - t_start, o->cfg.solver_nsteps, u, gt); return t_end;
+    default: return integrate_dopri5(o, y, t_start, t_end, u); /* adaptive stage times: no table for the external speed load */
   }
 }
 
@@ -684,6 +688,12 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
   if (nseg == 2) { seg_end[0] = t0 + c->interlocking_time; seg_end[1] = t0 + c->tau; }
   else seg_end[0] = t0 + c->tau;
   double t_solver = t0;
+  const double* gt = NULL; /* ExternalSpeedLoad: the tabulated profile restarts at every reset (e->k = steps since then) */
+  if (c->load_kind == GEMB200_LOAD_EXT_SPEED) {
+    const long per = 2L * c->solver_nsteps, last = (long)c->ext_speed_len - 1 - 2 * per;
+    const long j0 = e->k * per;
+    gt = c->ext_speed_table + (j0 < last ? j0 : last);
+  }
   double eps = 0.0, eps_fs = 0.0;
   for (int seg = 0; seg < nseg; ++seg) {
     /* currents flowing into the motor at the start of the segment, in converter coordinates */
@@ -730,7 +740,7 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
       } break;
       default: u_solver[0] = u_in[0]; u_solver[1] = u_in[1]; break;
     }
-    t_solver = integrate(o, y, t_solver, seg_end[seg], u_solver); /* :513 */
+    t_solver = integrate(o, y, t_solver, seg_end[seg], u_solver, gt); /* :513 */
   }
   e->t = t_solver;
   e->k += 1;

@@ -75,6 +75,10 @@ class RK4Solver(OdeSolver):
         return self._y
 
 
+def sin_profile(t, a, f, o):
+    return o + a * np.sin(2 * np.pi * f * t)
+
+
 def make_solver(name):
     if name == "euler":
         return EulerSolver()
@@ -146,6 +150,7 @@ def describe(env, case):
         j_total=float(load.j_total),
         load_parameter={k: float(v) for k, v in getattr(load, "load_parameter", {}).items()},
         omega_fixed=float(getattr(load, "omega_fixed", 0.0) or 0.0),
+        ext_speed=dict(tau=float(getattr(load, "_tau", 0.0)), **{k: float(v) for k, v in getattr(load, "speed_profile_kwargs", {}).items()}),
         supply_class=type(p.supply).__name__,
         u_sup=float(p.supply.u_nominal),
         supply_parameter=dict(R=float(getattr(p.supply, "_r", 0.0)), C=float(getattr(p.supply, "_c", 0.0)), f=float(getattr(p.supply, "_f", 0.0)),
@@ -185,6 +190,10 @@ def record(case):
     if case.get("supply_rc") is not None:  # [u_nominal, R, C]
         u0, r, c = case["supply_rc"]
         kwargs["supply"] = ps.RCVoltageSupply(u_nominal=u0, supply_parameter=dict(R=r, C=c))
+    if case.get("ext_speed") is not None:  # ExternalSpeedLoad with omega(t) = o + a sin(2 pi f t); [a, f, o]
+        a_, f_, o_ = case["ext_speed"]
+        kwargs["load"] = ps.ExternalSpeedLoad(speed_profile=sin_profile, tau=case.get("tau") or (1e-5 if case["env_id"].startswith("Finite") else 1e-4),
+                                              speed_profile_kwargs=dict(a=a_, f=f_, o=o_))
     if case.get("supply_ac") is not None:  # [u_nominal, f, phase]
         u0, f, ph = case["supply_ac"]
         kwargs["supply"] = ps.AC1PhaseSupply(u_nominal=u0, supply_parameter=dict(frequency=f, phase=ph))
@@ -312,6 +321,11 @@ CASES = [
     C("pmsm_cc_rc_interlock_euler3", "Cont-CC-PMSM-v0", "euler3", steps=1500, supply_rc=[300.0, 0.3, 4e-3], converter=dict(interlocking_time=2e-6)),
     C("eesm_fin_cc_rc_rk4", "Finite-CC-EESM-v0", "rk4", steps=2000, supply_rc=[300.0, 1.0, 2e-3]),
     C("dfim_cc_rc_rk4", "Cont-CC-DFIM-v0", "rk4", steps=1500, supply_rc=[420.0, 1.0, 4e-3]),
+    # ExternalSpeedLoad (external_speed_load.py): sinusoidal speed profiles on the fixed-step solvers
+    C("pmsm_cc_extspeed_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500, ext_speed=[80.0, 25.0, 120.0]),
+    C("permex_cc_extspeed_euler3", "Cont-CC-PermExDc-v0", "euler3", steps=1500, ext_speed=[150.0, 40.0, 50.0]),
+    C("scim_cc_extspeed_rk4x2", "Cont-CC-SCIM-v0", "rk4x2", steps=1500, ext_speed=[100.0, 10.0, 150.0]),
+    C("pmsm_fin_cc_extspeed_euler", "Finite-CC-PMSM-v0", "euler", steps=2000, ext_speed=[200.0, 100.0, 0.0]),
     # single-phase AC supply with a fixed phase (voltage_supplies.py:126-166)
     C("permex_sc_ac_rk4", "Cont-SC-PermExDc-v0", "rk4", steps=1500, supply_ac=[42.0, 50.0, 0.7]),
     C("series_fin_cc_ac_interlock_rk4", "Finite-CC-SeriesDc-v0", "rk4", steps=2000, supply_ac=[230.0, 400.0, 2.5], converter=dict(interlocking_time=1e-6)),

@@ -73,6 +73,10 @@ def solver_from_name(name):
     raise ValueError(name)
 
 
+def len_steps_hint(meta):
+    return int(meta["case"].get("steps", 2000))
+
+
 def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype=K.F64, layout=K.LAYOUT_AOS,
                      autoreset=K.AUTORESET_NONE, seed=0, reset_ode=None):
     cfg = K.new_config()
@@ -90,10 +94,19 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
         raise ValueError(cc)
     for i, kd in enumerate(kinds):
         cfg.converter_kind[i] = kd
-    cfg.load_kind = K.LOAD_CONST_SPEED if meta["load_class"] == "ConstantSpeedLoad" else K.LOAD_POLY_STATIC
+    cfg.load_kind = {"ConstantSpeedLoad": K.LOAD_CONST_SPEED, "ExternalSpeedLoad": K.LOAD_EXT_SPEED}.get(meta["load_class"], K.LOAD_POLY_STATIC)
     kind, nsteps = solver_from_name(solver or meta["case"]["solver"])
     cfg.solver_kind, cfg.solver_nsteps = kind, nsteps
     cfg.tau = meta["tau"]
+    if cfg.load_kind == K.LOAD_EXT_SPEED:  # tabulated speed profile: f(j tau / (2 nsteps) + tau_load), make_golden.py:sin_profile
+        es = meta["ext_speed"]
+        per = 2 * nsteps
+        j = np.arange(per * (len_steps_hint(meta) + 8) + 2 * per + 1)
+        t = j * (meta["tau"] / per) + es["tau"]
+        tab = np.ascontiguousarray(es["o"] + es["a"] * np.sin(2 * np.pi * es["f"] * t))
+        cfg.load_param[K.LP_TAU_LOAD] = es["tau"]
+        cfg.ext_speed_table, cfg.ext_speed_len = tab.ctypes.data, len(tab)
+        cfg._keepalive = tab
     cfg.interlocking_time = meta["interlocking_time"]
     cfg.u_sup = meta["u_sup"]
     if meta.get("supply_class") == "AC1PhaseSupply":

@@ -112,6 +112,8 @@ BATCH_CASES = [
     # RC voltage supply behind continuous / finite, single / multi converters
     ("permex_sc_rc_rk4", "rk4"), ("permex_fin_sc_rc_interlock_rk4", "rk4"), ("pmsm_fin_cc_rc_rk4", "rk4"), ("eesm_fin_cc_rc_rk4", "rk4"),
     ("pmsm_cc_rc_interlock_euler3", "euler3"), ("dfim_cc_rc_rk4", "rk4"),
+    # ExternalSpeedLoad: tabulated speed profile, incl. the Euler-n look-ahead quirk and RK4 sub-steps
+    ("pmsm_cc_extspeed_rk4", "rk4"), ("permex_cc_extspeed_euler3", "euler3"), ("scim_cc_extspeed_rk4x2", "rk4x2"), ("pmsm_fin_cc_extspeed_euler", "euler"),
     # single-phase AC supply; the batch test draws a random phase per env and reset (goldens: fixed phase)
     ("permex_sc_ac_rk4", "rk4"), ("series_fin_cc_ac_interlock_rk4", "rk4"), ("pmsm_cc_ac_rk4", "rk4"),
     ("dfim_cc_flux_dq_rk4", "rk4"), ("dfim_cc_rk4", "rk4"), ("dfim_sc_rk4", "rk4x2"), ("dfim_fin_sc_interlock_rk4", "rk4"), ("dfim_cc_interlock_rk4", "euler3"),

@@ -260,6 +260,31 @@ def test_switched_reference_generator_config():
         gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega")] * 4)).build_config()
 
 
+def test_external_speed_load_table():
+    """ExternalSpeedLoad: the callable is tabulated on the grid of solver stage times (+ tau_load), vectorised or scalar profiles
+    alike, and the initial speed is f(0); the table must equal the independent one tests/helpers.py builds from the golden meta."""
+    import ctypes as C
+
+    def profile(t, a, f, o):
+        return o + a * np.sin(2 * np.pi * f * t)
+
+    def scalar_profile(t, a, f, o):
+        return float(o + a * np.sin(2 * np.pi * f * float(t)))  # float() rejects arrays -> per-sample fallback
+
+    g = load_golden("pmsm_cc_extspeed_rk4")
+    ref = config_from_meta(g["meta"], reset_ode=g["reset_ode"], solver="rk4")
+    for prof in (profile, scalar_profile):
+        load = gem.physical_systems.ExternalSpeedLoad(prof, tau=1e-4, speed_profile_kwargs=dict(a=80.0, f=25.0, o=120.0), horizon_steps=1508)
+        env = gem.make("Cont-CC-PMSM-v0", load=load, ode_solver=gem.physical_systems.RK4Solver())
+        cfg = env.build_config()
+        assert cfg.load_kind == K.LOAD_EXT_SPEED == ref.load_kind and cfg.ext_speed_len == ref.ext_speed_len
+        assert cfg.load_param[K.LP_TAU_LOAD] == ref.load_param[K.LP_TAU_LOAD] == 1e-4 and cfg.init_ode[0] == 120.0
+        a = np.ctypeslib.as_array(C.cast(cfg.ext_speed_table, C.POINTER(C.c_double)), (cfg.ext_speed_len,))
+        b = np.ctypeslib.as_array(C.cast(ref.ext_speed_table, C.POINTER(C.c_double)), (ref.ext_speed_len,))
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
+    assert gem.make("Cont-CC-PMSM-v0", load=load, ode_solver=gem.physical_systems.EulerSolver(nsteps=3)).build_config().ext_speed_len == 6 * 1508 + 13
+
+
 def test_vector_facade_spaces():
     venv = gem.vector.make_vec("Cont-CC-PMSM-v0", num_envs=8, flatten_obs=True)
     assert venv.num_envs == 8 and venv.single_observation_space.shape == (16,) and venv.observation_space.shape == (8, 16)
