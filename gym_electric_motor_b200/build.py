@@ -48,8 +48,9 @@ def _units(only=None):
 
 
 def build(force=False, verbose=False, out=OUT, defines=(), only=None, jobs=None):
-    """Compile and link.  `defines`/`only`/`out` are for experiment builds (tools/variant_bench.py): extra -D flags, a subset of
-    (family, real) units (a missing unit makes the library fail to LOAD, on purpose: no silent holes), another output path."""
+    """Compile and link.  `defines`/`only`/`out` are for experiment builds (tools/build_variants.py): extra -D flags, a subset of
+    (family, real) units — pass -DGEMB200_ONLY_FAM=<family> with only={(family, "float")} so that the host code does not reference
+    the missing units (otherwise the library fails to LOAD, on purpose: no silent holes) — and another output path."""
     if not force and not is_stale(out):
         return out
     tag = hashlib.sha1(("|".join(defines) + "|" + os.path.abspath(out)).encode()).hexdigest()[:10]
@@ -76,8 +77,6 @@ def build(force=False, verbose=False, out=OUT, defines=(), only=None, jobs=None)
             raise RuntimeError("nvcc failed building libgemb200.so")
         objs.append(obj)
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
-    if only:
-        link += ["-Xlinker", "--unresolved-symbols=ignore-all"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stdout.write(res.stdout)

@@ -537,8 +537,14 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
 // ----------------------------------------------------------------------------------------------------------------
 // kernel dispatch (the instantiations live in gemb200_step_tu.cu, one TU per family x real)
 // ----------------------------------------------------------------------------------------------------------------
+// GEMB200_ONLY_FAM=<family>: experiment builds (tools/build_variants.py --only) that carry the fp32 kernels of ONE motor family; every
+// other configuration fails with cudaErrorInvalidValue instead of leaving unresolved symbols.  Never defined in the product build.
 template <typename real>
 static cudaError_t launch_step(int fam, bool finite, int nref, const StepParams<real>& p, cudaStream_t st) {
+#ifdef GEMB200_ONLY_FAM
+  if constexpr (std::is_same<real, float>::value) { if (fam == GEMB200_ONLY_FAM) return launch_step_f<GEMB200_ONLY_FAM, real>(finite, nref, p, st); }
+  return cudaErrorInvalidValue;
+#else
   switch (fam) {
     case kDC1: return launch_step_f<kDC1, real>(finite, nref, p, st);
     case kDC2: return launch_step_f<kDC2, real>(finite, nref, p, st);
@@ -548,9 +554,14 @@ static cudaError_t launch_step(int fam, bool finite, int nref, const StepParams<
     case kDFIM: return launch_step_f<kDFIM, real>(finite, nref, p, st);
   }
   return cudaErrorInvalidValue;
+#endif
 }
 template <typename real>
 static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cudaStream_t st) {
+#ifdef GEMB200_ONLY_FAM
+  if constexpr (std::is_same<real, float>::value) { if (fam == GEMB200_ONLY_FAM) return launch_reset_f<GEMB200_ONLY_FAM, real>(nref, p, st); }
+  return cudaErrorInvalidValue;
+#else
   switch (fam) {
     case kDC1: return launch_reset_f<kDC1, real>(nref, p, st);
     case kDC2: return launch_reset_f<kDC2, real>(nref, p, st);
@@ -560,6 +571,7 @@ static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cu
     case kDFIM: return launch_reset_f<kDFIM, real>(nref, p, st);
   }
   return cudaErrorInvalidValue;
+#endif
 }
 
 // One launch over envs [begin, end) (end < 0: all).  new_call: this launch starts a new API call (fresh RNG call id);
