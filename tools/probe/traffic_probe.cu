@@ -10,16 +10,26 @@
 
 struct Bufs { float4 *st0, *st1; float2* eps; float* act; float4* obs; float2* ref; float* rew; uint8_t* term; };
 
-template <bool WRITE_OBS, bool WRITE_STATE>
-__global__ void probe(Bufs b, int n) {
+// V6: the record layout since the hot/cold split — st0 (hot) is written back, st1 + one float (cold, 20 B) only read; PF: L2 prefetch of
+// the env `pf` positions ahead, as the step kernel does
+template <bool WRITE_OBS, bool WRITE_STATE, bool V6 = false>
+__global__ void probe(Bufs b, int n, int pf = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 a = b.st0[i], c = b.st1[i];
   float2 e = b.eps[i];
+  if (V6) a.y += b.rew[i] * 0.f + reinterpret_cast<const float*>(b.ref)[i];  // the 5th cold word (4 B)
+  if (pf > 0 && i + pf < n) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b.st0 + i + pf));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b.st1 + i + pf));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b.eps + i + pf));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b.act + (size_t)(i + pf) * 3));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float*>(b.ref) + i + pf));
+  }
   const float* ap = b.act + (size_t)i * 3;
   const float s = ap[0] + ap[1] + ap[2];
   a.x += s; c.y += e.x;
-  if (WRITE_STATE) { b.st0[i] = a; b.st1[i] = c; b.eps[i] = e; }
+  if (WRITE_STATE) { b.st0[i] = a; if (!V6) b.st1[i] = c; b.eps[i] = e; }
   b.ref[i] = make_float2(c.x, c.y);
   b.rew[i] = s;
   b.term[i] = (uint8_t)(s > 100.f);
@@ -51,7 +61,9 @@ int main() {
         Bufs& b = bs[k % R];
         if (mode == 0) probe<true, true><<<grid, block>>>(b, n);
         else if (mode == 1) probe<false, true><<<grid, block>>>(b, n);
-        else probe<true, false><<<grid, block>>>(b, n);
+        else if (mode == 2) probe<true, false><<<grid, block>>>(b, n);
+        else if (mode == 3) probe<true, true, true><<<grid, block>>>(b, n, 0);
+        else probe<true, true, true><<<grid, block>>>(b, n, 75776);
       }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
@@ -67,6 +79,10 @@ int main() {
     printf("{\"probe\": \"no obs rows (52 B read + 53 B written)\", \"block\": %d, \"us_per_launch\": %.2f, \"GBps\": %.0f}\n", block, t, (rd + 53.0) * n / t / 1e3);
     t = run(2, block);
     printf("{\"probe\": \"no state write-back (52 B read + 69 B written)\", \"block\": %d, \"us_per_launch\": %.2f, \"GBps\": %.0f}\n", block, t, (rd + 69.0) * n / t / 1e3);
+    t = run(3, block);
+    printf("{\"probe\": \"v6 traffic: hot/cold records (56 B read + 93 B written)\", \"block\": %d, \"us_per_launch\": %.2f, \"GBps\": %.0f}\n", block, t, 149.0 * n / t / 1e3);
+    t = run(4, block);
+    printf("{\"probe\": \"v6 traffic + L2 prefetch of env i+75776\", \"block\": %d, \"us_per_launch\": %.2f, \"GBps\": %.0f}\n", block, t, 149.0 * n / t / 1e3);
   }
   return 0;
 }
