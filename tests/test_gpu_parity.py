@@ -335,7 +335,8 @@ def _cfg(name, n, dtype=K.F32, **kw):
                                autoreset=K.AUTORESET_SAME_STEP, seed=3, **kw)
 
 
-@pytest.mark.parametrize("name", ["pmsm_cc_rk4", "eesm_cc_rk4", "permex_cc_rk4", "extex_cc_rk4", "scim_fin_sc_rk4"])
+@pytest.mark.parametrize("name", ["pmsm_cc_rk4", "eesm_cc_rk4", "permex_cc_rk4", "extex_cc_rk4", "scim_fin_sc_rk4", "dfim_cc_rk4",
+                                  "scim_sc_flux_cossin_dead1_rk4", "pmsm_sc_cossin_rm_rk4", "permex_sc_rc_rk4"])
 @pytest.mark.parametrize("n", [1, 31, 33, 257, 4096 + 5])
 def test_layouts_and_host_path_agree_bitwise(torch_cuda, name, n):
     """row-per-env (AoS, smem transpose + vector stores) vs the host-buffer entry point: bit-for-bit (same kernel).
@@ -369,11 +370,14 @@ def test_layouts_and_host_path_agree_bitwise(torch_cuda, name, n):
             assert np.array_equal(x.cpu().numpy(), y)
 
 
-def test_checkpoint_roundtrip(torch_cuda):
+@pytest.mark.parametrize("name", ["pmsm_fin_sc_rk4_interlock", "scim_sc_flux_cossin_dead1_rk4", "permex_fin_sc_rc_interlock_rk4", "pmsm_cc_ac_rk4",
+                                  "pmsm_cc_extspeed_rk4"])
+def test_checkpoint_roundtrip(torch_cuda, name):
+    """state_dict covers every persistent array: records, angle, switching states, dead-time queue, observer, supply, profile clock"""
     import torch
     from gym_electric_motor_b200.vector_sim import VectorSim
 
-    g, cfg = _cfg("pmsm_fin_sc_rk4_interlock", 513)
+    g, cfg = _cfg(name, 513)
     sim = VectorSim(cfg, reuse_outputs=False)
     rng = np.random.default_rng(1)
     acts = _random_actions(rng, g, 513, 30)
