@@ -65,7 +65,7 @@ class PhysicalSystem:
 class SCMLSystem(PhysicalSystem):
     """reference physical_systems.py:13-287, batched.
 
-    Extra args: num_envs (N), device (CUDA ordinal or 'cuda:k'), dtype ('float32' = fp32 state + fp64 rotor angle,
+    Extra args: num_envs (N), device (CUDA ordinal or 'cuda:k'), dtype ('float32' = fp32 state + double-float rotor angle,
     'float64'), layout ('aos' row-per-env [N, n_state] | 'soa' field-major [n_state, N])."""
 
     _MOTOR_BASE = ElectricMotor

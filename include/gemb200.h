@@ -138,7 +138,7 @@ enum gemb200_state_op {
 };
 enum gemb200_noise_dist { GEMB200_NOISE_NORMAL = 0, GEMB200_NOISE_UNIFORM = 1, GEMB200_NOISE_LAPLACE = 2 };
 
-enum gemb200_dtype { GEMB200_F32 = 0 /* fp32 state, fp64 rotor angle */, GEMB200_F64 = 1 };
+enum gemb200_dtype { GEMB200_F32 = 0 /* fp32 state; rotor angle as a double-float (two fp32, ~48 bits) in turns */, GEMB200_F64 = 1 };
 enum gemb200_layout {
   GEMB200_LAYOUT_AOS = 0, /* obs[N][n_state], action[N][n_act], ref[N][n_ref]  (row per env, the gym layout) */
   GEMB200_LAYOUT_SOA = 1  /* obs[n_state][N], action[n_act][N], ref[n_ref][N]  (field-major, fully coalesced) */
