@@ -813,7 +813,8 @@ int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void
   // Row-per-env buffers are contiguous per env range, so a large batch is cut into chunks that flow through three
   // streams: the D2H of chunk c overlaps the H2D + launch of chunk c+1 (PCIe is full duplex).  One API call = one RNG id.
   const bool pipelined = h->cfg.layout == GEMB200_LAYOUT_AOS && n >= (size_t)1 << 16;
-  const int nchunk = pipelined ? 8 : 1;
+  static const int chunks_env = [] { const char* e = std::getenv("GEMB200_HOST_CHUNKS"); return e ? std::atoi(e) : 0; }();  // experiment knob
+  const int nchunk = pipelined ? (chunks_env > 0 ? chunks_env : 4) : 1;  // 2..16 chunks measure the same (PCIe D2H bound, ~49 GB/s); 4 keeps the copy count low
   const size_t per = pipelined ? ((n / nchunk + 255) / 256) * 256 : n;
   bool first = true;
   for (int c = 0; c < nchunk; ++c) {
