@@ -82,6 +82,22 @@ def main():
         print(json.dumps({"config": label, "n_envs": n, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3), "alg_bytes_per_env_step": balg,
                           "alg_gbs": balg * n / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": balg * n / (ms * 1e-3) / 1e9 / PEAK}), flush=True)
         env.close()
+    # BASELINE.json configs[1]: Cont-CC-PMSM-v0 at N = 65536 (one partial wave: latency- and launch-bound, not bandwidth-bound):
+    # K back-to-back launches issued from C (gemb200_rollout), one event pair; RK4 x1 and x2
+    for label, kw in (("Cont-CC-PMSM-v0 N=65536 rk4x1 f32 (64 back-to-back launches)", dict(ode_solver=RK4())),
+                      ("Cont-CC-PMSM-v0 N=65536 rk4x2 f32 (64 back-to-back launches)", dict(ode_solver=RK4(nsteps=2)))):
+        ns = 1 << 16
+        env = gem.make("Cont-CC-PMSM-v0", num_envs=ns, autoreset="same_step", seed=0, **kw)
+        env.reset()
+        roll = torch.stack([actions_for(env, ns, dev, gen) for _ in range(64)]).contiguous()
+        for _ in range(3):
+            env.sim.rollout(roll)
+        best = 1e9
+        for _ in range(5):
+            env.sim.time_begin(); env.sim.rollout(roll); best = min(best, env.sim.time_end() / 64)
+        print(json.dumps({"config": label, "n_envs": ns, "ms_per_step": best, "env_steps_per_s": ns / (best * 1e-3), "alg_bytes_per_env_step": 129,
+                          "alg_gbs": 129 * ns / (best * 1e-3) / 1e9, "frac_of_measured_hbm": 129 * ns / (best * 1e-3) / 1e9 / PEAK}), flush=True)
+        env.close()
     # configs[4]: mixed PMSM + SynRM + EESM, interleaved ids, per-type kernels on separate streams
     ids = [("Cont-CC-PMSM-v0", dict(ode_solver=RK4())), ("Cont-CC-SynRM-v0", dict(ode_solver=RK4())), ("Cont-CC-EESM-v0", dict(ode_solver=RK4()))]
     nm = (n // 3) * 3
