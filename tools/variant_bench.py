@@ -35,8 +35,8 @@ for rep in range(5):
     best = min(best, ms)
 # (c) host cost of one env.step call (tiny batch)
 import time
-small = gem.make("Cont-CC-PMSM-v0", num_envs=256, ode_solver=gem.physical_systems.RK4Solver(), autoreset="same_step")
-small.reset(); a = torch.zeros((256, 3), device=dev)
+small = gem.make(os.environ.get("GEMB200_ENV", "Cont-CC-PMSM-v0"), num_envs=256, ode_solver=gem.physical_systems.RK4Solver(), autoreset="same_step")
+small.reset(); a = torch.zeros((256, small.sim.n_act), device=dev)
 for _ in range(200): small.step(a)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(2000): small.step(a)
