@@ -9,8 +9,9 @@
  * Pinning: tests/test_oracle_golden.py replays every trajectory in tests/golden/*.npz (recorded from the
  * UNMODIFIED reference by tests/golden/make_golden.py, including a regeneration of the reference's own
  * tests/integration_tests/ref_data.npz) through this file and requires agreement to <=1e-9 (Euler / RK4,
- * algorithm-identical) and <=2e-7 (dopri5, adaptive).  Reference converter truth tables
- * (tests/test_physical_systems/test_converters.py) are re-checked in the same test module.
+ * algorithm-identical) and <=2e-7 (dopri5, adaptive).  The known-answer vectors of the reference's own unit tests (converter
+ * truth tables, PolynomialStaticLoad ODE, constraint tables, reward cases; tests/golden/make_known_answers.py) are replayed through the
+ * probe entry points at the end of this file by tests/test_oracle_known_answers.py.
  *
  * Every function cites the reference lines it restates.  The structure deliberately follows the reference
  * (dense model-constant matrices, per-segment convert/integrate loop) rather than the optimised CUDA kernels.
@@ -1304,3 +1305,15 @@ void gem_oracle_periodic_block(const gem_oracle* o, int r, int kind, const uint3
 }
 /* exposed for the known-answer tests of the reference's converter tables / solver vectors */
 void gem_oracle_philox(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_10(ctr, k0, k1); }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* probe entry points for tests/test_oracle_known_answers.py: the reference's unit tests call converters, loads,  */
+/* constraints and the reward function directly, so the same granularity is exposed here (on env 0)               */
+/* ------------------------------------------------------------------------------------------------------------ */
+int gem_oracle_probe_set_action(gem_oracle* o, const double* act_f, const int32_t* act_i, double t) { return conv_set_action(o, o->env, act_f, act_i, t); }
+void gem_oracle_probe_convert(gem_oracle* o, const double* i_out, double t, double* u_out) { conv_convert(o, o->env, i_out, t, u_out); }
+void gem_oracle_probe_conv_reset(gem_oracle* o, double* u_out) { conv_reset(o, o->env, u_out); }
+double gem_oracle_probe_mechanical_ode(gem_oracle* o, double omega, double tq) { return mechanical_ode(o, omega, tq, 0.0); }
+double gem_oracle_probe_constraints(gem_oracle* o, const double* s) { return check_constraints(o, s); }
+double gem_oracle_probe_reward(gem_oracle* o, const double* s, const double* ref_full, double violation) { return reward(o, s, ref_full, violation); }
+

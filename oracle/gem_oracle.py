@@ -39,6 +39,15 @@ def lib():
             getattr(_lib, "gem_oracle_" + n).argtypes = [C.c_void_p, C.c_void_p]
         _lib.gem_oracle_get_ref_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.gem_oracle_philox.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.gem_oracle_probe_set_action.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        _lib.gem_oracle_probe_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        _lib.gem_oracle_probe_conv_reset.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.gem_oracle_probe_mechanical_ode.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        _lib.gem_oracle_probe_mechanical_ode.restype = C.c_double
+        _lib.gem_oracle_probe_constraints.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.gem_oracle_probe_constraints.restype = C.c_double
+        _lib.gem_oracle_probe_reward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        _lib.gem_oracle_probe_reward.restype = C.c_double
         _lib.gem_oracle_periodic_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -113,6 +122,40 @@ class Oracle:
         vals, par = np.zeros(length), np.zeros(5)
         self._lib.gem_oracle_periodic_block(self._h, slot, kind, _p(b), _p(c), length, _p(vals), _p(par))
         return vals, par
+
+    # ---- component-level probes (env 0) for tests/test_oracle_known_answers.py
+    def probe_set_action(self, action, t):
+        if self.finite:
+            a = np.ascontiguousarray(np.atleast_1d(action), dtype=np.int32)
+            return self._lib.gem_oracle_probe_set_action(self._h, None, _p(a), float(t))
+        a = np.ascontiguousarray(np.atleast_1d(action), dtype=np.float64)
+        return self._lib.gem_oracle_probe_set_action(self._h, _p(a), None, float(t))
+
+    def probe_convert(self, i_out, t):
+        i = np.zeros(6)
+        i[: len(np.atleast_1d(i_out))] = np.atleast_1d(i_out)
+        u = np.zeros(6)
+        self._lib.gem_oracle_probe_convert(self._h, _p(i), float(t), _p(u))
+        return u
+
+    def probe_conv_reset(self):
+        u = np.zeros(6)
+        self._lib.gem_oracle_probe_conv_reset(self._h, _p(u))
+        return u
+
+    def probe_mechanical_ode(self, omega, torque):
+        return self._lib.gem_oracle_probe_mechanical_ode(self._h, float(omega), float(torque))
+
+    def probe_constraints(self, state):
+        s = np.zeros(32)
+        s[: len(state)] = state
+        return self._lib.gem_oracle_probe_constraints(self._h, _p(s))
+
+    def probe_reward(self, state, reference, violation):
+        s, r = np.zeros(32), np.zeros(32)
+        s[: len(state)] = state
+        r[: len(reference)] = reference
+        return self._lib.gem_oracle_probe_reward(self._h, _p(s), _p(r), float(violation))
 
     def get_ref_aux(self):
         sigma = np.zeros((self.n, self.n_ref))
