@@ -321,21 +321,27 @@ static void system_equation(const gem_oracle* o, const double* y, const double* 
 /* ------------------------------------------------------------------------------------------------------------ */
 /* solvers                                                                                                       */
 /* ------------------------------------------------------------------------------------------------------------ */
-/* gt: external speed profile samples f(t_stage + tau_load) on the grid of half sub-steps of THIS step (NULL otherwise) */
-static void integrate_euler(const gem_oracle* o, double* y, double dt, int nsteps, const double* u, const double* gt) {
-  int n = o->n_ode;
+/* EulerSolver solvers.py:79-136 as a stepping scheme over an arbitrary right-hand side (the motor system below; the reference's
+ * test system in the known-answer probe at the end of the file).  gt: external speed profile samples f(t_stage + tau_load) on the
+ * grid of half sub-steps of THIS step (NULL otherwise). */
+typedef void (*rhs_fn)(const void* ctx, const double* y, const double* u, double* dy, double g);
+static void euler_core(rhs_fn f, const void* ctx, int n, double* y, double dt, int nsteps, const double* u, const double* gt) {
   double dy[GEMB200_MAX_ODE];
   if (nsteps <= 1) { /* solvers.py:124-136 */
-    system_equation(o, y, u, dy, gt ? gt[0] : 0.0);
+    f(ctx, y, u, dy, gt ? gt[0] : 0.0);
     for (int i = 0; i < n; ++i) y[i] = y[i] + dy[i] * dt;
     return;
   }
   /* solvers.py:103-122; the time quirk (RHS evaluated one step + one sub-step late) only matters for the external speed load */
   double tau = dt / nsteps;
   for (int s = 0; s < nsteps; ++s) {
-    system_equation(o, y, u, dy, gt ? gt[2 * nsteps + 2 * (s + 1)] : 0.0); /* current_t = t (the END time), RHS at current_t + tau :113-118 */
+    f(ctx, y, u, dy, gt ? gt[2 * nsteps + 2 * (s + 1)] : 0.0); /* current_t = t (the END time), RHS at current_t + tau :113-118 */
     for (int i = 0; i < n; ++i) y[i] = y[i] + dy[i] * tau;
   }
+}
+static void motor_rhs(const void* ctx, const double* y, const double* u, double* dy, double g) { system_equation((const gem_oracle*)ctx, y, u, dy, g); }
+static void integrate_euler(const gem_oracle* o, double* y, double dt, int nsteps, const double* u, const double* gt) {
+  euler_core(motor_rhs, o, o->n_ode, y, dt, nsteps, u, gt);
 }
 
 static void integrate_rk4(const gem_oracle* o, double* y, double dt, int nsteps, const double* u, const double* gt) {
@@ -1316,4 +1322,17 @@ void gem_oracle_probe_conv_reset(gem_oracle* o, double* u_out) { conv_reset(o, o
 double gem_oracle_probe_mechanical_ode(gem_oracle* o, double omega, double tq) { return mechanical_ode(o, omega, tq, 0.0); }
 double gem_oracle_probe_constraints(gem_oracle* o, const double* s) { return check_constraints(o, s); }
 double gem_oracle_probe_reward(gem_oracle* o, const double* s, const double* ref_full, double violation) { return reward(o, s, ref_full, violation); }
+/* EulerSolver known answers (tests/test_physical_systems/test_solvers.py:248-269): the stepping scheme above on the reference's test
+ * system tests/conf.py:418-434 */
+static void conf_system(const void* ctx, const double* st, const double* u, double* dy, double g) {
+  (void)ctx; (void)g;
+  const double x = st[0], y = st[1];
+  dy[0] = 3 * x + 5 * y - 2 * x * y + 3 * x * x - 0.5 * y * y;
+  dy[1] = 10 - 0.6 * x + 0.9 * y * y - 3 * x * x * y + u[0];
+}
+void gem_oracle_probe_euler(int nsteps, const double* y0, double dt, double u, double* out) {
+  double y[GEMB200_MAX_ODE] = {y0[0], y0[1]};
+  euler_core(conf_system, NULL, 2, y, dt, nsteps, &u, NULL);
+  out[0] = y[0]; out[1] = y[1];
+}
 

@@ -48,6 +48,7 @@ def lib():
         _lib.gem_oracle_probe_constraints.restype = C.c_double
         _lib.gem_oracle_probe_reward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         _lib.gem_oracle_probe_reward.restype = C.c_double
+        _lib.gem_oracle_probe_euler.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         _lib.gem_oracle_periodic_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -162,6 +163,14 @@ class Oracle:
         left = np.zeros((self.n, self.n_ref), dtype=np.int32)
         self._lib.gem_oracle_get_ref_aux(self._h, _p(sigma), _p(left))
         return sigma, left
+
+
+def probe_euler(nsteps, y0, dt, u):
+    """the oracle's EulerSolver stepping on the reference's test system (tests/conf.py:418-434)"""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    out = np.zeros(2)
+    lib().gem_oracle_probe_euler(int(nsteps), _p(y0), float(dt), float(u), _p(out))
+    return out
 
 
 def philox(counter, key):

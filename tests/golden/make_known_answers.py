@@ -9,6 +9,7 @@ by hand.  Sources:
   tests/test_physical_systems/test_converters.py:14-257 (tables), :260-300, :313-367 (finite 1QC/2QC/4QC protocol),
       :419-503 (continuous 1QC/2QC/4QC, comparable_voltage), :592-640 (finite B6 bridge, per-leg table)
   tests/test_physical_systems/test_mechanical_loads.py:191-211 (PolynomialStaticLoad.mechanical_ode known answers)
+  tests/test_physical_systems/test_solvers.py:248-269 (EulerSolver one-step / n-step known answers on tests/conf.py:418-434)
   tests/test_constraints/test_limit_constraint.py:33-66, test_squared_constraint.py:25-99 (truth tables)
   tests/test_reward_functions/test_weighted_sum_of_errors.py:150-218 (reward cases)
 """
@@ -128,6 +129,24 @@ def poly_load():
                 cases=[dict(omega=float(c[0]), expected=float(c[1])) for c in cases])
 
 
+def euler_solver():
+    """test_solvers.py:248-269 (TestEulerSolver.test_private_integration): system = tests/conf.py:418-434, y0 = [1, 6], tau = 1e-3, u = 2"""
+    import tests.test_physical_systems.test_solvers as ts
+
+    names, cases = params_of(ts.TestEulerSolver.test_private_integration, "expected_state")
+    out = []
+    for nsteps, expected in cases:
+        sol = ts.EulerSolver(nsteps=nsteps)
+        sol.set_system_equation(ts.system, ts.jacobian)
+        sol.set_initial_value(ts.TestEulerSolver._state, ts.TestEulerSolver._t)
+        sol.set_f_params(2)
+        got = sol.integrate(ts.TestEulerSolver._t + 1e-3)
+        assert sum(abs(got - expected)) < 1e-6
+        out.append(dict(nsteps=int(nsteps), y0=[float(v) for v in ts.TestEulerSolver._state], tau=1e-3, u=2.0, expected=[float(v) for v in expected],
+                        reference_result=[float(v) for v in got]))
+    return out
+
+
 def constraints():
     out = []
     for mod, cls_name, kind in ((tlc, "TestLimitConstraint", "limit"), (tsc, "TestSquaredConstraint", "squared")):
@@ -160,7 +179,8 @@ def wse_rewards():
 
 
 if __name__ == "__main__":
-    ka = dict(finite_qc=finite_qc(), finite_b6=finite_b6(), cont_qc=cont_qc(), poly_load=poly_load(), constraints=constraints(), wse_rewards=wse_rewards())
+    ka = dict(finite_qc=finite_qc(), finite_b6=finite_b6(), cont_qc=cont_qc(), poly_load=poly_load(), euler=euler_solver(), constraints=constraints(),
+              wse_rewards=wse_rewards())
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(ka, f)
     print({k: (len(v) if isinstance(v, list) else len(v["cases"])) for k, v in ka.items()},

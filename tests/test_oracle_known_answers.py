@@ -83,6 +83,15 @@ def test_polynomial_static_load_known_answers(oracle_lib):
         assert abs(sim.probe_mechanical_ode(c["omega"], pl["torque"]) - c["expected"]) < 1e-6  # abs_tol of the reference test
 
 
+@pytest.mark.parametrize("case", KA["euler"], ids=lambda c: f"nsteps{c['nsteps']}")
+def test_euler_solver_known_answers(oracle_lib, case):
+    """test_solvers.py:248-269: the oracle's Euler stepping (the code its motor integration runs) on the reference's test system;
+    the table value within the reference test's tolerance, the reference's own float result to round-off"""
+    got = oracle_lib.probe_euler(case["nsteps"], case["y0"], case["tau"], case["u"])
+    assert np.abs(got - np.array(case["expected"])).sum() < 1e-6
+    assert np.abs(got - np.array(case["reference_result"])).max() < 1e-13
+
+
 @pytest.mark.parametrize("case", KA["constraints"], ids=lambda c: f"{c['kind']}-{c['state']}")
 def test_constraint_truth_tables(oracle_lib, case):
     """test_limit_constraint.py:33-66, test_squared_constraint.py:25-99"""
