@@ -330,6 +330,14 @@ CASES = [
     C("permex_sc_ac_rk4", "Cont-SC-PermExDc-v0", "rk4", steps=1500, supply_ac=[42.0, 50.0, 0.7]),
     C("series_fin_cc_ac_interlock_rk4", "Finite-CC-SeriesDc-v0", "rk4", steps=2000, supply_ac=[230.0, 400.0, 2.5], converter=dict(interlocking_time=1e-6)),
     C("pmsm_cc_ac_rk4", "Cont-CC-PMSM-v0", "rk4", steps=1500, supply_ac=[230.0, 50.0, 4.0]),
+    # cross-feature combinations: supply x wrappers x load x converter family
+    C("eesm_cc_rc_dq_dead1_rk4", "Cont-CC-EESM-v0", "rk4", steps=1500, supply_rc=[300.0, 0.5, 2e-3], wrappers=[("DeadTime", 1), ("DqToAbc", "EESM")]),
+    C("dfim_fin_cc_rc_rk4", "Finite-CC-DFIM-v0", "rk4", steps=2000, supply_rc=[420.0, 1.0, 1e-3]),
+    C("extex_fin_cc_ac_rk4", "Finite-CC-ExtExDc-v0", "rk4", steps=2000, supply_ac=[42.0, 400.0, 1.0]),
+    C("scim_cc_extspeed_flux_dq_rk4", "Cont-CC-SCIM-v0", "rk4", steps=1500, ext_speed=[60.0, 15.0, 120.0],
+      wrappers=[("FluxObserver", None), ("DqToAbc", "SCIM")]),
+    C("pmsm_sc_rc_cossin_dq_euler3", "Cont-SC-PMSM-v0", "euler3", steps=1500, supply_rc=[420.0, 0.5, 4e-3],
+      wrappers=[("CosSin", ["epsilon", 0]), ("DqToAbc", "PMSM")]),
     # remaining DC family
     C("series_cc_rk4", "Cont-CC-SeriesDc-v0", "rk4", steps=1500),
     C("series_sc_dopri5", "Cont-SC-SeriesDc-v0", "dopri5", steps=1500),
