@@ -254,6 +254,28 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = sum(e.sim.launch_count for e in envs) - l0
     ms = ev0.elapsed_time(ev1)
+    # ---------------- N > 1 only: the sharded layout's ONE collective — a single NCCL all-gather of the packed (obs, ref, reward,
+    # terminated) buffer after every step (BASELINE.json north_star; SURVEY.md §8e asks for both figures) ----------------
+    ms_gather, gather_bytes = None, 0
+    if world > 1:
+        from gym_electric_motor_b200.distributed import PackedStepOutputs
+
+        packed = PackedStepOutputs(n, 14, 2, torch.float32, dev)
+        gather_bytes = packed.nbytes
+        gsim = envs[R - 1].sim
+        gsim.bind_outputs(*packed.local_views())  # the kernel writes straight into the packed buffer
+        for k in range(3):
+            envs[R - 1].step(pool[k % 8])
+            packed.gather_raw()
+        barrier()
+        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eg0.record()
+        for k in range(K):
+            envs[R - 1].step(pool[k % 8])
+            packed.gather_raw()
+        eg1.record()
+        barrier()
+        ms_gather = eg0.elapsed_time(eg1)
     # ---------------- one launch at a time: events around every launch, L2 flushed before it (reference figure) ----------------
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for k in range(K):
@@ -280,10 +302,10 @@ def main():
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, ms_hot, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_hot, t_e2e * 1e3, ms_gather or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_hot, ms_e2e = [float(x) for x in t.tolist()]
+    ms, ms_hot, ms_e2e, ms_gather = [float(x) for x in t.tolist()]
     if rank == 0:
         total_envs = n * world
         ms_per_step = ms / K
@@ -307,6 +329,11 @@ def main():
                             "note": "one launch at a time, CUDA events around each launch, 256 MiB L2 flush before it"},
             "wall_ms_timed_region": t_wall * 1e3,
         }
+        if world > 1:
+            line["with_all_gather"] = {"value": total_envs * K / (ms_gather * 1e-3), "unit": UNIT, "ms_per_step": ms_gather / K,
+                                       "bytes_per_rank_per_step": gather_bytes,
+                                       "note": "every step followed by ONE NCCL all_gather_into_tensor of the packed (obs, ref, reward, terminated) "
+                                               "buffer the kernel writes into; `value` above is the sharded layout without it (rank-local consumers)"}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_arm(65536, 0, 2, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,

@@ -48,6 +48,66 @@ def global_stats(reward, terminated):
     return float(t[0] / t[2]), int(t[1].item())
 
 
+class PackedStepOutputs:
+    """The ONE collective of the sharded layout (BASELINE.json north_star): every rank lets the step kernel write its
+    observation / next reference / reward / terminated directly into ONE contiguous byte buffer (the C-ABI's output tensors are
+    caller-owned), so that a single `all_gather_into_tensor` returns the aggregated batch of all ranks.
+
+        out = PackedStepOutputs(n_local, n_state, n_ref, dtype, device)
+        env.sim.bind_outputs(*out.local_views())          # the kernel writes straight into the packed buffer
+        env.step(actions); obs, ref, rew, term = out.gather()   # [world * n_local, ...] views, rank-major
+
+    Sections are 16-byte aligned (the kernel's vector stores need it).  Same n_local on every rank."""
+
+    def __init__(self, n_local, n_state, n_ref, dtype, device):
+        import torch
+        import torch.distributed as dist
+
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.n, self.n_state, self.n_ref, self.dtype = int(n_local), int(n_state), int(n_ref), dtype
+        isz = torch.empty((), dtype=dtype).element_size()
+        sizes = [self.n * n_state * isz, self.n * n_ref * isz, self.n * isz, self.n]
+        self.offsets, off = [], 0
+        for sz in sizes:
+            self.offsets.append(off)
+            off += (sz + 15) // 16 * 16
+        self.nbytes = off
+        self.local = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(self.world * self.nbytes, dtype=torch.uint8, device=device) if self.world > 1 else self.local
+
+    def _views(self, buf, base):
+        import torch
+
+        o = self.offsets
+        isz = torch.empty((), dtype=self.dtype).element_size()
+        obs = buf[base + o[0]: base + o[0] + self.n * self.n_state * isz].view(self.dtype).view(self.n, self.n_state)
+        ref = buf[base + o[1]: base + o[1] + self.n * self.n_ref * isz].view(self.dtype).view(self.n, self.n_ref)
+        rew = buf[base + o[2]: base + o[2] + self.n * isz].view(self.dtype)
+        term = buf[base + o[3]: base + o[3] + self.n]
+        return obs, ref, rew, term
+
+    def local_views(self):
+        return self._views(self.local, 0)
+
+    def gather(self):
+        """one NCCL (or gloo) all-gather of the packed buffer; returns per-field tensors [world, n_local, ...] (rank-major views)"""
+        import torch
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.local)
+        per = [self._views(self.gathered, r * self.nbytes) for r in range(self.world)]
+        return tuple(torch.stack([p[k] for p in per]) if self.world > 1 else per[0][k].unsqueeze(0) for k in range(4))
+
+    def gather_raw(self):
+        """the collective alone (no per-field re-assembly): what a consumer that reads the rank-major sections directly pays"""
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.local)
+        return self.gathered
+
+
 def all_gather_batch(*tensors):
     """Optional single all-gather of per-rank [n_local, ...] tensors into global [N, ...] tensors (same n_local on every
     rank).  For PMSM at N=2^20 this moves ~72 MB per step — several times the step itself; data-parallel

@@ -73,6 +73,17 @@ class VectorSim:
             self._out = out
         return out
 
+    def bind_outputs(self, obs, ref, reward, terminated):
+        """Let the step / reset launches write into caller-owned tensors (e.g. the sections of a packed all-gather buffer,
+        distributed.PackedStepOutputs).  Shapes, dtypes and device must match what `step` returns."""
+        exp = (self._shape(self.n_state), self._shape(self.n_ref), (self.n,), (self.n,))
+        for t, shp, dt in zip((obs, ref, reward, terminated), exp, (self.dtype, self.dtype, self.dtype, torch.uint8)):
+            if tuple(t.shape) != tuple(shp) or t.dtype != dt or t.device != self.device or not t.is_contiguous():
+                raise ValueError(f"output tensor mismatch: need {tuple(shp)} {dt} contiguous on {self.device}, got {tuple(t.shape)} {t.dtype} on {t.device}")
+            if t.data_ptr() % 16:
+                raise ValueError("output tensors must be 16-byte aligned")
+        self._reuse, self._out, self._out_ptrs = True, (obs, ref, reward, terminated), None
+
     def _as_action(self, action):
         if isinstance(action, torch.Tensor) and action.dtype == self.act_dtype and action.device == self.device and action.is_contiguous() \
                 and action.numel() == self.n * self.n_act:

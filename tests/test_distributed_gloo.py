@@ -52,7 +52,7 @@ WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, %r)
     import torch, torch.distributed as dist
-    from gym_electric_motor_b200.distributed import shard_envs, rank_world, global_stats, all_gather_batch
+    from gym_electric_motor_b200.distributed import shard_envs, rank_world, global_stats, all_gather_batch, PackedStepOutputs
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
     rank, world = rank_world()
     assert (rank, world) == (int(os.environ["RANK"]), 2)
@@ -63,6 +63,18 @@ WORKER = textwrap.dedent("""
     assert abs(mean - 4.5) < 1e-12 and n_term == 4, (mean, n_term)
     (g,) = all_gather_batch(reward.reshape(-1, 1))
     assert g.flatten().tolist() == [float(i) for i in range(10)]
+    # the single packed all-gather of (obs, ref, reward, terminated): sections 16-byte aligned, rank-major result
+    n_loc, n_state, n_ref = 5, 14, 2
+    out = PackedStepOutputs(n_loc, n_state, n_ref, torch.float32, torch.device("cpu"))
+    obs, ref, rew, trm = out.local_views()
+    assert all(t.data_ptr() %% 16 == 0 for t in (obs, ref, rew, trm)) and obs.shape == (5, 14) and trm.dtype == torch.uint8
+    obs.copy_(torch.arange(n_loc * n_state, dtype=torch.float32).reshape(n_loc, n_state) + 1000 * rank)
+    ref.fill_(rank + 0.5); rew.copy_(torch.arange(n_loc, dtype=torch.float32) - rank); trm.fill_(rank)
+    g_obs, g_ref, g_rew, g_trm = out.gather()
+    assert g_obs.shape == (2, 5, 14) and g_trm.shape == (2, 5)
+    for r in range(2):
+        assert torch.equal(g_obs[r], torch.arange(n_loc * n_state, dtype=torch.float32).reshape(n_loc, n_state) + 1000 * r)
+        assert (g_ref[r] == r + 0.5).all() and torch.equal(g_rew[r], torch.arange(n_loc, dtype=torch.float32) - r) and (g_trm[r] == r).all()
     dist.destroy_process_group()
     print("ok", rank)
 """) % ROOT
