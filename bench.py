@@ -276,33 +276,6 @@ def main():
         eg1.record()
         barrier()
         ms_gather = eg0.elapsed_time(eg1)
-        # the same exchange fused into the step kernel: peer-to-peer stores into every rank's buffer + a 4-byte all-reduce as fence
-        ms_p2p, p2p_err, p2p_ok = 0.0, "", torch.zeros(1, device=dev)
-        try:
-            from gym_electric_motor_b200.distributed import PeerGatherOutputs
-
-            peer = PeerGatherOutputs(envs[R - 2].sim)
-            for k in range(3):
-                envs[R - 2].step(pool[k % 8])
-                peer.fence()
-            barrier()
-            ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ep0.record()
-            for k in range(K):
-                envs[R - 2].step(pool[k % 8])
-                peer.fence()
-            ep1.record()
-            barrier()
-            ms_p2p = ep0.elapsed_time(ep1)
-            # every rank must see every rank's last reward slot identical to that rank's own copy
-            g_rew = peer.views()[2]
-            mine = g_rew[rank].clone()
-            allr = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allr, mine)
-            p2p_ok.fill_(float(all(torch.equal(g_rew[r], allr[r]) for r in range(world))))
-            peer.close()
-        except Exception as e:  # CUDA IPC may be unavailable in a sandbox: report, do not fail the bench
-            p2p_err = f"{type(e).__name__}: {e}"[:300]
     # ---------------- one launch at a time: events around every launch, L2 flushed before it (reference figure) ----------------
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for k in range(K):
@@ -329,11 +302,10 @@ def main():
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, ms_hot, t_e2e * 1e3, ms_gather or 0.0, ms_p2p if world > 1 else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_hot, t_e2e * 1e3, ms_gather or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(p2p_ok, op=dist.ReduceOp.MIN)
-    ms, ms_hot, ms_e2e, ms_gather, ms_p2p = [float(x) for x in t.tolist()]
+    ms, ms_hot, ms_e2e, ms_gather = [float(x) for x in t.tolist()]
     if rank == 0:
         total_envs = n * world
         ms_per_step = ms / K
@@ -362,13 +334,6 @@ def main():
                                        "bytes_per_rank_per_step": gather_bytes,
                                        "note": "every step followed by ONE NCCL all_gather_into_tensor of the packed (obs, ref, reward, terminated) "
                                                "buffer the kernel writes into; `value` above is the sharded layout without it (rank-local consumers)"}
-            if ms_p2p > 0 and not p2p_err:
-                line["with_fused_p2p_gather"] = {"value": total_envs * K / (ms_p2p * 1e-3), "unit": UNIT, "ms_per_step": ms_p2p / K,
-                                                 "verified_equal_on_all_ranks": bool(p2p_ok.item() == 1.0),
-                                                 "note": "the step kernel itself stores its outputs into every rank's gather buffer over NVLink "
-                                                         "(gemb200_set_peer_outputs, CUDA IPC); fence = one 4-byte all-reduce per step"}
-            else:
-                line["with_fused_p2p_gather"] = {"unavailable": p2p_err or "not measured"}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_arm(65536, 0, 2, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,

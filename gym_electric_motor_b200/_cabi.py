@@ -140,7 +140,7 @@ SYMBOLS = [
     "gemb200_destroy", "gemb200_reset", "gemb200_step", "gemb200_step_host", "gemb200_reset_host", "gemb200_rollout",
     "gemb200_get_ode_state", "gemb200_set_ode_state", "gemb200_get_reference", "gemb200_set_reference",
     "gemb200_checkpoint_size", "gemb200_checkpoint_save", "gemb200_checkpoint_load", "gemb200_launch_count",
-    "gemb200_kernel_time_begin", "gemb200_kernel_time_end", "gemb200_set_peer_outputs",
+    "gemb200_kernel_time_begin", "gemb200_kernel_time_end",
 ]
 
 
@@ -189,7 +189,6 @@ def load_library():
     lib.gemb200_checkpoint_size.restype = C.c_int64
     lib.gemb200_checkpoint_save.argtypes = [vp, vp]
     lib.gemb200_checkpoint_load.argtypes = [vp, vp]
-    lib.gemb200_set_peer_outputs.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.gemb200_launch_count.argtypes = [vp]
     lib.gemb200_launch_count.restype = C.c_int64
     lib.gemb200_kernel_time_begin.argtypes = [vp, vp]

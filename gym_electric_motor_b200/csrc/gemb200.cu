@@ -868,35 +868,6 @@ int gemb200_reset_host(gemb200_handle* h, const uint8_t* reset_mask, void* obs_o
   return GEMB200_OK;
 }
 
-int gemb200_set_peer_outputs(gemb200_handle* h, int32_t n_peers, void* const* obs, void* const* ref, void* const* reward, uint8_t* const* terminated) {
-  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
-  if (n_peers < 0 || n_peers > kMaxPeers) return fail(GEMB200_E_INVALID, "n_peers out of range");
-  if (n_peers > 0 && h->cfg.layout != GEMB200_LAYOUT_AOS) return fail(GEMB200_E_INVALID, "peer outputs need the row-per-env layout");
-  if (n_peers > 0 && (!obs || !reward || !terminated || (h->n_ref > 0 && !ref))) return fail(GEMB200_E_INVALID, "NULL peer pointer table");
-  DeviceGuard guard(h->cfg.device);
-  for (int q = 0; q < n_peers; ++q) {
-    cudaPointerAttributes at;
-    CUDA_TRY(cudaPointerGetAttributes(&at, obs[q]));
-    if (at.device != h->cfg.device) {
-      int can = 0;
-      CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->cfg.device, at.device));
-      if (!can) return fail(GEMB200_E_INVALID, "no peer-to-peer access between the two devices");
-      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(GEMB200_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
-      cudaGetLastError();  // clear the sticky "already enabled"
-    }
-  }
-  h->pf.n_peers = n_peers; h->pd.n_peers = n_peers;
-  for (int q = 0; q < kMaxPeers; ++q) {
-    const bool on = q < n_peers;
-    h->pf.peer_obs[q] = on ? (float*)obs[q] : nullptr;        h->pd.peer_obs[q] = on ? (double*)obs[q] : nullptr;
-    h->pf.peer_ref[q] = on && ref ? (float*)ref[q] : nullptr; h->pd.peer_ref[q] = on && ref ? (double*)ref[q] : nullptr;
-    h->pf.peer_rew[q] = on ? (float*)reward[q] : nullptr;     h->pd.peer_rew[q] = on ? (double*)reward[q] : nullptr;
-    h->pf.peer_term[q] = on ? terminated[q] : nullptr;        h->pd.peer_term[q] = on ? terminated[q] : nullptr;
-  }
-  return GEMB200_OK;
-}
-
 int gemb200_get_ode_state(gemb200_handle* h, double* ode_out, void* stream) {
   if (!h || !ode_out) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);

@@ -13,7 +13,6 @@ constexpr int kMaxState = 28;
 constexpr int kMaxRef = 4;
 constexpr int kMaxConstraints = 4;
 constexpr int kMaxStateOps = 4;
-constexpr int kMaxPeers = 7;  // other GPUs of an 8-GPU NVSwitch box
 constexpr int kMaxX = 6;  // real-typed ODE states per env (omega + motor states without the angle): SCIM 5
 
 // words of persistent state per env and their placement (shared by host and device code)
@@ -179,13 +178,6 @@ struct StepParams {
   real reset_obs_du[kMaxState];  // d reset_obs / d u_sup (supplies whose voltage at reset differs per env)
   real* sup;               // [2][n] RC supply: u_sup, 'has a previous call' flag (0 right after a reset); nullptr for the ideal supply
   real* obsv;              // [4][n] FluxObserver integrator (re, im, compensation terms); nullptr without one
-  // ---- fused all-gather (gemb200_set_peer_outputs): the outputs are ALSO stored into this rank's slot of every peer GPU's gather buffer
-  //      (NVLink P2P stores from inside the step kernel); row-per-env layout only ----
-  int32_t n_peers;
-  real* peer_obs[kMaxPeers];
-  real* peer_ref[kMaxPeers];
-  real* peer_rew[kMaxPeers];
-  uint8_t* peer_term[kMaxPeers];
   int32_t pf_dist;         // envs between a thread's env and the one it prefetches into L2 (0: off); ~ one wave of resident threads
   int32_t plain;           // 1: this configuration has the PLAIN shape (see step_kernel) -> specialised instantiation
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)

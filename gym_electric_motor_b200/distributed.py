@@ -108,71 +108,6 @@ class PackedStepOutputs:
         return self.gathered
 
 
-class PeerGatherOutputs:
-    """Fused step + all-gather over NVLink peer memory: every rank maps the gather buffers of all other ranks (CUDA IPC) and its step
-    kernel stores observation / reference / reward / terminated into its own slot of EVERY rank's buffer (`gemb200_set_peer_outputs`),
-    so no separate collective moves the data; `fence()` — a 4-byte all-reduce on the launch stream — is the only synchronisation.
-
-        out = PeerGatherOutputs(env.sim)        # collective constructor: exchanges IPC handles through torch.distributed
-        env.step(actions); out.fence(); obs, ref, rew, term = out.views()   # [world, n_local, ...], rank-major, on this GPU
-
-    Needs one process per GPU on one NVLink/NVSwitch node, the row-per-env layout and the same n_local on every rank."""
-
-    def __init__(self, sim):
-        import ctypes as C
-
-        import torch
-        import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
-
-        from . import _cabi as K
-
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.layout = PackedStepOutputs(sim.n, sim.n_state, sim.n_ref, sim.dtype, sim.device)  # section offsets / slot size only
-        nb = self.layout.nbytes
-        self.gathered = torch.zeros(self.world * nb, dtype=torch.uint8, device=sim.device)
-        sim.bind_outputs(*self.layout._views(self.gathered, self.rank * nb))  # own slot of the own buffer = the ordinary outputs
-        fn, args = reduce_tensor(self.gathered)
-        shared = [None] * self.world
-        dist.all_gather_object(shared, (fn, args))
-        self._peers = []  # mapped peer buffers (kept alive as long as this object)
-        tabs = [[], [], [], []]
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            pfn, pargs = shared[r]
-            t = pfn(*pargs)  # a uint8 tensor on the PEER's device, mapped into this process
-            self._peers.append(t)
-            base = t.data_ptr() + self.rank * nb
-            for k in range(4):
-                tabs[k].append(base + self.layout.offsets[k])
-        n_peers = len(self._peers)
-        arrs = [(C.c_void_p * max(n_peers, 1))(*tab) for tab in tabs]
-        K.check(sim._lib.gemb200_set_peer_outputs(sim._h, n_peers, arrs[0], arrs[1], arrs[2], arrs[3]), "gemb200_set_peer_outputs")
-        self._flag = torch.zeros(1, dtype=torch.float32, device=sim.device)
-        self._sim = sim
-        dist.barrier()
-
-    def fence(self):
-        """stream-ordered: when it completes on this rank, every rank's step kernel — and with it its peer stores — has completed"""
-        import torch.distributed as dist
-
-        dist.all_reduce(self._flag)
-
-    def views(self):
-        import torch
-
-        nb = self.layout.nbytes
-        per = [self.layout._views(self.gathered, r * nb) for r in range(self.world)]
-        return tuple(torch.stack([p[k] for p in per]) for k in range(4))
-
-    def close(self):
-        from . import _cabi as K
-
-        K.check(self._sim._lib.gemb200_set_peer_outputs(self._sim._h, 0, None, None, None, None), "gemb200_set_peer_outputs")
-        self._peers = []
-
-
 def all_gather_batch(*tensors):
     """Optional single all-gather of per-rank [n_local, ...] tensors into global [N, ...] tensors (same n_local on every
     rank).  For PMSM at N=2^20 this moves ~72 MB per step — several times the step itself; data-parallel

@@ -288,15 +288,6 @@ int gemb200_reset_host(gemb200_handle* h, const uint8_t* reset_mask, void* obs_o
 int gemb200_rollout(gemb200_handle* h, const void* actions, int32_t n_steps, void* obs_out, void* ref_out,
                     void* reward_out, uint8_t* terminated_out, void* stream);
 
-/* Fused all-gather for the sharded layout (one process per GPU): besides its own outputs, every step launch stores observation,
- * next reference, reward and terminated into this rank's slot of the gather buffers of `n_peers` other GPUs with NVLink peer-to-peer
- * stores from inside the kernel (no separate collective).  The pointers are device pointers in THIS process's address space that
- * map the peers' buffers (CUDA IPC; see gym_electric_motor_b200/distributed.py: PeerGatherOutputs), already offset to this rank's
- * slot; peer access is enabled here.  Row-per-env layout only; n_peers = 0 switches it off.  Completion on the peers is the caller's
- * business (e.g. a tiny all-reduce on the same stream after the step). */
-int gemb200_set_peer_outputs(gemb200_handle* h, int32_t n_peers, void* const* obs, void* const* ref, void* const* reward,
-                             uint8_t* const* terminated);
-
 /* OdeSolver.y / set_initial_value (physical_systems/solvers.py:4-76): ODE state as double [N][n_ode]
  * (AoS, device), angle unwrapped to (-pi, pi].  Used for checkpointing and oracle injection. */
 int gemb200_get_ode_state(gemb200_handle* h, double* ode_out, void* stream);
