@@ -164,6 +164,9 @@ static int validate(const gemb200_config* c) {
   if (c->supply_kind == GEMB200_SUPPLY_AC1 && !(c->supply_param[0] > 0)) return fail(GEMB200_E_INVALID, "AC supply needs a positive frequency");
   if (c->supply_kind == GEMB200_SUPPLY_RC && !(c->supply_param[0] > 0 && c->supply_param[1] > 0)) return fail(GEMB200_E_INVALID, "RC supply needs R > 0 and C > 0");
   if (c->n_constraints < 0 || c->n_constraints > GEMB200_MAX_CONSTRAINTS) return fail(GEMB200_E_INVALID, "n_constraints out of range");
+  for (int i = 0; i < c->n_constraints; ++i)
+    if (c->constraint_kind[i] != GEMB200_CONSTRAINT_LIMIT && c->constraint_kind[i] != GEMB200_CONSTRAINT_SQUARED) return fail(GEMB200_E_INVALID, "bad constraint_kind");
+  if (c->autoreset != GEMB200_AUTORESET_NONE && c->autoreset != GEMB200_AUTORESET_SAME_STEP) return fail(GEMB200_E_INVALID, "bad autoreset mode");
   Dims d;
   int rc = derive_dims(c, &d);
   if (rc) return rc;
@@ -195,6 +198,8 @@ static int validate(const gemb200_config* c) {
     if (c->ref_kind[r] >= GEMB200_REF_SINUS && !(c->ref_freq_lo[r] > 0 && c->ref_freq_hi[r] >= c->ref_freq_lo[r] && c->ref_amp_lo[r] >= 0))
       return fail(GEMB200_E_INVALID, "bad amplitude / frequency range of a periodic reference generator");
   }
+  for (int j = 0; j < d.n_obs; ++j)
+    if (c->reward_weight[j] != 0.0 && !(c->state_length[j] > 0)) return fail(GEMB200_E_INVALID, "state_length must be positive for every weighted state");
   for (int j = 0; j < d.n_state; ++j)
     if (!(c->limits[j] != 0.0) && !(c->motor_kind == GEMB200_MOTOR_SHUNT_DC && j == 6)) return fail(GEMB200_E_INVALID, "limits must be non-zero");
   const double j_total = c->load_param[GEMB200_LP_J_LOAD] + c->motor_param[GEMB200_MP_J_ROTOR];

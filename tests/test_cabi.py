@@ -106,3 +106,39 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
     env = gem.make("Cont-CC-PMSM-v0", num_envs=4)
     with pytest.raises(K.GemB200Error):
         env.reset()
+
+
+def _create_rc(lib, cfg):
+    h = C.c_void_p()
+    rc = lib.gemb200_create(C.byref(cfg), C.byref(h))
+    if rc == 0:  # a GPU is present: the handle is real
+        lib.gemb200_destroy(h)
+    return rc, lib.gemb200_last_error().decode()
+
+
+def test_every_registered_id_passes_validation(lib):
+    """gemb200_create validates before it touches CUDA: without a GPU every registered id must get past validation and fail
+    only at the CUDA stage (never E_INVALID / E_ABI); with a GPU it simply succeeds."""
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200.envs import env_ids
+
+    for env_id in env_ids():
+        cfg = gem.make(env_id, num_envs=8).build_config()
+        rc, msg = _create_rc(lib, cfg)
+        assert rc in (0, K.E_CUDA), (env_id, rc, msg)
+
+
+def test_every_golden_config_passes_validation(lib):
+    from helpers import config_from_meta, golden_names, load_golden
+
+    for name in golden_names():
+        g = load_golden(name)
+        for dtype in (K.F64, K.F32):
+            # dopri5 goldens: the device runs them as RK4 sub-stepping (DESIGN.md); the oracle-only solver id must be rejected
+            dopri = g["meta"]["case"]["solver"] == "dopri5"
+            if dopri:
+                rc, msg = _create_rc(lib, config_from_meta(g["meta"], n_envs=4, dtype=dtype))
+                assert rc == K.E_INVALID and "solver_kind" in msg
+            cfg = config_from_meta(g["meta"], n_envs=4, dtype=dtype, solver="rk4x2" if dopri else None)
+            rc, msg = _create_rc(lib, cfg)
+            assert rc in (0, K.E_CUDA), (name, rc, msg)
