@@ -157,13 +157,15 @@ def cpu_arm(n_envs, steps, warmup, budget_s=None):
     ora.reset()
     rng = np.random.default_rng(0)
     acts = rng.uniform(-1, 1, size=(4, n_envs, 3))
-    for k in range(warmup):
-        ora.step(acts[k % 4])
+    chunk = 16  # steps per rollout call: the oracle's worker threads persist over a call (two barriers per step, no thread creation)
+    for k in range(max(1, warmup // chunk)):
+        ora.rollout(acts, chunk)
     t0 = time.perf_counter()
     done = 0
     while True:
-        ora.step(acts[done % 4])
-        done += 1
+        c = chunk if budget_s is not None else min(chunk, steps - done)
+        ora.rollout(acts, c)
+        done += c
         el = time.perf_counter() - t0
         if budget_s is None:
             if done >= steps:

@@ -1282,6 +1282,44 @@ void gem_oracle_step(gem_oracle* o, const void* action, double* obs, double* ref
   free(th); free(jobs);
 }
 
+/* K consecutive env.step calls with a pool of `n_sets` prepared action arrays used round-robin (set k % n_sets for step k; each set
+ * is [N][n_act] doubles or [N][n_slots] int32, `set_stride_bytes` apart).  Same arithmetic and counters as K calls of gem_oracle_step;
+ * the difference is purely mechanical: the worker threads live for the whole rollout and meet at two barriers per step instead of
+ * being created and joined every step — what a CPU user with many cores would do, and what bench.py's CPU arm times.  Outputs hold
+ * the last step's values. */
+typedef struct { gem_oracle* o; const char* actions; size_t stride; int n_sets, K, tid; double* obs; double* ref; double* rew; uint8_t* term;
+                 int64_t lo, hi; pthread_barrier_t* bar; } roll_t;
+static void* roll_worker(void* arg) {
+  roll_t* j = (roll_t*)arg;
+  for (int k = 0; k < j->K; ++k) {
+    if (j->tid == 0) { j->o->gstep += 1; j->o->n_steps += 1; }
+    if (j->bar) pthread_barrier_wait(j->bar); /* the counters of step k are visible to every worker */
+    const void* act = j->actions + (size_t)(k % j->n_sets) * j->stride;
+    for (int64_t i = j->lo; i < j->hi; ++i) step_one(j->o, i, act, j->obs, j->ref, j->rew, j->term);
+    if (j->bar) pthread_barrier_wait(j->bar); /* nobody is still inside step k when the counters move on */
+  }
+  return NULL;
+}
+void gem_oracle_rollout(gem_oracle* o, const void* actions, int64_t set_stride_bytes, int n_sets, int n_steps, double* obs, double* ref_next,
+                        double* rew, uint8_t* term, int nthreads) {
+  int64_t n = o->cfg.n_envs;
+  if (nthreads > n) nthreads = (int)n;
+  if (nthreads < 1) nthreads = 1;
+  if (n_sets < 1 || n_steps < 1) return;
+  pthread_barrier_t bar;
+  if (nthreads > 1) pthread_barrier_init(&bar, NULL, (unsigned)nthreads);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+  roll_t* jobs = (roll_t*)malloc(sizeof(roll_t) * nthreads);
+  for (int t = 0; t < nthreads; ++t)
+    jobs[t] = (roll_t){o, (const char*)actions, (size_t)set_stride_bytes, n_sets, n_steps, t, obs, ref_next, rew, term,
+                       n * t / nthreads, n * (t + 1) / nthreads, nthreads > 1 ? &bar : NULL};
+  for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, roll_worker, &jobs[t]);
+  roll_worker(&jobs[0]);
+  for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+  if (nthreads > 1) pthread_barrier_destroy(&bar);
+  free(th); free(jobs);
+}
+
 void gem_oracle_get_ode_state(const gem_oracle* o, double* out) {
   for (int64_t i = 0; i < o->cfg.n_envs; ++i) memcpy(out + i * o->n_ode, o->env[i].ode, sizeof(double) * o->n_ode);
 }

@@ -35,6 +35,7 @@ def lib():
         _lib.gem_oracle_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
         _lib.gem_oracle_reset.argtypes = [C.c_void_p] * 4
         _lib.gem_oracle_step.argtypes = [C.c_void_p] * 6 + [C.c_int]
+        _lib.gem_oracle_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int]
         for n in ("get_ode_state", "set_ode_state", "get_reference", "set_reference"):
             getattr(_lib, "gem_oracle_" + n).argtypes = [C.c_void_p, C.c_void_p]
         _lib.gem_oracle_get_ref_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -97,6 +98,18 @@ class Oracle:
         rew = np.zeros(self.n)
         term = np.zeros(self.n, dtype=np.uint8)
         self._lib.gem_oracle_step(self._h, _p(a), _p(obs), _p(ref), _p(rew), _p(term), self.nthreads)
+        return obs, ref, rew, term
+
+    def rollout(self, action_pool, n_steps):
+        """n_steps consecutive steps, step k using action_pool[k % len(action_pool)]; returns the last step's outputs.  Identical results
+        to n_steps calls of step(); the worker threads persist over the rollout (what bench.py's CPU arm times)."""
+        dt = np.int32 if self.finite else np.float64
+        pool = np.ascontiguousarray(np.asarray(action_pool, dtype=dt).reshape(len(action_pool), self.n, self.n_act))
+        obs = np.zeros((self.n, self.n_state))
+        ref = np.zeros((self.n, self.n_ref))
+        rew = np.zeros(self.n)
+        term = np.zeros(self.n, dtype=np.uint8)
+        self._lib.gem_oracle_rollout(self._h, _p(pool), pool.strides[0], pool.shape[0], int(n_steps), _p(obs), _p(ref), _p(rew), _p(term), self.nthreads)
         return obs, ref, rew, term
 
     def get_ode_state(self):
