@@ -255,12 +255,17 @@ class _PeriodicReferenceGenerator(SubepisodedReferenceGenerator):
         self._amplitude_range = np.clip(self._amplitude_range, 0, (self._limit_margin[1] - self._limit_margin[0]) / 2)
         self._offset_range = np.clip(self._offset_range, self._limit_margin[0], self._limit_margin[1])
 
+    @staticmethod
+    def _pair(value_range):
+        """a number is a fixed value, a pair is a uniform range (SubepisodedReferenceGenerator._get_current_value :102-119)"""
+        if np.ndim(value_range) == 0:
+            return float(value_range), float(value_range)
+        return float(value_range[0]), float(value_range[1])
+
     def slots(self):
-        fr = self._frequency_range
-        freq = (float(fr), float(fr)) if type(fr) in (int, float) else (float(fr[0]), float(fr[1]))
         return [dict(kind=self.KIND, state=self._physical_system.state_positions[self._reference_state], margin=self._limit_margin,
-                     amp=(float(self._amplitude_range[0]), float(self._amplitude_range[1])), freq=freq,
-                     off=(float(self._offset_range[0]), float(self._offset_range[1])), length=self._length_range())]
+                     amp=self._pair(self._amplitude_range), freq=self._pair(self._frequency_range), off=self._pair(self._offset_range),
+                     length=self._length_range())]
 
 
 class SinusoidalReferenceGenerator(_PeriodicReferenceGenerator):

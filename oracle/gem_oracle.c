@@ -311,6 +311,11 @@ static double mechanical_ode(const gem_oracle* o, double omega, double tq, doubl
   return (tq - static_torque) / o->j_total;
 }
 
+/* RCVoltageSupply.system_equation voltage_supplies.py:104-113: d u_sup/dt = ((u_0 - u_sup) / R - i_sup) / C, written over the common
+ * denominator; AC1PhaseSupply.get_voltage :163-166: sqrt(2) u_nominal sin(2 pi f t + phi) */
+static double rc_supply_rhs(double u_sup, double u_0, double i_sup, double r, double cap) { return (u_0 - u_sup - r * i_sup) / (r * cap); }
+static double ac1_voltage(double u_nominal, double f, double phi, double t) { return sqrt(2.0) * u_nominal * sin(2 * M_PI * f * t + phi); }
+
 /* SCMLSystem._system_equation physical_systems.py:205-236 */
 static void system_equation(const gem_oracle* o, const double* y, const double* u, double* dy, double g) {
   double tq = torque(o, y + 1);
@@ -723,11 +728,11 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
     }
     double i_sup = conv_i_sup(o, e, i_in);    /* :507 */
     if (c->supply_kind == GEMB200_SUPPLY_AC1) /* AC1PhaseSupply.get_voltage(self._t) :163-166: the step's START time for all segments */
-      u_sup = sqrt(2.0) * c->u_sup * sin(2 * M_PI * c->supply_param[0] * t0 + e->ac_phase);
+      u_sup = ac1_voltage(c->u_sup, c->supply_param[0], e->ac_phase, t0);
     if (c->supply_kind == GEMB200_SUPPLY_RC) { /* RCVoltageSupply.get_voltage(self._t, i_sup) :115-123: one Euler step from the previous
                                                   call's time to this step's start time; a second segment sees dt = 0 */
       if (seg == 0) {
-        if (e->rc_started) e->u_rc += (c->u_sup - e->u_rc - c->supply_param[0] * i_sup) / (c->supply_param[0] * c->supply_param[1]) * c->tau;
+        if (e->rc_started) e->u_rc += rc_supply_rhs(e->u_rc, c->u_sup, i_sup, c->supply_param[0], c->supply_param[1]) * c->tau;
         e->rc_started = 1;
       }
       u_sup = e->u_rc;
@@ -849,7 +854,7 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
   if (c->supply_kind == GEMB200_SUPPLY_AC1) { /* AC1PhaseSupply.reset :157-161 */
     e->ac_phase = c->supply_param[1];
     if (c->supply_param[2] == 0.0) { uint32_t r[4]; rng4(o, e - o->env, STREAM_SUPPLY, r); e->ac_phase = u01(r[0]) * 2 * M_PI; }
-    u_sup0 = sqrt(2.0) * c->u_sup * sin(e->ac_phase);
+    u_sup0 = ac1_voltage(c->u_sup, c->supply_param[0], e->ac_phase, 0.0);
   }
   for (int j = 0; j < 6; ++j) u_abc[j] *= u_sup0;
   e->t = 0; e->k = 0;
@@ -1065,6 +1070,14 @@ static void switch_generator(const gem_oracle* o, env_t* e, int64_t idx, int r, 
   e->sw_k[r] = 0;
 }
 
+/* one step of the clipped random walk, wiener_process_reference_generator.py:35-40 (laplace_process_reference_generator.py:29-36 alike) */
+static double walk_next(const gemb200_config* c, int g, double value, double increment) {
+  double v = value + increment;
+  if (v > c->ref_margin_hi[g]) v = c->ref_margin_hi[g];
+  if (v < c->ref_margin_lo[g]) v = c->ref_margin_lo[g];
+  return v;
+}
+
 static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_reset) {
   const gemb200_config* c = &o->cfg;
   uint32_t rw[4], rs[4], rs2[4], rlap[4];
@@ -1125,10 +1138,7 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
       double rad = sqrt(-2.0 * log(u1));
       z = (r & 1) ? rad * sin(2 * M_PI * u2) : rad * cos(2 * M_PI * u2);
     }
-    double v = e->ref_value[r] + e->ref_sigma[r] * z; /* :35-40 */
-    if (v > c->ref_margin_hi[g]) v = c->ref_margin_hi[g];
-    if (v < c->ref_margin_lo[g]) v = c->ref_margin_lo[g];
-    e->ref_value[r] = v;
+    e->ref_value[r] = walk_next(c, g, e->ref_value[r], e->ref_sigma[r] * z);
     e->ref_left[r] -= 1;
   }
 }
@@ -1189,21 +1199,20 @@ void gem_oracle_reset(gem_oracle* o, const uint8_t* mask, double* obs, double* r
   }
 }
 
-static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, double* ref_next, double* rew, uint8_t* term) {
-  env_t* e = o->env + i;
-  double st[GEMB200_MAX_STATE], ref_full[GEMB200_MAX_STATE];
-  const double* af = o->cfg.finite ? NULL : (const double*)action + i * o->n_act;
-  const int32_t* ai = o->cfg.finite ? (const int32_t*)action + i * o->n_act : NULL;
-  /* physical-system wrappers (core.py:266-267): DeadTimeProcessor and DqToAbcActionProcessor in either order */
-  double abuf[GEMB200_MAX_ACT] = {0, 0, 0, 0, 0, 0};
-  int32_t ibuf[2] = {0, 0};
+/* physical-system wrappers on the ACTION side (core.py:266-267): DeadTimeProcessor and DqToAbcActionProcessor in either order.
+ * In: the caller's action of env e (af or ai); out: the action the inner SCMLSystem sees (pointers redirected to abuf / ibuf). */
+static void wrap_action(gem_oracle* o, env_t* e, const double** af_io, const int32_t** ai_io, double* abuf, int32_t* ibuf) {
+  const double* af = *af_io;
+  const int32_t* ai = *ai_io;
+  for (int j = 0; j < GEMB200_MAX_ACT; ++j) abuf[j] = 0.0;
+  ibuf[0] = ibuf[1] = 0;
   const gemb200_config* c = &o->cfg;
   const int slot = c->dead_time_steps > 0 ? (int)((o->n_steps - 1) % (uint64_t)c->dead_time_steps) : 0;
   if (c->finite) {
     for (int j = 0; j < o->n_act; ++j) ibuf[j] = ai[j];
     if (c->dead_time_steps > 0) /* dead_time_processor.py:80-90: apply the oldest action, store the new one */
       for (int j = 0; j < o->n_act; ++j) { int32_t old = (int32_t)e->fifo[slot][j]; e->fifo[slot][j] = ibuf[j]; ibuf[j] = old; }
-    ai = ibuf;
+    *ai_io = ibuf;
   } else {
     int na = o->n_act;
     for (int j = 0; j < na; ++j) abuf[j] = af[j];
@@ -1232,8 +1241,18 @@ static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, 
     }
     if (c->dead_time_steps > 0 && !c->dead_time_outer)
       for (int j = 0; j < na; ++j) { double old = e->fifo[slot][j]; e->fifo[slot][j] = abuf[j]; abuf[j] = old; }
-    af = abuf;
+    *af_io = abuf;
   }
+}
+
+static void step_one(gem_oracle* o, int64_t i, const void* action, double* obs, double* ref_next, double* rew, uint8_t* term) {
+  env_t* e = o->env + i;
+  double st[GEMB200_MAX_STATE], ref_full[GEMB200_MAX_STATE];
+  const double* af = o->cfg.finite ? NULL : (const double*)action + i * o->n_act;
+  const int32_t* ai = o->cfg.finite ? (const int32_t*)action + i * o->n_act : NULL;
+  double abuf[GEMB200_MAX_ACT];
+  int32_t ibuf[2];
+  wrap_action(o, e, &af, &ai, abuf, ibuf);
   simulate(o, e, af, ai, st);                                   /* core.py:344 */
   apply_state_ops(o, e, i, st, 0, 0);                           /* wrappers' simulate() */
   memset(ref_full, 0, sizeof(ref_full));
@@ -1358,6 +1377,29 @@ int gem_oracle_probe_set_action(gem_oracle* o, const double* act_f, const int32_
 void gem_oracle_probe_convert(gem_oracle* o, const double* i_out, double t, double* u_out) { conv_convert(o, o->env, i_out, t, u_out); }
 void gem_oracle_probe_conv_reset(gem_oracle* o, double* u_out) { conv_reset(o, o->env, u_out); }
 double gem_oracle_probe_mechanical_ode(gem_oracle* o, double omega, double tq) { return mechanical_ode(o, omega, tq, 0.0); }
+/* ExternalSpeedLoad: g = speed_profile(t + tau_load), one entry of the host-tabulated profile */
+double gem_oracle_probe_mechanical_ode_ext(gem_oracle* o, double omega, double tq, double g) { return mechanical_ode(o, omega, tq, g); }
+double gem_oracle_probe_rc_supply_rhs(double u_sup, double u_0, double i_sup, double r, double cap) { return rc_supply_rhs(u_sup, u_0, i_sup, r, cap); }
+double gem_oracle_probe_ac1_voltage(double u_nominal, double f, double phi, double t) { return ac1_voltage(u_nominal, f, phi, t); }
+/* the Wiener / Laplace walk of parameter entry g from `start` with the given (already scaled) increments */
+void gem_oracle_probe_walk(const gem_oracle* o, int g, double start, const double* increments, int n, double* out) {
+  double v = start;
+  for (int k = 0; k < n; ++k) { v = walk_next(&o->cfg, g, v, increments[k]); out[k] = v; }
+}
+/* the action-side wrappers of env 0 (dead-time FIFO, dq -> abc) exactly as step_one runs them, counted as one more step call; returns the
+ * number of values written: the action the inner system would see */
+int gem_oracle_probe_wrap_action(gem_oracle* o, const double* act_f, const int32_t* act_i, double* out_f, int32_t* out_i) {
+  double abuf[GEMB200_MAX_ACT];
+  int32_t ibuf[2];
+  const double* af = o->cfg.finite ? NULL : act_f;
+  const int32_t* ai = o->cfg.finite ? act_i : NULL;
+  o->n_steps += 1;
+  wrap_action(o, o->env, &af, &ai, abuf, ibuf);
+  if (o->cfg.finite) { for (int j = 0; j < o->n_act; ++j) out_i[j] = ai[j]; return o->n_act; }
+  const int na = o->cfg.action_dq == 3 ? 6 : (o->cfg.action_dq ? (o->cfg.motor_kind == GEMB200_MOTOR_EESM ? 4 : 3) : o->n_act);
+  for (int j = 0; j < na; ++j) out_f[j] = af[j];
+  return na;
+}
 double gem_oracle_probe_constraints(gem_oracle* o, const double* s) { return check_constraints(o, s); }
 double gem_oracle_probe_reward(gem_oracle* o, const double* s, const double* ref_full, double violation) { return reward(o, s, ref_full, violation); }
 /* EulerSolver known answers (tests/test_physical_systems/test_solvers.py:248-269): the stepping scheme above on the reference's test

@@ -45,6 +45,15 @@ def lib():
         _lib.gem_oracle_probe_conv_reset.argtypes = [C.c_void_p, C.c_void_p]
         _lib.gem_oracle_probe_mechanical_ode.argtypes = [C.c_void_p, C.c_double, C.c_double]
         _lib.gem_oracle_probe_mechanical_ode.restype = C.c_double
+        _lib.gem_oracle_probe_mechanical_ode_ext.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        _lib.gem_oracle_probe_mechanical_ode_ext.restype = C.c_double
+        _lib.gem_oracle_probe_rc_supply_rhs.argtypes = [C.c_double] * 5
+        _lib.gem_oracle_probe_rc_supply_rhs.restype = C.c_double
+        _lib.gem_oracle_probe_ac1_voltage.argtypes = [C.c_double] * 4
+        _lib.gem_oracle_probe_ac1_voltage.restype = C.c_double
+        _lib.gem_oracle_probe_walk.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+        _lib.gem_oracle_probe_wrap_action.argtypes = [C.c_void_p] * 5
+        _lib.gem_oracle_probe_wrap_action.restype = C.c_int
         _lib.gem_oracle_probe_constraints.argtypes = [C.c_void_p, C.c_void_p]
         _lib.gem_oracle_probe_constraints.restype = C.c_double
         _lib.gem_oracle_probe_reward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
@@ -160,6 +169,26 @@ class Oracle:
     def probe_mechanical_ode(self, omega, torque):
         return self._lib.gem_oracle_probe_mechanical_ode(self._h, float(omega), float(torque))
 
+    def probe_mechanical_ode_ext(self, omega, torque, profile_value):
+        return self._lib.gem_oracle_probe_mechanical_ode_ext(self._h, float(omega), float(torque), float(profile_value))
+
+    def probe_walk(self, entry, start, increments):
+        inc = np.ascontiguousarray(increments, dtype=np.float64)
+        out = np.zeros(len(inc))
+        self._lib.gem_oracle_probe_walk(self._h, int(entry), float(start), _p(inc), len(inc), _p(out))
+        return out
+
+    def probe_wrap_action(self, action):
+        """the action-side wrappers (dead-time FIFO, dq -> abc) of env 0 as one more step call; returns the inner system's action"""
+        out_f, out_i = np.zeros(8), np.zeros(2, dtype=np.int32)
+        if self.finite:
+            a = np.ascontiguousarray(np.atleast_1d(action), dtype=np.int32)
+            n = self._lib.gem_oracle_probe_wrap_action(self._h, None, _p(a), _p(out_f), _p(out_i))
+            return out_i[:n].copy()
+        a = np.ascontiguousarray(np.atleast_1d(action), dtype=np.float64)
+        n = self._lib.gem_oracle_probe_wrap_action(self._h, _p(a), None, _p(out_f), _p(out_i))
+        return out_f[:n].copy()
+
     def probe_constraints(self, state):
         s = np.zeros(32)
         s[: len(state)] = state
@@ -184,6 +213,14 @@ def probe_euler(nsteps, y0, dt, u):
     out = np.zeros(2)
     lib().gem_oracle_probe_euler(int(nsteps), _p(y0), float(dt), float(u), _p(out))
     return out
+
+
+def probe_rc_supply_rhs(u_sup, u_0, i_sup, r, c):
+    return lib().gem_oracle_probe_rc_supply_rhs(float(u_sup), float(u_0), float(i_sup), float(r), float(c))
+
+
+def probe_ac1_voltage(u_nominal, f, phi, t):
+    return lib().gem_oracle_probe_ac1_voltage(float(u_nominal), float(f), float(phi), float(t))
 
 
 def philox(counter, key):

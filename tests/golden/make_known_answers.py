@@ -12,6 +12,12 @@ by hand.  Sources:
   tests/test_physical_systems/test_solvers.py:248-269 (EulerSolver one-step / n-step known answers on tests/conf.py:418-434)
   tests/test_constraints/test_limit_constraint.py:33-66, test_squared_constraint.py:25-99 (truth tables)
   tests/test_reward_functions/test_weighted_sum_of_errors.py:150-218 (reward cases)
+  tests/test_physical_system_wrappers/test_dq_to_abc_action_processor.py:27-53 (dq -> abc known answers, advanced angle)
+  tests/test_physical_system_wrappers/test_dead_time_processor.py:28-75 (FIFO protocol: [reset_action] * steps + actions)
+  tests/test_physical_systems/test_voltage_supplies.py:86-97 (RC supply system equation), :141-163 (AC1PhaseSupply.get_voltage)
+  tests/test_physical_systems/test_mechanical_loads.py:36-42, :281-290 (ExternalSpeedLoad.mechanical_ode, sawtooth profile)
+  tests/test_reference_generators/test_reference_generators.py:540-627 (Sawtooth / Sinusoidal / Step / Triangular sub-episodes with the
+      tests' fixed random draws: uniform -> 0.25, triangular -> 0.45, testing_utils.py:586-606)
 """
 import json
 import os
@@ -129,6 +135,26 @@ def poly_load():
                 cases=[dict(omega=float(c[0]), expected=float(c[1])) for c in cases])
 
 
+def poly_load_formula():
+    """test_load.py:44-91 (test_polynomial_load): default and parametrised load, omega in {-10, 0, 10}, torque in {-3, 0, 5}; the expected
+    value is the test's own closed form sign(omega) (c omega^2 + b |omega| + a), replayed against the reference"""
+    import tests.test_physical_systems.test_load as tlo
+
+    tlo.test_polynomial_load()
+    out = []
+    for load in (tl.PolynomialStaticLoad(), tl.PolynomialStaticLoad(load_parameter=tlo.load_parameter["parameter"])):
+        load.set_j_rotor(tlo.load_parameter["j_rot_load"])
+        for omega in (-10, 0, 10):
+            t_l = float(np.sign(omega) * (load._c * omega ** 2 + load._b * abs(omega) + load._a))
+            assert load._static_load(omega) == t_l
+            for torque in (-3, 0, 5):
+                exp = (torque - t_l) / load.j_total
+                assert load.mechanical_ode(0, np.array([omega]), torque) == np.array([exp])
+                out.append(dict(a=float(load._a), b=float(load._b), c=float(load._c), j_load=float(load.load_parameter["j_load"]),
+                                j_rotor=float(tlo.load_parameter["j_rot_load"]), omega=float(omega), torque=float(torque), expected=float(exp)))
+    return out
+
+
 def euler_solver():
     """test_solvers.py:248-269 (TestEulerSolver.test_private_integration): system = tests/conf.py:418-434, y0 = [1, 6], tau = 1e-3, u = 2"""
     import tests.test_physical_systems.test_solvers as ts
@@ -178,10 +204,191 @@ def wse_rewards():
     return out
 
 
+def dq_to_abc():
+    """the three (dq action, physical state [omega, epsilon, i], abc action) vectors; DummyPhysicalSystem has tau = 1 (testing_utils.py:132-137),
+    the PMSM default p = 3, angle advance 0.5 (dq_to_abc_action_processor.py:69, :87-89).  Replayed against the reference first."""
+    import tests.test_physical_system_wrappers.test_dq_to_abc_action_processor as td
+    import gym_electric_motor as gem
+
+    names, cases = params_of(td.TestDqToAbcActionProcessor.test_simulate, "dq_action")
+    out = []
+    for c in cases:
+        d = dict(zip(names, c))
+        ps_ = td.DummyPhysicalSystem(state_names=["omega", "epsilon", "i"])
+        ps_.electrical_motor = gem.physical_systems.PermanentMagnetSynchronousMotor()
+        proc = gem.physical_system_wrappers.DqToAbcActionProcessor.make("PMSM", physical_system=ps_)
+        proc.reset()
+        proc._state = d["state"]
+        proc.simulate(d["dq_action"])
+        assert all(np.isclose(ps_.action, d["abc_action"]))
+        out.append(dict(dq_action=[float(v) for v in d["dq_action"]], omega=float(d["state"][0]), epsilon=float(d["state"][1]), tau=float(ps_.tau),
+                        p=float(ps_.electrical_motor.motor_parameter["p"]), angle_advance=float(proc._angle_advance),
+                        expected=[float(v) for v in d["abc_action"]], reference_result=[float(v) for v in ps_.action]))
+    return out
+
+
+def dead_time():
+    """every (steps, action space, action sequence) combination of test_execution; expected = [reset_action] * steps + actions"""
+    import tests.test_physical_system_wrappers.test_dead_time_processor as tdt
+    import gym_electric_motor as gem
+
+    f = tdt.TestDeadTimeProcessor.test_execution
+    _, procs = params_of(f, "unset_processor")
+    names, cases = params_of(f, "action_space")
+    out = []
+    for proc in procs:
+        steps = int(proc.dead_time)
+        for c in cases:
+            d = dict(zip(names, c))
+            ps_ = tdt.DummyPhysicalSystem()
+            ps_._action_space = d["action_space"]
+            pr = gem.physical_system_wrappers.DeadTimeProcessor(steps=steps)
+            pr.set_physical_system(ps_)
+            pr.reset()
+            expected = [d["reset_action"]] * steps + list(d["actions"])
+            seen = []
+            for i, a in enumerate(d["actions"]):
+                pr.simulate(a)
+                assert np.all(np.asarray(ps_.action) == np.asarray(expected[i]))
+                seen.append(np.asarray(ps_.action, dtype=float).ravel().tolist())
+            kind = type(d["action_space"]).__name__
+            out.append(dict(steps=steps, space=kind, actions=[np.asarray(a, dtype=float).ravel().tolist() for a in d["actions"]], applied=seen))
+    return out
+
+
+def supplies():
+    """RC: the (u_sup, u_0, i_sup, R, C) -> du/dt literals of test_system_equation, parsed from the test's source; AC1: the parameter sets and
+    times of test_get_voltage evaluated by the reference (the reference test itself is executed first so the values are known to satisfy it)."""
+    import ast
+    import inspect
+    import textwrap
+
+    import tests.test_physical_systems.test_voltage_supplies as tv
+
+    tv.TestRCVoltageSupply().test_system_equation()
+    tv.TestAC1PhaseSupply().test_get_voltage()
+    rc = []
+    tree = ast.parse(textwrap.dedent(inspect.getsource(tv.TestRCVoltageSupply.test_system_equation)))
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Assert) and isinstance(node.test, ast.Compare) and isinstance(node.test.left, ast.Call) \
+                and not isinstance(node.test.comparators[0], ast.Call):
+            t, u, u0, i_sup, r, c = [ast.literal_eval(a) for a in node.test.left.args]
+            expected = eval(compile(ast.Expression(node.test.comparators[0]), "<expected>", "eval"))
+            assert tv.vs.RCVoltageSupply().system_equation(t, u, u0, i_sup, r, c) == expected
+            rc.append(dict(u_sup=float(u[0]), u_0=float(u0), i_sup=float(i_sup), R=float(r), C=float(c), expected=float(expected)))
+    assert len(rc) == 3
+    ac = []
+    for par, times in ((dict(frequency=1, phase=0), [0, 1, 2, 1 / 4, 5 / 4, 9 / 4, 3 / 4, 7 / 4, 11 / 4]),           # :146-158
+                       (dict(frequency=36, phase=0.5), [1 / (2 * np.pi), 2 / (2 * np.pi), 3 / (2 * np.pi)])):       # :160-163
+        sup = tv.vs.AC1PhaseSupply(supply_parameter=par)
+        for t in times:
+            ac.append(dict(u_nominal=float(sup.u_nominal), frequency=float(par["frequency"]), phase=float(par["phase"]), t=float(t),
+                           expected=float(sup.get_voltage(t)[0])))
+    # the hand-calculated literals of :161-163 must be among them
+    assert np.allclose([a["expected"] for a in ac[-3:]], [-303.058731, -78.381295, 323.118651])
+    return dict(rc=rc, ac1=ac)
+
+
+def ext_speed_load():
+    import tests.test_physical_systems.test_mechanical_loads as tm
+
+    names, cases = params_of(tm.TestExtSpeedLoad.test_mechanical_ode, "expected_result")
+    load = tm.ExternalSpeedLoad(speed_profile=tm.speed_profile_, speed_profile_kwargs=dict(amp=tm.test_amp, bias=tm.test_bias, freq=tm.test_freq))
+    out = []
+    for omega, expected in cases:
+        got = load.mechanical_ode(1, np.array([omega]))[0]
+        assert abs(got - expected) < 1e-6
+        out.append(dict(omega=float(omega), t=1.0, expected=float(expected), reference_result=float(got)))
+    return dict(amp=float(tm.test_amp), bias=float(tm.test_bias), freq=float(tm.test_freq), tau_load=float(load._tau), cases=out)
+
+
+def periodic_references():
+    """test_reset_reference of TestFurtherReferenceGenerator: the scenario literals of the test body (:593-597), the tests' DummyRandom draws,
+    `_get_current_value` patched to the identity as in the test; replayed against the reference before recording"""
+    import tests.test_reference_generators.test_reference_generators as tr
+    from gym_electric_motor.reference_generators.subepisoded_reference_generator import SubepisodedReferenceGenerator
+
+    names, cases = params_of(tr.TestFurtherReferenceGenerator.test_reset_reference, "expected_reference")
+    rnd = tr.DummyRandom()
+
+    class FixedDraws:
+        def uniform(self, mu=0, sigma=1):
+            return rnd.monkey_random_rand()
+
+        def triangular(self, left=-1, mode=0, right=1):
+            return rnd.monkey_random_triangular(left, mode, right)
+
+    out = []
+    orig = SubepisodedReferenceGenerator._get_current_value
+    SubepisodedReferenceGenerator._get_current_value = lambda self, value: value
+    try:
+        for c in cases:
+            d = dict(zip(names, c))
+            gen = d["reference_class"](amplitude_range=0.8, frequency_range=d["frequency_range"], offset_range=0.5, limit_margin=0.4, episode_lengths=10,
+                                       reference_state="dummy_state_0")
+            gen._random_generator = FixedDraws()
+            ps_ = tr.DummyPhysicalSystem()
+            gen.set_modules(ps_)
+            gen._reset_reference()
+            assert sum(abs(d["expected_reference"] - gen._reference)) < 1e-6
+            out.append(dict(kind=d["reference_class"].__name__, amplitude=0.8, frequency=float(d["frequency_range"]), offset=0.5,
+                            margin=[float(v) for v in gen._limit_margin], length=10, tau=float(ps_.tau), uniform_draw=float(FixedDraws().uniform()),
+                            triangular_draw=float(FixedDraws().triangular(0, 0.5, 1)), expected=[float(v) for v in d["expected_reference"]],
+                            reference_result=[float(v) for v in gen._reference]))
+    finally:
+        SubepisodedReferenceGenerator._get_current_value = orig
+    return out
+
+
+def wiener_walk():
+    """TestWienerProcessReferenceGenerator.test_reset_reference (:384-414): clipped cumulative walk from 0.5 with the DummyRandom increments;
+    and TestSubepisodedReferenceGenerator.test_get_current_value (:840-870): lo + (hi - lo) * 0.25, numbers pass through"""
+    import tests.test_reference_generators.test_reference_generators as tr
+    from gym_electric_motor.reference_generators import WienerProcessReferenceGenerator
+    from gym_electric_motor.reference_generators.subepisoded_reference_generator import SubepisodedReferenceGenerator
+
+    rnd = tr.DummyRandom(exp_loc=0, exp_scale=1e-2, exp_size=10)  # :392
+    rnd_u = tr.DummyRandom()
+
+    class FixedDraws:
+        def normal(self, loc=0, scale=1, size=1):
+            return rnd.monkey_random_normal(loc, scale, size)
+
+        def uniform(self, mu=0, sigma=1):
+            return rnd_u.monkey_random_rand()
+
+    gen = WienerProcessReferenceGenerator(sigma_range=1e-2, episode_lengths=10, limit_margin=(-1, 1))  # literals of the test body :385-388
+    gen._random_generator = FixedDraws()
+    gen._reference_value = 0.5
+    gen._current_episode_length = 10
+    gen._limit_margin = (-1, 1)
+    orig = SubepisodedReferenceGenerator._get_current_value
+    SubepisodedReferenceGenerator._get_current_value = lambda self, value: value  # as the test does (:396-400)
+    try:
+        gen._reset_reference()
+    finally:
+        SubepisodedReferenceGenerator._get_current_value = orig
+    expected = [0.6, 0.4, 1, 1, 0.5, 0.2, -1, -0.9, -1, -0.6]  # :389
+    assert sum(abs(gen._reference - np.array(expected))) < 1e-6
+    walk = dict(start=0.5, margin=[-1.0, 1.0], increments=[float(v) for v in rnd.monkey_random_normal(0, 1e-2, 10)], expected=[float(v) for v in expected],
+                reference_result=[float(v) for v in gen._reference])
+    names, cases = params_of(tr.TestSubepisodedReferenceGenerator.test_get_current_value, "expected_value")
+    sub = SubepisodedReferenceGenerator()
+    sub._random_generator = FixedDraws()
+    cur = []
+    for value_range, expected_value in cases:
+        got = sub._get_current_value(value_range)
+        assert abs(got - expected_value) < 1e-6
+        cur.append(dict(value_range=np.asarray(value_range, dtype=float).ravel().tolist(), uniform_draw=0.25, expected=float(expected_value),
+                        reference_result=float(got)))
+    return dict(walk=walk, current_value=cur)
+
+
 if __name__ == "__main__":
-    ka = dict(finite_qc=finite_qc(), finite_b6=finite_b6(), cont_qc=cont_qc(), poly_load=poly_load(), euler=euler_solver(), constraints=constraints(),
+    ka = dict(wiener_walk=wiener_walk(), poly_load_formula=poly_load_formula(), periodic_references=periodic_references(), dq_to_abc=dq_to_abc(), dead_time=dead_time(), supplies=supplies(), ext_speed_load=ext_speed_load(),
+              finite_qc=finite_qc(), finite_b6=finite_b6(), cont_qc=cont_qc(), poly_load=poly_load(), euler=euler_solver(), constraints=constraints(),
               wse_rewards=wse_rewards())
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(ka, f)
-    print({k: (len(v) if isinstance(v, list) else len(v["cases"])) for k, v in ka.items()},
+    print({k: (len(v) if isinstance(v, list) else len(v.get("cases", v))) for k, v in ka.items()},
           "convert calls:", sum(len(c["calls"]) for k in ("finite_qc", "finite_b6", "cont_qc") for c in ka[k]))

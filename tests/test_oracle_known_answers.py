@@ -4,8 +4,11 @@ tests/golden/known_answers.json is produced by tests/golden/make_known_answers.p
 (tables in module globals / pytest.mark.parametrize arguments), replays the reference tests' call protocol against the reference
 implementation, and records every call with the value the reference's TABLE demands.  Here the same calls go through the oracle's
 component-level probes: converters (3471 convert calls: finite 1QC/2QC/4QC with and without interlocking over three taus, the B6
-bridge leg by leg, continuous 1QC/2QC/4QC against the tests' `comparable_voltage`), PolynomialStaticLoad.mechanical_ode, the Limit /
-Squared constraint truth tables and the WeightedSumOfErrors cases.
+bridge leg by leg, continuous 1QC/2QC/4QC against the tests' `comparable_voltage`), PolynomialStaticLoad.mechanical_ode (known answers
+and the closed form of test_load.py), ExternalSpeedLoad.mechanical_ode, the RC supply equation and AC1 supply voltages, the
+DqToAbcActionProcessor vectors, the DeadTimeProcessor FIFO protocol, one sub-episode of each periodic reference generator and the
+Wiener walk with the tests' fixed random draws, `_get_current_value`, the Limit / Squared constraint truth tables and the
+WeightedSumOfErrors cases.
 """
 import json
 import os
@@ -110,3 +113,147 @@ def test_weighted_sum_of_errors_cases(oracle_lib, case):
         cfg.reward_weight[j], cfg.reward_power[j], cfg.state_length[j] = case["reward_weights"][j], case["reward_power"][j], case["state_length"][j]
     cfg.reward_bias, cfg.violation_reward = case["bias"], case["violation_reward"]
     assert oracle_lib.Oracle(cfg).probe_reward(case["state"], case["reference"], case["violation_degree"]) == case["expected"]
+
+
+@pytest.mark.parametrize("case", KA["dq_to_abc"], ids=lambda c: f"dq{c['dq_action']}")
+def test_dq_to_abc_action_processor_known_answers(oracle_lib, case):
+    """test_dq_to_abc_action_processor.py:27-53: abc action for a dq action at the advanced angle epsilon + 0.5 tau omega p, through the
+    oracle's own action-wrapper code (the part of step_one in front of simulate)."""
+    cfg = _base_cfg(motor=K.MOTOR_PMSM, conv=(K.CONV_B6, K.CONV_NONE), tau=case["tau"])
+    cfg.motor_param[K.MP_P] = case["p"]
+    cfg.action_dq, cfg.angle_advance = 1, case["angle_advance"]
+    sim = oracle_lib.Oracle(cfg)
+    sim.reset()
+    sim.set_ode_state([[case["omega"], 0.0, 0.0, case["epsilon"]]])
+    abc = sim.probe_wrap_action(case["dq_action"])
+    assert np.allclose(abc, case["expected"])            # the test's own tolerance (np.isclose)
+    assert np.allclose(abc, case["reference_result"], rtol=0, atol=1e-14)   # and the reference's actual output
+
+
+@pytest.mark.parametrize("case", KA["dead_time"], ids=lambda c: f"steps{c['steps']}-{c['space']}-{len(c['actions'][0])}")
+def test_dead_time_processor_fifo_protocol(oracle_lib, case):
+    """test_dead_time_processor.py:28-75: the inner system sees [reset_action] * steps + actions.  Box(3) -> a PMSM with abc actions,
+    Box(1) -> a DC motor, Discrete -> the finite B6 slot, MultiDiscrete -> the two finite slots of an EESM (its first two columns; a
+    third finite slot exists in no system of the reference)."""
+    width = len(case["actions"][0])
+    if case["space"] == "Box":
+        cfg = _base_cfg(motor=K.MOTOR_PMSM, conv=(K.CONV_B6, K.CONV_NONE)) if width == 3 else _base_cfg()
+        cols = width
+    elif case["space"] == "Discrete":
+        cfg, cols = _base_cfg(motor=K.MOTOR_PMSM, conv=(K.CONV_B6, K.CONV_NONE), finite=1), 1
+    else:
+        cfg, cols = _base_cfg(motor=K.MOTOR_EESM, conv=(K.CONV_B6, K.CONV_4QC), finite=1), 2
+    cfg.dead_time_steps = case["steps"]
+    sim = oracle_lib.Oracle(cfg)
+    sim.reset()
+    for a, applied in zip(case["actions"], case["applied"]):
+        got = sim.probe_wrap_action(a[:cols])
+        assert list(got) == applied[:cols]
+
+
+@pytest.mark.parametrize("case", KA["supplies"]["rc"], ids=lambda c: f"u{c['u_sup']:g}")
+def test_rc_supply_system_equation_known_answers(oracle_lib, case):
+    """test_voltage_supplies.py:86-97 (hand-calculated values of the reference test)"""
+    got = oracle_lib.probe_rc_supply_rhs(case["u_sup"], case["u_0"], case["i_sup"], case["R"], case["C"])
+    assert abs(got - case["expected"]) <= 1e-14 * max(1.0, abs(case["expected"]))
+
+
+def test_ac1_supply_voltage_known_answers(oracle_lib):
+    """test_voltage_supplies.py:141-163: zero crossings, peaks and the three hand-calculated values"""
+    for c in KA["supplies"]["ac1"]:
+        got = oracle_lib.probe_ac1_voltage(c["u_nominal"], c["frequency"], c["phase"], c["t"])
+        assert abs(got - c["expected"]) < 1e-9, c
+
+
+def test_external_speed_load_known_answers(oracle_lib):
+    """test_mechanical_loads.py:281-290 with the profile of :36-42 (a triangular wave): d omega/dt = (profile(t + tau) - omega) / tau at
+    t = 1.  The profile goes through THIS repo's host tabulation (ExternalSpeedLoad.fill_config), the table entry of t = 1 through the
+    oracle's mechanical_ode."""
+    from scipy import signal
+
+    from gym_electric_motor_b200.physical_systems import ExternalSpeedLoad
+
+    d = KA["ext_speed_load"]
+    load = ExternalSpeedLoad(speed_profile=lambda t, amp, freq, bias: amp * signal.sawtooth(2 * np.pi * freq * t, width=0.5) + bias,
+                             speed_profile_kwargs=dict(amp=d["amp"], bias=d["bias"], freq=d["freq"]), tau=d["tau_load"])
+    cfg = _base_cfg(tau=1e-4)
+    cfg.solver_kind, cfg.solver_nsteps = K.SOLVER_RK4, 1
+    load.fill_config(cfg)
+    assert cfg.load_kind == K.LOAD_EXT_SPEED
+    table = load._table
+    dt = 1e-4 / 2  # one table entry per RK4 stage time: tau / (2 nsteps)
+    sim = oracle_lib.Oracle(cfg)
+    for c in d["cases"]:
+        j = int(round(c["t"] / dt))
+        got = sim.probe_mechanical_ode_ext(c["omega"], 0.0, table[j])
+        assert abs(got - c["expected"]) < 1e-6, c          # the test's own tolerance
+        assert abs(got - c["reference_result"]) < 1e-6
+
+
+@pytest.mark.parametrize("case", KA["periodic_references"], ids=lambda c: c["kind"])
+def test_periodic_reference_generators_known_answers(oracle_lib, case):
+    """test_reference_generators.py:540-627: one sub-episode of the Sawtooth / Sinusoidal / Step / Triangular generator with the tests'
+    fixed draws (uniform -> 0.25, triangular -> 0.45).  The scenario goes through THIS repo's host generator classes (scalar ranges,
+    the set_modules clipping of amplitude and offset) into the config, and through the oracle's sub-episode formula with Philox words
+    chosen to reproduce the draws."""
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200 import reference_generators as rg
+
+    cls = getattr(rg, case["kind"])
+    gen = cls(amplitude_range=case["amplitude"], frequency_range=case["frequency"], offset_range=case["offset"], limit_margin=0.4,
+              episode_lengths=case["length"], reference_state="omega")
+    env = gem.make("Cont-SC-PermExDc-v0", reference_generator=gen, tau=case["tau"])
+    cfg = env.build_config()
+    assert (cfg.ref_margin_lo[0], cfg.ref_margin_hi[0]) == tuple(case["margin"])
+    sim = oracle_lib.Oracle(cfg)
+
+    def word(u):  # the 32-bit word whose u01() is u (to 2^-33)
+        return int(u * 2.0 ** 32)
+
+    ratio = case["triangular_draw"]  # StepReferenceGenerator: high/low ratio ~ triangular(0, 0.5, 1); the oracle draws it by inverse CDF
+    second = word(2 * ratio * ratio if ratio < 0.5 else 1 - 2 * (1 - ratio) ** 2) if case["kind"].startswith("Step") else word(case["uniform_draw"])
+    vals, par = sim.periodic_block(0, cfg.ref_kind[0], [0, 0, 0, 0], [word(case["uniform_draw"]), second, 0, 0], case["length"])
+    assert np.sum(np.abs(vals - np.asarray(case["expected"]))) < 1e-6          # the test's own criterion
+    assert np.max(np.abs(vals - np.asarray(case["reference_result"]))) < 1e-8  # and the reference's actual sub-episode
+
+
+def test_wiener_walk_known_answer(oracle_lib):
+    """test_reference_generators.py:384-414: clipped cumulative walk from 0.5 with the tests' fixed normal draws"""
+    d = KA["wiener_walk"]["walk"]
+    cfg = _base_cfg()
+    cfg.n_ref, cfg.ref_kind[0], cfg.ref_state[0] = 1, K.REF_WIENER, 0
+    cfg.ref_margin_lo[0], cfg.ref_margin_hi[0] = d["margin"]
+    sim = oracle_lib.Oracle(cfg)
+    got = sim.probe_walk(0, d["start"], d["increments"])
+    assert np.sum(np.abs(got - np.asarray(d["expected"]))) < 1e-6
+    assert np.array_equal(got, np.asarray(d["reference_result"]))
+
+
+@pytest.mark.parametrize("case", KA["wiener_walk"]["current_value"], ids=lambda c: str(c["value_range"]))
+def test_get_current_value_known_answers(oracle_lib, case):
+    """test_reference_generators.py:840-870 (_get_current_value: a number is itself, a range is lo + (hi - lo) * U): through the host
+    generator's range handling into the config and the oracle's draw of a sub-episode parameter (the frequency of a periodic generator)"""
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200 import reference_generators as rg
+
+    vr = case["value_range"]
+    gen = rg.SinusoidalReferenceGenerator(frequency_range=vr[0] if len(vr) == 1 else tuple(vr), reference_state="omega")
+    cfg = gem.make("Cont-SC-PermExDc-v0", reference_generator=gen).build_config()
+    sim = oracle_lib.Oracle(cfg)
+    _, par = sim.periodic_block(0, cfg.ref_kind[0], [0, 0, int(case["uniform_draw"] * 2.0 ** 32), 0], [0, 0, 0, 0], 4)
+    assert abs(par[1] - case["expected"]) < 1e-6
+    assert abs(par[1] - case["reference_result"]) < 1e-9
+
+
+def test_polynomial_static_load_closed_form(oracle_lib):
+    """test_load.py:44-91: default and parametrised PolynomialStaticLoad, omega in {-10, 0, 10} x torque in {-3, 0, 5}; the reference test
+    demands exact equality with (T - sign(omega)(c omega^2 + b |omega| + a)) / j_total"""
+    for c in KA["poly_load_formula"]:
+        cfg = _base_cfg()
+        cfg.load_kind = K.LOAD_POLY_STATIC
+        cfg.load_param[K.LP_A], cfg.load_param[K.LP_B], cfg.load_param[K.LP_C], cfg.load_param[K.LP_J_LOAD] = c["a"], c["b"], c["c"], c["j_load"]
+        cfg.load_param[K.LP_TAU_DECAY] = 1e-3
+        cfg.motor_param[K.MP_J_ROTOR] = c["j_rotor"]
+        sim = oracle_lib.Oracle(cfg)
+        got = sim.probe_mechanical_ode(c["omega"], c["torque"])
+        assert abs(got - c["expected"]) <= 4e-16 * max(1.0, abs(c["expected"])), c
