@@ -43,3 +43,13 @@ def update_parameter_dict(source_dict, update_dict, copy=True):
     new_dict = source_dict.copy() if copy else source_dict
     new_dict.update(update_dict)
     return new_dict
+
+
+def state_dict_to_state_array(state_dict, state_array, state_names):
+    """write the entries of a {state name: value} dict into `state_array` in place; names are case-insensitive, unknown names assert
+    (reference utils.py:19-37)."""
+    low = {str(k).lower(): v for k, v in state_dict.items()}
+    assert all(k in state_names for k in low), f"A state name in {list(low)} is invalid."
+    for ind, key in enumerate(state_names):
+        if key in low:
+            state_array[ind] = low[key]

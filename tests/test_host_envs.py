@@ -291,3 +291,20 @@ def test_vector_facade_spaces():
     assert venv.single_action_space.shape == (3,) and venv.action_space.shape == (8, 3)
     v2 = gem.vector.make_vec("Finite-CC-PMSM-v0", num_envs=4)
     assert v2.single_action_space.n == 8 and len(v2.observation_space.spaces) == 2
+
+
+def test_utils_follow_the_reference_test_vectors():
+    """the cases of the reference's tests/test_utils.py (state_dict_to_state_array :8-30, set_state_array :33-56)"""
+    from gym_electric_motor_b200 import utils
+
+    names = ["a", "b", "c", "d"]
+    for state_dict, state_array, target in ((dict(A=5, b=12, c=10, d=12), [0, 0, 0, 0], [5, 12, 10, 12]), (dict(a=5, b=12, c=10), [0, 1, 2, 5], [5, 12, 10, 5])):
+        utils.state_dict_to_state_array(state_dict, state_array, names)
+        assert np.all(np.asarray(state_array) == target)
+    with pytest.raises(AssertionError):
+        utils.state_dict_to_state_array({"invalid_name": 0, "valid_name": 1}, np.zeros(3), ["valid_name", "a", "b"])
+    for input_values, target in ((dict(a=5, b=12, c=10, d=12), [5, 12, 10, 12]), (np.array([1, 2, 3, 4]), [1, 2, 3, 4]), ([1, 2, 3, 4], [1, 2, 3, 4]), (5, [5, 5, 5, 5])):
+        assert np.all(utils.set_state_array(input_values, names) == target)
+    for input_values, error in (("a", Exception), (np.array([1, 2, 3]), AssertionError), ([1, 2, 3], AssertionError)):
+        with pytest.raises(error):
+            utils.set_state_array(input_values, names)
