@@ -10,7 +10,7 @@ The package mirrors the reference's surface for the hot path only (SURVEY.md §8
 All compute runs in libgemb200.so (hand-written sm_100a CUDA, C-ABI in include/gemb200.h); importing this package
 does not need a GPU, creating an environment does.
 """
-from . import physical_system_wrappers, physical_systems, reference_generators, reward_functions, vector  # noqa: F401
+from . import envs, physical_system_wrappers, physical_systems, reference_generators, reward_functions, vector, visualization  # noqa: F401
 from .constraints import Constraint, ConstraintMonitor, LimitConstraint, SquaredConstraint  # noqa: F401
 from .core import Callback, ElectricMotorEnvironment, ElectricMotorVisualization  # noqa: F401
 from .envs import env_ids, make  # noqa: F401

@@ -123,6 +123,11 @@ class ElectricMotorEnvironment:
         return self._constraint_monitor
 
     @property
+    def visualizations(self):
+        """reference core.py:140-143 (agents look for a MotorDashboard in this list)"""
+        return self._visualizations
+
+    @property
     def limits(self):
         return self._physical_system.limits
 

@@ -10,12 +10,13 @@ tests/golden/env_table.json, which was dumped from the running reference.
 callbacks, …) with the same `env-arg` semantics: None -> default, instance -> used as is, dict -> default class with
 updated kwargs (utils.initialize).
 """
-from . import physical_systems as ps
-from .constraints import SquaredConstraint
-from .core import ElectricMotorEnvironment, ElectricMotorVisualization
-from .reference_generators import MultipleReferenceGenerator, ReferenceGenerator, WienerProcessReferenceGenerator
-from .reward_functions import RewardFunction, WeightedSumOfErrors
-from .utils import initialize
+from .. import physical_systems as ps
+from ..constraints import SquaredConstraint
+from ..core import ElectricMotorEnvironment, ElectricMotorVisualization
+from ..reference_generators import MultipleReferenceGenerator, ReferenceGenerator, WienerProcessReferenceGenerator
+from ..reward_functions import RewardFunction, WeightedSumOfErrors
+from ..utils import initialize
+from .motors import ActionType, ControlType, Motor, MotorType  # noqa: F401
 
 MOTORS = ["PermExDc", "SeriesDc", "ShuntDc", "ExtExDc", "PMSM", "SynRM", "EESM", "SCIM", "DFIM"]
 _DC = ("PermExDc", "SeriesDc", "ShuntDc", "ExtExDc")
@@ -123,6 +124,19 @@ def _default_constraints(m):
 
 _NOT_SET = object()
 
+# The reference has one class per id (envs/**: `ContCurrentControlPermanentMagnetSynchronousMotorEnv`, ...) and agents test
+# `type(env) in (envs.ContSpeedControlDcExternallyExcitedMotorEnv, ...)`; here the defaults are data, so the 54 names are thin
+# subclasses generated from the same table and `make` instantiates the one that belongs to the id.
+_ACTION_WORD = dict(Cont="Cont", Finite="Finite")
+_CONTROL_WORD = dict(CC="CurrentControl", TC="TorqueControl", SC="SpeedControl")
+ENV_CLASSES = {}
+for _a in _ACTION_WORD:
+    for _c in _CONTROL_WORD:
+        for _m in MOTORS:
+            _cls_name = f"{_ACTION_WORD[_a]}{_CONTROL_WORD[_c]}{_MOTOR_CLASS[_m].__name__}Env"
+            ENV_CLASSES[f"{_a}-{_c}-{_m}-v0"] = type(_cls_name, (ElectricMotorEnvironment,), {"__doc__": f"`{_a}-{_c}-{_m}-v0` (defaults: envs table)"})
+            globals()[_cls_name] = ENV_CLASSES[f"{_a}-{_c}-{_m}-v0"]
+
 
 def make(env_id, supply=None, converter=None, motor=None, load=None, ode_solver=None, reward_function=None, reference_generator=None,
          visualization=None, state_filter=None, callbacks=(), constraints=_NOT_SET, calc_jacobian=True, tau=None,
@@ -150,7 +164,7 @@ def make(env_id, supply=None, converter=None, motor=None, load=None, ode_solver=
         constraints = _default_constraints(m)
     if visualization is not None and not isinstance(visualization, (ElectricMotorVisualization, list, tuple)):
         visualization = None  # dict/str specs of the matplotlib dashboard: plotting is out of scope, ignored
-    env = ElectricMotorEnvironment(
+    env = ENV_CLASSES[env_id](
         physical_system=physical_system, reference_generator=reference_generator, reward_function=reward_function,
         constraints=constraints, visualization=visualization or (), state_filter=state_filter, callbacks=callbacks,
         physical_system_wrappers=physical_system_wrappers, num_envs=num_envs, autoreset=autoreset, seed=seed, **kwargs)

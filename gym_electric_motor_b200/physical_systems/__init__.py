@@ -11,3 +11,9 @@ from .physical_systems import (DcMotorSystem, DoublyFedInductionMotorSystem, Ext
                                SCMLSystem, SquirrelCageInductionMotorSystem, SynchronousMotorSystem, ThreePhaseMotorSystem)
 from .solvers import EulerSolver, OdeSolver, RK4Solver, ScipyOdeIntSolver, ScipyOdeSolver, ScipySolveIvpSolver
 from .voltage_supplies import AC1PhaseSupply, AC3PhaseSupply, IdealVoltageSupply, RCVoltageSupply, VoltageSupply
+
+# short names the reference exports for the converters (physical_systems/__init__.py:14-24)
+Cont1QC, Cont2QC, Cont4QC, ContB6C, ContMulti = (ContOneQuadrantConverter, ContTwoQuadrantConverter, ContFourQuadrantConverter, ContB6BridgeConverter,
+                                                  ContMultiConverter)
+Finite1QC, Finite2QC, Finite4QC, FiniteB6C, FiniteMulti = (FiniteOneQuadrantConverter, FiniteTwoQuadrantConverter, FiniteFourQuadrantConverter,
+                                                            FiniteB6BridgeConverter, FiniteMultiConverter)

@@ -278,10 +278,41 @@ class DcShuntMotor(DcMotor):
 
 # ------------------------------------------------------------------------------------------------------ three phase
 class ThreePhaseMotor(ElectricMotor):
-    """reference three_phase_motor.py (limit handling :127-133; the Clarke/Park transforms live in the kernel)."""
+    """reference three_phase_motor.py (limit handling :127-133).  The Clarke/Park transforms of the STEP run inside the kernel; the
+    host-side versions below exist for agents (field-oriented controllers call `motor.t_32(motor.q(u_dq, eps))`, three_phase_motor.py:18-88)."""
 
     IO_VOLTAGES = []
     IO_CURRENTS = []
+
+    _SQRT3_2 = 0.5 * np.sqrt(3.0)
+
+    @staticmethod
+    def t_23(quantities):
+        """Clarke: (a, b, c) -> (alpha, beta), amplitude invariant"""
+        a, b, c = quantities
+        return np.array([(2.0 * a - b - c) / 3.0, (b - c) / np.sqrt(3.0)])
+
+    @staticmethod
+    def t_32(quantities):
+        """inverse Clarke: (alpha, beta) -> (a, b, c)"""
+        al, be = quantities
+        h = ThreePhaseMotor._SQRT3_2 * be
+        return np.array([al, -0.5 * al + h, -0.5 * al - h])
+
+    @staticmethod
+    def q(quantities, epsilon):
+        """Park rotation dq -> alpha-beta by the electrical angle"""
+        c, s = np.cos(epsilon), np.sin(epsilon)
+        return c * quantities[0] - s * quantities[1], s * quantities[0] + c * quantities[1]
+
+    @staticmethod
+    def q_inv(quantities, epsilon):
+        """alpha-beta -> dq"""
+        return ThreePhaseMotor.q(quantities, -epsilon)
+
+    def q_me(self, quantities, epsilon):
+        """dq -> alpha-beta with the MECHANICAL angle (three_phase_motor.py:77-88)"""
+        return self.q(quantities, epsilon * self._motor_parameter["p"])
 
     def _torque_limit(self):
         raise NotImplementedError

@@ -85,7 +85,7 @@ class SCMLSystem(PhysicalSystem):
         self._env_index_offset = int(env_index_offset)
         self._mechanical_load.set_j_rotor(self._electrical_motor.motor_parameter["j_rotor"])  # :83
         state_names = self._build_state_names()
-        self._set_indices()
+        self._set_indices(state_names)
         state_space = self._build_state_space(state_names)
         super().__init__(self._converter.action_space, state_space, state_names, tau)
         self._limits = np.zeros(len(state_names))
@@ -234,9 +234,16 @@ class SCMLSystem(PhysicalSystem):
     def _build_state_space(self, state_names):
         raise NotImplementedError
 
-    def _set_indices(self):
-        self.OMEGA_IDX = 0
-        self.TORQUE_IDX = 1
+    def _set_indices(self, state_names):
+        """positions in the system's own state vector (before wrappers) with the attribute names agents read
+        (physical_systems.py:141-162, :462-485, :594-617, :737-763): currents are the `i*` names, voltages the `u*` names except u_sup"""
+        self.OMEGA_IDX = state_names.index("omega")
+        self.TORQUE_IDX = state_names.index("torque")
+        self.CURRENTS_IDX = [k for k, n in enumerate(state_names) if n.startswith("i") and n != "i_sum"]
+        self.VOLTAGES_IDX = [k for k, n in enumerate(state_names) if n.startswith("u") and n != "u_sup"]
+        self.U_SUP_IDX = [state_names.index("u_sup")]
+        if "epsilon" in state_names:
+            self.EPSILON_IDX = state_names.index("epsilon")
 
     def initial_ode_state(self):
         """[omega, motor states...] constant initial ODE state (SCMLSystem.reset :263-270)."""
@@ -395,9 +402,34 @@ class DcMotorSystem(SCMLSystem):
 
 
 class ThreePhaseMotorSystem(SCMLSystem):
-    """reference physical_systems.py:321-415 (the abc / alpha-beta / dq helpers run inside the kernel)."""
+    """reference physical_systems.py:321-415.  The transformations of the step run inside the kernel; the helper methods keep the
+    reference's names for agents (observers, field-oriented controllers)."""
 
     _NAMES = []
+
+    @staticmethod
+    def _angle(epsilon_el, normed_epsilon):
+        return epsilon_el * np.pi if normed_epsilon else epsilon_el
+
+    def abc_to_alphabeta_space(self, abc_quantities):
+        return self._electrical_motor.t_23(abc_quantities)
+
+    def alphabeta_to_abc_space(self, alphabeta_quantities):
+        return self._electrical_motor.t_32(alphabeta_quantities)
+
+    def abc_to_dq_space(self, abc_quantities, epsilon_el, normed_epsilon=False):
+        m = self._electrical_motor
+        return m.q_inv(m.t_23(abc_quantities), self._angle(epsilon_el, normed_epsilon))
+
+    def dq_to_abc_space(self, dq_quantities, epsilon_el, normed_epsilon=False):
+        m = self._electrical_motor
+        return m.t_32(m.q(dq_quantities, self._angle(epsilon_el, normed_epsilon)))
+
+    def alphabeta_to_dq_space(self, alphabeta_quantities, epsilon_el, normed_epsilon=False):
+        return self._electrical_motor.q_inv(alphabeta_quantities, self._angle(epsilon_el, normed_epsilon))
+
+    def dq_to_alphabeta_space(self, dq_quantities, epsilon_el, normed_epsilon=False):
+        return self._electrical_motor.q(dq_quantities, self._angle(epsilon_el, normed_epsilon))
 
     def __init__(self, control_space="abc", **kwargs):
         assert control_space in ("abc", "dq")

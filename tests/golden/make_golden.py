@@ -426,6 +426,9 @@ def env_table():
         load = p.mechanical_load
         conv = p.converter
         entry = dict(
+            env_class=type(env.unwrapped).__name__,
+            system_indices={k: jsonable(getattr(p, k)) for k in ("OMEGA_IDX", "TORQUE_IDX", "CURRENTS_IDX", "VOLTAGES_IDX", "U_SUP_IDX", "EPSILON_IDX")
+                            if hasattr(p, k)},
             system_class=type(p).__name__,
             wrappers=[type(w).__name__ for w in _wrapper_chain(wrapped)],
             state_names=list(wrapped.state_names),
@@ -587,13 +590,15 @@ if __name__ == "__main__":
     ap.add_argument("--skip-table", action="store_true")
     args = ap.parse_args()
     for case in CASES:
-        if args.only in ("ref_data", "init_bounds", "switched_stats") or (args.only and args.only not in case["name"]):
+        if args.only in ("ref_data", "init_bounds", "switched_stats", "env_table") or (args.only and args.only not in case["name"]):
             continue
         record(case)
     if not args.only or args.only == "init_bounds":
         init_bounds()
     if not args.only or args.only == "switched_stats":
         switched_stats()
+    if args.only == "env_table":
+        env_table()
     if not args.only or args.only == "ref_data":
         if not args.skip_table and not args.only:
             env_table()

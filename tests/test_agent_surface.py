@@ -1,0 +1,44 @@
+"""Agent drop-in at the surface level: the reference's own example agent (examples/classic_controllers) is built for every id and
+computes actions from fixed observations, once against the unmodified reference and once against this package aliased as
+`gym_electric_motor` (tests/agent_surface/harness.py).  Everything the agent reads — classes and isinstance relations, env class per
+id, spaces, names, limits, nominal values, parameters, tau, index attributes, transformation helpers — must lead to the same actions.
+Container-only (needs /root/reference); the portable part of the surface is pinned through env_table.json in test_host_envs.py."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HARNESS = os.path.join(HERE, "agent_surface", "harness.py")
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/examples/classic_controllers"), reason="needs the reference checkout")
+
+
+def _run(impl):
+    out = subprocess.run([sys.executable, HARNESS, "--impl", impl], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_reference_example_agent_reads_the_same_surface():
+    ref, mine = _run("reference"), _run("b200")
+    assert sorted(ref) == sorted(mine) and len(ref) == 54
+    built = [k for k, v in ref.items() if v["ok"]]
+    acted = [k for k in built if len(ref[k]["actions"]) == 3]
+    assert len(built) >= 38 and len(acted) >= 32  # the example is stale for the rest (numpy 2, its own bugs) - on both sides alike
+    for env_id in sorted(ref):
+        r, m = ref[env_id], mine[env_id]
+        if r["ok"]:
+            assert m["ok"], (env_id, m["error"])
+            assert r["error"] == m["error"], (env_id, r["error"], m["error"])  # control() failing inside the example fails identically
+            assert len(r["actions"]) == len(m["actions"])
+            for a, b in zip(r["actions"], m["actions"]):
+                assert len(a) == len(b) and np.allclose(a, b, rtol=1e-9, atol=1e-12), (env_id, a, b)
+        elif "ShuntDc" in env_id and env_id.split("-")[1] == "CC":
+            # the reference wraps the shunt system in a CurrentSumProcessor, which the example's isinstance(DcMotorSystem) rejects; here i_sum is
+            # produced by the system itself, so the agent can be built (a superset)
+            assert m["ok"]
+        else:
+            assert r["error"] == m["error"], (env_id, r["error"], m["error"])

@@ -308,3 +308,46 @@ def test_utils_follow_the_reference_test_vectors():
     for input_values, error in (("a", Exception), (np.array([1, 2, 3]), AssertionError), ([1, 2, 3], AssertionError)):
         with pytest.raises(error):
             utils.set_state_array(input_values, names)
+
+
+@pytest.mark.parametrize("env_id", IDS)
+def test_env_class_names_and_index_attributes(env_id):
+    """one env class per id with the reference's class name (agents test `type(env) in (envs.ContSpeedControl...Env, ...)`) and the
+    SCMLSystem index attributes agents read (physical_systems.py:141-162, :462-485, :594-617, :737-763); both recorded from the reference"""
+    import gym_electric_motor_b200.envs as envs
+
+    t = TABLE[env_id]
+    env = gem.make(env_id)
+    assert type(env).__name__ == t["env_class"] and type(env) is getattr(envs, t["env_class"])
+    assert isinstance(env, gem.ElectricMotorEnvironment) and env.unwrapped is env and env.visualizations == []
+    ps = env.physical_system.unwrapped
+    for key, val in t["system_indices"].items():
+        assert getattr(ps, key) == val, (key, getattr(ps, key), val)
+
+
+def test_motor_enum_helper_composes_every_id():
+    from gym_electric_motor_b200.envs.motors import ActionType, ControlType, Motor, MotorType
+
+    ids = {Motor(m, c, a).env_id() for m in MotorType for c in ControlType for a in ActionType}
+    assert ids == set(gem.env_ids())
+    assert Motor(MotorType.PermanentMagnetSynchronousMotor, ControlType.TorqueControl, ActionType.Continuous).env_id() == "Cont-TC-PMSM-v0"
+    for m in MotorType:  # the plotted state names are states of the env (minus u_sup, and the wrappers' extras)
+        env = gem.make(Motor(m, ControlType.SpeedControl, ActionType.Continuous).env_id())
+        assert set(Motor(m, ControlType.SpeedControl, ActionType.Continuous).states()) <= set(env.state_names), m
+
+
+def test_host_side_transformations_match_the_definitions():
+    """Clarke / Park helpers agents call (three_phase_motor.py:18-88, physical_systems.py:326-415)"""
+    ps = gem.make("Cont-CC-PMSM-v0").physical_system
+    m = ps.electrical_motor
+    abc = np.array([0.3, -0.7, 0.4])
+    ab = m.t_23(abc)
+    assert np.allclose(ab, 2 / 3 * np.array([[1, -0.5, -0.5], [0, np.sqrt(3) / 2, -np.sqrt(3) / 2]]) @ abc)
+    assert np.allclose(m.t_32(ab), abc - abc.mean())          # zero-sequence free round trip
+    dq = np.array(m.q_inv(ab, 0.83))
+    assert np.allclose(m.q(dq, 0.83), ab) and np.isclose(np.hypot(*dq), np.hypot(*ab))
+    assert np.allclose(ps.abc_to_dq_space(abc, 0.83 / np.pi, normed_epsilon=True), dq)
+    assert np.allclose(ps.dq_to_abc_space(dq, 0.83), abc - abc.mean())
+    assert np.allclose(ps.alphabeta_to_dq_space(ab, 0.83), dq) and np.allclose(ps.dq_to_alphabeta_space(dq, 0.83), ab)
+    assert np.allclose(ps.abc_to_alphabeta_space(abc), ab) and np.allclose(ps.alphabeta_to_abc_space(ab), abc - abc.mean())
+    assert np.allclose(m.q_me(dq, 0.2), m.q(dq, 0.2 * m.motor_parameter["p"]))
