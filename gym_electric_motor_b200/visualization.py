@@ -1,18 +1,30 @@
-"""Names of the reference's `visualization` package.  Plotting is out of scope for the device path, but agent code
-written against the reference looks the classes up (`isinstance(v, MotorDashboard)` over `env.visualizations`, classic_controllers.py
-of the reference's examples), so the names resolve; constructing one says what to use instead."""
+"""Names of the reference's `visualization` package.  Plotting is out of scope for the device path: the batched env
+returns tensors and nothing is drawn.  User scripts written for the reference pass `visualization=MotorDashboard(state_plots=[...])`
+to `gem.make`, and agent code looks the class up (`isinstance(v, MotorDashboard)` over `env.visualizations`), so the names resolve to
+inert objects: constructing one warns once that nothing will be plotted; every hook is a no-op."""
+import warnings
+
 from .core import ElectricMotorVisualization
 
 
-class _NotOnDevice(ElectricMotorVisualization):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(f"{type(self).__name__}: matplotlib visualisation is out of scope for gym_electric_motor_b200 (DESIGN.md §7); read the "
-                                  "tensors env.step returns, or pass your own ElectricMotorVisualization subclass (its hooks are called)")
+class _Inert(ElectricMotorVisualization):
+    _warned = False
+
+    def __init__(self, *args, update_interval=1000, **kwargs):
+        if not _Inert._warned:
+            warnings.warn(f"{type(self).__name__}: gym_electric_motor_b200 does not plot (DESIGN.md §7); the object is accepted and ignored",
+                          stacklevel=2)
+            _Inert._warned = True
+        self.update_interval = update_interval
+        self.kwargs = kwargs
+
+    def render(self):
+        pass
 
 
-class MotorDashboard(_NotOnDevice):
+class MotorDashboard(_Inert):
     pass
 
 
-class ConsolePrinter(_NotOnDevice):
+class ConsolePrinter(_Inert):
     pass

@@ -42,3 +42,20 @@ def test_reference_example_agent_reads_the_same_surface():
             assert m["ok"]
         else:
             assert r["error"] == m["error"], (env_id, r["error"], m["error"])
+
+
+def test_reference_example_scripts_run_up_to_make():
+    """examples/environment_features/*.py and examples/classic_controllers/*_example.py, unmodified, up to `env = gem.make(...)` +
+    `env.build_config()` (tests/agent_surface/examples_harness.py).  scim_ideal_grid_simulation.py simulates at import time, so without a
+    GPU it must stop exactly at the loud no-CUDA error — never earlier, never with a CPU fallback."""
+    import torch
+
+    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "examples_harness.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert len(res) >= 9
+    for script, verdict in res.items():
+        if script == "scim_ideal_grid_simulation.py" and not torch.cuda.is_available():
+            assert verdict.startswith("GemB200Error: no CUDA device"), verdict
+        else:
+            assert verdict == "ok", (script, verdict)
