@@ -99,6 +99,10 @@ class ElectricMotorEnvironment:
             visualization = [visualization]
         self._visualizations = [v for v in (visualization or []) if isinstance(v, ElectricMotorVisualization)]
         self._callbacks = list(callbacks) + list(self._visualizations)
+        if not self._visualizations:  # the reference's envs default to a MotorDashboard (user code reads env.visualizations[0]); here an
+            from .visualization import MotorDashboard  # inert one that is not even registered as a callback (nothing to call per step)
+
+            self._visualizations = [MotorDashboard(_quiet=True)]
         self._autoreset = K.AUTORESET_SAME_STEP if (autoreset in ("same_step", True, K.AUTORESET_SAME_STEP)) else K.AUTORESET_NONE
         self._seed_value = 0 if seed is None else int(seed)
         self._sim = None

@@ -10,8 +10,8 @@ from .core import ElectricMotorVisualization
 class _Inert(ElectricMotorVisualization):
     _warned = False
 
-    def __init__(self, *args, update_interval=1000, **kwargs):
-        if not _Inert._warned:
+    def __init__(self, *args, update_interval=1000, _quiet=False, **kwargs):
+        if not _Inert._warned and not _quiet:
             warnings.warn(f"{type(self).__name__}: gym_electric_motor_b200 does not plot (DESIGN.md §7); the object is accepted and ignored",
                           stacklevel=2)
             _Inert._warned = True
@@ -19,6 +19,9 @@ class _Inert(ElectricMotorVisualization):
         self.kwargs = kwargs
 
     def render(self):
+        pass
+
+    def initialize(self):
         pass
 
 

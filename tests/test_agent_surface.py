@@ -59,3 +59,16 @@ def test_reference_example_scripts_run_up_to_make():
             assert verdict.startswith("GemB200Error: no CUDA device"), verdict
         else:
             assert verdict == "ok", (script, verdict)
+
+
+def test_gem_cookbook_cells_build_the_same_environment():
+    """examples/environment_features/GEM_cookbook.ipynb, cell by cell (tests/agent_surface/cookbook_harness.py)"""
+    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "cookbook_harness.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["constraints"] == ["SquaredConstraint", "MyConstraint", "str", "function"]
+    assert res["custom_constraints"].startswith("TypeError")       # host code cannot run in the kernel: refused, not ignored
+    assert res["env_class"] == "FiniteCurrentControlPermanentMagnetSynchronousMotorEnv"
+    assert (res["n_state_ops"], res["n_ref"], res["init_random"]) == (2, 2, 1)  # CosSin + StateNoise, i_sq + i_sd, uniform initialiser
+    assert res["state_names"][-2:] == ["cos(epsilon)", "sin(epsilon)"]
+    assert res["tau"] == 1e-5 and res["u_sup"] == 350.0 and res["reward_i_sq"] == 10.0

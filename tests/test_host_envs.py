@@ -319,7 +319,8 @@ def test_env_class_names_and_index_attributes(env_id):
     t = TABLE[env_id]
     env = gem.make(env_id)
     assert type(env).__name__ == t["env_class"] and type(env) is getattr(envs, t["env_class"])
-    assert isinstance(env, gem.ElectricMotorEnvironment) and env.unwrapped is env and env.visualizations == []
+    assert isinstance(env, gem.ElectricMotorEnvironment) and env.unwrapped is env
+    assert isinstance(env.visualizations[0], gem.visualization.MotorDashboard)  # the reference's default; inert here
     ps = env.physical_system.unwrapped
     for key, val in t["system_indices"].items():
         assert getattr(ps, key) == val, (key, getattr(ps, key), val)
