@@ -19,3 +19,25 @@ from .reference_generators import ReferenceGenerator  # noqa: F401
 from .reward_functions import RewardFunction, WeightedSumOfErrors  # noqa: F401
 
 __version__ = "0.1.0"
+
+_ALIASED_SUBMODULES = ("physical_systems", "physical_systems.solvers", "physical_systems.mechanical_loads", "physical_systems.converters",
+                       "physical_systems.electric_motors", "physical_systems.voltage_supplies", "physical_systems.physical_systems",
+                       "reference_generators", "physical_system_wrappers", "reward_functions", "constraints", "core", "utils", "envs", "envs.motors",
+                       "visualization")
+
+
+def install_as_gym_electric_motor():
+    """Make `import gym_electric_motor as gem` (and `from gym_electric_motor.<submodule> import ...`) in EXISTING agent code resolve to
+    this package: registers it and its submodules under the reference's module names in `sys.modules`.  Call it once before the
+    agent's imports.  Refuses when the real gym_electric_motor has already been imported (the two cannot be mixed in one process)."""
+    import importlib
+    import sys
+
+    me = sys.modules[__name__]
+    other = sys.modules.get("gym_electric_motor")
+    if other is not None and other is not me:
+        raise RuntimeError("gym_electric_motor is already imported in this process; install the alias before importing agent code")
+    sys.modules["gym_electric_motor"] = me
+    for sub in _ALIASED_SUBMODULES:
+        sys.modules["gym_electric_motor." + sub] = importlib.import_module(__name__ + "." + sub)
+    return me

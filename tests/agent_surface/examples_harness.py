@@ -9,11 +9,7 @@ import numpy as np; np.complex = complex
 HERE = __file__.rsplit("/", 2)[0]
 sys.path.insert(0, HERE + "/_shims"); sys.path.insert(0, HERE.rsplit("/", 1)[0])
 import gym_electric_motor_b200 as gemb
-sys.modules["gym_electric_motor"] = gemb
-for sub in ("physical_systems", "physical_systems.solvers", "physical_systems.mechanical_loads", "physical_systems.converters", "physical_systems.electric_motors",
-            "physical_systems.voltage_supplies", "reference_generators", "physical_system_wrappers", "envs", "envs.motors", "visualization", "reward_functions",
-            "constraints", "core", "utils"):
-    sys.modules["gym_electric_motor." + sub] = importlib.import_module("gym_electric_motor_b200." + sub)
+gemb.install_as_gym_electric_motor()
 for name, classes in (("gym_electric_motor.visualization.motor_dashboard_plots", ("StatePlot", "TimePlot", "MeanEpisodeRewardPlot")),
                       ("gym_electric_motor.visualization.motor_dashboard_plots.base_plots", ("TimePlot",)),
                       ("gym_electric_motor.visualization.render_modes", ("RenderMode",))):

@@ -37,10 +37,7 @@ def main(impl):
         sys.path.insert(0, HERE.rsplit("/", 1)[0])
         import gym_electric_motor_b200 as gem
 
-        sys.modules["gym_electric_motor"] = gem
-        for sub in ("physical_systems", "reference_generators", "physical_system_wrappers", "envs", "envs.motors", "visualization", "reward_functions",
-                    "constraints", "core", "utils"):
-            sys.modules["gym_electric_motor." + sub] = importlib.import_module("gym_electric_motor_b200." + sub)
+        gem.install_as_gym_electric_motor()
         # plotting helpers of the example (out of scope): inert stand-ins so that its modules import
         for name, classes in (("gym_electric_motor.visualization.motor_dashboard_plots", ("StatePlot", "TimePlot")),
                               ("gym_electric_motor.visualization.motor_dashboard_plots.base_plots", ("TimePlot",)),
