@@ -40,4 +40,6 @@ def install_as_gym_electric_motor():
     sys.modules["gym_electric_motor"] = me
     for sub in _ALIASED_SUBMODULES:
         sys.modules["gym_electric_motor." + sub] = importlib.import_module(__name__ + "." + sub)
+    sys.modules["gym_electric_motor.visualization.motor_dashboard"] = sys.modules["gym_electric_motor.visualization"]  # one flat module here
+    me.gym_electric_motor = me  # `from gym_electric_motor import gym_electric_motor as gem` (seen in the reference's notebooks)
     return me

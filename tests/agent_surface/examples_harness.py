@@ -42,4 +42,42 @@ for f in files:
     except Exception as e:
         tb = traceback.extract_tb(e.__traceback__)[-1]
         out[os.path.basename(f)] = f"{type(e).__name__}: {str(e)[:160]} ({tb.filename.split('/')[-1]}:{tb.lineno})"
+
+
+# ---- notebooks: every code cell up to the one that calls gem.make; statements that need packages absent from this image (stable_baselines3,
+# gekko, gymnasium.wrappers) are skipped one by one, the gem imports / parameter definitions around them run
+NOTEBOOKS = sorted(glob.glob("/root/reference/examples/reinforcement_learning_controllers/*.ipynb") + glob.glob("/root/reference/examples/model_predictive_controllers/*.ipynb"))
+for f in NOTEBOOKS:
+    cells = ["".join(c["source"]) for c in json.load(open(f))["cells"] if c["cell_type"] == "code"]
+    ns = {}
+    verdict = "no gem.make cell"
+    for i, src in enumerate(cells):
+        src = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("%", "!")))
+        try:
+            nodes = ast.parse(src).body
+        except SyntaxError:
+            continue
+        made = None
+        for node in nodes:
+            is_make = isinstance(node, ast.Assign) and "Attribute(value=Name(id='gem', ctx=Load()), attr='make'" in ast.dump(node.value)
+            try:
+                exec(compile(ast.Module(body=[node], type_ignores=[]), f"cell{i}", "exec"), ns)
+                if is_make:
+                    made = ns[node.targets[0].id]
+            except Exception as e:
+                if is_make:
+                    tb = traceback.extract_tb(e.__traceback__)[-1]
+                    verdict = f"{type(e).__name__}: {str(e)[:160]} ({tb.filename.split('/')[-1]}:{tb.lineno})"
+                    made = False
+            if is_make:
+                break
+        if made is not None:
+            if made is not False:
+                try:
+                    made.build_config()
+                    verdict = "ok"
+                except Exception as e:
+                    verdict = f"{type(e).__name__}: {str(e)[:160]}"
+            break
+    out[os.path.basename(f)] = verdict
 print(json.dumps(out))
