@@ -19,6 +19,11 @@ from .reference_generators import ReferenceGenerator
 from .reward_functions import RewardFunction
 from .spaces import Box, Tuple
 
+try:  # a gymnasium.Env when gymnasium is installed, so that gymnasium.Wrapper / TimeLimit / FlattenObservation accept the scalar env
+    from gymnasium import Env as _EnvBase  # pragma: no cover - this image has no gymnasium
+except ImportError:
+    _EnvBase = object
+
 
 class Callback:
     """reference core.py:708-740 (hooks receive batched tensors)"""
@@ -51,7 +56,7 @@ class ElectricMotorVisualization(Callback):
         pass
 
 
-class ElectricMotorEnvironment:
+class ElectricMotorEnvironment(_EnvBase):
     """See module docstring.  Constructor signature follows reference core.py:197-209 plus the batch options
     `num_envs`, `autoreset` ('same_step' | None), `seed`."""
 

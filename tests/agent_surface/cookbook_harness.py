@@ -29,6 +29,8 @@ except Exception as e:
 ns["constraints"] = [c for c in ns["constraints"] if isinstance(c, gemb.constraints.SquaredConstraint) or isinstance(c, str)]
 run(15)
 cfg = ns["env"].build_config()
+import gymnasium  # the stand-in of tests/_shims here; the package subclasses whatever `gymnasium.Env` is importable
+out["is_gymnasium_env"] = isinstance(ns["env"], gymnasium.Env) and isinstance(ns["env"].action_space, gymnasium.spaces.Discrete)
 out.update(env_class=type(ns["env"]).__name__, n_state_ops=cfg.n_state_ops, n_ref=cfg.n_ref, init_random=cfg.init_random, tau=cfg.tau, u_sup=cfg.u_sup,
            solver_kind=cfg.solver_kind, state_names=list(ns["env"].state_names), reward_i_sq=cfg.reward_weight[ns["env"].state_names.index("i_sq")])
 print(json.dumps(out))

@@ -77,3 +77,4 @@ def test_gem_cookbook_cells_build_the_same_environment():
     assert (res["n_state_ops"], res["n_ref"], res["init_random"]) == (2, 2, 1)  # CosSin + StateNoise, i_sq + i_sd, uniform initialiser
     assert res["state_names"][-2:] == ["cos(epsilon)", "sin(epsilon)"]
     assert res["tau"] == 1e-5 and res["u_sup"] == 350.0 and res["reward_i_sq"] == 10.0
+    assert res["is_gymnasium_env"]  # gymnasium.Env / gymnasium.spaces when gymnasium is importable (wrappers such as TimeLimit check it)
