@@ -149,6 +149,7 @@ class DcMotor(ElectricMotor):
     CURRENTS = ["i_a", "i_e"]
     VOLTAGES = ["u_a", "u_e"]
     CURRENTS_IDX = [0, 1]
+    I_A_IDX, I_E_IDX = 0, 1  # positions in the motor's own ODE state (dc_motor.py)
     ODE_STATES = ["i_a", "i_e"]
     _default_motor_parameter = {"r_a": 16e-3, "r_e": 16e-2, "l_a": 19e-6, "l_e_prime": 1.7e-3, "l_e": 5.4e-3, "j_rotor": 0.0025}
     _default_nominal_values = dict(omega=300, torque=16.0, i=97, i_a=97, i_e=97, u=60, u_a=60, u_e=60)
@@ -204,6 +205,7 @@ class DcPermanentlyExcitedMotor(DcMotor):
     CURRENTS = ["i"]
     VOLTAGES = ["u"]
     CURRENTS_IDX = [0]
+    I_IDX = 0
     ODE_STATES = ["i"]
     _default_motor_parameter = {"r_a": 16e-3, "l_a": 19e-6, "psi_e": 0.165, "j_rotor": 0.025}
     _default_nominal_values = dict(omega=300, torque=16.0, i=97, u=60)
@@ -234,6 +236,7 @@ class DcSeriesMotor(DcMotor):
     CURRENTS = ["i"]
     VOLTAGES = ["u"]
     CURRENTS_IDX = [0]
+    I_IDX = 0
     ODE_STATES = ["i"]
     _default_motor_parameter = {"r_a": 16e-3, "r_e": 48e-3, "l_a": 19e-6, "l_e_prime": 1.7e-3, "l_e": 5.4e-3, "j_rotor": 0.0025}
     _default_initializer = {"states": {"i": 0.0}, "interval": None, "random_init": None, "random_params": (None, None)}
@@ -338,6 +341,7 @@ class SynchronousMotor(ThreePhaseMotor):
     CURRENTS = ["i_sd", "i_sq"]
     VOLTAGES = ["u_sd", "u_sq"]
     CURRENTS_IDX = [0, 1]
+    I_SD_IDX, I_SQ_IDX, EPSILON_IDX = 0, 1, 2  # positions in the motor's own ODE state (synchronous_motor.py)
     ODE_STATES = ["i_sd", "i_sq", "epsilon"]
     IO_VOLTAGES = ["u_a", "u_b", "u_c", "u_sd", "u_sq"]
     IO_CURRENTS = ["i_a", "i_b", "i_c", "i_sd", "i_sq"]
@@ -396,6 +400,7 @@ class ExternallyExcitedSynchronousMotor(SynchronousMotor):
     CURRENTS = ["i_sd", "i_sq", "i_e"]
     VOLTAGES = ["u_sd", "u_sq", "u_e"]
     CURRENTS_IDX = [0, 1, 2]
+    I_SD_IDX, I_SQ_IDX, I_E_IDX, EPSILON_IDX = 0, 1, 2, 3
     ODE_STATES = ["i_sd", "i_sq", "i_e", "epsilon"]
     IO_VOLTAGES = ["u_a", "u_b", "u_c", "u_sd", "u_sq", "u_e"]
     IO_CURRENTS = ["i_a", "i_b", "i_c", "i_sd", "i_sq", "i_e"]
@@ -438,6 +443,9 @@ class InductionMotor(ThreePhaseMotor):
     FLUXES = ["psi_ralpha", "psi_rbeta"]
     VOLTAGES = ["u_salpha", "u_sbeta"]
     CURRENTS_IDX = [0, 1]
+    I_SALPHA_IDX, I_SBETA_IDX, PSI_RALPHA_IDX, PSI_RBETA_IDX, EPSILON_IDX = 0, 1, 2, 3, 4  # induction_motor.py
+    FLUX_IDX = [2, 3]
+    STATOR_VOLTAGES = ["u_salpha", "u_sbeta"]
     ODE_STATES = ["i_salpha", "i_sbeta", "psi_ralpha", "psi_rbeta", "epsilon"]
     IO_VOLTAGES = ["u_sa", "u_sb", "u_sc", "u_salpha", "u_sbeta", "u_sd", "u_sq"]
     IO_CURRENTS = ["i_sa", "i_sb", "i_sc", "i_salpha", "i_sbeta", "i_sd", "i_sq"]

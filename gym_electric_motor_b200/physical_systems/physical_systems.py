@@ -68,6 +68,13 @@ class SCMLSystem(PhysicalSystem):
     Extra args: num_envs (N), device (CUDA ordinal or 'cuda:k'), dtype ('float32' = fp32 state + double-float rotor angle,
     'float64'), layout ('aos' row-per-env [N, n_state] | 'soa' field-major [n_state, N])."""
 
+    # class-level defaults of the index attributes, as in the reference (physical_systems.py:20-24); instances overwrite them in _set_indices
+    OMEGA_IDX = 0
+    TORQUE_IDX = 1
+    CURRENTS_IDX = []
+    VOLTAGES_IDX = []
+    U_SUP_IDX = -1
+
     _MOTOR_BASE = ElectricMotor
 
     def __init__(self, converter, motor, load, supply, ode_solver, tau=1e-4, calc_jacobian=None, num_envs=1, device=0,
