@@ -1376,6 +1376,7 @@ void gem_oracle_philox(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_1
 int gem_oracle_probe_set_action(gem_oracle* o, const double* act_f, const int32_t* act_i, double t) { return conv_set_action(o, o->env, act_f, act_i, t); }
 void gem_oracle_probe_convert(gem_oracle* o, const double* i_out, double t, double* u_out) { conv_convert(o, o->env, i_out, t, u_out); }
 void gem_oracle_probe_conv_reset(gem_oracle* o, double* u_out) { conv_reset(o, o->env, u_out); }
+double gem_oracle_probe_i_sup(gem_oracle* o, const double* i_out) { return conv_i_sup(o, o->env, i_out); }
 double gem_oracle_probe_mechanical_ode(gem_oracle* o, double omega, double tq) { return mechanical_ode(o, omega, tq, 0.0); }
 /* ExternalSpeedLoad: g = speed_profile(t + tau_load), one entry of the host-tabulated profile */
 double gem_oracle_probe_mechanical_ode_ext(gem_oracle* o, double omega, double tq, double g) { return mechanical_ode(o, omega, tq, g); }

@@ -43,6 +43,8 @@ def lib():
         _lib.gem_oracle_probe_set_action.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         _lib.gem_oracle_probe_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _lib.gem_oracle_probe_conv_reset.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.gem_oracle_probe_i_sup.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.gem_oracle_probe_i_sup.restype = C.c_double
         _lib.gem_oracle_probe_mechanical_ode.argtypes = [C.c_void_p, C.c_double, C.c_double]
         _lib.gem_oracle_probe_mechanical_ode.restype = C.c_double
         _lib.gem_oracle_probe_mechanical_ode_ext.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
@@ -160,6 +162,11 @@ class Oracle:
         u = np.zeros(6)
         self._lib.gem_oracle_probe_convert(self._h, _p(i), float(t), _p(u))
         return u
+
+    def probe_i_sup(self, i_out):
+        i = np.zeros(6)
+        i[: len(np.atleast_1d(i_out))] = np.atleast_1d(i_out)
+        return self._lib.gem_oracle_probe_i_sup(self._h, _p(i))
 
     def probe_conv_reset(self):
         u = np.zeros(6)

@@ -103,6 +103,110 @@ def finite_b6():
     return out
 
 
+def _literals_of(func, names, after=None):
+    """the LAST literal assigned to each of `names` in the body of test function `func` (optionally only assignments after the source line
+    containing `after`), evaluated with numpy in scope — the tests keep their tables as local literals"""
+    import ast
+    import inspect
+    import textwrap
+
+    src = textwrap.dedent(inspect.getsource(func))
+    start = 0
+    if after is not None:
+        start = next(i for i, l in enumerate(src.splitlines(), 1) if after in l)
+    found = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name) and node.targets[0].id in names \
+                and node.lineno >= start:
+            found[node.targets[0].id] = eval(compile(ast.Expression(node.value), "<literal>", "eval"), {"np": np})
+    missing = set(names) - set(found)
+    assert not missing, missing
+    return found
+
+
+def finite_b6_interlock():
+    """test_converters.py:634-697, second part of test_discrete_b6_bridge: bridge built from tests/conf.py:336 (tau = 2e-4, interlocking 1e-6),
+    ten actions, nineteen convert calls against the expected voltage table; replayed against the reference first"""
+    lit = _literals_of(tc.test_discrete_b6_bridge, ("actions", "i_ins", "expected_voltage"), after="# set parameter")
+    par = tc.cf.converter_parameter
+    conv = cv.FiniteB6BridgeConverter(**par)
+    conv.reset()
+    calls, k = [], 0
+    for t, a, i_in in zip(np.arange(len(lit["actions"])) * par["tau"], lit["actions"], lit["i_ins"]):
+        for ts in conv.set_action(a, t):
+            u = np.array(conv.convert(np.array(i_in), ts))
+            conv.i_sup(np.array(i_in))
+            assert all(u == lit["expected_voltage"][k])
+            calls.append(dict(action=int(a), t_set=float(t), i_in=[float(x[0]) for x in i_in], t_conv=float(ts), expected=[float(v) for v in lit["expected_voltage"][k]]))
+            k += 1
+    assert 10 < k <= len(lit["expected_voltage"])  # the table holds one row more than the protocol consumes
+    return dict(tau=float(par["tau"]), interlocking_time=float(par["interlocking_time"]), calls=calls)
+
+
+def cont_b6():
+    """test_converters.py:700-791 (test_continuous_b6_bridge): default bridge (u = action / 2) and the parametrised one (interlocking 1e-6 at
+    tau = 2e-4) against its expected voltage table; replayed against the reference first"""
+    lit = _literals_of(tc.test_continuous_b6_bridge, ("actions", "i_ins", "expected_voltages"))
+    out = []
+    for par, expected in ((dict(), np.asarray(lit["actions"]) / 2), (dict(tc.cf.converter_parameter), lit["expected_voltages"])):
+        conv = cv.ContB6BridgeConverter(**par)
+        assert all(conv.reset() == -0.5 * np.ones(3))
+        calls = []
+        for t, a, i_in, exp in zip(np.arange(len(lit["actions"])) * 1e-4, lit["actions"], lit["i_ins"], expected):
+            ts = conv.set_action(np.asarray(a).tolist(), t)
+            u = conv.convert(np.array(i_in), ts)
+            assert all(abs(float(np.ravel(v)[0]) - e) < 1e-9 for v, e in zip(u, exp))
+            calls.append(dict(action=[float(v) for v in a], t_set=float(t), i_in=[float(x[0]) for x in i_in], expected=[float(v) for v in exp],
+                              reference_result=[float(np.ravel(v)[0]) for v in u]))
+        out.append(dict(tau=float(conv._tau), interlocking_time=float(conv._interlocking_time), calls=calls))
+    return out
+
+
+def i_sup_grid():
+    """converter.i_sup (the supply current the RC supply integrates; converters.py:165-184, :289-298, :357-368, :425-435, :484-495, :831-839,
+    :903-911).  The reference's class-level tests pin it through properties (test_converters.py:929-935, :967-975, :1046-1055, :1081-1086,
+    :1091-1107 `i_sup == action * i_out` without interlocking and `|i_sup| <= |i_out|`, :1146-1154, :1419-1427, :1476-1486 sum over the
+    half bridges); here the same grids (plus the actions in between) are evaluated by the reference and recorded call by call."""
+    out = []
+    taus, ils = (1.0, 2.0), (0.0, 0.1, 1.0)  # :1091-1094
+    for kind, cls, actions, i_outs in (("1QC", cv.ContOneQuadrantConverter, ([0.0], [0.5], [1.0]), ([-1.0], [1.0], [0.0])),
+                                       ("2QC", cv.ContTwoQuadrantConverter, ([0.0], [0.5], [1.0]), ([0.0], [0.1], [-1.0])),
+                                       ("4QC", cv.ContFourQuadrantConverter, ([-1.0], [-0.3], [0.0], [0.5], [1.0]), ([0.0], [1.0], [-2.0])),
+                                       ("B6", cv.ContB6BridgeConverter, ([1, -1, 0.65], [0.75, -0.95, -0.3], [-0.25, 0.98, -1], [0, 0, 0]),
+                                        ([-1, -1, 0], [1, 1, -2], [0, 0, 1]))):
+        for tau in taus:
+            for il in ils:
+                if il >= tau:
+                    continue
+                conv = cls(tau=tau, interlocking_time=il)
+                conv.reset()
+                calls = []
+                for n, a in enumerate(actions):
+                    conv.set_action(list(a), n * tau)
+                    for i_out in i_outs:
+                        got = float(conv.i_sup(list(i_out)))  # flat [i_a, i_b, i_c] for the bridge (:911)
+                        if kind == "2QC":
+                            assert abs(got) <= abs(i_out[0]) and (il > 0 or got == a[0] * i_out[0])
+                        calls.append(dict(action=[float(v) for v in a], t_set=float(n * tau), i_out=[float(v) for v in i_out], expected=got))
+                out.append(dict(kind=kind, finite=0, tau=tau, interlocking_time=il, calls=calls))
+    for kind, cls, i_outs in (("1QC", cv.FiniteOneQuadrantConverter, ([-12.0], [12.0])), ("2QC", cv.FiniteTwoQuadrantConverter, ([-1.0], [0.0], [1.0])),
+                              ("4QC", cv.FiniteFourQuadrantConverter, ([-1.0], [0.0], [1.0])),
+                              ("B6", cv.FiniteB6BridgeConverter, ([-1, -1, 0], [1, 1, -2], [0, 0, 1]))):
+        for il in (0.0, 1e-6):
+            conv = cls(tau=1e-5, interlocking_time=il)
+            conv.reset()
+            calls = []
+            for n in range(2 * conv.action_space.n):
+                a = (n * 3) % conv.action_space.n
+                for ts in conv.set_action(a, n * 1e-5):
+                    for i_out in i_outs:
+                        conv.convert(list(i_out), ts)
+                        calls.append(dict(action=int(a), t_set=float(n * 1e-5), t_conv=float(ts), i_out=[float(v) for v in i_out],
+                                          expected=float(conv.i_sup(list(i_out)))))
+            out.append(dict(kind=kind, finite=1, tau=1e-5, interlocking_time=il, calls=calls))
+    return out
+
+
 def cont_qc():
     out = []
     for kind, cls in (("1QC", cv.ContOneQuadrantConverter), ("2QC", cv.ContTwoQuadrantConverter), ("4QC", cv.ContFourQuadrantConverter)):
@@ -385,10 +489,10 @@ def wiener_walk():
 
 
 if __name__ == "__main__":
-    ka = dict(wiener_walk=wiener_walk(), poly_load_formula=poly_load_formula(), periodic_references=periodic_references(), dq_to_abc=dq_to_abc(), dead_time=dead_time(), supplies=supplies(), ext_speed_load=ext_speed_load(),
+    ka = dict(i_sup=i_sup_grid(), finite_b6_interlock=finite_b6_interlock(), cont_b6=cont_b6(), wiener_walk=wiener_walk(), poly_load_formula=poly_load_formula(), periodic_references=periodic_references(), dq_to_abc=dq_to_abc(), dead_time=dead_time(), supplies=supplies(), ext_speed_load=ext_speed_load(),
               finite_qc=finite_qc(), finite_b6=finite_b6(), cont_qc=cont_qc(), poly_load=poly_load(), euler=euler_solver(), constraints=constraints(),
               wse_rewards=wse_rewards())
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(ka, f)
     print({k: (len(v) if isinstance(v, list) else len(v.get("cases", v))) for k, v in ka.items()},
-          "convert calls:", sum(len(c["calls"]) for k in ("finite_qc", "finite_b6", "cont_qc") for c in ka[k]))
+          "convert calls:", sum(len(c["calls"]) for k in ("finite_qc", "finite_b6", "cont_qc", "cont_b6") for c in ka[k]) + len(ka["finite_b6_interlock"]["calls"]))

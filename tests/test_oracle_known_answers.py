@@ -3,7 +3,7 @@
 tests/golden/known_answers.json is produced by tests/golden/make_known_answers.py, which imports the reference's test modules
 (tables in module globals / pytest.mark.parametrize arguments), replays the reference tests' call protocol against the reference
 implementation, and records every call with the value the reference's TABLE demands.  Here the same calls go through the oracle's
-component-level probes: converters (3471 convert calls: finite 1QC/2QC/4QC with and without interlocking over three taus, the B6
+component-level probes: converters (3509 convert calls and the supply current i_sup of every converter kind: finite 1QC/2QC/4QC with and without interlocking over three taus, the B6
 bridge leg by leg, continuous 1QC/2QC/4QC against the tests' `comparable_voltage`), PolynomialStaticLoad.mechanical_ode (known answers
 and the closed form of test_load.py), ExternalSpeedLoad.mechanical_ode, the RC supply equation and AC1 supply voltages, the
 DqToAbcActionProcessor vectors, the DeadTimeProcessor FIFO protocol, one sub-episode of each periodic reference generator and the
@@ -257,3 +257,48 @@ def test_polynomial_static_load_closed_form(oracle_lib):
         sim = oracle_lib.Oracle(cfg)
         got = sim.probe_mechanical_ode(c["omega"], c["torque"])
         assert abs(got - c["expected"]) <= 4e-16 * max(1.0, abs(c["expected"])), c
+
+
+def test_finite_b6_bridge_with_interlocking_follows_the_reference_table(oracle_lib):
+    """test_converters.py:634-697: tau = 2e-4, interlocking 1e-6, ten actions, the whole three-leg voltage vector per convert call"""
+    case = KA["finite_b6_interlock"]
+    sim = oracle_lib.Oracle(_base_cfg(motor=K.MOTOR_PMSM, conv=(K.CONV_B6, K.CONV_NONE), finite=1, tau=case["tau"], il=case["interlocking_time"]))
+    assert list(sim.probe_conv_reset()[:3]) == [-0.5, -0.5, -0.5]
+    last = None
+    assert len(case["calls"]) >= 18
+    for c in case["calls"]:
+        if (c["action"], c["t_set"]) != last:
+            sim.probe_set_action(c["action"], c["t_set"])
+            last = (c["action"], c["t_set"])
+        assert list(sim.probe_convert(c["i_in"], c["t_conv"])[:3]) == c["expected"], c
+
+
+@pytest.mark.parametrize("case", KA["cont_b6"], ids=lambda c: f"il{c['interlocking_time']:g}")
+def test_continuous_b6_bridge_known_answers(oracle_lib, case):
+    """test_converters.py:700-791: default bridge (u = action / 2) and the parametrised bridge's expected voltages with interlocking"""
+    sim = oracle_lib.Oracle(_base_cfg(motor=K.MOTOR_PMSM, conv=(K.CONV_B6, K.CONV_NONE), tau=case["tau"], il=case["interlocking_time"]))
+    assert list(sim.probe_conv_reset()[:3]) == [-0.5, -0.5, -0.5]
+    for c in case["calls"]:
+        sim.probe_set_action(c["action"], c["t_set"])
+        u = sim.probe_convert(c["i_in"], c["t_set"] + case["tau"])[:3]
+        assert np.max(np.abs(u - np.asarray(c["expected"]))) < 1e-9, c          # the test's own tolerance
+        assert np.max(np.abs(u - np.asarray(c["reference_result"]))) < 1e-14
+
+
+@pytest.mark.parametrize("case", KA["i_sup"], ids=lambda c: f"{'fin' if c['finite'] else 'cont'}-{c['kind']}-tau{c['tau']:g}-il{c['interlocking_time']:g}")
+def test_converter_supply_current_follows_the_reference(oracle_lib, case):
+    """converter.i_sup over the grids of the reference's class-level converter tests (test_converters.py:929-1486), values recorded from the
+    reference call by call: the quantity the RC supply integrates (and the kernel restates)."""
+    kind = K.CONV_B6 if case["kind"] == "B6" else CONV[case["kind"]]
+    motor = K.MOTOR_PMSM if case["kind"] == "B6" else K.MOTOR_PERMEX_DC
+    sim = oracle_lib.Oracle(_base_cfg(motor=motor, conv=(kind, K.CONV_NONE), finite=case["finite"], tau=case["tau"], il=case["interlocking_time"]))
+    sim.probe_conv_reset()
+    last = None
+    for c in case["calls"]:
+        if (c["action"], c["t_set"]) != last:
+            sim.probe_set_action(c["action"], c["t_set"])
+            last = (c["action"], c["t_set"])
+        if case["finite"]:
+            sim.probe_convert(c["i_out"], c["t_conv"])
+        got = sim.probe_i_sup(c["i_out"])
+        assert abs(got - c["expected"]) <= 1e-15 * max(1.0, abs(c["expected"])), c
