@@ -123,9 +123,37 @@ class ElectricMotorEnvironment(_EnvBase):
     def reference_generator(self):
         return self._reference_generator
 
+    @reference_generator.setter
+    def reference_generator(self, reference_generator):
+        """reference core.py:132-142: a new generator, then a reset is required.  Here the generator is part of the device handle's
+        configuration, so the handle is dropped and rebuilt at the next reset."""
+        if not isinstance(reference_generator, ReferenceGenerator):
+            raise TypeError("reference_generator must be a built-in gym_electric_motor_b200 ReferenceGenerator")
+        self._reference_generator = reference_generator
+        self._reference_generator.set_modules(self._physical_system)
+        self._reward_function.set_modules(self._physical_system, self._reference_generator, self._constraint_monitor)
+        self.observation_space = Tuple((self.observation_space.spaces[0], self._reference_generator.reference_space))
+        self._drop_handle()
+
     @property
     def reward_function(self):
         return self._reward_function
+
+    @reward_function.setter
+    def reward_function(self, reward_function):
+        """reference core.py:153-162"""
+        if not isinstance(reward_function, RewardFunction):
+            raise TypeError("reward_function must be a built-in gym_electric_motor_b200 RewardFunction")
+        self._reward_function = reward_function
+        self._reward_function.set_modules(self._physical_system, self._reference_generator, self._constraint_monitor)
+        self.reward_range = self._reward_function.reward_range
+        self._drop_handle()
+
+    def _drop_handle(self):
+        self._terminated = True
+        if self._sim is not None:
+            self._sim.close()
+            self._sim = None
 
     @property
     def constraint_monitor(self):
@@ -138,11 +166,12 @@ class ElectricMotorEnvironment(_EnvBase):
 
     @property
     def limits(self):
-        return self._physical_system.limits
+        """limits of the states the env returns, i.e. after the state filter (reference core.py:169-174)"""
+        return self._physical_system.limits[self.state_filter]
 
     @property
     def state_names(self):
-        return self._physical_system.state_names
+        return [self._physical_system.state_names[s] for s in self.state_filter]
 
     @property
     def reference_names(self):
@@ -150,7 +179,7 @@ class ElectricMotorEnvironment(_EnvBase):
 
     @property
     def nominal_state(self):
-        return self._physical_system.nominal_state
+        return self._physical_system.nominal_state[self.state_filter]
 
     @property
     def unwrapped(self):

@@ -111,6 +111,9 @@ def test_kwargs_semantics():
     assert env.physical_system.tau == 5e-5 and env.physical_system.converter.tau == 5e-5
     assert env.physical_system.limits[-1] == 400.0
     assert env.state_filter == [5, 6]
+    # env.limits / state_names / nominal_state are those of the FILTERED observation (reference core.py:169-190, tests/test_core.py:255-278)
+    assert env.state_names == ["i_sd", "i_sq"] and list(env.limits) == [400.0, 400.0] and list(env.nominal_state) == [240.0, 240.0]
+    assert len(env.physical_system.state_names) == 14
     cfg = env.build_config()
     assert cfg.solver_kind == K.SOLVER_EULER and cfg.solver_nsteps == 3
     with pytest.raises(KeyError):
@@ -352,3 +355,20 @@ def test_host_side_transformations_match_the_definitions():
     assert np.allclose(ps.alphabeta_to_dq_space(ab, 0.83), dq) and np.allclose(ps.dq_to_alphabeta_space(dq, 0.83), ab)
     assert np.allclose(ps.abc_to_alphabeta_space(abc), ab) and np.allclose(ps.alphabeta_to_abc_space(ab), abc - abc.mean())
     assert np.allclose(m.q_me(dq, 0.2), m.q(dq, 0.2 * m.motor_parameter["p"]))
+
+
+def test_reference_generator_and_reward_function_can_be_replaced():
+    """reference core.py:132-162 / tests/test_core.py:220-262: new component, reset required; here the device handle is rebuilt from the
+    new configuration at the next reset"""
+    env = gem.make("Cont-SC-PermExDc-v0")
+    assert env.build_config().ref_kind[0] == K.REF_WIENER
+    env.reference_generator = gem.reference_generators.SinusoidalReferenceGenerator(reference_state="omega", frequency_range=(5, 5))
+    cfg = env.build_config()
+    assert cfg.ref_kind[0] == K.REF_SINUS and cfg.ref_freq_lo[0] == 5.0 and env.reference_generator.reference_names == ["omega"]
+    env.reward_function = gem.reward_functions.WeightedSumOfErrors(reward_weights=dict(omega=2.0), gamma=0.5)
+    cfg = env.build_config()
+    assert cfg.reward_weight[0] == 2.0 and env.reward_range == env.reward_function.reward_range
+    with pytest.raises(TypeError):
+        env.reference_generator = object()
+    with pytest.raises(TypeError):
+        env.reward_function = lambda *a: 0.0
