@@ -154,6 +154,7 @@ class ElectricMotorEnvironment(_EnvBase):
         if self._sim is not None:
             self._sim.close()
             self._sim = None
+            self._physical_system.attach(None)
 
     @property
     def constraint_monitor(self):
