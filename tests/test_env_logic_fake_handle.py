@@ -122,3 +122,21 @@ def test_batched_contract_reseed_and_setters(scripted):
     assert third is not second and third.cfg.ref_kind[0] == K.REF_CONST and third.cfg.ref_value[0] == 0.3
     env.close()
     assert third.closed
+
+
+def test_vector_facade_flow(scripted):
+    """gymnasium.vector conventions of gem.vector.make_vec: (obs, info) / 5-tuple, flattened Box observation, same-step auto-reset mode"""
+    venv = gem.vector.make_vec("Cont-CC-PMSM-v0", num_envs=5, flatten_obs=True, seed=9)
+    obs, info = venv.reset(seed=9)
+    assert tuple(obs.shape) == (5, 16) and venv.observation_space.shape == (5, 16) and info == {}
+    handle = scripted.created[-1]
+    assert handle.cfg.autoreset == K.AUTORESET_SAME_STEP and venv.metadata["autoreset_mode"] == "same_step"
+    handle.terminate_at = 1
+    obs, rewards, terminations, truncations, infos = venv.step(torch.zeros(5, 3))
+    assert tuple(obs.shape) == (5, 16) and terminations.tolist() == [True, False, False, False, False] and not truncations.any()
+    assert torch.allclose(obs[:, 14:], torch.full((5, 2), 0.25)) and torch.allclose(rewards, torch.full((5,), -0.5))
+    plain = gem.vector.make_vec("Finite-SC-PMSM-v0", num_envs=3)
+    (state, ref), _ = plain.reset()
+    assert tuple(state.shape) == (3, 14) and tuple(ref.shape) == (3, 1) and plain.single_action_space.n == 8
+    venv.close(); plain.close()
+    assert handle.closed and venv.closed
