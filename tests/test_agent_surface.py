@@ -78,3 +78,16 @@ def test_gem_cookbook_cells_build_the_same_environment():
     assert res["state_names"][-2:] == ["cos(epsilon)", "sin(epsilon)"]
     assert res["tau"] == 1e-5 and res["u_sup"] == 350.0 and res["reward_i_sq"] == 10.0
     assert res["is_gymnasium_env"]  # gymnasium.Env / gymnasium.spaces when gymnasium is importable (wrappers such as TimeLimit check it)
+
+
+def test_integration_md_binding_stub_reaches_gemb200_create():
+    """the ctypes stub of INTEGRATION.md section B, run verbatim against a reference SCMLSystem (tests/agent_surface/integration_stub_harness.py)"""
+    import torch
+
+    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "integration_stub_harness.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    verdict = out.stdout.strip().splitlines()[-1]
+    if torch.cuda.is_available():
+        assert verdict.startswith("created"), verdict
+    else:
+        assert verdict.startswith("GemB200Error") and "rc=-2" in verdict, verdict   # GEMB200_E_CUDA: validation passed, no device
