@@ -112,6 +112,17 @@ def _default_reference(a, c, m):
     return WienerProcessReferenceGenerator, dict(reference_state="omega", sigma_range=_SC_SIGMA[m][0 if a == "Cont" else 1])
 
 
+def _default_reward_weights(c, m):
+    """the env classes name their reward weights explicitly — the controlled currents in equal shares, omega or torque (e.g.
+    envs/gym_pmsm/cont_cc_pmsm_env.py:172, gym_eesm/cont_cc_eesm_env.py:183, gym_pmsm/cont_sc_pmsm_env.py:169) — so a user-supplied
+    reference generator on another state does NOT move the default reward with it"""
+    if c == "SC":
+        return dict(omega=1.0)
+    if c == "TC":
+        return dict(torque=1.0)
+    return {name: 1.0 / len(_CC_STATES[m]) for name in _CC_STATES[m]}
+
+
 def _default_constraints(m):
     if m in ("PermExDc", "SeriesDc"):
         return ("i",)
@@ -159,7 +170,7 @@ def make(env_id, supply=None, converter=None, motor=None, load=None, ode_solver=
         calc_jacobian=calc_jacobian, tau=tau, num_envs=n, device=device, dtype=dtype, layout=layout, env_index_offset=env_index_offset,
     )
     reference_generator = initialize(ReferenceGenerator, reference_generator, ref_cls, ref_args)
-    reward_function = initialize(RewardFunction, reward_function, WeightedSumOfErrors, dict())
+    reward_function = initialize(RewardFunction, reward_function, WeightedSumOfErrors, dict(reward_weights=_default_reward_weights(c, m)))
     if constraints is _NOT_SET:
         constraints = _default_constraints(m)
     if visualization is not None and not isinstance(visualization, (ElectricMotorVisualization, list, tuple)):

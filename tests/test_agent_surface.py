@@ -44,26 +44,35 @@ def test_reference_example_agent_reads_the_same_surface():
             assert r["error"] == m["error"], (env_id, r["error"], m["error"])
 
 
-def test_reference_example_scripts_run_up_to_make():
-    """examples/environment_features/*.py and examples/classic_controllers/*_example.py, unmodified, up to `env = gem.make(...)` +
-    `env.build_config()` (tests/agent_surface/examples_harness.py).  scim_ideal_grid_simulation.py simulates at import time, so without a
-    GPU it must stop exactly at the loud no-CUDA error — never earlier, never with a CPU fallback."""
-    import torch
-
-    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "examples_harness.py")], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    res = json.loads(out.stdout.strip().splitlines()[-1])
-    assert len(res) >= 12
-    assert sum(k.endswith(".ipynb") for k in res) >= 3  # the RL (DDPG dq control with wrappers, DQN) and MPC notebooks' gem.make cells
-    for script, verdict in res.items():
-        if script == "scim_ideal_grid_simulation.py" and not torch.cuda.is_available():
-            assert verdict.startswith("GemB200Error: no CUDA device"), verdict
-        elif script == "pmsm_mpc_dq_current_control.ipynb":
+def test_reference_example_scripts_build_the_same_environments():
+    """examples/environment_features/*.py, examples/classic_controllers/*_example.py and the gem.make cells of the RL / MPC notebooks,
+    unmodified, up to `env = gem.make(...)` (tests/agent_surface/examples_harness.py), against the reference and against this package:
+    what the user's kwargs produced — names, limits, nominal state, spaces, tau, motor parameters, inertia, supply voltage, reward
+    weights and range — must be identical, and this package must also derive its C-ABI config from it."""
+    res = {}
+    for impl in ("reference", "b200"):
+        out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "examples_harness.py"), "--impl", impl], capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
+    ref, mine = res["reference"], res["b200"]
+    assert sorted(ref) == sorted(mine) and len(ref) >= 12 and sum(k.endswith(".ipynb") for k in ref) >= 3
+    compared = 0
+    for script in sorted(ref):
+        assert ref[script]["verdict"] == "ok", (script, ref[script]["verdict"])  # the harness itself must not be the reason for a gap
+        if script == "pmsm_mpc_dq_current_control.ipynb":
             # two switched generators with three sub-generators each = 8 generator entries; the kernel's table holds 4 (DESIGN.md §7, open):
             # refused loudly
-            assert verdict.startswith("NotImplementedError") and "generator entries" in verdict, verdict
-        else:
-            assert verdict == "ok", (script, verdict)
+            assert mine[script]["verdict"].startswith("NotImplementedError") and "generator entries" in mine[script]["verdict"]
+            continue
+        assert mine[script]["verdict"] == "ok", (script, mine[script]["verdict"])
+        a, b = ref[script]["summary"], mine[script]["summary"]
+        assert sorted(a) == sorted(b)
+        for field in a:
+            if a[field] != b[field]:
+                assert np.allclose(np.asarray(a[field], dtype=float), np.asarray(b[field], dtype=float), rtol=1e-12, atol=0), (script, field, a[field], b[field])
+        compared += 1
+    assert compared >= 11
 
 
 def test_gem_cookbook_cells_build_the_same_environment():
