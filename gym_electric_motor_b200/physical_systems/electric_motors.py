@@ -411,6 +411,16 @@ class ExternallyExcitedSynchronousMotor(SynchronousMotor):
     _default_initializer = {"states": {"i_sq": 0.0, "i_sd": 0.0, "i_e": 0.0, "epsilon": 0.0}, "interval": None,
                             "random_init": None, "random_params": (None, None)}
 
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        # the reference publishes the rotor quantities referred to the stator side in the same dict (agents read e.g. mp["sigma"]),
+        # externally_excited_synchronous_motor.py:125-136; the kernel derives its coefficients from the primary keys in gemb200.cu
+        mp = self._motor_parameter
+        turns = mp["k"]
+        mp["r_E"], mp["l_M"], mp["l_E"] = 1.5 * turns**2 * mp["r_e"], 1.5 * turns * mp["l_m"], 1.5 * turns**2 * mp["l_e"]
+        mp["i_k_rs"] = 2 / 3 / turns
+        mp["sigma"] = 1 - mp["l_M"] ** 2 / (mp["l_d"] * mp["l_E"])
+
     def _derived(self):
         mp = self._motor_parameter
         return mp["k"] * 3 / 2 * mp["l_m"], 2 / 3 / mp["k"]  # l_M, i_k_rs (:129-135)

@@ -1,0 +1,158 @@
+"""`gem.make(env_id, **kwargs)` for a matrix of user-level kwargs — motor parameters / limits / nominal values, supplies, loads, taus,
+state filters, reference generators with explicit ranges and margins, reward-function settings, constraint specs, wrappers — built once
+with the unmodified reference (`--impl reference`) and once with this repo's host package aliased as `gym_electric_motor`
+(`--impl b200`, which also derives the C-ABI config).  Each case is a source snippet evaluated with `gem` bound to the respective
+package, so both sides see literally the same user code.  Prints {case: {"verdict", "summary"}}; the summaries (names, limits, nominal
+state, spaces, tau, motor / load parameters, supply, reward weights / range / bias, constraint list, generator margins) must agree.
+No stepping, no GPU.  Container-only: needs /root/reference."""
+import json
+import sys
+import warnings
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = __file__.rsplit("/", 2)[0]
+
+PRELUDE = """
+import numpy as np
+ps = gem.physical_systems
+rg = gem.reference_generators
+rf = gem.reward_functions
+psw = gem.physical_system_wrappers
+"""
+
+CASES = {
+    "pmsm_motor_parameter": 'gem.make("Cont-CC-PMSM-v0", motor=dict(motor_parameter=dict(r_s=25e-3, l_d=0.5e-3, psi_p=70e-3, p=4)))',
+    "pmsm_limits_nominal": 'gem.make("Cont-SC-PMSM-v0", motor=dict(limit_values=dict(omega=500.0, i=300.0, u=400.0), nominal_values=dict(omega=400.0, i=200.0, u=400.0)))',
+    "pmsm_supply_dict": 'gem.make("Finite-CC-PMSM-v0", supply=dict(u_nominal=350.0))',
+    "pmsm_supply_instance": 'gem.make("Cont-TC-PMSM-v0", supply=ps.IdealVoltageSupply(u_nominal=500.0))',
+    "pmsm_tau_filter": 'gem.make("Cont-CC-PMSM-v0", tau=5e-5, state_filter=["omega", "i_sd", "i_sq", "epsilon"])',
+    "pmsm_load_poly": 'gem.make("Cont-CC-PMSM-v0", load=ps.PolynomialStaticLoad(load_parameter=dict(a=0.1, b=0.02, c=1e-4, j_load=0.01)))',
+    "pmsm_load_const": 'gem.make("Cont-TC-PMSM-v0", load=ps.ConstantSpeedLoad(omega_fixed=150.0))',
+    "pmsm_load_dict": 'gem.make("Cont-SC-PMSM-v0", load=dict(load_parameter=dict(a=0.0, b=0.0, c=0.0, j_load=2e-3)))',
+    "synrm_parameter": 'gem.make("Cont-CC-SynRM-v0", motor=dict(motor_parameter=dict(l_d=80e-3, l_q=20e-3, r_s=0.7)))',
+    "eesm_parameter": 'gem.make("Cont-CC-EESM-v0", motor=dict(motor_parameter=dict(r_e=8e-3, l_e=2e-3, l_m=1.4e-3)), supply=dict(u_nominal=320.0))',
+    "scim_parameter": 'gem.make("Cont-SC-SCIM-v0", motor=dict(motor_parameter=dict(r_s=3.0, r_r=1.4, l_m=0.15), limit_values=dict(i=8.0)))',
+    "dfim_parameter": 'gem.make("Cont-TC-DFIM-v0", motor=dict(motor_parameter=dict(r_s=5e-3, l_m=3e-3)))',
+    "permex_parameter": 'gem.make("Cont-SC-PermExDc-v0", motor=dict(motor_parameter=dict(r_a=25e-3, l_a=3e-5, psi_e=0.2, j_rotor=0.03)))',
+    "series_limits": 'gem.make("Cont-CC-SeriesDc-v0", motor=dict(limit_values=dict(i=120.0, omega=250.0), nominal_values=dict(i=60.0)))',
+    "shunt_supply": 'gem.make("Finite-SC-ShuntDc-v0", supply=dict(u_nominal=300.0), tau=2e-5)',
+    "extex_parameter": 'gem.make("Cont-TC-ExtExDc-v0", motor=dict(motor_parameter=dict(l_e_prime=0.01, r_e=6.0)))',
+    "interlock_b6": 'gem.make("Finite-CC-PMSM-v0", converter=dict(interlocking_time=1e-6))',
+    "converter_instance_1qc": 'gem.make("Cont-CC-PermExDc-v0", converter=ps.ContOneQuadrantConverter())',
+    "converter_instance_2qc": 'gem.make("Finite-SC-SeriesDc-v0", converter=ps.FiniteTwoQuadrantConverter(interlocking_time=2e-6))',
+    "wiener_ranges": 'gem.make("Cont-SC-PMSM-v0", reference_generator=rg.WienerProcessReferenceGenerator(reference_state="omega", sigma_range=(1e-3, 1e-2), episode_lengths=(200, 300), limit_margin=(-0.2, 0.7)))',
+    "wiener_dict": 'gem.make("Cont-TC-PMSM-v0", reference_generator=dict(sigma_range=(5e-3, 5e-2), limit_margin=0.4))',
+    "const_ref": 'gem.make("Cont-SC-PermExDc-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="omega", reference_value=0.35))',
+    "sinus_ref": 'gem.make("Cont-SC-SeriesDc-v0", reference_generator=rg.SinusoidalReferenceGenerator(reference_state="omega", amplitude_range=(0.1, 0.4), frequency_range=(2, 9), offset_range=(-0.1, 0.3), episode_lengths=1000))',
+    "step_ref_margin": 'gem.make("Cont-TC-SynRM-v0", reference_generator=rg.StepReferenceGenerator(reference_state="torque", limit_margin=(-0.5, 0.5), amplitude_range=(0, 0.6)))',
+    "triangle_ref_other_state": 'gem.make("Cont-CC-PermExDc-v0", reference_generator=rg.TriangularReferenceGenerator(reference_state="omega"))',
+    "multi_ref": 'gem.make("Cont-CC-PMSM-v0", reference_generator=rg.MultipleReferenceGenerator([rg.ConstReferenceGenerator(reference_state="i_sd", reference_value=-0.1), rg.WienerProcessReferenceGenerator(reference_state="i_sq", limit_margin=0.5)]))',
+    "switched_ref": 'gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator([rg.SinusoidalReferenceGenerator(reference_state="omega"), rg.WienerProcessReferenceGenerator(reference_state="omega")], p=[0.3, 0.7], super_episode_length=(500, 900)))',
+    "reward_dict": 'gem.make("Cont-CC-PMSM-v0", reward_function=dict(gamma=0.99, reward_power=2))',
+    "reward_weights_bias": 'gem.make("Cont-CC-PMSM-v0", reward_function=rf.WeightedSumOfErrors(reward_weights=dict(i_sd=2.0, i_sq=1.0, omega=0.5), bias="positive", gamma=0.8))',
+    "reward_violation": 'gem.make("Cont-SC-PermExDc-v0", reward_function=rf.WeightedSumOfErrors(reward_weights=[1, 0, 0.5, 0, 0], violation_reward=-42.0, reward_power=[1, 1, 0.5, 1, 1], bias=0.2))',
+    "constraints_names": 'gem.make("Cont-CC-PMSM-v0", constraints=("i_sd", "i_sq", "omega"))',
+    "constraints_squared": 'gem.make("Cont-CC-EESM-v0", constraints=(gem.constraints.SquaredConstraint(("i_sd", "i_sq")), gem.constraints.LimitConstraint(("i_e", "torque"))))',
+    "constraints_none": 'gem.make("Finite-TC-SCIM-v0", constraints=())',
+    "wrappers_cossin_dead": 'gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.CosSinProcessor(angle="epsilon"), psw.DqToAbcActionProcessor.make("PMSM"), psw.DeadTimeProcessor(steps=2)])',
+    "wrappers_flux_observer": 'gem.make("Cont-CC-SCIM-v0", physical_system_wrappers=[psw.FluxObserver()], state_filter=["i_sd", "i_sq", "psi_abs", "psi_angle"])',
+    "wrappers_noise": 'gem.make("Cont-SC-PermExDc-v0", physical_system_wrappers=[psw.StateNoiseProcessor(states=["omega", "i"], random_dist="uniform", random_kwargs=dict(low=-0.01, high=0.01))])',
+    "rc_supply": 'gem.make("Cont-SC-PermExDc-v0", supply=ps.RCVoltageSupply(u_nominal=80.0, supply_parameter=dict(R=0.5, C=2e-3)))',
+    "ac1_supply": 'gem.make("Cont-CC-SeriesDc-v0", supply=ps.AC1PhaseSupply(u_nominal=230.0, supply_parameter=dict(frequency=50, phase=0.3)))',
+    "motor_initializer": 'gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(states=dict(i_sd=-10.0, i_sq=20.0, epsilon=1.0))))',
+    "shunt_cc_default_filter": 'gem.make("Cont-CC-ShuntDc-v0", state_filter=["i_a", "i_e", "i_sum"])',
+    "shunt_limits": 'gem.make("Finite-TC-ShuntDc-v0", motor=dict(limit_values=dict(i_a=80.0, i_e=4.0, omega=300.0)))',
+    "extex_supply_limits": 'gem.make("Finite-CC-ExtExDc-v0", supply=dict(u_nominal=100.0), motor=dict(nominal_values=dict(i_a=40.0, i_e=3.0)))',
+    "dfim_supply": 'gem.make("Finite-SC-DFIM-v0", supply=dict(u_nominal=700.0))',
+    "scim_load": 'gem.make("Cont-TC-SCIM-v0", load=ps.PolynomialStaticLoad(dict(a=0.05, b=0.01, c=0.0, j_load=5e-3)))',
+    "eesm_sc_reward": 'gem.make("Cont-SC-EESM-v0", reward_function=dict(reward_weights=dict(omega=1.0, i_e=0.1), gamma=0.95))',
+    "eesm_ref_ie": 'gem.make("Cont-CC-EESM-v0", reference_generator=rg.MultipleReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="i_e", limit_margin=(0.0, 0.6)), rg.ConstReferenceGenerator(reference_state="i_sq", reference_value=0.2)]))',
+    "limit_constraint_all": 'gem.make("Cont-CC-PermExDc-v0", constraints=(gem.constraints.LimitConstraint("all_states"),))',
+    "limit_constraint_mixed": 'gem.make("Cont-SC-PMSM-v0", constraints=("omega", gem.constraints.SquaredConstraint(("i_sd", "i_sq")), "torque"))',
+    "reward_power_scalar": 'gem.make("Cont-TC-PermExDc-v0", reward_function=dict(reward_power=0.5, bias=1.0))',
+    "reward_normed": 'gem.make("Cont-CC-SCIM-v0", reward_function=rf.WeightedSumOfErrors(reward_weights=dict(i_sd=3.0, i_sq=1.0), normed_reward_weights=True))',
+    "laplace_ref": 'gem.make("Cont-SC-ShuntDc-v0", reference_generator=rg.LaplaceProcessReferenceGenerator(reference_state="omega", sigma_range=(1e-3, 1e-2)))',
+    "sawtooth_ref": 'gem.make("Finite-SC-PMSM-v0", reference_generator=rg.SawtoothReferenceGenerator(reference_state="omega", amplitude_range=(0.0, 0.3), frequency_range=(1, 4)))',
+    "gaussian_initializer": 'gem.make("Cont-CC-SeriesDc-v0", motor=dict(motor_initializer=dict(random_init="gaussian", random_params=(25.0, 3.0), states=dict(i=0.0))))',
+    "uniform_initializer_pmsm": 'gem.make("Finite-CC-PMSM-v0", motor=dict(motor_initializer=dict(random_init="uniform", interval=[[-100, 100], [-100, 100], [-3.0, 3.0]])))',
+    "tau_finite_dc": 'gem.make("Finite-CC-PermExDc-v0", tau=2e-5, converter=dict(interlocking_time=1e-6))',
+    "omega_load_instance_sc": 'gem.make("Cont-SC-SynRM-v0", load=ps.PolynomialStaticLoad(load_parameter=dict(a=0.01, b=0.01, c=0.0, j_load=1e-3), limits=dict(omega=200.0)))',
+    "dq_wrapper_scim": 'gem.make("Cont-CC-SCIM-v0", physical_system_wrappers=[psw.FluxObserver(), psw.DqToAbcActionProcessor.make("SCIM")])',
+    "cossin_remove": 'gem.make("Cont-SC-PMSM-v0", physical_system_wrappers=[psw.CosSinProcessor(angle="epsilon", remove_angle=True)])',
+    "dead_time_finite": 'gem.make("Finite-CC-SynRM-v0", physical_system_wrappers=[psw.DeadTimeProcessor(steps=3)])',
+    "load_initializer_uniform": 'gem.make("Cont-SC-PermExDc-v0", load=dict(load_initializer=dict(random_init="uniform", interval=[[20.0, 60.0]])))',
+}
+
+
+def summary(env):
+    ps_ = env.physical_system.unwrapped
+    sp = env.action_space
+    rgen = env.reference_generator
+    subs = getattr(rgen, "_sub_generators", [rgen])
+    margins = []
+    for g in subs:
+        for h in getattr(g, "_sub_generators", [g]):
+            m = getattr(h, "_limit_margin", None)
+            margins.append(None if m is None else [float(v) for v in np.ravel(m)])
+    cons = []
+    for c in env.constraint_monitor.constraints:
+        names = getattr(c, "_states", None)
+        if names is None:
+            names = list(np.asarray(env.physical_system.state_names)[np.asarray(c._observed_states, dtype=bool)])
+        cons.append([type(c).__name__, sorted(str(s) for s in names)])
+    return dict(
+        env_class=type(env.unwrapped).__name__, state_names=list(env.state_names), reference_names=list(rgen.reference_names),
+        limits=[float(v) for v in env.limits], nominal_state=[float(v) for v in env.nominal_state], tau=float(ps_.tau),
+        state_low=[float(v) for v in env.observation_space.spaces[0].low], state_high=[float(v) for v in env.observation_space.spaces[0].high],
+        ref_low=[float(v) for v in env.observation_space.spaces[1].low], ref_high=[float(v) for v in env.observation_space.spaces[1].high],
+        action=[type(sp).__name__, [int(v) for v in np.atleast_1d(getattr(sp, "nvec", getattr(sp, "n", 0)))] if not hasattr(sp, "low")
+                else [[float(v) for v in sp.low], [float(v) for v in sp.high]]],
+        motor_parameter={k: float(v) for k, v in sorted(ps_.electrical_motor.motor_parameter.items()) if np.ndim(v) == 0},
+        j_total=float(ps_.mechanical_load.j_total), u_sup=float(ps_.supply.u_nominal), supply_class=type(ps_.supply).__name__,
+        converter_class=type(ps_.converter).__name__, interlocking_time=float(ps_.converter._interlocking_time),
+        reward_weights=[float(v) for v in np.asarray(env.reward_function._reward_weights, dtype=float)],
+        reward_power=[float(v) for v in np.broadcast_to(np.asarray(env.reward_function._n, dtype=float), (len(env.physical_system.state_names),))],
+        reward_bias=float(env.reward_function._bias), violation_reward=float(env.reward_function._violation_reward),
+        reward_range=[float(v) for v in env.reward_function.reward_range], constraints=sorted(cons), generator_margins=margins,
+    )
+
+
+def main(impl):
+    warnings.filterwarnings("ignore")
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, HERE + "/_shims")
+    if impl == "reference":
+        sys.path.insert(0, REF + "/src")
+        import gym_electric_motor as gem
+        from gym_electric_motor.core import ElectricMotorVisualization
+
+        class NoViz(ElectricMotorVisualization):
+            pass
+
+        real_make = gem.make
+        gem.make = lambda env_id, **kw: real_make(env_id, visualization=NoViz(), **kw)  # keep matplotlib out of it
+    else:
+        sys.path.insert(0, HERE.rsplit("/", 1)[0])
+        import gym_electric_motor_b200 as gem
+
+        gem.install_as_gym_electric_motor()
+    out = {}
+    for name, src in CASES.items():
+        ns = {"gem": gem}
+        rec = dict(verdict="ok", summary=None)
+        try:
+            exec(PRELUDE, ns)
+            env = eval(src, ns)
+            if impl == "b200":
+                env.build_config()
+            rec["summary"] = summary(env)
+        except Exception as e:
+            rec["verdict"] = f"{type(e).__name__}: {str(e)[:200]}"
+        out[name] = rec
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main(sys.argv[sys.argv.index("--impl") + 1] if "--impl" in sys.argv else "b200")

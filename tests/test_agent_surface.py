@@ -100,3 +100,31 @@ def test_integration_md_binding_stub_reaches_gemb200_create():
         assert verdict.startswith("created"), verdict
     else:
         assert verdict.startswith("GemB200Error") and "rc=-2" in verdict, verdict   # GEMB200_E_CUDA: validation passed, no device
+
+
+def test_user_kwargs_matrix_builds_identical_environments():
+    """60 `gem.make(id, **kwargs)` snippets over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
+    evaluated literally against the reference and against this package: env class, names, limits, nominal state, spaces, tau, motor /
+    load parameters, supply, converter, reward weights / powers / bias / range / violation reward, constraint list and generator margins
+    must be equal.  One documented exception: a ConstReferenceGenerator's `reference_names` is the bare string in the reference
+    (const_reference_generator.py:24), which a MultipleReferenceGenerator then extends its list with character by character; here it is
+    the one-element list every other generator has."""
+    res = {}
+    for impl in ("reference", "b200"):
+        out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "kwargs_matrix_harness.py"), "--impl", impl], capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
+    ref, mine = res["reference"], res["b200"]
+    assert sorted(ref) == sorted(mine) and len(ref) >= 60
+    for case in sorted(ref):
+        assert ref[case]["verdict"] == "ok", (case, ref[case]["verdict"])
+        assert mine[case]["verdict"] == "ok", (case, mine[case]["verdict"])
+        a, b = ref[case]["summary"], mine[case]["summary"]
+        assert sorted(a) == sorted(b)
+        for field in a:
+            if a[field] == b[field]:
+                continue
+            if field == "reference_names" and "".join(a[field]) == "".join(b[field]):
+                continue  # the string quirk described above
+            assert np.allclose(np.asarray(a[field], dtype=float), np.asarray(b[field], dtype=float), rtol=1e-12, atol=0), (case, field, a[field], b[field])
