@@ -39,12 +39,16 @@ class ElectricMotor:
         self._initializer = update_parameter_dict(self._default_initializer, motor_initializer or {})
         if self._initializer.get("random_init") not in (None, "uniform", "normal", "gaussian"):
             raise NotImplementedError(f"random_init={self._initializer.get('random_init')!r} (electric_motor.py:233-262 knows uniform / normal / gaussian)")
-        self._initial_states = dict(self._default_initializer["states"])
-        if self._initializer["states"]:
-            unknown = set(self._initializer["states"]) - set(self._initial_states)
-            if unknown:
-                raise KeyError(f"unknown initial states {unknown}")
-            self._initial_states.update(self._initializer["states"])
+        # Key order matters (see initial_ode_state): the reference starts from the USER's `states` dict — which replaces the default one as a
+        # whole, electric_motor.py:133-137 — and `initialize` then adds the missing default keys behind it (:204-206).
+        defaults = self._default_initializer["states"]
+        given = self._initializer["states"] or {}
+        unknown = set(given) - set(defaults)
+        if unknown:
+            raise KeyError(f"unknown initial states {unknown}")
+        self._initial_states = {k: given[k] for k in given}
+        for k, v in defaults.items():
+            self._initial_states.setdefault(k, v)
 
     # ----- reference-compatible read-only views
     @property
@@ -67,10 +71,12 @@ class ElectricMotor:
         """Constant initial motor ODE state (reference reset(): `np.asarray(list(self._initial_states.values()))`,
         electric_motor.py:283-284 / synchronous_motor.py:125-131).
 
-        Reference quirk kept on purpose: the values are taken in the KEY ORDER of the initializer dict, not by name, and
-        the synchronous motors' default dict is ordered (i_sq, i_sd, epsilon) while the ODE state is (i_sd, i_sq, epsilon)
-        — a user's `i_sq=20` therefore initialises the d-current (pinned by tests/golden/pmsm_cc_custom_rk4.npz)."""
-        return np.array([float(self._initial_states[k]) for k in self._default_initializer["states"]])
+        Reference quirk kept on purpose: the values are taken in the KEY ORDER of the initial-state dict, not by name — the user's keys
+        in the user's order, then the default keys that were not given.  The synchronous motors' default dict is ordered
+        (i_sq, i_sd, epsilon) while the ODE state is (i_sd, i_sq, epsilon): `states=dict(i_sq=20)` alone therefore initialises the
+        d-current, `states=dict(i_sd=-10, i_sq=20, epsilon=1)` lands where the names say (tests/golden/pmsm_cc_custom_rk4.npz, and the
+        reference-vs-oracle trajectories of tests/agent_surface/kwargs_matrix_harness.py)."""
+        return np.array([float(v) for v in self._initial_states.values()])
 
     @property
     def random_init(self):
@@ -92,7 +98,7 @@ class ElectricMotor:
     def initial_bounds(self, state_low, state_positions):
         """(lower, upper) per initial state in the initializer's key order (electric_motor.py:214-232): upper = the motor's
         nominal value of the state, lower = upper * state_space.low, both clipped to `interval` when given."""
-        keys = list(self._default_initializer["states"])
+        keys = list(self._initial_states)
         upper = np.array([float(self._nominal_values[k]) for k in keys])
         lower = upper * np.array([float(state_low[state_positions[k]]) for k in keys])
         interval = self._initializer.get("interval")

@@ -62,6 +62,12 @@ CASES = {
     "rc_supply": 'gem.make("Cont-SC-PermExDc-v0", supply=ps.RCVoltageSupply(u_nominal=80.0, supply_parameter=dict(R=0.5, C=2e-3)))',
     "ac1_supply": 'gem.make("Cont-CC-SeriesDc-v0", supply=ps.AC1PhaseSupply(u_nominal=230.0, supply_parameter=dict(frequency=50, phase=0.3)))',
     "motor_initializer": 'gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(states=dict(i_sd=-10.0, i_sq=20.0, epsilon=1.0))))',
+    "initializer_partial_quirk": 'gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(states=dict(i_sq=20.0))))',
+    "initializer_reversed": 'gem.make("Cont-SC-PMSM-v0", motor=dict(motor_initializer=dict(states=dict(epsilon=0.5, i_sq=15.0, i_sd=-5.0))))',
+    "initializer_eesm": 'gem.make("Cont-CC-EESM-v0", motor=dict(motor_initializer=dict(states=dict(i_e=30.0, i_sd=-10.0))))',
+    "initializer_extex": 'gem.make("Cont-CC-ExtExDc-v0", motor=dict(motor_initializer=dict(states=dict(i_e=1.5, i_a=10.0))))',
+    "initializer_scim": 'gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(states=dict(i_sbeta=1.0, i_salpha=-0.5, psi_ralpha=0.0, psi_rbeta=0.0, epsilon=0.0))))',
+    "initializer_load_const": 'gem.make("Cont-SC-PermExDc-v0", load=dict(load_initializer=dict(states=dict(omega=50.0))))',
     "shunt_cc_default_filter": 'gem.make("Cont-CC-ShuntDc-v0", state_filter=["i_a", "i_e", "i_sum"])',
     "shunt_limits": 'gem.make("Finite-TC-ShuntDc-v0", motor=dict(limit_values=dict(i_a=80.0, i_e=4.0, omega=300.0)))',
     "extex_supply_limits": 'gem.make("Finite-CC-ExtExDc-v0", supply=dict(u_nominal=100.0), motor=dict(nominal_values=dict(i_a=40.0, i_e=3.0)))',
@@ -119,6 +125,58 @@ def summary(env):
     )
 
 
+def trajectory(env, impl):
+    """reset + three steps with fixed actions: the filtered state vectors.  Reference: the env itself (default dopri5 solver unless the
+    case names one).  This package: its C-ABI config run by the CPU ORACLE (tests may use it; the kernel is compared with the oracle in
+    the `-m gpu` tests) — so the whole chain user kwargs -> host classes -> gemb200_config -> physics is compared number by number.
+    Cases with random initial states, random supply phase or state noise have no comparable numbers (different RNG streams): None."""
+    sp = env.action_space
+    if hasattr(sp, "low"):
+        actions = [np.clip(np.full(sp.shape, v), sp.low, sp.high) for v in (0.3, -0.2, 0.5)]
+    elif hasattr(sp, "nvec"):
+        actions = [np.array([1, 1][: len(sp.nvec)]), np.array([2, 0][: len(sp.nvec)]), np.array([0, 1][: len(sp.nvec)])]
+    else:
+        actions = [1, 2, 0]
+    if impl == "reference":
+        ps_ = env.physical_system.unwrapped
+        if getattr(ps_.electrical_motor, "_initializer", {}).get("random_init") or getattr(ps_.mechanical_load, "_initializer", {}).get("random_init"):
+            return None
+        if type(ps_.supply).__name__ == "AC1PhaseSupply" and not ps_.supply._fixed_phi:
+            return None
+        chain, w = [], env.physical_system
+        while w is not w.unwrapped:
+            chain.append(type(w).__name__)
+            w = w._physical_system
+        if "StateNoiseProcessor" in chain:
+            return None
+        (state, _), _ = env.reset(seed=0)
+        states = [np.asarray(state, dtype=float).tolist()]
+        for a in actions:
+            (state, _), _, terminated, _, _ = env.step(a)
+            states.append(np.asarray(state, dtype=float).tolist())
+            if terminated:
+                break
+        return states
+    sys.path.insert(0, HERE.rsplit("/", 1)[0])
+    from gym_electric_motor_b200 import _cabi as K
+    from oracle.gem_oracle import Oracle
+
+    cfg = env.build_config()
+    if cfg.init_random or any(cfg.sop_kind[k] == K.SOP_NOISE for k in range(cfg.n_state_ops)) or (cfg.supply_kind == K.SUPPLY_AC1 and cfg.supply_param[2] == 0.0):
+        return None
+    cfg.dtype = K.F64
+    cfg.n_envs = 1
+    ora = Oracle(cfg)
+    obs, _ = ora.reset()
+    states = [obs[0][env.state_filter].tolist()]
+    for a in actions:
+        obs, _, _, term = ora.step(np.asarray(a).reshape(1, -1))
+        states.append(obs[0][env.state_filter].tolist())
+        if term[0]:
+            break
+    return states
+
+
 def main(impl):
     warnings.filterwarnings("ignore")
     sys.dont_write_bytecode = True
@@ -141,13 +199,12 @@ def main(impl):
     out = {}
     for name, src in CASES.items():
         ns = {"gem": gem}
-        rec = dict(verdict="ok", summary=None)
+        rec = dict(verdict="ok", summary=None, trajectory=None)
         try:
             exec(PRELUDE, ns)
             env = eval(src, ns)
-            if impl == "b200":
-                env.build_config()
             rec["summary"] = summary(env)
+            rec["trajectory"] = trajectory(env, impl)
         except Exception as e:
             rec["verdict"] = f"{type(e).__name__}: {str(e)[:200]}"
         out[name] = rec
