@@ -68,6 +68,18 @@ CASES = {
     "initializer_extex": 'gem.make("Cont-CC-ExtExDc-v0", motor=dict(motor_initializer=dict(states=dict(i_e=1.5, i_a=10.0))))',
     "initializer_scim": 'gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(states=dict(i_sbeta=1.0, i_salpha=-0.5, psi_ralpha=0.0, psi_rbeta=0.0, epsilon=0.0))))',
     "initializer_load_const": 'gem.make("Cont-SC-PermExDc-v0", load=dict(load_initializer=dict(states=dict(omega=50.0))))',
+    "euler_solver": 'gem.make("Cont-CC-PMSM-v0", ode_solver=ps.EulerSolver())',
+    "euler_solver_n": 'gem.make("Finite-SC-PermExDc-v0", ode_solver=ps.EulerSolver(nsteps=4))',
+    "solve_ivp_solver": 'gem.make("Cont-TC-SCIM-v0", ode_solver=ps.ScipySolveIvpSolver())',
+    "odeint_solver": 'gem.make("Cont-CC-SynRM-v0", ode_solver=ps.ScipyOdeIntSolver())',
+    "ext_speed_load": 'gem.make("Cont-CC-PMSM-v0", ode_solver=ps.EulerSolver(), load=ps.ExternalSpeedLoad(speed_profile=lambda t, a, f: a * np.sin(2 * np.pi * f * t) + 60.0, speed_profile_kwargs=dict(a=20.0, f=25.0)))',
+    "ext_speed_load_dc": 'gem.make("Cont-CC-SeriesDc-v0", ode_solver=ps.EulerSolver(nsteps=2), load=ps.ExternalSpeedLoad(speed_profile=lambda t: 30.0 + 500.0 * t, tau=1e-4))',
+    "control_space_dq": 'gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.DqToAbcActionProcessor.make("PMSM")], load=ps.ConstantSpeedLoad(omega_fixed=200.0))',
+    "dfim_dq_wrapper": 'gem.make("Cont-CC-DFIM-v0", physical_system_wrappers=[psw.FluxObserver(), psw.DqToAbcActionProcessor.make("DFIM")])',
+    "rc_supply_pmsm": 'gem.make("Cont-CC-PMSM-v0", supply=ps.RCVoltageSupply(u_nominal=300.0, supply_parameter=dict(R=0.2, C=1e-3)), converter=dict(interlocking_time=2e-6))',
+    "ac1_supply_finite": 'gem.make("Finite-CC-PermExDc-v0", supply=ps.AC1PhaseSupply(u_nominal=60.0, supply_parameter=dict(frequency=400, phase=1.0)))',
+    "interlock_cont_multi": 'gem.make("Cont-CC-ExtExDc-v0", converter=ps.ContMultiConverter([ps.ContFourQuadrantConverter(interlocking_time=1e-6), ps.ContTwoQuadrantConverter(interlocking_time=2e-6)]))',
+    "finite_multi_interlock": 'gem.make("Finite-CC-ExtExDc-v0", converter=ps.FiniteMultiConverter([ps.FiniteFourQuadrantConverter(interlocking_time=1e-6), ps.FiniteTwoQuadrantConverter()]))',
     "shunt_cc_default_filter": 'gem.make("Cont-CC-ShuntDc-v0", state_filter=["i_a", "i_e", "i_sum"])',
     "shunt_limits": 'gem.make("Finite-TC-ShuntDc-v0", motor=dict(limit_values=dict(i_a=80.0, i_e=4.0, omega=300.0)))',
     "extex_supply_limits": 'gem.make("Finite-CC-ExtExDc-v0", supply=dict(u_nominal=100.0), motor=dict(nominal_values=dict(i_a=40.0, i_e=3.0)))',
@@ -126,17 +138,17 @@ def summary(env):
 
 
 def trajectory(env, impl):
-    """reset + three steps with fixed actions: the filtered state vectors.  Reference: the env itself (default dopri5 solver unless the
+    """reset + five steps with fixed actions: the filtered state vectors.  Reference: the env itself (default dopri5 solver unless the
     case names one).  This package: its C-ABI config run by the CPU ORACLE (tests may use it; the kernel is compared with the oracle in
     the `-m gpu` tests) — so the whole chain user kwargs -> host classes -> gemb200_config -> physics is compared number by number.
     Cases with random initial states, random supply phase or state noise have no comparable numbers (different RNG streams): None."""
     sp = env.action_space
     if hasattr(sp, "low"):
-        actions = [np.clip(np.full(sp.shape, v), sp.low, sp.high) for v in (0.3, -0.2, 0.5)]
+        actions = [np.clip(np.full(sp.shape, v), sp.low, sp.high) for v in (0.3, -0.2, 0.5, -0.7, 0.1)]
     elif hasattr(sp, "nvec"):
-        actions = [np.array([1, 1][: len(sp.nvec)]), np.array([2, 0][: len(sp.nvec)]), np.array([0, 1][: len(sp.nvec)])]
+        actions = [np.array(v[: len(sp.nvec)]) for v in ([1, 1], [2, 0], [0, 1], [3, 2], [1, 0])]
     else:
-        actions = [1, 2, 0]
+        actions = [v % sp.n for v in (1, 2, 0, 5, 3)]
     if impl == "reference":
         ps_ = env.physical_system.unwrapped
         if getattr(ps_.electrical_motor, "_initializer", {}).get("random_init") or getattr(ps_.mechanical_load, "_initializer", {}).get("random_init"):
