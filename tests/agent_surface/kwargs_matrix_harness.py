@@ -80,6 +80,10 @@ CASES = {
     "ac1_supply_finite": 'gem.make("Finite-CC-PermExDc-v0", supply=ps.AC1PhaseSupply(u_nominal=60.0, supply_parameter=dict(frequency=400, phase=1.0)))',
     "interlock_cont_multi": 'gem.make("Cont-CC-ExtExDc-v0", converter=ps.ContMultiConverter([ps.ContFourQuadrantConverter(interlocking_time=1e-6), ps.ContTwoQuadrantConverter(interlocking_time=2e-6)]))',
     "finite_multi_interlock": 'gem.make("Finite-CC-ExtExDc-v0", converter=ps.FiniteMultiConverter([ps.FiniteFourQuadrantConverter(interlocking_time=1e-6), ps.FiniteTwoQuadrantConverter()]))',
+    "const_ref_reward_pmsm": 'gem.make("Cont-CC-PMSM-v0", reference_generator=rg.MultipleReferenceGenerator([rg.ConstReferenceGenerator(reference_state="i_sd", reference_value=-0.2), rg.ConstReferenceGenerator(reference_state="i_sq", reference_value=0.3)]), reward_function=dict(gamma=0.95, reward_power=2))',
+    "const_ref_terminates": 'gem.make("Cont-CC-PermExDc-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="i", reference_value=0.9), load=ps.ConstantSpeedLoad(omega_fixed=10.0))',
+    "const_ref_bias_violation": 'gem.make("Finite-SC-PermExDc-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="omega", reference_value=0.5), reward_function=rf.WeightedSumOfErrors(bias="positive", violation_reward=-7.0, gamma=0.5), tau=1e-4)',
+    "const_ref_squared_constraint": 'gem.make("Cont-TC-SynRM-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="torque", reference_value=0.1), constraints=(gem.constraints.SquaredConstraint(("i_sd", "i_sq")), "omega"), reward_function=dict(reward_power=0.5))',
     "shunt_cc_default_filter": 'gem.make("Cont-CC-ShuntDc-v0", state_filter=["i_a", "i_e", "i_sum"])',
     "shunt_limits": 'gem.make("Finite-TC-ShuntDc-v0", motor=dict(limit_values=dict(i_a=80.0, i_e=4.0, omega=300.0)))',
     "extex_supply_limits": 'gem.make("Finite-CC-ExtExDc-v0", supply=dict(u_nominal=100.0), motor=dict(nominal_values=dict(i_a=40.0, i_e=3.0)))',
@@ -138,7 +142,8 @@ def summary(env):
 
 
 def trajectory(env, impl):
-    """reset + five steps with fixed actions: the filtered state vectors.  Reference: the env itself (default dopri5 solver unless the
+    """reset + five steps with fixed actions: the filtered state vectors, the terminated flags and — when every reference generator is a
+    ConstReferenceGenerator, i.e. the references are not random — the rewards.  Reference: the env itself (default dopri5 solver unless the
     case names one).  This package: its C-ABI config run by the CPU ORACLE (tests may use it; the kernel is compared with the oracle in
     the `-m gpu` tests) — so the whole chain user kwargs -> host classes -> gemb200_config -> physics is compared number by number.
     Cases with random initial states, random supply phase or state noise have no comparable numbers (different RNG streams): None."""
@@ -161,14 +166,17 @@ def trajectory(env, impl):
             w = w._physical_system
         if "StateNoiseProcessor" in chain:
             return None
+        const_refs = all(type(g).__name__ == "ConstReferenceGenerator" for g in getattr(env.reference_generator, "_sub_generators", [env.reference_generator]))
         (state, _), _ = env.reset(seed=0)
-        states = [np.asarray(state, dtype=float).tolist()]
+        states, rewards, terms = [np.asarray(state, dtype=float).tolist()], [], []
         for a in actions:
-            (state, _), _, terminated, _, _ = env.step(a)
+            (state, _), reward, terminated, _, _ = env.step(a)
             states.append(np.asarray(state, dtype=float).tolist())
+            rewards.append(float(reward))
+            terms.append(bool(terminated))
             if terminated:
                 break
-        return states
+        return dict(states=states, terminated=terms, rewards=rewards if const_refs else None)
     sys.path.insert(0, HERE.rsplit("/", 1)[0])
     from gym_electric_motor_b200 import _cabi as K
     from oracle.gem_oracle import Oracle
@@ -179,14 +187,17 @@ def trajectory(env, impl):
     cfg.dtype = K.F64
     cfg.n_envs = 1
     ora = Oracle(cfg)
+    const_refs = all(cfg.ref_kind[r] == K.REF_CONST for r in range(cfg.n_ref))
     obs, _ = ora.reset()
-    states = [obs[0][env.state_filter].tolist()]
+    states, rewards, terms = [obs[0][env.state_filter].tolist()], [], []
     for a in actions:
-        obs, _, _, term = ora.step(np.asarray(a).reshape(1, -1))
+        obs, _, rew, term = ora.step(np.asarray(a).reshape(1, -1))
         states.append(obs[0][env.state_filter].tolist())
+        rewards.append(float(rew[0]))
+        terms.append(bool(term[0]))
         if term[0]:
             break
-    return states
+    return dict(states=states, terminated=terms, rewards=rewards if const_refs else None)
 
 
 def main(impl):

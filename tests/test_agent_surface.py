@@ -103,7 +103,7 @@ def test_integration_md_binding_stub_reaches_gemb200_create():
 
 
 def test_user_kwargs_matrix_builds_identical_environments():
-    """78 `gem.make(id, **kwargs)` snippets over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
+    """82 `gem.make(id, **kwargs)` snippets over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
     evaluated literally against the reference and against this package: env class, names, limits, nominal state, spaces, tau, motor /
     load parameters, supply, converter, reward weights / powers / bias / range / violation reward, constraint list and generator margins
     must be equal.  One documented exception: a ConstReferenceGenerator's `reference_names` is the bare string in the reference
@@ -116,8 +116,8 @@ def test_user_kwargs_matrix_builds_identical_environments():
         assert out.returncode == 0, out.stderr[-2000:]
         res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
     ref, mine = res["reference"], res["b200"]
-    assert sorted(ref) == sorted(mine) and len(ref) >= 78
-    compared_trajectories = 0
+    assert sorted(ref) == sorted(mine) and len(ref) >= 82
+    compared_trajectories = compared_rewards = 0
     for case in sorted(ref):
         assert ref[case]["verdict"] == "ok", (case, ref[case]["verdict"])
         if case in ("interlock_cont_multi", "finite_multi_interlock"):
@@ -139,9 +139,14 @@ def test_user_kwargs_matrix_builds_identical_environments():
         assert (ta is None) == (tb is None), case
         if ta is None:
             continue  # random initial state / supply phase / state noise: RNG streams differ by design
-        assert len(ta) == len(tb) and len(ta) >= 2, case
+        assert len(ta["states"]) == len(tb["states"]) and len(ta["states"]) >= 2, case
         first = 1 if case == "cossin_remove" else 0  # documented deviation at reset: compared from the first step on
-        for x, y in zip(ta[first:], tb[first:]):
+        for x, y in zip(ta["states"][first:], tb["states"][first:]):
             assert np.max(np.abs(np.asarray(x) - np.asarray(y))) < 1e-5, (case, x, y)
+        assert ta["terminated"] == tb["terminated"], case
+        assert (ta["rewards"] is None) == (tb["rewards"] is None), case
+        if ta["rewards"] is not None:  # constant references: the reward (incl. bias, powers, violation reward) is comparable too
+            assert np.allclose(ta["rewards"], tb["rewards"], rtol=0, atol=1e-5), (case, ta["rewards"], tb["rewards"])
+            compared_rewards += 1
         compared_trajectories += 1
-    assert compared_trajectories >= 70
+    assert compared_trajectories >= 72 and compared_rewards >= 5
