@@ -108,6 +108,13 @@ CASES = {
 }
 
 
+# every registered id with its defaults
+for _a in ("Cont", "Finite"):
+    for _c in ("CC", "TC", "SC"):
+        for _m in ("PermExDc", "SeriesDc", "ShuntDc", "ExtExDc", "PMSM", "SynRM", "EESM", "SCIM", "DFIM"):
+            CASES[f"default_{_a}-{_c}-{_m}"] = f'gem.make("{_a}-{_c}-{_m}-v0")'
+
+
 def summary(env):
     ps_ = env.physical_system.unwrapped
     sp = env.action_space

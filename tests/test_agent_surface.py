@@ -103,7 +103,7 @@ def test_integration_md_binding_stub_reaches_gemb200_create():
 
 
 def test_user_kwargs_matrix_builds_identical_environments():
-    """82 `gem.make(id, **kwargs)` snippets over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
+    """136 `gem.make(id, **kwargs)` snippets (82 kwarg combinations + all 54 ids with their defaults) over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
     evaluated literally against the reference and against this package: env class, names, limits, nominal state, spaces, tau, motor /
     load parameters, supply, converter, reward weights / powers / bias / range / violation reward, constraint list and generator margins
     must be equal.  One documented exception: a ConstReferenceGenerator's `reference_names` is the bare string in the reference
@@ -116,7 +116,7 @@ def test_user_kwargs_matrix_builds_identical_environments():
         assert out.returncode == 0, out.stderr[-2000:]
         res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
     ref, mine = res["reference"], res["b200"]
-    assert sorted(ref) == sorted(mine) and len(ref) >= 82
+    assert sorted(ref) == sorted(mine) and len(ref) >= 136
     compared_trajectories = compared_rewards = 0
     for case in sorted(ref):
         assert ref[case]["verdict"] == "ok", (case, ref[case]["verdict"])
@@ -149,4 +149,4 @@ def test_user_kwargs_matrix_builds_identical_environments():
             assert np.allclose(ta["rewards"], tb["rewards"], rtol=0, atol=1e-5), (case, ta["rewards"], tb["rewards"])
             compared_rewards += 1
         compared_trajectories += 1
-    assert compared_trajectories >= 72 and compared_rewards >= 5
+    assert compared_trajectories >= 126 and compared_rewards >= 5
