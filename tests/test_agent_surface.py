@@ -16,8 +16,11 @@ HARNESS = os.path.join(HERE, "agent_surface", "harness.py")
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/examples/classic_controllers"), reason="needs the reference checkout")
 
 
+SCRATCH = __import__("tempfile").mkdtemp(prefix="gemb200_agent_surface_")  # tutorial code creates files under the cwd: keep them out of the repo
+
+
 def _run(impl):
-    out = subprocess.run([sys.executable, HARNESS, "--impl", impl], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, HARNESS, "--impl", impl], capture_output=True, text=True, timeout=600, cwd=SCRATCH)
     assert out.returncode == 0, out.stderr[-2000:]
     return json.loads(out.stdout.strip().splitlines()[-1])
 
@@ -52,7 +55,7 @@ def test_reference_example_scripts_build_the_same_environments():
     res = {}
     for impl in ("reference", "b200"):
         out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "examples_harness.py"), "--impl", impl], capture_output=True, text=True,
-                             timeout=600)
+                             timeout=600, cwd=SCRATCH)
         assert out.returncode == 0, out.stderr[-2000:]
         res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
     ref, mine = res["reference"], res["b200"]
@@ -77,7 +80,7 @@ def test_reference_example_scripts_build_the_same_environments():
 
 def test_gem_cookbook_cells_build_the_same_environment():
     """examples/environment_features/GEM_cookbook.ipynb, cell by cell (tests/agent_surface/cookbook_harness.py)"""
-    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "cookbook_harness.py")], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "cookbook_harness.py")], capture_output=True, text=True, timeout=600, cwd=SCRATCH)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["constraints"] == ["SquaredConstraint", "MyConstraint", "str", "function"]
@@ -93,7 +96,7 @@ def test_integration_md_binding_stub_reaches_gemb200_create():
     """the ctypes stub of INTEGRATION.md section B, run verbatim against a reference SCMLSystem (tests/agent_surface/integration_stub_harness.py)"""
     import torch
 
-    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "integration_stub_harness.py")], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "integration_stub_harness.py")], capture_output=True, text=True, timeout=600, cwd=SCRATCH)
     assert out.returncode == 0, out.stderr[-2000:]
     verdict = out.stdout.strip().splitlines()[-1]
     if torch.cuda.is_available():
@@ -112,7 +115,7 @@ def test_user_kwargs_matrix_builds_identical_environments():
     res = {}
     for impl in ("reference", "b200"):
         out = subprocess.run([sys.executable, os.path.join(HERE, "agent_surface", "kwargs_matrix_harness.py"), "--impl", impl], capture_output=True, text=True,
-                             timeout=600)
+                             timeout=600, cwd=SCRATCH)
         assert out.returncode == 0, out.stderr[-2000:]
         res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
     ref, mine = res["reference"], res["b200"]
