@@ -11,6 +11,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "gpu_next: needs a CUDA device; written after the round's GPU budget was spent and never run on one yet — "
+                                       "run with `-m gpu_next` first thing, then promote to `gpu`")
 
 
 @pytest.fixture(scope="session")
