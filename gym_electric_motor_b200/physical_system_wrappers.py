@@ -29,7 +29,8 @@ class DqToAbcActionProcessor(PhysicalSystemWrapper):
 
     @classmethod
     def make(cls, motor_type, *args, **kwargs):
-        assert motor_type in ("PMSM", "SynRM", "EESM", "SCIM", "DFIM"), f"Not supported motor_type {motor_type}."
+        # the reference's registry (dq_to_abc_action_processor.py:96-153): a SynRM uses the "PMSM" entry there, so "SynRM" is refused here too
+        assert motor_type in ("PMSM", "EESM", "SCIM", "DFIM"), f"Not supported motor_type {motor_type}."
         if motor_type == "SCIM":  # dq_to_abc_action_processor.py:103-105
             kwargs.setdefault("angle_name", "psi_angle")
         inst = cls(*args, **kwargs)

@@ -126,8 +126,9 @@ class _MultiMixin:
         ils = {s.interlocking_time for s in self._sub_converters}
         if len(ils) > 1:
             raise NotImplementedError("sub-converters with different interlocking times are not supported")
-        if ils:
-            self._interlocking_time = ils.pop()
+        # `_interlocking_time` stays the multi converter's own (unused) kwarg like in the reference (converters.py:629-636, DESIGN.md finding 5);
+        # what the half bridges actually use is the sub-converters' value
+        self._sub_interlocking_time = ils.pop() if ils else self._interlocking_time
         self.currents = Box(np.concatenate([s.currents.low for s in self._sub_converters]),
                             np.concatenate([s.currents.high for s in self._sub_converters]), dtype=np.float64)
         self.voltages = Box(np.concatenate([s.voltages.low for s in self._sub_converters]),
@@ -135,6 +136,10 @@ class _MultiMixin:
 
     def sub_converters(self):
         return self._sub_converters
+
+    @property
+    def interlocking_time(self):
+        return self._sub_interlocking_time
 
     def slots(self):
         return [s.KIND for s in self._sub_converters]

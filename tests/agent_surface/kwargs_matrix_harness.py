@@ -84,6 +84,19 @@ CASES = {
     "const_ref_terminates": 'gem.make("Cont-CC-PermExDc-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="i", reference_value=0.9), load=ps.ConstantSpeedLoad(omega_fixed=10.0))',
     "const_ref_bias_violation": 'gem.make("Finite-SC-PermExDc-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="omega", reference_value=0.5), reward_function=rf.WeightedSumOfErrors(bias="positive", violation_reward=-7.0, gamma=0.5), tau=1e-4)',
     "const_ref_squared_constraint": 'gem.make("Cont-TC-SynRM-v0", reference_generator=rg.ConstReferenceGenerator(reference_state="torque", reference_value=0.1), constraints=(gem.constraints.SquaredConstraint(("i_sd", "i_sq")), "omega"), reward_function=dict(reward_power=0.5))',
+    "currentsum_extex": 'gem.make("Cont-CC-ExtExDc-v0", physical_system_wrappers=[psw.CurrentSumProcessor(currents=["i_a", "i_e"])])',
+    "dead_before_dq": 'gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.DeadTimeProcessor(steps=1), psw.DqToAbcActionProcessor.make("PMSM")])',
+    "dq_then_dead": 'gem.make("Cont-SC-PMSM-v0", physical_system_wrappers=[psw.DqToAbcActionProcessor.make("PMSM"), psw.DeadTimeProcessor(steps=2)])',
+    "eesm_dq": 'gem.make("Cont-CC-EESM-v0", physical_system_wrappers=[psw.DqToAbcActionProcessor.make("EESM")])',
+    "synrm_dq": 'gem.make("Cont-TC-SynRM-v0", physical_system_wrappers=[psw.DqToAbcActionProcessor.make("SynRM")])',
+    "torque_limit_explicit": 'gem.make("Cont-TC-PMSM-v0", motor=dict(limit_values=dict(torque=100.0), nominal_values=dict(torque=80.0)))',
+    "j_rotor_sc": 'gem.make("Cont-SC-PMSM-v0", motor=dict(motor_parameter=dict(j_rotor=0.01)), load=dict(load_parameter=dict(a=0.02, b=0.001, c=0.0, j_load=0.005)))',
+    "scim_fin_interlock": 'gem.make("Finite-CC-SCIM-v0", converter=dict(interlocking_time=5e-7))',
+    "dfim_fin_interlock": 'gem.make("Finite-TC-DFIM-v0", converter=ps.FiniteMultiConverter([ps.FiniteB6BridgeConverter(interlocking_time=1e-6), ps.FiniteB6BridgeConverter(interlocking_time=1e-6)]))',
+    "eesm_fin_defaults_tau": 'gem.make("Finite-CC-EESM-v0", tau=2e-5)',
+    "reward_weights_list": 'gem.make("Cont-CC-ShuntDc-v0", reward_function=dict(reward_weights=[0, 0, 1.0, 0.5, 0, 0, 0.25]))',
+    "limit_margin_multi": 'gem.make("Cont-CC-SCIM-v0", reference_generator=rg.MultipleReferenceGenerator([rg.WienerProcessReferenceGenerator, rg.WienerProcessReferenceGenerator], sub_args=[dict(reference_state="i_sd", limit_margin=(0.0, 0.3)), dict(reference_state="i_sq", limit_margin=0.6)]))',
+    "cossin_flux_angle": 'gem.make("Cont-SC-SCIM-v0", physical_system_wrappers=[psw.FluxObserver(), psw.CosSinProcessor(angle="psi_angle")])',
     "shunt_cc_default_filter": 'gem.make("Cont-CC-ShuntDc-v0", state_filter=["i_a", "i_e", "i_sum"])',
     "shunt_limits": 'gem.make("Finite-TC-ShuntDc-v0", motor=dict(limit_values=dict(i_a=80.0, i_e=4.0, omega=300.0)))',
     "extex_supply_limits": 'gem.make("Finite-CC-ExtExDc-v0", supply=dict(u_nominal=100.0), motor=dict(nominal_values=dict(i_a=40.0, i_e=3.0)))',

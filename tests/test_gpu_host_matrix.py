@@ -1,4 +1,4 @@
-"""Kernel vs oracle for every configuration of the user-kwargs matrix (tests/agent_surface/kwargs_matrix_harness.py: 82 kwarg combinations +
+"""Kernel vs oracle for every configuration of the user-kwargs matrix (tests/agent_surface/kwargs_matrix_harness.py: 95 kwarg combinations +
 the 54 default ids), built through the HOST API (`gem.make(**kwargs)` -> `env.build_config()`), float64 build, 6 envs, 12 steps with fixed
 actions: states, rewards, terminations, next references.
 
@@ -24,7 +24,7 @@ def _cases():
 
 
 CASES, PRELUDE = _cases()
-REFUSED = ("interlock_cont_multi", "finite_multi_interlock")
+REFUSED = ("interlock_cont_multi", "finite_multi_interlock", "currentsum_extex", "synrm_dq")  # refused on the host (tests/test_agent_surface.py)
 
 
 @pytest.mark.parametrize("case", sorted(c for c in CASES if c not in REFUSED))
