@@ -34,7 +34,7 @@ class LimitConstraint(Constraint):
             names = ps.state_names
         self._observed_state_names = list(names)
         low = [str(n).lower() for n in self._observed_state_names]
-        assert all(n in ps.state_names for n in low), f"A state name in {low} is invalid."
+        assert all(n in ps.state_names for n in low), f"A state name in {dict.fromkeys(low).keys()} is invalid."  # utils.set_state_array's wording
         self._observed_states = np.array([n in low for n in ps.state_names], dtype=bool)
 
     def mask(self):

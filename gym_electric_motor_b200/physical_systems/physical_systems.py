@@ -128,6 +128,12 @@ class SCMLSystem(PhysicalSystem):
                 self._dead_steps = w.dead_time
                 self._dead_outer = 1 if self._action_dq else 0  # it wraps an existing dq transformation -> queue of dq actions
             elif isinstance(w, DqToAbcActionProcessor):
+                from .electric_motors import ThreePhaseMotor
+
+                assert isinstance(self._electrical_motor, ThreePhaseMotor), \
+                    "The motor in the system has to derive from the ThreePhaseMotor to define transformations."  # dq_to_abc_action_processor.py:59-60
+                if w.angle_name not in self._state_names:  # the reference runs state_names.index(angle_name) first (:63): its ValueError
+                    raise ValueError(f"{w.angle_name!r} is not in list")
                 dfim = isinstance(self._electrical_motor, DoublyFedInductionMotor)
                 scim = isinstance(self._electrical_motor, InductionMotor) and not dfim
                 if dfim != bool(w.dfim):

@@ -97,6 +97,24 @@ CASES = {
     "reward_weights_list": 'gem.make("Cont-CC-ShuntDc-v0", reward_function=dict(reward_weights=[0, 0, 1.0, 0.5, 0, 0, 0.25]))',
     "limit_margin_multi": 'gem.make("Cont-CC-SCIM-v0", reference_generator=rg.MultipleReferenceGenerator([rg.WienerProcessReferenceGenerator, rg.WienerProcessReferenceGenerator], sub_args=[dict(reference_state="i_sd", limit_margin=(0.0, 0.3)), dict(reference_state="i_sq", limit_margin=0.6)]))',
     "cossin_flux_angle": 'gem.make("Cont-SC-SCIM-v0", physical_system_wrappers=[psw.FluxObserver(), psw.CosSinProcessor(angle="psi_angle")])',
+    # ---- user errors: both sides must refuse (tests compare the exception type; the message where the reference has a stable one)
+    "err_unknown_motor_key": 'gem.make("Cont-CC-PMSM-v0", motor=dict(motor_parameter=dict(r_x=1.0)))',
+    "err_unknown_limit_key": 'gem.make("Cont-CC-PMSM-v0", motor=dict(limit_values=dict(current=1.0)))',
+    "err_unknown_load_key": 'gem.make("Cont-SC-PMSM-v0", load=dict(load_parameter=dict(d=1.0)))',
+    "err_init_out_of_bounds": 'gem.make("Cont-CC-PMSM-v0", motor=dict(motor_initializer=dict(states=dict(i_sd=-1000.0))))',
+    "err_string_component": 'gem.make("Cont-CC-PMSM-v0", converter="Finite-B6C")',
+    "err_state_filter_name": 'gem.make("Cont-CC-PMSM-v0", state_filter=["i_sd", "nope"])',
+    "err_reference_state": 'gem.make("Cont-CC-PMSM-v0", reference_generator=rg.WienerProcessReferenceGenerator(reference_state="nope"))',
+    "err_reward_weight_name": 'gem.make("Cont-CC-PMSM-v0", reward_function=dict(reward_weights=dict(nope=1.0)))',
+    "err_constraint_name": 'gem.make("Cont-CC-PMSM-v0", constraints=("nope",))',
+    "err_dead_time_zero": 'gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.DeadTimeProcessor(steps=0)])',
+    "err_cossin_angle": 'gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.CosSinProcessor(angle="nope")])',
+    "err_flux_observer_pmsm": 'gem.make("Cont-CC-PMSM-v0", physical_system_wrappers=[psw.FluxObserver()])',
+    "err_dq_on_dc": 'gem.make("Cont-CC-PermExDc-v0", physical_system_wrappers=[psw.DqToAbcActionProcessor.make("PMSM")])',
+    "err_scim_dq_without_observer": 'gem.make("Cont-CC-SCIM-v0", physical_system_wrappers=[psw.DqToAbcActionProcessor.make("SCIM")])',
+    "err_limit_margin_type": 'gem.make("Cont-SC-PMSM-v0", reference_generator=rg.WienerProcessReferenceGenerator(reference_state="omega", limit_margin="wide"))',
+    "err_multi_same_state": 'gem.make("Cont-CC-PMSM-v0", reference_generator=rg.MultipleReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="i_sd"), rg.ConstReferenceGenerator(reference_state="i_sd")]))',
+    "err_unknown_env_id": 'gem.make("Cont-CC-BLDC-v0")',
     "shunt_cc_default_filter": 'gem.make("Cont-CC-ShuntDc-v0", state_filter=["i_a", "i_e", "i_sum"])',
     "shunt_limits": 'gem.make("Finite-TC-ShuntDc-v0", motor=dict(limit_values=dict(i_a=80.0, i_e=4.0, omega=300.0)))',
     "extex_supply_limits": 'gem.make("Finite-CC-ExtExDc-v0", supply=dict(u_nominal=100.0), motor=dict(nominal_values=dict(i_a=40.0, i_e=3.0)))',

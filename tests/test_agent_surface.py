@@ -106,7 +106,7 @@ def test_integration_md_binding_stub_reaches_gemb200_create():
 
 
 def test_user_kwargs_matrix_builds_identical_environments():
-    """149 `gem.make(id, **kwargs)` snippets (95 kwarg combinations + all 54 ids with their defaults) over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
+    """166 `gem.make(id, **kwargs)` snippets (95 kwarg combinations, 17 user errors + all 54 ids with their defaults) over every component kwarg a user can pass (tests/agent_surface/kwargs_matrix_harness.py),
     evaluated literally against the reference and against this package: env class, names, limits, nominal state, spaces, tau, motor /
     load parameters, supply, converter, reward weights / powers / bias / range / violation reward, constraint list and generator margins
     must be equal.  One documented exception: a ConstReferenceGenerator's `reference_names` is the bare string in the reference
@@ -119,12 +119,17 @@ def test_user_kwargs_matrix_builds_identical_environments():
         assert out.returncode == 0, out.stderr[-2000:]
         res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
     ref, mine = res["reference"], res["b200"]
-    assert sorted(ref) == sorted(mine) and len(ref) >= 149
-    compared_trajectories = compared_rewards = 0
+    assert sorted(ref) == sorted(mine) and len(ref) >= 166
+    compared_trajectories = compared_rewards = refused = 0
     for case in sorted(ref):
         if ref[case]["verdict"] != "ok":
-            # user errors: same exception type and message as the reference (e.g. DqToAbcActionProcessor.make("SynRM") is not in its registry)
-            assert mine[case]["verdict"] == ref[case]["verdict"], (case, ref[case]["verdict"], mine[case]["verdict"])
+            # user errors: same exception type and message as the reference (e.g. DqToAbcActionProcessor.make("SynRM") is not in its registry;
+            # unknown parameter keys, initial values outside the nominal range, strings for components, unknown state names, ...)
+            if case == "err_unknown_env_id":  # the reference's message comes from gymnasium's registry (here: its stand-in): the type is compared
+                assert mine[case]["verdict"].split(":")[0] == ref[case]["verdict"].split(":")[0] == "KeyError"
+            else:
+                assert mine[case]["verdict"] == ref[case]["verdict"], (case, ref[case]["verdict"], mine[case]["verdict"])
+            refused += 1
             continue
         if case in ("interlock_cont_multi", "finite_multi_interlock"):
             # one interlocking time per handle (a scalar of the kernel's parameter block): sub-converters that disagree are refused loudly
@@ -159,4 +164,4 @@ def test_user_kwargs_matrix_builds_identical_environments():
             assert np.allclose(ta["rewards"], tb["rewards"], rtol=0, atol=1e-5), (case, ta["rewards"], tb["rewards"])
             compared_rewards += 1
         compared_trajectories += 1
-    assert compared_trajectories >= 136 and compared_rewards >= 5
+    assert compared_trajectories >= 136 and compared_rewards >= 5 and refused >= 18

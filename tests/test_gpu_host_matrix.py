@@ -27,7 +27,7 @@ CASES, PRELUDE = _cases()
 REFUSED = ("interlock_cont_multi", "finite_multi_interlock", "currentsum_extex", "synrm_dq")  # refused on the host (tests/test_agent_surface.py)
 
 
-@pytest.mark.parametrize("case", sorted(c for c in CASES if c not in REFUSED))
+@pytest.mark.parametrize("case", sorted(c for c in CASES if c not in REFUSED and not c.startswith("err_")))
 def test_device_matches_oracle_for_host_built_config(oracle_lib, case):
     import torch
 

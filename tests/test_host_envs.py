@@ -148,7 +148,7 @@ def test_wrapper_descriptors_compile_like_the_reference_stack():
         assert int(np.prod(getattr(env.action_space, "shape", ()) or (1,))) == g["meta"]["action_dim"]
     with pytest.raises(NotImplementedError):
         gem.make("Finite-CC-PMSM-v0", physical_system_wrappers=[DqToAbcActionProcessor.make("PMSM")])
-    with pytest.raises(AssertionError):  # 'psi_angle' needs a FluxObserver first (dq_to_abc_action_processor.py:62-64)
+    with pytest.raises(ValueError):  # 'psi_angle' needs a FluxObserver first: the reference's state_names.index() fails (dq_to_abc_action_processor.py:63)
         gem.make("Cont-CC-SCIM-v0", physical_system_wrappers=[DqToAbcActionProcessor.make("SCIM")])
     # control_space='dq' (physical_systems.py:423-435): same transformation, no angle advance
     ps_ = gem.physical_systems
