@@ -248,6 +248,11 @@ class ElectricMotorEnvironment(_EnvBase):
         sim = self._ensure_sim()
         if self._scalar:
             assert not self._terminated, "A reset is required before the environment can perform further steps"
+            if not hasattr(self.action_space, "low"):  # finite converters assert their action (converters.py:204-206, :356-358, :827-829)
+                candidate = np.asarray(action)
+                candidate = int(candidate.reshape(-1)[0]) if candidate.size == 1 and hasattr(self.action_space, "n") else candidate.reshape(-1)
+                assert self.action_space.contains(candidate), \
+                    f"The selected action {action} is not a valid element of the action space {self.action_space}."
             action = np.asarray(action).reshape(1, -1)
         if self._callbacks:
             self._call_callbacks("on_step_begin", self._physical_system.k, action)

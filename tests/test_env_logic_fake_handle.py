@@ -140,3 +140,22 @@ def test_vector_facade_flow(scripted):
     assert tuple(state.shape) == (3, 14) and tuple(ref.shape) == (3, 1) and plain.single_action_space.n == 8
     venv.close(); plain.close()
     assert handle.closed and venv.closed
+
+
+def test_scalar_env_asserts_invalid_finite_actions(scripted):
+    """reference converters.py:204-206 / :827-829: a finite converter asserts that the action is an element of its action space"""
+    env = gem.make("Finite-CC-PMSM-v0")
+    env.reset()
+    env.step(7)
+    env.step(np.int64(0))
+    for bad in (8, -1):
+        with pytest.raises(AssertionError, match="not a valid element of the action space"):
+            env.step(bad)
+    multi = gem.make("Finite-CC-EESM-v0")  # MultiDiscrete([8, 4])
+    multi.reset()
+    multi.step([7, 3])
+    with pytest.raises(AssertionError):
+        multi.step([7, 4])
+    cont = gem.make("Cont-CC-PMSM-v0")      # continuous converters clip instead (converters.py:160-163)
+    cont.reset()
+    cont.step([2.0, -3.0, 0.0])
