@@ -186,8 +186,17 @@ def trajectory(env, impl):
     the `-m gpu` tests) — so the whole chain user kwargs -> host classes -> gemb200_config -> physics is compared number by number.
     Cases with random initial states, random supply phase or state noise have no comparable numbers (different RNG streams): None."""
     sp = env.action_space
+    solver = type(env.physical_system.unwrapped._ode_solver).__name__
     if hasattr(sp, "low"):
-        actions = [np.clip(np.full(sp.shape, v), sp.low, sp.high) for v in (0.3, -0.2, 0.5, -0.7, 0.1)]
+        shape = np.array([1.0, -0.6, 0.35, 0.8, -0.9, 0.5])[: sp.shape[0]]  # not the same value on every phase (that would be a zero vector)
+        actions = [np.clip(v * shape, sp.low, sp.high) for v in (0.3, -0.2, 0.5, -0.7, 0.1)]
+        if solver in ("ScipyOdeSolver", "EulerSolver"):
+            # solvers with an exact twin in the oracle (its dopri5 restatement / Euler): 300 more steps with seeded random actions, held
+            # for 10 steps each so that currents build up and constraints trigger; a terminated episode is followed by a reset on both sides
+            rng = np.random.default_rng(11)
+            for _ in range(30):
+                a = np.clip(rng.uniform(-0.8, 0.8, size=sp.shape), sp.low, sp.high)
+                actions += [a] * 10
     elif hasattr(sp, "nvec"):
         actions = [np.array(v[: len(sp.nvec)]) for v in ([1, 1], [2, 0], [0, 1], [3, 2], [1, 0])]
     else:
@@ -213,8 +222,11 @@ def trajectory(env, impl):
             rewards.append(float(reward))
             terms.append(bool(terminated))
             if terminated:
-                break
-        return dict(states=states, terminated=terms, rewards=rewards if const_refs else None)
+                if len(actions) <= 5:
+                    break
+                (state, _), _ = env.reset()
+                states.append(np.asarray(state, dtype=float).tolist())
+        return dict(states=states, terminated=terms, rewards=rewards if const_refs else None, solver=solver)
     sys.path.insert(0, HERE.rsplit("/", 1)[0])
     from gym_electric_motor_b200 import _cabi as K
     from oracle.gem_oracle import Oracle
@@ -224,6 +236,13 @@ def trajectory(env, impl):
         return None
     cfg.dtype = K.F64
     cfg.n_envs = 1
+    if solver == "ScipyOdeSolver":
+        # the device runs the scipy wrappers as RK4 x2 (accuracy pinned by the dopri5 goldens); HERE the point is the configuration chain, so
+        # the oracle runs its restatement of scipy's dopri5 — the reference's own algorithm, including its dropped-step pathology
+        # (DESIGN.md finding 1, which the zero-state SC envs hit) — and the comparison can be tight
+        from oracle.gem_oracle import SOLVER_DOPRI5
+
+        cfg.solver_kind, cfg.solver_nsteps = SOLVER_DOPRI5, 1
     ora = Oracle(cfg)
     const_refs = all(cfg.ref_kind[r] == K.REF_CONST for r in range(cfg.n_ref))
     obs, _ = ora.reset()
@@ -234,8 +253,11 @@ def trajectory(env, impl):
         rewards.append(float(rew[0]))
         terms.append(bool(term[0]))
         if term[0]:
-            break
-    return dict(states=states, terminated=terms, rewards=rewards if const_refs else None)
+            if len(actions) <= 5:
+                break
+            obs, _ = ora.reset()
+            states.append(obs[0][env.state_filter].tolist())
+    return dict(states=states, terminated=terms, rewards=rewards if const_refs else None, solver=solver)
 
 
 def main(impl):

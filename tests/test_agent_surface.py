@@ -120,7 +120,7 @@ def test_user_kwargs_matrix_builds_identical_environments():
         res[impl] = json.loads(out.stdout.strip().splitlines()[-1])
     ref, mine = res["reference"], res["b200"]
     assert sorted(ref) == sorted(mine) and len(ref) >= 166
-    compared_trajectories = compared_rewards = refused = 0
+    compared_trajectories = compared_rewards = refused = long_runs = terminations = 0
     for case in sorted(ref):
         if ref[case]["verdict"] != "ok":
             # user errors: same exception type and message as the reference (e.g. DqToAbcActionProcessor.make("SynRM") is not in its registry;
@@ -148,20 +148,33 @@ def test_user_kwargs_matrix_builds_identical_environments():
             if field == "reference_names" and "".join(a[field]) == "".join(b[field]):
                 continue  # the string quirk described above
             assert np.allclose(np.asarray(a[field], dtype=float), np.asarray(b[field], dtype=float), rtol=1e-12, atol=0), (case, field, a[field], b[field])
-        # reset + five steps: the reference env itself (its default dopri5) against the oracle run from THIS package's C-ABI config
-        # (RK4 x2 mapping): the whole chain kwargs -> host classes -> gemb200_config -> physics, number by number
+        # the reference env itself against the oracle run from THIS package's C-ABI config — the whole chain kwargs -> host classes ->
+        # gemb200_config -> physics, number by number: reset + 5 fixed steps, and for continuous converters 300 more steps of seeded random
+        # actions with a reset after every termination.  Where the reference's solver has an exact twin in the oracle (its default scipy
+        # dopri5, restated incl. the dropped-step pathology; Euler) the bar is 1e-9; odeint / solve_ivp cases (LSODA / RK45 with scipy's loose
+        # default tolerances) are compared with the device's RK4 x2 mapping at the reference solver's own accuracy.
         ta, tb = ref[case]["trajectory"], mine[case]["trajectory"]
         assert (ta is None) == (tb is None), case
         if ta is None:
             continue  # random initial state / supply phase / state noise: RNG streams differ by design
         assert len(ta["states"]) == len(tb["states"]) and len(ta["states"]) >= 2, case
-        first = 1 if case == "cossin_remove" else 0  # documented deviation at reset: compared from the first step on
-        for x, y in zip(ta["states"][first:], tb["states"][first:]):
-            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) < 1e-5, (case, x, y)
+        tol = {"ScipyOdeSolver": 1e-9, "EulerSolver": 1e-9, "ScipyOdeIntSolver": 1e-6, "ScipySolveIvpSolver": 1e-4}[ta["solver"]]
+        reset_rows, row = {0}, 0
+        for flag in ta["terminated"]:
+            row += 1
+            if flag and len(ta["terminated"]) > 5:
+                row += 1
+                reset_rows.add(row)
+        for i, (x, y) in enumerate(zip(ta["states"], tb["states"])):
+            if case == "cossin_remove" and i in reset_rows:
+                continue  # documented deviation at reset
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y))) < tol, (case, i, x, y)
+        long_runs += len(ta["terminated"]) > 5
+        terminations += sum(ta["terminated"])
         assert ta["terminated"] == tb["terminated"], case
         assert (ta["rewards"] is None) == (tb["rewards"] is None), case
         if ta["rewards"] is not None:  # constant references: the reward (incl. bias, powers, violation reward) is comparable too
             assert np.allclose(ta["rewards"], tb["rewards"], rtol=0, atol=1e-5), (case, ta["rewards"], tb["rewards"])
             compared_rewards += 1
         compared_trajectories += 1
-    assert compared_trajectories >= 136 and compared_rewards >= 5 and refused >= 18
+    assert compared_trajectories >= 136 and compared_rewards >= 5 and refused >= 18 and long_runs >= 90 and terminations >= 3000
