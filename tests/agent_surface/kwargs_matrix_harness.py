@@ -199,8 +199,16 @@ def trajectory(env, impl):
                 actions += [a] * 10
     elif hasattr(sp, "nvec"):
         actions = [np.array(v[: len(sp.nvec)]) for v in ([1, 1], [2, 0], [0, 1], [3, 2], [1, 0])]
+        if solver in ("ScipyOdeSolver", "EulerSolver"):
+            rng = np.random.default_rng(12)
+            for _ in range(60):
+                actions += [np.array([int(rng.integers(0, m)) for m in sp.nvec])] * 5
     else:
         actions = [v % sp.n for v in (1, 2, 0, 5, 3)]
+        if solver in ("ScipyOdeSolver", "EulerSolver"):
+            rng = np.random.default_rng(12)
+            for _ in range(60):
+                actions += [int(rng.integers(0, sp.n))] * 5
     if impl == "reference":
         ps_ = env.physical_system.unwrapped
         if getattr(ps_.electrical_motor, "_initializer", {}).get("random_init") or getattr(ps_.mechanical_load, "_initializer", {}).get("random_init"):

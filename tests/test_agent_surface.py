@@ -149,8 +149,8 @@ def test_user_kwargs_matrix_builds_identical_environments():
                 continue  # the string quirk described above
             assert np.allclose(np.asarray(a[field], dtype=float), np.asarray(b[field], dtype=float), rtol=1e-12, atol=0), (case, field, a[field], b[field])
         # the reference env itself against the oracle run from THIS package's C-ABI config — the whole chain kwargs -> host classes ->
-        # gemb200_config -> physics, number by number: reset + 5 fixed steps, and for continuous converters 300 more steps of seeded random
-        # actions with a reset after every termination.  Where the reference's solver has an exact twin in the oracle (its default scipy
+        # gemb200_config -> physics, number by number: reset + 5 fixed steps and 300 more steps of seeded random (continuous or discrete) actions with a
+        # reset after every termination.  Where the reference's solver has an exact twin in the oracle (its default scipy
         # dopri5, restated incl. the dropped-step pathology; Euler) the bar is 1e-9; odeint / solve_ivp cases (LSODA / RK45 with scipy's loose
         # default tolerances) are compared with the device's RK4 x2 mapping at the reference solver's own accuracy.
         ta, tb = ref[case]["trajectory"], mine[case]["trajectory"]
@@ -177,4 +177,4 @@ def test_user_kwargs_matrix_builds_identical_environments():
             assert np.allclose(ta["rewards"], tb["rewards"], rtol=0, atol=1e-5), (case, ta["rewards"], tb["rewards"])
             compared_rewards += 1
         compared_trajectories += 1
-    assert compared_trajectories >= 136 and compared_rewards >= 5 and refused >= 18 and long_runs >= 90 and terminations >= 3000
+    assert compared_trajectories >= 136 and compared_rewards >= 5 and refused >= 18 and long_runs >= 135 and terminations >= 4000
