@@ -1,24 +1,29 @@
 #!/usr/bin/env python
 """bench.py — env-steps/s of the fused GEM step on B200 (BASELINE.json metric), with roofline + CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs-per-gpu E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config pmsm|pmsm_64k|fin_sc_pmsm|scim|eesm|mixed] [--envs-per-gpu E]
 
-Workload (BASELINE.json configs[1]/metric): Cont-CC-PMSM-v0, RK4 (one step per tau = 1e-4), 2^20 envs per GPU, synthetic
-U(-1,1)^3 actions, Wiener references, in-kernel auto-reset; weak scaling: every rank steps its own 2^20-env shard
-(keyed by global env index), no data-path collective.
+Default workload (BASELINE.json metric / configs[1] at the size the metric is quoted on): Cont-CC-PMSM-v0, RK4 (one step per
+tau = 1e-4), 2^20 envs per GPU, synthetic U(-1,1)^3 actions, Wiener references, in-kernel auto-reset; weak scaling: every rank steps its
+own 2^20-env shard (keyed by global env index), no data-path collective.  `--config` selects the other BASELINE
+configs (configs[1] at N=65536, configs[2] Finite-SC-PMSM, configs[3] SCIM, configs[4] mixed PMSM+SynRM+EESM); the default run also times
+them briefly and reports them under `other_configs`, so that the driver's 1/2/4/8-GPU records hold them too.
 
-One "step" = one batched env.step = ONE launch of step_kernel over the rank's shard.
- * value    : whole-job env-steps/s with actions resident in HBM.  The K timed steps run back to back (one CUDA-event pair
-              on the launching stream around all K launches) and rotate over R=4 independent replicas of the 2^20-env batch
-              and 8 action tensors, so that every byte a launch touches was last touched >= 3 launches (~500 MB of traffic,
-              4x the 126 MB L2) earlier: inputs larger than L2, no flush kernels inside the timed region.
-              ms_per_step = event time / K, max over ranks.
- * cold_events : the same step timed one launch at a time (CUDA events around every launch, 256 MiB L2 flush before it);
-              includes ~8 us of event/launch overhead per step and is reported for reference.
+One "step" = one batched env.step over the rank's shard = one pass of the hot path (core.py:328-371).
+ * value    : whole-job env-steps/s with the actions resident in HBM, through `env.rollout` (gemb200_rollout_record): the K timed steps are
+              issued as fused launches of <= 32 steps each (rollout_kernel: the persistent records stay in registers across the steps of a
+              launch), and EVERY step's obs / next reference / reward / terminated is written to HBM (record_every = 1) — the same
+              outputs, bit for bit, as K env.step calls (tests/test_gpu_rollout.py).  One CUDA-event pair on the launching stream around
+              all K steps; ms_per_step = event time / K, max over ranks.  Inputs larger than L2: a launch reads K x 12.6 MB of actions and
+              writes K x 72.4 MB of outputs, nothing is re-read.
+ * per_step_launch : the same K steps as K separate gemb200_step launches (step_kernel; the closed-loop shape, round 1's `value`),
+              rotating over 4 replicas of the batch so that every launch finds its records in HBM, not in L2.
  * e2e      : same metric through the public host-buffer entry point (gemb200_step_host): pinned host actions -> H2D ->
               launch -> D2H of obs/ref/reward/terminated -> sync, every step.
- * roofline : algorithmic bytes per env-step (SURVEY.md §8d, 129 B for PMSM) * envs / mean kernel time vs the measured
-              HBM copy bandwidth in MEASURED_PEAKS.json.
+ * roofline : for the dominant kernel of `value` (rollout_kernel): algorithmic bytes per env-step (SURVEY.md §8d bookkeeping: action in,
+              obs/ref/reward/terminated out every step, record read + written once per launch) x envs / mean kernel time per step vs the
+              measured HBM copy bandwidth in MEASURED_PEAKS.json.  `per_step_launch.roofline` is the same for step_kernel with the
+              canonical 129 B/env-step.
  * cpu_baseline : the float64 C oracle (a port of the reference's algorithm, oracle/gem_oracle.c) on this box's host
               cores, bounded sample.  `--impl reference` runs only that arm.
 """
@@ -34,25 +39,66 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ENV_ID = "Cont-CC-PMSM-v0"
-B_ALG = 129  # algorithmic bytes per env-step, SURVEY.md §8(d): 4*3 act + 2*4*4 state + 4*14 obs + 4*2 ref + 2*4*2 gen + 4 + 1
 METRIC = "env-steps/sec at N=2^20 PMSM, 1/2/4/8 GPU; HBM GB/s vs roofline"
 UNIT = "env-steps/s"
+ROLL_MAX = 32  # steps per fused launch (bounds the size of the recorded trajectory: 32 x 72 MB at N = 2^20)
+
+# BASELINE.json configs; n_* feed the algorithmic-bytes bookkeeping of SURVEY.md §8(d)
+CONFIGS = {
+    "pmsm": dict(env_id="Cont-CC-PMSM-v0", n_act=3, n_ode=4, n_obs=14, n_ref=2, envs=1 << 20,
+                 what="ContB6 + IdealSupply + ConstantSpeedLoad(100 rad/s), Wiener refs (i_sd,i_sq) + WSE reward + SquaredConstraint fused"),
+    "pmsm_64k": dict(env_id="Cont-CC-PMSM-v0", n_act=3, n_ode=4, n_obs=14, n_ref=2, envs=1 << 16, what="BASELINE configs[1]: N=65536"),
+    "fin_sc_pmsm": dict(env_id="Finite-SC-PMSM-v0", n_act=1, n_ode=4, n_obs=14, n_ref=1, envs=1 << 20, n_finite=8,
+                        what="BASELINE configs[2]: FiniteB6 (8 switching states) + PolynomialStaticLoad, tau=1e-5, Wiener omega reference"),
+    "scim": dict(env_id="Cont-CC-SCIM-v0", n_act=3, n_ode=6, n_obs=14, n_ref=2, envs=1 << 20, what="BASELINE configs[3]: 5-state induction motor"),
+    "eesm": dict(env_id="Cont-CC-EESM-v0", n_act=4, n_ode=5, n_obs=16, n_ref=3, envs=1 << 20, what="B6 + 4QC excitation converter"),
+    "synrm": dict(env_id="Cont-CC-SynRM-v0", n_act=3, n_ode=4, n_obs=14, n_ref=2, envs=1 << 20, what="reluctance motor"),
+    "mixed": dict(types=("pmsm", "synrm", "eesm"), envs=(1 << 20) // 3 * 3,
+                  what="BASELINE configs[4]: env g of type g mod 3 in {PMSM, SynRM, EESM}, physically segmented per type, one fused launch per type "
+                       "on its own stream"),
+}
+for _c in CONFIGS.values():
+    if "types" not in _c:
+        _c["record_bytes"] = 8 * _c["n_ode"] + 8 * _c["n_ref"]
 
 
-def make_env(n_envs, device=0, rank=0):
+def b_alg(c):
+    """canonical algorithmic bytes per env-step of ONE single-step launch"""
+    if "types" in c:
+        return sum(b_alg(CONFIGS[t]) for t in c["types"]) / len(c["types"])
+    return 4 * c["n_act"] + 8 * c["n_ode"] + 4 * c["n_obs"] + 4 * c["n_ref"] + 8 * c["n_ref"] + 5
+
+
+def b_alg_rollout(c, k, every=1):
+    """same bookkeeping for a fused launch of k steps: action in every step, outputs every `every` steps, record once per launch"""
+    if "types" in c:
+        return sum(b_alg_rollout(CONFIGS[t], k, every) for t in c["types"]) / len(c["types"])
+    return 4 * c["n_act"] + (4 * c["n_obs"] + 4 * c["n_ref"] + 5) / every + (8 * c["n_ode"] + 8 * c["n_ref"]) / k
+
+
+def make_env(cfg_name, n_envs, device=0, rank=0):
     import gym_electric_motor_b200 as gem
 
-    return gem.make(ENV_ID, num_envs=n_envs, device=device, dtype="float32", ode_solver=gem.physical_systems.RK4Solver(),
+    c = CONFIGS[cfg_name]
+    if "types" in c:
+        from gym_electric_motor_b200.mixed import MixedEnvBatch
+
+        return MixedEnvBatch([CONFIGS[t]["env_id"] for t in c["types"]], n_envs, device=device, dtype="float32", ode_solver=gem.physical_systems.RK4Solver(),
+                             autoreset="same_step", seed=0, env_index_offset=rank * n_envs)
+    return gem.make(c["env_id"], num_envs=n_envs, device=device, dtype="float32", ode_solver=gem.physical_systems.RK4Solver(),
                     autoreset="same_step", seed=0, env_index_offset=rank * n_envs)
 
 
-def workload_config(n_envs, n_gpus):
-    return {"workload": f"{ENV_ID} x {n_envs} envs/GPU, RK4 x1 per tau=1e-4, ContB6 + IdealSupply + ConstantSpeedLoad(100 rad/s), "
-                        "Wiener refs (i_sd,i_sq) + WSE reward + SquaredConstraint fused, same-step auto-reset",
-            "env_id": ENV_ID, "envs_per_gpu": n_envs, "global_envs": n_envs * n_gpus, "solver": "rk4x1", "tau": 1e-4,
-            "parallelism": f"env-shard x{n_gpus} (no collective)", "l2": "inputs larger than L2: timed steps rotate over 4 replicas of the env batch (4 x 166 MB touched per cycle), back-to-back launches",
-            "layout": "obs [N,14] row-per-env (AoS), state SoA"}
+def workload_config(cfg_name, n_envs, n_gpus):
+    c = CONFIGS[cfg_name]
+    ids = c["env_id"] if "types" not in c else "+".join(CONFIGS[t]["env_id"] for t in c["types"])
+    tau = 1e-5 if cfg_name == "fin_sc_pmsm" else 1e-4
+    return {"workload": f"{ids} x {n_envs} envs/GPU, RK4 x1 per tau={tau:g}, {c['what']}, same-step auto-reset",
+            "name": cfg_name, "env_id": ids, "envs_per_gpu": n_envs, "global_envs": n_envs * n_gpus, "solver": "rk4x1", "tau": tau,
+            "parallelism": f"env-shard x{n_gpus} (no collective)",
+            "l2": "inputs larger than L2: fused launches stream K x (actions + outputs) through HBM once, nothing is re-read; the per-step-launch arm "
+                  "rotates over 4 replicas of the env batch",
+            "layout": "obs [K,N,n_obs] row-per-env (AoS), persistent state SoA of 16-byte chunks"}
 
 
 def peaks():
@@ -65,12 +111,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json), or None."""
+def ncu_traffic(key):
+    """dram bytes per launch from the committed ncu captures (profiles/ncu_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("step_kernel_pmsm_f32_aos_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
@@ -108,10 +154,13 @@ class ClockSampler:
     def mark(self):
         self.t_begin = time.perf_counter()
 
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        t_end = time.perf_counter()
+        t_end = getattr(self, "t_end", time.perf_counter())
         time.sleep(0.03)  # let the last row of the region arrive
         self.proc.terminate()
         try:
@@ -120,10 +169,10 @@ class ClockSampler:
             self.proc.kill()
         t_begin = getattr(self, "t_begin", 0.0)
         inside = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.03]
-        window = "timed region"
+        window = "timed regions (all arms)"
         if not inside:  # region shorter than the sampling period: take the rows closest to it
             inside = [r for (t, r) in self.rows if t_begin - 0.25 <= t <= t_end + 0.25]
-            window = "timed region +-250 ms"
+            window = "timed regions +-250 ms"
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in inside:
@@ -142,53 +191,138 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def cpu_arm(n_envs, steps, warmup, budget_s=None):
-    """Oracle (C port of the reference algorithm) on the host cores; returns (steps_per_s, cores, sample description)."""
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm (the oracle = C port of the reference's algorithm; bench.py's only use of oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_arm(cfg_name, n_envs, steps, warmup, min_seconds=2.0, max_seconds=None):
+    """Oracle on all host cores: `steps` timed steps over `n_envs` envs, the block repeated until >= min_seconds have been timed (or, with
+    max_seconds, as many 16-step blocks as fit).  Returns (env-steps/s, cores, sample description)."""
     import numpy as np
 
     from oracle.gem_oracle import Oracle
     from gym_electric_motor_b200 import _cabi as K
 
+    c = CONFIGS[cfg_name]
+    if "types" in c:
+        c, cfg_name = CONFIGS["pmsm"], "pmsm"
     cores = os.cpu_count() or 1
-    env = make_env(n_envs)  # host-side spec only; no device handle is created until the env is used
+    env = make_env(cfg_name, n_envs)  # host-side spec only; no device handle is created until the env is used
     cfg = env.build_config()
     cfg.dtype = K.F64
     ora = Oracle(cfg, nthreads=cores)
     ora.reset()
     rng = np.random.default_rng(0)
-    acts = rng.uniform(-1, 1, size=(4, n_envs, 3))
+    if "n_finite" in c:
+        acts = rng.integers(0, c["n_finite"], size=(4, n_envs, c["n_act"])).astype(np.int32)
+    else:
+        acts = rng.uniform(-1, 1, size=(4, n_envs, c["n_act"]))
     chunk = 16  # steps per rollout call: the oracle's worker threads persist over a call (two barriers per step, no thread creation)
-    for k in range(max(1, warmup // chunk)):
-        ora.rollout(acts, chunk)
+    ora.rollout(acts, max(1, warmup))
     t0 = time.perf_counter()
-    done = 0
+    done, blocks = 0, 0
     while True:
-        c = chunk if budget_s is not None else min(chunk, steps - done)
-        ora.rollout(acts, c)
-        done += c
+        todo = steps if max_seconds is None else chunk
+        k = 0
+        while k < todo:
+            cnt = min(chunk, todo - k)
+            ora.rollout(acts, cnt)
+            k += cnt
+        done += todo
+        blocks += 1
         el = time.perf_counter() - t0
-        if budget_s is None:
-            if done >= steps:
+        if max_seconds is not None:
+            if el >= max_seconds:
                 break
-        elif el >= budget_s or done >= 100000:
+        elif el >= min_seconds:
             break
     el = time.perf_counter() - t0
-    return n_envs * done / el, cores, f"{ENV_ID}, {n_envs} envs x {done} steps, RK4 x1, float64 C oracle, {cores} threads, {el:.1f} s"
+    how = f"{blocks} x {steps} steps" if max_seconds is None else f"{done} steps"
+    return n_envs * done / el, cores, f"{c['env_id']}, {n_envs} envs x {how}, RK4 x1, float64 C oracle (gem_oracle_rollout), {cores} threads, {el:.1f} s timed"
 
 
 def run_reference(args, rank):
     """--impl reference: the reference's CPU algorithm for the same path on the host cores (oracle port; the Python
-    reference itself cannot travel to this box and runs ~1e4 steps/s/core)."""
+    reference itself cannot travel to this box and runs ~1e4 steps/s/core).  Steps the SAME number of envs per step as the
+    GPU arm's config says (envs_per_gpu); K timed steps, repeated as a block until >= 2 s have been timed."""
     if rank != 0:
         return
-    n_ref = 65536
-    v, cores, sample = cpu_arm(n_ref, max(args.steps, 1), max(args.warmup, 1))
+    n = args.envs_per_gpu or CONFIGS[args.config]["envs"]
+    v, cores, sample = cpu_arm(args.config, n, max(args.steps, 1), max(args.warmup, 1), min_seconds=2.0)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * n_ref / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(1 << 20, args.gpus),
+            "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.config, n, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arms
+# ----------------------------------------------------------------------------------------------------------------------
+class Workload:
+    """One config on this rank: env (or mixed batch), action pools, recorded-output buffers; `rollout(k)` issues k fused steps."""
+
+    def __init__(self, cfg_name, n, device, rank, torch):
+        self.torch, self.name, self.c, self.n = torch, cfg_name, CONFIGS[cfg_name], n
+        self.env = make_env(cfg_name, n, device=device, rank=rank)
+        self.mixed = "types" in self.c
+        self.sims = [e.sim for e in self.env.envs] if self.mixed else [self.env.sim]
+        self.dev = self.sims[0].device
+        self.env.reset()
+        gen = torch.Generator(device=self.dev).manual_seed(1234 + rank)
+        self.acts, self.outs = [], []
+        for s in self.sims:
+            if s.finite:
+                a = torch.randint(0, 8, (ROLL_MAX, s.n, s.n_act), generator=gen, device=self.dev, dtype=torch.int32)
+            else:
+                a = torch.rand((ROLL_MAX, s.n, s.n_act), generator=gen, device=self.dev, dtype=torch.float32) * 2 - 1
+            self.acts.append(a)
+            self.outs.append((torch.empty((ROLL_MAX, s.n, s.n_state), device=self.dev), torch.empty((ROLL_MAX, s.n, max(s.n_ref, 1)), device=self.dev),
+                              torch.empty((ROLL_MAX, s.n), device=self.dev), torch.empty((ROLL_MAX, s.n), dtype=torch.uint8, device=self.dev)))
+        if self.mixed:
+            self.env._ensure_streams()
+
+    def launches(self):
+        return sum(s.launch_count for s in self.sims)
+
+    def rollout(self, k, every=1):
+        """k fused steps (k <= ROLL_MAX) on the current stream (mixed: one launch per type on its own stream, joined by events)"""
+        torch = self.torch
+        if not self.mixed:
+            self.sims[0].rollout_into(self.acts[0], k, every, *self.outs[0])
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        self.env._start.record(cur)
+        for s, a, o, st, ev in zip(self.sims, self.acts, self.outs, self.env._streams, self.env._events):
+            st.wait_event(self.env._start)
+            with torch.cuda.stream(st):
+                s.rollout_into(a, k, every, *o)
+            ev.record(st)
+        for ev in self.env._events:
+            cur.wait_event(ev)
+
+    def steps(self, total, every=1):
+        done = 0
+        while done < total:
+            k = min(ROLL_MAX, total - done)
+            self.rollout(k, every)
+            done += k
+
+    def close(self):
+        self.env.close()
+
+
+def time_rollout(wl, K, W, barrier, torch):
+    wl.steps(max(W, 3))
+    barrier()
+    l0 = wl.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    wl.steps(K)
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1), wl.launches() - l0, (time.perf_counter() - t0) * 1e3
 
 
 def main():
@@ -197,8 +331,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--config", default="pmsm", choices=sorted(CONFIGS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the brief timings of the other BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,6 +349,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    from gym_electric_motor_b200 import hostmem
+
+    hostmem.bind_to_device_numa_node(local_rank)  # pinned buffers of the e2e arm must sit on the GPU's NUMA node (first touch follows the thread)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -221,16 +360,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    n = args.envs_per_gpu
-    R = 4  # replicas of the env batch that the timed steps rotate over (working set >> L2)
-    envs = [make_env(n, device=local_rank, rank=rank * R + r) for r in range(R)]
-    env = envs[0]
-    sim = env.sim
-    for e in envs:
-        e.reset()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.rand((n, 3), generator=gen, device=dev, dtype=torch.float32) * 2 - 1 for _ in range(8)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cfg_name = args.config
+    c = CONFIGS[cfg_name]
+    n = args.envs_per_gpu or c["envs"]
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -238,106 +370,171 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm: K back-to-back launches rotating over R replicas, one event pair ----------------
-    for k in range(max(W, R)):
-        envs[k % R].step(pool[k % 8])
-    barrier()
+    # ---------------- primary arm: K steps as fused launches, every step's outputs recorded ----------------
+    wl = Workload(cfg_name, n, local_rank, rank, torch)
     if rank == 0:
         sampler.wait_first()
         sampler.mark()
-    l0 = sum(e.sim.launch_count for e in envs)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record()
-    for k in range(K):
-        envs[k % R].step(pool[k % 8])
-    ev1.record()
+    ms, launches, t_wall = time_rollout(wl, K, W, barrier, torch)
+    # the same K steps with only the LAST step's outputs written (what an open-loop consumer of the final state pays)
+    wl.steps(3, every=0)
     barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = sum(e.sim.launch_count for e in envs) - l0
-    ms = ev0.elapsed_time(ev1)
-    # ---------------- N > 1 only: the sharded layout's ONE collective — a single NCCL all-gather of the packed (obs, ref, reward,
-    # terminated) buffer after every step (BASELINE.json north_star; SURVEY.md §8e asks for both figures) ----------------
-    ms_gather, gather_bytes = None, 0
-    if world > 1:
-        from gym_electric_motor_b200.distributed import PackedStepOutputs
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wl.steps(K, every=0)
+    e1.record()
+    barrier()
+    ms_last = e0.elapsed_time(e1)
 
-        packed = PackedStepOutputs(n, 14, 2, torch.float32, dev)
-        gather_bytes = packed.nbytes
-        gsim = envs[R - 1].sim
-        gsim.bind_outputs(*packed.local_views())  # the kernel writes straight into the packed buffer
-        for k in range(3):
-            envs[R - 1].step(pool[k % 8])
-            packed.gather_raw()
+    # ---------------- per-step launches (closed-loop shape): K x gemb200_step rotating over R replicas ----------------
+    ms_step, step_launches = None, 0
+    if not wl.mixed:
+        R = 4 if n >= (1 << 18) else 16
+        envs = [wl.env] + [make_env(cfg_name, n, device=local_rank, rank=rank * R + r + 1000) for r in range(1, R)]
+        for e in envs[1:]:
+            e.reset()
+        pool = [wl.acts[0][j] for j in range(8)]
+        for k in range(max(W, R)):
+            envs[k % R].step(pool[k % 8])
         barrier()
-        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eg0.record()
+        l0 = sum(e.sim.launch_count for e in envs)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
         for k in range(K):
-            envs[R - 1].step(pool[k % 8])
-            packed.gather_raw()
-        eg1.record()
+            envs[k % R].step(pool[k % 8])
+        s1.record()
         barrier()
-        ms_gather = eg0.elapsed_time(eg1)
-    # ---------------- one launch at a time: events around every launch, L2 flushed before it (reference figure) ----------------
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for k in range(K):
-        flush.zero_()
-        evs[k][0].record()
-        env.step(pool[k % 8])
-        evs[k][1].record()
-    barrier()
-    ms_hot = sum(a.elapsed_time(b) for a, b in evs)
+        ms_step = s0.elapsed_time(s1)
+        step_launches = sum(e.sim.launch_count for e in envs) - l0
+        for e in envs[1:]:
+            e.close()
+
+    # ---------------- N > 1 only: the sharded layout's ONE collective — a single NCCL all-gather of the packed (obs, ref, reward,
+    # terminated) buffer after every step, double-buffered so that gather(k) overlaps step(k+1) ----------------
+    ms_gather, gather_bytes = None, 0
+    if world > 1 and not wl.mixed:
+        from gym_electric_motor_b200.distributed import OverlappedGather
+
+        sim = wl.sims[0]
+        og = OverlappedGather(sim, torch.float32)
+        gather_bytes = og.nbytes
+        pool = [wl.acts[0][j] for j in range(8)]
+        for k in range(3):
+            og.step(pool[k % 8])
+        og.finish()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(K):
+            og.step(pool[k % 8])
+        og.finish()
+        g1.record()
+        barrier()
+        ms_gather = g0.elapsed_time(g1)
+        og.release()
+
     # ---------------- e2e arm: host buffers through the C-ABI ----------------
-    h_act = [torch.rand((n, 3), dtype=torch.float32).mul_(2).sub_(1).pin_memory() for _ in range(2)]
-    h_obs = torch.empty((n, 14), dtype=torch.float32).pin_memory()
-    h_ref = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_term = torch.empty(n, dtype=torch.uint8).pin_memory()
-    ke = max(1, min(K, 50))
-    for k in range(3):
-        sim.step_host_ptr(h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_ref.data_ptr(), h_rew.data_ptr(), h_term.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(ke):
-        sim.step_host_ptr(h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_ref.data_ptr(), h_rew.data_ptr(), h_term.data_ptr())
-    barrier()
-    t_e2e = time.perf_counter() - t0
+    ms_e2e, ke, h2d, d2h = None, 0, 0, 0
+    if not wl.mixed:
+        sim = wl.sims[0]
+        adt = torch.int32 if sim.finite else torch.float32
+        h_act = []
+        for _ in range(2):
+            t = hostmem.pinned_empty((n, sim.n_act), adt, local_rank)
+            t.copy_(wl.acts[0][len(h_act)].cpu())
+            h_act.append(t)
+        h_obs = hostmem.pinned_empty((n, sim.n_state), torch.float32, local_rank)
+        h_ref = hostmem.pinned_empty((n, max(sim.n_ref, 1)), torch.float32, local_rank)
+        h_rew = hostmem.pinned_empty((n,), torch.float32, local_rank)
+        h_term = hostmem.pinned_empty((n,), torch.uint8, local_rank)
+        ke = max(1, min(K, 50))
+        for k in range(3):
+            sim.step_host_ptr(h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_ref.data_ptr(), h_rew.data_ptr(), h_term.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(ke):
+            sim.step_host_ptr(h_act[k % 2].data_ptr(), h_obs.data_ptr(), h_ref.data_ptr(), h_rew.data_ptr(), h_term.data_ptr())
+        barrier()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        h2d, d2h = n * sim.n_act * 4, n * (sim.n_state + sim.n_ref + 1) * 4 + n
+    if rank == 0:
+        sampler.mark_end()
+
+    # ---------------- the other BASELINE configs, briefly (fused launches, every step recorded) ----------------
+    others = {}
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
+    if not args.no_extra and cfg_name == "pmsm" and not args.envs_per_gpu:
+        for name in ("pmsm_64k", "fin_sc_pmsm", "scim", "mixed"):
+            oc = CONFIGS[name]
+            w2 = Workload(name, oc["envs"], local_rank, rank, torch)
+            k2 = max(K, 64) if name == "pmsm_64k" else min(max(K, 16), 64)
+            m2, l2, _ = time_rollout(w2, k2, 3, barrier, torch)
+            others[name] = (m2, k2, l2, oc["envs"])
+            w2.close()
+            del w2
+            torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, ms_hot, t_e2e * 1e3, ms_gather or 0.0], dtype=torch.float64, device=dev)
+    vals = [ms, ms_last, ms_step or 0.0, ms_gather or 0.0, ms_e2e or 0.0] + [others[k][0] for k in sorted(others)]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_hot, ms_e2e, ms_gather = [float(x) for x in t.tolist()]
+    vals = [float(x) for x in t.tolist()]
+    ms, ms_last, ms_step, ms_gather, ms_e2e = vals[:5]
+    for i, k in enumerate(sorted(others)):
+        others[k] = (vals[5 + i],) + others[k][1:]
     if rank == 0:
         total_envs = n * world
         ms_per_step = ms / K
         value = total_envs / (ms_per_step * 1e-3)
         peak, peak_src = peaks()
-        achieved = B_ALG * n / (ms_per_step * 1e-3) / 1e9  # per GPU: this kernel's algorithmic GB/s
-        traffic = ncu_traffic()
+        k_eff = min(K, ROLL_MAX)
+        ba = b_alg_rollout(c, k_eff, 1)
+        achieved = ba * n / (ms_per_step * 1e-3) / 1e9  # per GPU: this kernel's algorithmic GB/s
+        traffic = ncu_traffic(f"rollout_kernel_{cfg_name}_f32_aos_bytes_per_step")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(n, world),
+            "config": workload_config(cfg_name, n, world),
+            "api": f"env.rollout / gemb200_rollout_record: {launches} fused launches of <= {ROLL_MAX} steps, outputs of every step recorded",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "alg_bytes_per_env_step": B_ALG, "kernel": "step_kernel<SYNC,cont,f32,AoS>",
-                         "kernel_ms": ms_per_step},
-            "e2e": {"value": total_envs * ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 3 * 4,
-                    "d2h_bytes_per_step": n * (14 + 2 + 1) * 4 + n, "steps": ke, "ms_per_step": ms_e2e / ke,
-                    "api": "gemb200_step_host via VectorSim.step_host_ptr (pinned host buffers)"},
+                         "traffic_note": "DRAM bytes per env-batch step from profiles/ncu_traffic.json (ncu range replay over whole launches), or null",
+                         "peak_source": peak_src, "alg_bytes_per_env_step": ba,
+                         "alg_bytes_note": f"4*n_act + 4*n_obs + 4*n_ref + 5 per step + (8*n_ode + 8*n_ref)/{k_eff} (record read+written once per fused launch)",
+                         "kernel": "rollout_kernel" + ("<SYNC,cont,f32,NREF=2,AoS,PLAIN>" if cfg_name.startswith("pmsm") else ""), "kernel_ms_per_step": ms_per_step},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "cold_events": {"value": total_envs * K / (ms_hot * 1e-3), "ms_per_step": ms_hot / K,
-                            "note": "one launch at a time, CUDA events around each launch, 256 MiB L2 flush before it"},
-            "wall_ms_timed_region": t_wall * 1e3,
+            "rollout_last_only": {"value": total_envs * K / (ms_last * 1e-3), "ms_per_step": ms_last / K,
+                                  "note": "same fused launches writing only the last step's outputs (record_every = 0)"},
+            "wall_ms_timed_region": t_wall,
         }
-        if world > 1:
+        if ms_step:
+            a1 = b_alg(c) * n / (ms_step / K * 1e-3) / 1e9
+            line["per_step_launch"] = {"value": total_envs * K / (ms_step * 1e-3), "ms_per_step": ms_step / K, "gpu_launches": int(step_launches),
+                                       "roofline": {"bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak, "alg_bytes_per_env_step": b_alg(c),
+                                                    "traffic": ncu_traffic(f"step_kernel_{cfg_name}_f32_aos_bytes_per_launch"), "kernel": "step_kernel"},
+                                       "note": "K separate gemb200_step launches (one env.step per launch, closed-loop shape), rotating over replicas of the batch"}
+        if ms_e2e:
+            line["e2e"] = {"value": total_envs * ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
+                           "ms_per_step": ms_e2e / ke, "api": "gemb200_step_host via VectorSim.step_host_ptr (NUMA-local pinned host buffers)"}
+        if world > 1 and ms_gather:
             line["with_all_gather"] = {"value": total_envs * K / (ms_gather * 1e-3), "unit": UNIT, "ms_per_step": ms_gather / K,
                                        "bytes_per_rank_per_step": gather_bytes,
-                                       "note": "every step followed by ONE NCCL all_gather_into_tensor of the packed (obs, ref, reward, terminated) "
-                                               "buffer the kernel writes into; `value` above is the sharded layout without it (rank-local consumers)"}
+                                       "note": "every step followed by ONE NCCL all_gather_into_tensor of the packed (obs, ref, reward, terminated) buffer the "
+                                               "kernel writes into, double-buffered on a side stream so that gather(k) overlaps step(k+1); `value` above is the "
+                                               "sharded layout without it (rank-local consumers)"}
+        if others:
+            line["other_configs"] = {}
+            for name, (m2, k2, l2, n2) in others.items():
+                oc = CONFIGS[name]
+                ba2 = b_alg_rollout(oc, min(k2, ROLL_MAX), 1)
+                ach2 = ba2 * n2 / (m2 / k2 * 1e-3) / 1e9
+                line["other_configs"][name] = {"value": n2 * world * k2 / (m2 * 1e-3), "unit": UNIT, "envs_per_gpu": n2, "steps": k2, "ms_per_step": m2 / k2,
+                                               "gpu_launches": int(l2), "alg_bytes_per_env_step": ba2, "roofline_frac": ach2 / peak, "what": oc["what"]}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_arm(65536, 0, 2, budget_s=12.0)
+            v, cores, sample = cpu_arm(cfg_name, 1 << 16, 16, 2, max_seconds=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "note": "python reference itself: ~8.6e3 env.step/s/core (BASELINE.md §2, survey container)"}
         print(json.dumps(line))

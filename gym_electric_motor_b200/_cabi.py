@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 
 # enums (include/gemb200.h)
@@ -137,9 +137,9 @@ _lib = None
 
 SYMBOLS = [
     "gemb200_version", "gemb200_last_error", "gemb200_config_init", "gemb200_query_dims", "gemb200_create",
-    "gemb200_destroy", "gemb200_reset", "gemb200_step", "gemb200_step_host", "gemb200_reset_host", "gemb200_rollout",
+    "gemb200_destroy", "gemb200_reset", "gemb200_step", "gemb200_step_host", "gemb200_reset_host", "gemb200_rollout", "gemb200_rollout_record",
     "gemb200_get_ode_state", "gemb200_set_ode_state", "gemb200_get_reference", "gemb200_set_reference",
-    "gemb200_checkpoint_size", "gemb200_checkpoint_save", "gemb200_checkpoint_load", "gemb200_launch_count",
+    "gemb200_reseed", "gemb200_checkpoint_size", "gemb200_checkpoint_save", "gemb200_checkpoint_load", "gemb200_launch_count",
     "gemb200_kernel_time_begin", "gemb200_kernel_time_end",
 ]
 
@@ -181,10 +181,12 @@ def load_library():
     lib.gemb200_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.gemb200_reset_host.argtypes = [vp, vp, vp, vp]
     lib.gemb200_rollout.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.gemb200_rollout_record.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     lib.gemb200_get_ode_state.argtypes = [vp, vp, vp]
     lib.gemb200_set_ode_state.argtypes = [vp, vp, vp]
     lib.gemb200_get_reference.argtypes = [vp, vp, vp]
     lib.gemb200_set_reference.argtypes = [vp, vp, vp]
+    lib.gemb200_reseed.argtypes = [vp, C.c_uint64, vp]
     lib.gemb200_checkpoint_size.argtypes = [vp]
     lib.gemb200_checkpoint_size.restype = C.c_int64
     lib.gemb200_checkpoint_save.argtypes = [vp, vp]

@@ -72,6 +72,8 @@ class ElectricMotorEnvironment(_EnvBase):
         if not isinstance(reward_function, RewardFunction):
             raise TypeError("reward_function must be a built-in gym_electric_motor_b200 RewardFunction")
         self._scalar = num_envs is None
+        if self._scalar and getattr(physical_system, "_layout", K.LAYOUT_AOS) == K.LAYOUT_SOA:
+            raise ValueError("layout='soa' needs a batched environment (num_envs=...): the scalar contract returns one row per step")
         self._physical_system = physical_system
         self._reference_generator = reference_generator
         self._reward_function = reward_function
@@ -227,12 +229,12 @@ class ElectricMotorEnvironment(_EnvBase):
     def reset(self, seed=None, options=None, mask=None, *_, **__):
         """core.py:300-319.  `seed` re-keys the device RNG streams (new handle state); `mask` (batched mode only)
         resets a subset of envs and returns the full observation tensors."""
-        if seed is not None and int(seed) != self._seed_value:
+        reseed = seed is not None and self._sim is not None
+        if seed is not None:
             self._seed_value = int(seed)
-            if self._sim is not None:
-                self._sim.close()
-                self._sim = None
         sim = self._ensure_sim()
+        if reseed:  # the reference re-seeds every component on EVERY seeded reset (core.py:300-304): equal seeds, identical episodes
+            sim.reseed(self._seed_value)
         self._call_callbacks("on_reset_begin")
         obs, ref = sim.reset(mask)
         self._terminated = False
@@ -266,6 +268,24 @@ class ElectricMotorEnvironment(_EnvBase):
             self._terminated = term and self._autoreset == K.AUTORESET_NONE
             return (state.double().cpu().numpy()[0], ref.double().cpu().numpy()[0]), float(reward[0].item()), term, self._truncated, {}
         return (state, ref), reward, terminated.view(torch.bool), self._truncated, {}  # uint8 0/1 reinterpreted, no kernel
+
+    def rollout(self, actions, record_every=1):
+        """K consecutive `step` calls with pre-computed actions [K, N, n_act] in ONE kernel launch (open loop; bit-identical to calling
+        `step` K times, core.py:328-371).  Returns ((states, references), rewards, terminateds) with a leading axis of K // record_every
+        recorded steps (record_every = 0: only the last step, without the leading axis).  Batched mode only; callbacks see no
+        per-step hooks."""
+        if self._scalar:
+            raise TypeError("rollout() needs a batched environment (num_envs=...)")
+        sim = self._ensure_sim()
+        obs, ref, reward, terminated = sim.rollout(actions, record_every)
+        k = int(actions.shape[0]) if hasattr(actions, "shape") else len(actions)
+        self._physical_system._k += k
+        if not self._filter_identity:
+            if self._filter_index is None:
+                self._filter_index = torch.as_tensor(self.state_filter, device=obs.device)
+            dim = (0 if sim.soa else 1) + (1 if record_every else 0)
+            obs = obs.index_select(dim, self._filter_index)
+        return (obs, ref), reward, terminated.view(torch.bool)
 
     def set_reference(self, values):
         """Push reference values [N, n_ref] for ExternalReferenceGenerator slots (used by the next step's reward)."""

@@ -52,6 +52,7 @@ struct gemb200_handle {
   StepParams<double> pd;
   uint64_t gstep = 0;
   uint64_t n_steps = 0;  // step calls so far (dead-time ring position)
+  uint64_t ext_hash = 0; // FNV-1a of the external speed profile table (part of the checkpoint fingerprint)
   int64_t launches = 0;
   // host-buffer path
   cudaStream_t hstream = nullptr;
@@ -579,29 +580,34 @@ static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cu
 #endif
 }
 
-// One launch over envs [begin, end) (end < 0: all).  new_call: this launch starts a new API call (fresh RNG call id);
-// the chunks of one pipelined host step share the id.
+// One launch over envs [begin, end) (end < 0: all).  new_call: this launch starts a new API call (fresh RNG call ids);
+// the chunks of one pipelined host step share them.  roll > 0: `roll` fused steps (rollout_kernel) whose call ids, step clock and
+// dead-time ring positions are exactly those of `roll` consecutive single-step calls; outputs every `every` steps (0: last only).
 static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, void* rew, uint8_t* term, cudaStream_t st,
-                   int begin = 0, int end = -1, bool new_call = true) {
+                   int begin = 0, int end = -1, bool new_call = true, int roll = 0, int every = 0) {
   if (!action) return fail(GEMB200_E_INVALID, "action is NULL");
-  if (new_call) { h->gstep += 1; h->n_steps += 1; }
+  const uint64_t ksteps = roll > 0 ? (uint64_t)roll : 1;
+  if (new_call) { h->gstep += ksteps; h->n_steps += ksteps; }
+  const uint64_t g0 = h->gstep - (ksteps - 1), n0 = h->n_steps - (ksteps - 1);  // call id / step count of the FIRST step of this launch
   if (end < 0) end = h->cfg.n_envs;
-  const int fifo_slot = h->cfg.dead_time_steps > 0 ? (int)((h->n_steps - 1) % (uint64_t)h->cfg.dead_time_steps) : 0;
+  const int fifo_slot = h->cfg.dead_time_steps > 0 ? (int)((n0 - 1) % (uint64_t)h->cfg.dead_time_steps) : 0;
   cudaError_t e;
   if (h->cfg.dtype == GEMB200_F32) {
     StepParams<float>& p = h->pf;
-    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)h->n_steps;
-    p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)n0;
+    p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32);
+    p.roll_steps = roll; p.record_every = every;
     p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
     e = launch_step<float>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   } else {
     StepParams<double>& p = h->pd;
-    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)h->n_steps;
-    p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)n0;
+    p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32);
+    p.roll_steps = roll; p.record_every = every;
     p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
     e = launch_step<double>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   }
-  if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string("step launch: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string(roll > 0 ? "rollout launch: " : "step launch: ") + cudaGetErrorString(e));
   h->launches += 1;
   return GEMB200_OK;
 }
@@ -727,6 +733,12 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
     } else {
       cudaMemcpy(h->d_ext, cfg->ext_speed_table, (size_t)cfg->ext_speed_len * sizeof(double), cudaMemcpyHostToDevice);
     }
+    {
+      uint64_t x = 1469598103934665603ull;
+      const unsigned char* tb = reinterpret_cast<const unsigned char*>(cfg->ext_speed_table);
+      for (size_t q = 0; q < (size_t)cfg->ext_speed_len * sizeof(double); ++q) { x ^= tb[q]; x *= 1099511628211ull; }
+      h->ext_hash = x;
+    }
     h->cfg.ext_speed_table = nullptr;  // the caller's buffer is not referenced after create
   }
   if (h->any_switched) ALLOC(h->d_swst, n * 2 * cfg->n_ref * sizeof(uint32_t));
@@ -778,19 +790,18 @@ int gemb200_step(gemb200_handle* h, const void* action, void* obs_out, void* ref
   return do_step(h, action, obs_out, ref_out, reward_out, terminated_out, (cudaStream_t)stream);
 }
 
+int gemb200_rollout_record(gemb200_handle* h, const void* actions, int32_t n_steps, int32_t record_every, void* obs_out, void* ref_out,
+                           void* reward_out, uint8_t* terminated_out, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  if (n_steps < 1 || n_steps > (1 << 24)) return fail(GEMB200_E_INVALID, "n_steps must be in [1, 2^24]");
+  if (record_every < 0 || record_every > n_steps) return fail(GEMB200_E_INVALID, "record_every must be in [0, n_steps]");
+  DeviceGuard guard(h->cfg.device);
+  return do_step(h, actions, obs_out, ref_out, reward_out, terminated_out, (cudaStream_t)stream, 0, -1, true, n_steps, record_every);
+}
+
 int gemb200_rollout(gemb200_handle* h, const void* actions, int32_t n_steps, void* obs_out, void* ref_out, void* reward_out,
                     uint8_t* terminated_out, void* stream) {
-  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
-  if (n_steps < 1) return fail(GEMB200_E_INVALID, "n_steps must be >= 1");
-  DeviceGuard guard(h->cfg.device);
-  const size_t asz = (size_t)h->cfg.n_envs * h->n_act * (h->cfg.finite ? sizeof(int32_t) : h->rsz);
-  for (int k = 0; k < n_steps; ++k) {
-    const bool last = k == n_steps - 1;
-    int rc = do_step(h, (const char*)actions + asz * k, last ? obs_out : nullptr, last ? ref_out : nullptr, last ? reward_out : nullptr,
-                     last ? terminated_out : nullptr, (cudaStream_t)stream);
-    if (rc) return rc;
-  }
-  return GEMB200_OK;
+  return gemb200_rollout_record(h, actions, n_steps, 0, obs_out, ref_out, reward_out, terminated_out, stream);
 }
 
 static int ensure_host_buffers(gemb200_handle* h) {
@@ -916,7 +927,8 @@ int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream)
   return GEMB200_OK;
 }
 
-// checkpoint blob: [gstep u64][n_steps u64][hot records][cold records][eps][sw][dead-time queue]
+// checkpoint blob: [header][hot records][cold records][eps][sw][dead-time queue]...  The header pins the blob to the configuration that
+// wrote it: a blob of equal size from another motor / seed / tau / generator set is refused instead of being reinterpreted.
 struct Section { void* ptr; size_t bytes; };
 static int sections(gemb200_handle* h, Section* s) {
   const size_t n = (size_t)h->cfg.n_envs;
@@ -933,21 +945,47 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_kenv) s[k++] = {h->d_kenv, n * sizeof(uint32_t)};
   return k;
 }
+struct CheckpointHeader {
+  char magic[8];          // "GEMB200C"
+  int32_t abi, dtype, n_envs, n_sections, nh, nc, reserved[2];
+  uint64_t config_hash, payload_bytes, gstep, n_steps;
+};
+// FNV-1a over the configuration, leaving out what may legitimately differ between writer and reader: the device ordinal and the
+// host pointer of the speed-profile table (whose CONTENT is hashed at create)
+static uint64_t config_hash(const gemb200_handle* h) {
+  gemb200_config c = h->cfg;
+  c.device = 0;
+  c.ext_speed_table = nullptr;
+  uint64_t x = 1469598103934665603ull;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&c);
+  for (size_t i = 0; i < sizeof(c); ++i) { x ^= b[i]; x *= 1099511628211ull; }
+  x ^= h->ext_hash; x *= 1099511628211ull;
+  return x;
+}
+static void make_header(gemb200_handle* h, CheckpointHeader* hd) {
+  std::memset(hd, 0, sizeof(*hd));
+  std::memcpy(hd->magic, "GEMB200C", 8);
+  hd->abi = GEMB200_ABI_VERSION; hd->dtype = h->cfg.dtype; hd->n_envs = h->cfg.n_envs; hd->nh = h->NH; hd->nc = h->NC;
+  Section s[16];
+  hd->n_sections = sections(h, s);
+  for (int i = 0; i < hd->n_sections; ++i) hd->payload_bytes += s[i].bytes;
+  hd->config_hash = config_hash(h);
+  hd->gstep = h->gstep; hd->n_steps = h->n_steps;
+}
 int64_t gemb200_checkpoint_size(gemb200_handle* h) {
   if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
-  Section s[16];
-  const int k = sections(h, s);
-  int64_t total = 16;
-  for (int i = 0; i < k; ++i) total += (int64_t)s[i].bytes;
-  return total;
+  CheckpointHeader hd;
+  make_header(h, &hd);
+  return (int64_t)sizeof(hd) + (int64_t)hd.payload_bytes;
 }
 int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
   if (!h || !host_blob) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
   CUDA_TRY(cudaDeviceSynchronize());
   char* b = (char*)host_blob;
-  std::memcpy(b, &h->gstep, 8); b += 8;
-  std::memcpy(b, &h->n_steps, 8); b += 8;
+  CheckpointHeader hd;
+  make_header(h, &hd);
+  std::memcpy(b, &hd, sizeof(hd)); b += sizeof(hd);
   Section s[16];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(b, s[i].ptr, s[i].bytes, cudaMemcpyDeviceToHost)); b += s[i].bytes; }
@@ -956,14 +994,45 @@ int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
 int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob) {
   if (!h || !host_blob) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
+  CheckpointHeader want, got;
+  make_header(h, &want);
+  std::memcpy(&got, host_blob, sizeof(got));
+  if (std::memcmp(got.magic, want.magic, 8) != 0) return fail(GEMB200_E_INVALID, "checkpoint: not a gemb200 checkpoint blob (bad magic)");
+  if (got.abi != want.abi) return fail(GEMB200_E_ABI, "checkpoint: written by another ABI version");
+  if (got.dtype != want.dtype || got.n_envs != want.n_envs || got.n_sections != want.n_sections || got.nh != want.nh || got.nc != want.nc ||
+      got.payload_bytes != want.payload_bytes)
+    return fail(GEMB200_E_INVALID, "checkpoint: dtype / n_envs / record layout differ from this handle");
+  if (got.config_hash != want.config_hash)
+    return fail(GEMB200_E_INVALID, "checkpoint: written by a handle with a different configuration (motor, parameters, seed, tau, generators, ...)");
   CUDA_TRY(cudaDeviceSynchronize());
-  const char* b = (const char*)host_blob;
-  std::memcpy(&h->gstep, b, 8); b += 8;
-  std::memcpy(&h->n_steps, b, 8); b += 8;
+  const char* b = (const char*)host_blob + sizeof(got);
+  h->gstep = got.gstep; h->n_steps = got.n_steps;
   Section s[16];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(s[i].ptr, b, s[i].bytes, cudaMemcpyHostToDevice)); b += s[i].bytes; }
   return GEMB200_OK;
+}
+
+// ElectricMotorEnvironment.reset(seed) -> _seed(seed) re-seeds every component (core.py:300-319, utils / RandomComponent.seed): a handle
+// re-keyed with `seed` behaves exactly like a freshly created one with that seed — call ids, step clock, dead-time ring, switching
+// states and every other persistent array start over — so equal seeds give identical episodes.
+int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cfg.seed = seed;
+  h->gstep = 0; h->n_steps = 0;
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t lo = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u, hi = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    h->pf.rk[r][0] = lo; h->pf.rk[r][1] = hi; h->pd.rk[r][0] = lo; h->pd.rk[r][1] = hi;
+  }
+  h->pf.seed_lo = h->pd.seed_lo = (uint32_t)seed; h->pf.seed_hi = h->pd.seed_hi = (uint32_t)(seed >> 32);
+  Section s[16];
+  const int k = sections(h, s);
+  for (int i = 0; i < k; ++i) {
+    CUDA_TRY(cudaMemsetAsync(s[i].ptr, 0, s[i].bytes, st));
+  }
+  return do_reset(h, nullptr, nullptr, nullptr, st);
 }
 
 int64_t gemb200_launch_count(gemb200_handle* h) { return h ? h->launches : 0; }

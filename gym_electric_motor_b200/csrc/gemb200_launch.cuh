@@ -8,6 +8,7 @@
 
 namespace gemb200 {
 
+// p.roll_steps == 0: one step (step_kernel); >= 1: that many fused steps (rollout_kernel)
 template <int FAM, typename real> cudaError_t launch_step_f(bool finite, int nref, const StepParams<real>& p, cudaStream_t st);
 template <int FAM, typename real> cudaError_t launch_reset_f(int nref, const StepParams<real>& p, cudaStream_t st);
 
@@ -19,7 +20,8 @@ static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const size_t smem = (size_t)kBlock * (size_t)p.row_stride * sizeof(real);
   const int range = p.env_end - p.env_begin;
   const int grid = (range + kBlock - 1) / kBlock;
-  step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);
+  if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);
+  else step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);
   return cudaGetLastError();
 }
 // PLAIN instantiations (fp32): {cont, finite} x {constant speed, integrating load} x {AoS, SoA}

@@ -50,11 +50,27 @@ enum : uint32_t {
   kStreamInitState = 7, kStreamInitState2 = 8,                // random initial ODE state
   kStreamSwitch = 10, kStreamSwitchR = 14,                    // + slot: SwitchedReferenceGenerator super-episode (R: at a reset)
   kStreamSupply = 9,                                          // AC supply phase at reset
+  kStreamLaplace = 24, kStreamLaplaceR = 28,                  // Laplace walk increments (R: right after an in-kernel auto-reset)
   kStreamPeriodic = 32,                                       // + 2*slot (+1): sub-episode parameters of the periodic generators,
                                                               //   counter word 0 = step index of the sub-episode start
   kStreamNoise = 64,                                          // + 8*op + (state index >> 2): StateNoiseProcessor draws
   kStreamNoiseR = 128                                         //   ... right after an in-kernel auto-reset
 };
+
+// every stream id (base + its offsets) is used by exactly one consumer: ranges [base, base + width)
+constexpr bool streams_disjoint() {
+  constexpr uint32_t r[][2] = {{kStreamWalk, 1}, {kStreamSubep, 1}, {kStreamInit, 1}, {kStreamWalkR, 1}, {kStreamSubepR, 1}, {kStreamInitState, 1}, {kStreamInitState2, 1},
+                               {kStreamSupply, 1}, {kStreamSwitch, kMaxRef}, {kStreamSwitchR, kMaxRef}, {kStreamSubepHi, 1}, {kStreamSubepHiR, 1}, {kStreamLaplace, 1},
+                               {kStreamLaplaceR, 1}, {kStreamPeriodic, 2 * kMaxRef}, {kStreamNoise, 8 * kMaxStateOps}, {kStreamNoiseR, 8 * kMaxStateOps}};
+  constexpr int n = sizeof(r) / sizeof(r[0]);
+  for (int a = 0; a < n; ++a)
+    for (int b = a + 1; b < n; ++b)
+      if (r[a][0] < r[b][0] + r[b][1] && r[b][0] < r[a][0] + r[a][1]) return false;
+  for (int a = 0; a < n; ++a)
+    if (r[a][0] + r[a][1] > 256) return false;  // the id shares counter word 3 with the high bits of the env index: 8 bits
+  return true;
+}
+static_assert(streams_disjoint(), "RNG stream id ranges overlap");
 
 template <typename real>
 struct StepParams {
@@ -181,6 +197,8 @@ struct StepParams {
   int32_t pf_dist;         // envs between a thread's env and the one it prefetches into L2 (0: off); ~ one wave of resident threads
   int32_t plain;           // 1: this configuration has the PLAIN shape (see step_kernel) -> specialised instantiation
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
+  // ---- fused rollout (rollout_kernel): number of steps of this launch; outputs recorded every `record_every` steps (0: last step only) ----
+  int32_t roll_steps, record_every;
 };
 
 }  // namespace gemb200

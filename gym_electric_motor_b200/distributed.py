@@ -108,6 +108,65 @@ class PackedStepOutputs:
         return self.gathered
 
 
+class OverlappedGather:
+    """Double-buffered `PackedStepOutputs`: step k writes into buffer k % 2 on the caller's stream, its all-gather runs on a side
+    stream while step k+1 computes; buffer b is reused only after the gather that read it has finished (event, no host sync).
+
+        og = OverlappedGather(env.sim, torch.float32)
+        for a in actions: b = og.step(a)          # returns the buffer index whose gather was just enqueued
+        og.finish()                               # caller's stream waits for the outstanding gathers
+        obs, ref, rew, term = og.views(b)         # rank-major [world, n_local, ...] views of buffer b
+    """
+
+    def __init__(self, sim, dtype):
+        import torch
+
+        self.sim, self.torch = sim, torch
+        self.bufs = [PackedStepOutputs(sim.n, sim.n_state, sim.n_ref, dtype, sim.device) for _ in range(2)]
+        self.nbytes = self.bufs[0].nbytes
+        self.side = torch.cuda.Stream(device=sim.device)
+        self.done = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+        self._saved = (sim._reuse, sim._out, getattr(sim, "_out_ptrs", None))
+        self._bound = []
+        for b in self.bufs:  # resolve the output pointers once per buffer
+            sim.bind_outputs(*b.local_views())
+            self._bound.append(sim._out)
+
+    def step(self, action):
+        torch, b = self.torch, self.k % 2
+        cur = torch.cuda.current_stream(self.sim.device)
+        if self.done[b] is not None:
+            cur.wait_event(self.done[b])
+        self.sim._out, self.sim._out_ptrs = self._bound[b], None
+        self.sim.step(action)
+        self.ready[b].record(cur)
+        self.side.wait_event(self.ready[b])
+        with torch.cuda.stream(self.side):
+            self.bufs[b].gather_raw()
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[b] = ev
+        self.k += 1
+        return b
+
+    def finish(self):
+        cur = self.torch.cuda.current_stream(self.sim.device)
+        for ev in self.done:
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def views(self, b):
+        buf = self.bufs[b]
+        per = [buf._views(buf.gathered, r * buf.nbytes) for r in range(buf.world)]
+        return tuple(self.torch.stack([p[k] for p in per]) for k in range(4))
+
+    def release(self):
+        self.finish()
+        self.sim._reuse, self.sim._out, self.sim._out_ptrs = self._saved
+
+
 def all_gather_batch(*tensors):
     """Optional single all-gather of per-rank [n_local, ...] tensors into global [N, ...] tensors (same n_local on every
     rank).  For PMSM at N=2^20 this moves ~72 MB per step — several times the step itself; data-parallel

@@ -105,6 +105,11 @@ class VectorSim:
         K.check(self._lib.gemb200_reset(self._h, _ptr(m), _ptr(obs), _ptr(ref) if self.n_ref else None, self._stream()), "gemb200_reset")
         return obs, ref
 
+    def reseed(self, seed):
+        """re-key the RNG streams and start the handle over (gemb200_reseed): equal seeds -> identical episodes"""
+        K.check(self._lib.gemb200_reseed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), self._stream()), "gemb200_reseed")
+        self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+
     def step(self, action):
         """env.step: returns (obs, ref_next, reward, terminated) device tensors (views of reused buffers unless
         reuse_outputs=False)."""
@@ -123,13 +128,33 @@ class VectorSim:
             K.check(rc, "gemb200_step")
         return out
 
-    def rollout(self, actions):
-        """K open-loop steps with actions [K, ...]; returns the outputs of the last step."""
-        a = torch.as_tensor(actions, device=self.device).to(self.act_dtype).contiguous()
-        k = a.shape[0]
-        obs, ref, rew, term = self._alloc_outputs()
-        K.check(self._lib.gemb200_rollout(self._h, _ptr(a), k, _ptr(obs), _ptr(ref) if self.n_ref else None, _ptr(rew), _ptr(term), self._stream()), "gemb200_rollout")
+    def rollout(self, actions, record_every=0):
+        """K open-loop env.step calls fused into ONE launch (gemb200_rollout_record): every env's record stays in registers for all K
+        steps; bit-identical to K calls of `step`.  actions: [K, N, n_act] (SoA layout: [K, n_act, N]).
+        record_every = 0 -> the outputs of the last step (obs, ref, reward, terminated), shapes as `step`;
+        record_every = m >= 1 -> the outputs of steps m, 2m, ... stacked on a leading axis of length K // m (m = 1: full trajectory)."""
+        a = actions if (isinstance(actions, torch.Tensor) and actions.dtype == self.act_dtype and actions.device == self.device and actions.is_contiguous()) \
+            else torch.as_tensor(actions, device=self.device).to(self.act_dtype).contiguous()
+        k = int(a.shape[0])
+        if a.numel() != k * self.n * self.n_act:
+            raise ValueError(f"actions must hold K x {self.n} x {self.n_act} values")
+        m = int(record_every)
+        if m == 0:
+            obs, ref, rew, term = self._alloc_outputs()
+        else:
+            s = k // m
+            obs = torch.empty((s,) + self._shape(self.n_state), dtype=self.dtype, device=self.device)
+            ref = torch.empty((s,) + self._shape(self.n_ref), dtype=self.dtype, device=self.device)
+            rew = torch.empty((s, self.n), dtype=self.dtype, device=self.device)
+            term = torch.empty((s, self.n), dtype=torch.uint8, device=self.device)
+        K.check(self._lib.gemb200_rollout_record(self._h, _ptr(a), k, m, _ptr(obs), _ptr(ref) if self.n_ref else None, _ptr(rew), _ptr(term), self._stream()),
+                "gemb200_rollout_record")
         return obs, ref, rew, term
+
+    def rollout_into(self, actions, n_steps, record_every, obs, ref, rew, term):
+        """Raw variant for benchmarking: caller-owned output tensors (any may be None), no allocation, no conversion."""
+        K.check(self._lib.gemb200_rollout_record(self._h, _ptr(actions), int(n_steps), int(record_every), _ptr(obs), _ptr(ref) if self.n_ref else None,
+                                                 _ptr(rew), _ptr(term), self._stream()), "gemb200_rollout_record")
 
     # ------------------------------------------------------------------ host-buffer API (numpy)
     def step_host(self, action, out=None):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 8
+#define GEMB200_ABI_VERSION 9
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -283,10 +283,16 @@ int gemb200_step_host(gemb200_handle* h, const void* action, void* obs_out, void
                       uint8_t* terminated_out);
 int gemb200_reset_host(gemb200_handle* h, const uint8_t* reset_mask, void* obs_out, void* ref_out);
 
-/* K consecutive steps in one call with actions[K][N][n_act] resident on the device (open-loop rollout; the outputs
- * are those of the last step).  Used for benchmarking the kernel without per-step host work. */
+/* K consecutive env.step calls (core.py:328-371 called K times, open loop) fused into ONE launch: actions[K][N][n_act] resident on
+ * the device; every env's persistent record stays in registers for all K steps (loaded once, stored once), the clock, the RNG call
+ * ids and the dead-time ring advance exactly as K separate gemb200_step calls would, so results are bit-identical to them.
+ * gemb200_rollout returns the outputs of the LAST step ([N][..] tensors).  gemb200_rollout_record additionally streams the outputs
+ * of steps m, 2m, ... (m = record_every >= 1) into [K / m][N][..] tensors (m = 1: the full trajectory); record_every = 0 is
+ * gemb200_rollout.  Any output pointer may be NULL. */
 int gemb200_rollout(gemb200_handle* h, const void* actions, int32_t n_steps, void* obs_out, void* ref_out,
                     void* reward_out, uint8_t* terminated_out, void* stream);
+int gemb200_rollout_record(gemb200_handle* h, const void* actions, int32_t n_steps, int32_t record_every, void* obs_out, void* ref_out,
+                           void* reward_out, uint8_t* terminated_out, void* stream);
 
 /* OdeSolver.y / set_initial_value (physical_systems/solvers.py:4-76): ODE state as double [N][n_ode]
  * (AoS, device), angle unwrapped to (-pi, pi].  Used for checkpointing and oracle injection. */
@@ -298,8 +304,15 @@ int gemb200_set_ode_state(gemb200_handle* h, const double* ode_in, void* stream)
 int gemb200_get_reference(gemb200_handle* h, double* ref_out, void* stream);
 int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream);
 
+/* ElectricMotorEnvironment.reset(seed=...) -> _seed(seed) (core.py:300-319): re-key the handle's RNG streams with `seed` and start every
+ * counter and persistent array over, then reset all envs — afterwards the handle is indistinguishable from a freshly created one with
+ * cfg.seed = seed, so equal seeds give identical episodes.  Stream-ordered. */
+int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream);
+
 /* Opaque checkpoint of everything a handle owns (ODE state, switching state, reference state, step counter):
- * size query, export to / import from a HOST blob. */
+ * size query, export to / import from a HOST blob.  The blob starts with a header (magic, ABI version, dtype, n_envs, record layout,
+ * fingerprint of the configuration); gemb200_checkpoint_load refuses a blob written by a handle of another configuration
+ * (GEMB200_E_INVALID) or ABI (GEMB200_E_ABI) instead of reinterpreting it. */
 int64_t gemb200_checkpoint_size(gemb200_handle* h);
 int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob);
 int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob);

@@ -108,7 +108,7 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
        STREAM_SWITCH = 10, STREAM_SWITCH_R = 14 /* + slot: SwitchedReferenceGenerator super-episodes (R: at a reset) */,
-       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */,
+       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */, STREAM_LAPLACE = 24, STREAM_LAPLACE_R = 28 /* Laplace walk increments */,
        STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */,
        STREAM_NOISE = 64 /* + 8*op + (state >> 2): StateNoiseProcessor */, STREAM_NOISE_R = 128 /* ... right after an auto-reset */ };
 
@@ -1128,7 +1128,7 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
     }
     double z;
     if (kind == GEMB200_REF_LAPLACE) { /* random_generator.laplace(0, sigma): inverse CDF, laplace_process_reference_generator.py:25-28 */
-      if (!have_lap) { rng4(o, idx, (after_reset ? STREAM_WALK_R : STREAM_WALK) + 8, rlap); have_lap = 1; }
+      if (!have_lap) { rng4(o, idx, after_reset ? STREAM_LAPLACE_R : STREAM_LAPLACE, rlap); have_lap = 1; }
       double u = u01(rlap[r]);
       z = u < 0.5 ? log(2.0 * u) : -log(2.0 * (1.0 - u));
     } else {

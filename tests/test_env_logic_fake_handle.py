@@ -35,6 +35,10 @@ class ScriptedHandle:
             term[0] = 1
         return obs, torch.full((self.n, self.n_ref), 0.25), torch.full((self.n,), -0.5), term
 
+    def reseed(self, seed):
+        self.reseeds = getattr(self, "reseeds", []) + [int(seed)]
+        self.cfg.seed = int(seed)
+
     def close(self):
         self.closed = True
 
@@ -111,9 +115,13 @@ def test_batched_contract_reseed_and_setters(scripted):
     assert terminated.dtype == torch.bool and terminated.tolist() == [True] + [False] * 5 and tuple(reward.shape) == (6,)
     env.step(torch.zeros(6, 1))                                      # batched envs with auto-reset keep stepping
     env.reset(seed=3)
-    assert scripted.created[-1] is first                             # same seed: same handle
+    assert scripted.created[-1] is first and first.reseeds == [3]     # EVERY seeded reset re-keys the handle (reference core.py:300-304) ...
+    env.reset(seed=3)
+    assert first.reseeds == [3, 3]                                    # ... also with the seed it already has: equal seeds, identical episodes
     env.reset(seed=4)
-    assert first.closed and scripted.created[-1] is not first and scripted.created[-1].cfg.seed == 4   # new seed: re-keyed handle
+    assert scripted.created[-1] is first and first.reseeds == [3, 3, 4] and first.cfg.seed == 4
+    env.reset()
+    assert first.reseeds == [3, 3, 4]                                 # an unseeded reset continues the streams
     second = scripted.created[-1]
     env.reference_generator = gem.reference_generators.ConstReferenceGenerator(reference_state="omega", reference_value=0.3)
     assert second.closed and env.physical_system._sim is None

@@ -48,6 +48,11 @@ def test_device_matches_oracle_for_host_built_config(oracle_lib, case):
     assert np.abs(d_obs.double().cpu().numpy() - o_obs).max() < 1e-9 and np.abs(d_ref.double().cpu().numpy() - o_ref).max() < 1e-9
     rng = np.random.default_rng(3)
     sp = env.action_space
+    # Induction motors: the dq columns are expressed in the rotor-flux frame, whose angle is decided by round-off while the flux is
+    # still (numerically) zero after the reset — in the reference itself (DESIGN.md finding 3; same treatment as
+    # test_gpu_parity.test_device_reproduces_reference_trajectory): there the dq pairs are compared through their magnitude and the
+    # reward (which sees i_sd / i_sq in current-control envs) is not compared.
+    dq_pairs = {K.MOTOR_SCIM: ((5, 6), (10, 11)), K.MOTOR_DFIM: ((5, 6), (10, 11), (15, 16), (20, 21))}.get(cfg.motor_kind, ())
     for k in range(12):
         if hasattr(sp, "low"):
             a = rng.uniform(sp.low, sp.high, size=(n, len(sp.low)))
@@ -55,11 +60,21 @@ def test_device_matches_oracle_for_host_built_config(oracle_lib, case):
             a = np.stack([rng.integers(0, int(m), size=n) for m in sp.nvec], axis=1).astype(np.int32)
         else:
             a = rng.integers(0, sp.n, size=(n, 1)).astype(np.int32)
+        psi = ora.get_ode_state()[:, 3:5] if dq_pairs else None
         o = ora.step(a)
         d = sim.step(a)
         tol = 1e-8
-        assert np.abs(d[0].double().cpu().numpy() - o[0]).max() < tol, (case, k)
+        d_obs, o_obs = d[0].double().cpu().numpy().copy(), o[0].copy()
+        weak = np.zeros(n, dtype=bool)
+        if dq_pairs:
+            weak = np.hypot(psi[:, 0], psi[:, 1]) < 1e-3
+            for arr in (d_obs, o_obs):
+                for a_, b_ in dq_pairs:
+                    if b_ < arr.shape[1]:
+                        arr[weak, a_] = np.hypot(arr[weak, a_], arr[weak, b_])
+                        arr[weak, b_] = 0.0
+        assert np.abs(d_obs - o_obs).max() < tol, (case, k)
         assert np.abs(d[1].double().cpu().numpy() - o[1]).max() < tol, (case, k)
-        assert np.abs(d[2].double().cpu().numpy() - o[2]).max() < 10 * tol, (case, k)
-        assert np.array_equal(d[3].cpu().numpy().astype(np.uint8), o[3]), (case, k)
+        assert np.abs(d[2].double().cpu().numpy() - o[2])[~weak].max(initial=0.0) < 10 * tol, (case, k)
+        assert np.array_equal(d[3].cpu().numpy().astype(np.uint8)[~weak], o[3][~weak]), (case, k)
     sim.close()

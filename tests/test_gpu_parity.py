@@ -643,6 +643,65 @@ def test_more_reference_generators_match_oracle(torch_cuda, oracle_lib, kinds, d
     assert bad <= (0 if dtype == K.F64 else 0.004 * total), (bad, total)
 
 
+@pytest.mark.parametrize("env_id", ["Cont-CC-PMSM-v0", "Finite-SC-PMSM-v0", "Cont-SC-PermExDc-v0"])
+def test_repeated_seeded_reset_gives_identical_episodes(torch_cuda, env_id):
+    """reference: reset(seed) -> _seed(seed) re-seeds every component on EVERY seeded reset (core.py:300-304), so equal seeds give
+    identical episodes — also the seed the env already has, also seed 0 on a fresh env, also after steps."""
+    import torch
+    import gym_electric_motor_b200 as gem
+
+    n = 512
+    env = gem.make(env_id, num_envs=n, autoreset="same_step", ode_solver=gem.physical_systems.RK4Solver())
+    fresh = gem.make(env_id, num_envs=n, autoreset="same_step", ode_solver=gem.physical_systems.RK4Solver(), seed=42)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    if hasattr(env.action_space, "low"):
+        acts = [torch.rand((n, len(env.action_space.low)), generator=g, device="cuda") * 2 - 1 for _ in range(30)]
+    else:
+        acts = [torch.randint(0, env.action_space.n, (n, 1), generator=g, device="cuda", dtype=torch.int32) for _ in range(30)]
+
+    def episode(e, seed):
+        (s, r), _ = e.reset(seed=seed)
+        out = [(s.clone(), r.clone())]
+        for a in acts:
+            (s, r), w, t, _, _ = e.step(a)
+            out.append((s.clone(), r.clone(), w.clone(), t.clone()))
+        return out
+
+    def same(x, y):
+        return all(all(torch.equal(p, q) for p, q in zip(a, b)) for a, b in zip(x, y))
+
+    e0a, e0b = episode(env, 0), episode(env, 0)      # seed 0 on a fresh env (whose stored default is 0), then again
+    assert same(e0a, e0b)
+    e42a, e42b = episode(env, 42), episode(env, 42)  # repeated seed after other episodes
+    assert same(e42a, e42b) and not same(e0a, e42a)
+    assert same(e42a, episode(fresh, 42))            # and equal to a freshly made env with that seed
+    (s1, r1), _ = env.reset()                        # an unseeded reset continues the streams: new references
+    assert not torch.equal(r1, e42a[0][1])
+
+
+def test_checkpoint_of_another_configuration_is_refused(torch_cuda):
+    """a blob of EQUAL size from another configuration (PMSM vs SynRM, another seed, another tau) must not load"""
+    import gym_electric_motor_b200 as gem
+
+    n = 64
+    a = gem.make("Cont-CC-PMSM-v0", num_envs=n, seed=1)
+    others = [gem.make("Cont-CC-SynRM-v0", num_envs=n, seed=1), gem.make("Cont-CC-PMSM-v0", num_envs=n, seed=2), gem.make("Cont-CC-PMSM-v0", num_envs=n, seed=1, tau=5e-5)]
+    for e in [a] + others:
+        e.reset()
+    blob = a.state_dict()
+    twin = gem.make("Cont-CC-PMSM-v0", num_envs=n, seed=1)
+    twin.reset()
+    twin.load_state_dict(blob)  # same configuration: accepted
+    for e in others:
+        assert e.state_dict()["blob"].size == blob["blob"].size
+        with pytest.raises(K.GemB200Error, match="different configuration"):
+            e.load_state_dict(blob)
+    bad = {"blob": blob["blob"].copy()}
+    bad["blob"][0] ^= 0xFF
+    with pytest.raises(K.GemB200Error, match="bad magic"):
+        twin.load_state_dict(bad)
+
+
 def test_vector_facade_steps(torch_cuda):
     import gym_electric_motor_b200 as gem
 

@@ -1,0 +1,212 @@
+"""Fused K-step rollout (gemb200_rollout / gemb200_rollout_record = rollout_kernel) against K single-step launches (gemb200_step =
+step_kernel) of the SAME configuration: the reference semantics are `env.step` called K times (core.py:328-371), so the bar is
+bit-for-bit equality of every recorded output, of the persistent state afterwards (checkpoint blob) and of the steps that follow.
+Oracle parity of the rollout path itself: test_rollout_matches_oracle."""
+import numpy as np
+import pytest
+
+from helpers import config_from_meta, load_golden, switched_config
+from gym_electric_motor_b200 import _cabi as K
+from test_gpu_parity import _random_actions, torch_cuda  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+# plain / general instantiations, every motor family, the side state that lives outside the registers (switching states, dead-time
+# ring, RC / AC supply, flux observer, external speed profile position, switched generators)
+CASES = ["pmsm_cc_rk4", "pmsm_sc_polyload_rk4", "pmsm_fin_sc_rk4", "pmsm_fin_sc_rk4_interlock", "pmsm_cc_euler3", "synrm_cc_rk4", "eesm_cc_rk4",
+         "eesm_fin_cc_rk4", "scim_cc_rk4", "scim_fin_cc_interlock_rk4", "dfim_cc_rk4", "permex_cc_rk4", "series_cc_rk4", "shunt_cc_rk4", "extex_cc_rk4",
+         "permex_fin_sc_rc_interlock_rk4", "pmsm_cc_ac_rk4", "pmsm_cc_extspeed_rk4", "scim_sc_flux_cossin_dead1_rk4", "eesm_cc_rc_dq_dead1_rk4",
+         "pmsm_cc_cossin_rk4", "dfim_cc_flux_dq_rk4"]
+
+
+def _mk(name, n, dtype, layout, ref_kind=K.REF_WIENER):
+    g = load_golden(name)
+    init = np.array(g["reset_ode"], dtype=float)
+    n_ode = len(init)
+    init[1:] = [0.7, -0.4, 0.02, 0.03, 0.3][: n_ode - 1] if g["meta"]["motor_class"] in ("SquirrelCageInductionMotor", "DoublyFedInductionMotor") else \
+        [0.9, -0.6, 0.5, 0.3][: n_ode - 1]
+    cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=init, dtype=dtype, solver=None, ref_kind=ref_kind, autoreset=K.AUTORESET_SAME_STEP, seed=77,
+                           layout=layout)
+    for r in range(cfg.n_ref):
+        cfg.ref_margin_lo[r], cfg.ref_margin_hi[r] = -0.7, 0.7
+        cfg.ref_init_lo[r], cfg.ref_init_hi[r] = -0.7, 0.7
+        cfg.ref_len_lo[r], cfg.ref_len_hi[r] = 3, 9  # several sub-episode changes inside one rollout
+    cfg.env_index_offset = 12345
+    if cfg.supply_kind == K.SUPPLY_AC1:
+        cfg.supply_param[2] = 0.0
+    return g, cfg
+
+
+def _dev_actions(torch, sim, acts):
+    """[K, N, n_act] numpy -> device tensor in the sim's layout and action dtype"""
+    a = np.asarray(acts).reshape(acts.shape[0], sim.n, sim.n_act)
+    if sim.soa:
+        a = np.ascontiguousarray(a.transpose(0, 2, 1))
+    return torch.as_tensor(a, device=sim.device).to(sim.act_dtype).contiguous()
+
+
+@pytest.mark.parametrize("layout", [K.LAYOUT_AOS, K.LAYOUT_SOA], ids=["aos", "soa"])
+@pytest.mark.parametrize("dtype", [K.F32, K.F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("name", CASES)
+def test_rollout_is_bit_identical_to_repeated_steps(torch_cuda, name, dtype, layout):
+    torch = torch_cuda
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    n, k_total = 777, 24  # not a multiple of the warp / block size; long enough for terminations + auto-resets + new sub-episodes
+    g, cfg = _mk(name, n, dtype, layout)
+    a, b, c = VectorSim(cfg), VectorSim(cfg), VectorSim(cfg)
+    rng = np.random.default_rng(5)
+    acts = _random_actions(rng, g, n, k_total + 3)
+    dev = _dev_actions(torch, a, acts)
+    for s in (a, b, c):
+        s.reset()
+    # a: K single-step launches, keeping every output
+    per_step = []
+    for k in range(k_total):
+        per_step.append(tuple(t.clone() for t in a.step(dev[k])))
+    # b: ONE launch, full trajectory
+    obs, ref, rew, term = b.rollout(dev[:k_total], record_every=1)
+    for k in range(k_total):
+        assert torch.equal(obs[k], per_step[k][0]), (name, "obs", k)
+        assert torch.equal(ref[k], per_step[k][1]), (name, "ref", k)
+        assert torch.equal(rew[k], per_step[k][2]), (name, "reward", k)
+        assert torch.equal(term[k], per_step[k][3]), (name, "terminated", k)
+    # c: 5 fused steps (last only) + 7 (every step) + 12 (every 4th): the clock carries over between launches
+    last = c.rollout(dev[:5], record_every=0)
+    for x, y in zip(last, per_step[4]):
+        assert torch.equal(x, y), (name, "last-only")
+    o7 = c.rollout(dev[5:12], record_every=1)
+    for j in range(7):
+        assert torch.equal(o7[0][j], per_step[5 + j][0]) and torch.equal(o7[3][j], per_step[5 + j][3])
+    o12 = c.rollout(dev[12:24], record_every=4)
+    assert o12[0].shape[0] == 3
+    for j in range(3):
+        for q in range(4):
+            assert torch.equal(o12[q][j], per_step[12 + 4 * j + 3][q]), (name, "every 4th", j, q)
+    # persistent state afterwards: everything a handle owns, byte for byte
+    blobs = [s.state_dict()["blob"] for s in (a, b, c)]
+    assert np.array_equal(blobs[0], blobs[1]) and np.array_equal(blobs[0], blobs[2])
+    # and the steps that follow agree as well
+    for k in range(k_total, k_total + 3):
+        outs = [tuple(t.clone() for t in s.step(dev[k])) for s in (a, b, c)]
+        for q in range(4):
+            assert torch.equal(outs[0][q], outs[1][q]) and torch.equal(outs[0][q], outs[2][q])
+    n_term = sum(int(p[3].sum().item()) for p in per_step)
+    if name in ("pmsm_cc_rk4", "eesm_cc_rk4", "permex_cc_rk4"):
+        assert n_term > 0, "the case is meant to cross terminations + in-kernel resets inside the rollout"
+    for s in (a, b, c):
+        s.close()
+
+
+@pytest.mark.parametrize("case", ["wiener_sinus_step", "const_laplace_triangular"])
+def test_rollout_with_switched_and_periodic_generators(torch_cuda, case):
+    torch = torch_cuda
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    kinds = dict(
+        wiener_sinus_step=[dict(kind=K.REF_WIENER, margin=(-0.5, 0.5)), dict(kind=K.REF_SINUS), dict(kind=K.REF_STEP, amp=(0.05, 0.2))],
+        const_laplace_triangular=[dict(kind=K.REF_CONST, value=0.25), dict(kind=K.REF_LAPLACE, sigma=(1e-3, 5e-3)), dict(kind=K.REF_TRIANGULAR)])[case]
+    n, k_total = 300, 60
+    cfg = switched_config(n, kinds, [1.0 / 3] * 3, (5, 12), seed=21, dtype=K.F32)
+    cfg.n_constraints = 1
+    a, b = VectorSim(cfg), VectorSim(cfg)
+    rng = np.random.default_rng(1)
+    acts = rng.uniform(-1, 1, size=(k_total, n, a.n_act))
+    dev = _dev_actions(torch, a, acts)
+    a.reset()
+    b.reset()
+    per_step = [tuple(t.clone() for t in a.step(dev[k])) for k in range(k_total)]
+    out = b.rollout(dev, record_every=1)
+    for k in range(k_total):
+        for q in range(4):
+            assert torch.equal(out[q][k], per_step[k][q]), (case, k, q)
+    assert np.array_equal(a.state_dict()["blob"], b.state_dict()["blob"])
+
+
+@pytest.mark.parametrize("dtype,tol", [(K.F64, 1e-9), (K.F32, 1e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("name", ["pmsm_cc_rk4", "pmsm_fin_sc_rk4", "scim_cc_rk4", "eesm_cc_rk4", "permex_cc_rk4"])
+def test_rollout_matches_oracle(torch_cuda, oracle_lib, name, dtype, tol):
+    """the rollout path against the CPU oracle directly (not only through the step kernel): full trajectory of 1000 envs x 60 steps"""
+    torch = torch_cuda
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    n, k_total = 1000, 60
+    g, cfg = _mk(name, n, dtype, K.LAYOUT_AOS)
+    _, cfg_o = _mk(name, n, K.F64, K.LAYOUT_AOS)
+    sim, ora = VectorSim(cfg), oracle_lib.Oracle(cfg_o, nthreads=8)
+    rng = np.random.default_rng(11)
+    acts = _random_actions(rng, g, n, k_total)
+    sim.reset()
+    ora.reset()
+    obs, ref, rew, term = [t.cpu().numpy() for t in sim.rollout(_dev_actions(torch, sim, acts), record_every=1)]
+    alive = np.ones(n, dtype=bool)
+    scale = np.full(obs.shape[2], 1e-3)
+    weak_dq = ((5, 6), (10, 11)) if name.startswith("scim") else ()
+    for k in range(k_total):
+        psi = ora.get_ode_state()[:, 3:5] if weak_dq else None
+        o_obs, o_ref, o_rew, o_term = ora.step(acts[k])
+        d_obs = obs[k].astype(np.float64)
+        if weak_dq:  # field-frame columns while the rotor flux is ~0 (DESIGN.md finding 3): compare the magnitude
+            weak = np.hypot(psi[:, 0], psi[:, 1]) < 1e-3
+            for arr in (d_obs, o_obs):
+                for p_, q_ in weak_dq:
+                    arr[weak, p_] = np.hypot(arr[weak, p_], arr[weak, q_])
+                    arr[weak, q_] = 0.0
+        alive &= ~(alive & (o_term != term[k]))  # a constraint within rounding of its threshold: the episodes diverge from here
+        scale = np.maximum(scale, np.abs(o_obs[alive]).max(axis=0))
+        diff = np.abs(d_obs - o_obs)
+        for j, nm in enumerate(g["meta"]["state_names"]):
+            if nm == "epsilon":
+                diff[:, j] = np.abs((d_obs[:, j] - o_obs[:, j] + 1.0) % 2.0 - 1.0)
+        assert (diff[alive] / scale).max() < tol, (name, k)
+        assert np.abs(rew[k] - o_rew)[alive].max() < 20 * tol
+        if ref.shape[-1]:
+            assert np.abs(ref[k] - o_ref)[alive].max() < 20 * tol
+    assert alive.mean() > 0.995
+
+
+def test_env_rollout_public_api(torch_cuda):
+    """`env.rollout(actions)` of the batched environment == K x `env.step`, incl. the state filter"""
+    torch = torch_cuda
+    import gym_electric_motor_b200 as gem
+
+    n, k_total = 2048, 16
+    mk = lambda: gem.make("Cont-CC-PMSM-v0", num_envs=n, ode_solver=gem.physical_systems.RK4Solver(), autoreset="same_step", seed=3,  # noqa: E731
+                          state_filter=["omega", "i_sd", "i_sq", "epsilon"])
+    e1, e2 = mk(), mk()
+    e1.reset()
+    e2.reset()
+    acts = torch.rand((k_total, n, 3), device="cuda") * 2 - 1
+    (st, rf), rw, tm = e2.rollout(acts, record_every=1)
+    assert st.shape == (k_total, n, 4) and rf.shape == (k_total, n, 2) and tm.dtype == torch.bool
+    for k in range(k_total):
+        (s1, r1), w1, t1, _, _ = e1.step(acts[k])
+        assert torch.equal(s1, st[k]) and torch.equal(r1, rf[k]) and torch.equal(w1, rw[k]) and torch.equal(t1, tm[k])
+    assert e2.physical_system.k == k_total
+    e1.close()
+    e2.close()
+
+
+def test_full_size_rollout_replication_property(torch_cuda):
+    """BASELINE size (N = 2^20, Cont-CC-PMSM-v0, RK4), 16 fused steps: 1024 action streams replicated 1024 times across the grid;
+    every replica must be bit-identical to its prototype at every recorded step, and the last step must equal 16 single-step
+    launches of a second handle."""
+    torch = torch_cuda
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    g = load_golden("pmsm_cc_rk4")
+    n, proto, k_total = 1 << 20, 1024, 16
+    cfg = config_from_meta(g["meta"], n_envs=n, reset_ode=g["reset_ode"], dtype=K.F32, solver="rk4", ref_kind=K.REF_CONST)
+    for r in range(cfg.n_ref):
+        cfg.ref_value[r] = 0.1 * (r + 1)
+    a, b = VectorSim(cfg), VectorSim(cfg)
+    a.reset()
+    b.reset()
+    acts = (torch.rand((k_total, proto, 3), device="cuda") * 2 - 1).repeat(1, n // proto, 1).contiguous()
+    obs, ref, rew, term = b.rollout(acts, record_every=4)
+    for j in range(k_total // 4):
+        v = obs[j].view(n // proto, proto, -1)
+        assert torch.equal(v, v[0:1].expand_as(v))
+    for k in range(k_total):
+        last = a.step(acts[k])
+    assert torch.equal(last[0], obs[-1]) and torch.equal(last[2], rew[-1]) and torch.equal(last[3], term[-1])
