@@ -107,6 +107,8 @@ class GemB200Config(C.Structure):
         ("ext_speed_len", C.c_int32),
         ("supply_kind", C.c_int32),
         ("supply_param", C.c_double * 4),
+        ("init_im_valid", C.c_int32),
+        ("init_im", C.c_double * 8),
     ]
 
 

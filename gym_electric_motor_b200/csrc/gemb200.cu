@@ -47,6 +47,7 @@ struct gemb200_handle {
   uint32_t* d_kenv = nullptr;  // steps since the reset per env (external speed profile)
   uint32_t* d_swst = nullptr;  // switched reference generators [n_ref][2][n]
   void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
+  void* d_imprev = nullptr;  // induction motors with random initial states [2][n]: initial currents of the env's previous episode
   int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
   StepParams<double> pd;
@@ -155,11 +156,13 @@ static int validate(const gemb200_config* c) {
   }
   if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
   if (c->dead_time_steps < 0 || c->dead_time_steps > GEMB200_MAX_DEAD_TIME) return fail(GEMB200_E_INVALID, "dead_time_steps out of range");
-  if (c->init_random && (c->motor_kind == GEMB200_MOTOR_SCIM || c->motor_kind == GEMB200_MOTOR_DFIM))
-    return fail(GEMB200_E_INVALID, "random initial states are not supported for the induction motor (the reference draws its flux limits "
-                                   "from the unseeded global numpy RNG, squirrel_cage_induction_motor.py:146-157)");
+  const bool induction = c->motor_kind == GEMB200_MOTOR_SCIM || c->motor_kind == GEMB200_MOTOR_DFIM;
+  if (c->init_random && induction && !c->init_im_valid)
+    return fail(GEMB200_E_INVALID, "random initial states of an induction motor need init_im (flux-limit constants, see gemb200.h)");
+  if (c->init_im_valid && !(induction && c->init_random)) return fail(GEMB200_E_INVALID, "init_im is for induction motors with init_random");
+  if (c->init_im_valid && !(c->init_im[4] != 0.0)) return fail(GEMB200_E_INVALID, "init_im[4] (p * l_m / l_r) must be non-zero");
   for (int j = 0; j < GEMB200_MAX_ODE; ++j)
-    if (c->init_random && c->init_dist[j] && !(c->init_sigma[j] > 0 && c->init_hi[j] > c->init_lo[j]))
+    if (c->init_random && c->init_dist[j] && !(c->init_sigma[j] > 0 && (c->init_hi[j] > c->init_lo[j])))
       return fail(GEMB200_E_INVALID, "truncated-normal initial state needs sigma > 0 and a non-empty interval");
   if (c->supply_kind < GEMB200_SUPPLY_IDEAL || c->supply_kind > GEMB200_SUPPLY_AC1) return fail(GEMB200_E_INVALID, "bad supply_kind");
   if (c->supply_kind == GEMB200_SUPPLY_AC1 && !(c->supply_param[0] > 0)) return fail(GEMB200_E_INVALID, "AC supply needs a positive frequency");
@@ -413,12 +416,16 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     p->inv_lim[eps_idx] = real(1);  // the angle entry is already normalised by eps_out_scale
   }
   p->init_random = c.init_random;
+  p->init_im_valid = c.init_im_valid;
+  for (int j = 0; j < 8; ++j) p->init_im[j] = (real)c.init_im[j];
+  p->im_prev = static_cast<real*>(h->d_imprev);
   {  // truncated-normal states: CDF bounds prepared in double; the angle entry is converted to the stored unit like init_lo
     const int nst = dm.nx + (dm.has_eps ? 1 : 0);
     for (int j = 0; j < nst; ++j) {
       if (!c.init_random || !c.init_dist[j]) continue;
       const double unit = (j == dm.nx && sizeof(real) == 4) ? 1.0 / (2 * M_PI) : 1.0;
-      const double mu = c.init_mu[j], sg = c.init_sigma[j];
+      p->init_mid[j] = std::isnan(c.init_mu[j]);  // mue = middle of the (possibly per-env) interval
+      const double mu = p->init_mid[j] ? 0.5 * (c.init_hi[j] - c.init_lo[j]) + c.init_lo[j] : c.init_mu[j], sg = c.init_sigma[j];
       const double ca = 0.5 * std::erfc(-(c.init_lo[j] - mu) / sg * M_SQRT1_2), cb = 0.5 * std::erfc(-(c.init_hi[j] - mu) / sg * M_SQRT1_2);
       p->init_gauss = 1; p->init_dist[j] = 1;
       p->init_mu[j] = (real)(mu * unit); p->init_sigma[j] = (real)(sg * unit);
@@ -633,6 +640,24 @@ static int do_reset(gemb200_handle* h, const uint8_t* mask, void* obs, void* ref
   return GEMB200_OK;
 }
 
+// induction motors: before the first reset the "previous" initial currents are the constant ones (_initial_states of a fresh motor)
+static int fill_imprev(gemb200_handle* h, cudaStream_t st) {
+  if (!h->d_imprev) return GEMB200_OK;
+  const size_t n = (size_t)h->cfg.n_envs;
+  if (h->cfg.dtype == GEMB200_F32) {
+    std::vector<float> v(2 * n);
+    for (size_t q = 0; q < n; ++q) { v[q] = (float)h->cfg.init_ode[1]; v[n + q] = (float)h->cfg.init_ode[2]; }
+    CUDA_TRY(cudaMemcpyAsync(h->d_imprev, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  } else {
+    std::vector<double> v(2 * n);
+    for (size_t q = 0; q < n; ++q) { v[q] = h->cfg.init_ode[1]; v[n + q] = h->cfg.init_ode[2]; }
+    CUDA_TRY(cudaMemcpyAsync(h->d_imprev, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return GEMB200_OK;
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -743,6 +768,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   }
   if (h->any_switched) ALLOC(h->d_swst, n * 2 * cfg->n_ref * sizeof(uint32_t));
   if (d.has_observer) ALLOC(h->d_obsv, n * 4 * h->rsz);
+  if (cfg->init_im_valid) ALLOC(h->d_imprev, n * 2 * h->rsz);
 #undef ALLOC
   Derived dv;
   derive_model(cfg, d, &dv);
@@ -757,6 +783,8 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   fill_params<double>(h, d, dv, &h->pd);
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  rc = fill_imprev(h, nullptr);
+  if (rc) { gemb200_destroy(h); return rc; }
   rc = do_reset(h, nullptr, nullptr, nullptr, nullptr);
   if (rc) { gemb200_destroy(h); return rc; }
   cudaError_t e = cudaStreamSynchronize(nullptr);
@@ -768,7 +796,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv); cudaFree(h->d_imprev);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -943,6 +971,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_supph) s[k++] = {h->d_supph, n * sizeof(double)};
   if (h->d_swst) s[k++] = {h->d_swst, n * 2 * h->cfg.n_ref * sizeof(uint32_t)};
   if (h->d_kenv) s[k++] = {h->d_kenv, n * sizeof(uint32_t)};
+  if (h->d_imprev) s[k++] = {h->d_imprev, n * 2 * h->rsz};
   return k;
 }
 struct CheckpointHeader {
@@ -1032,6 +1061,8 @@ int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream) {
   for (int i = 0; i < k; ++i) {
     CUDA_TRY(cudaMemsetAsync(s[i].ptr, 0, s[i].bytes, st));
   }
+  int rc = fill_imprev(h, st);
+  if (rc) return rc;
   return do_reset(h, nullptr, nullptr, nullptr, st);
 }
 

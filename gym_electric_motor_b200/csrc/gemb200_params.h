@@ -134,6 +134,12 @@ struct StepParams {
   int32_t init_random;        // 1: uniform initial state per reset (init_lo + init_span * U); the angle entry [NX] is in the stored unit
   real init_lo[kMaxX + 1], init_span[kMaxX + 1];
   // truncated-normal initial states: x = mu + sigma * Phi^-1(ca + U * cspan), ca = Phi((lo - mu) / sigma); init_gauss = any such state
+  // induction motors: flux bounds re-derived per env and reset (gemb200.h: init_im); im_prev = [2][n] initial currents of the env's previous
+  // episode (what the reference keeps in _initial_states between initialize() calls); init_mid[j]: truncated normal around the interval's middle
+  int32_t init_im_valid;
+  real init_im[8];
+  real* im_prev;
+  int32_t init_mid[kMaxX + 1];
   int32_t init_gauss, init_dist[kMaxX + 1];
   real init_mu[kMaxX + 1], init_sigma[kMaxX + 1], init_ca[kMaxX + 1], init_cspan[kMaxX + 1];
   // ---- constraint monitor: merge = max, so all LimitConstraints collapse into ONE list of observed states; every

@@ -484,15 +484,57 @@ class InductionMotor(ThreePhaseMotor):
         mp = self._motor_parameter
         return 1.5 * mp["p"] * mp["l_m"] ** 2 / (mp["l_m"] + mp["l_sigr"]) * self._limits["i_sd"] * self._limits["i_sq"] / 2
 
+    # ----- initial states (induction_motor.py:178-185, :250-285; squirrel_cage_induction_motor.py:146-157; doubly_fed_induction_motor.py:154-165)
+    def flux_limit_constants(self):
+        """The constants of InductionMotor._flux_limit, for the device (gemb200.h: init_im): psi_d_max at omega = 0, the three numerator
+        terms and the denominator factor of the omega != 0 branch, l_m."""
+        mp = self._motor_parameter
+        l_s, l_r = mp["l_m"] + mp["l_sigs"], mp["l_m"] + mp["l_sigr"]
+        l_mr = mp["l_m"] / l_r
+        sigma = (l_s * l_r - mp["l_m"] ** 2) / (l_s * l_r)
+        u_q = float(self._nominal_values["u_sq"]) + l_mr * float(self._nominal_values.get("u_rq", 0.0) if self.KIND == K.MOTOR_DFIM else 0.0)
+        return [mp["l_m"] * float(self._nominal_values["i_sd"]), mp["p"] * sigma * l_s, mp["r_s"] + mp["r_r"] * l_mr**2, u_q, mp["p"] * l_mr, mp["l_m"], 0.0, 0.0]
+
+    def initial_bounds(self, state_low, state_positions):
+        """ElectricMotor.initialize, induction branch (electric_motor.py:197-213): upper = |initial limit| of the state, lower = -upper.
+        The two flux limits are re-derived per reset on the device (flux_limit_constants); here they only carry the user's `interval`."""
+        keys = list(self._initial_states)
+        big = 1e30
+        upper = np.array([big if k in self.FLUXES else abs(float(self._nominal_values[k])) for k in keys])
+        lower = -upper
+        interval = self._initializer.get("interval")
+        if interval is not None:
+            iv = np.asarray(interval, dtype=float)
+            lower = np.clip(lower, a_min=iv.T[0], a_max=None)
+            upper = np.clip(upper, a_min=None, a_max=iv.T[1])
+        return lower, upper
+
+    def gaussian_params(self, lower, upper):
+        """mue = random_params[0] or the middle of the interval — for the flux states the interval is per env and per reset, so a missing
+        mue is passed on as NaN and resolved on the device (gemb200.h: init_mu)"""
+        rp = self._initializer.get("random_params") or (None, None)
+        lower = np.asarray(lower, dtype=float)
+        mue = np.full(lower.shape, float(rp[0]) if rp[0] else np.nan)
+        sigma = np.full(lower.shape, float(rp[1] or 1))
+        return mue, sigma
+
     def check_initial_state(self, nominal_state, state_low, state_positions):
+        """Constant initial states are checked against +-|initial limit| (electric_motor.py:255-266).  The reference's flux limits depend on
+        a draw from the global numpy RNG, so a constant non-zero flux passes or raises at random there; here it is accepted up to the
+        omega = 0 limit l_m * i_sd_nominal and refused beyond it."""
         if self.random_init:
-            raise NotImplementedError("random initial states of induction motors use flux limits drawn from the unseeded global numpy "
-                                      "RNG in the reference (squirrel_cage_induction_motor.py:146-157); not supported")
-        # induction motors check against their own initial limits (electric_motor.py:197-213); zero always passes
+            return
+        psi_max = self.flux_limit_constants()[0]
         for name, val in self._initial_states.items():
-            if name in ("psi_ralpha", "psi_rbeta") and val != 0.0:
-                raise NotImplementedError("non-zero initial rotor flux needs the reference's randomised flux limits "
-                                          "(squirrel_cage_induction_motor.py:146-157); not supported")
+            lim = psi_max if name in self.FLUXES else abs(float(self._nominal_values[name]))
+            if not (-lim <= val <= lim):
+                raise Exception("Initialization value has to be within nominal boundaries")
+
+    def fill_init_config(self, cfg):
+        if self.random_init:
+            cfg.init_im_valid = 1
+            for j, v in enumerate(self.flux_limit_constants()):
+                cfg.init_im[j] = float(v)
 
 
 class SquirrelCageInductionMotor(InductionMotor):

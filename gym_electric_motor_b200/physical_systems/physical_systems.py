@@ -307,6 +307,8 @@ class SCMLSystem(PhysicalSystem):
                     if hi[1 + j] > lo[1 + j]:
                         cfg.init_dist[1 + j] = 1
                         cfg.init_mu[1 + j], cfg.init_sigma[1 + j] = float(mu[j]), float(sg[j])
+            if m.random_init and hasattr(m, "fill_init_config"):
+                m.fill_init_config(cfg)  # induction motors: constants of the per-reset flux limits
         cfg.action_dq = int(self._action_dq)
         cfg.angle_advance = float(self._angle_advance)
         cfg.dead_time_steps = int(self._dead_steps)

@@ -240,6 +240,18 @@ typedef struct gemb200_config {
   int32_t ext_speed_len;
   int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */
   double supply_param[4];
+  /* Induction motors (SCIM / DFIM) with init_random: the bounds of the two rotor-flux states are re-derived per env at EVERY reset from a
+   * random magnetic-field angle eps_mag ~ U(-pi, pi), the speed and the initial currents of the env's previous episode
+   * (squirrel_cage_induction_motor.py:146-157, doubly_fed_induction_motor.py:154-165, induction_motor.py:250-285):
+   *   omega == 0: psi_d_max = init_im[0]                                   (l_m * nominal i_sd)
+   *   else      : (i_d, i_q) = q_inv(previous initial (i_salpha, i_sbeta), eps_mag),
+   *               psi_d_max = 0.9 * clip((init_im[1]*omega*i_d + init_im[2]*i_q + init_im[3]) / (-init_im[4]*omega), 0, |init_im[5]*i_d|)
+   *   bounds    : +-|psi_d_max * (cos, sin)(eps_mag)|, clipped to init_lo / init_hi of the flux states (the user's `interval`, else +-1e30)
+   * init_im = {l_m*i_sd_nominal, p*sigma*l_s, r_s + r_r*(l_m/l_r)^2, u_sq_nominal (+ l_m/l_r * u_rq_nominal, DFIM), p*l_m/l_r, l_m, 0, 0}.
+   * The reference draws eps_mag from the UNSEEDED global numpy RNG; here it comes from the env's Philox stream like every other draw.
+   * A truncated-normal state (init_dist) whose init_mu is NaN takes the middle of its (per-env) interval as mue (electric_motor.py:247). */
+  int32_t init_im_valid;
+  double init_im[8];
   /* action_dq = 3: DFIM, 4 actions (stator dq, rotor dq): stator with eps + angle_advance*tau*omega*p, rotor with the FluxObserver's
    * psi_angle minus that angle (dq_to_abc_action_processor.py:108-137); requires a GEMB200_SOP_FLUX_OBSERVER op */
   /* action_dq = 2: SCIM with a FluxObserver — the transformation angle is the observer's psi_angle (+ angle_advance*tau*omega*p),

@@ -58,6 +58,7 @@ typedef struct {
   int sw_cur[GEMB200_MAX_REF], sw_k[GEMB200_MAX_REF], sw_len[GEMB200_MAX_REF]; /* SwitchedReferenceGenerator: current entry, _k, _current_episode_length */
   double ac_phase; /* AC1PhaseSupply._phi */
   double u_rc; int rc_started; /* RCVoltageSupply: solver state and 'a previous get_voltage call exists' (voltage_supplies.py:110-123) */
+  double im_prev[2]; int im_prev_set; /* induction motors: _initial_states i_salpha / i_sbeta left by the previous initialize() call */
 } env_t;
 
 typedef struct gem_oracle {
@@ -108,7 +109,7 @@ static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0);
 enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
        STREAM_SWITCH = 10, STREAM_SWITCH_R = 14 /* + slot: SwitchedReferenceGenerator super-episodes (R: at a reset) */,
-       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */, STREAM_LAPLACE = 24, STREAM_LAPLACE_R = 28 /* Laplace walk increments */,
+       STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */, /* induction motors: eps_mag = word 2 of STREAM_INIT_STATE2 */ STREAM_LAPLACE = 24, STREAM_LAPLACE_R = 28 /* Laplace walk increments */,
        STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */,
        STREAM_NOISE = 64 /* + 8*op + (state >> 2): StateNoiseProcessor */, STREAM_NOISE_R = 128 /* ... right after an auto-reset */ };
 
@@ -836,16 +837,35 @@ static void ps_reset(const gem_oracle* o, env_t* e, double* state) {
     int64_t idx = e - o->env;
     rng4(o, idx, STREAM_INIT_STATE, r0);
     rng4(o, idx, STREAM_INIT_STATE2, r1);
+    double lo[GEMB200_MAX_ODE], hi[GEMB200_MAX_ODE];
+    for (int j = 0; j < o->n_ode; ++j) { lo[j] = c->init_lo[j]; hi[j] = c->init_hi[j]; }
     for (int j = 0; j < o->n_ode; ++j) {
+      if (c->init_im_valid && j == 3) {
+        /* InductionMotor.reset -> _update_initial_limits(omega) (squirrel_cage_induction_motor.py:146-157, doubly_fed_induction_motor.py:154-165)
+         * -> _flux_limit (induction_motor.py:250-285); initialize() then takes +-|limit| (electric_motor.py:197-213).  omega = y[0] is
+         * this reset's speed, the currents are the ones the PREVIOUS initialize() call left in _initial_states. */
+        if (!e->im_prev_set) { e->im_prev[0] = c->init_ode[1]; e->im_prev[1] = c->init_ode[2]; e->im_prev_set = 1; }
+        const double eps_mag = 2 * M_PI * u01(r1[2]) - M_PI, ce = cos(eps_mag), se = sin(eps_mag), omega = y[0];
+        double psi_d_max;
+        if (omega == 0) psi_d_max = c->init_im[0];
+        else {
+          const double i_d = ce * e->im_prev[0] + se * e->im_prev[1], i_q = -se * e->im_prev[0] + ce * e->im_prev[1]; /* q_inv */
+          double psi = (c->init_im[1] * omega * i_d + c->init_im[2] * i_q + c->init_im[3]) / (-c->init_im[4] * omega);
+          psi_d_max = 0.9 * fmin(fmax(psi, 0.0), fabs(c->init_im[5] * i_d));
+        }
+        const double lim[2] = {fabs(psi_d_max * ce), fabs(psi_d_max * se)};
+        for (int q = 0; q < 2; ++q) { lo[3 + q] = fmax(-lim[q], c->init_lo[3 + q]); hi[3 + q] = fmin(lim[q], c->init_hi[3 + q]); }
+      }
       const double u = u01(j < 4 ? r0[j] : r1[j - 4]);
-      y[j] = c->init_lo[j] + (c->init_hi[j] - c->init_lo[j]) * u;
+      y[j] = lo[j] + (hi[j] - lo[j]) * u;
       if (c->init_dist[j]) { /* random_init='gaussian': scipy.stats.truncnorm(a, b, loc=mue, scale=sigma) electric_motor.py:245-258, by inversion */
-        const double mu = c->init_mu[j], sg = c->init_sigma[j];
-        const double ca = norm_cdf((c->init_lo[j] - mu) / sg), cb = norm_cdf((c->init_hi[j] - mu) / sg);
+        const double mu = isnan(c->init_mu[j]) ? 0.5 * (hi[j] - lo[j]) + lo[j] : c->init_mu[j], sg = c->init_sigma[j];
+        const double ca = norm_cdf((lo[j] - mu) / sg), cb = norm_cdf((hi[j] - mu) / sg);
         const double g = mu + sg * norm_ppf(ca + u * (cb - ca));
-        y[j] = fmin(fmax(g, c->init_lo[j]), c->init_hi[j]);
+        y[j] = hi[j] > lo[j] ? fmin(fmax(g, lo[j]), hi[j]) : lo[j];
       }
     }
+    if (c->init_im_valid) { e->im_prev[0] = y[1]; e->im_prev[1] = y[2]; }
   }
   double u_abc[6] = {0, 0, 0, 0, 0, 0};
   conv_reset(o, e, u_abc);

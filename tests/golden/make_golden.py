@@ -503,6 +503,31 @@ def init_bounds():
         json.dump(out, f, indent=1)
 
 
+def init_bounds_induction():
+    """Induction motors with random_init='uniform': the flux bounds are re-derived at every reset from a random field angle drawn from the GLOBAL
+    numpy RNG, the speed and the previous reset's initial currents (squirrel_cage_induction_motor.py:146-157, induction_motor.py:250-285), so
+    the device can only match the DISTRIBUTION: per ODE state min / max / mean / std over 20 000 resets (the first reset, which still sees
+    the default currents, left out), plus mean and max of the flux magnitude and the share of exactly-zero flux."""
+    out = {}
+    np.random.seed(12345)
+    for key, env_id, load_iv in [("sc_scim", "Cont-SC-SCIM-v0", None), ("cc_scim", "Cont-CC-SCIM-v0", None), ("sc_dfim", "Cont-SC-DFIM-v0", None),
+                                 ("cc_dfim", "Cont-CC-DFIM-v0", None), ("sc_scim_randload", "Cont-SC-SCIM-v0", [[-50.0, 120.0]])]:
+        load = dict(load_initializer=dict(random_init="uniform", interval=load_iv)) if load_iv else None
+        env = gem.make(env_id, visualization=NoViz(), ode_solver=make_solver("euler"), motor=dict(motor_initializer=dict(random_init="uniform")), load=load)
+        env.reset(seed=0)
+        ys = []
+        for _ in range(20000):
+            env.reset()
+            ys.append(ode_state(env))
+        ys = np.array(ys)
+        mag = np.hypot(ys[:, 3], ys[:, 4])
+        out[key] = dict(env_id=env_id, load_interval=load_iv, min=ys.min(axis=0).tolist(), max=ys.max(axis=0).tolist(), mean=ys.mean(axis=0).tolist(),
+                        std=ys.std(axis=0).tolist(), flux_mag_mean=float(mag.mean()), flux_mag_max=float(mag.max()), flux_zero_share=float((mag == 0).mean()))
+        print(key, "ode min", np.round(ys.min(axis=0), 3), "max", np.round(ys.max(axis=0), 3), "flux |.| mean", round(float(mag.mean()), 4), "zero share", float((mag == 0).mean()))
+    with open(os.path.join(HERE, "init_bounds_induction.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def switched_stats():
     """SwitchedReferenceGenerator semantics as statistics (its numpy streams cannot be matched on a device): three constant
     sub-generators with probabilities (.5, .3, .2), super-episodes of integers(5, 12) steps, 200 000 steps of the reference; recorded:
@@ -590,9 +615,11 @@ if __name__ == "__main__":
     ap.add_argument("--skip-table", action="store_true")
     args = ap.parse_args()
     for case in CASES:
-        if args.only in ("ref_data", "init_bounds", "switched_stats", "env_table") or (args.only and args.only not in case["name"]):
+        if args.only in ("ref_data", "init_bounds", "init_bounds_induction", "switched_stats", "env_table") or (args.only and args.only not in case["name"]):
             continue
         record(case)
+    if not args.only or args.only == "init_bounds_induction":
+        init_bounds_induction()
     if not args.only or args.only == "init_bounds":
         init_bounds()
     if not args.only or args.only == "switched_stats":

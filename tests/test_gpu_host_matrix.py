@@ -10,7 +10,7 @@ import pytest
 
 from gym_electric_motor_b200 import _cabi as K
 
-pytestmark = pytest.mark.gpu_next
+pytestmark = pytest.mark.gpu
 
 
 def _cases():
@@ -21,6 +21,12 @@ def _cases():
     import kwargs_matrix_harness as h
 
     return h.CASES, h.PRELUDE
+
+
+def sim_n_ode(cfg):
+    d = [K.C.c_int32() for _ in range(4)]
+    K.check(K.load_library().gemb200_query_dims(K.C.byref(cfg), *[K.C.byref(x) for x in d]), "query_dims")
+    return d[1].value
 
 
 CASES, PRELUDE = _cases()
@@ -42,6 +48,11 @@ def test_device_matches_oracle_for_host_built_config(oracle_lib, case):
     cfg = env.build_config()
     n = 6
     cfg.n_envs, cfg.dtype, cfg.seed, cfg.autoreset = n, K.F64, 5, K.AUTORESET_SAME_STEP
+    if cfg.finite and cfg.interlocking_time > 0 and not cfg.init_random:
+        # a leg in its interlock (freewheeling) state outputs by the SIGN of its current; from the exactly-zero initial state that sign is
+        # round-off noise — in the reference as well (tests/test_gpu_parity.py: BATCH_CASES note) — so start from non-zero currents
+        for j, v in enumerate([0.9, -0.6, 0.02, 0.03][: max(0, sim_n_ode(cfg) - 2)]):
+            cfg.init_ode[1 + j] = v
     ora, sim = oracle_lib.Oracle(cfg), VectorSim(cfg)
     o_obs, o_ref = ora.reset()
     d_obs, d_ref = sim.reset()

@@ -224,8 +224,10 @@ def test_random_initialiser_bounds_match_reference():
         assert np.all(mn >= lo - 1e-9) and np.all(mx <= hi + 1e-9), (env_id, lo, hi, mn, mx)
         assert np.all(mn - lo < 0.01 * span) and np.all(hi - mx < 0.01 * span), (env_id, lo, hi, mn, mx)
         assert np.all(np.abs(mean - 0.5 * (lo + hi)) < 0.03 * span)
-    with pytest.raises(NotImplementedError):
-        gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(random_init="uniform")))
+    # induction motors: constant bounds for currents / angle, the flux bounds are re-derived per reset on the device (gemb200.h: init_im)
+    cfg = gem.make("Cont-CC-SCIM-v0", motor=dict(motor_initializer=dict(random_init="uniform"))).build_config()
+    assert cfg.init_random == 1 and cfg.init_im_valid == 1
+    assert list(cfg.init_lo)[:6] == [100.0, -3.9, -3.9, -1e30, -1e30, -np.pi] and list(cfg.init_hi)[:6] == [100.0, 3.9, 3.9, 1e30, 1e30, np.pi]
 
 
 def test_gaussian_initialiser_config():

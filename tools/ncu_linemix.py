@@ -14,8 +14,13 @@ warps = int(sys.argv[4]) if len(sys.argv) > 4 else 32768
 nl = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], stdout=subprocess.PIPE, text=True).stdout
+dis = ""
+for f in sorted(os.listdir(tmp)):  # one cubin per translation unit: take the one that holds the kernel
+    if f.endswith(".cubin"):
+        d = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, f)], stdout=subprocess.PIPE, text=True).stdout
+        if "\t.section\t.text." + kname + "," in d:
+            dis = d
+            break
 lines_by_off = {}
 cur, on = None, False
 for ln in dis.splitlines():
@@ -31,7 +36,7 @@ for ln in dis.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
         lines_by_off[int(m.group(1), 16)] = (cur, m.group(2).strip())
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", "::regex:step_kernel:1"], stdout=subprocess.PIPE, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", "::regex:" + (sys.argv[6] if len(sys.argv) > 6 else "step_kernel") + ":1"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 hdr = rows[hi]
