@@ -9,6 +9,7 @@ import os
 
 ABI_VERSION = 9
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
+MAX_REF_ENTRIES = 12  # generator parameter entries: output slots + switched sub-generators
 
 # enums (include/gemb200.h)
 MOTOR_PERMEX_DC, MOTOR_SERIES_DC, MOTOR_SHUNT_DC, MOTOR_EXTEX_DC, MOTOR_PMSM, MOTOR_SYNRM, MOTOR_EESM, MOTOR_SCIM, MOTOR_DFIM = range(9)
@@ -64,17 +65,17 @@ class GemB200Config(C.Structure):
         ("reward_bias", C.c_double),
         ("violation_reward", C.c_double),
         ("n_ref", C.c_int32),
-        ("ref_kind", C.c_int32 * MAX_REF),
-        ("ref_state", C.c_int32 * MAX_REF),
-        ("ref_value", C.c_double * MAX_REF),
-        ("ref_margin_lo", C.c_double * MAX_REF),
-        ("ref_margin_hi", C.c_double * MAX_REF),
-        ("ref_init_lo", C.c_double * MAX_REF),
-        ("ref_init_hi", C.c_double * MAX_REF),
-        ("ref_sigma_lo", C.c_double * MAX_REF),
-        ("ref_sigma_hi", C.c_double * MAX_REF),
-        ("ref_len_lo", C.c_int32 * MAX_REF),
-        ("ref_len_hi", C.c_int32 * MAX_REF),
+        ("ref_kind", C.c_int32 * MAX_REF_ENTRIES),
+        ("ref_state", C.c_int32 * MAX_REF_ENTRIES),
+        ("ref_value", C.c_double * MAX_REF_ENTRIES),
+        ("ref_margin_lo", C.c_double * MAX_REF_ENTRIES),
+        ("ref_margin_hi", C.c_double * MAX_REF_ENTRIES),
+        ("ref_init_lo", C.c_double * MAX_REF_ENTRIES),
+        ("ref_init_hi", C.c_double * MAX_REF_ENTRIES),
+        ("ref_sigma_lo", C.c_double * MAX_REF_ENTRIES),
+        ("ref_sigma_hi", C.c_double * MAX_REF_ENTRIES),
+        ("ref_len_lo", C.c_int32 * MAX_REF_ENTRIES),
+        ("ref_len_hi", C.c_int32 * MAX_REF_ENTRIES),
         ("seed", C.c_uint64),
         ("env_index_offset", C.c_int64),
         ("action_dq", C.c_int32),
@@ -84,12 +85,12 @@ class GemB200Config(C.Structure):
         ("angle_advance", C.c_double),
         ("init_lo", C.c_double * MAX_ODE),
         ("init_hi", C.c_double * MAX_ODE),
-        ("ref_amp_lo", C.c_double * MAX_REF),
-        ("ref_amp_hi", C.c_double * MAX_REF),
-        ("ref_freq_lo", C.c_double * MAX_REF),
-        ("ref_freq_hi", C.c_double * MAX_REF),
-        ("ref_off_lo", C.c_double * MAX_REF),
-        ("ref_off_hi", C.c_double * MAX_REF),
+        ("ref_amp_lo", C.c_double * MAX_REF_ENTRIES),
+        ("ref_amp_hi", C.c_double * MAX_REF_ENTRIES),
+        ("ref_freq_lo", C.c_double * MAX_REF_ENTRIES),
+        ("ref_freq_hi", C.c_double * MAX_REF_ENTRIES),
+        ("ref_off_lo", C.c_double * MAX_REF_ENTRIES),
+        ("ref_off_hi", C.c_double * MAX_REF_ENTRIES),
         ("n_state_ops", C.c_int32),
         ("sop_kind", C.c_int32 * MAX_STATE_OPS),
         ("sop_idx", (C.c_int32 * 4) * MAX_STATE_OPS),
@@ -102,7 +103,7 @@ class GemB200Config(C.Structure):
         ("ref_sw_first", C.c_int32 * MAX_REF),
         ("ref_sw_len_lo", C.c_int32 * MAX_REF),
         ("ref_sw_len_hi", C.c_int32 * MAX_REF),
-        ("ref_sw_cdf", C.c_double * MAX_REF),
+        ("ref_sw_cdf", C.c_double * MAX_REF_ENTRIES),
         ("ext_speed_table", C.c_void_p),
         ("ext_speed_len", C.c_int32),
         ("supply_kind", C.c_int32),
@@ -126,7 +127,7 @@ def new_config():
         cfg.limits[i] = 1.0
         cfg.state_length[i] = 2.0
         cfg.reward_power[i] = 1.0
-    for r in range(MAX_REF):
+    for r in range(MAX_REF_ENTRIES):
         cfg.ref_len_lo[r], cfg.ref_len_hi[r] = 500, 2000
         cfg.ref_sigma_lo[r], cfg.ref_sigma_hi[r] = 1e-3, 1e-1
         cfg.ref_margin_lo[r], cfg.ref_margin_hi[r] = -1.0, 1.0

@@ -181,7 +181,7 @@ static int validate(const gemb200_config* c) {
   for (int r = 0; r < c->n_ref; ++r) {
     if (c->ref_sw_count[r] <= 1) continue;
     const int first = c->ref_sw_first[r], cnt = c->ref_sw_count[r];
-    if (first < 0 || first + cnt > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "switched reference generator: parameter entries out of range");
+    if (first < 0 || first + cnt > GEMB200_MAX_REF_ENTRIES) return fail(GEMB200_E_INVALID, "switched reference generator: parameter entries out of range");
     if (first + cnt > n_entries) n_entries = first + cnt;
     if (c->ref_sw_len_lo[r] < 1 || c->ref_sw_len_hi[r] <= c->ref_sw_len_lo[r]) return fail(GEMB200_E_INVALID, "switched reference generator: bad super-episode length range");
     for (int m = 0; m < cnt; ++m) {
@@ -528,10 +528,10 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     p->sw_first[r] = c.ref_sw_first[r];
     p->sw_len_lo[r] = c.ref_sw_len_lo[r]; p->sw_len_span[r] = c.ref_sw_len_hi[r] - c.ref_sw_len_lo[r];
   }
-  for (int r = 0; r < GEMB200_MAX_REF; ++r) p->sw_cdf[r] = (real)c.ref_sw_cdf[r];
+  for (int r = 0; r < GEMB200_MAX_REF_ENTRIES; ++r) p->sw_cdf[r] = (real)c.ref_sw_cdf[r];
   p->any_wiener = h->any_wiener;
   p->ref_tau = (real)c.tau;
-  for (int r = 0; r < GEMB200_MAX_REF; ++r) {  // all parameter entries (switched sub-generators live beyond n_ref)
+  for (int r = 0; r < GEMB200_MAX_REF_ENTRIES; ++r) {  // all parameter entries (switched sub-generators live beyond n_ref)
     p->ref_kind[r] = c.ref_kind[r]; p->ref_state[r] = c.ref_state[r];
     p->ref_const[r] = (real)c.ref_value[r];
     p->ref_lo[r] = (real)c.ref_margin_lo[r]; p->ref_hi[r] = (real)c.ref_margin_hi[r];
@@ -683,7 +683,7 @@ int gemb200_config_init(gemb200_config* cfg) {
   cfg->tau = 1e-4;
   cfg->load_param[GEMB200_LP_TAU_DECAY] = 1e-3;
   for (int i = 0; i < GEMB200_MAX_STATE; ++i) { cfg->limits[i] = 1.0; cfg->state_length[i] = 2.0; cfg->reward_power[i] = 1.0; }
-  for (int r = 0; r < GEMB200_MAX_REF; ++r) {
+  for (int r = 0; r < GEMB200_MAX_REF_ENTRIES; ++r) {
     cfg->ref_len_lo[r] = 500; cfg->ref_len_hi[r] = 2000;
     cfg->ref_sigma_lo[r] = 1e-3; cfg->ref_sigma_hi[r] = 1e-1;
     cfg->ref_margin_lo[r] = -1; cfg->ref_margin_hi[r] = 1; cfg->ref_init_lo[r] = -1; cfg->ref_init_hi[r] = 1;
@@ -723,7 +723,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   h->n_ref = cfg->n_ref;
   h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
   h->two_segment = cfg->finite && cfg->interlocking_time > 0;
-  for (int r = 0; r < GEMB200_MAX_REF; ++r) {  // any generator that advances by itself (Wiener, Laplace, periodic), incl. switched subs
+  for (int r = 0; r < GEMB200_MAX_REF_ENTRIES; ++r) {  // any generator that advances by itself (Wiener, Laplace, periodic), incl. switched subs
     bool used = r < cfg->n_ref;
     for (int q = 0; q < cfg->n_ref; ++q) used = used || (cfg->ref_sw_count[q] > 1 && r >= cfg->ref_sw_first[q] && r < cfg->ref_sw_first[q] + cfg->ref_sw_count[q]);
     if (used) h->any_wiener = h->any_wiener || cfg->ref_kind[r] == GEMB200_REF_WIENER || cfg->ref_kind[r] >= GEMB200_REF_LAPLACE;

@@ -10,7 +10,8 @@
 namespace gemb200 {
 
 constexpr int kMaxState = 28;
-constexpr int kMaxRef = 4;
+constexpr int kMaxRef = 4;          // referenced states = output slots
+constexpr int kMaxRefEntries = 12;  // generator parameter entries (slots + switched sub-generators)
 constexpr int kMaxConstraints = 4;
 constexpr int kMaxStateOps = 4;
 constexpr int kMaxX = 6;  // real-typed ODE states per env (omega + motor states without the angle): SCIM 5
@@ -163,19 +164,19 @@ struct StepParams {
   // ---- reference generators ----
   int32_t n_ref;
   int32_t any_wiener;
-  int32_t ref_kind[kMaxRef];
-  int32_t ref_state[kMaxRef];
-  real ref_const[kMaxRef];
-  real ref_lo[kMaxRef], ref_hi[kMaxRef];
-  real ref_init_lo[kMaxRef], ref_init_span[kMaxRef];
-  real ref_lsig_lo[kMaxRef], ref_lsig_span[kMaxRef];  // log10 sigma range
-  int32_t ref_len_lo[kMaxRef], ref_len_span[kMaxRef];
+  int32_t ref_kind[kMaxRefEntries];
+  int32_t ref_state[kMaxRefEntries];
+  real ref_const[kMaxRefEntries];
+  real ref_lo[kMaxRefEntries], ref_hi[kMaxRefEntries];
+  real ref_init_lo[kMaxRefEntries], ref_init_span[kMaxRefEntries];
+  real ref_lsig_lo[kMaxRefEntries], ref_lsig_span[kMaxRefEntries];  // log10 sigma range
+  int32_t ref_len_lo[kMaxRefEntries], ref_len_span[kMaxRefEntries];
   // periodic generators (sinus / step / sawtooth / triangular): parameter ranges per slot, tau for the phase increment
-  real ref_amp_lo[kMaxRef], ref_amp_span[kMaxRef], ref_freq_lo[kMaxRef], ref_freq_span[kMaxRef], ref_off_lo[kMaxRef], ref_off_hi[kMaxRef];
+  real ref_amp_lo[kMaxRefEntries], ref_amp_span[kMaxRefEntries], ref_freq_lo[kMaxRefEntries], ref_freq_span[kMaxRefEntries], ref_off_lo[kMaxRefEntries], ref_off_hi[kMaxRefEntries];
   real ref_tau;
   // SwitchedReferenceGenerator: output slot r switches between the parameter entries sw_first[r] .. +sw_count[r]-1 of the arrays above
   int32_t sw_count[kMaxRef], sw_first[kMaxRef], sw_len_lo[kMaxRef], sw_len_span[kMaxRef];
-  real sw_cdf[kMaxRef];
+  real sw_cdf[kMaxRefEntries];
   uint32_t* swst;          // [n_ref][2][n]: current parameter entry, step at which the super-episode ends; nullptr unless switched
   // ---- state-vector wrappers (gemb200.h: gemb200_state_op), applied in order after the system's own vector is assembled ----
   int32_t n_sops;

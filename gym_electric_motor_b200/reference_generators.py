@@ -64,8 +64,8 @@ class ReferenceGenerator:
             if not sw or len(sw["subs"]) < 2:
                 continue
             m = len(sw["subs"])
-            if nxt + m > K.MAX_REF:
-                raise NotImplementedError(f"referenced states + switched sub-generators exceed the {K.MAX_REF} generator entries of the kernel")
+            if nxt + m > K.MAX_REF_ENTRIES:
+                raise NotImplementedError(f"referenced states + switched sub-generators exceed the {K.MAX_REF_ENTRIES} generator entries of the kernel")
             cfg.ref_sw_count[r], cfg.ref_sw_first[r] = m, nxt
             cfg.ref_sw_len_lo[r], cfg.ref_sw_len_hi[r] = sw["length"]
             acc = 0.0

@@ -29,7 +29,8 @@ extern "C" {
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
 #define GEMB200_MAX_ODE 8      /* SCIM: omega + 4 + eps = 6 */
 #define GEMB200_MAX_ACT 6      /* DFIM: two B6 bridges; EESM: 3 (B6) + 1 (4QC) */
-#define GEMB200_MAX_REF 4
+#define GEMB200_MAX_REF 4          /* referenced states = output slots of the reference generator */
+#define GEMB200_MAX_REF_ENTRIES 12 /* generator parameter entries: the slots + the extra sub-generators of SwitchedReferenceGenerators */
 #define GEMB200_MAX_DEAD_TIME 8
 #define GEMB200_MAX_CONSTRAINTS 4
 #define GEMB200_MAX_MOTOR_PARAM 16
@@ -187,13 +188,13 @@ typedef struct gemb200_config {
 
   /* reference generators: one slot per referenced state (MultipleReferenceGenerator = several slots) */
   int32_t n_ref;
-  int32_t ref_kind[GEMB200_MAX_REF];
-  int32_t ref_state[GEMB200_MAX_REF];       /* index into the state vector */
-  double ref_value[GEMB200_MAX_REF];        /* CONST: the value; others: value after reset when no random init */
-  double ref_margin_lo[GEMB200_MAX_REF], ref_margin_hi[GEMB200_MAX_REF];   /* clip range of the walk */
-  double ref_init_lo[GEMB200_MAX_REF], ref_init_hi[GEMB200_MAX_REF];       /* U() range of the value at reset */
-  double ref_sigma_lo[GEMB200_MAX_REF], ref_sigma_hi[GEMB200_MAX_REF];     /* log-uniform sigma range */
-  int32_t ref_len_lo[GEMB200_MAX_REF], ref_len_hi[GEMB200_MAX_REF];        /* sub-episode length U(lo,hi) */
+  int32_t ref_kind[GEMB200_MAX_REF_ENTRIES];
+  int32_t ref_state[GEMB200_MAX_REF_ENTRIES];       /* index into the state vector */
+  double ref_value[GEMB200_MAX_REF_ENTRIES];        /* CONST: the value; others: value after reset when no random init */
+  double ref_margin_lo[GEMB200_MAX_REF_ENTRIES], ref_margin_hi[GEMB200_MAX_REF_ENTRIES];   /* clip range of the walk */
+  double ref_init_lo[GEMB200_MAX_REF_ENTRIES], ref_init_hi[GEMB200_MAX_REF_ENTRIES];       /* U() range of the value at reset */
+  double ref_sigma_lo[GEMB200_MAX_REF_ENTRIES], ref_sigma_hi[GEMB200_MAX_REF_ENTRIES];     /* log-uniform sigma range */
+  int32_t ref_len_lo[GEMB200_MAX_REF_ENTRIES], ref_len_hi[GEMB200_MAX_REF_ENTRIES];        /* sub-episode length U(lo,hi) */
 
   uint64_t seed;            /* Philox key; streams are keyed by (seed, global env index) */
   int64_t env_index_offset; /* global index of env 0 of this handle (rank*N_local when sharded) */
@@ -215,9 +216,9 @@ typedef struct gemb200_config {
   /* periodic reference generators (SINUS/STEP/SAWTOOTH/TRIANGULAR): per sub-episode amplitude ~ U(amp), frequency ~ U(freq) [Hz],
    * offset ~ U(clip(off, -margin_hi + A | margin_lo + A (STEP), margin_hi - A)); ranges already clipped to the limit margin
    * as in the generators' set_modules() */
-  double ref_amp_lo[GEMB200_MAX_REF], ref_amp_hi[GEMB200_MAX_REF];
-  double ref_freq_lo[GEMB200_MAX_REF], ref_freq_hi[GEMB200_MAX_REF];
-  double ref_off_lo[GEMB200_MAX_REF], ref_off_hi[GEMB200_MAX_REF];
+  double ref_amp_lo[GEMB200_MAX_REF_ENTRIES], ref_amp_hi[GEMB200_MAX_REF_ENTRIES];
+  double ref_freq_lo[GEMB200_MAX_REF_ENTRIES], ref_freq_hi[GEMB200_MAX_REF_ENTRIES];
+  double ref_off_lo[GEMB200_MAX_REF_ENTRIES], ref_off_hi[GEMB200_MAX_REF_ENTRIES];
 
   /* state-vector wrappers (see gemb200_state_op).  limits[] above stays the INNER system's limits (they normalise the assembled
    * vector); the ops carry their own scaling in sop_param. */
@@ -232,10 +233,10 @@ typedef struct gemb200_config {
   double init_mu[GEMB200_MAX_ODE], init_sigma[GEMB200_MAX_ODE];
   /* SwitchedReferenceGenerator (reference_generators/switched_reference_generator.py): output slot r (r < n_ref) switches between
    * ref_sw_count[r] generators (0 or 1: not switched) whose parameters occupy the entries ref_sw_first[r] .. +count-1 of the per-slot
-   * arrays above; entries >= n_ref are parameter-only entries, so n_ref + extra entries <= GEMB200_MAX_REF.  ref_sw_cdf[entry] is the
+   * arrays above; entries >= n_ref are parameter-only entries, so n_ref + extra entries <= GEMB200_MAX_REF_ENTRIES.  ref_sw_cdf[entry] is the
    * cumulative probability inside its group; the super-episode length is integers(ref_sw_len_lo[r], ref_sw_len_hi[r]). */
   int32_t ref_sw_count[GEMB200_MAX_REF], ref_sw_first[GEMB200_MAX_REF], ref_sw_len_lo[GEMB200_MAX_REF], ref_sw_len_hi[GEMB200_MAX_REF];
-  double ref_sw_cdf[GEMB200_MAX_REF];
+  double ref_sw_cdf[GEMB200_MAX_REF_ENTRIES];
   const double* ext_speed_table; /* HOST pointer, copied at gemb200_create (GEMB200_LOAD_EXT_SPEED only) */
   int32_t ext_speed_len;
   int32_t supply_kind;      /* gemb200_supply_kind; u_sup above is u_nominal (= u_0 of the RC supply) */

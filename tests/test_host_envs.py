@@ -261,8 +261,10 @@ def test_switched_reference_generator_config():
     assert env.reference_names == ["omega"] and env.reference_generator.reference_space.shape == (1,)
     with pytest.raises(AssertionError):
         rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega"), rg.WienerProcessReferenceGenerator(reference_state="torque")])
-    with pytest.raises(NotImplementedError):  # 1 output + 4 sub-generators > 4 entries
-        gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega")] * 4)).build_config()
+    c8 = gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega")] * 8)).build_config()
+    assert (c8.ref_sw_count[0], c8.ref_sw_first[0]) == (8, 1) and list(c8.ref_kind)[1:9] == [K.REF_WIENER] * 8  # 1 output slot + 8 entries <= 12
+    with pytest.raises(NotImplementedError):  # 1 output + 12 sub-generators > GEMB200_MAX_REF_ENTRIES = 12
+        gem.make("Cont-SC-PMSM-v0", reference_generator=rg.SwitchedReferenceGenerator([rg.WienerProcessReferenceGenerator(reference_state="omega")] * 12)).build_config()
 
 
 def test_external_speed_load_table():
