@@ -287,6 +287,35 @@ class ElectricMotorEnvironment(_EnvBase):
             obs = obs.index_select(dim, self._filter_index)
         return (obs, ref), reward, terminated.view(torch.bool)
 
+    _MP_SLOT = dict(p=K.MP_P, r_s=K.MP_R_S, l_d=K.MP_L_D, l_q=K.MP_L_Q, psi_p=K.MP_PSI_P, j_rotor=K.MP_J_ROTOR, r_a=K.MP_R_A, l_a=K.MP_L_A, psi_e=K.MP_PSI_E,
+                    r_e=K.MP_R_E, l_e=K.MP_L_E, l_e_prime=K.MP_L_E_PRIME, l_m=K.MP_L_M, k=K.MP_K, l_sigs=K.MP_L_SIGS, l_sigr=K.MP_L_SIGR, r_r=K.MP_R_E)
+    _LP_SLOT = dict(a=K.LP_A, b=K.LP_B, c=K.LP_C, j_load=K.LP_J_LOAD)
+
+    def set_env_parameters(self, motor_parameter=None, load_parameter=None):
+        """Domain randomisation: give every env of the batch its own physical parameters — the batched counterpart of constructing N
+        reference envs with N `motor_parameter` / `load_parameter` dicts (electric_motor.py:118-131, polynomial_static_load.py:46-64).
+        Both arguments are dicts  name -> array of N values  with the reference's parameter names (`r_s`, `l_d`, `psi_p`, `j_rotor`, ...;
+        `a`, `b`, `c`, `j_load`); parameters that are not named keep the value the env was made with.  Limits, nominal values and the
+        normalisation stay those of the env.  `set_env_parameters()` without arguments returns to the shared parameters."""
+        if self._scalar:
+            raise TypeError("set_env_parameters() needs a batched environment (num_envs=...)")
+        sim = self._ensure_sim()
+        if not motor_parameter and not load_parameter:
+            sim.set_env_params(None, None)
+            return
+        cfg = sim.cfg
+        mp = np.tile(np.array(list(cfg.motor_param), dtype=np.float64), (sim.n, 1))
+        lp = np.tile(np.array(list(cfg.load_param), dtype=np.float64), (sim.n, 1))
+        for name, vals in (motor_parameter or {}).items():
+            if name not in self._MP_SLOT:
+                raise KeyError(f"unknown motor parameter {name!r}")
+            mp[:, self._MP_SLOT[name]] = np.broadcast_to(np.asarray(vals, dtype=np.float64), (sim.n,))
+        for name, vals in (load_parameter or {}).items():
+            if name not in self._LP_SLOT:
+                raise KeyError(f"unknown load parameter {name!r}")
+            lp[:, self._LP_SLOT[name]] = np.broadcast_to(np.asarray(vals, dtype=np.float64), (sim.n,))
+        sim.set_env_params(mp, lp)
+
     def set_reference(self, values):
         """Push reference values [N, n_ref] for ExternalReferenceGenerator slots (used by the next step's reward)."""
         self._ensure_sim().set_reference(values)

@@ -47,6 +47,8 @@ struct gemb200_handle {
   uint32_t* d_kenv = nullptr;  // steps since the reset per env (external speed profile)
   uint32_t* d_swst = nullptr;  // switched reference generators [n_ref][2][n]
   void* d_obsv = nullptr;  // FluxObserver integrator [4][n]: re, im, compensation of re, of im
+  void* d_envp = nullptr;    // per-env model coefficients [kCoefWords][n] (gemb200_set_env_params), nullptr: shared coefficients
+  int plain_shape = 0;       // the configuration has the PLAIN shape (before per-env parameters switch the specialisation off)
   void* d_imprev = nullptr;  // induction motors with random initial states [2][n]: initial currents of the env's previous episode
   int n_obs = 0, row_stride = 0;
   StepParams<float> pf;
@@ -391,10 +393,10 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
       }
     }
   }
-  for (int j = 0; j < 20; ++j) p->c[j] = (real)dv.c[j];
-  for (int j = 0; j < 4; ++j) p->tq[j] = (real)dv.tq[j];
-  p->load_a = (real)c.load_param[GEMB200_LP_A]; p->load_b = (real)c.load_param[GEMB200_LP_B]; p->load_c = (real)c.load_param[GEMB200_LP_C];
-  p->inv_j = (real)dv.inv_j; p->omega_lim = (real)dv.omega_lim; p->omega_lin = (real)dv.omega_lin;
+  for (int j = 0; j < 20; ++j) p->k.c[j] = (real)dv.c[j];
+  for (int j = 0; j < 4; ++j) p->k.tq[j] = (real)dv.tq[j];
+  p->k.load_a = (real)c.load_param[GEMB200_LP_A]; p->k.load_b = (real)c.load_param[GEMB200_LP_B]; p->k.load_c = (real)c.load_param[GEMB200_LP_C];
+  p->k.inv_j = (real)dv.inv_j; p->k.omega_lim = (real)dv.omega_lim; p->k.omega_lin = (real)dv.omega_lin;
   for (int j = 0; j < dm.n_state; ++j) {
     p->inv_lim[j] = c.limits[j] != 0.0 ? (real)(1.0 / c.limits[j]) : real(0);
     p->reset_obs[j] = (real)dv.reset_obs[j];
@@ -483,6 +485,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
     for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r] && c.ref_sw_count[r] <= 1;
     const char* off = std::getenv("GEMB200_NO_PLAIN");
     p->plain = plain && !(off && off[0] == '1');
+    const_cast<gemb200_handle*>(h)->plain_shape = p->plain;
   }
   {  // L2 prefetch distance: one wave of resident threads (SMs x blocks/SM x block size); GEMB200_PF_DIST overrides (0 = off)
     int sms = 148;
@@ -796,7 +799,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv); cudaFree(h->d_imprev);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv); cudaFree(h->d_imprev); cudaFree(h->d_envp);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -830,6 +833,49 @@ int gemb200_rollout_record(gemb200_handle* h, const void* actions, int32_t n_ste
 int gemb200_rollout(gemb200_handle* h, const void* actions, int32_t n_steps, void* obs_out, void* ref_out, void* reward_out,
                     uint8_t* terminated_out, void* stream) {
   return gemb200_rollout_record(h, actions, n_steps, 0, obs_out, ref_out, reward_out, terminated_out, stream);
+}
+
+// Domain randomisation (the batched counterpart of constructing N reference envs with N motor_parameter / load_parameter
+// dicts): every env gets its own model coefficients, derived here exactly like the shared ones (the *_update_model methods,
+// mechanical_load.py:188-193) from ITS physical parameters.  Limits, nominal values, reward and reference settings stay those of the
+// handle's configuration.  NULL motor_param: back to the shared coefficients.
+int gemb200_set_env_params(gemb200_handle* h, const double* motor_param, const double* load_param) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (!motor_param && !load_param) {
+    h->pf.envp = nullptr; h->pd.envp = nullptr;
+    h->pf.plain = h->plain_shape; h->pd.plain = h->plain_shape;
+    return GEMB200_OK;
+  }
+  const size_t n = (size_t)h->cfg.n_envs;
+  Dims d;
+  derive_dims(&h->cfg, &d);
+  std::vector<double> tab((size_t)kCoefWords * n);
+  gemb200_config c = h->cfg;
+  for (size_t i = 0; i < n; ++i) {
+    if (motor_param) std::memcpy(c.motor_param, motor_param + i * GEMB200_MAX_MOTOR_PARAM, sizeof(c.motor_param));
+    if (load_param) std::memcpy(c.load_param, load_param + i * 8, sizeof(c.load_param));
+    if (c.load_kind == GEMB200_LOAD_POLY_STATIC && !(c.load_param[GEMB200_LP_J_LOAD] + c.motor_param[GEMB200_MP_J_ROTOR] > 0))
+      return fail(GEMB200_E_INVALID, "per-env parameters: total inertia must be positive for every env");
+    Derived dv;
+    derive_model(&c, d, &dv);
+    for (int w = 0; w < 20; ++w) tab[(size_t)w * n + i] = dv.c[w];
+    for (int w = 0; w < 4; ++w) tab[(size_t)(20 + w) * n + i] = dv.tq[w];
+    tab[(size_t)24 * n + i] = c.load_param[GEMB200_LP_A]; tab[(size_t)25 * n + i] = c.load_param[GEMB200_LP_B]; tab[(size_t)26 * n + i] = c.load_param[GEMB200_LP_C];
+    tab[(size_t)27 * n + i] = dv.inv_j; tab[(size_t)28 * n + i] = dv.omega_lim; tab[(size_t)29 * n + i] = dv.omega_lin;
+  }
+  for (double v : tab) if (!std::isfinite(v)) return fail(GEMB200_E_INVALID, "per-env parameters: a derived model coefficient is not finite (zero inductance?)");
+  if (!h->d_envp) CUDA_TRY(cudaMalloc(&h->d_envp, tab.size() * h->rsz));
+  if (h->cfg.dtype == GEMB200_F32) {
+    std::vector<float> tf(tab.begin(), tab.end());
+    CUDA_TRY(cudaMemcpy(h->d_envp, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    CUDA_TRY(cudaMemcpy(h->d_envp, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  h->pf.envp = static_cast<const float*>(h->d_envp); h->pd.envp = static_cast<const double*>(h->d_envp);
+  h->pf.plain = 0; h->pd.plain = 0;  // the PLAIN instantiations read the shared constant-bank coefficients
+  return GEMB200_OK;
 }
 
 static int ensure_host_buffers(gemb200_handle* h) {
@@ -972,7 +1018,7 @@ static int sections(gemb200_handle* h, Section* s) {
   if (h->d_swst) s[k++] = {h->d_swst, n * 2 * h->cfg.n_ref * sizeof(uint32_t)};
   if (h->d_kenv) s[k++] = {h->d_kenv, n * sizeof(uint32_t)};
   if (h->d_imprev) s[k++] = {h->d_imprev, n * 2 * h->rsz};
-  return k;
+  return k;  // (the per-env parameter table is configuration, not state: re-apply gemb200_set_env_params after a load)
 }
 struct CheckpointHeader {
   char magic[8];          // "GEMB200C"

@@ -73,6 +73,17 @@ constexpr bool streams_disjoint() {
 }
 static_assert(streams_disjoint(), "RNG stream id ranges overlap");
 
+// Model coefficients of ONE env: the motor's sparse constant matrix (layout per family, gemb200.cu: derive_model), torque coefficients,
+// load polynomial and inertia.  Shared by the whole batch in the constant bank (StepParams::k) — or, with per-env parameter blocks
+// (gemb200_set_env_params: domain randomisation), loaded per thread from StepParams::envp.
+constexpr int kCoefWords = 30;
+template <typename real>
+struct Coef {
+  real c[20];  // motor model coefficients
+  real tq[4];  // torque coefficients
+  real load_a, load_b, load_c, inv_j, omega_lim, omega_lin;
+};
+
 template <typename real>
 struct StepParams {
   // ---- batch ----
@@ -126,9 +137,8 @@ struct StepParams {
   real kang[2][3][2];
   real eps_out_scale;     // normalised angle output = (hi + lo) * eps_out_scale  (2*pi/limit in turns, 1/limit in radians)
   real init_ang[2];       // initial angle in the stored representation
-  real c[20];             // motor model coefficients (sparse layout per family, see fill_motor_coeffs)
-  real tq[4];             // torque coefficients
-  real load_a, load_b, load_c, inv_j, omega_lim, omega_lin;
+  Coef<real> k;           // shared model coefficients
+  const real* envp;       // [kCoefWords][n] per-env coefficients (word w of env i at envp[w * n + i]); nullptr: every env uses `k`
   real inv_lim[kMaxState];
   real init_x[kMaxX];
   real reset_obs[kMaxState];  // observation right after a reset (constant initial state)

@@ -110,6 +110,14 @@ class VectorSim:
         K.check(self._lib.gemb200_reseed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), self._stream()), "gemb200_reseed")
         self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
 
+    def set_env_params(self, motor_param=None, load_param=None):
+        """Per-env parameter blocks (gemb200_set_env_params): motor_param [N, 16] / load_param [N, 8] float64 host arrays in the slot order of
+        `_cabi.MP_*` / `_cabi.LP_*`; None keeps the configuration's values; both None: back to the shared coefficients."""
+        mp = None if motor_param is None else np.ascontiguousarray(motor_param, dtype=np.float64).reshape(self.n, K.MAX_MOTOR_PARAM)
+        lp = None if load_param is None else np.ascontiguousarray(load_param, dtype=np.float64).reshape(self.n, 8)
+        vp = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        K.check(self._lib.gemb200_set_env_params(self._h, vp(mp), vp(lp)), "gemb200_set_env_params")
+
     def step(self, action):
         """env.step: returns (obs, ref_next, reward, terminated) device tensors (views of reused buffers unless
         reuse_outputs=False)."""

@@ -322,6 +322,15 @@ int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream)
  * cfg.seed = seed, so equal seeds give identical episodes.  Stream-ordered. */
 int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream);
 
+/* Per-env parameter blocks (domain randomisation; SURVEY.md §8f row 4 — the batched counterpart of constructing N reference envs with N
+ * different motor_parameter / load_parameter dicts): env i takes its motor constants from motor_param[i][GEMB200_MAX_MOTOR_PARAM] and its load
+ * polynomial / inertia from load_param[i][8] (HOST arrays, same slot enums as gemb200_config; either may be NULL = keep the configuration's
+ * values).  The model coefficients are derived per env on the host exactly like the shared ones and live in a [30][N] device table that
+ * every thread reads instead of the constant bank (36 B per PMSM env and launch; a fused rollout reads them once per K steps).  Limits,
+ * nominal values, reward, constraints and references stay those of the configuration.  Both NULL: back to shared coefficients.
+ * Takes effect from the next reset / step; synchronises the device. */
+int gemb200_set_env_params(gemb200_handle* h, const double* motor_param, const double* load_param);
+
 /* Opaque checkpoint of everything a handle owns (ODE state, switching state, reference state, step counter):
  * size query, export to / import from a HOST blob.  The blob starts with a header (magic, ABI version, dtype, n_envs, record layout,
  * fingerprint of the configuration); gemb200_checkpoint_load refuses a blob written by a handle of another configuration

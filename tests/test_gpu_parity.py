@@ -179,6 +179,7 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
     scale = np.maximum(np.abs(o_obs).max(axis=0), 1e-3)
     ang_cols = [j for j, nm in enumerate(g["meta"]["state_names"]) if nm in ("epsilon", "psi_angle")]
     feedback = "flux_dq" in name or "flux_cossin_dead1" in name
+    within_plain = np.ones(n, dtype=bool)  # feedback configurations: envs that never left the PLAIN tolerance
     n_term = 0
     for k in range(steps):
         o_obs, o_ref, o_rew, o_term = ora.step(actions[k])
@@ -192,6 +193,7 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
         if feedback and dtype == K.F32:
             # closed loop through angle(psi_obs): an env whose observer flux passes near zero amplifies rounding-level differences
             # without bound (see TOL_OBSERVER_FEEDBACK); such envs are counted as diverged — at most 1 % may — instead of failing the run
+            within_plain &= ~(alive & ((diff / scale).max(axis=1) >= TOL[dtype]))
             alive &= ~((diff / scale).max(axis=1) >= tol)
         err = (diff[alive] / scale).max()
         assert err < tol, f"step {k}: state error {err:.3e}"
@@ -199,6 +201,10 @@ def test_device_matches_oracle_on_batch(torch_cuda, oracle_lib, name, solver, dt
         assert np.abs(d_rew - o_rew)[alive].max() < 20 * tol
         n_term += int(o_term[alive].sum())
     assert alive.mean() > (0.99 if feedback else 0.995), f"too many diverged envs: {n - alive.sum()}"
+    if feedback and dtype == K.F32:
+        # the loose tolerance is a TAIL allowance (tests/test_oracle_golden.py::test_observer_feedback_configuration_amplifies_rounding: fewer
+        # than 5 % of the envs amplify rounding by > 100x): the bulk of the batch has to hold the plain fp32 bar
+        assert within_plain.mean() > 0.9, f"only {within_plain.mean():.3f} of the envs within {TOL[dtype]:g}"
     if name not in ("series_cc_rk4",) and "_fin" not in name:  # finite envs: tau = 1e-5, 150 steps are too short to trip
         assert n_term > 0, "test is meant to exercise termination + auto-reset"
 
@@ -451,6 +457,44 @@ def test_full_size_replication_property(torch_cuda, oracle_lib):
         assert np.abs(rew[:proto].double().cpu().numpy() - o_rew).max() < 1e-4
 
 
+@pytest.mark.parametrize("name,solver", [("pmsm_fin_sc_rk4", "rk4"), ("scim_cc_rk4", "rk4")])
+def test_full_size_replication_property_other_configs(torch_cuda, oracle_lib, name, solver):
+    """BASELINE configs[2] (Finite-SC-PMSM, N = 2^20) and configs[3] (Cont-CC-SCIM, N = 2^20): 1024 action streams replicated 1024 times
+    across the grid; every replica bit-identical to its prototype after single-step launches AND after a fused rollout, the prototypes
+    equal to the oracle."""
+    import torch
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    g = load_golden(name)
+    n, proto, steps = 1 << 20, 1024, 20
+    init = np.array(g["reset_ode"], dtype=float)
+    if name.startswith("scim"):
+        init[1:] = [0.7, -0.4, 0.02, 0.03, 0.3]  # a defined field frame from step 0 on (DESIGN.md finding 3)
+    mk = lambda nn, dt: config_from_meta(g["meta"], n_envs=nn, reset_ode=init, dtype=dt, solver=solver, ref_kind=K.REF_CONST)  # noqa: E731
+    cfg, cfg_o = mk(n, K.F32), mk(proto, K.F64)
+    for c in (cfg, cfg_o):
+        for r in range(c.n_ref):
+            c.ref_value[r] = 0.1 * (r + 1)
+    sim, sim2, ora = VectorSim(cfg), VectorSim(cfg), oracle_lib.Oracle(cfg_o, nthreads=8)
+    sim.reset()
+    sim2.reset()
+    ora.reset()
+    rng = np.random.default_rng(9)
+    acts = _random_actions(rng, g, proto, steps)
+    adt = torch.int32 if sim.finite else torch.float32
+    dev = torch.as_tensor(acts.reshape(steps, proto, sim.n_act), device="cuda").to(adt).repeat(1, n // proto, 1).contiguous()
+    for k in range(steps):
+        obs, ref, rew, term = sim.step(dev[k])
+        o_obs, _, o_rew, o_term = ora.step(acts[k])
+        v = obs.view(n // proto, proto, -1)
+        assert torch.equal(v, v[0:1].expand_as(v)) and torch.equal(rew.view(-1, proto), rew[:proto].expand(n // proto, proto))
+        d = obs[:proto].double().cpu().numpy()
+        assert col_rel_err(d, o_obs) < 1e-5 or np.abs(d - o_obs).max() < 1e-6, k
+        assert np.array_equal(term[:proto].cpu().numpy(), o_term)
+    last = sim2.rollout(dev, record_every=0)
+    assert torch.equal(last[0], obs) and torch.equal(last[2], rew) and torch.equal(last[3], term)
+
+
 def test_public_api_scalar_and_batched(torch_cuda):
     """gem.make surface: scalar (num_envs=None) contract of the reference and the batched contract agree with each other and
     with the recorded reference trajectory (Cont-CC-PMSM-v0, RK4 plugin golden)."""
@@ -517,6 +561,47 @@ def test_mixed_motor_batch(torch_cuda, oracle_lib):
     glob = torch.arange(n, device="cuda")
     parts = mixed.split_interleaved(glob)
     assert [int(p[1]) for p in parts] == [3, 4, 5]
+
+
+def test_mixed_motor_batch_matches_oracle(torch_cuda, oracle_lib):
+    """configs[4] against the ORACLE (not against the kernel itself): every type segment of a mixed PMSM + SynRM + EESM batch, stepped
+    through MixedEnvBatch (one launch per type, own stream) and through the fused rollout, equals the float64 oracle of that segment's
+    configuration (same global env indices -> same Philox streams) within the fp32 bar."""
+    import torch
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200.mixed import MixedEnvBatch
+
+    RK4 = gem.physical_systems.RK4Solver
+    ids = [("Cont-CC-PMSM-v0", dict(ode_solver=RK4())), ("Cont-CC-SynRM-v0", dict(ode_solver=RK4())), ("Cont-CC-EESM-v0", dict(ode_solver=RK4()))]
+    per, steps = 512, 60
+    mixed = MixedEnvBatch(ids, 3 * per, autoreset="same_step", seed=9, env_index_offset=3000)
+    oras = []
+    for env in mixed.envs:
+        cfg = env.build_config()
+        cfg.dtype = K.F64
+        oras.append(oracle_lib.Oracle(cfg, nthreads=8))
+    res = mixed.reset()
+    for t, ora in enumerate(oras):
+        o_obs, o_ref = ora.reset()
+        assert np.abs(res[t][0][0].double().cpu().numpy() - o_obs).max() < 1e-6
+    rng = np.random.default_rng(2)
+    alive = [np.ones(per, dtype=bool) for _ in ids]
+    n_term = 0
+    for k in range(steps):
+        acts = [rng.uniform(-1, 1, size=(per, 4 if t == 2 else 3)) for t in range(3)]
+        res = mixed.step([torch.as_tensor(a, dtype=torch.float32, device="cuda") for a in acts])
+        torch.cuda.synchronize()
+        for t, ora in enumerate(oras):
+            o_obs, o_ref, o_rew, o_term = ora.step(acts[t])
+            (s, r), rew, term, _, _ = res[t]
+            alive[t] &= ~(o_term != term.cpu().numpy().astype(np.uint8))
+            d = np.abs(s.double().cpu().numpy() - o_obs)
+            eps_col = mixed.envs[t].physical_system.state_names.index("epsilon")
+            d[:, eps_col] = np.abs((s.double().cpu().numpy()[:, eps_col] - o_obs[:, eps_col] + 1.0) % 2.0 - 1.0)
+            assert d[alive[t]].max() < 2e-5, (t, k)
+            assert np.abs(r.double().cpu().numpy() - o_ref)[alive[t]].max() < 2e-4 and np.abs(rew.double().cpu().numpy() - o_rew)[alive[t]].max() < 2e-4
+            n_term += int(o_term[alive[t]].sum())
+    assert all(a.mean() > 0.99 for a in alive) and n_term > 0
 
 
 @pytest.mark.parametrize("dtype", [K.F64, K.F32], ids=["f64", "f32"])
