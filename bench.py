@@ -50,6 +50,8 @@ CONFIGS = {
     "pmsm_64k": dict(env_id="Cont-CC-PMSM-v0", n_act=3, n_ode=4, n_obs=14, n_ref=2, envs=1 << 16, what="BASELINE configs[1]: N=65536"),
     "fin_sc_pmsm": dict(env_id="Finite-SC-PMSM-v0", n_act=1, n_ode=4, n_obs=14, n_ref=1, envs=1 << 20, n_finite=8,
                         what="BASELINE configs[2]: FiniteB6 (8 switching states) + PolynomialStaticLoad, tau=1e-5, Wiener omega reference"),
+    "fin_sc_pmsm_il": dict(env_id="Finite-SC-PMSM-v0", n_act=1, n_ode=4, n_obs=14, n_ref=1, envs=1 << 20, n_finite=8, interlock=1e-6,
+                           what="configs[2] variant: interlocking time 1 us (two switching segments per step, general kernel instantiation)"),
     "scim": dict(env_id="Cont-CC-SCIM-v0", n_act=3, n_ode=6, n_obs=14, n_ref=2, envs=1 << 20, what="BASELINE configs[3]: 5-state induction motor"),
     "eesm": dict(env_id="Cont-CC-EESM-v0", n_act=4, n_ode=5, n_obs=16, n_ref=3, envs=1 << 20, what="B6 + 4QC excitation converter"),
     "synrm": dict(env_id="Cont-CC-SynRM-v0", n_act=3, n_ode=4, n_obs=14, n_ref=2, envs=1 << 20, what="reluctance motor"),
@@ -85,14 +87,15 @@ def make_env(cfg_name, n_envs, device=0, rank=0):
 
         return MixedEnvBatch([CONFIGS[t]["env_id"] for t in c["types"]], n_envs, device=device, dtype="float32", ode_solver=gem.physical_systems.RK4Solver(),
                              autoreset="same_step", seed=0, env_index_offset=rank * n_envs)
+    extra = dict(converter=dict(interlocking_time=c["interlock"])) if "interlock" in c else {}
     return gem.make(c["env_id"], num_envs=n_envs, device=device, dtype="float32", ode_solver=gem.physical_systems.RK4Solver(),
-                    autoreset="same_step", seed=0, env_index_offset=rank * n_envs)
+                    autoreset="same_step", seed=0, env_index_offset=rank * n_envs, **extra)
 
 
 def workload_config(cfg_name, n_envs, n_gpus):
     c = CONFIGS[cfg_name]
     ids = c["env_id"] if "types" not in c else "+".join(CONFIGS[t]["env_id"] for t in c["types"])
-    tau = 1e-5 if cfg_name == "fin_sc_pmsm" else 1e-4
+    tau = 1e-5 if cfg_name.startswith("fin_sc_pmsm") else 1e-4
     return {"workload": f"{ids} x {n_envs} envs/GPU, RK4 x1 per tau={tau:g}, {c['what']}, same-step auto-reset",
             "name": cfg_name, "env_id": ids, "envs_per_gpu": n_envs, "global_envs": n_envs * n_gpus, "solver": "rk4x1", "tau": tau,
             "parallelism": f"env-shard x{n_gpus} (no collective)",

@@ -24,7 +24,7 @@ REF_CONST, REF_WIENER, REF_EXTERNAL, REF_LAPLACE, REF_SINUS, REF_STEP, REF_SAWTO
 F32, F64 = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 AUTORESET_NONE, AUTORESET_SAME_STEP = 0, 1
-SOP_NONE, SOP_COS_SIN, SOP_FLUX_OBSERVER, SOP_NOISE = range(4)
+SOP_NONE, SOP_COS_SIN, SOP_FLUX_OBSERVER, SOP_NOISE, SOP_CURRENT_SUM = range(5)
 NOISE_NORMAL, NOISE_UNIFORM, NOISE_LAPLACE = range(3)
 SUPPLY_IDEAL, SUPPLY_RC, SUPPLY_AC1 = 0, 1, 2
 

@@ -20,7 +20,10 @@ OUT = os.path.join(HERE, "libgemb200.so")
 OBJ_DIR = os.path.join(HERE, "..", "build", "gemb200")
 # -fmad=false: no implicit contraction of a*b+c — every fused multiply-add of the kernels is written out (fm() in gemb200_kernels.cuh), so
 # that all instantiations of the step (step / rollout kernel, AoS / SoA, PLAIN / general) round identically: bit-identical results
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
+# -lineinfo (ncu source pages) on the host unit and the fp32 kernels — the ones that are profiled; the fp64 units go without it: line tables are
+# ~60 % of a unit's size and the library travels to the GPU box with every gpurun call
+LINEINFO = ["-lineinfo"]
 FAMILIES = (0, 1, 2, 3, 4, 5)  # gemb200_params.h: MotorFamily
 REALS = ("float", "double")
 
@@ -40,12 +43,12 @@ def is_stale(out=OUT):
 
 
 def _units(only=None):
-    units = [("host", SOURCES[0], [])]
+    units = [("host", SOURCES[0], LINEINFO)]
     for fam in FAMILIES:
         for real in REALS:
             if only and (fam, real) not in only:
                 continue
-            units.append((f"step_f{fam}_{real}", SOURCES[1], [f"-DGEMB200_TU_FAM={fam}", f"-DGEMB200_TU_REAL={real}"]))
+            units.append((f"step_f{fam}_{real}", SOURCES[1], [f"-DGEMB200_TU_FAM={fam}", f"-DGEMB200_TU_REAL={real}"] + (LINEINFO if real == "float" else [])))
     return units
 
 

@@ -109,6 +109,10 @@ static int derive_dims(const gemb200_config* c, Dims* d) {
         d->has_observer = true;
         d->n_obs += 2;
         break;
+      case GEMB200_SOP_CURRENT_SUM:
+        if (c->sop_mask[k] == 0 || (d->n_obs < 32 && (c->sop_mask[k] >> d->n_obs) != 0)) return fail(GEMB200_E_INVALID, "CurrentSumProcessor: state indices out of range");
+        d->n_obs += 1;
+        break;
       case GEMB200_SOP_NOISE:
         if (c->sop_idx[k][0] < GEMB200_NOISE_NORMAL || c->sop_idx[k][0] > GEMB200_NOISE_LAPLACE) return fail(GEMB200_E_INVALID, "StateNoiseProcessor: unknown distribution");
         if (d->n_obs < 32 && (c->sop_mask[k] >> d->n_obs) != 0) return fail(GEMB200_E_INVALID, "StateNoiseProcessor: state index out of range");
@@ -590,6 +594,16 @@ static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cu
 #endif
 }
 
+template <typename real>
+static void set_roll_strides(const gemb200_handle* h, StepParams<real>& p) {
+  const int64_t n = h->cfg.n_envs;
+  p.roll_act_inc = n * h->n_act * (int64_t)(h->cfg.finite ? sizeof(int32_t) : sizeof(real));
+  p.roll_obs_inc = p.obs ? n * h->n_obs : 0;
+  p.roll_ref_inc = p.ref_out ? n * h->n_ref : 0;
+  p.roll_rew_inc = p.reward ? n : 0;
+  p.roll_term_inc = p.term ? n : 0;
+}
+
 // One launch over envs [begin, end) (end < 0: all).  new_call: this launch starts a new API call (fresh RNG call ids);
 // the chunks of one pipelined host step share them.  roll > 0: `roll` fused steps (rollout_kernel) whose call ids, step clock and
 // dead-time ring positions are exactly those of `roll` consecutive single-step calls; outputs every `every` steps (0: last only).
@@ -608,6 +622,7 @@ static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, 
     p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32);
     p.roll_steps = roll; p.record_every = every;
     p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
+    set_roll_strides(h, p);
     e = launch_step<float>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   } else {
     StepParams<double>& p = h->pd;
@@ -615,6 +630,7 @@ static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, 
     p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32);
     p.roll_steps = roll; p.record_every = every;
     p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
+    set_roll_strides(h, p);
     e = launch_step<double>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   }
   if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string(roll > 0 ? "rollout launch: " : "step launch: ") + cudaGetErrorString(e));
@@ -843,6 +859,8 @@ int gemb200_set_env_params(gemb200_handle* h, const double* motor_param, const d
   if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
   DeviceGuard guard(h->cfg.device);
   CUDA_TRY(cudaDeviceSynchronize());
+  if (h->cfg.layout != GEMB200_LAYOUT_AOS && (motor_param || load_param))
+    return fail(GEMB200_E_INVALID, "per-env parameter blocks need the row-per-env (AoS) I/O layout");
   if (!motor_param && !load_param) {
     h->pf.envp = nullptr; h->pd.envp = nullptr;
     h->pf.plain = h->plain_shape; h->pd.plain = h->plain_shape;

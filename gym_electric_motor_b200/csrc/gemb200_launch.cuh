@@ -21,10 +21,13 @@ static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const int range = p.env_end - p.env_begin;
   const int grid = (range + kBlock - 1) / kBlock;
   if constexpr (!PLAIN) {
-    if (p.envp) {  // per-env parameter blocks: the ENVP instantiation of the general kernel
+    if (p.envp) {  // per-env parameter blocks: the ENVP instantiation of the general kernel (row-per-env I/O layout only, checked by the host)
+      if constexpr (SOA) return cudaErrorInvalidValue;
+      else {
       if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, false, false, true><<<grid, kBlock, smem, st>>>(p);
       else step_kernel<FAM, FINITE, real, NREF, SOA, false, false, true><<<grid, kBlock, smem, st>>>(p);
       return cudaGetLastError();
+      }
     }
   }
   if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);

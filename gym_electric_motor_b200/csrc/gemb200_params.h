@@ -216,6 +216,9 @@ struct StepParams {
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
   // ---- fused rollout (rollout_kernel): number of steps of this launch; outputs recorded every `record_every` steps (0: last step only) ----
   int32_t roll_steps, record_every;
+  // per-step strides of the rollout's cursors, prepared on the host (elements; 0 for an output that is not requested): action tensor
+  // in BYTES per step, obs / ref / reward / terminated slices in elements per recorded step
+  int64_t roll_act_inc, roll_obs_inc, roll_ref_inc, roll_rew_inc, roll_term_inc;
 };
 
 }  // namespace gemb200

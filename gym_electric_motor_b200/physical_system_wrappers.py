@@ -59,11 +59,14 @@ class DeadTimeProcessor(PhysicalSystemWrapper):
 
 
 class CurrentSumProcessor(PhysicalSystemWrapper):
-    """Built into DcMotorSystem for the shunt motor (state `i_sum`); accepted here so that reference-style wrapper lists work."""
+    """Appends `i_sum`, the sum of the named (normalised) current states (current_sum_processor.py:7-66); its limit / nominal value is the
+    maximum or the sum of the source currents' limits.  Built into DcMotorSystem for the shunt motor (the reference's ShuntDc envs wrap
+    their system with it); on every other system it runs as a state op of the step kernel (GEMB200_SOP_CURRENT_SUM)."""
 
-    def __init__(self, currents=("i_a", "i_e"), limit="max"):
-        if tuple(currents) != ("i_a", "i_e") or limit != "max":
-            raise NotImplementedError("only CurrentSumProcessor(('i_a','i_e'), limit='max') — the ShuntDc default — is built in")
+    def __init__(self, currents=("i_a", "i_e"), limit="max", physical_system=None):
+        assert limit in ["max", "sum"]  # current_sum_processor.py:19
+        self._currents = tuple(currents)
+        self._limit = limit
 
 
 class CosSinProcessor(PhysicalSystemWrapper):

@@ -120,8 +120,10 @@ class SCMLSystem(PhysicalSystem):
 
         for w in wrappers:
             if isinstance(w, CurrentSumProcessor):
-                if not isinstance(self._electrical_motor, DcShuntMotor):
-                    raise NotImplementedError("CurrentSumProcessor is only built in for the shunt DC motor")
+                if isinstance(self._electrical_motor, DcShuntMotor) and w._currents == ("i_a", "i_e") and w._limit == "max" and "i_sum" in self._state_names \
+                        and not self._state_ops:
+                    continue  # the shunt system's own i_sum state (the reference's ShuntDc envs wrap the system with exactly this processor)
+                self._add_state_op(w)
             elif isinstance(w, DeadTimeProcessor):
                 if self._dead_steps:
                     raise NotImplementedError("only one DeadTimeProcessor is supported")
@@ -160,7 +162,7 @@ class SCMLSystem(PhysicalSystem):
     def _add_state_op(self, w):
         """State-vector wrappers: the bookkeeping of their set_physical_system (names, positions, limits, nominal state, space);
         the arithmetic runs in the kernel (gemb200_state_op)."""
-        from ..physical_system_wrappers import CosSinProcessor, FluxObserver
+        from ..physical_system_wrappers import CosSinProcessor, CurrentSumProcessor, FluxObserver
         from .electric_motors import InductionMotor
 
         if len(self._state_ops) >= K.MAX_STATE_OPS:
@@ -175,6 +177,19 @@ class SCMLSystem(PhysicalSystem):
             self._nominal_state = np.concatenate((np.delete(self._nominal_state, rm), [1.0, 1.0]))
             names = list(np.delete(names, rm)) + [f"cos({w.angle})", f"sin({w.angle})"]
             self._state_ops.append(dict(kind=K.SOP_COS_SIN, idx=[idx, int(w._remove_angle), 0, 0], mask=0, param=[]))
+        elif isinstance(w, CurrentSumProcessor):  # current_sum_processor.py:24-44
+            if "i_sum" in names:
+                raise NotImplementedError("the system already has an i_sum state")
+            ci = [self._state_positions[c] for c in w._currents]  # KeyError for an unknown current, like the reference
+            pick = max if w._limit == "max" else np.sum
+            low, high = np.concatenate((low, [-1.0])), np.concatenate((high, [1.0]))
+            self._limits = np.concatenate((self._limits, [pick(self._limits[ci])]))
+            self._nominal_state = np.concatenate((self._nominal_state, [pick(self._nominal_state[ci])]))
+            names = names + ["i_sum"]
+            mask = 0
+            for j in ci:
+                mask |= 1 << j
+            self._state_ops.append(dict(kind=K.SOP_CURRENT_SUM, idx=[0, 0, 0, 0], mask=mask, param=[]))
         elif isinstance(w, FluxObserver):  # flux_observer.py:56-79
             assert isinstance(self._electrical_motor, InductionMotor)
             mp = self._electrical_motor.motor_parameter

@@ -134,6 +134,7 @@ enum gemb200_state_op {
   GEMB200_SOP_FLUX_OBSERVER = 2, /* flux_observer.py:85-101 (induction motor): rotor-flux estimate integrated with explicit Euler,
                                     appends |psi|/psi_limit and angle(psi)/pi.  sop_idx = {i_sa, i_sb, i_sc, omega} indices,
                                     sop_param = {r_r*l_m/l_r, r_r/l_r, p, psi_limit, limit of i_sa, i_sb, i_sc, omega} */
+  GEMB200_SOP_CURRENT_SUM = 4,   /* current_sum_processor.py:7-66: append i_sum = sum of the (normalised) states in sop_mask */
   GEMB200_SOP_NOISE = 3          /* state_noise_processor.py: s[j] += noise for the states in sop_mask, i.i.d. per step and env.
                                     sop_idx[0] = gemb200_noise_dist, sop_param = {loc, scale} (normal, laplace) or {low, high} */
 };

@@ -159,6 +159,7 @@ static int dims(gem_oracle* o) {
   for (int k = 0; k < c->n_state_ops; ++k) {
     if (c->sop_kind[k] == GEMB200_SOP_COS_SIN) o->n_obs += c->sop_idx[k][1] ? 1 : 2;
     else if (c->sop_kind[k] == GEMB200_SOP_FLUX_OBSERVER) o->n_obs += 2;
+    else if (c->sop_kind[k] == GEMB200_SOP_CURRENT_SUM) o->n_obs += 1; /* current_sum_processor.py:29-31 */
   }
   return 0;
 }
@@ -977,6 +978,11 @@ static void apply_state_ops(const gem_oracle* o, env_t* e, int64_t idx, double* 
         e->psi_re += dre * c->tau; e->psi_im += dim * c->tau;                  /* :97 */
         st[w++] = sqrt(e->psi_re * e->psi_re + e->psi_im * e->psi_im) / q[3];
         st[w++] = atan2(e->psi_im, e->psi_re) / M_PI;                          /* limits [psi_limit, pi] :69,:98 */
+      } break;
+      case GEMB200_SOP_CURRENT_SUM: { /* current_sum_processor.py:46-66: np.sum(state[self._current_indices]) on the normalised state */
+        double sum = 0.0;
+        for (int j = 0; j < w; ++j) if ((c->sop_mask[k] >> j) & 1u) sum += st[j];
+        st[w++] = sum;
       } break;
       case GEMB200_SOP_NOISE: { /* state_noise_processor.py:74-98; one i.i.d. draw per step (Philox instead of numpy) */
         const uint32_t mask = c->sop_mask[k];

@@ -132,10 +132,6 @@ def test_user_kwargs_matrix_builds_identical_environments():
             # one interlocking time per handle (a scalar of the kernel's parameter block): sub-converters that disagree are refused loudly
             assert mine[case]["verdict"].startswith("NotImplementedError") and "interlocking" in mine[case]["verdict"]
             continue
-        if case == "currentsum_extex":
-            # the current sum is produced by the shunt system itself (the only env that uses the processor); as a general wrapper it is refused
-            assert mine[case]["verdict"].startswith("NotImplementedError") and "CurrentSumProcessor" in mine[case]["verdict"]
-            continue
         assert mine[case]["verdict"] == "ok", (case, mine[case]["verdict"])
         a, b = ref[case]["summary"], mine[case]["summary"]
         assert sorted(a) == sorted(b)

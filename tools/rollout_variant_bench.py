@@ -11,13 +11,19 @@ import sys, json, os
 sys.path.insert(0, %r)
 import torch
 import gym_electric_motor_b200 as gem
-out = {"lib": os.path.basename(os.environ.get("GEMB200_LIB", "default"))}
+import bench
+cfgname = os.environ.get("GEMB200_BENCH_CONFIG", "pmsm")
+out = {"lib": os.path.basename(os.environ.get("GEMB200_LIB", "default")), "config": cfgname}
 for n, k in ((1 << 20, 16), (1 << 16, 64)):
-    envs = [gem.make("Cont-CC-PMSM-v0", num_envs=n, ode_solver=gem.physical_systems.RK4Solver(), autoreset="same_step", seed=r) for r in range(2)]
+    envs = [bench.make_env(cfgname, n, 0, r) for r in range(2)]
     for e in envs: e.reset()
-    dev = envs[0].sim.device
-    acts = [torch.rand((k, n, 3), device=dev) * 2 - 1 for _ in range(2)]
-    outs = [(torch.empty((k, n, 14), device=dev), torch.empty((k, n, 2), device=dev), torch.empty((k, n), device=dev), torch.empty((k, n), dtype=torch.uint8, device=dev)) for _ in range(2)]
+    sim = envs[0].sim
+    dev = sim.device
+    if sim.finite:
+        acts = [torch.randint(0, 8, (k, n, sim.n_act), device=dev, dtype=torch.int32) for _ in range(2)]
+    else:
+        acts = [torch.rand((k, n, sim.n_act), device=dev) * 2 - 1 for _ in range(2)]
+    outs = [(torch.empty((k, n, sim.n_state), device=dev), torch.empty((k, n, max(sim.n_ref, 1)), device=dev), torch.empty((k, n), device=dev), torch.empty((k, n), dtype=torch.uint8, device=dev)) for _ in range(2)]
     for every in (1, 0):
         for r in range(3): envs[r %% 2].sim.rollout_into(acts[r %% 2], k, every, *outs[r %% 2])
         torch.cuda.synchronize()
