@@ -110,6 +110,7 @@ class GemB200Config(C.Structure):
         ("supply_param", C.c_double * 4),
         ("init_im_valid", C.c_int32),
         ("init_im", C.c_double * 8),
+        ("interlocking_time1", C.c_double),
     ]
 
 
@@ -123,6 +124,7 @@ def new_config():
     cfg.solver_nsteps = 1
     cfg.tau = 1e-4
     cfg.load_param[LP_TAU_DECAY] = 1e-3
+    cfg.interlocking_time1 = -1.0
     for i in range(MAX_STATE):
         cfg.limits[i] = 1.0
         cfg.state_length[i] = 2.0

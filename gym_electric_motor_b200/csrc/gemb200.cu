@@ -154,11 +154,12 @@ static int validate(const gemb200_config* c) {
   if (c->solver_nsteps < 1 || c->solver_nsteps > 1024) return fail(GEMB200_E_INVALID, "solver_nsteps out of range");
   if (!(c->tau > 0)) return fail(GEMB200_E_INVALID, "tau must be positive");
   if (c->interlocking_time < 0 || c->interlocking_time >= c->tau) return fail(GEMB200_E_INVALID, "interlocking_time must be in [0, tau)");
+  if (c->interlocking_time1 >= c->tau) return fail(GEMB200_E_INVALID, "interlocking_time1 must be < tau (negative: same as interlocking_time)");
   if (c->load_kind < GEMB200_LOAD_CONST_SPEED || c->load_kind > GEMB200_LOAD_EXT_SPEED) return fail(GEMB200_E_INVALID, "bad load_kind");
   if (c->load_kind == GEMB200_LOAD_EXT_SPEED) {
     if (!c->ext_speed_table || c->ext_speed_len < 4 * c->solver_nsteps + 2) return fail(GEMB200_E_INVALID, "external speed load: table missing or shorter than two steps");
     if (!(c->load_param[GEMB200_LP_TAU_LOAD] > 0)) return fail(GEMB200_E_INVALID, "external speed load: tau_load must be positive");
-    if (c->finite && c->interlocking_time > 0) return fail(GEMB200_E_INVALID, "external speed load with two-segment steps (finite converter + interlocking time) is not supported: the segment times are off the table grid");
+    if (c->finite && (c->interlocking_time > 0 || c->interlocking_time1 > 0)) return fail(GEMB200_E_INVALID, "external speed load with two-segment steps (finite converter + interlocking time) is not supported: the segment times are off the table grid");
   }
   if (c->n_ref < 0 || c->n_ref > GEMB200_MAX_REF) return fail(GEMB200_E_INVALID, "n_ref out of range");
   if (c->dead_time_steps < 0 || c->dead_time_steps > GEMB200_MAX_DEAD_TIME) return fail(GEMB200_E_INVALID, "dead_time_steps out of range");
@@ -180,7 +181,7 @@ static int validate(const gemb200_config* c) {
   Dims d;
   int rc = derive_dims(c, &d);
   if (rc) return rc;
-  if (c->finite && c->interlocking_time > 0 && c->motor_kind == GEMB200_MOTOR_EESM)
+  if (c->finite && (c->interlocking_time > 0 || c->interlocking_time1 > 0) && c->motor_kind == GEMB200_MOTOR_EESM)
     return fail(GEMB200_E_INVALID, "finite EESM with interlocking time: the reference raises in this configuration "
                                    "(physical_systems.py:632 slices u_in[:2]); not supported");
   int n_entries = c->n_ref;  // parameter entries in use: the output slots plus the extra sub-generators of switched slots
@@ -381,13 +382,19 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   p->load_kind = c.load_kind; p->solver_kind = c.solver_kind; p->nsteps = c.solver_nsteps;
   p->autoreset = c.autoreset;
   p->two_segment = h->two_segment;
-  p->tau = (real)c.tau; p->til = (real)c.interlocking_time; p->til_over_tau = (real)(c.interlocking_time / c.tau);
+  const double til0 = c.interlocking_time, til1 = c.interlocking_time1 < 0 ? c.interlocking_time : c.interlocking_time1;
+  p->tau = (real)c.tau;
+  p->til2[0] = (real)til0; p->til2[1] = (real)til1;
+  p->tot2[0] = (real)(til0 / c.tau); p->tot2[1] = (real)(til1 / c.tau);
+  p->lo_slot = til1 < til0 ? 1 : 0;
+  p->promote = std::fabs(til1 - til0) - c.tau / 1000 > 0;  // t_hi - tau/1000 > t_start + t_lo (converters.py:273)
+  const double hs[6] = {c.tau, til0, c.tau - til0, til1, c.tau - til1, std::fabs(til1 - til0)};
+  for (int q = 0; q < 6; ++q) p->seg_len[q] = (real)hs[q];
   p->u_sup = (real)c.u_sup;
-  {  // angle increment factors (see StepParams::kang): segments 0 = tau, 1 = interlocking time, 2 = tau - interlocking time
+  {  // angle increment factors (see StepParams::kang) for every segment length of seg_len
     const double pp = c.motor_param[GEMB200_MP_P];
-    const double hs[3] = {c.tau, c.interlocking_time, c.tau - c.interlocking_time};
     const double unit = sizeof(real) == 4 ? 1.0 / (2 * M_PI) : 1.0;  // fp32 build keeps the angle in turns
-    for (int sidx = 0; sidx < 3; ++sidx) {
+    for (int sidx = 0; sidx < 6; ++sidx) {
       const double k_tot = pp * hs[sidx] * unit;
       const double k_sub = pp * (hs[sidx] / c.solver_nsteps) * (c.solver_kind == GEMB200_SOLVER_RK4 ? 1.0 / 6.0 : 1.0) * unit;
       const double ks[2] = {k_tot, k_sub};
@@ -483,7 +490,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   // PLAIN shape (step_kernel): decided here once; GEMB200_NO_PLAIN=1 in the environment forces the general instantiation (A/B runs)
   {
     bool plain =
-                 c.load_kind != GEMB200_LOAD_EXT_SPEED && c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
+                 c.load_kind != GEMB200_LOAD_EXT_SPEED && c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && !(c.interlocking_time1 > 0.0) && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
     for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r] && c.ref_sw_count[r] <= 1;
@@ -701,6 +708,7 @@ int gemb200_config_init(gemb200_config* cfg) {
   cfg->solver_nsteps = 1;
   cfg->tau = 1e-4;
   cfg->load_param[GEMB200_LP_TAU_DECAY] = 1e-3;
+  cfg->interlocking_time1 = -1.0;
   for (int i = 0; i < GEMB200_MAX_STATE; ++i) { cfg->limits[i] = 1.0; cfg->state_length[i] = 2.0; cfg->reward_power[i] = 1.0; }
   for (int r = 0; r < GEMB200_MAX_REF_ENTRIES; ++r) {
     cfg->ref_len_lo[r] = 500; cfg->ref_len_hi[r] = 2000;
@@ -741,7 +749,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
   h->row_stride = cfg->n_state_ops > 0 ? (d.n_obs | 1) : (d.fam == kEESM ? 17 : (d.fam == kDFIM ? 25 : d.n_state));  // Fam<>::PAD without wrappers
   h->n_ref = cfg->n_ref;
   h->rsz = cfg->dtype == GEMB200_F32 ? 4 : 8;
-  h->two_segment = cfg->finite && cfg->interlocking_time > 0;
+  h->two_segment = cfg->finite && (cfg->interlocking_time > 0 || cfg->interlocking_time1 > 0);
   for (int r = 0; r < GEMB200_MAX_REF_ENTRIES; ++r) {  // any generator that advances by itself (Wiener, Laplace, periodic), incl. switched subs
     bool used = r < cfg->n_ref;
     for (int q = 0; q < cfg->n_ref; ++q) used = used || (cfg->ref_sw_count[q] > 1 && r >= cfg->ref_sw_first[q] && r < cfg->ref_sw_first[q] + cfg->ref_sw_count[q]);

@@ -126,15 +126,20 @@ struct StepParams {
   real adv_k;             // angle advance per (rad/s) of omega, in the stored angle unit: angle_advance * tau * p (/2pi in turns)
   real inv_nsteps;
   real tau;               // step
-  real til;               // interlocking time
-  real til_over_tau;
+  // interlocking time per converter slot (multi converters may give their sub-converters different ones, converters.py:615-740);
+  // seg_len = lengths a switching segment can have: {tau, til0, tau - til0, til1, tau - til1, |til1 - til0|}; lo_slot = the slot with the
+  // smaller time; promote = the legs of lo_slot reach their commanded state in a THIRD segment (|til1 - til0| > tau / 1000, converters.py:273)
+  real til2[2];
+  real tot2[2];           // til / tau per slot
+  real seg_len[6];
+  int32_t lo_slot, promote;
   real u_sup;
   // Electrical angle: d eps/dt = p * omega.  fp64 build: radians in a double.  fp32 build: TURNS as an unevaluated sum of two
   // floats (hi, lo) — "double-float", ~48 bits — so that neither fp64 arithmetic nor fp64<->fp32 conversions (slow XU-pipe
   // instructions on B200) are needed.  kang[m][s] = factor that turns the integrator's omega sum of segment s
-  // (0: whole tau, 1: interlock part, 2: rest) into the angle increment; m = 0: constant speed (sum = omega, factor = p*h_seg),
+  // (index into seg_len) into the angle increment; m = 0: constant speed (sum = omega, factor = p*h_seg),
   // m = 1: sum over sub-steps (factor = p*h or p*h/6 for RK4); units: turns (fp32 build) or radians (fp64 build); [..][2] = hi, lo.
-  real kang[2][3][2];
+  real kang[2][6][2];
   real eps_out_scale;     // normalised angle output = (hi + lo) * eps_out_scale  (2*pi/limit in turns, 1/limit in radians)
   real init_ang[2];       // initial angle in the stored representation
   Coef<real> k;           // shared model coefficients

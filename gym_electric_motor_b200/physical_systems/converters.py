@@ -123,12 +123,11 @@ class _MultiMixin:
             self._sub_converters.append(sub)
         if len(self._sub_converters) > 2:
             raise NotImplementedError("at most two sub-converters are supported on the device")
-        ils = {s.interlocking_time for s in self._sub_converters}
-        if len(ils) > 1:
-            raise NotImplementedError("sub-converters with different interlocking times are not supported")
         # `_interlocking_time` stays the multi converter's own (unused) kwarg like in the reference (converters.py:629-636, DESIGN.md finding 5);
-        # what the half bridges actually use is the sub-converters' value
-        self._sub_interlocking_time = ils.pop() if ils else self._interlocking_time
+        # what the half bridges actually use are the sub-converters' values — one per converter slot of the kernel (gemb200.h: interlocking_time,
+        # interlocking_time1)
+        self._sub_interlocking_times = [float(s.interlocking_time) for s in self._sub_converters] or [float(self._interlocking_time)]
+        self._sub_interlocking_time = self._sub_interlocking_times[0]
         self.currents = Box(np.concatenate([s.currents.low for s in self._sub_converters]),
                             np.concatenate([s.currents.high for s in self._sub_converters]), dtype=np.float64)
         self.voltages = Box(np.concatenate([s.voltages.low for s in self._sub_converters]),
@@ -140,6 +139,10 @@ class _MultiMixin:
     @property
     def interlocking_time(self):
         return self._sub_interlocking_time
+
+    def interlocking_times(self):
+        """interlocking time per converter slot (sub-converter)"""
+        return list(self._sub_interlocking_times)
 
     def slots(self):
         return [s.KIND for s in self._sub_converters]

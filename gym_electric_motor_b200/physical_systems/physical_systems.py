@@ -291,6 +291,8 @@ class SCMLSystem(PhysicalSystem):
             cfg.converter_kind[i] = slots[i] if i < len(slots) else K.CONV_NONE
         cfg.tau = float(self.tau)
         cfg.interlocking_time = float(self._converter.interlocking_time)
+        ils = self._converter.interlocking_times() if hasattr(self._converter, "interlocking_times") else []
+        cfg.interlocking_time1 = float(ils[1]) if len(ils) > 1 and ils[1] != ils[0] else -1.0
         self._supply.fill_config(cfg)
         self._electrical_motor.fill_config(cfg)
         self._ode_solver.fill_config(cfg)

@@ -254,6 +254,9 @@ typedef struct gemb200_config {
    * A truncated-normal state (init_dist) whose init_mu is NaN takes the middle of its (per-env) interval as mue (electric_motor.py:247). */
   int32_t init_im_valid;
   double init_im[8];
+  /* interlocking time of converter slot 1 when a multi converter's sub-converters differ (converters.py:615-740); < 0: same as slot 0
+   * (interlocking_time above).  Finite converters with two different times integrate a switching step in up to three segments. */
+  double interlocking_time1;
   /* action_dq = 3: DFIM, 4 actions (stator dq, rotor dq): stator with eps + angle_advance*tau*omega*p, rotor with the FluxObserver's
    * psi_angle minus that angle (dq_to_abc_action_processor.py:108-137); requires a GEMB200_SOP_FLUX_OBSERVER op */
   /* action_dq = 2: SCIM with a FluxObserver — the transformation angle is the observer's psi_angle (+ angle_advance*tau*omega*p),

@@ -469,11 +469,15 @@ static double integrate(const gem_oracle* o, double* y, double t_start, double t
 static double clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); } /* min(max(.)) :146 */
 static double sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }         /* np.sign :184 */
 
+/* interlocking time of the sub-converter a half bridge belongs to (slot 1 of a multi converter may have its own, converters.py:615-740) */
+static double il_slot(const gem_oracle* o, int slot) {
+  return (slot == 1 && o->cfg.interlocking_time1 >= 0) ? o->cfg.interlocking_time1 : o->cfg.interlocking_time;
+}
 /* FiniteTwoQuadrantConverter._set_switching_pattern :300-310; returns number of switching times (1 or 2) */
-static int f2qc_set_action(const gem_oracle* o, sub2qc_t* s, int action, double t) {
+static int f2qc_set_action(const gem_oracle* o, sub2qc_t* s, int action, double t, double il) {
   s->action_start_time = t;
   s->cur_action_i = action;
-  if (action == 0 || s->switching_state == 0 || action == s->switching_state || o->cfg.interlocking_time == 0) {
+  if (action == 0 || s->switching_state == 0 || action == s->switching_state || il == 0) {
     s->pattern[0] = action; s->pattern_len = 1;
     return 1;
   }
@@ -481,8 +485,8 @@ static int f2qc_set_action(const gem_oracle* o, sub2qc_t* s, int action, double 
   return 2;
 }
 /* FiniteTwoQuadrantConverter.convert :270-287 */
-static double f2qc_convert(const gem_oracle* o, sub2qc_t* s, double i_out, double t) {
-  if (t - o->cfg.tau / 1000 > s->action_start_time + o->cfg.interlocking_time) s->switching_state = s->pattern[s->pattern_len - 1];
+static double f2qc_convert(const gem_oracle* o, sub2qc_t* s, double i_out, double t, double il) {
+  if (t - o->cfg.tau / 1000 > s->action_start_time + il) s->switching_state = s->pattern[s->pattern_len - 1];
   else s->switching_state = s->pattern[0];
   if (s->switching_state == 0) return i_out < 0 ? 1.0 : 0.0;
   if (s->switching_state == 1) return 1.0;
@@ -495,21 +499,22 @@ static double f2qc_i_sup(const sub2qc_t* s, double i_out) {
   return 0.0;
 }
 /* ContTwoQuadrantConverter via ContDynamicallyAveragedConverter.convert :148-158, _interlock :176-184 */
-static double c2qc_convert(const gem_oracle* o, const sub2qc_t* s, double i_out) {
-  return clip(s->cur_action - sgn(i_out) / o->cfg.tau * o->cfg.interlocking_time, 0.0, 1.0);
+static double c2qc_convert(const gem_oracle* o, const sub2qc_t* s, double i_out, double il) {
+  return clip(s->cur_action - sgn(i_out) / o->cfg.tau * il, 0.0, 1.0);
 }
 /* ContTwoQuadrantConverter.i_sup :429-435 */
-static double c2qc_i_sup(const gem_oracle* o, const sub2qc_t* s, double i_out) {
+static double c2qc_i_sup(const gem_oracle* o, const sub2qc_t* s, double i_out, double il) {
   double ic = i_out < 0 ? 1.0 : 0.0;
-  return (s->cur_action + o->cfg.interlocking_time / o->cfg.tau * (ic - s->cur_action)) * i_out;
+  return (s->cur_action + il / o->cfg.tau * (ic - s->cur_action)) * i_out;
 }
 
 static const int B6_SUBACTIONS[8][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 2}, {2, 1, 1}, {1, 2, 2}, {1, 2, 1}, {1, 1, 2}, {1, 1, 1}}; /* :788-797 */
 
-/* converter.set_action: returns the number of switching segments (1 or 2) and the first switching time offset.
- * With equal interlocking times on all legs the sorted unique set of times is {t+t_il, t+tau} or {t+tau}. */
-static int conv_set_action(const gem_oracle* o, env_t* e, const double* act_f, const int32_t* act_i, double t) {
-  int nseg = 1;
+/* converter.set_action: returns the number of switching segments (1..3) and their END times: the sorted unique switching times of the
+ * sub-converters (FiniteMultiConverter.set_action :583-595) — {t+tau}, {t+t_il, t+tau}, or with two different interlocking times
+ * {t+t_lo, t+t_hi, t+tau}. */
+static int conv_set_action(const gem_oracle* o, env_t* e, const double* act_f, const int32_t* act_i, double t, double* seg_end) {
+  int sw[2] = {0, 0};
   int ai = 0, af = 0;
   for (int slot = 0; slot < 2; ++slot) {
     int kind = o->cfg.converter_kind[slot];
@@ -519,14 +524,14 @@ static int conv_set_action(const gem_oracle* o, env_t* e, const double* act_f, c
       int a = act_i[ai++];
       switch (kind) {
         case GEMB200_CONV_1QC: e->cur_action1qc[slot] = a; break; /* :59-61 */
-        case GEMB200_CONV_2QC: if (f2qc_set_action(o, s, a, t) > 1) nseg = 2; break;
+        case GEMB200_CONV_2QC: if (f2qc_set_action(o, s, a, t, il_slot(o, slot)) > 1) sw[slot] = 1; break;
         case GEMB200_CONV_4QC: { /* :350-360 */
           static const int a0[4] = {1, 1, 2, 2}, a1[4] = {1, 2, 1, 2};
-          if (f2qc_set_action(o, s, a0[a], t) > 1) nseg = 2;
-          if (f2qc_set_action(o, s + 1, a1[a], t) > 1) nseg = 2;
+          if (f2qc_set_action(o, s, a0[a], t, il_slot(o, slot)) > 1) sw[slot] = 1;
+          if (f2qc_set_action(o, s + 1, a1[a], t, il_slot(o, slot)) > 1) sw[slot] = 1;
         } break;
         case GEMB200_CONV_B6: /* :824-835 */
-          for (int l = 0; l < 3; ++l) if (f2qc_set_action(o, s + l, B6_SUBACTIONS[a][l], t) > 1) nseg = 2;
+          for (int l = 0; l < 3; ++l) if (f2qc_set_action(o, s + l, B6_SUBACTIONS[a][l], t, il_slot(o, slot)) > 1) sw[slot] = 1;
           break;
       }
     } else {
@@ -544,6 +549,12 @@ static int conv_set_action(const gem_oracle* o, env_t* e, const double* act_f, c
       }
     }
   }
+  int nseg = 0;
+  const double t0 = t + il_slot(o, 0), t1 = t + il_slot(o, 1);
+  if (sw[0] && sw[1] && t0 != t1) { seg_end[nseg++] = fmin(t0, t1); seg_end[nseg++] = fmax(t0, t1); }
+  else if (sw[0]) seg_end[nseg++] = t0;
+  else if (sw[1]) seg_end[nseg++] = t1;
+  seg_end[nseg++] = t + o->cfg.tau;
   return nseg;
 }
 
@@ -557,16 +568,16 @@ static void conv_convert(const gem_oracle* o, env_t* e, const double* i_out, dou
     if (o->cfg.finite) {
       switch (kind) {
         case GEMB200_CONV_1QC: u_out[uo++] = i_out[io] >= 0 ? (double)e->cur_action1qc[slot] : 1.0; io++; break; /* :236-238 */
-        case GEMB200_CONV_2QC: u_out[uo++] = f2qc_convert(o, s, i_out[io], t); io++; break;
-        case GEMB200_CONV_4QC: u_out[uo++] = f2qc_convert(o, s, i_out[io], t) - f2qc_convert(o, s + 1, -i_out[io], t); io++; break; /* :346-348 */
-        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) u_out[uo++] = f2qc_convert(o, s + l, i_out[io++], t) - 0.5; break; /* :814-822 */
+        case GEMB200_CONV_2QC: u_out[uo++] = f2qc_convert(o, s, i_out[io], t, il_slot(o, slot)); io++; break;
+        case GEMB200_CONV_4QC: u_out[uo++] = f2qc_convert(o, s, i_out[io], t, il_slot(o, slot)) - f2qc_convert(o, s + 1, -i_out[io], t, il_slot(o, slot)); io++; break; /* :346-348 */
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) u_out[uo++] = f2qc_convert(o, s + l, i_out[io++], t, il_slot(o, slot)) - 0.5; break; /* :814-822 */
       }
     } else {
       switch (kind) {
         case GEMB200_CONV_1QC: u_out[uo++] = clip(i_out[io] >= 0 ? s->cur_action : 1.0, 0.0, 1.0); io++; break; /* :388-394 */
-        case GEMB200_CONV_2QC: u_out[uo++] = c2qc_convert(o, s, i_out[io]); io++; break;
-        case GEMB200_CONV_4QC: u_out[uo++] = c2qc_convert(o, s, i_out[io]) - c2qc_convert(o, s + 1, i_out[io]); io++; break; /* :480-482 (same i_out for both) */
-        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) u_out[uo++] = c2qc_convert(o, s + l, i_out[io++]) - 0.5; break; /* :888-895 */
+        case GEMB200_CONV_2QC: u_out[uo++] = c2qc_convert(o, s, i_out[io], il_slot(o, slot)); io++; break;
+        case GEMB200_CONV_4QC: u_out[uo++] = c2qc_convert(o, s, i_out[io], il_slot(o, slot)) - c2qc_convert(o, s + 1, i_out[io], il_slot(o, slot)); io++; break; /* :480-482 (same i_out for both) */
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) u_out[uo++] = c2qc_convert(o, s + l, i_out[io++], il_slot(o, slot)) - 0.5; break; /* :888-895 */
       }
     }
   }
@@ -590,9 +601,9 @@ static double conv_i_sup(const gem_oracle* o, const env_t* e, const double* i_ou
     } else {
       switch (kind) {
         case GEMB200_CONV_1QC: r += s->cur_action * i_out[io]; io++; break;
-        case GEMB200_CONV_2QC: r += c2qc_i_sup(o, s, i_out[io]); io++; break;
-        case GEMB200_CONV_4QC: r += c2qc_i_sup(o, s, i_out[io]) + c2qc_i_sup(o, s + 1, -i_out[io]); io++; break;
-        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) r += c2qc_i_sup(o, s + l, i_out[io++]); break;
+        case GEMB200_CONV_2QC: r += c2qc_i_sup(o, s, i_out[io], il_slot(o, slot)); io++; break;
+        case GEMB200_CONV_4QC: r += c2qc_i_sup(o, s, i_out[io], il_slot(o, slot)) + c2qc_i_sup(o, s + 1, -i_out[io], il_slot(o, slot)); io++; break;
+        case GEMB200_CONV_B6: for (int l = 0; l < 3; ++l) r += c2qc_i_sup(o, s + l, i_out[io++], il_slot(o, slot)); break;
       }
     }
   }
@@ -697,10 +708,8 @@ static void simulate(const gem_oracle* o, env_t* e, const double* act_f, const i
   double* y = e->ode;
   double i_in[6], u_in[6], u_solver[4];
   double t0 = e->t;
-  int nseg = conv_set_action(o, e, act_f, act_i, t0);
-  double seg_end[2];
-  if (nseg == 2) { seg_end[0] = t0 + c->interlocking_time; seg_end[1] = t0 + c->tau; }
-  else seg_end[0] = t0 + c->tau;
+  double seg_end[3];
+  int nseg = conv_set_action(o, e, act_f, act_i, t0, seg_end);
   double t_solver = t0;
   const double* gt = NULL; /* ExternalSpeedLoad: the tabulated profile restarts at every reset (e->k = steps since then) */
   if (c->load_kind == GEMB200_LOAD_EXT_SPEED) {
@@ -1399,7 +1408,7 @@ void gem_oracle_philox(uint32_t ctr[4], uint32_t k0, uint32_t k1) { philox4x32_1
 /* probe entry points for tests/test_oracle_known_answers.py: the reference's unit tests call converters, loads,  */
 /* constraints and the reward function directly, so the same granularity is exposed here (on env 0)               */
 /* ------------------------------------------------------------------------------------------------------------ */
-int gem_oracle_probe_set_action(gem_oracle* o, const double* act_f, const int32_t* act_i, double t) { return conv_set_action(o, o->env, act_f, act_i, t); }
+int gem_oracle_probe_set_action(gem_oracle* o, const double* act_f, const int32_t* act_i, double t) { double seg_end[3]; return conv_set_action(o, o->env, act_f, act_i, t, seg_end); }
 void gem_oracle_probe_convert(gem_oracle* o, const double* i_out, double t, double* u_out) { conv_convert(o, o->env, i_out, t, u_out); }
 void gem_oracle_probe_conv_reset(gem_oracle* o, double* u_out) { conv_reset(o, o->env, u_out); }
 double gem_oracle_probe_i_sup(gem_oracle* o, const double* i_out) { return conv_i_sup(o, o->env, i_out); }

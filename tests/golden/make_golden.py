@@ -159,6 +159,8 @@ def describe(env, case):
         # a multi converter keeps its own (unused) copy; the sub-converters' value is the one in force
         interlocking_time=float(max([conv._interlocking_time] + [sc._interlocking_time for sc in getattr(conv, "_sub_converters", [])])
                                 if case.get("multi") is not None else conv._interlocking_time),
+        # per sub-converter (slot) when they differ: [slot 0, slot 1]
+        interlocking_times=[float(sc._interlocking_time) for sc in getattr(conv, "_sub_converters", [])],
         reference_names=list(env.reference_generator.reference_names),
         referenced_states=np.asarray(env.reference_generator.referenced_states).astype(int).tolist(),
         reward_weights=np.asarray(env.reward_function._reward_weights, dtype=float).tolist(),
@@ -356,6 +358,19 @@ CASES = [
       converter_args=dict(interlocking_time=1e-6)),
     C("permex_fin4qc_interlock_rk4", "Finite-SC-PermExDc-v0", "rk4", steps=1000, converter=dict(interlocking_time=1e-6)),
     C("scim_fin_cc_interlock_rk4", "Finite-CC-SCIM-v0", "rk4", steps=1500, converter=dict(interlocking_time=1e-6)),
+    # multi converters whose sub-converters have DIFFERENT interlocking times (converters.py:498-740): per-slot dead time of the continuous
+    # converters; finite: up to three switching segments per step, the legs of the sub-converter with the shorter time reach their commanded
+    # state at the other one's switching time (converters.py:273)
+    C("extex_cc_interlock2_rk4", "Cont-CC-ExtExDc-v0", "rk4", steps=1500,
+      multi=[("ContFourQuadrantConverter", dict(interlocking_time=1e-6)), ("ContTwoQuadrantConverter", dict(interlocking_time=3e-6))]),
+    C("eesm_cc_interlock2_rk4", "Cont-CC-EESM-v0", "rk4", steps=1500,
+      multi=[("ContB6BridgeConverter", dict(interlocking_time=2e-6)), ("ContFourQuadrantConverter", dict(interlocking_time=5e-6))]),
+    C("extex_fin_cc_interlock2_rk4", "Finite-CC-ExtExDc-v0", "rk4", steps=2500,
+      multi=[("FiniteFourQuadrantConverter", dict(interlocking_time=1e-6)), ("FiniteFourQuadrantConverter", dict(interlocking_time=2.5e-6))]),
+    C("extex_fin_cc_interlock2b_rk4", "Finite-CC-ExtExDc-v0", "rk4", steps=2500,
+      multi=[("FiniteFourQuadrantConverter", dict(interlocking_time=3e-6)), ("FiniteTwoQuadrantConverter", dict())]),
+    C("dfim_fin_sc_interlock2_rk4", "Finite-SC-DFIM-v0", "rk4", steps=2000,
+      multi=[("FiniteB6BridgeConverter", dict(interlocking_time=2e-6)), ("FiniteB6BridgeConverter", dict(interlocking_time=0.5e-6))]),
     # non-default parameters: load polynomial with all terms, custom motor, non-zero constant initial state
     C("pmsm_sc_polyload_rk4", "Cont-SC-PMSM-v0", "rk4", steps=1500,
       load=dict(load_parameter=dict(a=0.5, b=0.02, c=1e-4, j_load=2e-3))),

@@ -89,7 +89,14 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
         cfg.finite, kinds = CONV[cc]
     elif cc in ("ContMultiConverter", "FiniteMultiConverter"):
         cfg.finite = int(cc.startswith("Finite"))
-        kinds = [K.CONV_B6, K.CONV_4QC] if mk == K.MOTOR_EESM else ([K.CONV_B6, K.CONV_B6] if mk == K.MOTOR_DFIM else [K.CONV_4QC, K.CONV_4QC])
+        sub = {"ContFourQuadrantConverter": K.CONV_4QC, "ContTwoQuadrantConverter": K.CONV_2QC, "ContOneQuadrantConverter": K.CONV_1QC,
+               "FiniteFourQuadrantConverter": K.CONV_4QC, "FiniteTwoQuadrantConverter": K.CONV_2QC, "FiniteOneQuadrantConverter": K.CONV_1QC,
+               "ContB6BridgeConverter": K.CONV_B6, "FiniteB6BridgeConverter": K.CONV_B6}
+        multi = meta["case"].get("multi")
+        if multi:
+            kinds = [sub[name] for name, _ in multi]
+        else:
+            kinds = [K.CONV_B6, K.CONV_4QC] if mk == K.MOTOR_EESM else ([K.CONV_B6, K.CONV_B6] if mk == K.MOTOR_DFIM else [K.CONV_4QC, K.CONV_4QC])
     else:
         raise ValueError(cc)
     for i, kd in enumerate(kinds):
@@ -108,6 +115,9 @@ def config_from_meta(meta, n_envs=1, solver=None, ref_kind=K.REF_EXTERNAL, dtype
         cfg.ext_speed_table, cfg.ext_speed_len = tab.ctypes.data, len(tab)
         cfg._keepalive = tab
     cfg.interlocking_time = meta["interlocking_time"]
+    ils = meta.get("interlocking_times") or []
+    if len(ils) == 2 and ils[0] != ils[1]:  # multi converter whose sub-converters differ: one time per converter slot
+        cfg.interlocking_time, cfg.interlocking_time1 = ils[0], ils[1]
     cfg.u_sup = meta["u_sup"]
     if meta.get("supply_class") == "AC1PhaseSupply":
         cfg.supply_kind = K.SUPPLY_AC1

@@ -30,7 +30,7 @@ def sim_n_ode(cfg):
 
 
 CASES, PRELUDE = _cases()
-REFUSED = ("interlock_cont_multi", "finite_multi_interlock", "synrm_dq")  # refused on the host (tests/test_agent_surface.py)
+REFUSED = ("synrm_dq",)  # refused on the host (tests/test_agent_surface.py)
 
 
 @pytest.mark.parametrize("case", sorted(c for c in CASES if c not in REFUSED and not c.startswith("err_")))

@@ -117,6 +117,9 @@ BATCH_CASES = [
     # single-phase AC supply; the batch test draws a random phase per env and reset (goldens: fixed phase)
     ("permex_sc_ac_rk4", "rk4"), ("series_fin_cc_ac_interlock_rk4", "rk4"), ("pmsm_cc_ac_rk4", "rk4"),
     ("dfim_cc_flux_dq_rk4", "rk4"), ("dfim_cc_rk4", "rk4"), ("dfim_sc_rk4", "rk4x2"), ("dfim_fin_sc_interlock_rk4", "rk4"), ("dfim_cc_interlock_rk4", "euler3"),
+    # multi converters whose sub-converters have different interlocking times (per-slot dead time; three switching segments when finite)
+    ("extex_cc_interlock2_rk4", "rk4"), ("eesm_cc_interlock2_rk4", "rk4"), ("extex_fin_cc_interlock2_rk4", "rk4"), ("extex_fin_cc_interlock2b_rk4", "euler3"),
+    ("dfim_fin_sc_interlock2_rk4", "rk4"),
     # state-vector wrappers (CosSinProcessor, FluxObserver, FluxObserver angle for dq actions, dead time in front)
     ("pmsm_cc_cossin_rk4", "rk4"), ("pmsm_sc_cossin_rm_rk4", "rk4"), ("scim_cc_flux_dq_rk4", "rk4"), ("scim_sc_flux_cossin_dead1_rk4", "rk4"),
 ]

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["pmsm_cc_rk4", "pmsm_sc_polyload_rk4", "pmsm_fin_sc_rk4", "pmsm_fin_sc_rk4_interlock", "pmsm_cc_euler3", "synrm_cc_rk4", "eesm_cc_rk4",
          "eesm_fin_cc_rk4", "scim_cc_rk4", "scim_fin_cc_interlock_rk4", "dfim_cc_rk4", "permex_cc_rk4", "series_cc_rk4", "shunt_cc_rk4", "extex_cc_rk4",
          "permex_fin_sc_rc_interlock_rk4", "pmsm_cc_ac_rk4", "pmsm_cc_extspeed_rk4", "scim_sc_flux_cossin_dead1_rk4", "eesm_cc_rc_dq_dead1_rk4",
-         "pmsm_cc_cossin_rk4", "dfim_cc_flux_dq_rk4"]
+         "pmsm_cc_cossin_rk4", "dfim_cc_flux_dq_rk4", "extex_fin_cc_interlock2_rk4", "dfim_fin_sc_interlock2_rk4"]
 
 
 def _mk(name, n, dtype, layout, ref_kind=K.REF_WIENER):
