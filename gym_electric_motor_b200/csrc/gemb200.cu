@@ -871,7 +871,7 @@ int gemb200_set_env_params(gemb200_handle* h, const double* motor_param, const d
     return fail(GEMB200_E_INVALID, "per-env parameter blocks need the row-per-env (AoS) I/O layout");
   if (!motor_param && !load_param) {
     h->pf.envp = nullptr; h->pd.envp = nullptr;
-    h->pf.plain = h->plain_shape; h->pd.plain = h->plain_shape;
+    h->pf.plain = h->pf.n_dst == 0 ? h->plain_shape : 0; h->pd.plain = h->pf.plain;
     return GEMB200_OK;
   }
   const size_t n = (size_t)h->cfg.n_envs;
@@ -901,6 +901,88 @@ int gemb200_set_env_params(gemb200_handle* h, const double* motor_param, const d
   }
   h->pf.envp = static_cast<const float*>(h->d_envp); h->pd.envp = static_cast<const double*>(h->d_envp);
   h->pf.plain = 0; h->pd.plain = 0;  // the PLAIN instantiations read the shared constant-bank coefficients
+  return GEMB200_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Fused aggregated return over NVLink (the sharded layout's ONE collective, done by the step kernel itself)
+// ----------------------------------------------------------------------------------------------------------------
+// Flags: one uint32 per (slot, source rank), written by the source with a system-scope store after its step kernel has finished (every
+// thread of the step kernel fences its peer stores at system scope before it exits), polled by the owner.
+__global__ void peer_signal_kernel(uint32_t* const* flags, int n, uint32_t value) {
+  const int d = threadIdx.x;
+  if (d < n) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(flags[d]) = value;
+    __threadfence_system();
+  }
+}
+// spins until all n flags are >= value (wrap-safe signed distance); gives up after ~4e9 cycles and raises *err so that a lost peer cannot hang the GPU
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t value, int* err) {
+  const int s = threadIdx.x;
+  if (s < n) {
+    const long long t0 = clock64();
+    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flags + s) - value) < 0) {
+      if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1 + s); break; }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+}
+
+int gemb200_peer_buffer_alloc(int32_t device, int64_t bytes, void** dev_ptr, void* ipc_handle64) {
+  if (!dev_ptr || !ipc_handle64 || bytes <= 0) return fail(GEMB200_E_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaMalloc(dev_ptr, (size_t)bytes));
+  CUDA_TRY(cudaMemset(*dev_ptr, 0, (size_t)bytes));
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, *dev_ptr));
+  std::memcpy(ipc_handle64, &hd, sizeof(hd));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return GEMB200_OK;
+}
+int gemb200_peer_buffer_open(int32_t device, const void* ipc_handle64, void** dev_ptr) {
+  if (!dev_ptr || !ipc_handle64) return fail(GEMB200_E_INVALID, "bad argument");
+  DeviceGuard guard(device);  // the CONSUMER's device is current: the mapping lives in this context and peer access is enabled lazily
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, ipc_handle64, sizeof(hd));
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return GEMB200_OK;
+}
+int gemb200_peer_buffer_close(int32_t device, void* dev_ptr) {
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return GEMB200_OK;
+}
+int gemb200_peer_buffer_free(int32_t device, void* dev_ptr) {
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaFree(dev_ptr));
+  return GEMB200_OK;
+}
+int gemb200_bind_peers(gemb200_handle* h, int32_t n_dst, const int64_t* dst_delta) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  if (n_dst < 0 || n_dst > 8 || (n_dst > 0 && !dst_delta)) return fail(GEMB200_E_INVALID, "n_dst must be in [0, 8]");
+  if (n_dst > 0 && h->cfg.layout != GEMB200_LAYOUT_AOS) return fail(GEMB200_E_INVALID, "peer destinations need the row-per-env (AoS) layout");
+  h->pf.n_dst = n_dst; h->pd.n_dst = n_dst;
+  for (int d = 0; d < n_dst; ++d) { h->pf.dst_delta[d] = dst_delta[d]; h->pd.dst_delta[d] = dst_delta[d]; }
+  // the PLAIN instantiations store to the caller's tensors only
+  h->pf.plain = (n_dst == 0 && !h->pf.envp) ? h->plain_shape : 0;
+  h->pd.plain = h->pf.plain;
+  return GEMB200_OK;
+}
+int gemb200_peer_signal(gemb200_handle* h, int32_t n_dst, uint32_t* const* flag_ptrs_dev, uint32_t value, void* stream) {
+  if (!h || n_dst < 1 || n_dst > 32 || !flag_ptrs_dev) return fail(GEMB200_E_INVALID, "bad argument");
+  DeviceGuard guard(h->cfg.device);
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_ptrs_dev, n_dst, value);
+  CUDA_TRY(cudaGetLastError());
+  return GEMB200_OK;
+}
+int gemb200_peer_wait(gemb200_handle* h, int32_t n_src, const uint32_t* flags_dev, uint32_t value, int32_t* err_dev, void* stream) {
+  if (!h || n_src < 1 || n_src > 32 || !flags_dev || !err_dev) return fail(GEMB200_E_INVALID, "bad argument");
+  DeviceGuard guard(h->cfg.device);
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_dev, n_src, value, err_dev);
+  CUDA_TRY(cudaGetLastError());
   return GEMB200_OK;
 }
 

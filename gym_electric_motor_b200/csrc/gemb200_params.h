@@ -224,6 +224,10 @@ struct StepParams {
   // per-step strides of the rollout's cursors, prepared on the host (elements; 0 for an output that is not requested): action tensor
   // in BYTES per step, obs / ref / reward / terminated slices in elements per recorded step
   int64_t roll_act_inc, roll_obs_inc, roll_ref_inc, roll_rew_inc, roll_term_inc;
+  // ---- fused aggregated return over NVLink (gemb200_bind_peers): destinations of the output stores as byte distances from the caller's
+  //      tensors; 0 destinations = the caller's tensors only ----
+  int32_t n_dst;
+  int64_t dst_delta[8];
 };
 
 }  // namespace gemb200

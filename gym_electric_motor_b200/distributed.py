@@ -167,6 +167,156 @@ class OverlappedGather:
         self.sim._reuse, self.sim._out, self.sim._out_ptrs = self._saved
 
 
+class _RawDeviceBytes:
+    """zero-copy torch view of library-allocated device memory (CUDA array interface)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """The sharded layout's ONE collective fused into the step itself (include/gemb200.h: gemb200_bind_peers): every rank's step kernel stores
+    obs | ref | reward | terminated of its shard straight into section `rank` of EVERY rank's gather buffer over NVLink (peer stores through
+    CUDA-IPC mappings of library-allocated buffers), so no all-gather runs at all; a per-(buffer, source) flag written after the step replaces the
+    collective's synchronisation and a credit flag guards the reuse of the two buffers.
+
+        pg = PeerGather(env.sim, torch.float32)         # collective: exchanges the IPC handles (torch.distributed, any backend)
+        for a in actions: b = pg.step(a)                # step k on the caller's stream; its arrival is awaited on a side stream
+        pg.finish()                                     # caller's stream waits until every outstanding step has arrived from every rank
+        obs, ref, rew, term = pg.views(b)               # [world, n_local, ...] rank-major views of buffer b (valid until 2 more steps)
+    """
+
+    FLAG_BYTES = 4096
+
+    def __init__(self, sim, dtype):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _cabi as K
+
+        self.sim, self.torch, self._lib, self._C = sim, torch, K.load_library(), C
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        if self.world > 8:
+            raise ValueError("PeerGather: at most 8 ranks (one NVLink domain)")
+        self.layout = PackedStepOutputs.__new__(PackedStepOutputs)  # section layout only (no buffers)
+        isz = torch.empty((), dtype=dtype).element_size()
+        lay = self.layout
+        lay.world, lay.n, lay.n_state, lay.n_ref, lay.dtype = self.world, sim.n, sim.n_state, sim.n_ref, dtype
+        sizes = [sim.n * sim.n_state * isz, sim.n * sim.n_ref * isz, sim.n * isz, sim.n]
+        lay.offsets, off = [], 0
+        for sz in sizes:
+            lay.offsets.append(off)
+            off += (sz + 15) // 16 * 16
+        lay.nbytes = self.nbytes = off
+        self.dev = int(sim.device.index)
+        self.total = 2 * self.world * self.nbytes + self.FLAG_BYTES
+        ptr, handle = C.c_void_p(), (C.c_char * 64)()
+        K.check(self._lib.gemb200_peer_buffer_alloc(self.dev, self.total, C.byref(ptr), handle), "gemb200_peer_buffer_alloc")
+        self.own = ptr.value
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw))
+        self.bases, self._opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.bases.append(self.own)
+                continue
+            m = C.c_void_p()
+            hb = (C.c_char * 64).from_buffer_copy(handles[r])
+            K.check(self._lib.gemb200_peer_buffer_open(self.dev, hb, C.byref(m)), "gemb200_peer_buffer_open")
+            self.bases.append(m.value)
+            self._opened.append(m.value)
+        self.buf = torch.as_tensor(_RawDeviceBytes(self.own, self.total), device=sim.device)
+        flag0 = 2 * self.world * self.nbytes
+        # flag pointer tables (device): for buffer b, the address of ready[b][rank] / credit[b][rank] in every rank's buffer
+        def table(kind, b):
+            off_ = flag0 + kind * 1024 + (b * self.world + self.rank) * 4
+            return torch.tensor([base + off_ for base in self.bases], dtype=torch.int64, device=sim.device)
+
+        self._ready_tab = [table(0, b) for b in range(2)]
+        self._credit_tab = [table(1, b) for b in range(2)]
+        self._ready_local = [self.own + flag0 + b * self.world * 4 for b in range(2)]
+        self._credit_local = [self.own + flag0 + 1024 + b * self.world * 4 for b in range(2)]
+        self.err = torch.zeros(1, dtype=torch.int32, device=sim.device)
+        self.side = torch.cuda.Stream(device=sim.device)
+        self._arrived = [None, None]
+        self.k = 0
+        self._saved = (sim._reuse, sim._out, getattr(sim, "_out_ptrs", None))
+        self._local = []
+        for b in range(2):
+            base = (b * self.world + self.rank) * self.nbytes
+            self._local.append(lay._views(self.buf, base))
+        delta = (C.c_int64 * self.world)(*[base - self.own for base in self.bases])
+        K.check(self._lib.gemb200_bind_peers(sim._h, self.world, delta), "gemb200_bind_peers")
+        if self.world > 1:
+            dist.barrier()  # every rank has mapped every buffer before the first peer store
+
+    def _vp(self, x):
+        return self._C.c_void_p(int(x))
+
+    def step(self, action):
+        torch, K_ = self.torch, self.k + 1
+        b = self.k % 2
+        sim, cur = self.sim, torch.cuda.current_stream(self.sim.device)
+        from . import _cabi as K
+
+        if K_ > 2:  # buffer b still holds step K_ - 2: every rank must have consumed it
+            K.check(self._lib.gemb200_peer_wait(sim._h, self.world, self._vp(self._credit_local[b]), K_ - 2, self._vp(self.err.data_ptr()), self._vp(cur.cuda_stream)),
+                    "gemb200_peer_wait")
+        sim._reuse, sim._out, sim._out_ptrs = True, self._local[b], None
+        sim.step(action)
+        K.check(self._lib.gemb200_peer_signal(sim._h, self.world, self._vp(self._ready_tab[b].data_ptr()), K_, self._vp(cur.cuda_stream)), "gemb200_peer_signal")
+        # consumer side: await the arrival of step K_ from every rank, then hand the buffer back
+        with torch.cuda.stream(self.side):
+            K.check(self._lib.gemb200_peer_wait(sim._h, self.world, self._vp(self._ready_local[b]), K_, self._vp(self.err.data_ptr()), self._vp(self.side.cuda_stream)),
+                    "gemb200_peer_wait")
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            K.check(self._lib.gemb200_peer_signal(sim._h, self.world, self._vp(self._credit_tab[b].data_ptr()), K_, self._vp(self.side.cuda_stream)), "gemb200_peer_signal")
+        self._arrived[b] = ev
+        self.k += 1
+        return b
+
+    def finish(self):
+        cur = self.torch.cuda.current_stream(self.sim.device)
+        for ev in self._arrived:
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def check(self):
+        """host-side check of the flag protocol's time-out indicator (synchronises)"""
+        self.torch.cuda.synchronize(self.sim.device)
+        e = int(self.err.item())
+        if e:
+            raise RuntimeError(f"PeerGather: rank {self.rank} gave up waiting for the flag of rank {e - 1}")
+
+    def views(self, b):
+        per = [self.layout._views(self.buf, (b * self.world + r) * self.nbytes) for r in range(self.world)]
+        return tuple(self.torch.stack([p[k] for p in per]) for k in range(4))
+
+    def release(self):
+        import torch.distributed as dist
+
+        from . import _cabi as K
+
+        self.finish()
+        self.torch.cuda.synchronize(self.sim.device)
+        K.check(self._lib.gemb200_bind_peers(self.sim._h, 0, None), "gemb200_bind_peers")
+        self.sim._reuse, self.sim._out, self.sim._out_ptrs = self._saved
+        if self.world > 1:
+            dist.barrier()  # nobody stores into a buffer that is about to be unmapped
+        for m in self._opened:
+            self._lib.gemb200_peer_buffer_close(self.dev, self._vp(m))
+        self._opened = []
+        if self.world > 1:
+            dist.barrier()
+        del self.buf
+        self._lib.gemb200_peer_buffer_free(self.dev, self._vp(self.own))
+
+
 def all_gather_batch(*tensors):
     """Optional single all-gather of per-rank [n_local, ...] tensors into global [N, ...] tensors (same n_local on every
     rank).  For PMSM at N=2^20 this moves ~72 MB per step — several times the step itself; data-parallel

@@ -335,6 +335,23 @@ int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream);
  * Takes effect from the next reset / step; synchronises the device. */
 int gemb200_set_env_params(gemb200_handle* h, const double* motor_param, const double* load_param);
 
+/* Fused aggregated return of the sharded layout (one process per GPU, SURVEY.md §8e: the ONE collective of the north star, done by the
+ * step kernel itself instead of a separate NCCL all-gather).  Every rank owns a gather buffer (gemb200_peer_buffer_alloc: cudaMalloc +
+ * IPC handle) of world sections; the ranks exchange the 64-byte handles out of band and map each other's buffers
+ * (gemb200_peer_buffer_open: cudaIpcOpenMemHandle with the consumer's device current, peer access enabled lazily).  After
+ * gemb200_bind_peers(h, world, delta) every step launch stores obs / ref / reward / terminated not only into the caller's tensors (which
+ * must be this rank's section of its OWN buffer) but also at the same byte offset + delta[d] — i.e. into this rank's section of every
+ * destination d — over NVLink, and fences the stores at system scope.  gemb200_peer_signal (flag store after the step, stream-ordered)
+ * and gemb200_peer_wait (polls local flags; gives up after ~2 s and reports through *err_dev instead of hanging) are the flag protocol
+ * that replaces the collective's synchronisation.  n_dst = 0 unbinds.  Row-per-env (AoS) layout only. */
+int gemb200_peer_buffer_alloc(int32_t device, int64_t bytes, void** dev_ptr, void* ipc_handle64);
+int gemb200_peer_buffer_open(int32_t device, const void* ipc_handle64, void** dev_ptr);
+int gemb200_peer_buffer_close(int32_t device, void* dev_ptr);
+int gemb200_peer_buffer_free(int32_t device, void* dev_ptr);
+int gemb200_bind_peers(gemb200_handle* h, int32_t n_dst, const int64_t* dst_delta);
+int gemb200_peer_signal(gemb200_handle* h, int32_t n_dst, uint32_t* const* flag_ptrs_dev, uint32_t value, void* stream);
+int gemb200_peer_wait(gemb200_handle* h, int32_t n_src, const uint32_t* flags_dev, uint32_t value, int32_t* err_dev, void* stream);
+
 /* Opaque checkpoint of everything a handle owns (ODE state, switching state, reference state, step counter):
  * size query, export to / import from a HOST blob.  The blob starts with a header (magic, ABI version, dtype, n_envs, record layout,
  * fingerprint of the configuration); gemb200_checkpoint_load refuses a blob written by a handle of another configuration
