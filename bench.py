@@ -415,7 +415,7 @@ def main():
 
     # ---------------- N > 1 only: the sharded layout's ONE collective — a single NCCL all-gather of the packed (obs, ref, reward,
     # terminated) buffer after every step, double-buffered so that gather(k) overlaps step(k+1) ----------------
-    ms_gather, gather_bytes = None, 0
+    ms_gather, gather_bytes, ms_peer, peer_error = None, 0, None, None
     if world > 1 and not wl.mixed:
         from gym_electric_motor_b200.distributed import OverlappedGather
 
@@ -436,6 +436,28 @@ def main():
         barrier()
         ms_gather = g0.elapsed_time(g1)
         og.release()
+        # the same aggregated return FUSED into the step: the kernel stores its outputs into every rank's gather buffer over NVLink
+        # (distributed.PeerGather, gemb200_bind_peers) — no collective call, a flag per (buffer, source) instead
+        try:
+            from gym_electric_motor_b200.distributed import PeerGather
+
+            pg = PeerGather(sim, torch.float32)
+            for k in range(3):
+                pg.step(pool[k % 8])
+            pg.finish()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for k in range(K):
+                pg.step(pool[k % 8])
+            pg.finish()
+            p1.record()
+            barrier()
+            ms_peer = p0.elapsed_time(p1)
+            pg.check()
+            pg.release()
+        except Exception as exc:  # e.g. CUDA IPC not permitted in this container: keep the NCCL figure, say why
+            ms_peer, peer_error = None, f"{type(exc).__name__}: {exc}"[:300]
 
     # ---------------- e2e arm: host buffers through the C-ABI ----------------
     ms_e2e, ke, h2d, d2h = None, 0, 0, 0
@@ -481,14 +503,14 @@ def main():
             torch.cuda.empty_cache()
     clocks = sampler.stop() if rank == 0 else None
 
-    vals = [ms, ms_last, ms_step or 0.0, ms_gather or 0.0, ms_e2e or 0.0] + [others[k][0] for k in sorted(others)]
+    vals = [ms, ms_last, ms_step or 0.0, ms_gather or 0.0, ms_e2e or 0.0, ms_peer or 0.0] + [others[k][0] for k in sorted(others)]
     t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     vals = [float(x) for x in t.tolist()]
-    ms, ms_last, ms_step, ms_gather, ms_e2e = vals[:5]
+    ms, ms_last, ms_step, ms_gather, ms_e2e, ms_peer = vals[:6]
     for i, k in enumerate(sorted(others)):
-        others[k] = (vals[5 + i],) + others[k][1:]
+        others[k] = (vals[6 + i],) + others[k][1:]
     if rank == 0:
         total_envs = n * world
         ms_per_step = ms / K
@@ -524,11 +546,19 @@ def main():
             line["e2e"] = {"value": total_envs * ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
                            "ms_per_step": ms_e2e / ke, "api": "gemb200_step_host via VectorSim.step_host_ptr (NUMA-local pinned host buffers)"}
         if world > 1 and ms_gather:
-            line["with_all_gather"] = {"value": total_envs * K / (ms_gather * 1e-3), "unit": UNIT, "ms_per_step": ms_gather / K,
-                                       "bytes_per_rank_per_step": gather_bytes,
-                                       "note": "every step followed by ONE NCCL all_gather_into_tensor of the packed (obs, ref, reward, terminated) buffer the "
-                                               "kernel writes into, double-buffered on a side stream so that gather(k) overlaps step(k+1); `value` above is the "
-                                               "sharded layout without it (rank-local consumers)"}
+            best = min(ms_gather, ms_peer) if ms_peer else ms_gather
+            line["with_all_gather"] = {"value": total_envs * K / (best * 1e-3), "unit": UNIT, "ms_per_step": best / K,
+                                       "bytes_per_rank_per_step": gather_bytes, "ingress_GBps_per_gpu": (world - 1) * gather_bytes / (best / K * 1e-3) / 1e9,
+                                       "how": "peer_store" if (ms_peer and ms_peer <= ms_gather) else "nccl_overlapped",
+                                       "nccl_overlapped": {"value": total_envs * K / (ms_gather * 1e-3), "ms_per_step": ms_gather / K,
+                                                           "note": "every step followed by ONE NCCL all_gather_into_tensor of the packed (obs, ref, reward, "
+                                                                   "terminated) buffer the kernel writes into, double-buffered on a side stream: gather(k) "
+                                                                   "overlaps step(k+1)"},
+                                       "peer_store": ({"value": total_envs * K / (ms_peer * 1e-3), "ms_per_step": ms_peer / K,
+                                                       "note": "fused step + gather: the step kernel stores obs / ref / reward / terminated into every rank's "
+                                                               "gather buffer over NVLink (gemb200_bind_peers), flags instead of a collective call"}
+                                                      if ms_peer else {"unavailable": peer_error}),
+                                       "note": "`value` above is the sharded layout without the aggregated return (rank-local consumers)"}
         if others:
             line["other_configs"] = {}
             for name, (m2, k2, l2, n2) in others.items():

@@ -51,6 +51,8 @@ enum : uint32_t {
   kStreamInitState = 7, kStreamInitState2 = 8,                // random initial ODE state
   kStreamSwitch = 10, kStreamSwitchR = 14,                    // + slot: SwitchedReferenceGenerator super-episode (R: at a reset)
   kStreamSupply = 9,                                          // AC supply phase at reset
+  kStreamWalk2 = 4,                                           // walk increments of envs with <= 2 reference slots: ONE block serves two
+                                                              //   consecutive call ids (counter words 0,1 = id >> 1, word pair = id & 1)
   kStreamLaplace = 24, kStreamLaplaceR = 28,                  // Laplace walk increments (R: right after an in-kernel auto-reset)
   kStreamPeriodic = 32,                                       // + 2*slot (+1): sub-episode parameters of the periodic generators,
                                                               //   counter word 0 = step index of the sub-episode start
@@ -62,7 +64,7 @@ enum : uint32_t {
 constexpr bool streams_disjoint() {
   constexpr uint32_t r[][2] = {{kStreamWalk, 1}, {kStreamSubep, 1}, {kStreamInit, 1}, {kStreamWalkR, 1}, {kStreamSubepR, 1}, {kStreamInitState, 1}, {kStreamInitState2, 1},
                                {kStreamSupply, 1}, {kStreamSwitch, kMaxRef}, {kStreamSwitchR, kMaxRef}, {kStreamSubepHi, 1}, {kStreamSubepHiR, 1}, {kStreamLaplace, 1},
-                               {kStreamLaplaceR, 1}, {kStreamPeriodic, 2 * kMaxRef}, {kStreamNoise, 8 * kMaxStateOps}, {kStreamNoiseR, 8 * kMaxStateOps}};
+                               {kStreamLaplaceR, 1}, {kStreamWalk2, 1}, {kStreamPeriodic, 2 * kMaxRef}, {kStreamNoise, 8 * kMaxStateOps}, {kStreamNoiseR, 8 * kMaxStateOps}};
   constexpr int n = sizeof(r) / sizeof(r[0]);
   for (int a = 0; a < n; ++a)
     for (int b = a + 1; b < n; ++b)

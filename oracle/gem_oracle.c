@@ -110,6 +110,7 @@ enum { STREAM_WALK = 1, STREAM_SUBEP = 2, STREAM_INIT = 3, STREAM_SUBEP_HI = 18,
        STREAM_WALK_R = 5, STREAM_SUBEP_R = 6, STREAM_SUBEP_HI_R = 22 /* _R: draws right after a reset */,
        STREAM_SWITCH = 10, STREAM_SWITCH_R = 14 /* + slot: SwitchedReferenceGenerator super-episodes (R: at a reset) */,
        STREAM_INIT_STATE = 7, STREAM_INIT_STATE2 = 8 /* random initial ODE state */, STREAM_SUPPLY = 9 /* AC supply phase */, /* induction motors: eps_mag = word 2 of STREAM_INIT_STATE2 */ STREAM_LAPLACE = 24, STREAM_LAPLACE_R = 28 /* Laplace walk increments */,
+       STREAM_WALK2 = 4 /* walk increments with <= 2 reference slots: one block per TWO call ids (counter = id >> 1, word pair = id & 1) */,
        STREAM_PERIODIC = 32 /* + 2*slot (+1): sub-episode parameters of the periodic generators, counter word 0 = start step */,
        STREAM_NOISE = 64 /* + 8*op + (state >> 2): StateNoiseProcessor */, STREAM_NOISE_R = 128 /* ... right after an auto-reset */ };
 
@@ -1167,7 +1168,19 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
       double u = u01(rlap[r]);
       z = u < 0.5 ? log(2.0 * u) : -log(2.0 * (1.0 - u));
     } else {
-      if (!have_w) { rng4(o, idx, after_reset ? STREAM_WALK_R : STREAM_WALK, rw); have_w = 1; }
+      if (!have_w) {
+        if (o->n_ref <= 2 && !after_reset) { /* the device serves two consecutive steps from one Philox block (gemb200_kernels.cuh: WalkCache) */
+          uint32_t blk[4];
+          const uint64_t g = (uint64_t)(idx + c->env_index_offset), id = o->gstep >> 1;
+          blk[0] = (uint32_t)id; blk[1] = (uint32_t)(id >> 32); blk[2] = (uint32_t)g; blk[3] = ((uint32_t)(g >> 32) << 8) | STREAM_WALK2;
+          philox4x32_10(blk, (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
+          const int odd = (int)(o->gstep & 1);
+          rw[0] = blk[2 * odd]; rw[1] = blk[2 * odd + 1]; rw[2] = 0; rw[3] = 0;
+        } else {
+          rng4(o, idx, after_reset ? STREAM_WALK_R : STREAM_WALK, rw);
+        }
+        have_w = 1;
+      }
       /* Box-Muller: slots (0,1) from words (0,1), slots (2,3) from words (2,3) */
       double u1 = u01(rw[2 * (r >> 1)]), u2 = u01(rw[2 * (r >> 1) + 1]);
       double rad = sqrt(-2.0 * log(u1));
