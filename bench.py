@@ -315,6 +315,13 @@ class Workload:
         self.env.close()
 
 
+def gate(torch):
+    """Keep the GPU busy for ~0.15 ms right before a timed region starts: the start event is recorded BEHIND this spin kernel, so the host
+    has queued the timed launches by the time the event fires and the event-to-event time is device time of the K steps only — no host
+    launch latency inside (at 0.4 ms per 20-step launch a 15 us submission gap would be 4 %; it also differs per rank under torchrun)."""
+    torch.cuda._sleep(300000)
+
+
 def time_rollout(wl, K, W, barrier, torch):
     wl.rollout(ROLL_MAX)  # untimed: every slice of the output buffers has been written once before the timed region
     wl.steps(max(W, 3))
@@ -322,6 +329,7 @@ def time_rollout(wl, K, W, barrier, torch):
     l0 = wl.launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    gate(torch)
     ev0.record()
     wl.steps(K)
     ev1.record()
@@ -384,6 +392,7 @@ def main():
     wl.steps(3, every=0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gate(torch)
     e0.record()
     wl.steps(K, every=0)
     e1.record()
@@ -403,6 +412,7 @@ def main():
         barrier()
         l0 = sum(e.sim.launch_count for e in envs)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gate(torch)
         s0.record()
         for k in range(K):
             envs[k % R].step(pool[k % 8])
@@ -428,6 +438,7 @@ def main():
         og.finish()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gate(torch)
         g0.record()
         for k in range(K):
             og.step(pool[k % 8])
@@ -447,6 +458,7 @@ def main():
             pg.finish()
             barrier()
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gate(torch)
             p0.record()
             for k in range(K):
                 pg.step(pool[k % 8])
