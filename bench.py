@@ -363,9 +363,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     from gym_electric_motor_b200 import hostmem
 
-    hostmem.bind_to_device_numa_node(local_rank)  # pinned buffers of the e2e arm must sit on the GPU's NUMA node (first touch follows the thread)
-    torch.cuda.set_device(local_rank)
+    torch.cuda.set_device(local_rank)  # first: nothing may create a context on device 0 from the other ranks
     dev = torch.device("cuda", local_rank)
+    hostmem.bind_to_device_numa_node(local_rank)  # pinned buffers of the e2e arm must sit on the GPU's NUMA node (first touch follows the thread)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)

@@ -376,3 +376,10 @@ def test_reference_generator_and_reward_function_can_be_replaced():
         env.reference_generator = object()
     with pytest.raises(TypeError):
         env.reward_function = lambda *a: 0.0
+
+
+def test_scalar_env_refuses_field_major_layout():
+    """the scalar contract (num_envs=None) returns one row per step, which only exists in the row-per-env layout"""
+    with pytest.raises(ValueError, match="layout='soa' needs a batched environment"):
+        gem.make("Cont-CC-PMSM-v0", layout="soa")
+    assert gem.make("Cont-CC-PMSM-v0", layout="soa", num_envs=4).build_config().layout == K.LAYOUT_SOA

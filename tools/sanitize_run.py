@@ -41,13 +41,23 @@ CASES = [
                                                                                  rg.SinusoidalReferenceGenerator(reference_state="omega"),
                                                                                  rg.StepReferenceGenerator(reference_state="omega")], super_episode_length=(2, 5)))),
     ("Cont-TC-SeriesDc-v0", dict(ode_solver=RK4(), reference_generator=rg.LaplaceProcessReferenceGenerator(reference_state="torque"))),
+    # round 2
+    ("Cont-SC-SCIM-v0", dict(ode_solver=RK4(), motor=dict(motor_initializer=dict(random_init="uniform")), load=dict(load_initializer=dict(random_init="uniform", interval=[[-50.0, 120.0]])))),
+    ("Finite-CC-ExtExDc-v0", dict(ode_solver=RK4(), converter=ps.FiniteMultiConverter([ps.FiniteFourQuadrantConverter(interlocking_time=1e-6),
+                                                                                         ps.FiniteFourQuadrantConverter(interlocking_time=2.5e-6)]))),
+    ("Cont-CC-ExtExDc-v0", dict(ode_solver=RK4(), physical_system_wrappers=[psw.CurrentSumProcessor(currents=["i_a", "i_e"], limit="sum")])),
+    ("Cont-SC-PMSM-v0", dict(ode_solver=RK4(), _env_params=True)),
 ]
 if os.environ.get("SANITIZE_CASES"):  # e.g. "0,1,5,7" for the slower racecheck tool
     CASES = [CASES[int(k)] for k in os.environ["SANITIZE_CASES"].split(",")]
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(0)
 for env_id, kw in CASES:
+    kw = dict(kw)
+    env_params = kw.pop("_env_params", False)
     env = gem.make(env_id, num_envs=N, autoreset="same_step", seed=1, **kw)
+    if env_params:  # per-env parameter blocks (ENVP instantiation)
+        env.set_env_parameters(motor_parameter=dict(r_s=np.linspace(15e-3, 25e-3, N), psi_p=np.linspace(0.15, 0.19, N)), load_parameter=dict(j_load=np.linspace(1e-4, 3e-4, N)))
     env.reset()
     sp = env.action_space
     for k in range(6):
@@ -61,6 +71,12 @@ for env_id, kw in CASES:
         if env.sim.soa:
             a = a.T.contiguous()
         (obs, ref), rew, term, _, _ = env.step(a)
+    if not env.sim.soa:  # fused rollout: 5 steps in one launch, every step recorded, then 3 with only the last one
+        acts = torch.stack([a] * 5).contiguous()
+        (st, rf), rw_, tm = env.rollout(acts, record_every=1)
+        env.rollout(acts[:3], record_every=0)
+        assert torch.isfinite(st).all()
+    env.reset(seed=3)  # gemb200_reseed
     env.reset(mask=torch.ones(N, dtype=torch.uint8, device=dev))
     sd = env.state_dict()
     env.load_state_dict(sd)
