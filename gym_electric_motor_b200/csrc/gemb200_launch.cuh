@@ -4,6 +4,8 @@
 // (family, real) pair is compiled in its own translation unit (gemb200_step_tu.cu with -DGEMB200_TU_FAM / -DGEMB200_TU_REAL) so that
 // the library builds in parallel.  gemb200.cu only sees the declarations below.
 #pragma once
+#include <cstdlib>
+
 #include "gemb200_kernels.cuh"
 
 namespace gemb200 {
@@ -15,23 +17,36 @@ template <int FAM, typename real> cudaError_t launch_reset_f(int nref, const Ste
 #ifdef GEMB200_TU_FAM
 constexpr int kBlock = GEMB200_BLOCK;
 
+// Block size of a launch: kBlock (128) threads, or — for batches too small to give every SM its share of 128-thread blocks — 64 or 32, so that
+// the blocks spread evenly (N = 65 536: 512 blocks of 128 threads are 3.46 per SM, i.e. a 4-vs-3 imbalance; 2048 blocks of 32 are 13.8).  The
+// kernels index with blockDim.x, so the choice is a launch parameter.  GEMB200_BLOCK_RT=<32|64|128> overrides (experiments).
+static int pick_block(int range) {
+  static const int forced = [] { const char* e = std::getenv("GEMB200_BLOCK_RT"); return e ? std::atoi(e) : 0; }();
+  if (forced == 32 || forced == 64 || forced == 128) return forced;
+  static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+  int block = kBlock;
+  while (block > 32 && (range + block - 1) / block < sms * 8) block >>= 1;
+  return block;
+}
+
 template <int FAM, bool FINITE, typename real, int NREF, bool SOA, bool PLAIN = false, bool MECH = false>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
-  const size_t smem = (size_t)kBlock * (size_t)p.row_stride * sizeof(real);
   const int range = p.env_end - p.env_begin;
-  const int grid = (range + kBlock - 1) / kBlock;
+  const int block = pick_block(range);
+  const size_t smem = (size_t)block * (size_t)p.row_stride * sizeof(real);
+  const int grid = (range + block - 1) / block;
   if constexpr (!PLAIN) {
     if (p.envp) {  // per-env parameter blocks: the ENVP instantiation of the general kernel (row-per-env I/O layout only, checked by the host)
       if constexpr (SOA) return cudaErrorInvalidValue;
       else {
-      if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, false, false, true><<<grid, kBlock, smem, st>>>(p);
-      else step_kernel<FAM, FINITE, real, NREF, SOA, false, false, true><<<grid, kBlock, smem, st>>>(p);
+      if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, false, false, true><<<grid, block, smem, st>>>(p);
+      else step_kernel<FAM, FINITE, real, NREF, SOA, false, false, true><<<grid, block, smem, st>>>(p);
       return cudaGetLastError();
       }
     }
   }
-  if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);
-  else step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, kBlock, smem, st>>>(p);
+  if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, block, smem, st>>>(p);
+  else step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, block, smem, st>>>(p);
   return cudaGetLastError();
 }
 // PLAIN instantiations (fp32): {cont, finite} x {constant speed, integrating load} x {AoS, SoA}
