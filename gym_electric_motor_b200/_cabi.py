@@ -7,7 +7,7 @@ or cannot be loaded, `load_library()` raises — the product path never routes t
 import ctypes as C
 import os
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_STATE, MAX_ODE, MAX_ACT, MAX_REF, MAX_CONSTRAINTS, MAX_MOTOR_PARAM, MAX_STATE_OPS = 28, 8, 6, 4, 4, 16, 4
 MAX_REF_ENTRIES = 12  # generator parameter entries: output slots + switched sub-generators
 
@@ -144,7 +144,7 @@ SYMBOLS = [
     "gemb200_version", "gemb200_last_error", "gemb200_config_init", "gemb200_query_dims", "gemb200_create",
     "gemb200_destroy", "gemb200_reset", "gemb200_step", "gemb200_step_host", "gemb200_reset_host", "gemb200_rollout", "gemb200_rollout_record",
     "gemb200_get_ode_state", "gemb200_set_ode_state", "gemb200_get_reference", "gemb200_set_reference",
-    "gemb200_reseed", "gemb200_set_env_params", "gemb200_peer_buffer_alloc", "gemb200_peer_buffer_open", "gemb200_peer_buffer_close",
+    "gemb200_reseed", "gemb200_set_device_clock", "gemb200_get_clock", "gemb200_set_env_params", "gemb200_peer_buffer_alloc", "gemb200_peer_buffer_open", "gemb200_peer_buffer_close",
     "gemb200_peer_buffer_free", "gemb200_bind_peers", "gemb200_peer_signal", "gemb200_peer_wait", "gemb200_checkpoint_size", "gemb200_checkpoint_save", "gemb200_checkpoint_load", "gemb200_launch_count",
     "gemb200_kernel_time_begin", "gemb200_kernel_time_end",
 ]
@@ -193,6 +193,8 @@ def load_library():
     lib.gemb200_get_reference.argtypes = [vp, vp, vp]
     lib.gemb200_set_reference.argtypes = [vp, vp, vp]
     lib.gemb200_reseed.argtypes = [vp, C.c_uint64, vp]
+    lib.gemb200_set_device_clock.argtypes = [vp, C.c_int32, vp]
+    lib.gemb200_get_clock.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]
     lib.gemb200_set_env_params.argtypes = [vp, vp, vp]
     lib.gemb200_peer_buffer_alloc.argtypes = [C.c_int32, C.c_int64, C.POINTER(vp), vp]
     lib.gemb200_peer_buffer_open.argtypes = [C.c_int32, vp, C.POINTER(vp)]

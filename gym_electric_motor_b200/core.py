@@ -287,6 +287,13 @@ class ElectricMotorEnvironment(_EnvBase):
             obs = obs.index_select(dim, self._filter_index)
         return (obs, ref), reward, terminated.view(torch.bool)
 
+    def capture_steps(self, policy, n_steps, record=False, warmup=1):
+        """`n_steps` closed-loop steps — action = policy(state, reference); env.step(action) — captured ONCE in a CUDA graph (graph.py);
+        `.replay()` of the returned object runs them with a single call.  Batched mode only."""
+        from .graph import CapturedSteps
+
+        return CapturedSteps(self, policy, n_steps, record=record, warmup=warmup)
+
     _MP_SLOT = dict(p=K.MP_P, r_s=K.MP_R_S, l_d=K.MP_L_D, l_q=K.MP_L_Q, psi_p=K.MP_PSI_P, j_rotor=K.MP_J_ROTOR, r_a=K.MP_R_A, l_a=K.MP_L_A, psi_e=K.MP_PSI_E,
                     r_e=K.MP_R_E, l_e=K.MP_L_E, l_e_prime=K.MP_L_E_PRIME, l_m=K.MP_L_M, k=K.MP_K, l_sigs=K.MP_L_SIGS, l_sigr=K.MP_L_SIGR, r_r=K.MP_R_E)
     _LP_SLOT = dict(a=K.LP_A, b=K.LP_B, c=K.LP_C, j_load=K.LP_J_LOAD)

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,8 @@ struct gemb200_handle {
   uint64_t gstep = 0;
   uint64_t n_steps = 0;  // step calls so far (dead-time ring position)
   uint64_t ext_hash = 0; // FNV-1a of the external speed profile table (part of the checkpoint fingerprint)
+  uint32_t* d_clock = nullptr;  // device-resident clock (gemb200_set_device_clock): {call id lo, hi, step count lo, ring position, step count hi, -, -, -}
+  bool dev_clock = false;       // launches read d_clock instead of gstep / n_steps (which are then stale until the clock is pulled back)
   int64_t launches = 0;
   // host-buffer path
   cudaStream_t hstream = nullptr;
@@ -494,6 +497,12 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
     for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r] && c.ref_sw_count[r] <= 1;
+    // PLAIN monitor, branch-free: word offsets of the (at most) two limit-checked states and the two states of the squared constraint in the
+    // staged row; an unused check compares entry 0 with +inf
+    const real inf = std::numeric_limits<real>::infinity();
+    for (int q = 0; q < 2; ++q) { p->mon_off[q] = p->n_lim > q ? p->lim_idx[q] * (int)sizeof(real) : 0; p->mon_thr[q] = p->n_lim > q ? real(1) : inf; }
+    for (int q = 0; q < 2; ++q) p->mon_off[2 + q] = (p->n_sq > 0 && p->sq_cnt[0] == 2) ? p->sq_idx[0][q] * (int)sizeof(real) : 0;
+    p->mon_thr[2] = p->n_sq > 0 ? real(1) : inf;
     const char* off = std::getenv("GEMB200_NO_PLAIN");
     p->plain = plain && !(off && off[0] == '1');
     const_cast<gemb200_handle*>(h)->plain_shape = p->plain;
@@ -604,11 +613,41 @@ static cudaError_t launch_reset(int fam, int nref, const StepParams<real>& p, cu
 template <typename real>
 static void set_roll_strides(const gemb200_handle* h, StepParams<real>& p) {
   const int64_t n = h->cfg.n_envs;
+  p.out_has = (p.obs ? 1 : 0) | ((p.ref_out && h->n_ref > 0) ? 2 : 0) | (p.reward ? 4 : 0) | (p.term ? 8 : 0);
   p.roll_act_inc = n * h->n_act * (int64_t)(h->cfg.finite ? sizeof(int32_t) : sizeof(real));
-  p.roll_obs_inc = p.obs ? n * h->n_obs : 0;
-  p.roll_ref_inc = p.ref_out ? n * h->n_ref : 0;
-  p.roll_rew_inc = p.reward ? n : 0;
+  p.roll_obs_inc = p.obs ? n * h->n_obs * (int64_t)sizeof(real) : 0;
+  p.roll_ref_inc = p.ref_out ? n * h->n_ref * (int64_t)sizeof(real) : 0;
+  p.roll_rew_inc = p.reward ? n * (int64_t)sizeof(real) : 0;
   p.roll_term_inc = p.term ? n : 0;
+}
+
+// ---- device-resident clock: the call id of the NEXT call, the step count and the dead-time ring position live in device memory and are
+// advanced by a one-thread kernel behind every launch, so that a launch depends on nothing the host changes between calls (CUDA graphs)
+__global__ void clock_tick_kernel(uint32_t* c, uint32_t d_call, uint32_t d_step, uint32_t dead_steps) {
+  const uint64_t g = (((uint64_t)c[1] << 32) | c[0]) + d_call, s = (((uint64_t)c[4] << 32) | c[2]) + d_step;
+  c[0] = (uint32_t)g; c[1] = (uint32_t)(g >> 32); c[2] = (uint32_t)s; c[4] = (uint32_t)(s >> 32);
+  c[3] = dead_steps ? (uint32_t)(s % dead_steps) : 0u;
+}
+static int push_clock(gemb200_handle* h, cudaStream_t st) {  // host counters -> device (stream-ordered; the source is a by-value kernel argument)
+  const uint64_t g1 = h->gstep + 1, s = h->n_steps;
+  const uint32_t dead = (uint32_t)h->cfg.dead_time_steps;
+  const uint32_t v[8] = {(uint32_t)g1, (uint32_t)(g1 >> 32), (uint32_t)s, dead ? (uint32_t)(s % dead) : 0u, (uint32_t)(s >> 32), 0u, 0u, 0u};
+  CUDA_TRY(cudaMemcpyAsync(h->d_clock, v, sizeof(v), cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+  return GEMB200_OK;
+}
+static int pull_clock(gemb200_handle* h, cudaStream_t st) {  // device -> host counters (synchronises the stream)
+  uint32_t v[8];
+  CUDA_TRY(cudaMemcpyAsync(v, h->d_clock, sizeof(v), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  h->gstep = ((((uint64_t)v[1]) << 32) | v[0]) - 1;
+  h->n_steps = (((uint64_t)v[4]) << 32) | v[2];
+  return GEMB200_OK;
+}
+static int tick_clock(gemb200_handle* h, uint32_t d_call, uint32_t d_step, cudaStream_t st) {
+  clock_tick_kernel<<<1, 1, 0, st>>>(h->d_clock, d_call, d_step, (uint32_t)h->cfg.dead_time_steps);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GEMB200_OK;
 }
 
 // One launch over envs [begin, end) (end < 0: all).  new_call: this launch starts a new API call (fresh RNG call ids);
@@ -618,23 +657,26 @@ static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, 
                    int begin = 0, int end = -1, bool new_call = true, int roll = 0, int every = 0) {
   if (!action) return fail(GEMB200_E_INVALID, "action is NULL");
   const uint64_t ksteps = roll > 0 ? (uint64_t)roll : 1;
-  if (new_call) { h->gstep += ksteps; h->n_steps += ksteps; }
+  const bool dev_clock = h->dev_clock;
+  if (dev_clock && (!new_call || begin != 0 || (end >= 0 && end != h->cfg.n_envs)))
+    return fail(GEMB200_E_INVALID, "the host-buffer step is not available while the device-resident clock is enabled");
+  if (new_call && !dev_clock) { h->gstep += ksteps; h->n_steps += ksteps; }
   const uint64_t g0 = h->gstep - (ksteps - 1), n0 = h->n_steps - (ksteps - 1);  // call id / step count of the FIRST step of this launch
   if (end < 0) end = h->cfg.n_envs;
   const int fifo_slot = h->cfg.dead_time_steps > 0 ? (int)((n0 - 1) % (uint64_t)h->cfg.dead_time_steps) : 0;
   cudaError_t e;
   if (h->cfg.dtype == GEMB200_F32) {
     StepParams<float>& p = h->pf;
-    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)n0;
-    p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32);
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = dev_clock ? 1u : (uint32_t)n0;
+    p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32); p.clock_dev = dev_clock ? h->d_clock : nullptr;
     p.roll_steps = roll; p.record_every = every;
     p.action = action; p.obs = (float*)obs; p.ref_out = (float*)ref; p.reward = (float*)rew; p.term = term;
     set_roll_strides(h, p);
     e = launch_step<float>(h->fam, h->cfg.finite != 0, h->n_ref, p, st);
   } else {
     StepParams<double>& p = h->pd;
-    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = (uint32_t)n0;
-    p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32);
+    p.env_begin = begin; p.env_end = end; p.fifo_slot = fifo_slot; p.kstep = dev_clock ? 1u : (uint32_t)n0;
+    p.gstep_lo = (uint32_t)g0; p.gstep_hi = (uint32_t)(g0 >> 32); p.clock_dev = dev_clock ? h->d_clock : nullptr;
     p.roll_steps = roll; p.record_every = every;
     p.action = action; p.obs = (double*)obs; p.ref_out = (double*)ref; p.reward = (double*)rew; p.term = term;
     set_roll_strides(h, p);
@@ -642,27 +684,31 @@ static int do_step(gemb200_handle* h, const void* action, void* obs, void* ref, 
   }
   if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string(roll > 0 ? "rollout launch: " : "step launch: ") + cudaGetErrorString(e));
   h->launches += 1;
+  if (dev_clock) return tick_clock(h, (uint32_t)ksteps, (uint32_t)ksteps, st);
   return GEMB200_OK;
 }
 
 static int do_reset(gemb200_handle* h, const uint8_t* mask, void* obs, void* ref, cudaStream_t st) {
-  h->gstep += 1;
+  const bool dev_clock = h->dev_clock;
+  if (!dev_clock) h->gstep += 1;
+  h->pf.clock_dev = h->pd.clock_dev = dev_clock ? h->d_clock : nullptr;
   cudaError_t e;
   if (h->cfg.dtype == GEMB200_F32) {
     StepParams<float>& p = h->pf;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
-    p.reset_mask = mask; p.obs = (float*)obs; p.ref_out = (float*)ref; p.kstep = (uint32_t)h->n_steps;
+    p.reset_mask = mask; p.obs = (float*)obs; p.ref_out = (float*)ref; p.kstep = dev_clock ? 0u : (uint32_t)h->n_steps;
     e = launch_reset<float>(h->fam, h->n_ref, p, st);
     p.reset_mask = nullptr;
   } else {
     StepParams<double>& p = h->pd;
     p.gstep_lo = (uint32_t)h->gstep; p.gstep_hi = (uint32_t)(h->gstep >> 32);
-    p.reset_mask = mask; p.obs = (double*)obs; p.ref_out = (double*)ref; p.kstep = (uint32_t)h->n_steps;
+    p.reset_mask = mask; p.obs = (double*)obs; p.ref_out = (double*)ref; p.kstep = dev_clock ? 0u : (uint32_t)h->n_steps;
     e = launch_reset<double>(h->fam, h->n_ref, p, st);
     p.reset_mask = nullptr;
   }
   if (e != cudaSuccess) return fail(GEMB200_E_CUDA, std::string("reset launch: ") + cudaGetErrorString(e));
   h->launches += 1;
+  if (dev_clock) return tick_clock(h, 1u, 0u, st);
   return GEMB200_OK;
 }
 
@@ -823,7 +869,7 @@ int gemb200_create(const gemb200_config* cfg, gemb200_handle** out) {
 int gemb200_destroy(gemb200_handle* h) {
   if (!h) return GEMB200_OK;
   DeviceGuard guard(h->cfg.device);
-  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv); cudaFree(h->d_imprev); cudaFree(h->d_envp);
+  cudaFree(h->d_st); cudaFree(h->d_stc); cudaFree(h->d_eps); cudaFree(h->d_sw); cudaFree(h->d_fifo); cudaFree(h->d_obsv); cudaFree(h->d_sup); cudaFree(h->d_supph); cudaFree(h->d_swst); cudaFree(h->d_ext); cudaFree(h->d_kenv); cudaFree(h->d_imprev); cudaFree(h->d_envp); cudaFree(h->d_clock);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_ref); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_mask);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   for (int k = 0; k < 3; ++k) if (h->hpipe[k]) cudaStreamDestroy(h->hpipe[k]);
@@ -1165,6 +1211,7 @@ int gemb200_checkpoint_save(gemb200_handle* h, void* host_blob) {
   if (!h || !host_blob) return fail(GEMB200_E_INVALID, "NULL argument");
   DeviceGuard guard(h->cfg.device);
   CUDA_TRY(cudaDeviceSynchronize());
+  if (h->dev_clock) { int rc = pull_clock(h, nullptr); if (rc) return rc; }  // the header carries the clock
   char* b = (char*)host_blob;
   CheckpointHeader hd;
   make_header(h, &hd);
@@ -1193,6 +1240,7 @@ int gemb200_checkpoint_load(gemb200_handle* h, const void* host_blob) {
   Section s[16];
   const int k = sections(h, s);
   for (int i = 0; i < k; ++i) { CUDA_TRY(cudaMemcpy(s[i].ptr, b, s[i].bytes, cudaMemcpyHostToDevice)); b += s[i].bytes; }
+  if (h->dev_clock) { int rc = push_clock(h, nullptr); if (rc) return rc; CUDA_TRY(cudaDeviceSynchronize()); }
   return GEMB200_OK;
 }
 
@@ -1205,6 +1253,7 @@ int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   h->cfg.seed = seed;
   h->gstep = 0; h->n_steps = 0;
+  if (h->dev_clock) { int rc = push_clock(h, st); if (rc) return rc; }
   for (int r = 0; r < 10; ++r) {
     const uint32_t lo = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u, hi = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     h->pf.rk[r][0] = lo; h->pf.rk[r][1] = hi; h->pd.rk[r][0] = lo; h->pd.rk[r][1] = hi;
@@ -1218,6 +1267,32 @@ int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream) {
   int rc = fill_imprev(h, st);
   if (rc) return rc;
   return do_reset(h, nullptr, nullptr, nullptr, st);
+}
+
+// Device-resident clock on / off (include/gemb200.h).  On: the host counters are uploaded; off: they are read back (synchronises `stream`).
+int gemb200_set_device_clock(gemb200_handle* h, int32_t enable, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (enable && !h->dev_clock) {
+    if (!h->d_clock) CUDA_TRY(cudaMalloc(&h->d_clock, 8 * sizeof(uint32_t)));
+    int rc = push_clock(h, st);
+    if (rc) return rc;
+    h->dev_clock = true;
+  } else if (!enable && h->dev_clock) {
+    int rc = pull_clock(h, st);
+    if (rc) return rc;
+    h->dev_clock = false;
+  }
+  return GEMB200_OK;
+}
+int gemb200_get_clock(gemb200_handle* h, uint64_t* call_id, uint64_t* n_steps, void* stream) {
+  if (!h) return fail(GEMB200_E_INVALID, "handle is NULL");
+  DeviceGuard guard(h->cfg.device);
+  if (h->dev_clock) { int rc = pull_clock(h, (cudaStream_t)stream); if (rc) return rc; }
+  if (call_id) *call_id = h->gstep;
+  if (n_steps) *n_steps = h->n_steps;
+  return GEMB200_OK;
 }
 
 int64_t gemb200_launch_count(gemb200_handle* h) { return h ? h->launches : 0; }

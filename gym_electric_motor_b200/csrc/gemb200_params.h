@@ -103,6 +103,10 @@ struct StepParams {
   real* st;
   real* stc;
   uint32_t kstep;         // number of step calls so far: the clock of the sub-episode ends
+  // Device-resident clock (gemb200_set_device_clock: launches that a CUDA graph can replay): {call id lo, hi, step count, dead-time ring
+  // position} of the NEXT call, advanced by a one-thread kernel behind every launch; kstep then holds the bias (1: step, 0: reset) and the
+  // gstep_* / fifo_slot fields are ignored.  nullptr: the clock comes from the host with every launch.
+  const uint32_t* clock_dev;
   double* eps;            // [n]       electrical angle, wrapped to (-pi, pi]; nullptr for DC
   uint16_t* sw;           // [n] finite 2QC switching states, 2 bits per leg; nullptr unless finite && interlock
   real* fifo;             // [dead_steps][fifo_dim][n] DeadTimeProcessor action queue (ring, slot fifo_slot is oldest = next to overwrite)
@@ -113,6 +117,7 @@ struct StepParams {
   real* reward;
   uint8_t* term;
   const uint8_t* reset_mask;  // reset kernel only
+  int32_t out_has;            // which of obs / ref_out / reward / term are requested (bits 0..3; set by the host with the pointers)
   // ---- system ----
   int32_t motor_kind;     // gemb200_motor_kind (runtime variant inside a family)
   int32_t conv_kind[2];
@@ -167,6 +172,8 @@ struct StepParams {
   int32_t n_sq;
   int32_t sq_cnt[kMaxConstraints];
   int32_t sq_idx[kMaxConstraints][kMaxState];
+  int32_t mon_off[4];     // PLAIN shape: BYTE offsets in the staged row of the <= 2 limit-checked states and of the squared constraint's two states (0 when unused)
+  real mon_thr[3];        //              their thresholds: 1, or +inf for an unused check
   // ---- reward: sum of  w * (|s[idx] - ref| * inv_len)^pow.  Terms of referenced states are indexed by reference slot (the
   //      reference value is then a register); rw_* are the weighted states WITHOUT a reference (compared with 0) ----
   real rwr_w[kMaxRef], rwr_inv_len[kMaxRef], rwr_pow[kMaxRef];
@@ -223,8 +230,8 @@ struct StepParams {
   int32_t any_random_ref;  // any slot that draws random numbers per step (Wiener / Laplace / periodic)
   // ---- fused rollout (rollout_kernel): number of steps of this launch; outputs recorded every `record_every` steps (0: last step only) ----
   int32_t roll_steps, record_every;
-  // per-step strides of the rollout's cursors, prepared on the host (elements; 0 for an output that is not requested): action tensor
-  // in BYTES per step, obs / ref / reward / terminated slices in elements per recorded step
+  // per-step strides of the rollout's cursors, prepared on the host, all in BYTES (0 for an output that is not requested): action tensor
+  // per step, obs / ref / reward / terminated slices per recorded step
   int64_t roll_act_inc, roll_obs_inc, roll_ref_inc, roll_rew_inc, roll_term_inc;
   // ---- fused aggregated return over NVLink (gemb200_bind_peers): destinations of the output stores as byte distances from the caller's
   //      tensors; 0 destinations = the caller's tensors only ----

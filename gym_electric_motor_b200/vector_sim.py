@@ -110,6 +110,18 @@ class VectorSim:
         K.check(self._lib.gemb200_reseed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), self._stream()), "gemb200_reseed")
         self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
 
+    def set_device_clock(self, enable=True):
+        """Device-resident clock (gemb200_set_device_clock): while on, step / rollout / reset launches read the RNG call id, the step count
+        and the dead-time ring position from device memory and advance them with a one-thread kernel, so the launches can be captured in a
+        CUDA graph and replayed (graph.CapturedSteps).  Same results as with the host clock, bit for bit."""
+        K.check(self._lib.gemb200_set_device_clock(self._h, 1 if enable else 0, self._stream()), "gemb200_set_device_clock")
+
+    def clock(self):
+        """(number of API calls that drew random numbers, number of env steps) so far; synchronises when the device clock is on"""
+        a, b = C.c_uint64(), C.c_uint64()
+        K.check(self._lib.gemb200_get_clock(self._h, C.byref(a), C.byref(b), self._stream()), "gemb200_get_clock")
+        return int(a.value), int(b.value)
+
     def set_env_params(self, motor_param=None, load_param=None):
         """Per-env parameter blocks (gemb200_set_env_params): motor_param [N, 16] / load_param [N, 8] float64 host arrays in the slot order of
         `_cabi.MP_*` / `_cabi.LP_*`; None keeps the configuration's values; both None: back to the shared coefficients."""

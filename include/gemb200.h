@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GEMB200_ABI_VERSION 9
+#define GEMB200_ABI_VERSION 10
 
 /* limits of the POD config */
 #define GEMB200_MAX_STATE 28   /* longest state vector in scope: DFIM 24 (+ wrappers) */
@@ -325,6 +325,19 @@ int gemb200_set_reference(gemb200_handle* h, const double* ref_in, void* stream)
  * counter and persistent array over, then reset all envs — afterwards the handle is indistinguishable from a freshly created one with
  * cfg.seed = seed, so equal seeds give identical episodes.  Stream-ordered. */
 int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream);
+
+/* Device-resident clock — CUDA-graph support for the closed loop (core.py:328-371 called once per control step with a policy in between;
+ * SURVEY.md §8f row 4).  By default every launch carries its clock (RNG call id, step count = sub-episode clock, dead-time ring position)
+ * in the kernel parameters, taken from the handle's host counters, so no two launches are alike and a captured launch cannot be replayed.
+ * While the device clock is enabled, gemb200_step / gemb200_rollout(_record) / gemb200_reset read the clock from device memory instead and
+ * enqueue a one-thread kernel behind the launch that advances it: a launch then depends on nothing the host changes between calls, and
+ * { policy, gemb200_step } x K can be captured ONCE (cudaStreamBeginCapture / torch.cuda.graph) and replayed any number of times — the
+ * results are bit-identical to the same sequence of ordinary calls.  The host counters are stale while it is on; gemb200_get_clock,
+ * gemb200_checkpoint_save and switching it off read the clock back (synchronising `stream`).  gemb200_step_host's chunked pipeline is not
+ * available in this mode.  enable: 1 = on (uploads the current clock, stream-ordered), 0 = off. */
+int gemb200_set_device_clock(gemb200_handle* h, int32_t enable, void* stream);
+/* Number of API calls that drew random numbers (RNG call id) and of env steps so far; synchronises `stream` when the device clock is on. */
+int gemb200_get_clock(gemb200_handle* h, uint64_t* call_id, uint64_t* n_steps, void* stream);
 
 /* Per-env parameter blocks (domain randomisation; SURVEY.md §8f row 4 — the batched counterpart of constructing N reference envs with N
  * different motor_parameter / load_parameter dicts): env i takes its motor constants from motor_param[i][GEMB200_MAX_MOTOR_PARAM] and its load

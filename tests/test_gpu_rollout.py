@@ -165,6 +165,133 @@ def test_rollout_matches_oracle(torch_cuda, oracle_lib, name, dtype, tol):
     assert alive.mean() > 0.995
 
 
+@pytest.mark.parametrize("layout", [K.LAYOUT_AOS, K.LAYOUT_SOA], ids=["aos", "soa"])
+@pytest.mark.parametrize("name", ["pmsm_cc_rk4", "eesm_cc_rc_dq_dead1_rk4"])  # PLAIN and general instantiation
+def test_any_subset_of_outputs_may_be_requested(torch_cuda, name, layout):
+    """Every output of gemb200_step / gemb200_rollout_record is optional (NULL): the requested ones carry the same bits as in the all-outputs
+    call (the kernels have a fast path for "all four" and a per-output path), the others are not written, the persistent state does not
+    depend on what was asked for."""
+    torch = torch_cuda
+    from gym_electric_motor_b200.vector_sim import VectorSim, _ptr
+
+    n, k_total, every = 333, 6, 2
+    g, cfg = _mk(name, n, K.F32, layout)
+    rng = np.random.default_rng(11)
+    acts = _random_actions(rng, g, n, k_total + 1)
+    full = VectorSim(cfg)
+    dev = _dev_actions(torch, full, acts)
+    full.reset()
+    want = full.rollout(dev[:k_total], record_every=every)
+    want_step = tuple(t.clone() for t in full.step(dev[k_total]))
+    blob = full.state_dict()["blob"]
+    for mask in (0b0001, 0b0110, 0b1000, 0b1011, 0b0000):
+        sim = VectorSim(cfg)
+        sim.reset()
+        outs = [torch.full_like(w, 7) for w in want]
+        sel = [o if (mask >> q) & 1 else None for q, o in enumerate(outs)]
+        sim.rollout_into(dev[:k_total], k_total, every, *sel)
+        single = [torch.full_like(w, 7) for w in want_step]
+        ssel = [o if (mask >> q) & 1 else None for q, o in enumerate(single)]
+        K.check(sim._lib.gemb200_step(sim._h, _ptr(dev[k_total]), _ptr(ssel[0]), _ptr(ssel[1]) if sim.n_ref else None, _ptr(ssel[2]), _ptr(ssel[3]),
+                                      sim._stream()), "gemb200_step")
+        torch.cuda.synchronize()
+        for q in range(4):
+            if (mask >> q) & 1:
+                assert torch.equal(outs[q], want[q]) and torch.equal(single[q], want_step[q]), (name, mask, q)
+            else:
+                assert bool((outs[q] == 7).all()) and bool((single[q] == 7).all()), (name, mask, q, "written although not requested")
+        assert np.array_equal(sim.state_dict()["blob"], blob), (name, mask)
+        sim.close()
+    full.close()
+
+
+@pytest.mark.parametrize("name", ["pmsm_cc_rk4", "eesm_cc_rc_dq_dead1_rk4", "pmsm_fin_sc_rk4_interlock"])
+def test_device_clock_gives_the_same_bits_as_the_host_clock(torch_cuda, name):
+    """gemb200_set_device_clock: step / rollout / reset launches that read the RNG call id, the step count and the dead-time ring position
+    from device memory (and tick them with a one-thread kernel) must reproduce the host-clocked launches exactly — outputs, persistent
+    state and the clock itself — also across switching the mode on and off and a checkpoint taken while it is on."""
+    torch = torch_cuda
+    from gym_electric_motor_b200.vector_sim import VectorSim
+
+    n = 500
+    g, cfg = _mk(name, n, K.F32, K.LAYOUT_AOS)
+    if cfg.dead_time_steps:
+        cfg.dead_time_steps = 3  # a ring longer than one slot: the position is (step count) mod 3
+    rng = np.random.default_rng(3)
+    acts = _random_actions(rng, g, n, 40)
+    a, b = VectorSim(cfg), VectorSim(cfg)
+    dev = _dev_actions(torch, a, acts)
+    for s in (a, b):
+        s.reset()
+    b.set_device_clock(True)
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::7] = 1
+
+    def both(fn):
+        ra, rb = fn(a), fn(b)
+        for x, y in zip(ra, rb):
+            assert torch.equal(x, y)
+
+    for k in range(5):
+        both(lambda s: tuple(t.clone() for t in s.step(dev[k])))
+    both(lambda s: s.rollout(dev[5:16], record_every=1))
+    both(lambda s: tuple(t.clone() for t in s.reset(mask)))
+    both(lambda s: s.rollout(dev[16:23], record_every=0))
+    assert a.clock() == b.clock() and a.clock()[1] == 5 + 11 + 7
+    sd = b.state_dict()  # taken with the device clock on: carries the clock
+    assert np.array_equal(a.state_dict()["blob"], sd["blob"])
+    b.set_device_clock(False)  # back to the host clock: the counters were read back
+    for k in range(23, 27):
+        both(lambda s: tuple(t.clone() for t in s.step(dev[k])))
+    b.set_device_clock(True)
+    b.load_state_dict(sd)  # rewind b to step 23 while the device clock is on
+    a.load_state_dict(sd)
+    for k in range(23, 30):
+        both(lambda s: tuple(t.clone() for t in s.step(dev[k])))
+    assert a.clock() == b.clock()
+    for s in (a, b):
+        s.close()
+
+
+def test_captured_closed_loop_steps_match_the_eager_loop(torch_cuda):
+    """env.capture_steps: K x (policy, env.step) in ONE CUDA graph (device-resident clock); three replays against the same closed loop run
+    step by step on a second env — every recorded step, the clock and the persistent state afterwards, and ordinary steps that follow."""
+    torch = torch_cuda
+    import gym_electric_motor_b200 as gem
+
+    n, k_steps = 4096, 8
+    mk = lambda: gem.make("Cont-CC-PMSM-v0", num_envs=n, ode_solver=gem.physical_systems.RK4Solver(), autoreset="same_step", seed=5)  # noqa: E731
+    e1, e2 = mk(), mk()
+    (s1, r1), _ = e1.reset()
+    e2.reset()
+    idx = torch.as_tensor([e1.physical_system.state_names.index(nm) for nm in e1.reference_generator.reference_names], device="cuda")
+
+    def policy(state, ref):  # a P controller on the referenced currents, spread over the three phases
+        err = (ref - state.index_select(1, idx)) * 3.0
+        return torch.stack([err[:, 0], err[:, 1], -(err[:, 0] + err[:, 1])], dim=1).clamp(-1.0, 1.0).contiguous()
+
+    cap = e2.capture_steps(policy, k_steps, record=True)
+    launches0 = e2.sim.launch_count
+    for rep in range(3):
+        (st, rf), rw, tm = cap.replay()
+        for k in range(k_steps):
+            (s1, r1), w1, t1, _, _ = e1.step(policy(s1, r1))
+            assert torch.equal(cap.states[k], s1) and torch.equal(cap.references[k], r1), (rep, k)
+            assert torch.equal(cap.rewards[k], w1) and torch.equal(cap.terminateds[k], t1), (rep, k)
+        assert torch.equal(st, s1) and torch.equal(rw, w1) and torch.equal(tm, t1)
+    assert e2.sim.launch_count == launches0, "a replay goes through no library call"
+    assert e2.physical_system.k == e1.physical_system.k == 3 * k_steps
+    cap.release()
+    assert e1.sim.clock() == e2.sim.clock()
+    assert np.array_equal(e1.sim.state_dict()["blob"], e2.sim.state_dict()["blob"])
+    a = torch.rand((n, 3), device="cuda") * 2 - 1
+    (x1, y1), w1, t1, _, _ = e1.step(a)
+    (x2, y2), w2, t2, _, _ = e2.step(a)
+    assert torch.equal(x1, x2) and torch.equal(y1, y2) and torch.equal(w1, w2) and torch.equal(t1, t2)
+    e1.close()
+    e2.close()
+
+
 def test_env_rollout_public_api(torch_cuda):
     """`env.rollout(actions)` of the batched environment == K x `env.step`, incl. the state filter"""
     torch = torch_cuda
