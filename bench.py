@@ -337,6 +337,54 @@ def time_rollout(wl, K, W, barrier, torch):
     return ev0.elapsed_time(ev1), wl.launches() - l0, (time.perf_counter() - t0) * 1e3
 
 
+def time_closed_loop(torch, device, barrier, n=1 << 16, k=32, reps=24):
+    """BASELINE configs[1] (N = 65 536) in CLOSED loop — action = controller(state, reference) between the steps, the reference's control
+    loop (core.py:328-371 per step).  eager: policy kernels + ONE gemb200_step launch per step, issued from Python; graph: the same k steps
+    captured once in a CUDA graph (env.capture_steps: device-resident clock of the C-ABI) and replayed.  Device time per step (CUDA events
+    around reps x k steps, the queue kept full) and wall time per step."""
+    env = make_env("pmsm_64k", n, device=device, rank=77)
+    (st, rf), _ = env.reset()
+    idx = torch.as_tensor([env.physical_system.state_names.index(nm) for nm in env.reference_names], device=st.device)
+
+    def policy(state, ref):  # P controller on the referenced currents, spread over the three phases
+        err = (ref - state.index_select(1, idx)) * 3.0
+        return torch.stack([err[:, 0], err[:, 1], -(err[:, 0] + err[:, 1])], dim=1).clamp(-1.0, 1.0).contiguous()
+
+    out = {"envs": n, "steps_per_graph": k, "policy": "P controller on (i_sd, i_sq): 5 small torch kernels per step"}
+    for _ in range(k):
+        (st, rf), _, _, _, _ = env.step(policy(st, rf))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps * k):
+        (st, rf), _, _, _, _ = env.step(policy(st, rf))
+    e1.record()
+    barrier()
+    out["eager_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (reps * k)
+    out["eager_wall_us_per_step"] = 1e6 * (time.perf_counter() - t0) / (reps * k)
+    cap = env.capture_steps(policy, k)
+    l0 = env.sim.launch_count
+    for _ in range(3):
+        cap.replay()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        cap.replay()
+    e1.record()
+    barrier()
+    out["graph_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (reps * k)
+    out["graph_wall_us_per_step"] = 1e6 * (time.perf_counter() - t0) / (reps * k)
+    out["graph_env_steps_per_s"] = n / (out["graph_us_per_step"] * 1e-6)
+    out["eager_env_steps_per_s"] = n / (out["eager_us_per_step"] * 1e-6)
+    out["library_calls_during_replays"] = env.sim.launch_count - l0
+    out["note"] = "kernel nodes per captured step: policy kernels + step_kernel + the one-thread clock tick; the open-loop equivalent is other_configs.pmsm_64k"
+    cap.release()
+    env.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -513,6 +561,9 @@ def main():
             w2.close()
             del w2
             torch.cuda.empty_cache()
+    closed = None
+    if not args.no_extra and cfg_name == "pmsm" and not args.envs_per_gpu and world == 1:
+        closed = time_closed_loop(torch, local_rank, barrier)
     clocks = sampler.stop() if rank == 0 else None
 
     vals = [ms, ms_last, ms_step or 0.0, ms_gather or 0.0, ms_e2e or 0.0, ms_peer or 0.0] + [others[k][0] for k in sorted(others)]
@@ -554,6 +605,8 @@ def main():
                                        "roofline": {"bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak, "alg_bytes_per_env_step": b_alg(c),
                                                     "traffic": ncu_traffic(f"step_kernel_{cfg_name}_f32_aos_bytes_per_launch"), "kernel": "step_kernel"},
                                        "note": "K separate gemb200_step launches (one env.step per launch, closed-loop shape), rotating over replicas of the batch"}
+        if closed:
+            line["closed_loop_64k"] = closed
         if ms_e2e:
             line["e2e"] = {"value": total_envs * ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
                            "ms_per_step": ms_e2e / ke, "api": "gemb200_step_host via VectorSim.step_host_ptr (NUMA-local pinned host buffers)"}

@@ -292,6 +292,38 @@ def test_captured_closed_loop_steps_match_the_eager_loop(torch_cuda):
     e2.close()
 
 
+def test_peer_store_path_with_one_rank_matches_plain_steps(torch_cuda):
+    """distributed.PeerGather with a single rank: the step kernel writes its outputs through the multi-destination store path
+    (gemb200_bind_peers, here one destination: the library-allocated gather buffer) — the same bits as an ordinary step of a second
+    handle; the flag protocol (signal / wait kernels) runs as with N ranks.  The N-rank form needs torchrun: tools/peer_gather_check.py."""
+    torch = torch_cuda
+    import gym_electric_motor_b200 as gem
+    from gym_electric_motor_b200.distributed import PeerGather
+
+    n = 3000
+    mk = lambda: gem.make("Cont-CC-PMSM-v0", num_envs=n, ode_solver=gem.physical_systems.RK4Solver(), autoreset="same_step", seed=9)  # noqa: E731
+    e1, e2 = mk(), mk()
+    e1.reset()
+    e2.reset()
+    pg = PeerGather(e2.sim, torch.float32)
+    acts = torch.rand((7, n, 3), device="cuda") * 2 - 1
+    for k in range(7):
+        obs, ref, rew, term = e1.sim.step(acts[k])
+        b = pg.step(acts[k])
+        pg.finish()
+        g_obs, g_ref, g_rew, g_term = pg.views(b)
+        assert g_obs.shape[0] == 1
+        assert torch.equal(g_obs[0], obs) and torch.equal(g_ref[0], ref) and torch.equal(g_rew[0], rew) and torch.equal(g_term[0], term), k
+    pg.check()
+    pg.release()
+    a = torch.rand((n, 3), device="cuda") * 2 - 1  # unbound again: the specialised single-destination kernels
+    o1, o2 = e1.sim.step(a), e2.sim.step(a)
+    for x, y in zip(o1, o2):
+        assert torch.equal(x, y)
+    e1.close()
+    e2.close()
+
+
 def test_env_rollout_public_api(torch_cuda):
     """`env.rollout(actions)` of the batched environment == K x `env.step`, incl. the state filter"""
     torch = torch_cuda
