@@ -340,48 +340,61 @@ def time_rollout(wl, K, W, barrier, torch):
 def time_closed_loop(torch, device, barrier, n=1 << 16, k=32, reps=24):
     """BASELINE configs[1] (N = 65 536) in CLOSED loop — action = controller(state, reference) between the steps, the reference's control
     loop (core.py:328-371 per step).  eager: policy kernels + ONE gemb200_step launch per step, issued from Python; graph: the same k steps
-    captured once in a CUDA graph (env.capture_steps: device-resident clock of the C-ABI) and replayed.  Device time per step (CUDA events
-    around reps x k steps, the queue kept full) and wall time per step."""
-    env = make_env("pmsm_64k", n, device=device, rank=77)
-    (st, rf), _ = env.reset()
-    idx = torch.as_tensor([env.physical_system.state_names.index(nm) for nm in env.reference_names], device=st.device)
+    captured once in a CUDA graph (env.capture_steps: device-resident clock of the C-ABI) and replayed.  Two policies: `hold` (a constant
+    action tensor: what is left is the env step itself — step_kernel + the one-thread clock tick per step) and `linear` (state feedback
+    a = clamp(state Ws + ref Wr): two small GEMMs + clamp = 3 kernels per step).  Device time per step (CUDA events around reps x k steps
+    with the queue kept full) and wall time per step."""
+    out = {"envs": n, "steps_per_graph": k}
+    for pname in ("hold", "linear"):
+        env = make_env("pmsm_64k", n, device=device, rank=77)
+        (st, rf), _ = env.reset()
+        dev = st.device
+        idx = [env.physical_system.state_names.index(nm) for nm in env.reference_names]
+        ws = torch.zeros((st.shape[1], 3), device=dev)
+        wr = torch.zeros((rf.shape[1], 3), device=dev)
+        for j, col in enumerate(idx):  # P controller on the referenced currents, spread over the three phases
+            for ph, g in enumerate((1.0, -0.5, -0.5) if j == 0 else (0.0, 0.866, -0.866)):
+                ws[col, ph] -= 3.0 * g
+                wr[j, ph] += 3.0 * g
+        hold = torch.rand((n, 3), device=dev) * 0.4 - 0.2
 
-    def policy(state, ref):  # P controller on the referenced currents, spread over the three phases
-        err = (ref - state.index_select(1, idx)) * 3.0
-        return torch.stack([err[:, 0], err[:, 1], -(err[:, 0] + err[:, 1])], dim=1).clamp(-1.0, 1.0).contiguous()
+        def policy(state, ref):
+            if pname == "hold":
+                return hold
+            return torch.addmm(state @ ws, ref, wr).clamp_(-1.0, 1.0)
 
-    out = {"envs": n, "steps_per_graph": k, "policy": "P controller on (i_sd, i_sq): 5 small torch kernels per step"}
-    for _ in range(k):
-        (st, rf), _, _, _, _ = env.step(policy(st, rf))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(reps * k):
-        (st, rf), _, _, _, _ = env.step(policy(st, rf))
-    e1.record()
-    barrier()
-    out["eager_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (reps * k)
-    out["eager_wall_us_per_step"] = 1e6 * (time.perf_counter() - t0) / (reps * k)
-    cap = env.capture_steps(policy, k)
-    l0 = env.sim.launch_count
-    for _ in range(3):
-        cap.replay()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(reps):
-        cap.replay()
-    e1.record()
-    barrier()
-    out["graph_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (reps * k)
-    out["graph_wall_us_per_step"] = 1e6 * (time.perf_counter() - t0) / (reps * k)
-    out["graph_env_steps_per_s"] = n / (out["graph_us_per_step"] * 1e-6)
-    out["eager_env_steps_per_s"] = n / (out["eager_us_per_step"] * 1e-6)
-    out["library_calls_during_replays"] = env.sim.launch_count - l0
-    out["note"] = "kernel nodes per captured step: policy kernels + step_kernel + the one-thread clock tick; the open-loop equivalent is other_configs.pmsm_64k"
-    cap.release()
-    env.close()
+        for _ in range(k):
+            (st, rf), _, _, _, _ = env.step(policy(st, rf))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps * k):
+            (st, rf), _, _, _, _ = env.step(policy(st, rf))
+        e1.record()
+        barrier()
+        r = {"eager_us_per_step": 1e3 * e0.elapsed_time(e1) / (reps * k), "eager_wall_us_per_step": 1e6 * (time.perf_counter() - t0) / (reps * k)}
+        cap = env.capture_steps(policy, k)
+        l0 = env.sim.launch_count
+        for _ in range(3):
+            cap.replay()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps):
+            cap.replay()
+        e1.record()
+        barrier()
+        r["graph_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (reps * k)
+        r["graph_wall_us_per_step"] = 1e6 * (time.perf_counter() - t0) / (reps * k)
+        r["graph_env_steps_per_s"] = n / (r["graph_us_per_step"] * 1e-6)
+        r["eager_env_steps_per_s"] = n / (r["eager_us_per_step"] * 1e-6)
+        r["library_calls_during_replays"] = env.sim.launch_count - l0
+        out[pname] = r
+        cap.release()
+        env.close()
+    out["note"] = ("kernel nodes per captured step: policy kernels (hold: 0, linear: 3) + step_kernel + the one-thread clock tick; the open-loop "
+                   "equivalent (pre-computed actions, one fused launch) is other_configs.pmsm_64k")
     return out
 
 
@@ -609,7 +622,9 @@ def main():
             line["closed_loop_64k"] = closed
         if ms_e2e:
             line["e2e"] = {"value": total_envs * ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
-                           "ms_per_step": ms_e2e / ke, "api": "gemb200_step_host via VectorSim.step_host_ptr (NUMA-local pinned host buffers)"}
+                           "ms_per_step": ms_e2e / ke, "api": "gemb200_step_host via VectorSim.step_host_ptr (NUMA-local pinned host buffers)",
+                           "host_placement": hostmem.placement.get(local_rank), "pcie_link": hostmem.pcie_link(local_rank),
+                           "d2h_GBps": d2h * ke / (ms_e2e * 1e-3) / 1e9}
         if world > 1 and ms_gather:
             best = min(ms_gather, ms_peer) if ms_peer else ms_gather
             line["with_all_gather"] = {"value": total_envs * K / (best * 1e-3), "unit": UNIT, "ms_per_step": best / K,
