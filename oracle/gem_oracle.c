@@ -1185,6 +1185,8 @@ static void ref_advance(const gem_oracle* o, env_t* e, int64_t idx, int after_re
       double u1 = u01(rw[2 * (r >> 1)]), u2 = u01(rw[2 * (r >> 1) + 1]);
       double rad = sqrt(-2.0 * log(u1));
       z = (r & 1) ? rad * sin(2 * M_PI * u2) : rad * cos(2 * M_PI * u2);
+      /* <= 2 slots: words 2, 3 of the after-reset walk block are the slots' initial values (gemb200_kernels.cuh: init_from_walk) */
+      if (o->n_ref <= 2 && after_reset) e->ref_value[r] = c->ref_init_lo[g] + (c->ref_init_hi[g] - c->ref_init_lo[g]) * u01(rw[2 + r]);
     }
     e->ref_value[r] = walk_next(c, g, e->ref_value[r], e->ref_sigma[r] * z);
     e->ref_left[r] -= 1;
@@ -1200,7 +1202,8 @@ static void ref_reset(const gem_oracle* o, env_t* e, int64_t idx) {
     int g = r;
     if (c->ref_sw_count[r] > 1) { switch_generator(o, e, idx, r, 1); g = e->sw_cur[r]; } /* switched_reference_generator.py:64-68 */
     if (c->ref_kind[g] == GEMB200_REF_WIENER) {
-      e->ref_value[r] = c->ref_init_lo[g] + (c->ref_init_hi[g] - c->ref_init_lo[g]) * u01(ri[r]);
+      /* with <= 2 slots the value comes from the after-reset walk block instead (set in ref_advance) */
+      e->ref_value[r] = o->n_ref <= 2 ? 0.0 : c->ref_init_lo[g] + (c->ref_init_hi[g] - c->ref_init_lo[g]) * u01(ri[r]);
       e->ref_left[r] = 0; /* _current_episode_length = -1 forces a new sub-episode */
       e->ref_sigma[r] = 0;
     } else if (c->ref_kind[g] >= GEMB200_REF_LAPLACE) { /* SubepisodedReferenceGenerator.reset :71-91: value 0, new sub-episode */
