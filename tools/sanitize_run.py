@@ -76,6 +76,17 @@ for env_id, kw in CASES:
         (st, rf), rw_, tm = env.rollout(acts, record_every=1)
         env.rollout(acts[:3], record_every=0)
         assert torch.isfinite(st).all()
+        # round 2, second half: a subset of the outputs (the kernels' per-output store path), then the device-resident clock (clock read from
+        # device memory, one-thread tick kernel) for steps, a rollout and a masked reset, and back to the host clock
+        sim = env.sim
+        part = [torch.empty_like(st), None, torch.empty_like(rw_), None]
+        sim.rollout_into(acts, 5, 1, *part)
+        sim.set_device_clock(True)
+        env.step(a)
+        env.rollout(acts[:4], record_every=2)
+        env.reset(mask=torch.ones(N, dtype=torch.uint8, device=dev))
+        env.step(a)
+        sim.set_device_clock(False)
     env.reset(seed=3)  # gemb200_reseed
     env.reset(mask=torch.ones(N, dtype=torch.uint8, device=dev))
     sd = env.state_dict()
@@ -84,4 +95,18 @@ for env_id, kw in CASES:
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all(), env_id
     print("ok", env_id, list(obs.shape), flush=True)
     env.close()
+# the multi-destination store path (gemb200_bind_peers) with one rank: outputs go through the destination list into a library-allocated buffer
+from gym_electric_motor_b200.distributed import PeerGather  # noqa: E402
+
+env = gem.make("Cont-CC-PMSM-v0", num_envs=N, autoreset="same_step", seed=1, ode_solver=RK4())
+env.reset()
+pg = PeerGather(env.sim, torch.float32)
+for k in range(4):
+    b = pg.step(torch.rand((N, 3), generator=gen, device=dev) * 2 - 1)
+pg.finish()
+pg.check()
+assert torch.isfinite(pg.views(b)[0]).all()
+pg.release()
+env.close()
+print("ok peer stores (1 rank)")
 print("all paths ran")
