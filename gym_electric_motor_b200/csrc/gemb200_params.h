@@ -104,9 +104,8 @@ struct StepParams {
   real* stc;
   uint32_t kstep;         // number of step calls so far: the clock of the sub-episode ends
   // Device-resident clock (gemb200_set_device_clock: launches that a CUDA graph can replay): {call id lo, hi, step count, dead-time ring
-  // position, ...} of the NEXT call, advanced by the launch itself (clock_tick_by_last_block; resets: a one-thread kernel behind the launch);
-  // kstep then holds the bias (1: step, 0: reset) and the gstep_* / fifo_slot fields are ignored.  nullptr: the clock comes from the host
-  // with every launch.
+  // position} of the NEXT call, advanced by a one-thread kernel behind every launch; kstep then holds the bias (1: step, 0: reset) and the
+  // gstep_* / fifo_slot fields are ignored.  nullptr: the clock comes from the host with every launch.
   const uint32_t* clock_dev;
   double* eps;            // [n]       electrical angle, wrapped to (-pi, pi]; nullptr for DC
   uint16_t* sw;           // [n] finite 2QC switching states, 2 bits per leg; nullptr unless finite && interlock

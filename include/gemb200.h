@@ -330,8 +330,7 @@ int gemb200_reseed(gemb200_handle* h, uint64_t seed, void* stream);
  * SURVEY.md §8f row 4).  By default every launch carries its clock (RNG call id, step count = sub-episode clock, dead-time ring position)
  * in the kernel parameters, taken from the handle's host counters, so no two launches are alike and a captured launch cannot be replayed.
  * While the device clock is enabled, gemb200_step / gemb200_rollout(_record) / gemb200_reset read the clock from device memory instead and
- * advance it on the device (the last block of a step / rollout launch to finish; a one-thread kernel behind a reset): a launch then depends
- * on nothing the host changes between calls, and
+ * enqueue a one-thread kernel behind the launch that advances it: a launch then depends on nothing the host changes between calls, and
  * { policy, gemb200_step } x K can be captured ONCE (cudaStreamBeginCapture / torch.cuda.graph) and replayed any number of times — the
  * results are bit-identical to the same sequence of ordinary calls.  The host counters are stale while it is on; gemb200_get_clock,
  * gemb200_checkpoint_save and switching it off read the clock back (synchronising `stream`).  gemb200_step_host's chunked pipeline is not
