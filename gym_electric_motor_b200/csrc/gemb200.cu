@@ -493,7 +493,7 @@ static void fill_params(const gemb200_handle* h, const Dims& dm, const Derived& 
   // PLAIN shape (step_kernel): decided here once; GEMB200_NO_PLAIN=1 in the environment forces the general instantiation (A/B runs)
   {
     bool plain =
-                 c.load_kind != GEMB200_LOAD_EXT_SPEED && c.supply_kind == GEMB200_SUPPLY_IDEAL && c.interlocking_time == 0.0 && !(c.interlocking_time1 > 0.0) && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
+                 c.load_kind != GEMB200_LOAD_EXT_SPEED && c.supply_kind == GEMB200_SUPPLY_IDEAL && (c.finite || (c.interlocking_time == 0.0 && !(c.interlocking_time1 > 0.0))) && c.dead_time_steps == 0 && !c.action_dq && c.n_state_ops == 0 &&
                  c.converter_kind[0] != GEMB200_CONV_1QC && c.converter_kind[1] != GEMB200_CONV_1QC &&
                  p->n_rw == 0 && p->n_lim <= 2 && p->n_sq <= 1 && (p->n_sq == 0 || p->sq_cnt[0] == 2);
     for (int r = 0; r < c.n_ref; ++r) plain = plain && c.ref_kind[r] == GEMB200_REF_WIENER && p->rwr_pow1[r] && c.ref_sw_count[r] <= 1;

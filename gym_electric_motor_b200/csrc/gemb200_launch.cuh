@@ -29,7 +29,7 @@ static int pick_block(int range) {
   return block;
 }
 
-template <int FAM, bool FINITE, typename real, int NREF, bool SOA, bool PLAIN = false, bool MECH = false>
+template <int FAM, bool FINITE, typename real, int NREF, bool SOA, bool PLAIN = false, bool MECH = false, bool IL = false>
 static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
   const int range = p.env_end - p.env_begin;
   const int block = pick_block(range);
@@ -45,14 +45,18 @@ static cudaError_t launch_step_t(const StepParams<real>& p, cudaStream_t st) {
       }
     }
   }
-  if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, block, smem, st>>>(p);
-  else step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH><<<grid, block, smem, st>>>(p);
+  if (p.roll_steps > 0) rollout_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH, false, IL><<<grid, block, smem, st>>>(p);
+  else step_kernel<FAM, FINITE, real, NREF, SOA, PLAIN, MECH, false, IL><<<grid, block, smem, st>>>(p);
   return cudaGetLastError();
 }
-// PLAIN instantiations (fp32): {cont, finite} x {constant speed, integrating load} x {AoS, SoA}
+// PLAIN instantiations (fp32): {cont, finite, finite with interlocking time} x {constant speed, integrating load} x {AoS, SoA}
 template <int FAM, typename real, int NREF>
 static cudaError_t launch_plain_t(bool finite, const StepParams<real>& p, cudaStream_t st) {
   const bool soa = p.layout == GEMB200_LAYOUT_SOA, mech = p.load_kind != GEMB200_LOAD_CONST_SPEED;
+  if (finite && p.two_segment) {  // IL: the legs wait in their interlock state, up to three switching segments per step
+    if (mech) return soa ? launch_step_t<FAM, true, real, NREF, true, true, true, true>(p, st) : launch_step_t<FAM, true, real, NREF, false, true, true, true>(p, st);
+    return soa ? launch_step_t<FAM, true, real, NREF, true, true, false, true>(p, st) : launch_step_t<FAM, true, real, NREF, false, true, false, true>(p, st);
+  }
 #define GEMB200_PLAIN(F, M)                                                                                   \
   if (finite == F && mech == M)                                                                               \
     return soa ? launch_step_t<FAM, F, real, NREF, true, true, M>(p, st) : launch_step_t<FAM, F, real, NREF, false, true, M>(p, st);

@@ -315,7 +315,10 @@ def test_headline_config_long_horizon(torch_cuda, oracle_lib, dev_solver, ora_so
 
 
 @pytest.mark.parametrize("name,solver", [("pmsm_cc_rk4", "rk4"), ("pmsm_fin_sc_rk4", "rk4"), ("eesm_cc_rk4", "rk4x2"), ("scim_sc_rk4", "euler"),
-                                         ("dfim_cc_rk4", "rk4"), ("extex_cc_rk4", "rk4"), ("permex_cc_rk4", "euler3")])
+                                         ("dfim_cc_rk4", "rk4"), ("extex_cc_rk4", "rk4"), ("permex_cc_rk4", "euler3"),
+                                         # finite converters with an interlocking time: the PLAIN instantiations' IL variant (two / three switching segments)
+                                         ("pmsm_fin_sc_rk4_interlock", "rk4"), ("scim_fin_cc_interlock_rk4", "rk4"), ("permex_fin4qc_interlock_rk4", "rk4"),
+                                         ("extex_fin_cc_interlock2_rk4", "rk4"), ("dfim_fin_sc_interlock2_rk4", "rk4")])
 def test_plain_and_general_instantiations_agree(torch_cuda, monkeypatch, name, solver):
     """The PLAIN instantiation (compile-time folded switches, the headline path) and the general one (GEMB200_NO_PLAIN=1) are the same
     source: same envs, same Philox streams, same actions -> same trajectories up to fp32 contraction differences, identical
