@@ -576,7 +576,11 @@ def main():
             torch.cuda.empty_cache()
     closed = None
     if not args.no_extra and cfg_name == "pmsm" and not args.envs_per_gpu and world == 1:
-        closed = time_closed_loop(torch, local_rank, barrier)
+        try:
+            closed = time_closed_loop(torch, local_rank, barrier)
+        except Exception as exc:  # a secondary arm must not take the bench line down with it
+            closed = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     vals = [ms, ms_last, ms_step or 0.0, ms_gather or 0.0, ms_e2e or 0.0, ms_peer or 0.0] + [others[k][0] for k in sorted(others)]

@@ -59,6 +59,8 @@ class CapturedSteps:
 
     def replay(self):
         """run the captured steps once more from the env's current state (stream-ordered on the current stream)"""
+        if self.graph is None:
+            raise RuntimeError("CapturedSteps.replay() after release(): the captured launches read the device-resident clock, which is off")
         self.graph.replay()
         self.env._physical_system._k += self.n_steps
         return (self.state, self.reference), self.reward, self.terminated
@@ -66,3 +68,4 @@ class CapturedSteps:
     def release(self):
         """back to host-clocked launches (reads the clock back: synchronises)"""
         self._sim.set_device_clock(False)
+        self.graph = None
