@@ -88,3 +88,31 @@ def test_two_rank_gloo_collectives(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_host_placement_helpers_degrade_quietly(monkeypatch):
+    """hostmem: on a machine with one NUMA node (or without sysfs / NVML / CUDA) there is nothing to bind and nothing to probe — the helpers
+    return None / {} and leave the process's CPU affinity alone; with a fake two-node sysfs answer the binding narrows the affinity to that
+    node's CPUs (the e2e arm of bench.py allocates its pinned buffers after this call)."""
+    import os
+
+    from gym_electric_motor_b200 import hostmem
+
+    before = os.sched_getaffinity(0)
+    nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()] if os.path.isdir("/sys/devices/system/node") else []
+    if len(nodes) < 2:
+        assert hostmem.probe_numa_node(0) == (None, {})
+    assert isinstance(hostmem.pcie_link(0), dict)
+    monkeypatch.setattr(hostmem, "device_numa_node", lambda d: None)
+    monkeypatch.setattr(hostmem, "probe_numa_node", lambda d: (None, {}))
+    assert hostmem.bind_to_device_numa_node(0) is None and hostmem.placement[0]["node"] is None
+    assert os.sched_getaffinity(0) == before
+    some = sorted(before)[: max(1, len(before) // 2)]
+    monkeypatch.setattr(hostmem, "device_numa_node", lambda d: 0)
+    monkeypatch.setattr(hostmem, "_node_cpus", lambda n: set(some))
+    try:
+        assert hostmem.bind_to_device_numa_node(0) == 0
+        assert os.sched_getaffinity(0) == set(some) and hostmem.placement[0] == {"node": 0, "how": "sysfs", "d2h_GBps_by_node": {}}
+    finally:
+        os.sched_setaffinity(0, before)
+        hostmem._set_preferred_node(None)
